@@ -1,0 +1,265 @@
+/*
+ * pssr_b200.h -- C ABI of libpssr_b200.so: the B200 (sm_100a) kernels behind PSSR2's
+ * test/predict hot path (crappify -> SR network forward -> stitch -> score).
+ *
+ * The reference (ucsdmanorlab/PSSR2 v2.4.0) is pure Python and has no FFI; each entry
+ * point below names the reference call site (file:line under /root/reference) whose
+ * arithmetic it replaces.  INTEGRATION.md shows the ctypes binding a PSSR2 maintainer
+ * would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative PSSR_E* code on failure; the message
+ *    is available (thread-local) from pssr_last_error().
+ *  - all pointers are DEVICE pointers owned by the caller unless the name says host_;
+ *    the library never frees caller memory and never allocates behind the caller's back
+ *    except inside an opaque plan (pssr_plan_create / pssr_plan_destroy).
+ *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous w.r.t. the host.
+ *  - images are row-major, innermost dimension last; shapes are explicit.
+ */
+#ifndef PSSR_B200_H
+#define PSSR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSSR_OK 0
+#define PSSR_EINVAL (-1)   /* bad argument                        */
+#define PSSR_ECUDA (-2)    /* CUDA runtime / driver error         */
+#define PSSR_EUNSUP (-3)   /* shape or mode outside the supported set */
+
+const char* pssr_last_error(void);
+/* Library version string, e.g. "pssr_b200 0.1 sm_100a". */
+const char* pssr_version(void);
+/* Number of kernels this library has launched so far in this process (bench.py's
+ * gpu_launches counter). */
+int64_t pssr_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Family 1: fused crappify  (pssr/data.py:471-495 `_gen_pair`, :629-638 `_sliding_window`,
+ * :536-551 `_square_crop`/`_pad_image`, Pillow `Image.resize(BILINEAR)` at :483,
+ * pssr/crappifiers.py:26-105, round/clip at data.py:487).
+ *
+ * One launch turns `n_tiles` HR tiles, addressed inside resident sheets, into LR tiles:
+ *   tile gather (+ reflect pad) -> Pillow-exact two-pass antialiased triangle downscale
+ *   (uint8: 22-bit fixed point, uint16: double) -> noise stages -> round-half-even ->
+ *   clip [0,255] -> float32 (and optionally the network's u8 staging copy).
+ * ------------------------------------------------------------------------------------ */
+
+/* noise stage kinds, applied in order (MultiCrappifier, crappifiers.py:38-43) */
+#define PSSR_NOISE_POISSON 1   /* crappifiers.py:82-86 */
+#define PSSR_NOISE_GAUSSIAN 2  /* crappifiers.py:62-64 */
+#define PSSR_NOISE_SALTPEPPER 3/* crappifiers.py:103-105 */
+
+/* noise sources */
+#define PSSR_RNG_INJECTED 0    /* draws supplied by the caller (bit-exact parity mode) */
+#define PSSR_RNG_PHILOX 1      /* on-device counter-based Philox4x32-10, keyed by (seed, tile, pixel) */
+
+typedef struct {
+  int32_t kind;          /* PSSR_NOISE_*                                                  */
+  int32_t rng;           /* PSSR_RNG_*                                                    */
+  double intensity;      /* already resolved for this call (spread draw done by the host):
+                            POISSON mix i; GAUSSIAN sigma and SALTPEPPER amount (Philox only) */
+  double gain;
+  int32_t mix_in_f32;    /* POISSON: 1 = x*(1-i) is evaluated in float32 (python-scalar intensity),
+                            0 = in float64 (np.float64 intensity, i.e. spread > 0) -- NumPy>=2 promotion */
+  int32_t reserved;
+  /* injected draws, one value per LR pixel of every tile, layout [n_tiles][frames][lr][lr]:
+   *   POISSON:    int64 samples  y  (np.random.poisson output)
+   *   GAUSSIAN:   double samples g  (np.random.normal(gain, intensity) output, i.e. already
+   *               shifted/scaled)
+   *   SALTPEPPER: uint8 bit0 = flipped, bit1 = salted                                     */
+  const void* injected;
+} pssr_noise_stage_t;
+
+typedef struct {
+  /* source sheets: `sheets` points at a DEVICE array of n_sheets device pointers; every sheet is
+   * [frames_total][sheet_h][sheet_w], dtype uint8 (elem_bytes=1) or uint16 (elem_bytes=2) */
+  const void* const* sheets;
+  int32_t n_sheets;
+  int32_t elem_bytes;
+  int32_t sheet_h, sheet_w;
+  /* per tile (device int32 arrays of length n_tiles): sheet index, first frame, top row,
+   * left column of the valid region, and its valid height/width (< hr_res => reflect pad on the
+   * bottom/right as np.pad(..., "reflect") does, data.py:548-551) */
+  const int32_t* tile_sheet;
+  const int32_t* tile_frame;
+  const int32_t* tile_y;
+  const int32_t* tile_x;
+  const int32_t* tile_vh;
+  const int32_t* tile_vw;
+  int32_t n_tiles;
+  int32_t frames;        /* frames in the tile's window = max(n_frames); ALL are crappified */
+  int32_t hr_res;        /* HR tile edge                                        */
+  int32_t lr_scale;      /* integer downscale factor                            */
+  /* noise: n_stages == 0 means crappifier=None (no round/clip either, data.py:484)      */
+  pssr_noise_stage_t stages[4];
+  int32_t n_stages;
+  int32_t clip_between;  /* MultiCrappifier(clip=True), crappifiers.py:41-42            */
+  uint64_t seed;         /* Philox key                                                  */
+  uint64_t tile_index0;  /* global index of tile 0 (so results do not depend on #GPUs)  */
+  /* outputs */
+  float* lr_out;         /* [n_tiles][lr_frames][lr][lr] float32 (what _tensor_ready yields) */
+  float* hr_out;         /* optional [n_tiles][hr_frames][hr][hr] float32 HR tiles (raw values,
+                            data.py:495), or NULL                                         */
+  uint8_t* hr_u8_out;    /* optional [n_tiles][hr][hr] uint8 = trunc(clip(centre HR frame,0,255))
+                            (`_pred_array(hr)`, predict.py:185,245-246), or NULL          */
+  int32_t hr_frame0;     /* first frame (relative to the tile's frame window) and count of */
+  int32_t hr_frames;     /* the HR frames kept by _slice_center (data.py:489-491)          */
+  int32_t lr_frame0;     /* first LR frame kept by _slice_center (data.py:492-493) ...     */
+  int32_t lr_frames;     /* ... and how many (= frames when n_frames[0] == n_frames[1])    */
+} pssr_crappify_args_t;
+
+int pssr_crappify(const pssr_crappify_args_t* args, void* stream);
+/* The resample stage alone (Pillow parity tests): src [n][h][w] -> dst [n][h/scale][w/scale],
+ * same dtype (uint8 / uint16) as Pillow returns before `.astype(np.float32)`. */
+int pssr_resize_bilinear(const void* src, void* dst, int32_t n, int32_t h, int32_t w,
+                         int32_t scale, int32_t elem_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Family 2: network forward as a plan of fused ops  (pssr/models/resunet.py:65-96,
+ * _blocks.py:15-18,39-41, rdresunet.py:104-130, _rdnet.py:95-206).
+ * The host mirror (pssr2_b200/models.py) folds BatchNorm into the weights, packs them
+ * K-major, and describes the forward as a list of ops; the plan owns only TMA descriptors.
+ * Activations are NHWC 16-bit (bf16 or fp16, one format per plan) in caller-owned HBM.
+ * ------------------------------------------------------------------------------------ */
+#define PSSR_DT_BF16 0
+#define PSSR_DT_FP16 1
+
+#define PSSR_ACT_NONE 0
+#define PSSR_ACT_RELU 1
+#define PSSR_ACT_GELU 2      /* exact erf GELU, _rdnet.py:186 */
+
+#define PSSR_OP_CONV 1        /* implicit-GEMM convolution on tcgen05 tensor cores          */
+#define PSSR_OP_PREP 2        /* x/128-1 -> BatchNorm(eval) -> 3x3 im2col of the input      */
+#define PSSR_OP_MAXPOOL 3     /* 2x2 max pool, NHWC                                         */
+#define PSSR_OP_TAIL 4        /* Reconstruction.conv + *128+128 (+ clip/trunc to u8)        */
+#define PSSR_OP_DWCONV_LN 5   /* depthwise 7x7 + LayerNorm2d over C (RDNet Block)           */
+#define PSSR_OP_LAYERNORM 6   /* LayerNorm2d over C                                         */
+#define PSSR_OP_ESE 7         /* EffectiveSE gate + layer-scale gamma                       */
+#define PSSR_OP_COPY 8        /* channel-slice copy between NHWC buffers                    */
+
+/* One NHWC source view of an implicit-GEMM op. */
+typedef struct {
+  const void* base;      /* address of channel 0 of the view (16-byte aligned)             */
+  int32_t channels;      /* valid channels of the view                                     */
+  int32_t cstride;       /* elements between consecutive pixels (>= channels, % 8 == 0)    */
+  int32_t H, W, B;       /* spatial size / batch of the source tensor                      */
+  int32_t reserved;
+} pssr_src_t;
+
+/* A run of K blocks: for every tap (dy,dx) of the filter and every 64-channel block of
+ * the source, one [128 pixels x 64] operand tile is fetched by TMA (out-of-image taps are
+ * zero-filled by the TMA unit = the convolution's zero padding). */
+typedef struct {
+  int32_t src;           /* index into srcs[]                                              */
+  int32_t taps;          /* 1: 1x1,  9: 3x3 pad 1,  4: 2x2 stride 2                        */
+  int32_t cblocks;       /* 64-channel blocks per tap                                      */
+  int32_t reserved;
+} pssr_kseg_t;
+
+typedef struct {
+  pssr_src_t srcs[3];
+  int32_t n_srcs;
+  pssr_kseg_t segs[4];
+  int32_t n_segs;
+  const void* weights;   /* [n][k_total] 16-bit, K-major, K ordered seg -> tap -> cblock -> c */
+  const float* bias;     /* [n] fp32 (BatchNorm shift and conv biases folded)               */
+  int32_t n;             /* GEMM N = output channels incl. zero padding (multiple of 32)    */
+  int32_t n_valid;       /* channels actually stored (<= n, multiple of 8)                  */
+  int32_t Ho, Wo, B;     /* output pixel grid before pixel shuffle                          */
+  void* out;             /* NHWC 16-bit [B][Ho*r][Wo*r][out_cstride], written at out_choff  */
+  int32_t out_cstride;
+  int32_t out_choff;
+  int32_t shuffle;       /* r: F.pixel_shuffle factor applied by the epilogue (1 = none);   */
+                         /* weights' N is ordered (i*r+j)*C' + c' so it is pure addressing  */
+  int32_t act;           /* PSSR_ACT_*                                                      */
+  const float* out_scale;/* optional per-channel multiplier applied after act (layer-scale) */
+  float* out_f32;        /* optional fp32 NHWC copy of the output (same geometry) or NULL   */
+} pssr_conv_desc_t;
+
+typedef struct {
+  const void* x;         /* [B][C][H][W] float32 (0..255) or uint8 if x_u8                   */
+  int32_t x_u8;
+  int32_t B, C, H, W;
+  const float* scale;    /* [C] BN scale  s  (1 if no norm)                                  */
+  const float* shift;    /* [C] BN shift  t                                                   */
+  void* im2col;          /* NHWC 16-bit [B][H][W][64]: channel (c*9+tap) = norm(x) at the tap,
+                            zero outside the image and for channels >= 9*C                   */
+  float* xnorm_f32;      /* [B][C][H][W] fp32 normalised input (the final skip), may be NULL */
+} pssr_prep_desc_t;
+
+typedef struct {
+  const void* in; int32_t in_cstride; int32_t in_choff;
+  void* out; int32_t out_cstride; int32_t out_choff;
+  int32_t B, H, W, C;    /* input spatial size; output is H/2 x W/2                          */
+} pssr_pool_desc_t;
+
+typedef struct {
+  const void* in;        /* NHWC 16-bit [B][H][W][cstride], C valid                          */
+  int32_t cstride, C;
+  int32_t B, H, W;
+  const float* weight;   /* [Cout][3][3][C] fp32                                             */
+  const float* bias;     /* [Cout]                                                           */
+  int32_t Cout;
+  float mul, add;        /* y = acc*mul + add  (resunet.py:95: 128, 128)                     */
+  float* out_f32;        /* [B][Cout][H][W] fp32 or NULL                                     */
+  uint8_t* out_u8;       /* [B][H][W] uint8 = trunc(clip(y,0,255)) of channel Cout/2
+                            (predict.py:245-246 `_pred_array`) or NULL                       */
+} pssr_tail_desc_t;
+
+typedef struct {
+  int32_t kind;          /* PSSR_OP_*                                                       */
+  int32_t reserved;
+  union {
+    pssr_conv_desc_t conv;
+    pssr_prep_desc_t prep;
+    pssr_pool_desc_t pool;
+    pssr_tail_desc_t tail;
+    uint8_t pad[512];
+  } u;
+} pssr_op_t;
+
+typedef struct pssr_plan pssr_plan_t;
+
+/* Builds TMA descriptors for every op.  `dtype` is PSSR_DT_*.  The op list is copied. */
+int pssr_plan_create(const pssr_op_t* ops, int32_t n_ops, int32_t dtype, pssr_plan_t** out);
+/* Launches every op of the plan in order on `stream`. */
+int pssr_plan_run(pssr_plan_t* plan, void* stream);
+/* Launches ops [first, first+count) only (profiling / tests). */
+int pssr_plan_run_range(pssr_plan_t* plan, int32_t first, int32_t count, void* stream);
+int32_t pssr_plan_num_ops(const pssr_plan_t* plan);
+void pssr_plan_destroy(pssr_plan_t* plan);
+
+/* ------------------------------------------------------------------------------------
+ * Family 3: overlap-weighted tile stitch  (pssr/util.py:116-137 `_patch_images`, :96-100).
+ * tiles [n_stacks][n_rows*n_cols][T][T] uint8 -> sheets [n_stacks][n_rows*step+ov][n_cols*step+ov]
+ * uint8 with step = T-ov; every output pixel gathers its <=4 contributors (no atomics),
+ * sum / count in exact integer arithmetic == the reference's float64 sum/count truncated.
+ * ------------------------------------------------------------------------------------ */
+int pssr_stitch(const uint8_t* tiles, uint8_t* sheets, int32_t n_stacks, int32_t n_rows,
+                int32_t n_cols, int32_t tile, int32_t overlap, int32_t margin, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Family 4: scoring  (pssr/predict.py:193-203, skimage PSNR / SSIM, pssr/util.py:139-191).
+ * ------------------------------------------------------------------------------------ */
+/* Per image pair (uint8 [n][h][w]): exact integer reductions
+ *   sums[i][0] = sum (a-b)^2  (int64)
+ *   ssim[i]    = sum over the (h-6)x(w-6) interior of the 7x7-window SSIM map (double)
+ * from which mse / pixel / psnr / ssim follow on the host (pssr2_b200/predict.py). */
+int pssr_metric_sums(const uint8_t* a, const uint8_t* b, int32_t n, int32_t h, int32_t w,
+                     int64_t* sq_err, double* ssim_sum, void* stream);
+/* normalize_preds (util.py:139-191) for uint8 pairs of equal shape: 256-bin histograms give
+ * the exact percentiles/means; second pass applies the affine maps, clips and truncates.
+ * workspace: >= pssr_normalize_workspace_bytes(n) bytes of device scratch. */
+int64_t pssr_normalize_workspace_bytes(int32_t n);
+int pssr_normalize_preds(const uint8_t* hr, const uint8_t* hr_hat, uint8_t* hr_out,
+                         uint8_t* hr_hat_out, int32_t n, int32_t h, int32_t w, double pmin,
+                         double pmax, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSSR_B200_H */

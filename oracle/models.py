@@ -1,0 +1,187 @@
+"""fp32 CPU restatement of the reference network forwards, driven by a plain state_dict.
+
+TEST INFRASTRUCTURE ONLY.  Follows
+  ResUNet.forward       pssr/models/resunet.py:65-96
+  ResBlock.forward      pssr/models/_blocks.py:39-41   (conv/BN/ReLU stack :23-33)
+  Reconstruction        pssr/models/_blocks.py:15-18
+  RDResUNet.forward     pssr/models/rdresunet.py:104-130
+  RDNet.forward         pssr/models/_rdnet.py:95-104, DenseStage :133-138,
+                        DenseBlock :168-175, Block/BlockESE :181-203
+Pinned against the reference modules themselves (imported via oracle/refshim.py) in
+tests/test_oracle_vs_reference.py and through tests/golden/net_*.npz.
+
+``emulate`` ("bf16" | "fp16" | None) additionally models the arithmetic of the CUDA plan
+(BN folded into 16-bit weights, 16-bit activations in HBM, fp32 accumulation and fp32
+epilogues); it is used only to derive the tolerances written in the GPU parity tests.
+"""
+import torch
+import torch.nn.functional as F
+
+_EMU = {"bf16": torch.bfloat16, "fp16": torch.float16, None: None}
+
+
+def _q(t, emulate):
+    dt = _EMU[emulate]
+    return t if dt is None else t.to(dt).to(torch.float32)
+
+
+def _bn_fold(sd, prefix, eps=1e-5):
+    """BatchNorm2d(eval) as y = s*x + t  (torch default eps, pssr/models/_blocks.py:30)."""
+    s = sd[prefix + ".weight"] / torch.sqrt(sd[prefix + ".running_var"] + eps)
+    t = sd[prefix + ".bias"] - sd[prefix + ".running_mean"] * s
+    return s, t
+
+
+def _n_convs(sd, prefix):
+    n = 0
+    while f"{prefix}.conv.{3 * n}.weight" in sd:
+        n += 1
+    return n
+
+
+def resblock(sd, prefix, x, emulate=None):
+    """relu( [conv3x3 -> BN -> ReLU]*depth -> conv3x3 -> BN  +  conv1x1(x) )  (_blocks.py:20-41)."""
+    n = _n_convs(sd, prefix)
+    if emulate is None:
+        h = x
+        for i in range(n):
+            h = F.conv2d(h, sd[f"{prefix}.conv.{3 * i}.weight"], sd[f"{prefix}.conv.{3 * i}.bias"], padding=1)
+            s, t = _bn_fold(sd, f"{prefix}.conv.{3 * i + 1}")
+            h = h * s.view(1, -1, 1, 1) + t.view(1, -1, 1, 1)
+            if i + 1 < n:
+                h = F.relu(h)
+        r = F.conv2d(x, sd[f"{prefix}.respass.weight"], sd[f"{prefix}.respass.bias"])
+        return F.relu(h + r)
+    # emulation of the plan: folded weights, 16-bit operands, fp32 accumulate
+    h = x  # already quantised by the caller
+    for i in range(n):
+        w = sd[f"{prefix}.conv.{3 * i}.weight"]
+        b = sd[f"{prefix}.conv.{3 * i}.bias"]
+        s, t = _bn_fold(sd, f"{prefix}.conv.{3 * i + 1}")
+        wf = _q(w * s.view(-1, 1, 1, 1), emulate)
+        bf = b * s + t
+        acc = F.conv2d(h, wf, None, padding=1) + bf.view(1, -1, 1, 1)
+        if i + 1 < n:
+            h = _q(F.relu(acc), emulate)
+        else:
+            wr = _q(sd[f"{prefix}.respass.weight"], emulate)
+            acc = acc + F.conv2d(x, wr, sd[f"{prefix}.respass.bias"])
+            h = _q(F.relu(acc), emulate)
+    return h
+
+
+def reconstruction(sd, x, scale, emulate=None):
+    """relu(pre(x)) -> pixel_shuffle(scale) -> conv   (_blocks.py:15-18)."""
+    wp, bp = sd["reconstruction.pre.weight"], sd["reconstruction.pre.bias"]
+    wc, bc = sd["reconstruction.conv.weight"], sd["reconstruction.conv.bias"]
+    h = F.relu(F.conv2d(x, _q(wp, emulate), bp, padding=1))
+    h = _q(h, emulate)
+    h = F.pixel_shuffle(h, scale)
+    # the tail conv runs on CUDA cores with fp32 weights in the plan
+    return F.conv2d(h, wc, bc, padding=1)
+
+
+def _input_norm(sd, x):
+    x = x / 128 - 1                                    # resunet.py:66
+    if "norm.weight" in sd:                            # resunet.py:67-68 (BN, eval)
+        s, t = _bn_fold(sd, "norm")
+        x = x * s.view(1, -1, 1, 1) + t.view(1, -1, 1, 1)
+    return x
+
+
+def resunet_forward(sd, x, scale=None, emulate=None):
+    """ResUNet.forward (resunet.py:65-96), default (non-atrous, no PSP) configuration."""
+    sd = {k: v.float() for k, v in sd.items() if v.is_floating_point()}
+    if scale is None:
+        hidden0 = sd["reconstruction.conv.weight"].shape[1]
+        scale = int(round((sd["reconstruction.pre.weight"].shape[0] / hidden0) ** 0.5))
+    n_enc = 0
+    while f"encoder.{n_enc}.respass.weight" in sd:
+        n_enc += 1
+    x = _q(_input_norm(sd, x.float()), emulate)
+    skips = [x]
+    for i in range(n_enc):
+        x = resblock(sd, f"encoder.{i}", x, emulate)
+        if i + 1 < n_enc:
+            skips.append(x)
+            x = F.max_pool2d(x, 2)
+    for i in range(n_enc - 1):
+        x = F.pixel_shuffle(x, 2)
+        x = torch.cat([x, skips.pop()], 1)
+        x = resblock(sd, f"decoder.{i}", x, emulate)
+    x = torch.cat([x, skips.pop()], 1)
+    x = reconstruction(sd, x, scale, emulate)
+    return x * 128 + 128                               # resunet.py:95
+
+
+# ------------------------------------------------------------------------------ RDNet
+def _ln2d(x, w, b, eps=1e-6):
+    x = x.permute(0, 2, 3, 1)
+    x = F.layer_norm(x, (x.shape[-1],), w, b, eps)
+    return x.permute(0, 3, 1, 2)
+
+
+def _rd_block(sd, p, x):
+    """Block / BlockESE (_rdnet.py:177-206) followed by layer-scale gamma (:172-174)."""
+    L = p + ".layers.layers"
+    c = x.shape[1]
+    h = F.conv2d(x, sd[L + ".0.weight"], sd[L + ".0.bias"], padding=3, groups=c)
+    h = _ln2d(h, sd[L + ".1.weight"], sd[L + ".1.bias"])
+    h = F.conv2d(h, sd[L + ".2.weight"], sd[L + ".2.bias"])
+    h = F.gelu(h)
+    h = F.conv2d(h, sd[L + ".4.weight"], sd[L + ".4.bias"])
+    if L + ".5.fc.weight" in sd:
+        se = h.mean((2, 3), keepdim=True)
+        se = F.conv2d(se, sd[L + ".5.fc.weight"], sd[L + ".5.fc.bias"])
+        h = h * (F.relu6(se + 3.0) / 6.0)
+    if p + ".gamma" in sd:
+        h = h * sd[p + ".gamma"].view(1, -1, 1, 1)
+    return h
+
+
+def rdnet_forward(sd, x, ds_blocks, prefix="encoder"):
+    """RDNet.forward (_rdnet.py:95-104): stem, dense stages, skips before each downsample."""
+    P = prefix
+    w = sd[P + ".stem.stem.0.weight"]
+    x = F.conv2d(x, w, sd[P + ".stem.stem.0.bias"], stride=w.shape[-1])
+    x = _ln2d(x, sd[P + ".stem.stem.1.weight"], sd[P + ".stem.stem.1.bias"])
+    skips = []
+    for i, ds in enumerate(ds_blocks):
+        if ds:
+            skips.append(x)
+        S = f"{P}.dense_stages.{i}"
+        stage_idx = 0
+        if f"{S}.0.weight" in sd:  # transition: LayerNorm2d + conv (k = stride = 1 or 2)
+            x = _ln2d(x, sd[f"{S}.0.weight"], sd[f"{S}.0.bias"])
+            wt = sd[f"{S}.1.weight"]
+            x = F.conv2d(x, wt, sd[f"{S}.1.bias"], stride=wt.shape[-1])
+            stage_idx = 2
+        feats = [x]
+        j = 0
+        while f"{S}.{stage_idx}.dense_block{j}.layers.layers.0.weight" in sd:
+            feats.append(_rd_block(sd, f"{S}.{stage_idx}.dense_block{j}", torch.cat(feats, 1)))
+            j += 1
+        x = torch.cat(feats, 1)
+    return skips + [x]
+
+
+def rdresunet_forward(sd, x, ds_blocks=(False, True, True, False, False, False, True), scale=None,
+                      patch_size=2):
+    """RDResUNet.forward (rdresunet.py:104-130), default (non-atrous, no PSP) configuration."""
+    sd = {k: v.float() for k, v in sd.items() if v.is_floating_point()}
+    hidden_last = sd["reconstruction.conv.weight"].shape[1]
+    if scale is None:
+        scale = int(round((sd["reconstruction.pre.weight"].shape[0] / hidden_last) ** 0.5))
+    x = _input_norm(sd, x.float())
+    skips = [x] + rdnet_forward(sd, x, ds_blocks)
+    n_dec = 0
+    while f"decoder.{n_dec}.respass.weight" in sd:
+        n_dec += 1
+    ratios = [1] + [2] * (n_dec - 1) + [patch_size]
+    for i in range(n_dec):
+        x = torch.cat([x, skips.pop()], 1) if i != 0 else skips.pop()
+        x = resblock(sd, f"decoder.{i}", x)
+        x = F.pixel_shuffle(x, ratios[i + 1])
+    x = torch.cat([x, skips.pop()], 1)
+    x = reconstruction(sd, x, scale)
+    return x * 128 + 128

@@ -1,0 +1,534 @@
+// Family 1: fused crappify.  One launch = tile gather from resident sheets (+ reflect pad) ->
+// Pillow-exact two-pass antialiased triangle downscale -> noise stages -> round-half-even ->
+// clip -> float32 LR tiles.  Replaces, per tile,
+//   _sliding_window / _square_crop / _pad_image      pssr/data.py:629-638, :536-551
+//   Image.fromarray(ch).resize(.., BILINEAR)          pssr/data.py:483 (Pillow Resample.c, see
+//                                                      oracle/pillow_resize.py for the restatement)
+//   crappifier.crappify + np.clip(lr.round(),0,255)   pssr/data.py:486-487, pssr/crappifiers.py:26-105
+//   _slice_center + float32 cast                      pssr/data.py:489-495, :526-534
+//
+// A CTA owns a TL x TL patch of one LR frame.  It stages the HR window it needs in shared memory
+// with 16-byte coalesced loads (each HR byte is read from HBM once, plus a 2*scale halo), runs the
+// horizontal pass into a second shared buffer rounded to the image dtype exactly as Pillow does,
+// then the vertical pass, the noise chain and the store.  uint8 uses Pillow's 22-bit fixed point;
+// uint16 uses Pillow's sequential double accumulation (explicit __dmul_rn/__dadd_rn: an FMA would
+// change the bits).
+#include <math.h>
+#include <map>
+#include <mutex>
+#include <vector>
+#include "common.cuh"
+
+namespace pssr {
+
+static constexpr int kCrapThreads = 256;
+static constexpr int kPrecisionBits = 32 - 8 - 2;
+
+struct ResampleTable {
+  int in_size = 0, out_size = 0, ksize = 0;
+  int2* bounds = nullptr;    // device [out] (xmin, count)
+  int32_t* kq = nullptr;     // device [out][ksize] 8 bpc fixed-point coefficients
+  double* kd = nullptr;      // device [out][ksize] double coefficients
+  std::vector<int2> h_bounds;
+};
+
+// Host restatement of Resample.c precompute_coeffs / normalize_coeffs_8bpc (bilinear filter).
+static void build_coeffs(int in_size, int out_size, std::vector<int2>& bounds, std::vector<double>& kk,
+                         std::vector<int32_t>& kq, int& ksize) {
+  double scale = (double)in_size / (double)out_size;
+  double filterscale = scale;
+  if (filterscale < 1.0) filterscale = 1.0;
+  const double support = 1.0 * filterscale;
+  ksize = (int)ceil(support) * 2 + 1;
+  bounds.assign(out_size, make_int2(0, 0));
+  kk.assign((size_t)out_size * ksize, 0.0);
+  kq.assign((size_t)out_size * ksize, 0);
+  const double ss = 1.0 / filterscale;
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = (xx + 0.5) * scale;
+    int xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double* k = &kk[(size_t)xx * ksize];
+    volatile double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      double a = (x + xmin - center + 0.5) * ss;
+      if (a < 0.0) a = -a;
+      const double w = a < 1.0 ? 1.0 - a : 0.0;
+      k[x] = w;
+      ww = ww + w;
+    }
+    for (int x = 0; x < xmax; ++x)
+      if (ww != 0.0) k[x] /= ww;
+    bounds[xx] = make_int2(xmin, xmax);
+    for (int x = 0; x < ksize; ++x) {
+      const double v = k[x];
+      kq[(size_t)xx * ksize + x] = v < 0 ? (int32_t)(-0.5 + v * (double)(1 << kPrecisionBits))
+                                         : (int32_t)(0.5 + v * (double)(1 << kPrecisionBits));
+    }
+  }
+}
+
+static std::mutex g_table_mu;
+static std::map<std::pair<int, std::pair<int, int>>, ResampleTable> g_tables;  // (device, (in, out))
+
+static int get_table(int in_size, int out_size, const ResampleTable** out) {
+  int dev = 0;
+  PSSR_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_table_mu);
+  auto key = std::make_pair(dev, std::make_pair(in_size, out_size));
+  auto it = g_tables.find(key);
+  if (it != g_tables.end()) {
+    *out = &it->second;
+    return PSSR_OK;
+  }
+  ResampleTable t;
+  std::vector<double> kk;
+  std::vector<int32_t> kq;
+  build_coeffs(in_size, out_size, t.h_bounds, kk, kq, t.ksize);
+  t.in_size = in_size;
+  t.out_size = out_size;
+  PSSR_CHECK_CUDA(cudaMalloc(&t.bounds, sizeof(int2) * out_size));
+  PSSR_CHECK_CUDA(cudaMalloc(&t.kq, sizeof(int32_t) * kq.size()));
+  PSSR_CHECK_CUDA(cudaMalloc(&t.kd, sizeof(double) * kk.size()));
+  PSSR_CHECK_CUDA(cudaMemcpy(t.bounds, t.h_bounds.data(), sizeof(int2) * out_size, cudaMemcpyHostToDevice));
+  PSSR_CHECK_CUDA(cudaMemcpy(t.kq, kq.data(), sizeof(int32_t) * kq.size(), cudaMemcpyHostToDevice));
+  PSSR_CHECK_CUDA(cudaMemcpy(t.kd, kk.data(), sizeof(double) * kk.size(), cudaMemcpyHostToDevice));
+  auto ins = g_tables.emplace(key, std::move(t));
+  *out = &ins.first->second;
+  return PSSR_OK;
+}
+
+// ------------------------------------------------------------------------------ Philox
+struct Philox {
+  uint32_t k0, k1;
+  __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
+    uint32_t a = k0, b = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      const uint32_t n0 = hi1 ^ c1 ^ a, n1 = lo1, n2 = hi0 ^ c3 ^ b, n3 = lo0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      a += 0x9E3779B9u;
+      b += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+__device__ __forceinline__ float u01f(uint32_t x) { return ((x >> 8) + 0.5f) * (1.0f / 16777216.0f); }  // (0,1)
+__device__ __forceinline__ double u01d(uint32_t hi, uint32_t lo) {
+  return (double)((((uint64_t)hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);  // [0,1)
+}
+
+// Poisson(lam): Knuth's product method below 10, Hoermann's PTRS above (the pair NumPy's legacy
+// generator uses; the stream of uniforms differs, so free-running mode is validated statistically).
+__device__ double poisson_sample(const Philox& ph, uint32_t pix, uint32_t stage, double lam) {
+  if (!(lam > 0.0)) return 0.0;
+  uint32_t draw = 0;
+  if (lam < 10.0) {
+    const double enlam = exp(-lam);
+    double prod = 1.0;
+    int k = 0;
+    while (true) {
+      const uint4 r = ph(pix, stage, draw++, 0x504F4953u);
+      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        prod *= (double)u01f(w[j]);
+        if (prod <= enlam) return (double)k;
+        ++k;
+      }
+    }
+  }
+  const double slam = sqrt(lam), loglam = log(lam);
+  const double b = 0.931 + 2.53 * slam;
+  const double a = -0.059 + 0.02483 * b;
+  const double invalpha = 1.1239 + 1.1328 / (b - 3.4);
+  const double vr = 0.9277 - 3.6224 / (b - 2.0);
+  while (true) {
+    const uint4 r = ph(pix, stage, draw++, 0x50545253u);
+    const double U = u01d(r.x, r.y) - 0.5;
+    const double V = u01d(r.z, r.w);
+    const double us = 0.5 - fabs(U);
+    const double k = floor((2.0 * a / us + b) * U + lam + 0.43);
+    if (us >= 0.07 && V <= vr) return k;
+    if (k < 0.0 || (us < 0.013 && V > us)) continue;
+    if ((log(V) + log(invalpha) - log(a / (us * us) + b)) <= (-lam + k * loglam - lgamma(k + 1.0))) return k;
+  }
+}
+
+// ------------------------------------------------------------------------------ kernel
+struct StageK {
+  int kind, rng, mix_in_f32, pad;
+  double intensity, gain;
+  const void* injected;
+};
+
+struct CrapK {
+  const void* const* sheets;
+  int elem_bytes, sheet_h, sheet_w;
+  const int32_t *tile_sheet, *tile_frame, *tile_y, *tile_x, *tile_vh, *tile_vw;
+  int n_tiles, frames, lr_frame0, lr_frames, hr_res, lr_res;
+  int TL, tiles_per_side, ksize;
+  int max_rows, raw_pitch;  // shared staging geometry (bytes per raw row, multiple of 16)
+  const int2* bounds;
+  const int32_t* kq;
+  const double* kd;
+  StageK stages[4];
+  int n_stages, clip_between;
+  uint32_t seed_lo, seed_hi;
+  unsigned long long tile_index0;
+  float* lr_out;
+};
+
+template <typename T>
+__device__ __forceinline__ T load_reflect(const T* frame_base, int sheet_w, int ty, int tx, int r, int c, int vh,
+                                          int vw) {
+  const int rr = r < vh ? r : 2 * vh - 2 - r;   // np.pad(mode="reflect")
+  const int cc = c < vw ? c : 2 * vw - 2 - c;
+  return frame_base[(size_t)(ty + rr) * sheet_w + tx + cc];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kCrapThreads) crappify_kernel(const CrapK p) {
+  extern __shared__ __align__(16) uint8_t csm[];
+  const int TL = p.TL;
+  int* lead = reinterpret_cast<int*>(csm);                         // [max_rows] byte offset of each staged row
+  uint8_t* raw = csm + (((size_t)p.max_rows * 4 + 15) & ~(size_t)15);  // [max_rows][raw_pitch]
+  T* inter = reinterpret_cast<T*>(raw + (size_t)p.max_rows * p.raw_pitch);  // [max_rows][TL]
+
+  int bid = blockIdx.x;
+  const int txl = bid % p.tiles_per_side;
+  bid /= p.tiles_per_side;
+  const int tyl = bid % p.tiles_per_side;
+  bid /= p.tiles_per_side;
+  const int fo = bid % p.lr_frames;  // output frame index
+  const int tile = bid / p.lr_frames;
+  const int f = p.lr_frame0 + fo;    // frame inside the tile's window
+
+  const int xx0 = txl * TL, xx1 = min(xx0 + TL, p.lr_res);
+  const int yy0 = tyl * TL, yy1 = min(yy0 + TL, p.lr_res);
+  const int2 bx0 = p.bounds[xx0], bx1 = p.bounds[xx1 - 1];
+  const int2 by0 = p.bounds[yy0], by1 = p.bounds[yy1 - 1];
+  const int col0 = bx0.x, ncols = bx1.x + bx1.y - col0;
+  const int row0 = by0.x, nrows = by1.x + by1.y - row0;
+
+  const int ty = p.tile_y[tile], tx = p.tile_x[tile], vh = p.tile_vh[tile], vw = p.tile_vw[tile];
+  const size_t frame_elems = (size_t)p.sheet_h * p.sheet_w;
+  const T* sheet = reinterpret_cast<const T*>(p.sheets[p.tile_sheet[tile]]);
+  const T* fbase = sheet + (size_t)(p.tile_frame[tile] + f) * frame_elems;
+
+  // ---- stage 1: HR window -> shared (16-byte vectors on the aligned fast path) ----------
+  const bool interior = (row0 + nrows <= vh) && (col0 + ncols <= vw);
+  const bool vec_ok = interior && ((reinterpret_cast<uintptr_t>(sheet) & 15) == 0);
+  if (vec_ok) {
+    const int vec_per_row = p.raw_pitch / 16;
+    for (int i = threadIdx.x; i < nrows * vec_per_row; i += kCrapThreads) {
+      const int r = i / vec_per_row, v = i - r * vec_per_row;
+      const uint8_t* g = reinterpret_cast<const uint8_t*>(fbase + (size_t)(ty + row0 + r) * p.sheet_w + tx + col0);
+      const int ld = (int)(reinterpret_cast<uintptr_t>(g) & 15);
+      if (v == 0) lead[r] = ld;
+      const uint8_t* src = g - ld + (size_t)v * 16;
+      if (src < g + (size_t)ncols * sizeof(T)) {
+        // the vector holds at least one needed byte, lies inside the sheet's 16-byte-aligned extent
+        *reinterpret_cast<uint4*>(raw + (size_t)r * p.raw_pitch + v * 16) = __ldg(reinterpret_cast<const uint4*>(src));
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < nrows * ncols; i += kCrapThreads) {
+      const int r = i / ncols, c = i - r * ncols;
+      reinterpret_cast<T*>(raw + (size_t)r * p.raw_pitch)[c] = load_reflect<T>(fbase, p.sheet_w, ty, tx, row0 + r, col0 + c, vh, vw);
+    }
+    for (int r = threadIdx.x; r < nrows; r += kCrapThreads) lead[r] = 0;
+  }
+  __syncthreads();
+
+  // ---- stage 2: horizontal pass, rounded to the image dtype ------------------------------
+  const int nx = xx1 - xx0, ny = yy1 - yy0;
+  for (int i = threadIdx.x; i < nrows * nx; i += kCrapThreads) {
+    const int r = i / nx, xo = i - r * nx;
+    const int2 b = p.bounds[xx0 + xo];
+    const T* src = reinterpret_cast<const T*>(raw + (size_t)r * p.raw_pitch + lead[r]) + (b.x - col0);
+    if (sizeof(T) == 1) {
+      const int32_t* k = p.kq + (size_t)(xx0 + xo) * p.ksize;
+      int32_t ss = 1 << (kPrecisionBits - 1);
+      for (int x = 0; x < b.y; ++x) ss += (int32_t)src[x] * __ldg(k + x);
+      ss >>= kPrecisionBits;
+      inter[r * TL + xo] = (T)min(max(ss, 0), 255);
+    } else {
+      const double* k = p.kd + (size_t)(xx0 + xo) * p.ksize;
+      double ss = 0.0;
+      for (int x = 0; x < b.y; ++x) ss = __dadd_rn(ss, __dmul_rn((double)src[x], __ldg(k + x)));
+      const int si = (int)(ss + 0.5);
+      inter[r * TL + xo] = (T)((si & 255) | (min(max(si >> 8, 0), 255) << 8));
+    }
+  }
+  __syncthreads();
+
+  // ---- stage 3: vertical pass + noise chain + store -------------------------------------
+  const Philox ph{p.seed_lo ^ (uint32_t)(p.tile_index0 + tile), p.seed_hi ^ (uint32_t)((p.tile_index0 + tile) >> 32)};
+  for (int i = threadIdx.x; i < ny * nx; i += kCrapThreads) {
+    const int yo = i / nx, xo = i - yo * nx;
+    const int2 b = p.bounds[yy0 + yo];
+    const T* src = inter + (size_t)(b.x - row0) * TL + xo;
+    double val;  // carries either a float32 or a float64 quantity, exactly
+    if (sizeof(T) == 1) {
+      const int32_t* k = p.kq + (size_t)(yy0 + yo) * p.ksize;
+      int32_t ss = 1 << (kPrecisionBits - 1);
+      for (int y = 0; y < b.y; ++y) ss += (int32_t)src[(size_t)y * TL] * __ldg(k + y);
+      ss >>= kPrecisionBits;
+      val = (double)min(max(ss, 0), 255);
+    } else {
+      const double* k = p.kd + (size_t)(yy0 + yo) * p.ksize;
+      double ss = 0.0;
+      for (int y = 0; y < b.y; ++y) ss = __dadd_rn(ss, __dmul_rn((double)src[(size_t)y * TL], __ldg(k + y)));
+      const int si = (int)(ss + 0.5);
+      val = (double)((si & 255) | (min(max(si >> 8, 0), 255) << 8));
+    }
+    // `.astype(np.float32)`: exact for values <= 65535 (data.py:483)
+    const int yy = yy0 + yo, xx = xx0 + xo;
+    const uint32_t pix = (uint32_t)((f * p.lr_res + yy) * p.lr_res + xx);
+    const size_t inj = (((size_t)tile * p.frames + f) * p.lr_res + yy) * p.lr_res + xx;
+    for (int s = 0; s < p.n_stages; ++s) {
+      const StageK& st = p.stages[s];
+      if (st.kind == PSSR_NOISE_POISSON) {
+        // x.astype(f32) * (1 - i) + y * i + gain          (crappifiers.py:82-86)
+        const float xf = (float)val;
+        double y;
+        if (st.rng == PSSR_RNG_INJECTED) y = (double)reinterpret_cast<const long long*>(st.injected)[inj];
+        else y = poisson_sample(ph, pix, (uint32_t)s, fmax(val, 0.0));
+        double t;
+        if (st.mix_in_f32) t = (double)__fmul_rn(xf, (float)(1.0 - st.intensity));
+        else t = __dmul_rn((double)xf, 1.0 - st.intensity);
+        val = __dadd_rn(__dadd_rn(t, __dmul_rn(y, st.intensity)), st.gain);
+      } else if (st.kind == PSSR_NOISE_GAUSSIAN) {
+        // x.astype(f32) + normal(gain, intensity)           (crappifiers.py:62-64)
+        const float xf = (float)val;
+        double g;
+        if (st.rng == PSSR_RNG_INJECTED) g = reinterpret_cast<const double*>(st.injected)[inj];
+        else {
+          const uint4 r = ph(pix, (uint32_t)s, 0u, 0x47415553u);
+          const float rad = sqrtf(-2.0f * logf(u01f(r.x)));
+          const float z = rad * cospif(2.0f * u01f(r.y));
+          g = __dadd_rn(st.gain, __dmul_rn(st.intensity, (double)z));
+        }
+        val = __dadd_rn((double)xf, g);
+      } else {
+        // random_noise(clip(x.astype(f32) + gain, 0, 255) / 255, "s&p", amount) * 255   (crappifiers.py:103-105)
+        float v = __fadd_rn((float)val, (float)st.gain);
+        v = fminf(fmaxf(v, 0.f), 255.f);
+        v = __fdiv_rn(v, 255.f);
+        bool flipped, salted;
+        if (st.rng == PSSR_RNG_INJECTED) {
+          const uint8_t m = reinterpret_cast<const uint8_t*>(st.injected)[inj];
+          flipped = m & 1;
+          salted = m & 2;
+        } else {
+          const uint4 r = ph(pix, (uint32_t)s, 0u, 0x53414C54u);
+          flipped = u01d(r.x, r.y) <= st.intensity;
+          salted = u01d(r.z, r.w) <= 0.5;
+        }
+        if (flipped) v = salted ? 1.f : 0.f;
+        v = fminf(fmaxf(v, 0.f), 1.f);
+        val = (double)__fmul_rn(v, 255.f);
+      }
+      if (p.clip_between) val = fmin(fmax(val, 0.0), 255.0);  // MultiCrappifier clip (crappifiers.py:41-42)
+    }
+    if (p.n_stages > 0) val = fmin(fmax(rint(val), 0.0), 255.0);  // np.clip(lr.round(), 0, 255), data.py:487
+    p.lr_out[(((size_t)tile * p.lr_frames + fo) * p.lr_res + yy) * p.lr_res + xx] = (float)val;
+  }
+}
+
+// HR tiles as the dataset returns them (float32 raw values, data.py:495) and/or as `_pred_array`
+// sees them (uint8 clip+trunc of the centre frame, predict.py:245-246).  Pure gather/convert.
+template <typename T>
+__global__ void hr_gather_kernel(const void* const* sheets, const int32_t* tile_sheet, const int32_t* tile_frame,
+                                 const int32_t* tile_y, const int32_t* tile_x, const int32_t* tile_vh,
+                                 const int32_t* tile_vw, int sheet_h, int sheet_w, int hr_res, int hr_frame0,
+                                 int hr_frames, float* hr_out, uint8_t* hr_u8) {
+  const int tile = blockIdx.z;
+  const int fo = blockIdx.y;
+  const T* sheet = reinterpret_cast<const T*>(sheets[tile_sheet[tile]]);
+  const T* fbase = sheet + (size_t)(tile_frame[tile] + hr_frame0 + fo) * sheet_h * sheet_w;
+  const int ty = tile_y[tile], tx = tile_x[tile], vh = tile_vh[tile], vw = tile_vw[tile];
+  const int centre = hr_frames / 2;  // _slice_center(x, 1) keeps index shape//2
+  const size_t n = (size_t)hr_res * hr_res;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / hr_res), c = (int)(i - (size_t)r * hr_res);
+    const T v = load_reflect<T>(fbase, sheet_w, ty, tx, r, c, vh, vw);
+    if (hr_out) hr_out[((size_t)tile * hr_frames + fo) * n + i] = (float)v;
+    if (hr_u8 && fo == centre) hr_u8[(size_t)tile * n + i] = (uint8_t)min((int)v, 255);
+  }
+}
+
+// Standalone resample (Pillow parity tests)
+template <typename T>
+__global__ void resize_plain_kernel(const T* src, T* dst, int n, int h, int w, int oh, int ow, const int2* bh,
+                                    const int2* bw, const int32_t* kqh, const int32_t* kqw, const double* kdh,
+                                    const double* kdw, int ksh, int ksw, T* tmp) {
+  // pass 1: horizontal into tmp [n][h][ow]; pass 2 runs as a second launch (phase flag via dst==nullptr)
+  const size_t total = dst == nullptr ? (size_t)n * h * ow : (size_t)n * oh * ow;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    if (dst == nullptr) {
+      const int xo = (int)(i % ow);
+      const size_t row = i / ow;
+      const int2 b = bw[xo];
+      const T* s = src + row * w + b.x;
+      if (sizeof(T) == 1) {
+        int32_t ss = 1 << (kPrecisionBits - 1);
+        for (int x = 0; x < b.y; ++x) ss += (int32_t)s[x] * kqw[(size_t)xo * ksw + x];
+        tmp[i] = (T)min(max(ss >> kPrecisionBits, 0), 255);
+      } else {
+        double ss = 0.0;
+        for (int x = 0; x < b.y; ++x) ss = __dadd_rn(ss, __dmul_rn((double)s[x], kdw[(size_t)xo * ksw + x]));
+        const int si = (int)(ss + 0.5);
+        tmp[i] = (T)((si & 255) | (min(max(si >> 8, 0), 255) << 8));
+      }
+    } else {
+      const int xo = (int)(i % ow);
+      const int yo = (int)((i / ow) % oh);
+      const size_t img = i / ((size_t)ow * oh);
+      const int2 b = bh[yo];
+      const T* s = tmp + (img * h + b.x) * ow + xo;
+      if (sizeof(T) == 1) {
+        int32_t ss = 1 << (kPrecisionBits - 1);
+        for (int y = 0; y < b.y; ++y) ss += (int32_t)s[(size_t)y * ow] * kqh[(size_t)yo * ksh + y];
+        dst[i] = (T)min(max(ss >> kPrecisionBits, 0), 255);
+      } else {
+        double ss = 0.0;
+        for (int y = 0; y < b.y; ++y) ss = __dadd_rn(ss, __dmul_rn((double)s[(size_t)y * ow], kdh[(size_t)yo * ksh + y]));
+        const int si = (int)(ss + 0.5);
+        dst[i] = (T)((si & 255) | (min(max(si >> 8, 0), 255) << 8));
+      }
+    }
+  }
+}
+
+}  // namespace pssr
+
+using namespace pssr;
+
+extern "C" int pssr_crappify(const pssr_crappify_args_t* a, void* stream) {
+  PSSR_REQUIRE(a != nullptr, PSSR_EINVAL, "crappify: null args");
+  PSSR_REQUIRE(a->elem_bytes == 1 || a->elem_bytes == 2, PSSR_EUNSUP, "crappify: elem_bytes must be 1 (uint8) or 2 (uint16)");
+  PSSR_REQUIRE(a->n_tiles >= 0 && a->frames >= 1 && a->hr_res >= 1 && a->lr_scale >= 1, PSSR_EINVAL, "crappify: bad sizes");
+  PSSR_REQUIRE(a->lr_frames >= 1 && a->lr_frame0 >= 0 && a->lr_frame0 + a->lr_frames <= a->frames, PSSR_EINVAL,
+               "crappify: LR frame window [%d,+%d) outside the %d frames of the tile", a->lr_frame0, a->lr_frames, a->frames);
+  PSSR_REQUIRE(a->n_stages >= 0 && a->n_stages <= 4, PSSR_EINVAL, "crappify: at most 4 noise stages");
+  PSSR_REQUIRE(a->sheets && a->tile_sheet && a->tile_frame && a->tile_y && a->tile_x && a->tile_vh && a->tile_vw,
+               PSSR_EINVAL, "crappify: null tile table");
+  if (a->n_tiles == 0) return PSSR_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int lr_res = a->hr_res / a->lr_scale;
+  PSSR_REQUIRE(lr_res >= 1, PSSR_EINVAL, "crappify: lr_scale larger than hr_res");
+
+  if (a->lr_out != nullptr) {
+    const ResampleTable* tab = nullptr;
+    int rc = get_table(a->hr_res, lr_res, &tab);
+    if (rc != PSSR_OK) return rc;
+    CrapK p;
+    memset(&p, 0, sizeof(p));
+    p.sheets = a->sheets;
+    p.elem_bytes = a->elem_bytes;
+    p.sheet_h = a->sheet_h;
+    p.sheet_w = a->sheet_w;
+    p.tile_sheet = a->tile_sheet; p.tile_frame = a->tile_frame; p.tile_y = a->tile_y; p.tile_x = a->tile_x;
+    p.tile_vh = a->tile_vh; p.tile_vw = a->tile_vw;
+    p.n_tiles = a->n_tiles; p.frames = a->frames; p.lr_frame0 = a->lr_frame0; p.lr_frames = a->lr_frames;
+    p.hr_res = a->hr_res; p.lr_res = lr_res;
+    int TL = 128 / a->lr_scale;
+    if (TL < 4) TL = 4;
+    if (TL > 64) TL = 64;
+    if (TL > lr_res) TL = lr_res;
+    p.TL = TL;
+    p.tiles_per_side = (lr_res + TL - 1) / TL;
+    p.ksize = tab->ksize;
+    int max_span = 0;
+    for (int t = 0; t < p.tiles_per_side; ++t) {
+      const int x0 = t * TL, x1 = (x0 + TL < lr_res ? x0 + TL : lr_res) - 1;
+      const int span = tab->h_bounds[x1].x + tab->h_bounds[x1].y - tab->h_bounds[x0].x;
+      if (span > max_span) max_span = span;
+    }
+    p.max_rows = max_span;
+    p.raw_pitch = ((max_span * a->elem_bytes + 15 + 15) / 16) * 16;  // + worst-case 15-byte lead
+    p.bounds = tab->bounds; p.kq = tab->kq; p.kd = tab->kd;
+    p.n_stages = a->n_stages;
+    p.clip_between = a->clip_between;
+    for (int s = 0; s < a->n_stages; ++s) {
+      const pssr_noise_stage_t& ns = a->stages[s];
+      PSSR_REQUIRE(ns.kind >= PSSR_NOISE_POISSON && ns.kind <= PSSR_NOISE_SALTPEPPER, PSSR_EINVAL, "crappify: bad noise kind %d", ns.kind);
+      PSSR_REQUIRE(ns.rng == PSSR_RNG_PHILOX || ns.injected != nullptr, PSSR_EINVAL, "crappify: injected noise buffer missing for stage %d", s);
+      p.stages[s].kind = ns.kind; p.stages[s].rng = ns.rng; p.stages[s].mix_in_f32 = ns.mix_in_f32;
+      p.stages[s].intensity = ns.intensity; p.stages[s].gain = ns.gain; p.stages[s].injected = ns.injected;
+    }
+    p.seed_lo = (uint32_t)a->seed; p.seed_hi = (uint32_t)(a->seed >> 32);
+    p.tile_index0 = a->tile_index0;
+    p.lr_out = a->lr_out;
+    const size_t smem = (size_t)p.max_rows * p.raw_pitch + (size_t)p.max_rows * TL * a->elem_bytes + (size_t)p.max_rows * 4 + 32;
+    PSSR_REQUIRE(smem <= 200 * 1024, PSSR_EUNSUP, "crappify: staging needs %zu bytes of shared memory (scale %d too large)", smem, a->lr_scale);
+    const long long blocks = (long long)a->n_tiles * a->lr_frames * p.tiles_per_side * p.tiles_per_side;
+    PSSR_REQUIRE(blocks < (1ll << 31), PSSR_EUNSUP, "crappify: too many blocks");
+    if (a->elem_bytes == 1) {
+      static bool attr1 = false;
+      if (!attr1) { PSSR_CHECK_CUDA(cudaFuncSetAttribute(crappify_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr1 = true; }
+      crappify_kernel<uint8_t><<<(unsigned)blocks, kCrapThreads, smem, st>>>(p);
+    } else {
+      static bool attr2 = false;
+      if (!attr2) { PSSR_CHECK_CUDA(cudaFuncSetAttribute(crappify_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr2 = true; }
+      crappify_kernel<uint16_t><<<(unsigned)blocks, kCrapThreads, smem, st>>>(p);
+    }
+    count_launch();
+    PSSR_CHECK_CUDA(cudaGetLastError());
+  }
+  if (a->hr_out != nullptr || a->hr_u8_out != nullptr) {
+    PSSR_REQUIRE(a->hr_frames >= 1 && a->hr_frame0 >= 0 && a->hr_frame0 + a->hr_frames <= a->frames, PSSR_EINVAL,
+                 "crappify: HR frame window outside the tile");
+    dim3 grid(64, a->hr_frames, a->n_tiles);
+    if (a->elem_bytes == 1)
+      hr_gather_kernel<uint8_t><<<grid, 256, 0, st>>>(a->sheets, a->tile_sheet, a->tile_frame, a->tile_y, a->tile_x, a->tile_vh,
+                                                      a->tile_vw, a->sheet_h, a->sheet_w, a->hr_res, a->hr_frame0, a->hr_frames,
+                                                      a->hr_out, a->hr_u8_out);
+    else
+      hr_gather_kernel<uint16_t><<<grid, 256, 0, st>>>(a->sheets, a->tile_sheet, a->tile_frame, a->tile_y, a->tile_x, a->tile_vh,
+                                                       a->tile_vw, a->sheet_h, a->sheet_w, a->hr_res, a->hr_frame0, a->hr_frames,
+                                                       a->hr_out, a->hr_u8_out);
+    count_launch();
+    PSSR_CHECK_CUDA(cudaGetLastError());
+  }
+  return PSSR_OK;
+}
+
+extern "C" int pssr_resize_bilinear(const void* src, void* dst, int32_t n, int32_t h, int32_t w, int32_t scale,
+                                    int32_t elem_bytes, void* stream) {
+  PSSR_REQUIRE(src && dst && n >= 1 && h >= 1 && w >= 1 && scale >= 1, PSSR_EINVAL, "resize: bad arguments");
+  PSSR_REQUIRE(elem_bytes == 1 || elem_bytes == 2, PSSR_EUNSUP, "resize: elem_bytes must be 1 or 2");
+  const int oh = h / scale, ow = w / scale;
+  PSSR_REQUIRE(oh >= 1 && ow >= 1, PSSR_EINVAL, "resize: scale larger than the image");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const ResampleTable *th = nullptr, *tw = nullptr;
+  int rc = get_table(h, oh, &th);
+  if (rc != PSSR_OK) return rc;
+  rc = get_table(w, ow, &tw);
+  if (rc != PSSR_OK) return rc;
+  void* tmp = nullptr;
+  PSSR_CHECK_CUDA(cudaMallocAsync(&tmp, (size_t)n * h * ow * elem_bytes, st));
+  const int blocks = device_sm_count() * 8;
+  if (elem_bytes == 1) {
+    resize_plain_kernel<uint8_t><<<blocks, 256, 0, st>>>((const uint8_t*)src, nullptr, n, h, w, oh, ow, th->bounds, tw->bounds, th->kq,
+                                                         tw->kq, th->kd, tw->kd, th->ksize, tw->ksize, (uint8_t*)tmp);
+    resize_plain_kernel<uint8_t><<<blocks, 256, 0, st>>>((const uint8_t*)src, (uint8_t*)dst, n, h, w, oh, ow, th->bounds, tw->bounds,
+                                                         th->kq, tw->kq, th->kd, tw->kd, th->ksize, tw->ksize, (uint8_t*)tmp);
+  } else {
+    resize_plain_kernel<uint16_t><<<blocks, 256, 0, st>>>((const uint16_t*)src, nullptr, n, h, w, oh, ow, th->bounds, tw->bounds,
+                                                          th->kq, tw->kq, th->kd, tw->kd, th->ksize, tw->ksize, (uint16_t*)tmp);
+    resize_plain_kernel<uint16_t><<<blocks, 256, 0, st>>>((const uint16_t*)src, (uint16_t*)dst, n, h, w, oh, ow, th->bounds,
+                                                          tw->bounds, th->kq, tw->kq, th->kd, tw->kd, th->ksize, tw->ksize, (uint16_t*)tmp);
+  }
+  count_launch(2);
+  PSSR_CHECK_CUDA(cudaGetLastError());
+  PSSR_CHECK_CUDA(cudaFreeAsync(tmp, st));
+  return PSSR_OK;
+}

@@ -1,0 +1,218 @@
+// HBM-bound companions of the tensor-core convolution (family 2):
+//   prep  : x/128-1 -> BatchNorm2d(eval) -> 3x3 im2col of the (few-channel) network input
+//           pssr/models/resunet.py:66-70 (the normalised input is also the last skip, :90)
+//   pool  : F.max_pool2d(x, 2) on NHWC 16-bit                 pssr/models/resunet.py:76
+//   tail  : Reconstruction.conv (3x3, hidden -> out channels) + x*128+128, with the fused
+//           clip -> uint8 truncation -> centre channel of `_pred_array`
+//           pssr/models/_blocks.py:17, resunet.py:95, pssr/predict.py:245-246
+#include "common.cuh"
+#include "plan.h"
+
+namespace pssr {
+
+// ------------------------------------------------------------------------------ prep
+// One thread per pixel writes its 64-channel (128 B) im2col row.  Zero padding is applied AFTER
+// normalisation (reference quirk: BN acts before the conv's padding), so out-of-image taps are 0.
+__global__ void prep_im2col_kernel(pssr_prep_desc_t d, int fp16) {
+  const long long total = (long long)d.B * d.H * d.W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % d.W);
+    const int y = (int)((i / d.W) % d.H);
+    const int n = (int)(i / ((long long)d.W * d.H));
+    uint32_t row[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) row[k] = 0u;
+    uint16_t* r16 = reinterpret_cast<uint16_t*>(row);
+    for (int c = 0; c < d.C; ++c) {
+      const float s = d.scale[c], t = d.shift[c];
+      const size_t plane = ((size_t)n * d.C + c) * d.H * (size_t)d.W;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        float v = 0.f;
+        if (yy >= 0 && yy < d.H && xx >= 0 && xx < d.W) {
+          const size_t idx = plane + (size_t)yy * d.W + xx;
+          const float raw = d.x_u8 ? (float)reinterpret_cast<const uint8_t*>(d.x)[idx]
+                                   : reinterpret_cast<const float*>(d.x)[idx];
+          v = (raw / 128.f - 1.f) * s + t;
+          if (tap == 4 && d.xnorm_f32 != nullptr) d.xnorm_f32[idx] = v;
+        }
+        r16[c * 9 + tap] = pack1(v, fp16);
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(d.im2col) + (size_t)i * 64);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dst[k] = make_uint4(row[4 * k], row[4 * k + 1], row[4 * k + 2], row[4 * k + 3]);
+  }
+}
+
+int prep_launch(const pssr_prep_desc_t& d, int dtype, cudaStream_t stream) {
+  PSSR_REQUIRE(d.C >= 1 && d.C * 9 <= 64, PSSR_EUNSUP, "prep: %d input channels unsupported (9*C must be <= 64)", d.C);
+  PSSR_REQUIRE(d.x && d.im2col && d.scale && d.shift, PSSR_EINVAL, "prep: null pointer");
+  const long long total = (long long)d.B * d.H * d.W;
+  const int threads = 128;
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = (long long)device_sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  prep_im2col_kernel<<<(int)blocks, threads, 0, stream>>>(d, dtype == PSSR_DT_FP16);
+  count_launch();
+  PSSR_CHECK_CUDA(cudaGetLastError());
+  return PSSR_OK;
+}
+
+// ------------------------------------------------------------------------------ pool
+__device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b, int fp16) {
+  if (fp16) {
+    __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint4 max4(uint4 a, uint4 b, int fp16) {
+  return make_uint4(max2(a.x, b.x, fp16), max2(a.y, b.y, fp16), max2(a.z, b.z, fp16), max2(a.w, b.w, fp16));
+}
+
+// One thread per (output pixel, 8-channel group): 4 x 16-byte loads, 1 x 16-byte store.
+__global__ void maxpool2_kernel(pssr_pool_desc_t d, int fp16) {
+  const int groups = d.C / 8;
+  const int Ho = d.H / 2, Wo = d.W / 2;
+  const long long total = (long long)d.B * Ho * Wo * groups;
+  const uint16_t* in = reinterpret_cast<const uint16_t*>(d.in) + d.in_choff;
+  uint16_t* out = reinterpret_cast<uint16_t*>(d.out) + d.out_choff;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long pix = i / groups;
+    const int x = (int)(pix % Wo);
+    const int y = (int)((pix / Wo) % Ho);
+    const int n = (int)(pix / ((long long)Wo * Ho));
+    const size_t p00 = (((size_t)n * d.H + 2 * y) * d.W + 2 * x) * d.in_cstride + g * 8;
+    const size_t rowstride = (size_t)d.W * d.in_cstride;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(in + p00));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(in + p00 + d.in_cstride));
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(in + p00 + rowstride));
+    const uint4 e = __ldg(reinterpret_cast<const uint4*>(in + p00 + rowstride + d.in_cstride));
+    const uint4 m = max4(max4(a, b, fp16), max4(c, e, fp16), fp16);
+    *reinterpret_cast<uint4*>(out + (size_t)pix * d.out_cstride + g * 8) = m;
+  }
+}
+
+int pool_launch(const pssr_pool_desc_t& d, int dtype, cudaStream_t stream) {
+  PSSR_REQUIRE(d.C % 8 == 0 && d.in_cstride % 8 == 0 && d.out_cstride % 8 == 0 && d.in_choff % 8 == 0 &&
+                   d.out_choff % 8 == 0,
+               PSSR_EUNSUP, "pool: channel counts/strides/offsets must be multiples of 8");
+  PSSR_REQUIRE(d.H % 2 == 0 && d.W % 2 == 0, PSSR_EUNSUP, "pool: odd spatial size %dx%d", d.H, d.W);
+  const long long total = (long long)d.B * (d.H / 2) * (d.W / 2) * (d.C / 8);
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = (long long)device_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  maxpool2_kernel<<<(int)blocks, threads, 0, stream>>>(d, dtype == PSSR_DT_FP16);
+  count_launch();
+  PSSR_CHECK_CUDA(cudaGetLastError());
+  return PSSR_OK;
+}
+
+// ------------------------------------------------------------------------------ tail
+// 3x3 conv from C (<=128) NHWC 16-bit channels to Cout (<=4) fp32 channels on CUDA cores: the
+// layer has N = 1..4 outputs, far below a tensor-core tile, and is bound by reading its input.
+// A CTA computes a 32x8 pixel tile from a (34x10) halo tile staged in shared memory; 16-byte
+// channel chunks are XOR-swizzled by pixel so that the 8 threads of a quarter-warp hit 8
+// different bank groups.
+static constexpr int kTailTW = 32, kTailTH = 8, kTailMaxCout = 4;
+
+__global__ void __launch_bounds__(kTailTW* kTailTH) tail_conv_kernel(pssr_tail_desc_t d, int fp16) {
+  extern __shared__ uint8_t tail_smem[];
+  const int C = d.C;
+  const int chunks = C / 8;                 // 16-byte chunks per pixel
+  const int HW = kTailTW + 2, HH = kTailTH + 2;
+  uint4* tile = reinterpret_cast<uint4*>(tail_smem);                      // [HH*HW][chunks] swizzled
+  float* wsm = reinterpret_cast<float*>(tail_smem + (size_t)HH * HW * chunks * 16);  // [Cout][9][C]
+
+  const int tiles_x = (d.W + kTailTW - 1) / kTailTW;
+  const int tiles_y = (d.H + kTailTH - 1) / kTailTH;
+  const int n = blockIdx.x / (tiles_x * tiles_y);
+  const int trem = blockIdx.x % (tiles_x * tiles_y);
+  const int x0 = (trem % tiles_x) * kTailTW, y0 = (trem / tiles_x) * kTailTH;
+
+  for (int i = threadIdx.x; i < d.Cout * 9 * C; i += blockDim.x) wsm[i] = d.weight[i];
+  const uint16_t* in = reinterpret_cast<const uint16_t*>(d.in);
+  const int mask = chunks >= 8 ? 7 : (chunks - 1);  // chunks is 1,2,4 or a multiple of 8 (checked on host)
+  for (int i = threadIdx.x; i < HH * HW * chunks; i += blockDim.x) {
+    const int ch = i % chunks;
+    const int pp = i / chunks;
+    const int yy = y0 + pp / HW - 1, xx = x0 + pp % HW - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (yy >= 0 && yy < d.H && xx >= 0 && xx < d.W)
+      v = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)n * d.H + yy) * d.W + xx) * d.cstride + ch * 8));
+    tile[pp * chunks + (ch ^ (pp & mask))] = v;
+  }
+  __syncthreads();
+
+  const int lx = threadIdx.x % kTailTW, ly = threadIdx.x / kTailTW;
+  float acc[kTailMaxCout];
+#pragma unroll
+  for (int o = 0; o < kTailMaxCout; ++o) acc[o] = 0.f;
+  for (int tap = 0; tap < 9; ++tap) {
+    const int pp = (ly + tap / 3) * HW + lx + tap % 3;
+    const uint4* prow = tile + pp * chunks;
+    const int sw = pp & mask;
+    for (int ch = 0; ch < chunks; ++ch) {
+      const uint4 v = prow[ch ^ sw];
+      float f[8];
+      const uint32_t w32[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        f[2 * k] = unpack1((uint16_t)(w32[k] & 0xFFFFu), fp16);
+        f[2 * k + 1] = unpack1((uint16_t)(w32[k] >> 16), fp16);
+      }
+#pragma unroll
+      for (int o = 0; o < kTailMaxCout; ++o) {
+        if (o < d.Cout) {
+          const float* w = wsm + ((size_t)o * 9 + tap) * C + ch * 8;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[o] = fmaf(f[k], w[k], acc[o]);
+        }
+      }
+    }
+  }
+  const int x = x0 + lx, y = y0 + ly;
+  if (x < d.W && y < d.H) {
+#pragma unroll
+    for (int o = 0; o < kTailMaxCout; ++o) {
+      if (o < d.Cout) {
+        const float yv = (acc[o] + d.bias[o]) * d.mul + d.add;
+        if (d.out_f32 != nullptr) d.out_f32[(((size_t)n * d.Cout + o) * d.H + y) * d.W + x] = yv;
+        if (d.out_u8 != nullptr && o == d.Cout / 2) {
+          // np.clip(., 0, 255).astype(np.uint8): truncation toward zero (predict.py:246)
+          const float cl = fminf(fmaxf(yv, 0.f), 255.f);
+          d.out_u8[((size_t)n * d.H + y) * d.W + x] = (uint8_t)(int)cl;
+        }
+      }
+    }
+  }
+}
+
+int tail_launch(const pssr_tail_desc_t& d, int dtype, cudaStream_t stream) {
+  PSSR_REQUIRE(d.Cout >= 1 && d.Cout <= kTailMaxCout, PSSR_EUNSUP, "tail: Cout=%d unsupported (1..4)", d.Cout);
+  const int chunks = d.C / 8;
+  PSSR_REQUIRE(d.C % 8 == 0 && d.C <= 128 && (chunks == 1 || chunks == 2 || chunks == 4 || chunks % 8 == 0),
+               PSSR_EUNSUP, "tail: C=%d unsupported", d.C);
+  PSSR_REQUIRE(d.cstride % 8 == 0 && d.cstride >= d.C, PSSR_EUNSUP, "tail: bad channel stride");
+  const size_t smem = (size_t)(kTailTW + 2) * (kTailTH + 2) * chunks * 16 + (size_t)d.Cout * 9 * d.C * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PSSR_CHECK_CUDA(cudaFuncSetAttribute(tail_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  const int tiles = ((d.W + kTailTW - 1) / kTailTW) * ((d.H + kTailTH - 1) / kTailTH);
+  tail_conv_kernel<<<d.B * tiles, kTailTW * kTailTH, smem, stream>>>(d, dtype == PSSR_DT_FP16);
+  count_launch();
+  PSSR_CHECK_CUDA(cudaGetLastError());
+  return PSSR_OK;
+}
+
+}  // namespace pssr

@@ -1,0 +1,32 @@
+// Internal plan structures shared by the op implementations (family 2).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <vector>
+#include "../../include/pssr_b200.h"
+
+namespace pssr {
+
+struct ConvOp {
+  CUtensorMap tmaps[4];           // host copies; uploaded into the plan's device table
+  alignas(16) uint8_t kparams[320];
+  int grid = 0;
+  int smem_bytes = 0;
+};
+
+int conv_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op);
+int conv_launch(const ConvOp& op, const void* tmaps_dev, cudaStream_t stream);
+
+int prep_launch(const pssr_prep_desc_t& d, int dtype, cudaStream_t stream);
+int pool_launch(const pssr_pool_desc_t& d, int dtype, cudaStream_t stream);
+int tail_launch(const pssr_tail_desc_t& d, int dtype, cudaStream_t stream);
+
+}  // namespace pssr
+
+struct pssr_plan {
+  int dtype = 0;
+  std::vector<pssr_op_t> ops;
+  std::vector<pssr::ConvOp> convs;     // one per PSSR_OP_CONV, in op order
+  std::vector<int> conv_index;          // op index -> index into convs (or -1)
+  void* tmaps_dev = nullptr;            // device table: 4 CUtensorMap per conv op
+};

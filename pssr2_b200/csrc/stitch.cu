@@ -1,0 +1,63 @@
+// Family 3: overlap-weighted tile stitch.  Replaces `_patch_images` (pssr/util.py:116-137) and the
+// uint8 cast at pssr/util.py:100.  The reference accumulates every tile into a float64 canvas plus a
+// float64 count canvas and divides; here every OUTPUT pixel gathers its contributors directly
+// (tile rows/cols whose kept span covers it), so there are no atomics and no intermediate canvases:
+// integer sum / integer count, truncated, equals the reference's float64 quotient truncated to uint8.
+// Inner tiles drop `margin` pixels on interior edges (util.py:131); pixels nobody covers stay 0
+// (count forced to 1, util.py:136).
+#include "common.cuh"
+
+namespace pssr {
+
+__global__ void stitch_kernel(const uint8_t* __restrict__ tiles, uint8_t* __restrict__ sheets, int n_rows, int n_cols,
+                              int T, int step, int margin, int out_h, int out_w) {
+  const int stack = blockIdx.z;
+  const size_t tile_px = (size_t)T * T;
+  const uint8_t* tb = tiles + (size_t)stack * n_rows * n_cols * tile_px;
+  uint8_t* ob = sheets + (size_t)stack * out_h * out_w;
+  const int Y = blockIdx.y;
+  // tile rows whose kept span [r*step + m0, r*step + T - m1) contains Y
+  int r_lo = Y - T + 1 <= 0 ? 0 : (Y - T + step) / step;  // ceil((Y-T+1)/step)
+  int r_hi = Y / step;
+  if (r_hi > n_rows - 1) r_hi = n_rows - 1;
+  for (int X = blockIdx.x * blockDim.x + threadIdx.x; X < out_w; X += gridDim.x * blockDim.x) {
+    int c_lo = X - T + 1 <= 0 ? 0 : (X - T + step) / step;
+    int c_hi = X / step;
+    if (c_hi > n_cols - 1) c_hi = n_cols - 1;
+    int sum = 0, cnt = 0;
+    for (int r = r_lo; r <= r_hi; ++r) {
+      const int ly = Y - r * step;
+      const int m0 = r != 0 ? margin : 0, m1 = r != n_rows - 1 ? margin : 0;
+      if (ly < m0 || ly >= T - m1) continue;
+      for (int c = c_lo; c <= c_hi; ++c) {
+        const int lx = X - c * step;
+        const int n0 = c != 0 ? margin : 0, n1 = c != n_cols - 1 ? margin : 0;
+        if (lx < n0 || lx >= T - n1) continue;
+        sum += tb[(size_t)(r * n_cols + c) * tile_px + (size_t)ly * T + lx];
+        ++cnt;
+      }
+    }
+    ob[(size_t)Y * out_w + X] = (uint8_t)(cnt > 0 ? sum / cnt : 0);
+  }
+}
+
+}  // namespace pssr
+
+using namespace pssr;
+
+extern "C" int pssr_stitch(const uint8_t* tiles, uint8_t* sheets, int32_t n_stacks, int32_t n_rows, int32_t n_cols,
+                           int32_t tile, int32_t overlap, int32_t margin, void* stream) {
+  PSSR_REQUIRE(tiles && sheets, PSSR_EINVAL, "stitch: null pointer");
+  PSSR_REQUIRE(n_stacks >= 1 && n_rows >= 1 && n_cols >= 1 && tile >= 1, PSSR_EINVAL, "stitch: bad sizes");
+  PSSR_REQUIRE(overlap >= 0 && overlap < tile, PSSR_EINVAL, "stitch: overlap must be in [0, tile)");
+  // same contract as reassemble_sheets (util.py:76-77)
+  PSSR_REQUIRE(margin >= 0 && margin <= overlap, PSSR_EINVAL, "The value of margin cannot be greater than overlap. Given %d and %d respectively.", margin, overlap);
+  const int step = tile - overlap;
+  const int out_h = n_rows * step + overlap, out_w = n_cols * step + overlap;
+  PSSR_REQUIRE(n_stacks <= 65535 && out_h <= 65535, PSSR_EUNSUP, "stitch: sheet too large for the launch grid");
+  dim3 grid((out_w + 255) / 256, out_h, n_stacks);
+  stitch_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tiles, sheets, n_rows, n_cols, tile, step, margin, out_h, out_w);
+  count_launch();
+  PSSR_CHECK_CUDA(cudaGetLastError());
+  return PSSR_OK;
+}

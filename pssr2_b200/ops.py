@@ -1,0 +1,166 @@
+"""Thin torch-tensor wrappers over the C ABI for kernel families 1, 3 and 4
+(``include/pssr_b200.h``).  torch provides device memory and the current stream only.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (NOISE_GAUSSIAN, NOISE_POISSON, NOISE_SALTPEPPER, RNG_INJECTED, RNG_PHILOX, CrappifyArgs, NoiseStage)
+
+
+def _cuda(t, what):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError(f"{what} must be a CUDA tensor (pssr2_b200 has no CPU path)")
+    return t
+
+
+class NoiseSpec:
+    """One resolved noise stage of a crappify call."""
+
+    def __init__(self, kind, intensity=0.0, gain=0.0, mix_in_f32=True, injected=None):
+        self.kind, self.intensity, self.gain, self.mix_in_f32, self.injected = kind, float(intensity), float(gain), mix_in_f32, injected
+
+
+class TileTable:
+    """Device-resident description of where each HR tile lives inside the resident sheets."""
+
+    def __init__(self, sheets, tile_sheet, tile_frame, tile_y, tile_x, tile_vh, tile_vw):
+        dev = sheets[0].device
+        self.sheets = [_cuda(s, "sheet").contiguous() for s in sheets]
+        s0 = self.sheets[0]
+        for s in self.sheets:
+            if s.dim() != 3 or s.shape[1:] != s0.shape[1:] or s.dtype != s0.dtype:
+                raise ValueError("all sheets must be [frames, H, W] with one shape and dtype")
+        if s0.dtype == torch.uint8:
+            self.elem_bytes = 1
+        elif s0.dtype in (torch.uint16, torch.int16):
+            self.elem_bytes = 2
+        else:
+            raise TypeError(f"sheets must be uint8 or uint16, got {s0.dtype}")
+        self.sheet_h, self.sheet_w = int(s0.shape[1]), int(s0.shape[2])
+        self.ptrs = torch.tensor([s.data_ptr() for s in self.sheets], dtype=torch.int64, device=dev)
+        mk = lambda a: torch.as_tensor(np.asarray(a, dtype=np.int32), device=dev)
+        self.tile_sheet, self.tile_frame, self.tile_y, self.tile_x = mk(tile_sheet), mk(tile_frame), mk(tile_y), mk(tile_x)
+        self.tile_vh, self.tile_vw = mk(tile_vh), mk(tile_vw)
+        self.n_tiles = int(self.tile_sheet.numel())
+        self.device = dev
+
+    def slice(self, start, count):
+        t = object.__new__(TileTable)
+        t.__dict__.update(self.__dict__)
+        for k in ("tile_sheet", "tile_frame", "tile_y", "tile_x", "tile_vh", "tile_vw"):
+            setattr(t, k, getattr(self, k)[start:start + count])
+        t.n_tiles = count
+        return t
+
+
+def crappify(table: TileTable, hr_res, lr_scale, stages, *, frames=1, lr_frame0=0, lr_frames=None, hr_frame0=0, hr_frames=None,
+             clip_between=False, seed=0, tile_index0=0, want_lr=True, want_hr_f32=False, want_hr_u8=False):
+    """Fused tile gather + Pillow-exact BILINEAR downscale + noise + round/clip (pssr/data.py:471-495).
+    stages: list[NoiseSpec] or None (crappifier=None).  Returns (lr f32 [n, lr_frames, lr, lr] | None,
+    hr f32 [n, hr_frames, hr, hr] | None, hr u8 [n, 1, hr, hr] | None)."""
+    n = table.n_tiles
+    lr_res = hr_res // lr_scale
+    lr_frames = frames if lr_frames is None else lr_frames
+    hr_frames = frames if hr_frames is None else hr_frames
+    dev = table.device
+    a = CrappifyArgs()
+    a.sheets = table.ptrs.data_ptr()
+    a.n_sheets = len(table.sheets)
+    a.elem_bytes = table.elem_bytes
+    a.sheet_h, a.sheet_w = table.sheet_h, table.sheet_w
+    a.tile_sheet, a.tile_frame = table.tile_sheet.data_ptr(), table.tile_frame.data_ptr()
+    a.tile_y, a.tile_x = table.tile_y.data_ptr(), table.tile_x.data_ptr()
+    a.tile_vh, a.tile_vw = table.tile_vh.data_ptr(), table.tile_vw.data_ptr()
+    a.n_tiles, a.frames, a.hr_res, a.lr_scale = n, frames, hr_res, lr_scale
+    keep = []
+    stages = [] if stages is None else stages
+    if len(stages) > 4:
+        raise ValueError("at most 4 chained noise stages are supported")
+    for i, s in enumerate(stages):
+        st = NoiseStage()
+        st.kind = s.kind
+        st.intensity, st.gain = s.intensity, s.gain
+        st.mix_in_f32 = 1 if s.mix_in_f32 else 0
+        if s.injected is not None:
+            inj = _cuda(s.injected, "injected noise").contiguous()
+            want = {NOISE_POISSON: torch.int64, NOISE_GAUSSIAN: torch.float64, NOISE_SALTPEPPER: torch.uint8}[s.kind]
+            if inj.dtype != want or inj.numel() != n * frames * lr_res * lr_res:
+                raise ValueError(f"injected noise for stage {i} must be {want} with {n * frames * lr_res * lr_res} elements")
+            keep.append(inj)
+            st.rng, st.injected = RNG_INJECTED, inj.data_ptr()
+        else:
+            st.rng, st.injected = RNG_PHILOX, None
+        a.stages[i] = st
+    a.n_stages = len(stages)
+    a.clip_between = 1 if clip_between else 0
+    a.seed, a.tile_index0 = int(seed) & (2 ** 64 - 1), int(tile_index0)
+    a.hr_frame0, a.hr_frames, a.lr_frame0, a.lr_frames = hr_frame0, hr_frames, lr_frame0, lr_frames
+    lr = torch.empty(n, lr_frames, lr_res, lr_res, dtype=torch.float32, device=dev) if want_lr else None
+    hr = torch.empty(n, hr_frames, hr_res, hr_res, dtype=torch.float32, device=dev) if want_hr_f32 else None
+    hr8 = torch.empty(n, 1, hr_res, hr_res, dtype=torch.uint8, device=dev) if want_hr_u8 else None
+    a.lr_out = lr.data_ptr() if lr is not None else None
+    a.hr_out = hr.data_ptr() if hr is not None else None
+    a.hr_u8_out = hr8.data_ptr() if hr8 is not None else None
+    _lib.check(_lib.lib().pssr_crappify(ctypes.byref(a), _lib.current_stream_ptr()), "pssr_crappify")
+    return lr, hr, hr8
+
+
+def resize_bilinear(img: torch.Tensor, scale: int) -> torch.Tensor:
+    """Pillow-exact `Image.resize(BILINEAR)` by an integer factor on [n, h, w] uint8/uint16."""
+    img = _cuda(img, "img").contiguous()
+    n, h, w = img.shape
+    eb = img.element_size()
+    out = torch.empty(n, h // scale, w // scale, dtype=img.dtype, device=img.device)
+    _lib.check(_lib.lib().pssr_resize_bilinear(img.data_ptr(), out.data_ptr(), n, h, w, scale, eb, _lib.current_stream_ptr()),
+               "pssr_resize_bilinear")
+    return out
+
+
+def stitch(tiles: torch.Tensor, n_rows, n_cols, overlap, margin) -> torch.Tensor:
+    """`_patch_images` + uint8 cast (pssr/util.py:96-137): tiles [stacks*n_rows*n_cols, T, T] uint8."""
+    tiles = _cuda(tiles, "tiles").contiguous()
+    if tiles.dtype != torch.uint8 or tiles.dim() != 3 or tiles.shape[1] != tiles.shape[2]:
+        raise ValueError("tiles must be uint8 [n, T, T]")
+    per = n_rows * n_cols
+    stacks = tiles.shape[0] // per
+    T = int(tiles.shape[1])
+    step = T - overlap
+    out = torch.empty(stacks, n_rows * step + overlap, n_cols * step + overlap, dtype=torch.uint8, device=tiles.device)
+    rc = _lib.lib().pssr_stitch(tiles.data_ptr(), out.data_ptr(), stacks, n_rows, n_cols, T, overlap, margin, _lib.current_stream_ptr())
+    if rc == -1 and b"margin" in _lib.lib().pssr_last_error():
+        raise ValueError(_lib.lib().pssr_last_error().decode())
+    _lib.check(rc, "pssr_stitch")
+    return out
+
+
+def metric_sums(a: torch.Tensor, b: torch.Tensor, want_ssim=True):
+    """Exact per-image sums for uint8 pairs [n, h, w]: (sum (a-b)^2 int64 [n], SSIM-map sum float64 [n] | None)."""
+    a, b = _cuda(a, "a").contiguous(), _cuda(b, "b").contiguous()
+    if a.dtype != torch.uint8 or b.dtype != torch.uint8 or a.shape != b.shape or a.dim() != 3:
+        raise ValueError("metric_sums expects two uint8 tensors of identical shape [n, h, w]")
+    n, h, w = a.shape
+    sq = torch.empty(n, dtype=torch.int64, device=a.device)
+    ss = torch.empty(n, dtype=torch.float64, device=a.device) if want_ssim else None
+    rc = _lib.lib().pssr_metric_sums(a.data_ptr(), b.data_ptr(), n, h, w, sq.data_ptr(), ss.data_ptr() if ss is not None else None,
+                                     _lib.current_stream_ptr())
+    if rc == -1 and b"win_size" in _lib.lib().pssr_last_error():
+        raise ValueError(_lib.lib().pssr_last_error().decode())
+    _lib.check(rc, "pssr_metric_sums")
+    return sq, ss
+
+
+def normalize_preds_u8(hr: torch.Tensor, hr_hat: torch.Tensor, pmin=0.1, pmax=99.9):
+    """`normalize_preds` (pssr/util.py:139-191) on device for uint8 pairs [n, h, w] of equal shape."""
+    hr, hr_hat = _cuda(hr, "hr").contiguous(), _cuda(hr_hat, "hr_hat").contiguous()
+    if hr.dtype != torch.uint8 or hr_hat.dtype != torch.uint8 or hr.shape != hr_hat.shape or hr.dim() != 3:
+        raise ValueError("normalize_preds_u8 expects two uint8 tensors of identical shape [n, h, w]")
+    n, h, w = hr.shape
+    ws = torch.empty(int(_lib.lib().pssr_normalize_workspace_bytes(n)), dtype=torch.uint8, device=hr.device)
+    oa, ob = torch.empty_like(hr), torch.empty_like(hr_hat)
+    _lib.check(_lib.lib().pssr_normalize_preds(hr.data_ptr(), hr_hat.data_ptr(), oa.data_ptr(), ob.data_ptr(), n, h, w, pmin, pmax,
+                                               ws.data_ptr(), _lib.current_stream_ptr()), "pssr_normalize_preds")
+    return oa, ob

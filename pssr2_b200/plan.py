@@ -1,0 +1,201 @@
+"""Host-side builder for a network plan (family 2 of ``include/pssr_b200.h``).
+
+The modules in ``pssr2_b200/models.py`` describe their forward pass (pssr/models/resunet.py:65-96,
+rdresunet.py:104-130) as a list of fused ops over NHWC 16-bit activation buffers; this module packs
+weights into the K-major layout the tcgen05 kernel reads, fills the C structs and owns the
+``pssr_plan_t`` handle.  torch is used for device memory only.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_NONE, ACT_RELU, DT_BF16, DT_FP16, OP_CONV, OP_MAXPOOL, OP_PREP, OP_TAIL, ConvDesc, KSeg, Op,
+                   PoolDesc, PrepDesc, Src, TailDesc)
+
+TORCH_DT = {DT_BF16: torch.bfloat16, DT_FP16: torch.float16}
+DT_NAMES = {"bf16": DT_BF16, "fp16": DT_FP16}
+
+
+DRY_RUN = False
+
+
+def ceil_div(a, b):
+    return -(-a // b)
+
+
+class View:
+    """A channel slice [choff, choff+channels) of an NHWC 16-bit buffer [B, H, W, cstride]."""
+
+    def __init__(self, buf: torch.Tensor, choff: int = 0, channels: int = None):
+        assert buf.dim() == 4 and buf.is_contiguous()
+        self.buf = buf
+        self.choff = choff
+        self.channels = buf.shape[3] - choff if channels is None else channels
+        assert self.choff % 8 == 0 and self.choff + self.channels <= buf.shape[3]
+
+    @property
+    def B(self):
+        return self.buf.shape[0]
+
+    @property
+    def H(self):
+        return self.buf.shape[1]
+
+    @property
+    def W(self):
+        return self.buf.shape[2]
+
+    @property
+    def cstride(self):
+        return self.buf.shape[3]
+
+    def ptr(self):
+        return self.buf.data_ptr() + self.choff * self.buf.element_size()
+
+
+def pack_weight(parts, dtype, shuffle=1, n_pad=None):
+    """parts: list of fp32 tensors [Cout, Cin, kh, kw] in K-schedule order (one per K segment).
+    Returns ([n_pad, Ktot] 16-bit, K-major, K ordered tap-major then 64-padded channel) where the N
+    rows are permuted so that F.pixel_shuffle(., shuffle) becomes a contiguous store:
+    new n = (i*r + j)*C' + c'  <-  old c = c'*r*r + i*r + j   (torch pixel_shuffle channel order)."""
+    cols = []
+    cout = parts[0].shape[0]
+    for w in parts:
+        co, ci, kh, kw = w.shape
+        assert co == cout
+        cb = ceil_div(ci, 64)
+        wp = torch.zeros(co, kh * kw, cb * 64, dtype=torch.float32, device=w.device)
+        wp[:, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, kh * kw, ci)
+        cols.append(wp.reshape(co, -1))
+    W = torch.cat(cols, 1)
+    W = permute_n(W, shuffle)
+    n_pad = cout if n_pad is None else n_pad
+    if n_pad > cout:
+        W = torch.cat([W, torch.zeros(n_pad - cout, W.shape[1], device=W.device)], 0)
+    return W.to(TORCH_DT[dtype]).contiguous()
+
+
+def permute_n(t, shuffle):
+    """Reorders dim 0 (output channels) for the pixel-shuffle epilogue."""
+    if shuffle == 1:
+        return t
+    r2 = shuffle * shuffle
+    c = t.shape[0]
+    assert c % r2 == 0
+    rest = t.shape[1:]
+    return t.reshape(c // r2, r2, *rest).transpose(0, 1).reshape(c, *rest)
+
+
+class Plan:
+    def __init__(self, dtype="bf16"):
+        self.dtype = DT_NAMES[dtype] if isinstance(dtype, str) else dtype
+        self.tdtype = TORCH_DT[self.dtype]
+        self.ops = []
+        self.keep = []      # tensors that must outlive the plan
+        self.handle = None
+        self.flops = 0      # algorithmic conv FLOPs (2*MAC, unpadded)
+        self.records = []   # python-level mirror of the op list (used by the CPU plan interpreter in tests/)
+
+    # ---- op builders -----------------------------------------------------------------
+    def conv(self, srcs, segs, weight, bias, out: View, *, Ho, Wo, B, n=None, n_valid=None, shuffle=1, act=ACT_NONE,
+             out_scale=None, out_f32=None):
+        """srcs: list[View]; segs: list[(src_index, taps, cblocks)]; weight [n, Ktot] 16-bit; bias [n] fp32."""
+        d = ConvDesc()
+        d.n_srcs = len(srcs)
+        for i, s in enumerate(srcs):
+            d.srcs[i] = Src(s.ptr(), s.channels, s.cstride, s.H, s.W, s.B, 0)
+        d.n_segs = len(segs)
+        ktot = 0
+        for i, (si, taps, cb) in enumerate(segs):
+            d.segs[i] = KSeg(si, taps, cb, 0)
+            ktot += taps * cb * 64
+        n = weight.shape[0] if n is None else n
+        assert weight.shape == (n, ktot) and weight.dtype == self.tdtype and weight.is_contiguous()
+        assert bias.shape == (n,) and bias.dtype == torch.float32
+        d.weights = weight.data_ptr()
+        d.bias = bias.data_ptr()
+        d.n = n
+        d.n_valid = n if n_valid is None else n_valid
+        d.Ho, d.Wo, d.B = Ho, Wo, B
+        d.out = out.buf.data_ptr() if out is not None else None
+        d.out_cstride = out.cstride if out is not None else out_f32.shape[3]
+        d.out_choff = out.choff if out is not None else 0
+        d.shuffle = shuffle
+        d.act = act
+        d.out_scale = out_scale.data_ptr() if out_scale is not None else None
+        d.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
+        op = Op()
+        op.kind = OP_CONV
+        op.u.conv = d
+        self.ops.append(op)
+        self.keep += [weight, bias, out_scale, out_f32] + [s.buf for s in srcs] + ([out.buf] if out is not None else [])
+        self.records.append(("conv", dict(srcs=list(srcs), segs=list(segs), weight=weight, bias=bias, out=out, Ho=Ho, Wo=Wo, B=B,
+                                          n=n, n_valid=d.n_valid, shuffle=shuffle, act=act, out_scale=out_scale, out_f32=out_f32)))
+
+    def prep(self, x, scale, shift, im2col, xnorm=None):
+        B, C, H, W = x.shape
+        d = PrepDesc(x.data_ptr(), 1 if x.dtype == torch.uint8 else 0, B, C, H, W, scale.data_ptr(), shift.data_ptr(),
+                     im2col.data_ptr(), xnorm.data_ptr() if xnorm is not None else None)
+        op = Op()
+        op.kind = OP_PREP
+        op.u.prep = d
+        self.ops.append(op)
+        self.keep += [x, scale, shift, im2col, xnorm]
+        self.records.append(("prep", dict(x=x, scale=scale, shift=shift, im2col=im2col, xnorm=xnorm)))
+
+    def maxpool(self, src: View, dst: View):
+        d = PoolDesc(src.buf.data_ptr(), src.cstride, src.choff, dst.buf.data_ptr(), dst.cstride, dst.choff, src.B, src.H,
+                     src.W, src.channels)
+        op = Op()
+        op.kind = OP_MAXPOOL
+        op.u.pool = d
+        self.ops.append(op)
+        self.keep += [src.buf, dst.buf]
+        self.records.append(("maxpool", dict(src=src, dst=dst)))
+
+    def tail(self, src: View, weight, bias, mul, add, out_f32=None, out_u8=None):
+        cout = weight.shape[0]
+        d = TailDesc(src.ptr(), src.cstride, src.channels, src.B, src.H, src.W, weight.data_ptr(), bias.data_ptr(), cout,
+                     mul, add, out_f32.data_ptr() if out_f32 is not None else None,
+                     out_u8.data_ptr() if out_u8 is not None else None)
+        op = Op()
+        op.kind = OP_TAIL
+        op.u.tail = d
+        self.ops.append(op)
+        self.keep += [src.buf, weight, bias, out_f32, out_u8]
+        self.records.append(("tail", dict(src=src, weight=weight, bias=bias, mul=mul, add=add, out_f32=out_f32, out_u8=out_u8)))
+
+    # ---- lifecycle ---------------------------------------------------------------------
+    def finalize(self):
+        if DRY_RUN:   # tests/: build the op list on CPU tensors without creating the native plan
+            return self
+        arr = (Op * len(self.ops))(*self.ops)
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib().pssr_plan_create(arr, len(self.ops), self.dtype, ctypes.byref(h)), "pssr_plan_create")
+        self.handle = h
+        return self
+
+    def run(self, first=None, count=None):
+        if self.handle is None:
+            raise RuntimeError("plan not finalized")
+        st = _lib.current_stream_ptr()
+        if first is None:
+            _lib.check(_lib.lib().pssr_plan_run(self.handle, st), "pssr_plan_run")
+        else:
+            _lib.check(_lib.lib().pssr_plan_run_range(self.handle, first, count, st), "pssr_plan_run_range")
+
+    def __len__(self):
+        return len(self.ops)
+
+    def close(self):
+        if self.handle is not None:
+            _lib.lib().pssr_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

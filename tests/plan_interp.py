@@ -1,0 +1,76 @@
+"""CPU interpreter for the python-level records of a ``pssr2_b200.plan.Plan`` (test infrastructure).
+
+It executes the op list with plain PyTorch fp32 ops, reading the SAME packed weights and writing the
+SAME activation buffers the CUDA kernels would, so that weight packing, BatchNorm folding, K-segment
+scheduling, concat offsets and the pixel-shuffle permutation are checked on a CPU-only box."""
+import torch
+import torch.nn.functional as F
+
+
+def _view_nchw(v, pad_to=None):
+    t = v.buf[..., v.choff:v.choff + v.channels].float().permute(0, 3, 1, 2)
+    if pad_to is not None and pad_to > v.channels:
+        t = F.pad(t, (0, 0, 0, 0, 0, pad_to - v.channels))
+    return t
+
+
+def run_records(plan):
+    for kind, r in plan.records:
+        if kind == "prep":
+            x = r["x"].float()
+            B, C, H, W = x.shape
+            xn = (x / 128 - 1) * r["scale"].view(1, -1, 1, 1) + r["shift"].view(1, -1, 1, 1)
+            cols = F.unfold(xn, 3, padding=1).view(B, C * 9, H, W)
+            r["im2col"].zero_()
+            r["im2col"][..., :C * 9] = cols.permute(0, 2, 3, 1).to(r["im2col"].dtype)
+        elif kind == "maxpool":
+            s, d = r["src"], r["dst"]
+            d.buf[..., d.choff:d.choff + s.channels] = F.max_pool2d(_view_nchw(s), 2).permute(0, 2, 3, 1).to(d.buf.dtype)
+        elif kind == "tail":
+            s = r["src"]
+            w = r["weight"].permute(0, 3, 1, 2)  # [Cout][3][3][C] -> [Cout][C][3][3]
+            y = (F.conv2d(_view_nchw(s), w, r["bias"], padding=1)) * r["mul"] + r["add"]
+            if r["out_f32"] is not None:
+                r["out_f32"].copy_(y)
+            if r["out_u8"] is not None:
+                c = y.shape[1] // 2
+                r["out_u8"].copy_(y[:, c:c + 1].clamp(0, 255).to(torch.uint8))
+        elif kind == "conv":
+            W = r["weight"].float()
+            n = W.shape[0]
+            acc = None
+            k0 = 0
+            for (si, taps, cb) in r["segs"]:
+                v = r["srcs"][si]
+                kw = taps * cb * 64
+                wseg = W[:, k0:k0 + kw].reshape(n, taps, cb * 64)
+                k0 += kw
+                x = _view_nchw(v, cb * 64)
+                if taps == 9:
+                    y = F.conv2d(x, wseg.permute(0, 2, 1).reshape(n, cb * 64, 3, 3), padding=1)
+                elif taps == 1:
+                    y = F.conv2d(x, wseg.permute(0, 2, 1).reshape(n, cb * 64, 1, 1))
+                else:
+                    y = F.conv2d(x, wseg.permute(0, 2, 1).reshape(n, cb * 64, 2, 2), stride=2)
+                acc = y if acc is None else acc + y
+            assert k0 == W.shape[1]
+            acc = acc + r["bias"].view(1, -1, 1, 1)
+            if r["act"] == 1:
+                acc = F.relu(acc)
+            elif r["act"] == 2:
+                acc = F.gelu(acc)
+            if r["out_scale"] is not None:
+                acc = acc * r["out_scale"].view(1, -1, 1, 1)
+            acc = acc[:, :r["n_valid"]]
+            rr = r["shuffle"]
+            if rr > 1:  # stored order n = (i*r+j)*cps + cc
+                B, N, H, Wd = acc.shape
+                cps = N // (rr * rr)
+                acc = acc.view(B, rr, rr, cps, H, Wd).permute(0, 3, 4, 1, 5, 2).reshape(B, cps, H * rr, Wd * rr)
+            o = r["out"]
+            if o is not None:
+                o.buf[..., o.choff:o.choff + acc.shape[1]] = acc.permute(0, 2, 3, 1).to(o.buf.dtype)
+            if r["out_f32"] is not None:
+                r["out_f32"][..., :acc.shape[1]] = acc.permute(0, 2, 3, 1)
+        else:
+            raise ValueError(kind)
