@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- HR megapixels/s of the PSSR2 test/predict hot path on B200 (BASELINE.json metric).
+
+Workload (N=1): BASELINE.json configs[1] -- ResUNet scale=4, batch 64 of 128->512 tiles, synthetic
+16-bit EM-like images, random-init weights.  One step = one pass of the hot path over one batch:
+fused crappify (HR uint16 tiles -> LR, Poisson + AdditiveGaussian, on-device Philox) -> ResUNet forward
+(tcgen05 implicit-GEMM plan, fused `_pred_array`) -> PSNR/SSIM/MSE sums against the HR tiles.
+With N > 1 (torchrun, one rank per GPU) every rank processes its own batch (tile-wise sharding, weak
+scaling) and the metric sums are all-reduced over NCCL each step.
+
+  value : whole-job HR MP/s with the HR tiles already resident in HBM
+  e2e   : the same through the public API (ImageDataset + predict_images) from pinned HOST buffers,
+          H2D of the tiles and D2H of the uint8 predictions inside the timed region
+  roofline / cpu_baseline : see DESIGN.md "Measurement"
+  --impl reference : the oracle port of the reference's CPU path on the host cores (same metric/config).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TILE, SCALE, BATCH = 512, 4, 64
+ALG_FLOPS_PER_TILE = 63.305e9          # ResUNet scale 4 conv FLOPs per 128^2 -> 512^2 tile
+TAIL_FLOPS_PER_TILE = 0.302e9          # Reconstruction.conv runs on CUDA cores, excluded from the tensor roofline
+METRIC, UNIT = "HR megapixels/sec (ResUNet 4x)", "HR MP/s"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops"]), float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 1590.0, 6650.0, "fallback"
+
+
+def _synthetic_tiles(n, seed, device):
+    """Microscopy-like uint16 tiles in a 0..255 range: smooth structure + shot noise."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator(device=device).manual_seed(seed)
+    base = torch.rand(n, 1, 24, 24, generator=g, device=device)
+    base = F.interpolate(base, size=(TILE, TILE), mode="bicubic", align_corners=False).clamp(0, 1) * 160 + 20
+    img = torch.poisson(base, generator=g).clamp(0, 255)
+    return img[:, 0].to(torch.int16).contiguous()   # uint16 container (values < 32768)
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 8 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) >= 8 and r[2].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------- reference / CPU arm
+def _cpu_reference_steps(steps, warmup, tiles_per_step):
+    """The oracle port of the reference's CPU predict path (pssr/predict.py:144-211 through
+    pssr/data.py:471-495 and pssr/models/resunet.py:65-96) on the host cores: crappify -> fp32 forward ->
+    `_pred_array` -> PSNR/SSIM.  Returns (HR MP/s, seconds per step, threads)."""
+    import numpy as np
+    import torch
+    from oracle import pipeline as OP
+    from oracle.models import resunet_forward
+    from pssr2_b200.models import ResUNet
+    torch.manual_seed(0)
+    sd = {k: v.clone() for k, v in ResUNet().eval().state_dict().items()}
+    rng = np.random.default_rng(1234)
+    hr_tiles = rng.poisson(100, (tiles_per_step, 1, TILE, TILE)).clip(0, 255).astype(np.uint16)
+
+    def one_step():
+        np.random.seed(0)
+        for t in hr_tiles:
+            lr0 = OP.resize_bilinear(t, TILE // SCALE, TILE // SCALE).astype(np.float32)
+            stages = [("poisson", np.random.poisson(np.clip(lr0, 0, np.inf)), 1, 0), ("gaussian", np.random.normal(0, 13, lr0.shape))]
+            hr, lr = OP.gen_pair(t, TILE, SCALE, stages)
+            with torch.no_grad():
+                out = resunet_forward(sd, torch.as_tensor(lr)[None])
+            a, b = OP.pred_array(hr[None]), OP.pred_array(out.numpy())
+            OP.image_metrics(a[0], b[0])
+
+    for _ in range(warmup):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = (time.perf_counter() - t0) / steps
+    return tiles_per_step * TILE * TILE / dt / 1e6, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    tiles = 2
+    warm = min(args.warmup, 1)
+    mp, dt, threads = _cpu_reference_steps(args.steps, warm, tiles)
+    sample = f"{tiles} tiles/step x {args.steps} steps of the same workload on the host CPU (oracle port, torch fp32 + NumPy/Pillow-exact)"
+    line = {"metric": METRIC, "value": round(mp, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
+            "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": "ResUNet scale=4, 128->512 tiles, crappify+forward+metrics (BASELINE configs[1] sampled)",
+                       "tiles_per_step": tiles},
+            "cpu_baseline": {"value": round(mp, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": round(mp, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# -------------------------------------------------------------------------------- own arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pssr2_b200 import _lib, ops
+    from pssr2_b200 import dist as D
+    from pssr2_b200.crappifiers import AdditiveGaussian, MultiCrappifier, Poisson
+    from pssr2_b200.data import ImageDataset
+    from pssr2_b200.models import ResUNet
+    from pssr2_b200.predict import predict_images
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        D.init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.lib()   # fails loudly if the CUDA extension is missing
+
+    torch.manual_seed(0)
+    model = ResUNet().eval()
+    model.precision = args.precision
+    model = model.to(dev)
+    crap = MultiCrappifier(Poisson(), AdditiveGaussian())
+    NB = 8   # resident input batches rotated between steps: 8 x 33.5 MB > 126 MB L2
+    batches = [_synthetic_tiles(BATCH, 1234 + rank * 100 + i, dev) for i in range(NB)]
+    tables = [ops.TileTable([b], [0] * BATCH, list(range(BATCH)), [0] * BATCH, [0] * BATCH, [TILE] * BATCH, [TILE] * BATCH) for b in batches]
+    sums = torch.zeros(4, dtype=torch.float64, device=dev)
+
+    def step(i):
+        specs = crap.noise_specs()
+        lr, _, hr8 = ops.crappify(tables[i % NB], TILE, SCALE, specs, clip_between=True, seed=i, tile_index0=(rank * 1000003 + i) * BATCH,
+                                  want_hr_u8=True)
+        _, out8 = model.forward_u8(lr)
+        sq, ss = ops.metric_sums(hr8[:, 0], out8[:, 0])
+        part = torch.stack([sq.double().sum(), ss.sum(), torch.tensor(float(BATCH), dtype=torch.float64, device=dev),
+                            torch.zeros((), dtype=torch.float64, device=dev)])
+        if world > 1:
+            dist.all_reduce(part)       # the path's only collective: metric sums
+        sums.add_(part)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(100 + i)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    launches = _lib.launch_count() - launches0
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = float(ms) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * BATCH * TILE * TILE / (ms_step * 1e-3) / 1e6
+
+    # ---- e2e through the public API from pinned host buffers ---------------------------------
+    host = [b.cpu().pin_memory() for b in batches[:2]]
+
+    def e2e_step(i):
+        ds = ImageDataset([host[i % 2]], hr_res=TILE, lr_scale=SCALE, crappifier=crap, n_frames=1, val_split=1, device=dev)
+        preds = predict_images(model, ds, device=str(dev), batch_size=BATCH, out_dir=None)
+        return preds
+
+    import contextlib
+    import io
+    with contextlib.redirect_stderr(io.StringIO()), contextlib.redirect_stdout(io.StringIO()):
+        for i in range(2):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(2, min(args.steps, 10))
+        for i in range(e2e_steps):
+            preds = e2e_step(i)
+        torch.cuda.synchronize()
+        e2e_dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+    e2e_value = world * BATCH * TILE * TILE / float(e2e_dt) / 1e6
+    h2d = BATCH * TILE * TILE * 2
+    d2h = BATCH * TILE * TILE
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return
+
+    # ---- roofline of the dominant kernel (the tcgen05 implicit-GEMM conv), measured live -----------
+    st = next(iter(model._plans.values()))
+    plan = st["plan"]
+    conv_ms, other_ms = 0.0, 0.0
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_conv = 0
+    for i, (kind, _) in enumerate(plan.records):
+        plan.run(i, 1)
+        torch.cuda.synchronize()
+        a0.record()
+        for _ in range(3):
+            plan.run(i, 1)
+        a1.record()
+        torch.cuda.synchronize()
+        t = a0.elapsed_time(a1) / 3
+        if kind == "conv":
+            conv_ms += t
+            n_conv += 1
+        else:
+            other_ms += t
+    peak_tf, peak_hbm, peak_src = _peaks()
+    conv_flops = (ALG_FLOPS_PER_TILE - TAIL_FLOPS_PER_TILE) * BATCH
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05)", "achieved": round(achieved, 1), "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4), "traffic": None, "peak_source": peak_src,
+                "launches_per_step": n_conv, "kernel_ms_per_step": round(conv_ms, 3), "other_net_ms_per_step": round(other_ms, 3),
+                "step_frac_of_peak": round(ALG_FLOPS_PER_TILE * BATCH / (ms_step * 1e-3) / 1e12 / peak_tf, 4)}
+
+    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ------------------------
+    cpu_mp, cpu_dt, threads = _cpu_reference_steps(2, 1, 2)
+    cpu = {"value": round(cpu_mp, 4), "unit": UNIT, "cores": threads, "kind": "port",
+           "sample": "2 steps x 2 tiles of the same workload (oracle port: Pillow-exact resize + NumPy noise + torch fp32 forward + SSIM)"}
+
+    line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": f"{args.precision} operands / f32 accumulate", "data": "synthetic",
+            "config": {"workload": "ResUNet scale=4, batch 64 of 128->512 tiles per GPU, synthetic 16-bit EM tiles: crappify "
+                                   "(Poisson+AdditiveGaussian) + forward + PSNR/SSIM/MSE sums (BASELINE configs[1])",
+                       "global_batch": BATCH * world, "tile": f"{TILE // SCALE}->{TILE}", "parallelism": f"tile-sharded x{world}",
+                       "l2": f"inputs rotate over {NB} resident batches ({NB * h2d / 1e6:.0f} MB) and each step streams >4 GB of "
+                             "activations, both > 126 MB L2"},
+            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "ImageDataset(pinned host stack) + predict_images(out_dir=None)"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "metric_check": {"mean_psnr_db": None}}
+    s = sums.cpu()
+    mse = float(s[0]) / max(float(s[2]), 1) / (TILE * TILE)
+    import math
+    line["metric_check"] = {"mean_mse_255": round(mse, 3), "psnr_of_mean_mse_db": round(10 * math.log10(255.0 ** 2 / mse), 3) if mse > 0 else None,
+                            "mean_ssim": round(float(s[1]) / max(float(s[2]), 1) / ((TILE - 6) ** 2), 5)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

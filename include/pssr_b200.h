@@ -113,6 +113,12 @@ typedef struct {
 } pssr_crappify_args_t;
 
 int pssr_crappify(const pssr_crappify_args_t* args, void* stream);
+/* The operator interface `Crappifier.crappify(image)` (pssr/crappifiers.py:13-24): the noise chain
+ * alone on an arbitrary float32 / float64 array of n elements -- no downscale, no final round/clip.
+ * Output is float64 (exactly representable when the reference would return float32). */
+int pssr_noise_chain(const void* in, int32_t in_is_f64, double* out, int64_t n,
+                     const pssr_noise_stage_t* stages, int32_t n_stages, int32_t clip_between,
+                     uint64_t seed, void* stream);
 /* The resample stage alone (Pillow parity tests): src [n][h][w] -> dst [n][h/scale][w/scale],
  * same dtype (uint8 / uint16) as Pillow returns before `.astype(np.float32)`. */
 int pssr_resize_bilinear(const void* src, void* dst, int32_t n, int32_t h, int32_t w,

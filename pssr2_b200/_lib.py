@@ -60,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 # ------------------------------------------------------------------------------ structs
 class NoiseStage(Structure):
     _fields_ = [("kind", c_int32), ("rng", c_int32), ("intensity", c_double), ("gain", c_double),
-                ("injected", c_void_p)]
+                ("mix_in_f32", c_int32), ("reserved", c_int32), ("injected", c_void_p)]
 
 
 class CrappifyArgs(Structure):
@@ -71,7 +71,8 @@ class CrappifyArgs(Structure):
                 ("n_tiles", c_int32), ("frames", c_int32), ("hr_res", c_int32), ("lr_scale", c_int32),
                 ("stages", NoiseStage * 4), ("n_stages", c_int32), ("clip_between", c_int32),
                 ("seed", c_uint64), ("tile_index0", c_uint64),
-                ("lr_out", c_void_p), ("hr_out", c_void_p)]
+                ("lr_out", c_void_p), ("hr_out", c_void_p), ("hr_u8_out", c_void_p),
+                ("hr_frame0", c_int32), ("hr_frames", c_int32), ("lr_frame0", c_int32), ("lr_frames", c_int32)]
 
 
 class Src(Structure):
@@ -130,6 +131,7 @@ SYMBOLS = {
     "pssr_version": (c_char_p, []),
     "pssr_launch_count": (c_int64, []),
     "pssr_crappify": (c_int32, [POINTER(CrappifyArgs), c_void_p]),
+    "pssr_noise_chain": (c_int32, [c_void_p, c_int32, c_void_p, c_int64, POINTER(NoiseStage), c_int32, c_int32, c_uint64, c_void_p]),
     "pssr_resize_bilinear": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "pssr_plan_create": (c_int32, [POINTER(Op), c_int32, c_int32, POINTER(c_void_p)]),
     "pssr_plan_run": (c_int32, [c_void_p, c_void_p]),

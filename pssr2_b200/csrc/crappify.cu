@@ -167,6 +167,58 @@ struct StageK {
   const void* injected;
 };
 
+// The crappifier chain on one value (MultiCrappifier.crappify, pssr/crappifiers.py:38-43).  `val`
+// carries either a float32 or a float64 quantity exactly; casts reproduce NumPy's dtype flow.
+__device__ __forceinline__ double noise_chain(double val, const StageK* stages, int n_stages, int clip_between,
+                                              const Philox& ph, uint32_t pix, size_t inj) {
+  for (int s = 0; s < n_stages; ++s) {
+    const StageK& st = stages[s];
+    if (st.kind == PSSR_NOISE_POISSON) {
+      // x.astype(f32) * (1 - i) + y * i + gain          (crappifiers.py:82-86)
+      const float xf = (float)val;
+      double y;
+      if (st.rng == PSSR_RNG_INJECTED) y = (double)reinterpret_cast<const long long*>(st.injected)[inj];
+      else y = poisson_sample(ph, pix, (uint32_t)s, fmax(val, 0.0));
+      double t;
+      if (st.mix_in_f32) t = (double)__fmul_rn(xf, (float)(1.0 - st.intensity));
+      else t = __dmul_rn((double)xf, 1.0 - st.intensity);
+      val = __dadd_rn(__dadd_rn(t, __dmul_rn(y, st.intensity)), st.gain);
+    } else if (st.kind == PSSR_NOISE_GAUSSIAN) {
+      // x.astype(f32) + normal(gain, intensity)           (crappifiers.py:62-64)
+      const float xf = (float)val;
+      double g;
+      if (st.rng == PSSR_RNG_INJECTED) g = reinterpret_cast<const double*>(st.injected)[inj];
+      else {
+        const uint4 r = ph(pix, (uint32_t)s, 0u, 0x47415553u);
+        const float rad = sqrtf(-2.0f * logf(u01f(r.x)));
+        const float z = rad * cospif(2.0f * u01f(r.y));
+        g = __dadd_rn(st.gain, __dmul_rn(st.intensity, (double)z));
+      }
+      val = __dadd_rn((double)xf, g);
+    } else {
+      // random_noise(clip(x.astype(f32) + gain, 0, 255) / 255, "s&p", amount) * 255   (crappifiers.py:103-105)
+      float v = __fadd_rn((float)val, (float)st.gain);
+      v = fminf(fmaxf(v, 0.f), 255.f);
+      v = __fdiv_rn(v, 255.f);
+      bool flipped, salted;
+      if (st.rng == PSSR_RNG_INJECTED) {
+        const uint8_t m = reinterpret_cast<const uint8_t*>(st.injected)[inj];
+        flipped = m & 1;
+        salted = m & 2;
+      } else {
+        const uint4 r = ph(pix, (uint32_t)s, 0u, 0x53414C54u);
+        flipped = u01d(r.x, r.y) <= st.intensity;
+        salted = u01d(r.z, r.w) <= 0.5;
+      }
+      if (flipped) v = salted ? 1.f : 0.f;
+      v = fminf(fmaxf(v, 0.f), 1.f);
+      val = (double)__fmul_rn(v, 255.f);
+    }
+    if (clip_between) val = fmin(fmax(val, 0.0), 255.0);  // MultiCrappifier clip (crappifiers.py:41-42)
+  }
+  return val;
+}
+
 struct CrapK {
   const void* const* sheets;
   int elem_bytes, sheet_h, sheet_w;
@@ -292,51 +344,7 @@ __global__ void __launch_bounds__(kCrapThreads) crappify_kernel(const CrapK p) {
     const int yy = yy0 + yo, xx = xx0 + xo;
     const uint32_t pix = (uint32_t)((f * p.lr_res + yy) * p.lr_res + xx);
     const size_t inj = (((size_t)tile * p.frames + f) * p.lr_res + yy) * p.lr_res + xx;
-    for (int s = 0; s < p.n_stages; ++s) {
-      const StageK& st = p.stages[s];
-      if (st.kind == PSSR_NOISE_POISSON) {
-        // x.astype(f32) * (1 - i) + y * i + gain          (crappifiers.py:82-86)
-        const float xf = (float)val;
-        double y;
-        if (st.rng == PSSR_RNG_INJECTED) y = (double)reinterpret_cast<const long long*>(st.injected)[inj];
-        else y = poisson_sample(ph, pix, (uint32_t)s, fmax(val, 0.0));
-        double t;
-        if (st.mix_in_f32) t = (double)__fmul_rn(xf, (float)(1.0 - st.intensity));
-        else t = __dmul_rn((double)xf, 1.0 - st.intensity);
-        val = __dadd_rn(__dadd_rn(t, __dmul_rn(y, st.intensity)), st.gain);
-      } else if (st.kind == PSSR_NOISE_GAUSSIAN) {
-        // x.astype(f32) + normal(gain, intensity)           (crappifiers.py:62-64)
-        const float xf = (float)val;
-        double g;
-        if (st.rng == PSSR_RNG_INJECTED) g = reinterpret_cast<const double*>(st.injected)[inj];
-        else {
-          const uint4 r = ph(pix, (uint32_t)s, 0u, 0x47415553u);
-          const float rad = sqrtf(-2.0f * logf(u01f(r.x)));
-          const float z = rad * cospif(2.0f * u01f(r.y));
-          g = __dadd_rn(st.gain, __dmul_rn(st.intensity, (double)z));
-        }
-        val = __dadd_rn((double)xf, g);
-      } else {
-        // random_noise(clip(x.astype(f32) + gain, 0, 255) / 255, "s&p", amount) * 255   (crappifiers.py:103-105)
-        float v = __fadd_rn((float)val, (float)st.gain);
-        v = fminf(fmaxf(v, 0.f), 255.f);
-        v = __fdiv_rn(v, 255.f);
-        bool flipped, salted;
-        if (st.rng == PSSR_RNG_INJECTED) {
-          const uint8_t m = reinterpret_cast<const uint8_t*>(st.injected)[inj];
-          flipped = m & 1;
-          salted = m & 2;
-        } else {
-          const uint4 r = ph(pix, (uint32_t)s, 0u, 0x53414C54u);
-          flipped = u01d(r.x, r.y) <= st.intensity;
-          salted = u01d(r.z, r.w) <= 0.5;
-        }
-        if (flipped) v = salted ? 1.f : 0.f;
-        v = fminf(fmaxf(v, 0.f), 1.f);
-        val = (double)__fmul_rn(v, 255.f);
-      }
-      if (p.clip_between) val = fmin(fmax(val, 0.0), 255.0);  // MultiCrappifier clip (crappifiers.py:41-42)
-    }
+    val = noise_chain(val, p.stages, p.n_stages, p.clip_between, ph, pix, inj);
     if (p.n_stages > 0) val = fmin(fmax(rint(val), 0.0), 255.0);  // np.clip(lr.round(), 0, 255), data.py:487
     p.lr_out[(((size_t)tile * p.lr_frames + fo) * p.lr_res + yy) * p.lr_res + xx] = (float)val;
   }
@@ -361,6 +369,23 @@ __global__ void hr_gather_kernel(const void* const* sheets, const int32_t* tile_
     const T v = load_reflect<T>(fbase, sheet_w, ty, tx, r, c, vh, vw);
     if (hr_out) hr_out[((size_t)tile * hr_frames + fo) * n + i] = (float)v;
     if (hr_u8 && fo == centre) hr_u8[(size_t)tile * n + i] = (uint8_t)min((int)v, 255);
+  }
+}
+
+// Crappifier.crappify(image) on an arbitrary float array (the reference operator interface,
+// pssr/crappifiers.py:13-24): noise only, no downscale, no final round/clip.
+struct NoiseK {
+  StageK stages[4];
+  int n_stages, clip_between;
+  uint32_t seed_lo, seed_hi;
+};
+__global__ void noise_chain_kernel(const void* in, int in_f64, double* out, size_t n, NoiseK p) {
+  const Philox ph{p.seed_lo, p.seed_hi};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double v = in_f64 ? reinterpret_cast<const double*>(in)[i] : (double)reinterpret_cast<const float*>(in)[i];
+    // Philox counter: low 32 bits in `pix`, high bits folded into the key so >4G-element arrays stay distinct
+    const Philox phi{ph.k0 ^ (uint32_t)(i >> 32), ph.k1};
+    out[i] = noise_chain(v, p.stages, p.n_stages, p.clip_between, phi, (uint32_t)i, i);
   }
 }
 
@@ -498,6 +523,30 @@ extern "C" int pssr_crappify(const pssr_crappify_args_t* a, void* stream) {
     count_launch();
     PSSR_CHECK_CUDA(cudaGetLastError());
   }
+  return PSSR_OK;
+}
+
+extern "C" int pssr_noise_chain(const void* in, int32_t in_is_f64, double* out, int64_t n, const pssr_noise_stage_t* stages,
+                                int32_t n_stages, int32_t clip_between, uint64_t seed, void* stream) {
+  PSSR_REQUIRE(in && out && n >= 0 && stages && n_stages >= 1 && n_stages <= 4, PSSR_EINVAL, "noise_chain: bad arguments");
+  if (n == 0) return PSSR_OK;
+  NoiseK p;
+  memset(&p, 0, sizeof(p));
+  for (int s = 0; s < n_stages; ++s) {
+    const pssr_noise_stage_t& ns = stages[s];
+    PSSR_REQUIRE(ns.kind >= PSSR_NOISE_POISSON && ns.kind <= PSSR_NOISE_SALTPEPPER, PSSR_EINVAL, "noise_chain: bad noise kind %d", ns.kind);
+    PSSR_REQUIRE(ns.rng == PSSR_RNG_PHILOX || ns.injected != nullptr, PSSR_EINVAL, "noise_chain: injected buffer missing for stage %d", s);
+    p.stages[s].kind = ns.kind; p.stages[s].rng = ns.rng; p.stages[s].mix_in_f32 = ns.mix_in_f32;
+    p.stages[s].intensity = ns.intensity; p.stages[s].gain = ns.gain; p.stages[s].injected = ns.injected;
+  }
+  p.n_stages = n_stages; p.clip_between = clip_between;
+  p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)device_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  noise_chain_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, in_is_f64, out, (size_t)n, p);
+  count_launch();
+  PSSR_CHECK_CUDA(cudaGetLastError());
   return PSSR_OK;
 }
 

@@ -35,7 +35,7 @@ __global__ void prep_im2col_kernel(pssr_prep_desc_t d, int fp16) {
           const size_t idx = plane + (size_t)yy * d.W + xx;
           const float raw = d.x_u8 ? (float)reinterpret_cast<const uint8_t*>(d.x)[idx]
                                    : reinterpret_cast<const float*>(d.x)[idx];
-          v = (raw / 128.f - 1.f) * s + t;
+          v = __fadd_rn(__fmul_rn(__fsub_rn(__fdiv_rn(raw, 128.f), 1.f), s), t);  // no FMA contraction: same bits as the unfused ops
           if (tap == 4 && d.xnorm_f32 != nullptr) d.xnorm_f32[idx] = v;
         }
         r16[c * 9 + tap] = pack1(v, fp16);

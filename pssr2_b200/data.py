@@ -1,0 +1,336 @@
+"""Device-resident mirrors of the reference datasets' predict path (pssr/data.py).
+
+``SlidingDataset`` (pssr/data.py:132-266) and ``ImageDataset`` (:12-130) keep the reference's
+constructor arguments, index math (``_get_image_idx`` :697-706, ``_get_val_idx`` :708-730,
+``_n_tiles`` :682-687, ``_sliding_window`` :629-638, ``_slice_image`` :649-660) and the attributes
+``predict_images`` / ``test_metrics`` read (``val_idx``, ``is_lr``, ``crop_res``, ``lr_scale``,
+``hr_res``, ``n_frames``, ``_get_name``).  What changes is where the work happens: sheets are
+uploaded to HBM once, and ``batch(indices)`` produces a whole batch of (HR, LR) tiles with ONE fused
+CUDA launch (tile gather, crop/reflect-pad, Pillow-exact downscale, noise, round/clip) instead of
+per-item NumPy / Pillow work on the host.
+
+Sources: besides a directory path (TIFF / PNG read with Pillow), ``path`` may be a dict
+``{name: ndarray}`` or a list of ndarrays ``[frames, H, W]`` / ``[H, W]`` (uint8 or uint16) -- the
+benchmark inputs are synthetic in-memory arrays.  File readers for .czi, ``extra_path``, ``transforms``
+and training-time rotation are outside the accelerated hot path.
+"""
+import glob
+import os
+import warnings
+from pathlib import Path
+
+import numpy as np
+import torch
+from torch.utils.data import Dataset
+
+from . import ops
+from .crappifiers import Crappifier, Poisson, _fresh_seed
+
+
+def _force_list(item):
+    if type(item) is not list:
+        try:
+            return list(item)
+        except Exception:
+            return [item]
+    return item
+
+
+def _get_n_frames(n_frames):
+    """pssr/data.py:689-695 -> None or [in (LR), out (HR)]."""
+    if n_frames in [None, -1, [-1]]:
+        return None
+    n_frames = _force_list(n_frames)
+    return n_frames * 2 if len(n_frames) == 1 else n_frames
+
+
+def _get_image_idx(idx, slices, tiles=None):
+    """pssr/data.py:697-706."""
+    tiles = [1] * len(slices) if tiles is None else tiles
+    image_idx = 0
+    for s, t in zip(slices, tiles):
+        if idx < s * t:
+            return image_idx, idx
+        idx -= s * t
+        image_idx += 1
+    raise IndexError("index out of range")
+
+
+def _get_val_idx(slices, split, seed, tiles=None):
+    """pssr/data.py:708-730 (same use of NumPy's global generator, so the same validation items)."""
+    if tiles is not None:
+        ts = []
+        for s, t in zip(slices, tiles):
+            ts.extend([s] * t)
+        slices = ts
+    val_slices = list(range(len(slices)))
+    if seed is not None and split < 1:
+        np.random.seed(seed)
+        np.random.shuffle(val_slices)
+    val_slices = set(val_slices[-max(1, int(split * len(slices))):])
+    val_idx, idx = [], 0
+    for i, s in enumerate(slices):
+        if i in val_slices:
+            val_idx.extend(range(idx, idx + s))
+        idx += s
+    return val_idx
+
+
+def _n_tiles(shape_hw, size, stride):
+    """pssr/data.py:682-687."""
+    x, y = shape_hw
+    return max(0, (x - size) // stride + 1), max(0, (y - size) // stride + 1)
+
+
+def _slice_center_range(total, n):
+    """pssr/data.py:662-668 as a (start, count) pair."""
+    center, half = total // 2, n // 2
+    return (center - half, 2 * half) if n % 2 == 0 else (center - half, 2 * half + 1)
+
+
+def _load_sources(path, extension):
+    """-> (names, arrays [F,H,W] uint8/uint16)."""
+    if isinstance(path, dict):
+        names, arrays = list(path.keys()), list(path.values())
+    elif isinstance(path, (list, tuple)):
+        arrays = list(path)
+        names = [f"image_{i}" for i in range(len(arrays))]
+    else:
+        p = Path(path) if type(path) is str else path
+        if not path or not p.exists():
+            raise FileNotFoundError(f'Path "{p}" does not exist.')
+        files = sorted(glob.glob(f"{p}/**/*.{extension}", recursive=True))
+        if not len(files) > 0:
+            raise FileNotFoundError(f'No .{extension} files exist in path "{p}".')
+        if extension.lower() == "czi":
+            raise NotImplementedError("czi decoding is outside the accelerated hot path; convert sheets to TIFF or pass arrays")
+        from PIL import Image
+        names, arrays = [], []
+        for f in files:
+            im = Image.open(f)
+            frames = []
+            for i in range(getattr(im, "n_frames", 1)):
+                im.seek(i)
+                frames.append(np.asarray(im))
+            arrays.append(np.stack(frames))
+            names.append(os.path.relpath(f, p))
+    out = []
+    for a in arrays:
+        if isinstance(a, torch.Tensor):   # e.g. a pinned host stack: uploaded as is (int16 = uint16 container)
+            if a.dim() == 2:
+                a = a[None]
+            if a.dim() != 3 or a.dtype not in (torch.uint8, torch.int16, torch.uint16):
+                raise TypeError(f"tensor images must be [frames, H, W] uint8 / uint16, got {tuple(a.shape)} {a.dtype}")
+            out.append(a.contiguous())
+            continue
+        a = np.asarray(a)
+        if a.ndim == 2:
+            a = a[np.newaxis]
+        if a.ndim != 3:
+            raise ValueError(f"images must be [frames, H, W] or [H, W], got shape {a.shape}")
+        if a.dtype == np.bool_:
+            a = a.astype(np.uint8)
+        if a.dtype not in (np.uint8, np.uint16):
+            raise TypeError(f"images must be uint8 or uint16 (Pillow modes L / I;16), got {a.dtype}")
+        out.append(np.ascontiguousarray(a))
+    return names, out
+
+
+class _DeviceDataset(Dataset):
+    """Shared machinery: resident sheets, tile table, fused batch generation."""
+
+    def _upload(self, arrays, device):
+        shapes = {tuple(a.shape[1:]) for a in arrays}
+        dtypes = {str(a.dtype).replace("torch.", "").replace("int16", "uint16").replace("uuint16", "uint16") for a in arrays}
+        if len(shapes) != 1 or len(dtypes) != 1:
+            raise NotImplementedError("all images of one dataset must share height, width and dtype on the device path")
+        self.device = torch.device(device)
+        self._sheets = []
+        for a in arrays:
+            t = a if isinstance(a, torch.Tensor) else torch.as_tensor(a.view(np.int16) if a.dtype == np.uint16 else a)
+            self._sheets.append(t.to(self.device, non_blocking=True))
+        self._frames_total = [a.shape[0] for a in arrays]
+        self._shape = next(iter(shapes))
+
+    # per-item geometry, implemented by subclasses: (sheet, frame0, y, x, vh, vw)
+    def _locate(self, idx):
+        raise NotImplementedError
+
+    def _frames_window(self, image_idx):
+        return max(self.n_frames) if self.n_frames is not None else self._frames_total[image_idx]
+
+    def _table(self, indices):
+        locs = [self._locate(i) for i in indices]
+        cols = list(zip(*locs))
+        return ops.TileTable(self._sheets, *cols)
+
+    def batch(self, indices, want_hr=True, want_hr_u8=False, want_lr=True, tile_index0=None, seed=None):
+        """One fused launch for many items.  Returns dict(lr=[n,f_lr,h,w] f32, hr=[n,f_hr,H,W] f32 | None,
+        hr_u8=[n,1,H,W] u8 | None), all on the device.  (pssr/data.py:100-120 / :236-256 + _gen_pair :471-495)"""
+        indices = list(indices)
+        frames = self._frames_window(_get_image_idx(indices[0], self.slices, getattr(self, "tiles", None))[0])
+        table = self._table(indices)
+        lr_res_scale = self.lr_scale
+        if self.is_lr:
+            # LR mode (_ready_lr, data.py:518-524): crop/pad only -- identity resample, no noise
+            lr, _, _ = ops.crappify(table, self._lr_mode_res, 1, None, frames=frames)
+            return {"lr": lr, "hr": None, "hr_u8": None}
+        lr0, lrn, hr0, hrn = 0, frames, 0, frames
+        if self.n_frames is not None and self.n_frames[0] != self.n_frames[1]:
+            if not self.n_frames[1] > frames:
+                hr0, hrn = _slice_center_range(frames, self.n_frames[1])
+            if not self.n_frames[0] > frames:
+                lr0, lrn = _slice_center_range(frames, self.n_frames[0])
+        crap = self.crappifier
+        specs, clip_between, host_crap = None, False, None
+        if crap is not None:
+            specs = crap.noise_specs() if isinstance(crap, Crappifier) and hasattr(crap, "noise_specs") else None
+            if specs is None:
+                host_crap = crap
+            else:
+                clip_between = bool(getattr(crap, "clip_between", False))
+        seed = _fresh_seed() if seed is None else seed
+        t0 = indices[0] if tile_index0 is None else tile_index0
+        if host_crap is None:
+            lr, hr, hr8 = ops.crappify(table, self.hr_res, lr_res_scale, specs, frames=frames, lr_frame0=lr0, lr_frames=lrn,
+                                       hr_frame0=hr0, hr_frames=hrn, clip_between=clip_between, seed=seed, tile_index0=t0,
+                                       want_lr=want_lr, want_hr_f32=want_hr, want_hr_u8=want_hr_u8)
+        else:
+            # user-supplied callable / host-only Crappifier (data.py:485-486): the device does tile gather + downscale,
+            # the user's own function runs on the host, round/clip follows (data.py:487)
+            lr_all, hr, hr8 = ops.crappify(table, self.hr_res, lr_res_scale, None, frames=frames, hr_frame0=hr0, hr_frames=hrn,
+                                           want_hr_f32=want_hr, want_hr_u8=want_hr_u8)
+            res = []
+            for tile in lr_all.cpu().numpy():
+                out = host_crap.crappify(tile) if isinstance(host_crap, Crappifier) else host_crap(tile)
+                out = np.asarray(out.detach().cpu() if isinstance(out, torch.Tensor) else out)
+                res.append(np.clip(out.round(), 0, 255)[lr0:lr0 + lrn].astype(np.float32))
+            lr = torch.as_tensor(np.stack(res)).to(self.device)
+        return {"lr": lr, "hr": hr, "hr_u8": hr8}
+
+    def __getitem__(self, idx, pp=False):
+        if idx >= len(self):
+            raise IndexError(f"Tried to retrieve invalid image. Index {idx} is not less than {len(self)} total image frame slices.")
+        b = self.batch([idx])
+        if self.is_lr:
+            return b["lr"][0]
+        return b["hr"][0], b["lr"][0]
+
+
+class SlidingDataset(_DeviceDataset):
+    def __init__(self, path, hr_res: int = 512, lr_scale: int = 4, crappifier=Poisson(), overlap: int = 128, n_frames=-1,
+                 slide: bool = False, stack: str = "TZ", extension: str = "czi", preload: bool = True, val_split: float = 0.1,
+                 rotation: bool = True, split_seed: int = 0, extra_path=None, extra_scale: int = 1, transforms=None,
+                 device="cuda"):
+        r"""Tiles image sheets into overlapping ``hr_res`` tiles and returns crappified high/low-resolution
+        pairs (pssr/data.py:132-266).  Sheets stay resident on ``device``; see the module docstring."""
+        super().__init__()
+        if extra_path is not None or transforms is not None:
+            raise NotImplementedError("extra_path / transforms are training-time options outside the accelerated predict path")
+        self.path = path
+        names, arrays = _load_sources(path, extension)
+        self.hr_files = names
+        overlap = 0 if overlap is None else overlap
+        if not hr_res > overlap:
+            raise ValueError(f"hr_res must be greater than overlap. Given values are {hr_res} and {overlap} respectively.")
+        self.stride = hr_res - overlap
+        self.stack = stack.upper()
+        lr_scale = None if lr_scale == -1 else lr_scale
+        self.n_frames = _get_n_frames(n_frames)
+        self.slide = slide
+        self.preload = True
+        self.tiles, self.slices, self._tiles_y = [], [], []
+        for a in arrays:
+            tx, ty = _n_tiles(a.shape[-2:], hr_res, self.stride)
+            self.tiles.append(tx * ty)
+            self._tiles_y.append(ty)
+            self.slices.append(1 if self.n_frames is None else
+                               ((a.shape[0] - max(self.n_frames) + 1) if slide else (a.shape[0] // max(self.n_frames))))
+        self.val_idx = _get_val_idx(self.slices, val_split, split_seed, self.tiles)
+        self.crop_res = hr_res
+        self.is_lr = lr_scale is None
+        if self.is_lr:
+            print("LR mode is enabled, dataset will load only unmodified low-resolution images.")
+            if val_split < 1:
+                warnings.warn("val_split is less than 1, not all low-resolution images will be used in prediciton.", stacklevel=2)
+        self.hr_res, self.lr_scale = hr_res, lr_scale
+        self._lr_mode_res = hr_res
+        self.crappifier, self.rotation, self.extra_scale, self.transforms = crappifier, rotation, extra_scale, transforms
+        self._upload(arrays, device)
+
+    def _locate(self, idx):
+        image_idx, local = _get_image_idx(idx, self.slices, self.tiles)
+        n_slices = self.slices[image_idx]
+        tile_idx = local // n_slices
+        ty = self._tiles_y[image_idx]
+        y, x = tile_idx // ty * self.stride, tile_idx % ty * self.stride          # data.py:633-634
+        f0 = 0 if self.n_frames is None else (local % n_slices) * (1 if self.slide else max(self.n_frames))
+        return image_idx, f0, y, x, self.hr_res, self.hr_res
+
+    def __len__(self):
+        return sum(t * s for t, s in zip(self.tiles, self.slices))
+
+    def __repr__(self):
+        res = f"low-res: {self.hr_res}" if self.is_lr else f"high-res: {self.hr_res}, low-res: {self.hr_res // self.lr_scale}"
+        return f'SlidingDataset from path "{self.path if isinstance(self.path, (str, Path)) else "<memory>"}"\n{len(self.hr_files)} files with {len(self)} total frame slices\n{res}'
+
+    def _get_name(self, idx):
+        image_idx, idx = _get_image_idx(idx, self.slices, self.tiles)
+        return f"{self.hr_files[image_idx].split('.')[0]}_{idx // self.slices[image_idx]}_{idx % self.slices[image_idx]}"
+
+
+class ImageDataset(_DeviceDataset):
+    def __init__(self, path, hr_res: int = 512, lr_scale: int = 4, crappifier=Poisson(), n_frames=-1, extension: str = "tif",
+                 val_split: float = 0.1, rotation: bool = True, split_seed: int = 0, extra_path=None, extra_scale: int = 1,
+                 transforms=None, device="cuda"):
+        r"""Pre-tiled images -> centre crop / reflect pad to ``hr_res`` -> crappified pairs (pssr/data.py:12-130)."""
+        super().__init__()
+        if extra_path is not None or transforms is not None:
+            raise NotImplementedError("extra_path / transforms are training-time options outside the accelerated predict path")
+        self.path = path
+        names, arrays = _load_sources(path, extension)
+        self.hr_files = names
+        lr_scale = None if lr_scale == -1 else lr_scale
+        self.n_frames = _get_n_frames(n_frames)
+        self.slices, max_size = [], 0
+        for a in arrays:
+            self.slices.append(1 if self.n_frames is None else a.shape[0] // max(self.n_frames))
+            max_size = max(max(a.shape[-2:]), max_size)
+        self.val_idx = _get_val_idx(self.slices, val_split, split_seed)
+        self.crop_res = min(hr_res, max_size)
+        self.is_lr = lr_scale is None or max_size <= hr_res // lr_scale
+        if self.is_lr:
+            print("LR mode is enabled, dataset will load only unmodified low-resolution images.")
+            if val_split < 1:
+                warnings.warn("val_split is less than 1, not all low-resolution images will be used in prediciton.", stacklevel=2)
+        self.hr_res = hr_res
+        self.lr_scale = lr_scale if lr_scale is not None else 1
+        self._lr_mode_res = hr_res // self.lr_scale
+        self.crappifier, self.rotation, self.extra_scale, self.transforms = crappifier, rotation, extra_scale, transforms
+        self._upload(arrays, device)
+
+    def _locate(self, idx):
+        image_idx, local = _get_image_idx(idx, self.slices)
+        h, w = self._shape
+        res = self._lr_mode_res if self.is_lr else self.hr_res
+        if [h, w] == [res] * 2:                                   # _square_crop, data.py:536-546
+            y = x = 0
+            size = res
+        else:
+            size = min(h, w, res)
+            y, x = (h - size) // 2, (w - size) // 2
+        if res - size > size - 1:
+            raise NotImplementedError("reflect padding wider than the image itself is not supported")
+        f0 = 0 if self.n_frames is None else (local % self.slices[image_idx]) * max(self.n_frames)
+        return image_idx, f0, y, x, size, size
+
+    def __len__(self):
+        return sum(self.slices)
+
+    def __repr__(self):
+        res = f"low-res: {self.hr_res // self.lr_scale}" if self.is_lr else f"high-res: {self.hr_res}, low-res: {self.hr_res // self.lr_scale}"
+        return f'ImageDataset from path "{self.path if isinstance(self.path, (str, Path)) else "<memory>"}"\n{len(self.hr_files)} files with {len(self)} total frame slices\n{res}'
+
+    def _get_name(self, idx):
+        image_idx, idx = _get_image_idx(idx, self.slices)
+        return self.hr_files[image_idx].split('.')[0] + (f"_{idx}" if self.n_frames is not None else "")

@@ -1,0 +1,98 @@
+"""Tile-wise sharding across the GPUs of one box.
+
+Tiles are independent (a dataset item is pure given its noise draw; the forward is per-sample in
+eval mode; metrics are per-image), so the path shards with NO data-path collective: every rank takes a
+contiguous block of the validation items.  ``torch.distributed`` (NCCL over NVLink on GPUs, gloo in the
+CPU tests) is used only to (1) all-gather per-image metric values / all-reduce their sums and
+(2) gather predicted tiles or stitched sheets on rank 0.  Without an initialised process group every
+function degenerates to the single-process case.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def is_dist() -> bool:
+    return dist.is_available() and dist.is_initialized()
+
+
+def rank() -> int:
+    return dist.get_rank() if is_dist() else 0
+
+
+def world_size() -> int:
+    return dist.get_world_size() if is_dist() else 1
+
+
+def init_from_env(backend: str = None):
+    """One process per GPU, launched by torchrun: reads RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*."""
+    if is_dist() or int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return rank(), world_size()
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if backend == "nccl":
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group(backend=backend)
+    return rank(), world_size()
+
+
+def shard_bounds(n_items: int, r: int, w: int):
+    """Contiguous, balanced block [lo, hi) of rank r among w ranks (first n % w ranks get one extra)."""
+    base, extra = divmod(n_items, w)
+    lo = r * base + min(r, extra)
+    return lo, lo + base + (1 if r < extra else 0)
+
+
+def shard_range(n_items: int):
+    return shard_bounds(n_items, rank(), world_size())
+
+
+def _device():
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def allreduce_sums(values):
+    """Sum a small float64 vector over ranks (metric sums, counts)."""
+    t = torch.as_tensor(values, dtype=torch.float64)
+    if not is_dist():
+        return t
+    t = t.to(_device())
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu()
+
+
+def gather_metric_lists(per_image: dict, names):
+    """All-gather the per-image metric lists in validation order (rank blocks are contiguous)."""
+    if not is_dist():
+        return per_image
+    gathered = [None] * world_size()
+    dist.all_gather_object(gathered, {m: per_image[m] for m in names})
+    return {m: [v for g in gathered for v in g[m]] for m in names}
+
+
+def gather_dict(outs: dict):
+    """Predicted tiles name -> uint8 array: rank 0 receives the union (others get their own share)."""
+    if not is_dist():
+        return outs
+    gathered = [None] * world_size() if rank() == 0 else None
+    dist.gather_object(outs, gathered, dst=0)
+    if rank() == 0:
+        merged = {}
+        for g in gathered:
+            merged.update(g)
+        return merged
+    return outs
+
+
+def gather_tensor_to_rank0(t: torch.Tensor):
+    """Gather equally-shaped device tensors (e.g. stitched uint8 sheets) on rank 0 with one collective."""
+    if not is_dist():
+        return [t]
+    if dist.get_backend() == "nccl":
+        bufs = [torch.empty_like(t) for _ in range(world_size())]
+        dist.all_gather(bufs, t.contiguous())
+        return bufs if rank() == 0 else None
+    bufs = [torch.empty_like(t) for _ in range(world_size())] if rank() == 0 else None
+    dist.gather(t.contiguous(), bufs, dst=0)
+    return bufs

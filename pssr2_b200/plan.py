@@ -132,7 +132,8 @@ class Plan:
         self.ops.append(op)
         self.keep += [weight, bias, out_scale, out_f32] + [s.buf for s in srcs] + ([out.buf] if out is not None else [])
         self.records.append(("conv", dict(srcs=list(srcs), segs=list(segs), weight=weight, bias=bias, out=out, Ho=Ho, Wo=Wo, B=B,
-                                          n=n, n_valid=d.n_valid, shuffle=shuffle, act=act, out_scale=out_scale, out_f32=out_f32)))
+                                          n=n, n_valid=d.n_valid, shuffle=shuffle, act=act, out_scale=out_scale, out_f32=out_f32,
+                                          issued_flops=2 * B * Ho * Wo * n * ktot)))
 
     def prep(self, x, scale, shift, im2col, xnorm=None):
         B, C, H, W = x.shape

@@ -1,0 +1,127 @@
+"""Generates the committed golden vectors by running the UNMODIFIED reference (/root/reference/pssr,
+imported through oracle/refshim.py) in the build container.  The reference cannot travel to the GPU
+box, these small fixtures do.  Run:  python tests/golden/gen_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle.refshim import import_reference  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+pssr = import_reference()
+from pssr import crappifiers as RC, data as RD, util as RU  # noqa: E402
+from pssr.models import ResUNet, RDResUNet  # noqa: E402
+from pssr.predict import _pred_array  # noqa: E402
+
+
+class Recorder:
+    """Wraps np.random.poisson / normal so the reference's own draws can be replayed on the device."""
+
+    def __enter__(self):
+        self.draws = []
+        self.p, self.n = np.random.poisson, np.random.normal
+
+        def poisson(lam, *a, **k):
+            y = self.p(lam, *a, **k)
+            self.draws.append(("poisson", np.asarray(y)))
+            return y
+
+        def normal(loc=0.0, scale=1.0, size=None):
+            g = self.n(loc, scale, size)
+            self.draws.append(("normal", np.asarray(g)))
+            return g
+
+        np.random.poisson, np.random.normal = poisson, normal
+        return self
+
+    def __exit__(self, *a):
+        np.random.poisson, np.random.normal = self.p, self.n
+
+
+def gen_pair_cases():
+    rng = np.random.default_rng(42)
+    out = {}
+    for tag, dtype, hr_res, scale, shape in [("u8_s4", np.uint8, 128, 4, (2, 128, 128)), ("u16_s4", np.uint16, 128, 4, (1, 128, 128)),
+                                             ("u8_s8_pad", np.uint8, 128, 8, (1, 120, 124)), ("u16_s2_frames", np.uint16, 64, 2, (5, 64, 64))]:
+        hr = rng.poisson(90, shape).clip(0, 255).astype(dtype)
+        crap = RC.MultiCrappifier(RC.Poisson(intensity=0.8, gain=2), RC.AdditiveGaussian(intensity=9, gain=-1))
+        n_frames = [3, 1] if "frames" in tag else None
+        np.random.seed(7)
+        with Recorder() as rec:
+            h, l = RD._gen_pair(hr, hr_res, scale, False, crap, None, n_frames)
+        out[f"{tag}_in"] = hr
+        out[f"{tag}_hr"] = h.numpy()
+        out[f"{tag}_lr"] = l.numpy()
+        out[f"{tag}_poisson"] = rec.draws[0][1].astype(np.int64)
+        out[f"{tag}_normal"] = rec.draws[1][1].astype(np.float64)
+        out[f"{tag}_meta"] = np.array([hr_res, scale, 0 if n_frames is None else 1])
+    # crappifier=None (no round / clip)
+    hr = rng.integers(0, 256, (1, 96, 96)).astype(np.uint8)
+    h, l = RD._gen_pair(hr, 96, 3, False, None, None, None)
+    out["none_in"], out["none_hr"], out["none_lr"] = hr, h.numpy(), l.numpy()
+    np.savez_compressed(os.path.join(OUT, "gen_pair.npz"), **out)
+
+
+def tiling_stitch_cases():
+    rng = np.random.default_rng(3)
+    sheet = rng.integers(0, 256, (4, 150, 209)).astype(np.uint8)
+    out = {"sheet": sheet}
+    for tag, size, stride, nf, slide in [("a", 64, 48, None, False), ("b", 32, 32, 2, False), ("c", 50, 37, 3, True)]:
+        tx, ty = RD._n_tiles(sheet, size, stride)
+        n_slices = 1 if nf is None else ((sheet.shape[0] - nf + 1) if slide else sheet.shape[0] // nf)
+        tiles = np.stack([RD._sliding_window(sheet, size, stride, nf, n_slices, i, slide) for i in range(tx * ty * n_slices)])
+        out[f"tiles_{tag}"] = tiles
+        out[f"meta_{tag}"] = np.array([size, stride, -1 if nf is None else nf, int(slide), tx, ty, n_slices])
+    for tag, n_rows, n_cols, T, ov, margin in [("p0", 3, 4, 32, 8, 0), ("p1", 3, 3, 32, 8, 4), ("p2", 2, 5, 32, 8, 6), ("p3", 4, 4, 16, 10, 2)]:
+        tiles = rng.integers(0, 256, (n_rows * n_cols, T, T)).astype(np.uint8)
+        out[f"{tag}_tiles"] = tiles
+        out[f"{tag}_sheet"] = np.asarray(RU._patch_images(tiles, n_cols, n_rows, ov, margin), dtype=np.uint8)
+        out[f"{tag}_meta"] = np.array([n_rows, n_cols, T, ov, margin])
+    out["val_idx_a"] = np.array(RD._get_val_idx([2, 3, 1, 4], 0.5, 0, [3, 2, 4, 1]))
+    out["val_idx_b"] = np.array(RD._get_val_idx([1] * 10, 0.1, 0))
+    np.savez_compressed(os.path.join(OUT, "tiling_stitch.npz"), **out)
+
+
+def normalize_cases():
+    rng = np.random.default_rng(5)
+    base = rng.poisson(90, (3, 1, 96, 96)).clip(0, 255)
+    hr = base.astype(np.uint8)
+    hat = np.clip(base * 0.8 + 20 + rng.normal(0, 6, base.shape), 0, 255).astype(np.uint8)
+    a, b = RU.normalize_preds(hr, hat)
+    np.savez_compressed(os.path.join(OUT, "normalize.npz"), hr=hr, hat=hat, hr_norm=a, hat_norm=b)
+
+
+def net_cases():
+    out = {}
+    rng = np.random.default_rng(9)
+    for tag, cls, kw, shape in [("resunet_small", ResUNet, dict(hidden=[64, 128], scale=2, depth=1), (2, 1, 32, 32)),
+                                ("resunet_5ch_s8", ResUNet, dict(channels=[5, 1], hidden=[64, 128], scale=8, depth=0), (1, 5, 16, 16))]:
+        torch.manual_seed(1234)
+        m = cls(**kw).eval()
+        g = torch.Generator().manual_seed(1)
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.copy_(torch.randn(mod.running_mean.shape, generator=g) * 0.1)
+                mod.running_var.copy_(torch.rand(mod.running_var.shape, generator=g) + 0.5)
+        x = torch.tensor(rng.integers(0, 256, shape).astype(np.float32))
+        with torch.no_grad():
+            y = m(x)
+        out[f"{tag}_x"] = x.numpy()
+        out[f"{tag}_y"] = y.numpy()
+        out[f"{tag}_pred"] = _pred_array(y)
+        out[f"{tag}_wsum"] = np.array([float(sum(p.double().sum() for p in m.state_dict().values() if p.is_floating_point()))])
+    np.savez_compressed(os.path.join(OUT, "net.npz"), **out)
+
+
+if __name__ == "__main__":
+    gen_pair_cases()
+    tiling_stitch_cases()
+    normalize_cases()
+    net_cases()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -1,0 +1,86 @@
+"""Pins the oracle restatements against the reference's own code, imported live from /root/reference
+(skipped where the reference is absent, e.g. on the GPU box; the golden vectors cover that case)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pipeline as OP
+from oracle.refshim import import_reference, reference_available
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="/root/reference not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return import_reference()
+
+
+def test_models_match_reference(ref):
+    from oracle.models import rdresunet_forward, resunet_forward
+    from pssr.models import RDResUNet, ResUNet
+    torch.manual_seed(0)
+    x = torch.tensor(np.random.default_rng(0).integers(0, 256, (1, 1, 64, 64)).astype(np.float32))
+    with torch.no_grad():
+        m = ResUNet().eval()
+        assert float((m(x) - resunet_forward(m.state_dict(), x)).abs().max()) < 1e-4
+        m = ResUNet(channels=[3, 3], hidden=[64, 128, 256], scale=2, depth=1).eval()
+        x3 = x.repeat(1, 3, 1, 1)
+        assert float((m(x3) - resunet_forward(m.state_dict(), x3)).abs().max()) < 1e-4
+        r = RDResUNet().eval()
+        assert float((r(x) - rdresunet_forward(r.state_dict(), x)).abs().max()) < 1e-4
+
+
+def test_state_dict_keys_match_reference(ref):
+    from pssr.models import ResUNet as RefResUNet
+    from pssr2_b200.models import ResUNet
+    for kw in (dict(), dict(channels=[3, 1], hidden=[64, 128, 256], scale=2, depth=2)):
+        a, b = RefResUNet(**kw).state_dict(), ResUNet(**kw).state_dict()
+        assert list(a.keys()) == list(b.keys())
+        assert all(a[k].shape == b[k].shape for k in a)
+        ResUNet(**kw).load_state_dict(a, strict=True)
+
+
+def test_crappifier_stage_arithmetic_matches_reference(ref):
+    from pssr import crappifiers as RC
+    rng = np.random.default_rng(2)
+    lr = rng.integers(0, 256, (2, 32, 32)).astype(np.float32)
+    for intensity in (1, 0.5, 2):
+        np.random.seed(3)
+        want = RC.Poisson(intensity=intensity, gain=3).crappify(lr)
+        np.random.seed(3)
+        y = np.random.poisson(np.clip(lr, 0, np.inf))
+        got = OP.poisson_stage(lr, y, intensity, 3)
+        assert got.dtype == want.dtype and np.array_equal(got, want)
+    np.random.seed(4)
+    want = RC.AdditiveGaussian(intensity=7, gain=1).crappify(lr)
+    np.random.seed(4)
+    got = OP.gaussian_stage(lr, np.random.normal(1, 7, lr.shape))
+    assert got.dtype == want.dtype and np.array_equal(got, want)
+
+
+def test_normalize_and_patch_match_reference(ref):
+    from pssr import util as RU
+    rng = np.random.default_rng(6)
+    hr = rng.poisson(80, (2, 1, 64, 64)).clip(0, 255).astype(np.uint8)
+    hat = np.clip(hr * 0.7 + 30 + rng.normal(0, 5, hr.shape), 0, 255).astype(np.uint8)
+    a, b = RU.normalize_preds(hr, hat)
+    c, d = OP.normalize_preds(hr, hat)
+    assert np.array_equal(a, c) and np.array_equal(b, d)
+    tiles = rng.integers(0, 256, (12, 32, 32)).astype(np.uint8)
+    assert np.array_equal(np.asarray(RU._patch_images(tiles, 4, 3, 8, 4), dtype=np.uint8), OP.stitch_sheets(tiles, 3, 4, 8, 4)[0])
+
+
+def test_dataset_index_math_matches_reference(ref):
+    from pssr import data as RD
+    from pssr2_b200 import data as MD
+    for slices, tiles in (([2, 3, 1], [4, 2, 3]), ([1, 1, 1, 1], None)):
+        total = sum(s * (t if tiles else 1) for s, t in zip(slices, tiles or [1] * len(slices)))
+        for idx in range(total):
+            assert RD._get_image_idx(idx, slices, tiles) == MD._get_image_idx(idx, slices, tiles)
+        for split, seed in ((0.5, 0), (0.1, 3), (1, None)):
+            assert RD._get_val_idx(slices, split, seed, tiles) == MD._get_val_idx(slices, split, seed, tiles)
+    for n in (-1, None, 3, [5, 1]):
+        assert RD._get_n_frames(n) == MD._get_n_frames(n)
+    for total, n in ((5, 1), (5, 3), (6, 2), (7, 4)):
+        s, c = MD._slice_center_range(total, n)
+        assert np.array_equal(RD._slice_center(np.arange(total).reshape(total, 1, 1), n).ravel(), np.arange(s, s + c))
