@@ -212,6 +212,12 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     value = world * BATCH * TILE * TILE / (ms_step * 1e-3) / 1e6
 
+    if args.kernels_only:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": round(value, 1), "unit": UNIT, "ms_per_step": round(ms_step, 3),
+                              "gpu_launches": int(launches), "note": "--kernels-only run (profiling), not a bench line"}))
+        return
+
     # ---- e2e through the public API from pinned host buffers ---------------------------------
     host = [b.cpu().pin_memory() for b in batches[:2]]
 
@@ -305,6 +311,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--kernels-only", action="store_true", help="timed region only (for ncu launch lists): skip e2e / roofline / CPU legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -13,7 +13,7 @@ from ctypes import (POINTER, Structure, Union, c_char_p, c_double, c_float, c_in
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libpssr_b200.so")
-SOURCES = ["api.cu", "conv_igemm.cu", "net_aux.cu", "crappify.cu", "stitch.cu", "metrics.cu"]
+SOURCES = ["api.cu", "conv_igemm.cu", "conv_strip.cu", "net_aux.cu", "crappify.cu", "stitch.cu", "metrics.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

@@ -54,7 +54,7 @@ int pssr_plan_create(const pssr_op_t* ops, int32_t n_ops, int32_t dtype, pssr_pl
     switch (op.kind) {
       case PSSR_OP_CONV: {
         ConvOp c;
-        int rc = conv_prepare(op.u.conv, dtype, c);
+        int rc = strip_supported(op.u.conv) ? strip_prepare(op.u.conv, dtype, c) : conv_prepare(op.u.conv, dtype, c);
         if (rc != PSSR_OK) {
           char msg[400];
           snprintf(msg, sizeof(msg), "%s", g_err);
@@ -109,7 +109,8 @@ int pssr_plan_run_range(pssr_plan_t* plan, int32_t first, int32_t count, void* s
     switch (op.kind) {
       case PSSR_OP_CONV: {
         const int ci = plan->conv_index[i];
-        rc = conv_launch(plan->convs[ci], reinterpret_cast<uint8_t*>(plan->tmaps_dev) + (size_t)ci * 4 * sizeof(CUtensorMap), st);
+        const void* tm = reinterpret_cast<uint8_t*>(plan->tmaps_dev) + (size_t)ci * 4 * sizeof(CUtensorMap);
+        rc = plan->convs[ci].variant == 2 ? strip_launch(plan->convs[ci], tm, st) : conv_launch(plan->convs[ci], tm, st);
         break;
       }
       case PSSR_OP_PREP:

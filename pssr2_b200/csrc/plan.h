@@ -9,13 +9,17 @@ namespace pssr {
 
 struct ConvOp {
   CUtensorMap tmaps[4];           // host copies; uploaded into the plan's device table
-  alignas(16) uint8_t kparams[320];
+  alignas(16) uint8_t kparams[512];
   int grid = 0;
   int smem_bytes = 0;
+  int variant = 1;                // 1 = conv_igemm.cu (box per tap), 2 = conv_strip.cu (halo strips)
 };
 
 int conv_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op);
 int conv_launch(const ConvOp& op, const void* tmaps_dev, cudaStream_t stream);
+bool strip_supported(const pssr_conv_desc_t& d);
+int strip_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op);
+int strip_launch(const ConvOp& op, const void* tmaps_dev, cudaStream_t stream);
 
 int prep_launch(const pssr_prep_desc_t& d, int dtype, cudaStream_t stream);
 int pool_launch(const pssr_pool_desc_t& d, int dtype, cudaStream_t stream);
