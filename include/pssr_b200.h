@@ -146,6 +146,7 @@ int pssr_resize_bilinear(const void* src, void* dst, int32_t n, int32_t h, int32
 #define PSSR_OP_LAYERNORM 6   /* LayerNorm2d over C                                         */
 #define PSSR_OP_ESE 7         /* EffectiveSE gate + layer-scale gamma                       */
 #define PSSR_OP_COPY 8        /* channel-slice copy between NHWC buffers                    */
+#define PSSR_OP_TAILSUM 9     /* 9-tap gather of the fused Reconstruction tail + *128+128   */
 
 /* One NHWC source view of an implicit-GEMM op. */
 typedef struct {
@@ -184,6 +185,14 @@ typedef struct {
   int32_t act;           /* PSSR_ACT_*                                                      */
   const float* out_scale;/* optional per-channel multiplier applied after act (layer-scale) */
   float* out_f32;        /* optional fp32 NHWC copy of the output (same geometry) or NULL   */
+  /* Fused Reconstruction tail (pssr/models/_blocks.py:15-18): when tail_z != NULL the epilogue does not
+   * store the activation (out may be NULL).  Instead, per output pixel and per pixel-shuffle sub-position
+   * s = i*r+j it reduces the C' = n/r^2 post-ReLU channels against the 3x3 tail weights in fp32:
+   *     z[b][s*9 + t][y][x] = sum_c tail_weight[t][c] * act(acc[s*C' + c] + bias)        t = 0..8
+   * (a 1x1 "per-tap" projection; PSSR_OP_TAILSUM then gathers the 9 shifted taps at HR resolution).
+   * The r^2*C'-channel HR feature map -- 2 GB per 64-tile batch -- never exists in memory.            */
+  const float* tail_weight; /* fp32 [9][C'] (single output channel)                               */
+  float* tail_z;            /* fp32 planar [B][r*r*9][Ho][Wo]                                     */
 } pssr_conv_desc_t;
 
 typedef struct {
@@ -216,6 +225,18 @@ typedef struct {
                             (predict.py:245-246 `_pred_array`) or NULL                       */
 } pssr_tail_desc_t;
 
+/* Second half of the fused tail: out[b][0][Y][X] = (bias + sum_t zHR[(Y+dy, X+dx)][t]) * mul + add with
+ * zHR[(Y,X)][t] = z[b][((Y%r)*r + X%r)*9 + t][Y/r][X/r] and zero outside the HR image
+ * (= Reconstruction.conv's zero padding), plus the fused `_pred_array` uint8 output.               */
+typedef struct {
+  const float* z;        /* [B][r*r*9][H][W]                                                  */
+  int32_t B, H, W, r;    /* LR geometry and pixel-shuffle factor; output is [B][1][H*r][W*r]  */
+  float bias, mul, add;
+  int32_t reserved;
+  float* out_f32;        /* [B][1][H*r][W*r] or NULL                                          */
+  uint8_t* out_u8;       /* [B][H*r][W*r] or NULL                                             */
+} pssr_tailsum_desc_t;
+
 typedef struct {
   int32_t kind;          /* PSSR_OP_*                                                       */
   int32_t reserved;
@@ -224,6 +245,7 @@ typedef struct {
     pssr_prep_desc_t prep;
     pssr_pool_desc_t pool;
     pssr_tail_desc_t tail;
+    pssr_tailsum_desc_t tailsum;
     uint8_t pad[512];
   } u;
 } pssr_op_t;

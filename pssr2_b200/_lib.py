@@ -89,7 +89,7 @@ class ConvDesc(Structure):
                 ("weights", c_void_p), ("bias", c_void_p), ("n", c_int32), ("n_valid", c_int32),
                 ("Ho", c_int32), ("Wo", c_int32), ("B", c_int32), ("out", c_void_p),
                 ("out_cstride", c_int32), ("out_choff", c_int32), ("shuffle", c_int32), ("act", c_int32),
-                ("out_scale", c_void_p), ("out_f32", c_void_p)]
+                ("out_scale", c_void_p), ("out_f32", c_void_p), ("tail_weight", c_void_p), ("tail_z", c_void_p)]
 
 
 class PrepDesc(Structure):
@@ -110,8 +110,13 @@ class TailDesc(Structure):
                 ("mul", c_float), ("add", c_float), ("out_f32", c_void_p), ("out_u8", c_void_p)]
 
 
+class TailSumDesc(Structure):
+    _fields_ = [("z", c_void_p), ("B", c_int32), ("H", c_int32), ("W", c_int32), ("r", c_int32), ("bias", c_float),
+                ("mul", c_float), ("add", c_float), ("reserved", c_int32), ("out_f32", c_void_p), ("out_u8", c_void_p)]
+
+
 class _OpU(Union):
-    _fields_ = [("conv", ConvDesc), ("prep", PrepDesc), ("pool", PoolDesc), ("tail", TailDesc),
+    _fields_ = [("conv", ConvDesc), ("prep", PrepDesc), ("pool", PoolDesc), ("tail", TailDesc), ("tailsum", TailSumDesc),
                 ("pad", c_uint8 * 512)]
 
 
@@ -119,7 +124,7 @@ class Op(Structure):
     _fields_ = [("kind", c_int32), ("reserved", c_int32), ("u", _OpU)]
 
 
-OP_CONV, OP_PREP, OP_MAXPOOL, OP_TAIL = 1, 2, 3, 4
+OP_CONV, OP_PREP, OP_MAXPOOL, OP_TAIL, OP_TAILSUM = 1, 2, 3, 4, 9
 DT_BF16, DT_FP16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 NOISE_POISSON, NOISE_GAUSSIAN, NOISE_SALTPEPPER = 1, 2, 3

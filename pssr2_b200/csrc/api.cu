@@ -69,6 +69,7 @@ int pssr_plan_create(const pssr_op_t* ops, int32_t n_ops, int32_t dtype, pssr_pl
       case PSSR_OP_PREP:
       case PSSR_OP_MAXPOOL:
       case PSSR_OP_TAIL:
+      case PSSR_OP_TAILSUM:
         break;
       default:
         set_error("plan_create: op %d has unsupported kind %d", i, op.kind);
@@ -121,6 +122,9 @@ int pssr_plan_run_range(pssr_plan_t* plan, int32_t first, int32_t count, void* s
         break;
       case PSSR_OP_TAIL:
         rc = tail_launch(op.u.tail, plan->dtype, st);
+        break;
+      case PSSR_OP_TAILSUM:
+        rc = tailsum_launch(op.u.tailsum, st);
         break;
       default:
         set_error("plan_run: op %d has unsupported kind %d", i, op.kind);

@@ -294,6 +294,7 @@ int conv_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
   PSSR_REQUIRE(d.shuffle == 1 || d.n == d.n_valid, PSSR_EUNSUP, "conv: padded N with pixel shuffle unsupported");
   PSSR_REQUIRE(d.out_cstride % 8 == 0 && d.out_choff % 8 == 0, PSSR_EUNSUP,
                "conv: output channel stride/offset must be multiples of 8");
+  PSSR_REQUIRE(d.tail_z == nullptr, PSSR_EUNSUP, "conv: the fused Reconstruction tail needs the strip kernel (stride-1 3x3/1x1 taps)");
   PSSR_REQUIRE(d.out != nullptr || d.out_f32 != nullptr, PSSR_EINVAL, "conv: no output buffer");
 
   ConvKParams& p = *reinterpret_cast<ConvKParams*>(op.kparams);

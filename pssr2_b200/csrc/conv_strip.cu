@@ -52,6 +52,8 @@ struct StripKParams {
   float* out_f32;
   int out_cstride, out_choff, shuffle, cps, act, fp16;
   int Hout, Wout;
+  const float* tail_w;        // fused Reconstruction tail: fp32 [9][cps] or nullptr
+  float* tail_z;              // fp32 planar [B][r*r*9][H][W]
 };
 
 __device__ __forceinline__ uint64_t strip_desc(uint32_t addr, int mode) {
@@ -84,10 +86,13 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
   // bias (and optional per-channel scale) of the whole layer, staged once per CTA
   float* bias_s = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + 2u * p.a_bytes + (uint32_t)p.b_stages * p.b_bytes);
   float* scale_s = bias_s + p.n_total;
+  float* tailw_s = scale_s + p.n_total;
   for (int i = threadIdx.x; i < p.n_total; i += kSThreads) {
     bias_s[i] = p.bias[i];
     if (p.out_scale != nullptr) scale_s[i] = p.out_scale[i];
   }
+  if (p.tail_w != nullptr)
+    for (int i = threadIdx.x; i < 9 * p.cps; i += kSThreads) tailw_s[i] = p.tail_w[i];
   const uint32_t bar0 = smem_u32(bars);
   auto a_full = [&](int s) { return bar0 + 8u * s; };
   auto a_empty = [&](int s) { return bar0 + 8u * (2 + s); };
@@ -268,12 +273,54 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
         int cc = n_tile * block_n - sub * p.cps;
         int si = sub / r, sj = sub - si * r;
         const size_t pix00 = ((size_t)n * p.Hout + (size_t)(y * r)) * p.Wout + (size_t)(x * r);
+        float zacc[9];
         const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * T * block_n + mt * block_n);
         for (int c0 = 0; c0 < block_n; c0 += 32) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + (uint32_t)c0, v);
           tmem_ld_wait();
-          {
+          if (p.tail_z != nullptr) {
+            // fused Reconstruction tail: per-tap projection of this sub-pixel's channels, fp32 on CUDA cores
+            if (valid && !(p.dbg & 1)) {
+              const int nbase = n_tile * block_n + c0;
+              const int sub_t = nbase / p.cps;
+              const int ccb = nbase - sub_t * p.cps;
+              if (ccb == 0) {
+#pragma unroll
+                for (int t = 0; t < 9; ++t) zacc[t] = 0.f;
+              }
+              float rr[32];
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 bb = *reinterpret_cast<const float4*>(bias_s + nbase + 4 * j4);
+                rr[4 * j4 + 0] = fmaxf(__uint_as_float(v[4 * j4 + 0]) + bb.x, 0.f);
+                rr[4 * j4 + 1] = fmaxf(__uint_as_float(v[4 * j4 + 1]) + bb.y, 0.f);
+                rr[4 * j4 + 2] = fmaxf(__uint_as_float(v[4 * j4 + 2]) + bb.z, 0.f);
+                rr[4 * j4 + 3] = fmaxf(__uint_as_float(v[4 * j4 + 3]) + bb.w, 0.f);
+              }
+#pragma unroll
+              for (int t = 0; t < 9; ++t) {
+                const float* wt = tailw_s + t * p.cps + ccb;
+                float a = zacc[t];
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 w4 = *reinterpret_cast<const float4*>(wt + 4 * j4);
+                  a = fmaf(rr[4 * j4 + 0], w4.x, a);
+                  a = fmaf(rr[4 * j4 + 1], w4.y, a);
+                  a = fmaf(rr[4 * j4 + 2], w4.z, a);
+                  a = fmaf(rr[4 * j4 + 3], w4.w, a);
+                }
+                zacc[t] = a;
+              }
+              if (ccb + 32 == p.cps) {
+                const int planes = r * r * 9;
+                float* zp = p.tail_z + (((size_t)n * planes + (size_t)sub_t * 9) * p.H + y) * p.W + x;
+                const size_t plane = (size_t)p.H * p.W;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) zp[(size_t)t * plane] = zacc[t];
+              }
+            }
+          } else {
             const int nbase = n_tile * block_n + c0;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -373,7 +420,7 @@ bool strip_supported(const pssr_conv_desc_t& d) {
   if (d.n % 32 != 0 || d.n < 32) return false;
   // small feature maps: the padded pixel space wastes (1 - HW/((H+2)(W+2))) of the MMAs (36 % at 8x8, 21 % at 16x16)
   // and the exact-tile kernel (conv_igemm.cu) is faster there
-  if (d.Wo < 32 && getenv("PSSR_STRIP_ALWAYS") == nullptr) return false;
+  if (d.Wo < 32 && d.tail_z == nullptr && getenv("PSSR_STRIP_ALWAYS") == nullptr) return false;
   return true;
 }
 
@@ -387,8 +434,12 @@ int strip_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
   PSSR_REQUIRE(cps % 8 == 0, PSSR_EUNSUP, "conv: channels after pixel shuffle (%d) must be a multiple of 8", cps);
   PSSR_REQUIRE(d.shuffle == 1 || d.n == d.n_valid, PSSR_EUNSUP, "conv: padded N with pixel shuffle unsupported");
   PSSR_REQUIRE(d.out_cstride % 8 == 0 && d.out_choff % 8 == 0, PSSR_EUNSUP, "conv: output channel stride/offset must be multiples of 8");
-  PSSR_REQUIRE(d.out != nullptr || d.out_f32 != nullptr, PSSR_EINVAL, "conv: no output buffer");
+  PSSR_REQUIRE(d.out != nullptr || d.out_f32 != nullptr || d.tail_z != nullptr, PSSR_EINVAL, "conv: no output buffer");
   PSSR_REQUIRE(d.bias != nullptr && ((uintptr_t)d.bias & 15) == 0, PSSR_EINVAL, "conv: bias missing or misaligned");
+  if (d.tail_z != nullptr) {
+    PSSR_REQUIRE(d.tail_weight != nullptr && ((uintptr_t)d.tail_weight & 15) == 0, PSSR_EINVAL, "conv: tail_weight missing or misaligned");
+    PSSR_REQUIRE(cps % 32 == 0 && d.act == PSSR_ACT_RELU && d.n == d.n_valid, PSSR_EUNSUP, "conv: fused tail needs C' %% 32 == 0, ReLU and unpadded N");
+  }
 
   StripKParams& p = *reinterpret_cast<StripKParams*>(op.kparams);
   static_assert(sizeof(StripKParams) <= sizeof(op.kparams), "ConvOp::kparams too small");
@@ -423,7 +474,8 @@ int strip_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
 
   // T: as many M tiles per unit as TMEM (512 columns) and shared memory allow, capped at 2 so the A halo
   // buffers can be double-buffered; TMEM is double-buffered when T * block_n <= 256.
-  const int smem_cap = 226 * 1024 - 1024 - 8 * d.n;   // minus the staged bias / scale vectors
+  const int tailw_bytes = d.tail_z != nullptr ? 9 * cps * 4 : 0;
+  const int smem_cap = 226 * 1024 - 1024 - 8 * d.n - tailw_bytes;   // minus the staged bias / scale / tail-weight vectors
   // measured on B200 (scripts/dev_time_layer.py): keeping T * block_n <= 256 so that TMEM is double-buffered and the
   // epilogue of unit i overlaps the MMAs of unit i+1 beats the halved weight traffic of a larger T.
   int T = 256 / block_n;
@@ -480,12 +532,14 @@ int strip_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PSSR_REQUIRE(r == CUDA_SUCCESS, PSSR_ECUDA, "cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
   }
-  op.smem_bytes = (int)(2 * p.a_bytes + (uint32_t)b_stages * p.b_bytes + 1024 + 8 * (uint32_t)d.n);
+  op.smem_bytes = (int)(2 * p.a_bytes + (uint32_t)b_stages * p.b_bytes + 1024 + 8 * (uint32_t)d.n + (uint32_t)tailw_bytes);
 
   p.bias = d.bias;
   p.out_scale = d.out_scale;
   p.out = reinterpret_cast<uint16_t*>(d.out);
   p.out_f32 = d.out_f32;
+  p.tail_w = d.tail_weight;
+  p.tail_z = d.tail_z;
   p.out_cstride = d.out_cstride;
   p.out_choff = d.out_choff;
   p.shuffle = d.shuffle;

@@ -215,4 +215,47 @@ int tail_launch(const pssr_tail_desc_t& d, int dtype, cudaStream_t stream) {
   return PSSR_OK;
 }
 
+// --------------------------------------------------------------------------- tailsum
+// Second half of the fused Reconstruction tail: gather the nine per-tap projections the conv epilogue
+// left at LR resolution (planar z[b][s*9+t][y][x]) at their shifted HR positions, add the bias, apply
+// x*128+128 (resunet.py:95) and emit fp32 + `_pred_array` uint8.  Pure streaming: ~r^2*9*4 B read and 5 B
+// written per LR pixel.
+__global__ void __launch_bounds__(256) tailsum_kernel(pssr_tailsum_desc_t d) {
+  const int Hh = d.H * d.r, Wh = d.W * d.r;
+  const long long total = (long long)d.B * Hh * Wh;
+  const size_t plane = (size_t)d.H * d.W;
+  const int planes = d.r * d.r * 9;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int X = (int)(i % Wh);
+    const int Y = (int)((i / Wh) % Hh);
+    const int n = (int)(i / ((long long)Wh * Hh));
+    const float* zb = d.z + (size_t)n * planes * plane;
+    float acc = d.bias;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int Yt = Y + t / 3 - 1, Xt = X + t % 3 - 1;
+      if (Yt >= 0 && Yt < Hh && Xt >= 0 && Xt < Wh) {
+        const int y = Yt / d.r, x = Xt / d.r;
+        const int s = (Yt - y * d.r) * d.r + (Xt - x * d.r);
+        acc += __ldg(zb + (size_t)(s * 9 + t) * plane + (size_t)y * d.W + x);
+      }
+    }
+    const float yv = acc * d.mul + d.add;
+    if (d.out_f32 != nullptr) d.out_f32[i] = yv;
+    if (d.out_u8 != nullptr) d.out_u8[i] = (uint8_t)(int)fminf(fmaxf(yv, 0.f), 255.f);
+  }
+}
+
+int tailsum_launch(const pssr_tailsum_desc_t& d, cudaStream_t stream) {
+  PSSR_REQUIRE(d.z != nullptr && d.B >= 1 && d.H >= 1 && d.W >= 1 && d.r >= 1, PSSR_EINVAL, "tailsum: bad arguments");
+  const long long total = (long long)d.B * d.H * d.r * d.W * d.r;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)device_sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  tailsum_kernel<<<(int)blocks, 256, 0, stream>>>(d);
+  count_launch();
+  PSSR_CHECK_CUDA(cudaGetLastError());
+  return PSSR_OK;
+}
+
 }  // namespace pssr

@@ -24,6 +24,7 @@ int strip_launch(const ConvOp& op, const void* tmaps_dev, cudaStream_t stream);
 int prep_launch(const pssr_prep_desc_t& d, int dtype, cudaStream_t stream);
 int pool_launch(const pssr_pool_desc_t& d, int dtype, cudaStream_t stream);
 int tail_launch(const pssr_tail_desc_t& d, int dtype, cudaStream_t stream);
+int tailsum_launch(const pssr_tailsum_desc_t& d, cudaStream_t stream);
 
 }  // namespace pssr
 

@@ -80,6 +80,7 @@ class _PlanModule(nn.Module):
     parameters may have changed (load_state_dict, .to(), train())."""
 
     precision = "fp16"   # operand format of the tensor-core path: "fp16" or "bf16" (fp32 accumulate)
+    fuse_tail = True     # fuse Reconstruction.conv into Reconstruction.pre's epilogue (single output channel)
 
     def __init__(self):
         super().__init__()
@@ -110,7 +111,7 @@ class _PlanModule(nn.Module):
             raise RuntimeError("pssr2_b200 models implement the eval()/predict path only (call model.eval())")
         if x.dtype not in (torch.float32, torch.uint8):
             x = x.float()
-        key = (tuple(x.shape), x.dtype, x.device.index, self.precision)
+        key = (tuple(x.shape), x.dtype, x.device.index, self.precision, self.fuse_tail)
         st = self._plans.get(key)
         if st is None:
             with torch.no_grad():
@@ -314,16 +315,24 @@ class ResUNet(_PlanModule):
         bp = rec.pre.bias.detach().float()
         parts = [wp[:, :hid[0]], _im2col_parts(wp[:, hid[0]:])]
         wpk = pack_weight(parts, plan.dtype, s)
-        ps_out = z(B, H * s, W * s, hid[0])
-        plan.conv([View(final), xcol], [(0, 9, ceil_div(hid[0], 64)), (1, 1, 1)], wpk, permute_n(bp, s).contiguous(), View(ps_out),
-                  Ho=H, Wo=W, B=B, shuffle=s, act=ACT_RELU)
-        plan.flops += 2 * wp.numel() * B * H * W
-        wc = rec.conv.weight.detach().float().permute(0, 2, 3, 1).contiguous()  # [Cout][3][3][C]
+        wc = rec.conv.weight.detach().float()
         bc = rec.conv.bias.detach().float().contiguous()
         cout = wc.shape[0]
         out = torch.empty(B, cout, H * s, W * s, dtype=torch.float32, device=dev)
         out_u8 = torch.empty(B, 1, H * s, W * s, dtype=torch.uint8, device=dev)
-        plan.tail(View(ps_out), wc, bc, 128.0, 128.0, out, out_u8)  # x*128+128 (resunet.py:95)
-        plan.flops += 2 * wc.numel() * B * H * s * W * s
+        srcs, segs = [View(final), xcol], [(0, 9, ceil_div(hid[0], 64)), (1, 1, 1)]
+        plan.flops += 2 * wp.numel() * B * H * W + 2 * wc.numel() * B * H * s * W * s
+        if cout == 1 and hid[0] % 32 == 0 and W >= 1 and self.fuse_tail:
+            # fused tail: relu(pre) is reduced against the 3x3 tail weights inside the conv epilogue (fp32), the
+            # scale^2*hidden-channel HR map is never written; PSSR_OP_TAILSUM gathers the 9 taps (see include/pssr_b200.h)
+            tw = wc[0].permute(1, 2, 0).reshape(9, hid[0]).contiguous()      # [tap][c]
+            zbuf = torch.zeros(B, s * s * 9, H, W, dtype=torch.float32, device=dev)
+            plan.conv(srcs, segs, wpk, permute_n(bp, s).contiguous(), None, Ho=H, Wo=W, B=B, shuffle=s, act=ACT_RELU,
+                      tail_weight=tw, tail_z=zbuf)
+            plan.tailsum(zbuf, s, float(bc[0]), 128.0, 128.0, out, out_u8)    # x*128+128 (resunet.py:95)
+        else:
+            ps_out = z(B, H * s, W * s, hid[0])
+            plan.conv(srcs, segs, wpk, permute_n(bp, s).contiguous(), View(ps_out), Ho=H, Wo=W, B=B, shuffle=s, act=ACT_RELU)
+            plan.tail(View(ps_out), wc.permute(0, 2, 3, 1).contiguous(), bc, 128.0, 128.0, out, out_u8)
         plan.finalize()
         return {"plan": plan, "x": x_in, "out": out, "out_u8": out_u8}

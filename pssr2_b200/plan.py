@@ -11,8 +11,8 @@ import math
 import torch
 
 from . import _lib
-from ._lib import (ACT_NONE, ACT_RELU, DT_BF16, DT_FP16, OP_CONV, OP_MAXPOOL, OP_PREP, OP_TAIL, ConvDesc, KSeg, Op,
-                   PoolDesc, PrepDesc, Src, TailDesc)
+from ._lib import (ACT_NONE, ACT_RELU, DT_BF16, DT_FP16, OP_CONV, OP_MAXPOOL, OP_PREP, OP_TAIL, OP_TAILSUM, ConvDesc, KSeg, Op,
+                   PoolDesc, PrepDesc, Src, TailDesc, TailSumDesc)
 
 TORCH_DT = {DT_BF16: torch.bfloat16, DT_FP16: torch.float16}
 DT_NAMES = {"bf16": DT_BF16, "fp16": DT_FP16}
@@ -100,7 +100,7 @@ class Plan:
 
     # ---- op builders -----------------------------------------------------------------
     def conv(self, srcs, segs, weight, bias, out: View, *, Ho, Wo, B, n=None, n_valid=None, shuffle=1, act=ACT_NONE,
-             out_scale=None, out_f32=None):
+             out_scale=None, out_f32=None, tail_weight=None, tail_z=None):
         """srcs: list[View]; segs: list[(src_index, taps, cblocks)]; weight [n, Ktot] 16-bit; bias [n] fp32."""
         d = ConvDesc()
         d.n_srcs = len(srcs)
@@ -120,20 +120,22 @@ class Plan:
         d.n_valid = n if n_valid is None else n_valid
         d.Ho, d.Wo, d.B = Ho, Wo, B
         d.out = out.buf.data_ptr() if out is not None else None
-        d.out_cstride = out.cstride if out is not None else out_f32.shape[3]
+        d.out_cstride = out.cstride if out is not None else (out_f32.shape[3] if out_f32 is not None else 16)
         d.out_choff = out.choff if out is not None else 0
         d.shuffle = shuffle
         d.act = act
         d.out_scale = out_scale.data_ptr() if out_scale is not None else None
         d.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
+        d.tail_weight = tail_weight.data_ptr() if tail_weight is not None else None
+        d.tail_z = tail_z.data_ptr() if tail_z is not None else None
         op = Op()
         op.kind = OP_CONV
         op.u.conv = d
         self.ops.append(op)
-        self.keep += [weight, bias, out_scale, out_f32] + [s.buf for s in srcs] + ([out.buf] if out is not None else [])
+        self.keep += [weight, bias, out_scale, out_f32, tail_weight, tail_z] + [s.buf for s in srcs] + ([out.buf] if out is not None else [])
         self.records.append(("conv", dict(srcs=list(srcs), segs=list(segs), weight=weight, bias=bias, out=out, Ho=Ho, Wo=Wo, B=B,
                                           n=n, n_valid=d.n_valid, shuffle=shuffle, act=act, out_scale=out_scale, out_f32=out_f32,
-                                          issued_flops=2 * B * Ho * Wo * n * ktot)))
+                                          issued_flops=2 * B * Ho * Wo * n * ktot, tail_weight=tail_weight, tail_z=tail_z)))
 
     def prep(self, x, scale, shift, im2col, xnorm=None):
         B, C, H, W = x.shape
@@ -167,6 +169,18 @@ class Plan:
         self.ops.append(op)
         self.keep += [src.buf, weight, bias, out_f32, out_u8]
         self.records.append(("tail", dict(src=src, weight=weight, bias=bias, mul=mul, add=add, out_f32=out_f32, out_u8=out_u8)))
+
+    def tailsum(self, z, r, bias, mul, add, out_f32=None, out_u8=None):
+        B, planes, H, W = z.shape
+        assert planes == r * r * 9 and z.dtype == torch.float32 and z.is_contiguous()
+        d = TailSumDesc(z.data_ptr(), B, H, W, r, float(bias), mul, add, 0, out_f32.data_ptr() if out_f32 is not None else None,
+                        out_u8.data_ptr() if out_u8 is not None else None)
+        op = Op()
+        op.kind = OP_TAILSUM
+        op.u.tailsum = d
+        self.ops.append(op)
+        self.keep += [z, out_f32, out_u8]
+        self.records.append(("tailsum", dict(z=z, r=r, bias=float(bias), mul=mul, add=add, out_f32=out_f32, out_u8=out_u8)))
 
     # ---- lifecycle ---------------------------------------------------------------------
     def finalize(self):

@@ -67,10 +67,33 @@ def run_records(plan):
                 B, N, H, Wd = acc.shape
                 cps = N // (rr * rr)
                 acc = acc.view(B, rr, rr, cps, H, Wd).permute(0, 3, 4, 1, 5, 2).reshape(B, cps, H * rr, Wd * rr)
+            if r.get("tail_z") is not None:
+                # acc is the pixel-shuffled post-activation map [B, C', H*r, W*r] (fp32): per-tap 1x1 projection, stored
+                # planar per sub-pixel:  z[b][s*9+t][y][x]
+                tw = r["tail_weight"]                                   # [9][C']
+                zt = torch.einsum("bchw,tc->bthw", acc, tw)             # [B, 9, H*r, W*r]
+                B_, _, Hh, Wh = zt.shape
+                zt = zt.view(B_, 9, Hh // rr, rr, Wh // rr, rr).permute(0, 3, 5, 1, 2, 4).reshape(B_, rr * rr * 9, Hh // rr, Wh // rr)
+                r["tail_z"].copy_(zt)
+                continue
             o = r["out"]
             if o is not None:
                 o.buf[..., o.choff:o.choff + acc.shape[1]] = acc.permute(0, 2, 3, 1).to(o.buf.dtype)
             if r["out_f32"] is not None:
                 r["out_f32"][..., :acc.shape[1]] = acc.permute(0, 2, 3, 1)
+        elif kind == "tailsum":
+            z, rr = r["z"], r["r"]
+            B_, _, H, W = z.shape
+            zh = z.view(B_, rr, rr, 9, H, W).permute(0, 3, 4, 1, 5, 2).reshape(B_, 9, H * rr, W * rr)   # zHR[b][t][Y][X]
+            zp = F.pad(zh, (1, 1, 1, 1))
+            acc = torch.full((B_, 1, H * rr, W * rr), r["bias"])
+            for t in range(9):
+                dy, dx = t // 3 - 1, t % 3 - 1
+                acc[:, 0] += zp[:, t, 1 + dy:1 + dy + H * rr, 1 + dx:1 + dx + W * rr]
+            y = acc * r["mul"] + r["add"]
+            if r["out_f32"] is not None:
+                r["out_f32"].copy_(y)
+            if r["out_u8"] is not None:
+                r["out_u8"].copy_(y.clamp(0, 255).to(torch.uint8))
         else:
             raise ValueError(kind)
