@@ -17,7 +17,8 @@
 // the epilogue.
 //
 // Warps: 0 = A producer (TMA rows), 1 = MMA issuer + TMEM owner, 2 = B producer (TMA weights), 3 idle,
-// 4..7 = epilogue (TMEM -> registers -> bias / act -> 16-bit NHWC stores, pixel-shuffle as addressing).
+// 4..11 = epilogue, two warps per TMEM lane quarter splitting the columns (TMEM -> registers -> bias / act ->
+// 16-bit NHWC stores with pixel-shuffle as addressing, or the fused Reconstruction tail).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -26,7 +27,7 @@
 
 namespace pssr {
 
-static constexpr int kSThreads = 256;
+static constexpr int kSThreads = 384;   // 4 control warps + 8 epilogue warps (two per TMEM lane quarter)
 static constexpr int kSMaxB = 8;
 
 struct StripKParams {
@@ -43,6 +44,8 @@ struct StripKParams {
   int rmax;                   // padded rows per A buffer
   uint32_t a_bytes, b_bytes;  // bytes per A buffer / per B stage
   int b_stages, tmem_bufs;
+  int G;                      // filter taps fetched per B stage for 3x3 segments (1, 3 or 9): fewer barrier round trips
+  uint32_t tap_bytes;         // bytes of one tap's weight block = block_n * 128
   int desc_mode;              // 0 (default): base_offset field = 0 -- measured on B200: the UMMA swizzle is a function of the
                               // absolute shared-memory address, a non-zero base offset double-applies the phase
   int dbg;                    // developer experiments (PSSR_DBG): 1 no stores, 2 no MMA, 4 no A loads, 8 no B loads
@@ -91,8 +94,11 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
     bias_s[i] = p.bias[i];
     if (p.out_scale != nullptr) scale_s[i] = p.out_scale[i];
   }
-  if (p.tail_w != nullptr)
-    for (int i = threadIdx.x; i < 9 * p.cps; i += kSThreads) tailw_s[i] = p.tail_w[i];
+  if (p.tail_w != nullptr)   // global [tap][c]  ->  shared [c/4][tap][c%4]
+    for (int i = threadIdx.x; i < 9 * p.cps; i += kSThreads) {
+      const int t = i / p.cps, c = i - t * p.cps;
+      tailw_s[((c >> 2) * 9 + t) * 4 + (c & 3)] = p.tail_w[i];
+    }
   const uint32_t bar0 = smem_u32(bars);
   auto a_full = [&](int s) { return bar0 + 8u * s; };
   auto a_empty = [&](int s) { return bar0 + 8u * (2 + s); };
@@ -104,7 +110,7 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(t_full(b), 1); mbar_init(t_empty(b), 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(t_full(b), 1); mbar_init(t_empty(b), 8); }
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), 512);
@@ -163,13 +169,16 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
         for (int sg = 0; sg < p.n_segs; ++sg) {
           const int taps = p.seg_taps[sg], cbs = p.seg_cblocks[sg];
           for (int cb = 0; cb < cbs; ++cb) {
-            for (int t = 0; t < taps; ++t) {
-              const int kb = p.seg_kb0[sg] + t * cbs + cb;   // weights are packed tap-major, then channel block
+            const int gs = taps == 9 ? p.G : 1;
+            for (int t0 = 0; t0 < taps; t0 += gs) {
               mbar_wait(b_empty(bs), bphase ^ 1u);
               if (p.dbg & 8) mbar_arrive(b_full(bs));
               else {
-                mbar_arrive_expect_tx(b_full(bs), p.b_bytes);
-                tma_load_2d(b_base + (uint32_t)bs * p.b_bytes, tmB, b_full(bs), kb * 64, n_tile * block_n);
+                mbar_arrive_expect_tx(b_full(bs), (uint32_t)gs * p.tap_bytes);
+                for (int t = 0; t < gs; ++t) {
+                  const int kb = p.seg_kb0[sg] + (t0 + t) * cbs + cb;   // weights are packed tap-major, then channel block
+                  tma_load_2d(b_base + (uint32_t)bs * p.b_bytes + (uint32_t)t * p.tap_bytes, tmB, b_full(bs), kb * 64, n_tile * block_n);
+                }
               }
               if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; }
             }
@@ -206,21 +215,16 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
           tc_fence_after();
           // descriptor of the unit's first pixel row in this A buffer; +8 per 128-byte row, +2 per 16 K elements
           const uint64_t adesc0 = strip_desc(a_base + (uint32_t)as * p.a_bytes + (uint32_t)row_off0 * 128u, 0);
-          for (int t = 0; t < taps; ++t) {
-            const int shift = taps == 9 ? (t / 3 - 1) * p.P + (t % 3 - 1) : 0;
+          const int gs = taps == 9 ? p.G : 1;
+          for (int t0 = 0; t0 < taps; t0 += gs) {
             mbar_wait(b_full(bs), bphase);
             tc_fence_after();
             if (elect_one()) {
-              const uint64_t bdesc = strip_desc(b_base + (uint32_t)bs * p.b_bytes, 0);
-              uint64_t adesc_t = adesc0 + (uint64_t)(long long)(shift * 8);
-              if (p.dbg & 16) adesc_t = strip_desc(a_base + (uint32_t)as * p.a_bytes, 0);   // experiment: 1024-aligned A start
-              if (p.dbg & 32) {   // experiment: alternate accumulators between consecutive MMAs
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  for (int mt = 0; mt < tv; ++mt)
-                    umma_f16(d0 + (uint32_t)(mt * block_n), adesc_t + (uint64_t)(mt * 128 * 8 + 2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                             (first && k == 0) ? 0u : 1u);
-              } else {
+              for (int tt = 0; tt < gs; ++tt) {
+                const int t = t0 + tt;
+                const int shift = taps == 9 ? (t / 3 - 1) * p.P + (t % 3 - 1) : 0;
+                const uint64_t bdesc = strip_desc(b_base + (uint32_t)bs * p.b_bytes + (uint32_t)tt * p.tap_bytes, 0);
+                const uint64_t adesc_t = adesc0 + (uint64_t)(long long)(shift * 8);
                 for (int mt = 0; mt < tv; ++mt) {
                   const uint64_t ad = adesc_t + (uint64_t)(mt * 128 * 8);
                   const uint32_t dcol = d0 + (uint32_t)(mt * block_n);
@@ -229,6 +233,7 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
                   umma_f16(dcol, ad + 4, bdesc + 4, idesc, 1u);
                   umma_f16(dcol, ad + 6, bdesc + 6, idesc, 1u);
                 }
+                first = 0;
               }
               umma_commit(b_empty(bs));
             }
@@ -247,8 +252,11 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
   } else if (warp >= 4) {
     // ==================================== epilogue ==========================================
     const int q4 = warp & 3;
+    const int eg = (warp - 4) >> 2;           // epilogue group 0 / 1
     const int row = q4 * 32 + lane;
     const int r = p.shuffle;
+    const int pw = p.tail_z != nullptr ? p.cps : 64;        // columns per work item (a whole sub-pixel in tail mode)
+    const int npairs = (block_n + pw - 1) / pw;
     int it = 0;
     for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x, ++it) {
       const int n_tile = unit % p.n_tiles;
@@ -260,7 +268,11 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
       const uint32_t use = p.tmem_bufs == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
       mbar_wait(t_full(buf), use & 1u);
       tc_fence_after();
-      for (int mt = 0; mt < tv; ++mt) {
+      for (int item = eg; item < tv * npairs; item += 2) {
+        const int mt = item / npairs;
+        const int pi = item - mt * npairs;
+        const int c_lo = pi * pw;
+        const int c_hi = c_lo + pw < block_n ? c_lo + pw : block_n;
         const int q = qa + mt * 128 + row;
         const int n = q / p.IP;
         const int rem = q - n * p.IP;
@@ -269,13 +281,13 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
         const bool valid = (q < p.q_end) && px >= 1 && px <= p.W && py >= 1 && py <= p.H;
         const int x = px - 1, y = py - 1;
         // sub-pixel / channel position of the unit's first output column, advanced incrementally (no divisions per chunk)
-        int sub = (n_tile * block_n) / p.cps;
-        int cc = n_tile * block_n - sub * p.cps;
+        int sub = (n_tile * block_n + c_lo) / p.cps;
+        int cc = n_tile * block_n + c_lo - sub * p.cps;
         int si = sub / r, sj = sub - si * r;
         const size_t pix00 = ((size_t)n * p.Hout + (size_t)(y * r)) * p.Wout + (size_t)(x * r);
         float zacc[9];
         const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * T * block_n + mt * block_n);
-        for (int c0 = 0; c0 < block_n; c0 += 32) {
+        for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + (uint32_t)c0, v);
           tmem_ld_wait();
@@ -298,19 +310,18 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
                 rr[4 * j4 + 2] = fmaxf(__uint_as_float(v[4 * j4 + 2]) + bb.z, 0.f);
                 rr[4 * j4 + 3] = fmaxf(__uint_as_float(v[4 * j4 + 3]) + bb.w, 0.f);
               }
+              // 9 independent accumulation chains interleaved (one per tap): weights are staged as [c/4][tap][4]
+              const float4* w4p = reinterpret_cast<const float4*>(tailw_s) + (ccb >> 2) * 9;
 #pragma unroll
-              for (int t = 0; t < 9; ++t) {
-                const float* wt = tailw_s + t * p.cps + ccb;
-                float a = zacc[t];
+              for (int j4 = 0; j4 < 8; ++j4) {
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                  const float4 w4 = *reinterpret_cast<const float4*>(wt + 4 * j4);
-                  a = fmaf(rr[4 * j4 + 0], w4.x, a);
-                  a = fmaf(rr[4 * j4 + 1], w4.y, a);
-                  a = fmaf(rr[4 * j4 + 2], w4.z, a);
-                  a = fmaf(rr[4 * j4 + 3], w4.w, a);
+                for (int t = 0; t < 9; ++t) {
+                  const float4 w4 = w4p[j4 * 9 + t];
+                  zacc[t] = fmaf(rr[4 * j4 + 0], w4.x, zacc[t]);
+                  zacc[t] = fmaf(rr[4 * j4 + 1], w4.y, zacc[t]);
+                  zacc[t] = fmaf(rr[4 * j4 + 2], w4.z, zacc[t]);
+                  zacc[t] = fmaf(rr[4 * j4 + 3], w4.w, zacc[t]);
                 }
-                zacc[t] = a;
               }
               if (ccb + 32 == p.cps) {
                 const int planes = r * r * 9;
@@ -325,7 +336,7 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int nn = nbase + h * 16;
-              if (h == 1 || c0 > 0) {   // advance the (sub-pixel, channel) cursor by 16 columns
+              if (h == 1 || c0 > c_lo) {   // advance the (sub-pixel, channel) cursor by 16 columns
                 cc += 16;
                 if (cc >= p.cps) { cc -= p.cps; if (++sj == r) { sj = 0; ++si; } }
               }
@@ -483,20 +494,35 @@ int strip_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
   if (T < 1) T = 1;
   const char* envT = getenv("PSSR_STRIP_T");
   if (envT) { int t = atoi(envT); if (t >= 1 && t * block_n <= 512) T = t; }
-  int rmax = 0, b_stages = 0;
+  int rmax = 0, b_stages = 0, G = 1;
+  bool has9 = false;
+  for (int s2 = 0; s2 < d.n_segs; ++s2) has9 = has9 || d.segs[s2].taps == 9;
+  const char* envG = getenv("PSSR_STRIP_G");
   for (;; --T) {
     rmax = (128 * T + 1) / p.P + 4;   // rows [floor((qa-P-1)/P), floor((qb+P)/P)] plus the overhang a partial last tile may read
     const long long a_bytes = (long long)rmax * p.P * 128;
     const long long a_total = ((2 * a_bytes + 1023) / 1024) * 1024;
-    b_stages = (int)((smem_cap - a_total) / (block_n * 128));
+    const long long left = smem_cap - a_total;
+    // taps per B stage: as many as still leave two stages (a stage holds G weight blocks on one barrier)
+    G = 1;
+    if (has9) {
+      for (int g : {9, 3}) {
+        if (envG && atoi(envG) != g) continue;
+        if (left >= 2LL * g * block_n * 128) { G = g; break; }
+      }
+      if (envG && atoi(envG) == 1) G = 1;
+    }
+    b_stages = (int)(left / ((long long)G * block_n * 128));
     if (b_stages > kSMaxB) b_stages = kSMaxB;
     if (b_stages >= 2 || T == 1) break;
   }
   PSSR_REQUIRE(b_stages >= 2, PSSR_EUNSUP, "conv: image width %d needs more shared memory than available for the strip kernel", d.Wo);
+  p.G = G;
+  p.tap_bytes = (uint32_t)(block_n * 128);
   p.T = T;
   p.rmax = rmax;
   p.a_bytes = (uint32_t)((((long long)rmax * p.P * 128 + 1023) / 1024) * 1024);
-  p.b_bytes = (uint32_t)(block_n * 128);
+  p.b_bytes = (uint32_t)(G * block_n * 128);
   p.b_stages = b_stages;
   p.tmem_bufs = (T * block_n <= 256) ? 2 : 1;
   const char* envm = getenv("PSSR_DESC_MODE");

@@ -220,7 +220,8 @@ int tail_launch(const pssr_tail_desc_t& d, int dtype, cudaStream_t stream) {
 // left at LR resolution (planar z[b][s*9+t][y][x]) at their shifted HR positions, add the bias, apply
 // x*128+128 (resunet.py:95) and emit fp32 + `_pred_array` uint8.  Pure streaming: ~r^2*9*4 B read and 5 B
 // written per LR pixel.
-__global__ void __launch_bounds__(256) tailsum_kernel(pssr_tailsum_desc_t d) {
+template <bool POW2>
+__global__ void __launch_bounds__(256) tailsum_kernel(pssr_tailsum_desc_t d, int lg) {
   const int Hh = d.H * d.r, Wh = d.W * d.r;
   const long long total = (long long)d.B * Hh * Wh;
   const size_t plane = (size_t)d.H * d.W;
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(256) tailsum_kernel(pssr_tailsum_desc_t d) {
     for (int t = 0; t < 9; ++t) {
       const int Yt = Y + t / 3 - 1, Xt = X + t % 3 - 1;
       if (Yt >= 0 && Yt < Hh && Xt >= 0 && Xt < Wh) {
-        const int y = Yt / d.r, x = Xt / d.r;
+        const int y = POW2 ? (Yt >> lg) : Yt / d.r, x = POW2 ? (Xt >> lg) : Xt / d.r;
         const int s = (Yt - y * d.r) * d.r + (Xt - x * d.r);
         acc += __ldg(zb + (size_t)(s * 9 + t) * plane + (size_t)y * d.W + x);
       }
@@ -252,7 +253,10 @@ int tailsum_launch(const pssr_tailsum_desc_t& d, cudaStream_t stream) {
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)device_sm_count() * 32;
   if (blocks > cap) blocks = cap;
-  tailsum_kernel<<<(int)blocks, 256, 0, stream>>>(d);
+  int lg = 0;
+  while ((1 << lg) < d.r) ++lg;
+  if ((1 << lg) == d.r) tailsum_kernel<true><<<(int)blocks, 256, 0, stream>>>(d, lg);
+  else tailsum_kernel<false><<<(int)blocks, 256, 0, stream>>>(d, lg);
   count_launch();
   PSSR_CHECK_CUDA(cudaGetLastError());
   return PSSR_OK;
