@@ -147,6 +147,7 @@ int pssr_resize_bilinear(const void* src, void* dst, int32_t n, int32_t h, int32
 #define PSSR_OP_ESE 7         /* EffectiveSE gate + layer-scale gamma                       */
 #define PSSR_OP_COPY 8        /* channel-slice copy between NHWC buffers                    */
 #define PSSR_OP_TAILSUM 9     /* 9-tap gather of the fused Reconstruction tail + *128+128   */
+#define PSSR_OP_STEM 10       /* RDNet PatchifyStem: normalise + patch conv + LayerNorm2d   */
 
 /* One NHWC source view of an implicit-GEMM op. */
 typedef struct {
@@ -237,6 +238,45 @@ typedef struct {
   uint8_t* out_u8;       /* [B][H*r][W*r] or NULL                                             */
 } pssr_tailsum_desc_t;
 
+/* ---- RDNet encoder ops (pssr/models/_rdnet.py) ---------------------------------------------- */
+/* PSSR_OP_STEM: x/128-1 -> BatchNorm(eval) -> PatchifyStem conv (kernel = stride = patch, _rdnet.py:106-116)
+ * -> LayerNorm2d over channels (timm, eps 1e-6).  Output NHWC 16-bit [B][H/patch][W/patch][.].        */
+typedef struct {
+  const void* x; int32_t x_u8; int32_t B, C, H, W;
+  const float* in_scale; const float* in_shift;     /* [C] folded input BatchNorm                      */
+  int32_t patch, Cout;
+  const float* weight;   /* [Cout][C*patch*patch] fp32                                               */
+  const float* bias; const float* ln_w; const float* ln_b; float eps; int32_t reserved;
+  void* out; int32_t out_cstride, out_choff;
+} pssr_stem_desc_t;
+
+/* PSSR_OP_LAYERNORM: LayerNorm2d over C of an NHWC 16-bit view (transition layers, _rdnet.py:57-58).  With
+ * s2d = 2 the output is space-to-depth'ed: [B][H/2][W/2][(dy*2+dx)*C + c], which turns the following 2x2
+ * stride-2 transition conv (_rdnet.py:59-62) into a 1x1 GEMM.                                           */
+typedef struct {
+  const void* in; int32_t in_cstride, in_choff, C; int32_t B, H, W; int32_t s2d;
+  const float* w; const float* b; float eps; int32_t reserved;
+  void* out; int32_t out_cstride, out_choff;
+} pssr_ln_desc_t;
+
+/* PSSR_OP_DWCONV_LN: depthwise 7x7 conv (pad 3) + bias + LayerNorm2d (Block, _rdnet.py:181-183).     */
+typedef struct {
+  const void* in; int32_t in_cstride, in_choff, C; int32_t B, H, W; int32_t reserved;
+  const float* dw_w;     /* [49][C] fp32                                                             */
+  const float* dw_b; const float* ln_w; const float* ln_b; float eps; int32_t reserved2;
+  void* out; int32_t out_cstride, out_choff;
+} pssr_dwln_desc_t;
+
+/* PSSR_OP_ESE: EffectiveSEModule (timm) + layer-scale gamma (_rdnet.py:172-174,200-202):
+ * out[b][y][x][choff+c] = in[b][y][x][c] * hardsigmoid(fc(mean_yx in[b]))[c] * gamma[c].               */
+typedef struct {
+  const void* in; int32_t in_cstride, C; int32_t B, H, W; int32_t reserved;
+  const float* fc_w;     /* [C][C] fp32                                                              */
+  const float* fc_b; const float* gamma;
+  float* gate_ws;        /* [B][C] fp32 scratch                                                      */
+  void* out; int32_t out_cstride, out_choff;
+} pssr_ese_desc_t;
+
 typedef struct {
   int32_t kind;          /* PSSR_OP_*                                                       */
   int32_t reserved;
@@ -246,6 +286,10 @@ typedef struct {
     pssr_pool_desc_t pool;
     pssr_tail_desc_t tail;
     pssr_tailsum_desc_t tailsum;
+    pssr_stem_desc_t stem;
+    pssr_ln_desc_t ln;
+    pssr_dwln_desc_t dwln;
+    pssr_ese_desc_t ese;
     uint8_t pad[512];
   } u;
 } pssr_op_t;

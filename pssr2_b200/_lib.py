@@ -13,7 +13,7 @@ from ctypes import (POINTER, Structure, Union, c_char_p, c_double, c_float, c_in
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libpssr_b200.so")
-SOURCES = ["api.cu", "conv_igemm.cu", "conv_strip.cu", "net_aux.cu", "crappify.cu", "stitch.cu", "metrics.cu"]
+SOURCES = ["api.cu", "conv_igemm.cu", "conv_strip.cu", "net_aux.cu", "rdnet.cu", "crappify.cu", "stitch.cu", "metrics.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
@@ -115,8 +115,33 @@ class TailSumDesc(Structure):
                 ("mul", c_float), ("add", c_float), ("reserved", c_int32), ("out_f32", c_void_p), ("out_u8", c_void_p)]
 
 
+class StemDesc(Structure):
+    _fields_ = [("x", c_void_p), ("x_u8", c_int32), ("B", c_int32), ("C", c_int32), ("H", c_int32), ("W", c_int32),
+                ("in_scale", c_void_p), ("in_shift", c_void_p), ("patch", c_int32), ("Cout", c_int32), ("weight", c_void_p),
+                ("bias", c_void_p), ("ln_w", c_void_p), ("ln_b", c_void_p), ("eps", c_float), ("reserved", c_int32),
+                ("out", c_void_p), ("out_cstride", c_int32), ("out_choff", c_int32)]
+
+
+class LnDesc(Structure):
+    _fields_ = [("in_", c_void_p), ("in_cstride", c_int32), ("in_choff", c_int32), ("C", c_int32), ("B", c_int32), ("H", c_int32),
+                ("W", c_int32), ("s2d", c_int32), ("w", c_void_p), ("b", c_void_p), ("eps", c_float), ("reserved", c_int32),
+                ("out", c_void_p), ("out_cstride", c_int32), ("out_choff", c_int32)]
+
+
+class DwLnDesc(Structure):
+    _fields_ = [("in_", c_void_p), ("in_cstride", c_int32), ("in_choff", c_int32), ("C", c_int32), ("B", c_int32), ("H", c_int32),
+                ("W", c_int32), ("reserved", c_int32), ("dw_w", c_void_p), ("dw_b", c_void_p), ("ln_w", c_void_p), ("ln_b", c_void_p),
+                ("eps", c_float), ("reserved2", c_int32), ("out", c_void_p), ("out_cstride", c_int32), ("out_choff", c_int32)]
+
+
+class EseDesc(Structure):
+    _fields_ = [("in_", c_void_p), ("in_cstride", c_int32), ("C", c_int32), ("B", c_int32), ("H", c_int32), ("W", c_int32),
+                ("reserved", c_int32), ("fc_w", c_void_p), ("fc_b", c_void_p), ("gamma", c_void_p), ("gate_ws", c_void_p),
+                ("out", c_void_p), ("out_cstride", c_int32), ("out_choff", c_int32)]
+
+
 class _OpU(Union):
-    _fields_ = [("conv", ConvDesc), ("prep", PrepDesc), ("pool", PoolDesc), ("tail", TailDesc), ("tailsum", TailSumDesc),
+    _fields_ = [("conv", ConvDesc), ("prep", PrepDesc), ("pool", PoolDesc), ("tail", TailDesc), ("tailsum", TailSumDesc), ("stem", StemDesc), ("ln", LnDesc), ("dwln", DwLnDesc), ("ese", EseDesc),
                 ("pad", c_uint8 * 512)]
 
 
@@ -125,6 +150,7 @@ class Op(Structure):
 
 
 OP_CONV, OP_PREP, OP_MAXPOOL, OP_TAIL, OP_TAILSUM = 1, 2, 3, 4, 9
+OP_DWCONV_LN, OP_LAYERNORM, OP_ESE, OP_STEM = 5, 6, 7, 10
 DT_BF16, DT_FP16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 NOISE_POISSON, NOISE_GAUSSIAN, NOISE_SALTPEPPER = 1, 2, 3

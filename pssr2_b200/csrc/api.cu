@@ -70,6 +70,10 @@ int pssr_plan_create(const pssr_op_t* ops, int32_t n_ops, int32_t dtype, pssr_pl
       case PSSR_OP_MAXPOOL:
       case PSSR_OP_TAIL:
       case PSSR_OP_TAILSUM:
+      case PSSR_OP_STEM:
+      case PSSR_OP_LAYERNORM:
+      case PSSR_OP_DWCONV_LN:
+      case PSSR_OP_ESE:
         break;
       default:
         set_error("plan_create: op %d has unsupported kind %d", i, op.kind);
@@ -125,6 +129,18 @@ int pssr_plan_run_range(pssr_plan_t* plan, int32_t first, int32_t count, void* s
         break;
       case PSSR_OP_TAILSUM:
         rc = tailsum_launch(op.u.tailsum, st);
+        break;
+      case PSSR_OP_STEM:
+        rc = stem_launch(op.u.stem, plan->dtype, st);
+        break;
+      case PSSR_OP_LAYERNORM:
+        rc = ln_launch(op.u.ln, plan->dtype, st);
+        break;
+      case PSSR_OP_DWCONV_LN:
+        rc = dwln_launch(op.u.dwln, plan->dtype, st);
+        break;
+      case PSSR_OP_ESE:
+        rc = ese_launch(op.u.ese, plan->dtype, st);
         break;
       default:
         set_error("plan_run: op %d has unsupported kind %d", i, op.kind);

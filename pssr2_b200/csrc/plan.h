@@ -25,6 +25,10 @@ int prep_launch(const pssr_prep_desc_t& d, int dtype, cudaStream_t stream);
 int pool_launch(const pssr_pool_desc_t& d, int dtype, cudaStream_t stream);
 int tail_launch(const pssr_tail_desc_t& d, int dtype, cudaStream_t stream);
 int tailsum_launch(const pssr_tailsum_desc_t& d, cudaStream_t stream);
+int stem_launch(const pssr_stem_desc_t& d, int dtype, cudaStream_t stream);
+int ln_launch(const pssr_ln_desc_t& d, int dtype, cudaStream_t stream);
+int dwln_launch(const pssr_dwln_desc_t& d, int dtype, cudaStream_t stream);
+int ese_launch(const pssr_ese_desc_t& d, int dtype, cudaStream_t stream);
 
 }  // namespace pssr
 

@@ -136,6 +136,38 @@ class _PlanModule(nn.Module):
         return st["out"], st["out_u8"]
 
     # helpers used by subclasses ---------------------------------------------------------
+    def _emit_reconstruction(self, plan, final, xcol, B, H, W, dev):
+        """Reconstruction (resunet.py:90-95, _blocks.py:15-18): cat([x, xnorm]) -> pre -> relu -> shuffle(s) -> conv -> *128+128."""
+        dt = plan.tdtype
+        z = lambda *sh: torch.zeros(*sh, dtype=dt, device=dev)
+        s = self.scale
+        hid0 = final.shape[3]
+        rec = self.reconstruction
+        wp = rec.pre.weight.detach().float()
+        bp = rec.pre.bias.detach().float()
+        parts = [wp[:, :hid0], _im2col_parts(wp[:, hid0:])]
+        wpk = pack_weight(parts, plan.dtype, s)
+        wc = rec.conv.weight.detach().float()
+        bc = rec.conv.bias.detach().float().contiguous()
+        cout = wc.shape[0]
+        out = torch.empty(B, cout, H * s, W * s, dtype=torch.float32, device=dev)
+        out_u8 = torch.empty(B, 1, H * s, W * s, dtype=torch.uint8, device=dev)
+        srcs, segs = [View(final), xcol], [(0, 9, ceil_div(hid0, 64)), (1, 1, 1)]
+        plan.flops += 2 * wp.numel() * B * H * W + 2 * wc.numel() * B * H * s * W * s
+        if cout == 1 and hid0 % 32 == 0 and W >= 1 and self.fuse_tail:
+            # fused tail: relu(pre) is reduced against the 3x3 tail weights inside the conv epilogue (fp32), the
+            # scale^2*hidden-channel HR map is never written; PSSR_OP_TAILSUM gathers the 9 taps (see include/pssr_b200.h)
+            tw = wc[0].permute(1, 2, 0).reshape(9, hid0).contiguous()      # [tap][c]
+            zbuf = torch.zeros(B, s * s * 9, H, W, dtype=torch.float32, device=dev)
+            plan.conv(srcs, segs, wpk, permute_n(bp, s).contiguous(), None, Ho=H, Wo=W, B=B, shuffle=s, act=ACT_RELU,
+                      tail_weight=tw, tail_z=zbuf)
+            plan.tailsum(zbuf, s, float(bc[0]), 128.0, 128.0, out, out_u8)    # x*128+128 (resunet.py:95)
+        else:
+            ps_out = z(B, H * s, W * s, hid0)
+            plan.conv(srcs, segs, wpk, permute_n(bp, s).contiguous(), View(ps_out), Ho=H, Wo=W, B=B, shuffle=s, act=ACT_RELU)
+            plan.tail(View(ps_out), wc.permute(0, 2, 3, 1).contiguous(), bc, 128.0, 128.0, out, out_u8)
+        self._out, self._out_u8 = out, out_u8
+
     @staticmethod
     def _emit_resblock(plan, blk, srcs, seg_spec, w0_parts_fn, wr_parts_fn, scratch, dst, shuffle, B, H, W):
         """Emits the convs of one ResBlock.
@@ -309,30 +341,299 @@ class ResUNet(_PlanModule):
                 dst, shf = View(final), 1
             self._emit_resblock(plan, blk, srcs, segs, w0f, wrf, scratch(l), dst, shf, B, h, w)
 
-        # Reconstruction (resunet.py:90-95, _blocks.py:15-18): cat([x, xnorm]) -> pre -> relu -> shuffle(s) -> conv
-        rec = self.reconstruction
-        wp = rec.pre.weight.detach().float()
-        bp = rec.pre.bias.detach().float()
-        parts = [wp[:, :hid[0]], _im2col_parts(wp[:, hid[0]:])]
-        wpk = pack_weight(parts, plan.dtype, s)
-        wc = rec.conv.weight.detach().float()
-        bc = rec.conv.bias.detach().float().contiguous()
-        cout = wc.shape[0]
-        out = torch.empty(B, cout, H * s, W * s, dtype=torch.float32, device=dev)
-        out_u8 = torch.empty(B, 1, H * s, W * s, dtype=torch.uint8, device=dev)
-        srcs, segs = [View(final), xcol], [(0, 9, ceil_div(hid[0], 64)), (1, 1, 1)]
-        plan.flops += 2 * wp.numel() * B * H * W + 2 * wc.numel() * B * H * s * W * s
-        if cout == 1 and hid[0] % 32 == 0 and W >= 1 and self.fuse_tail:
-            # fused tail: relu(pre) is reduced against the 3x3 tail weights inside the conv epilogue (fp32), the
-            # scale^2*hidden-channel HR map is never written; PSSR_OP_TAILSUM gathers the 9 taps (see include/pssr_b200.h)
-            tw = wc[0].permute(1, 2, 0).reshape(9, hid[0]).contiguous()      # [tap][c]
-            zbuf = torch.zeros(B, s * s * 9, H, W, dtype=torch.float32, device=dev)
-            plan.conv(srcs, segs, wpk, permute_n(bp, s).contiguous(), None, Ho=H, Wo=W, B=B, shuffle=s, act=ACT_RELU,
-                      tail_weight=tw, tail_z=zbuf)
-            plan.tailsum(zbuf, s, float(bc[0]), 128.0, 128.0, out, out_u8)    # x*128+128 (resunet.py:95)
-        else:
-            ps_out = z(B, H * s, W * s, hid[0])
-            plan.conv(srcs, segs, wpk, permute_n(bp, s).contiguous(), View(ps_out), Ho=H, Wo=W, B=B, shuffle=s, act=ACT_RELU)
-            plan.tail(View(ps_out), wc.permute(0, 2, 3, 1).contiguous(), bc, 128.0, 128.0, out, out_u8)
+        self._emit_reconstruction(plan, final, xcol, B, H, W, dev)
+        out, out_u8 = self._out, self._out_u8
         plan.finalize()
         return {"plan": plan, "x": x_in, "out": out, "out_u8": out_u8}
+
+
+# =============================================================================== RDResUNet
+class LayerNorm2d(nn.Module):
+    """Parameter container for timm.layers.LayerNorm2d (weight, bias; LayerNorm over C of NCHW, eps 1e-6)."""
+
+    def __init__(self, num_channels, eps=1e-6):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(num_channels))
+        self.bias = nn.Parameter(torch.zeros(num_channels))
+        self.eps = eps
+
+
+class EffectiveSEModule(nn.Module):
+    """Parameter container for timm.layers.EffectiveSEModule (fc = 1x1 conv, hard-sigmoid gate)."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.fc = nn.Conv2d(channels, channels, kernel_size=1, padding=0)
+
+
+class _RDBlock(nn.Module):
+    """Block / BlockESE (pssr/models/_rdnet.py:177-206): layers.{0 dw7x7, 1 LN, 2 1x1, 3 GELU, 4 1x1[, 5 eSE]}."""
+
+    def __init__(self, in_chs, inter_chs, out_chs, ese):
+        super().__init__()
+        mods = [nn.Conv2d(in_chs, in_chs, groups=in_chs, kernel_size=7, stride=1, padding=3), LayerNorm2d(in_chs, eps=1e-6),
+                nn.Conv2d(in_chs, inter_chs, kernel_size=1), nn.GELU(), nn.Conv2d(inter_chs, out_chs, kernel_size=1)]
+        if ese:
+            mods.append(EffectiveSEModule(out_chs))
+        self.layers = nn.Sequential(*mods)
+
+
+class DenseBlock(nn.Module):
+    """pssr/models/_rdnet.py:140-175: gamma (layer scale) + Block."""
+
+    def __init__(self, num_input_features, growth_rate, bottleneck_width_ratio, ese, ls_init_value=1e-6):
+        super().__init__()
+        self.growth_rate = growth_rate
+        self.gamma = nn.Parameter(ls_init_value * torch.ones(growth_rate)) if ls_init_value > 0 else None
+        inter_chs = int(num_input_features * bottleneck_width_ratio / 8) * 8
+        self.drop_path = nn.Identity()
+        self.layers = _RDBlock(num_input_features, inter_chs, int(growth_rate), ese)
+        self.in_chs, self.inter_chs = num_input_features, inter_chs
+
+
+class DenseStage(nn.Sequential):
+    """pssr/models/_rdnet.py:118-138."""
+
+    def __init__(self, num_block, num_input_features, growth_rate, bottleneck_width_ratio, ese, ls_init_value):
+        super().__init__()
+        for i in range(num_block):
+            self.add_module(f"dense_block{i}", DenseBlock(num_input_features, growth_rate, bottleneck_width_ratio, ese, ls_init_value))
+            num_input_features += growth_rate
+        self.num_out_features = num_input_features
+
+
+class PatchifyStem(nn.Module):
+    """pssr/models/_rdnet.py:106-116."""
+
+    def __init__(self, cin, cout, patch_size):
+        super().__init__()
+        self.stem = nn.Sequential(nn.Conv2d(cin, cout, kernel_size=patch_size, stride=patch_size), LayerNorm2d(cout))
+
+
+class RDNet(nn.Module):
+    """Parameter container for the RDNet encoder (pssr/models/_rdnet.py:15-104)."""
+
+    def __init__(self, in_channels, n_init_features, patch_size, growth_rates, ds_blocks, ese_blocks, n_blocks, bottleneck_width_ratio,
+                 drop_path_rate, transition_compression_ratio, ls_init_value=1e-6):
+        super().__init__()
+        n_blocks = [n_blocks] * len(growth_rates) if type(n_blocks) is int else list(n_blocks)
+        if not len(growth_rates) == len(ds_blocks):
+            raise ValueError(f"growth_rates and ds_blocks must have the same length. Given values are {len(growth_rates)} and {len(ds_blocks)} respectively.")
+        if not len(growth_rates) == len(ese_blocks):
+            raise ValueError(f"growth_rates and block_type must have the same length. Given values are {len(growth_rates)} and {len(ese_blocks)} respectively.")
+        if not len(growth_rates) == len(n_blocks):
+            raise ValueError(f"growth_rates and n_blocks must have the same length. Given values are {len(growth_rates)} and {len(n_blocks)} respectively.")
+        self.stem = PatchifyStem(in_channels, n_init_features, patch_size)
+        self.feature_info = []
+        num_features = n_init_features
+        curr_stride = 4
+        stages = []
+        for i in range(len(growth_rates)):
+            layers = []
+            if i != 0:
+                compressed = int(num_features * transition_compression_ratio / 8) * 8
+                k = 1
+                if ds_blocks[i]:
+                    curr_stride *= 2
+                    k = 2
+                layers.append(LayerNorm2d(num_features))
+                layers.append(nn.Conv2d(num_features, compressed, kernel_size=k, stride=k, padding=0))
+                num_features = compressed
+            layers.append(DenseStage(n_blocks[i], num_features, growth_rates[i], bottleneck_width_ratio, bool(ese_blocks[i]), ls_init_value))
+            num_features += n_blocks[i] * growth_rates[i]
+            if i + 1 == len(growth_rates) or ds_blocks[i + 1]:
+                self.feature_info.append(dict(num_chs=num_features, reduction=curr_stride, module=f"dense_stages.{i}", growth_rate=growth_rates[i]))
+            stages.append(nn.Sequential(*layers))
+        self.dense_stages = nn.ModuleList(stages)
+        self.ds_blocks = list(ds_blocks)
+        self.patch_size = patch_size
+        # same initialisation walk as the reference (named_apply(_init_weights), _rdnet.py:90,208-213)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight)
+
+
+class RDResUNet(_PlanModule):
+    """RDNet encoder + ResUNet decoder + upscaling block (pssr/models/rdresunet.py:8-133), default (non-atrous) path."""
+
+    def __init__(self, channels=1, hidden=[1024, 1024, 512, 256], scale=4, depth=3, dilations=None, pool_sizes=None, encoder_pool=False,
+                 rdnet_init=128, growth_rates=[64, 104, 128, 128, 128, 128, 224], ds_blocks=[False, True, True, False, False, False, True],
+                 ese_blocks=[False, False, True, True, True, True, True], n_blocks=[3, 3, 3, 3, 3, 3, 3], patch_size=2, bottleneck=4,
+                 compression=0.5, drop_rate=0):
+        super().__init__()
+        channels = _force_list(channels)
+        channels = channels * 2 if len(channels) == 1 else channels
+        if dilations or pool_sizes or encoder_pool:
+            raise NotImplementedError("pssr2_b200.RDResUNet implements the default residual decoder; the atrous / PSP-pooling variants "
+                                      "are outside the accelerated hot path")
+        hidden = list(hidden)
+        self.norm = nn.BatchNorm2d(channels[0])
+        if sum(ds_blocks) != len(hidden) - 1:
+            raise ValueError(f"Number of downsampling blocks must be one less than ResUNet hidden layers. Given {sum(ds_blocks)} downsampling blocks but {len(hidden)} hidden layers.")
+        self.encoder = RDNet(channels[0], rdnet_init, patch_size, growth_rates, ds_blocks, ese_blocks, n_blocks, bottleneck, drop_rate, compression)
+        skips = [f["num_chs"] for f in self.encoder.feature_info]
+        skips.reverse()
+        if len(skips) != len(hidden):
+            raise ValueError(f"Each encoder skip connection must have a corresponding decoder hidden layer. There are {len(skips)} skip connections but {len(hidden)} hidden layers.")
+        self.ratios = [1] + [2] * (len(skips) - 1) + [patch_size]
+        layers = [0, *hidden]
+        self.decoder = nn.ModuleList()
+        for i in range(len(layers) - 1):
+            self.decoder.append(ResBlock(layers[i] // self.ratios[i] ** 2 + skips[i], layers[i + 1], depth))
+        self.encoder_pool = None
+        self.reconstruction_pool = None
+        self.reconstruction = Reconstruction(channels[0], channels[1], hidden[-1] // self.ratios[-1] ** 2, scale)
+        self.skips = skips
+        self.channels, self.hidden, self.scale, self.patch_size = channels, hidden, scale, patch_size
+
+    def extra_repr(self):
+        return (f"RDResUNet with {self.reconstruction.scale}x upscaling\n{len(self.decoder)} residual blocks with {self.decoder[0].depth} "
+                f"hidden layers each\nSkip connection sizes: {self.skips}\nPSP pooling disabled")
+
+    # -------------------------------------------------------------------------------------
+    def _build(self, shape, in_dtype, dev):
+        from .plan import ACT_GELU
+        B, C, H, W = shape
+        enc, hid, s, pch = self.encoder, self.hidden, self.scale, self.patch_size
+        if C != self.channels[0]:
+            raise ValueError(f"expected {self.channels[0]} input channels, got {C}")
+        n_ds = sum(enc.ds_blocks)
+        if H % (pch << n_ds) or W % (pch << n_ds):
+            raise ValueError(f"input size {H}x{W} must be divisible by {pch << n_ds}")
+        plan = Plan(self.precision)
+        dt = plan.tdtype
+        z = lambda *sh: torch.zeros(*sh, dtype=dt, device=dev)
+        f32 = lambda t: t.detach().float().contiguous()
+        x_in = torch.zeros(B, C, H, W, dtype=in_dtype, device=dev)
+        bn = self.norm
+        sc = (bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + bn.eps)).contiguous()
+        sh = (bn.bias.detach().float() - bn.running_mean.float() * sc).contiguous()
+        im2col = z(B, H, W, 64)
+        plan.prep(x_in, sc, sh, im2col)
+        xcol = View(im2col, 0, 64)
+
+        # ---- encoder geometry: which stage outputs are decoder skips, and where they live -----------------
+        n_st = len(enc.dense_stages)
+        stage_mods = [list(st) for st in enc.dense_stages]
+        ctot, cin_st, hw = [], [], []
+        h, w = H // pch, W // pch
+        for i, mods in enumerate(stage_mods):
+            if i != 0 and enc.ds_blocks[i]:
+                h, w = h // 2, w // 2
+            ds = mods[-1]
+            first = ds.dense_block0
+            cin_st.append(first.in_chs)
+            ctot.append(ds.num_out_features)
+            hw.append((h, w))
+        skip_stage = [i for i in range(n_st) if i + 1 == n_st or enc.ds_blocks[i + 1]]     # shallow -> deep
+        n_dec = len(self.decoder)
+        assert len(skip_stage) == n_dec
+        dec_of_stage = {st: n_dec - 1 - k for k, st in enumerate(skip_stage)}            # decoder index consuming this skip
+        up = [0] + [hid[k - 1] // self.ratios[k] ** 2 for k in range(1, n_dec)]
+        for k in range(1, n_dec):
+            if up[k] % 8:
+                raise NotImplementedError("decoder widths must keep 8-channel alignment after pixel shuffle")
+        cat = {}
+        stage_view = []
+        for i in range(n_st):
+            hh, ww = hw[i]
+            if i in dec_of_stage:
+                k = dec_of_stage[i]
+                buf = z(B, hh, ww, up[k] + ctot[i])
+                cat[k] = buf
+                stage_view.append(View(buf, up[k], ctot[i]))
+            else:
+                stage_view.append(View(z(B, hh, ww, ctot[i])))
+
+        def sub(v: View, c0, c):      # channel slice of a view
+            return View(v.buf, v.choff + c0, c)
+
+        # ---- stem (_rdnet.py:106-116) ---------------------------------------------------------------------
+        st0 = enc.stem.stem
+        plan.stem(x_in, sc, sh, pch, f32(st0[0].weight).reshape(st0[0].weight.shape[0], -1).contiguous(), f32(st0[0].bias), f32(st0[1].weight),
+                  f32(st0[1].bias), st0[1].eps, sub(stage_view[0], 0, cin_st[0]))
+        max_px = max(B * a * b for a, b in hw)
+        max_c = max(max(blk.in_chs for blk in mods[-1]) for mods in stage_mods)
+        max_inter = max(max(blk.inter_chs for blk in mods[-1]) for mods in stage_mods)
+        max_g = max(mods[-1].dense_block0.growth_rate for mods in stage_mods)
+        dw_pool = torch.zeros(max(B * a * b * max(blk.in_chs for blk in m[-1]) for (a, b), m in zip(hw, stage_mods)), dtype=dt, device=dev)
+        mid_pool = torch.zeros(max(B * a * b * max(blk.inter_chs for blk in m[-1]) for (a, b), m in zip(hw, stage_mods)), dtype=dt, device=dev)
+        g_pool = torch.zeros(max_px * max_g, dtype=dt, device=dev)
+        ln_pool = torch.zeros(max(B * a * b * c for (a, b), c in zip(hw, ctot)), dtype=dt, device=dev)
+        gate_ws = torch.zeros(B * max_g, dtype=torch.float32, device=dev)
+
+        def pad_n(wt, bias, n_pad, extra=None):
+            co = wt.shape[0]
+            if n_pad > co:
+                bias = torch.cat([bias, torch.zeros(n_pad - co, device=dev)])
+                if extra is not None:
+                    extra = torch.cat([extra, torch.zeros(n_pad - co, device=dev)])
+            return pack_weight([wt], plan.dtype, 1, n_pad), bias.contiguous(), (extra.contiguous() if extra is not None else None)
+
+        def r32(v):
+            return ceil_div(v, 32) * 32
+
+        for i, mods in enumerate(stage_mods):
+            hh, ww = hw[i]
+            sv = stage_view[i]
+            if i != 0:
+                # transition: LayerNorm2d + conv (k = stride = 1 or 2); the 2x2 stride-2 conv runs as a 1x1 GEMM on
+                # the space-to-depth'ed LayerNorm output
+                ln, cv = mods[0], mods[1]
+                k = cv.kernel_size[0]
+                prev = stage_view[i - 1]
+                cprev = ctot[i - 1]
+                lnb = ln_pool[:B * hh * ww * k * k * cprev].view(B, hh, ww, k * k * cprev)
+                plan.layernorm(prev, f32(ln.weight), f32(ln.bias), ln.eps, View(lnb), s2d=k)
+                wt = f32(cv.weight).permute(0, 2, 3, 1).reshape(cv.weight.shape[0], k * k * cprev, 1, 1)
+                cout = wt.shape[0]
+                wp, bp, _ = pad_n(wt, f32(cv.bias), r32(cout))
+                plan.conv([View(lnb)], [(0, 1, ceil_div(k * k * cprev, 64))], wp, bp, sub(sv, 0, cout), Ho=hh, Wo=ww, B=B, n_valid=cout)
+                plan.flops += 2 * wt.numel() * B * hh * ww
+            for j, blk in enumerate(mods[-1]):
+                L = blk.layers.layers
+                ck, inter, g = blk.in_chs, blk.inter_chs, blk.growth_rate
+                xin = sub(sv, 0, ck)
+                dwb = dw_pool[:B * hh * ww * ck].view(B, hh, ww, ck)
+                plan.dwconv_ln(xin, f32(L[0].weight).view(ck, 49).t().contiguous(), f32(L[0].bias), f32(L[1].weight), f32(L[1].bias), L[1].eps, View(dwb))
+                midb = mid_pool[:B * hh * ww * inter].view(B, hh, ww, inter)
+                w1, b1, _ = pad_n(f32(L[2].weight), f32(L[2].bias), r32(inter))
+                plan.conv([View(dwb)], [(0, 1, ceil_div(ck, 64))], w1, b1, View(midb), Ho=hh, Wo=ww, B=B, n_valid=inter, act=ACT_GELU)
+                gamma = f32(blk.gamma) if blk.gamma is not None else None
+                dst = sub(sv, ck, g)
+                has_ese = len(L) > 5
+                w2, b2, gpad = pad_n(f32(L[4].weight), f32(L[4].bias), r32(g), None if has_ese else gamma)
+                if has_ese:
+                    gb = g_pool[:B * hh * ww * g].view(B, hh, ww, g)
+                    plan.conv([View(midb)], [(0, 1, ceil_div(inter, 64))], w2, b2, View(gb), Ho=hh, Wo=ww, B=B, n_valid=g)
+                    plan.ese(View(gb), f32(L[5].fc.weight).view(g, g).contiguous(), f32(L[5].fc.bias), gamma, gate_ws, dst)
+                else:
+                    plan.conv([View(midb)], [(0, 1, ceil_div(inter, 64))], w2, b2, dst, Ho=hh, Wo=ww, B=B, n_valid=g, out_scale=gpad)
+                plan.flops += 2 * (L[2].weight.numel() + L[4].weight.numel() + 49 * ck) * B * hh * ww
+
+        # ---- decoder (rdresunet.py:115-120) -------------------------------------------------------------------
+        deep = skip_stage[-1]
+        dec_in = {0: stage_view[deep]}
+        for k in range(1, n_dec):
+            dec_in[k] = View(cat[k])
+        dec_hw = {dec_of_stage[st]: hw[st] for st in skip_stage}
+        scratch_elems = max(B * dec_hw[k][0] * dec_hw[k][1] * hid[k] for k in range(n_dec))
+        sbuf = [torch.zeros(scratch_elems, dtype=dt, device=dev) for _ in range(2)]
+        final = z(B, H, W, hid[-1] // self.ratios[-1] ** 2)
+        for k in range(n_dec):
+            hh, ww = dec_hw[k]
+            blk = self.decoder[k]
+            cin = dec_in[k].channels
+            srcs, segs = [dec_in[k]], [(0, 9, ceil_div(cin, 64))]
+            w0f = lambda wt: [wt]
+            wrf = (lambda cin: (lambda wt: ([wt], [(0, 1, ceil_div(cin, 64))])))(cin)
+            n = B * hh * ww * hid[k]
+            scr = [sb[:n].view(B, hh, ww, hid[k]) for sb in sbuf]
+            shf = self.ratios[k + 1]
+            dst = View(cat[k + 1], 0, up[k + 1]) if k + 1 < n_dec else View(final)
+            self._emit_resblock(plan, blk, srcs, segs, w0f, wrf, scr, dst, shf, B, hh, ww)
+
+        # ---- Reconstruction (rdresunet.py:125-130) -----------------------------------------------------------
+        self._emit_reconstruction(plan, final, xcol, B, H, W, dev)
+        plan.finalize()
+        return {"plan": plan, "x": x_in, "out": self._out, "out_u8": self._out_u8}

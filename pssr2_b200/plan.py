@@ -11,8 +11,9 @@ import math
 import torch
 
 from . import _lib
-from ._lib import (ACT_NONE, ACT_RELU, DT_BF16, DT_FP16, OP_CONV, OP_MAXPOOL, OP_PREP, OP_TAIL, OP_TAILSUM, ConvDesc, KSeg, Op,
-                   PoolDesc, PrepDesc, Src, TailDesc, TailSumDesc)
+from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, DT_BF16, DT_FP16, OP_CONV, OP_DWCONV_LN, OP_ESE, OP_LAYERNORM, OP_MAXPOOL, OP_PREP,
+                   OP_STEM, OP_TAIL, OP_TAILSUM, ConvDesc, DwLnDesc, EseDesc, KSeg, LnDesc, Op, PoolDesc, PrepDesc, Src, StemDesc,
+                   TailDesc, TailSumDesc)
 
 TORCH_DT = {DT_BF16: torch.bfloat16, DT_FP16: torch.float16}
 DT_NAMES = {"bf16": DT_BF16, "fp16": DT_FP16}
@@ -181,6 +182,49 @@ class Plan:
         self.ops.append(op)
         self.keep += [z, out_f32, out_u8]
         self.records.append(("tailsum", dict(z=z, r=r, bias=float(bias), mul=mul, add=add, out_f32=out_f32, out_u8=out_u8)))
+
+    def stem(self, x, in_scale, in_shift, patch, weight, bias, ln_w, ln_b, eps, out: View):
+        B, C, H, W = x.shape
+        cout = weight.shape[0]
+        d = StemDesc(x.data_ptr(), 1 if x.dtype == torch.uint8 else 0, B, C, H, W, in_scale.data_ptr(), in_shift.data_ptr(), patch, cout,
+                     weight.data_ptr(), bias.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), eps, 0, out.buf.data_ptr(), out.cstride, out.choff)
+        op = Op()
+        op.kind = OP_STEM
+        op.u.stem = d
+        self.ops.append(op)
+        self.keep += [x, in_scale, in_shift, weight, bias, ln_w, ln_b, out.buf]
+        self.records.append(("stem", dict(x=x, in_scale=in_scale, in_shift=in_shift, patch=patch, weight=weight, bias=bias, ln_w=ln_w,
+                                          ln_b=ln_b, eps=eps, out=out)))
+
+    def layernorm(self, src: View, w, b, eps, out: View, s2d=1):
+        d = LnDesc(src.buf.data_ptr(), src.cstride, src.choff, src.channels, src.B, src.H, src.W, s2d, w.data_ptr(), b.data_ptr(), eps, 0,
+                   out.buf.data_ptr(), out.cstride, out.choff)
+        op = Op()
+        op.kind = OP_LAYERNORM
+        op.u.ln = d
+        self.ops.append(op)
+        self.keep += [src.buf, w, b, out.buf]
+        self.records.append(("ln", dict(src=src, w=w, b=b, eps=eps, out=out, s2d=s2d)))
+
+    def dwconv_ln(self, src: View, dw_w, dw_b, ln_w, ln_b, eps, out: View):
+        d = DwLnDesc(src.buf.data_ptr(), src.cstride, src.choff, src.channels, src.B, src.H, src.W, 0, dw_w.data_ptr(), dw_b.data_ptr(),
+                     ln_w.data_ptr(), ln_b.data_ptr(), eps, 0, out.buf.data_ptr(), out.cstride, out.choff)
+        op = Op()
+        op.kind = OP_DWCONV_LN
+        op.u.dwln = d
+        self.ops.append(op)
+        self.keep += [src.buf, dw_w, dw_b, ln_w, ln_b, out.buf]
+        self.records.append(("dwln", dict(src=src, dw_w=dw_w, dw_b=dw_b, ln_w=ln_w, ln_b=ln_b, eps=eps, out=out)))
+
+    def ese(self, src: View, fc_w, fc_b, gamma, gate_ws, out: View):
+        d = EseDesc(src.buf.data_ptr(), src.cstride, src.channels, src.B, src.H, src.W, 0, fc_w.data_ptr(), fc_b.data_ptr(),
+                    gamma.data_ptr() if gamma is not None else None, gate_ws.data_ptr(), out.buf.data_ptr(), out.cstride, out.choff)
+        op = Op()
+        op.kind = OP_ESE
+        op.u.ese = d
+        self.ops.append(op)
+        self.keep += [src.buf, fc_w, fc_b, gamma, gate_ws, out.buf]
+        self.records.append(("ese", dict(src=src, fc_w=fc_w, fc_b=fc_b, gamma=gamma, out=out)))
 
     # ---- lifecycle ---------------------------------------------------------------------
     def finalize(self):

@@ -81,6 +81,41 @@ def run_records(plan):
                 o.buf[..., o.choff:o.choff + acc.shape[1]] = acc.permute(0, 2, 3, 1).to(o.buf.dtype)
             if r["out_f32"] is not None:
                 r["out_f32"][..., :acc.shape[1]] = acc.permute(0, 2, 3, 1)
+        elif kind == "stem":
+            x = r["x"].float()
+            xn = (x / 128 - 1) * r["in_scale"].view(1, -1, 1, 1) + r["in_shift"].view(1, -1, 1, 1)
+            pch = r["patch"]
+            w = r["weight"].view(r["weight"].shape[0], x.shape[1], pch, pch)
+            y = F.conv2d(xn, w, r["bias"], stride=pch).permute(0, 2, 3, 1)
+            y = F.layer_norm(y, (y.shape[-1],), r["ln_w"], r["ln_b"], r["eps"])
+            o = r["out"]
+            o.buf[..., o.choff:o.choff + y.shape[-1]] = y.to(o.buf.dtype)
+        elif kind == "ln":
+            v, o = r["src"], r["out"]
+            y = _view_nchw(v).permute(0, 2, 3, 1)
+            y = F.layer_norm(y, (y.shape[-1],), r["w"], r["b"], r["eps"])
+            if r["s2d"] == 2:
+                B_, H, W, C = y.shape
+                y = y.view(B_, H // 2, 2, W // 2, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(B_, H // 2, W // 2, 4 * C)
+            o.buf[..., o.choff:o.choff + y.shape[-1]] = y.to(o.buf.dtype)
+        elif kind == "dwln":
+            v, o = r["src"], r["out"]
+            x = _view_nchw(v)
+            C = x.shape[1]
+            w = r["dw_w"].t().reshape(C, 1, 7, 7)
+            y = F.conv2d(x, w, r["dw_b"], padding=3, groups=C).permute(0, 2, 3, 1)
+            y = F.layer_norm(y, (C,), r["ln_w"], r["ln_b"], r["eps"])
+            o.buf[..., o.choff:o.choff + C] = y.to(o.buf.dtype)
+        elif kind == "ese":
+            v, o = r["src"], r["out"]
+            x = _view_nchw(v)
+            C = x.shape[1]
+            se = x.mean((2, 3), keepdim=True)
+            se = F.conv2d(se, r["fc_w"].view(C, C, 1, 1), r["fc_b"])
+            y = x * (F.relu6(se + 3.0) / 6.0)
+            if r["gamma"] is not None:
+                y = y * r["gamma"].view(1, -1, 1, 1)
+            o.buf[..., o.choff:o.choff + C] = y.permute(0, 2, 3, 1).to(o.buf.dtype)
         elif kind == "tailsum":
             z, rr = r["z"], r["r"]
             B_, _, H, W = z.shape

@@ -84,3 +84,34 @@ def test_state_dict_roundtrip_and_errors():
         m.eval()(torch.zeros(1, 1, 128, 128))          # CPU input: no fallback
     with pytest.raises(RuntimeError):
         m.train().cuda()(torch.zeros(1, 1, 128, 128).cuda())
+
+
+def _randomise_rd(model, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("gamma"):
+                p.copy_(torch.rand(p.shape, generator=g) * 0.5 + 0.25)
+
+
+@pytest.mark.parametrize("cfg,shape", [(dict(), (2, 1, 128, 128)),
+                                       (dict(hidden=[128, 64], growth_rates=[32, 40, 64], ds_blocks=[False, True, False], ese_blocks=[False, True, True],
+                                             n_blocks=[2, 1, 2], rdnet_init=64, scale=2, depth=1), (3, 1, 32, 48))])
+def test_rdresunet_matches_oracle(cfg, shape):
+    """RDNet encoder (stem, LayerNorm2d, depthwise 7x7, GELU, eSE, layer scale, dense concat, 2x2-s2 transitions) +
+    ResUNet decoder against the fp32 oracle (pssr/models/rdresunet.py:104-130).  Same tolerance budget as ResUNet."""
+    from oracle.models import rdresunet_forward
+    from pssr2_b200.models import RDResUNet
+    torch.manual_seed(0)
+    model = RDResUNet(**cfg).eval()
+    _randomise_bn(model)
+    _randomise_rd(model)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x = torch.tensor(np.random.default_rng(0).integers(0, 256, shape).astype(np.float32))
+    ds = cfg.get("ds_blocks", (False, True, True, False, False, False, True))
+    want = rdresunet_forward(sd, x, ds_blocks=ds)
+    got = model.cuda()(x.cuda()).cpu()
+    d = float((got - want).abs().max())
+    print(f"[rdresunet {shape}] max-abs vs fp32 oracle {d:.5f}, PSNR {_psnr(got, want):.1f} dB")
+    assert got.shape == want.shape
+    assert _psnr(got, want) >= 50.0 and d <= 6e-2

@@ -84,3 +84,18 @@ def test_dataset_index_math_matches_reference(ref):
     for total, n in ((5, 1), (5, 3), (6, 2), (7, 4)):
         s, c = MD._slice_center_range(total, n)
         assert np.array_equal(RD._slice_center(np.arange(total).reshape(total, 1, 1), n).ravel(), np.arange(s, s + c))
+
+
+def test_rdresunet_state_dict_keys_match_reference(ref):
+    from pssr.models import RDResUNet as RefRD
+    from pssr2_b200.models import RDResUNet
+    torch.manual_seed(0)
+    a = RefRD().state_dict()
+    torch.manual_seed(0)
+    m = RDResUNet()
+    b = m.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(a[k].shape == b[k].shape for k in a)
+    m.load_state_dict(a, strict=True)
+    # same construction order and the same kaiming re-initialisation walk => the same seeded weights as the reference
+    assert all(torch.equal(a[k], b[k]) for k in a if a[k].is_floating_point()), [k for k in a if a[k].is_floating_point() and not torch.equal(a[k], b[k])][:5]

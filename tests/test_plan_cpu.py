@@ -40,3 +40,32 @@ def test_resunet_plan_matches_oracle_on_cpu(dry_run, cfg):
     assert float((got - want).abs().max()) < 3e-2
     c = got.shape[1] // 2
     assert torch.equal(st["out_u8"], got[:, c:c + 1].clamp(0, 255).to(torch.uint8))
+
+
+@pytest.mark.parametrize("cfg", [dict(), dict(hidden=[128, 64], growth_rates=[32, 40, 64], ds_blocks=[False, True, False],
+                                                ese_blocks=[False, True, True], n_blocks=[2, 1, 2], rdnet_init=64, scale=2, depth=1)])
+def test_rdresunet_plan_matches_oracle_on_cpu(dry_run, cfg):
+    from oracle.models import rdresunet_forward
+    from pssr2_b200.models import RDResUNet
+    torch.manual_seed(0)
+    model = RDResUNet(**cfg).eval()
+    _randomise_bn(model)
+    with torch.no_grad():   # make layer-scale / LayerNorm parameters non-trivial (default gamma = 1e-6 hides the dense blocks)
+        g = torch.Generator().manual_seed(5)
+        for n, p in model.named_parameters():
+            if n.endswith("gamma"):
+                p.copy_(torch.rand(p.shape, generator=g) * 0.5 + 0.25)
+            elif "encoder" in n and p.dim() == 1 and ("weight" in n) and p.shape[0] > 1 and "layers.0" not in n and "fc" not in n:
+                p.mul_(torch.rand(p.shape, generator=g) * 0.4 + 0.8)
+    B, H, W = (1, 64, 64) if not cfg else (2, 32, 48)
+    x = torch.tensor(np.random.default_rng(0).integers(0, 256, (B, 1, H, W)).astype(np.float32))
+    ds = cfg.get("ds_blocks", (False, True, True, False, False, False, True))
+    want = rdresunet_forward(model.state_dict(), x, ds_blocks=ds)
+    model.precision = "fp16"
+    st = model._build(x.shape, x.dtype, torch.device("cpu"))
+    st["x"].copy_(x)
+    run_records(st["plan"])
+    got = st["out"]
+    assert got.shape == want.shape
+    err = float((got - want).abs().max())
+    assert err < 6e-2, err      # 16-bit activations through ~60 layers incl. LayerNorm/GELU; packing bugs give O(1..100)
