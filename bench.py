@@ -196,7 +196,7 @@ def run_ours(args):
         step(i)
     barrier()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("PSSR_NO_CLOCK_SAMPLER"):
         sampler.start()
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

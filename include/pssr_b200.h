@@ -320,9 +320,11 @@ int pssr_stitch(const uint8_t* tiles, uint8_t* sheets, int32_t n_stacks, int32_t
 /* Per image pair (uint8 [n][h][w]): exact integer reductions
  *   sums[i][0] = sum (a-b)^2  (int64)
  *   ssim[i]    = sum over the (h-6)x(w-6) interior of the 7x7-window SSIM map (double)
- * from which mse / pixel / psnr / ssim follow on the host (pssr2_b200/predict.py). */
+ * from which mse / pixel / psnr / ssim follow on the host (pssr2_b200/predict.py).
+ * workspace: >= pssr_metric_workspace_bytes(n, h, w) bytes of device scratch (per-CTA partials). */
+int64_t pssr_metric_workspace_bytes(int32_t n, int32_t h, int32_t w);
 int pssr_metric_sums(const uint8_t* a, const uint8_t* b, int32_t n, int32_t h, int32_t w,
-                     int64_t* sq_err, double* ssim_sum, void* stream);
+                     int64_t* sq_err, double* ssim_sum, void* workspace, void* stream);
 /* normalize_preds (util.py:139-191) for uint8 pairs of equal shape: 256-bin histograms give
  * the exact percentiles/means; second pass applies the affine maps, clips and truncates.
  * workspace: >= pssr_normalize_workspace_bytes(n) bytes of device scratch. */

@@ -170,7 +170,8 @@ SYMBOLS = {
     "pssr_plan_num_ops": (c_int32, [c_void_p]),
     "pssr_plan_destroy": (None, [c_void_p]),
     "pssr_stitch": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
-    "pssr_metric_sums": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "pssr_metric_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32]),
+    "pssr_metric_sums": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pssr_normalize_workspace_bytes": (c_int64, [c_int32]),
     "pssr_normalize_preds": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                        c_double, c_double, c_void_p, c_void_p]),

@@ -234,23 +234,26 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const uint8_t* __restri
 
 using namespace pssr;
 
+extern "C" int64_t pssr_metric_workspace_bytes(int32_t n, int32_t h, int32_t w) {
+  const int64_t parts = (int64_t)((w + kSsimT - 1) / kSsimT) * ((h + kSsimT - 1) / kSsimT);
+  return (int64_t)(n > 0 ? n : 0) * parts * 16;
+}
+
 extern "C" int pssr_metric_sums(const uint8_t* a, const uint8_t* b, int32_t n, int32_t h, int32_t w, int64_t* sq_err,
-                                double* ssim_sum, void* stream) {
+                                double* ssim_sum, void* workspace, void* stream) {
   PSSR_REQUIRE(a && b && n >= 1 && h >= 1 && w >= 1, PSSR_EINVAL, "metric_sums: bad arguments");
   PSSR_REQUIRE(ssim_sum == nullptr || (h >= 7 && w >= 7), PSSR_EINVAL, "win_size exceeds image extent.");
   PSSR_REQUIRE(n <= 65535, PSSR_EUNSUP, "metric_sums: at most 65535 images per call");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int tiles_x = (w + kSsimT - 1) / kSsimT, tiles_y = (h + kSsimT - 1) / kSsimT;
   const int parts = tiles_x * tiles_y;
-  void* scratch = nullptr;
-  PSSR_CHECK_CUDA(cudaMallocAsync(&scratch, (size_t)n * parts * 16, st));
-  long long* sse_part = reinterpret_cast<long long*>(scratch);
+  PSSR_REQUIRE(workspace != nullptr && ((uintptr_t)workspace & 15) == 0, PSSR_EINVAL, "metric_sums: workspace missing or misaligned");
+  long long* sse_part = reinterpret_cast<long long*>(workspace);
   double* ssim_part = reinterpret_cast<double*>(sse_part + (size_t)n * parts);
   metric_kernel<<<dim3(parts, n), 256, 0, st>>>(a, b, h, w, tiles_x, tiles_y, sse_part, ssim_part);
   metric_finish_kernel<<<n, 32, 0, st>>>(sse_part, ssim_part, parts, reinterpret_cast<long long*>(sq_err), ssim_sum);
   count_launch(2);
   PSSR_CHECK_CUDA(cudaGetLastError());
-  PSSR_CHECK_CUDA(cudaFreeAsync(scratch, st));
   return PSSR_OK;
 }
 

@@ -145,8 +145,9 @@ def metric_sums(a: torch.Tensor, b: torch.Tensor, want_ssim=True):
     n, h, w = a.shape
     sq = torch.empty(n, dtype=torch.int64, device=a.device)
     ss = torch.empty(n, dtype=torch.float64, device=a.device) if want_ssim else None
+    ws = torch.empty(max(16, int(_lib.lib().pssr_metric_workspace_bytes(n, h, w))), dtype=torch.uint8, device=a.device)
     rc = _lib.lib().pssr_metric_sums(a.data_ptr(), b.data_ptr(), n, h, w, sq.data_ptr(), ss.data_ptr() if ss is not None else None,
-                                     _lib.current_stream_ptr())
+                                     ws.data_ptr(), _lib.current_stream_ptr())
     if rc == -1 and b"win_size" in _lib.lib().pssr_last_error():
         raise ValueError(_lib.lib().pssr_last_error().decode())
     _lib.check(rc, "pssr_metric_sums")
