@@ -35,8 +35,11 @@ struct StripKParams {
   int n_segs;
   int seg_src[4], seg_taps[4], seg_cblocks[4], seg_kb0[4];
   int num_kb;
-  int H, W, B, P, IP;         // P = W + 2 (padded row pitch), IP = (H + 2) * P
-  int boxes_per_row, box_w;   // a padded row is fetched as 1 or 2 boxes of box_w pixels
+  int H, W, B, P, IP;         // P = Wb + 2*pad (row pitch of a virtual image), IP = (H + 2*pad) * P
+  int pad;                    // 1 when a 3x3 segment needs the zero halo, 0 for pure 1x1 layers (exact pixels, no waste)
+  int HP;                     // H + 2*pad
+  int NJ, Wb;                 // images wider than 128 are split into NJ column blocks of Wb pixels: each block is a
+                              // virtual image of pitch P = Wb + 2 whose halo columns are the neighbouring block's pixels
   int q_begin, q_end;         // first / one-past-last real pixel in q space (host checks it fits 31 bits)
   int T;                      // M tiles per unit
   int units_m, n_tiles, total_units;
@@ -74,7 +77,18 @@ __device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&o)[8]) 
                : "memory");
 }
 
-__device__ __forceinline__ float gelu_erf2(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// exact-erf GELU (nn.GELU(), _rdnet.py:186) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the 16-bit
+// rounding of the stored activation) -- erff() costs ~3x more instructions and made the RDNet 1x1 expansions epilogue-bound
+__device__ __forceinline__ float gelu_erf2(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = 1.0f - poly * t * __expf(-z * z);      // erf(|x|/sqrt2)
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
 
 __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_constant__ StripKParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -89,7 +103,7 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
   // bias (and optional per-channel scale) of the whole layer, staged once per CTA
   float* bias_s = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + 2u * p.a_bytes + (uint32_t)p.b_stages * p.b_bytes);
   float* scale_s = bias_s + p.n_total;
-  float* tailw_s = scale_s + p.n_total;
+  float* tailw_s = scale_s + (p.out_scale != nullptr ? p.n_total : 0);
   for (int i = threadIdx.x; i < p.n_total; i += kSThreads) {
     bias_s[i] = p.bias[i];
     if (p.out_scale != nullptr) scale_s[i] = p.out_scale[i];
@@ -127,14 +141,15 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
     if (lane == 0) {
       int as = 0;
       uint32_t aphase = 0;
-      const int rows_total = p.B * (p.H + 2);
+      const int rows_total = p.B * p.NJ * p.HP;
       for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
         const int um = unit / p.n_tiles;
         const int qa = p.q_begin + um * unit_q;
         int qb = qa + unit_q;
         if (qb > p.q_end) qb = p.q_end;
-        const int r0 = (qa - p.P - 1) / p.P;
-        int r1 = (qb + p.P) / p.P;
+        const int halo = p.pad * (p.P + 1);
+        const int r0 = (qa - halo) / p.P;
+        int r1 = (qb - 1 + halo) / p.P;
         if (r1 > rows_total - 1) r1 = rows_total - 1;
         const int nrows = r1 - r0 + 1;
         for (int sg = 0; sg < p.n_segs; ++sg) {
@@ -142,16 +157,23 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
           for (int cb = 0; cb < p.seg_cblocks[sg]; ++cb) {
             mbar_wait(a_empty(as), aphase ^ 1u);
             if (p.dbg & 4) { mbar_arrive(a_full(as)); if (++as == 2) { as = 0; aphase ^= 1u; } continue; }
+            if (!p.pad) {
+              // pure 1x1 layer: pixel space is the flat NHWC pixel index, the whole A tile is ONE 2-D box [128T px x 64 ch]
+              mbar_arrive_expect_tx(a_full(as), (uint32_t)unit_q * 128u);
+              tma_load_2d(a_base + (uint32_t)as * p.a_bytes, tm, a_full(as), cb * 64, qa);
+              if (++as == 2) { as = 0; aphase ^= 1u; }
+              continue;
+            }
             mbar_arrive_expect_tx(a_full(as), (uint32_t)nrows * (uint32_t)p.P * 128u);
             const uint32_t dst0 = a_base + (uint32_t)as * p.a_bytes;
             for (int r = 0; r < nrows; ++r) {
               const int rho = r0 + r;
-              const int n = rho / (p.H + 2);
-              const int py = rho - n * (p.H + 2);
+              const int v = rho / p.HP;
+              const int py = rho - v * p.HP;
+              const int n = v / p.NJ;
+              const int j = v - n * p.NJ;
               const uint32_t dst = dst0 + (uint32_t)r * (uint32_t)p.P * 128u;
-              tma_load_4d(dst, tm, a_full(as), cb * 64, -1, py - 1, n);
-              if (p.boxes_per_row == 2)
-                tma_load_4d(dst + (uint32_t)p.box_w * 128u, tm, a_full(as), cb * 64, -1 + p.box_w, py - 1, n);
+              tma_load_4d(dst, tm, a_full(as), cb * 64, j * p.Wb - p.pad, py - p.pad, n);
             }
             if (++as == 2) { as = 0; aphase ^= 1u; }
           }
@@ -197,8 +219,8 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
     for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x, ++it) {
       const int um = unit / p.n_tiles;
       const int qa = p.q_begin + um * (128 * T);
-      const int r0 = (qa - p.P - 1) / p.P;
-      const int row_off0 = qa - r0 * p.P;     // smem row of the unit's first pixel
+      const int r0 = (qa - p.pad * (p.P + 1)) / p.P;
+      const int row_off0 = p.pad ? qa - r0 * p.P : 0;     // smem row of the unit's first pixel
       int tv = (p.q_end - qa + 127) / 128;
       if (tv > T) tv = T;
       if (p.dbg & 2) tv = 0;
@@ -274,12 +296,13 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
         const int c_lo = pi * pw;
         const int c_hi = c_lo + pw < block_n ? c_lo + pw : block_n;
         const int q = qa + mt * 128 + row;
-        const int n = q / p.IP;
-        const int rem = q - n * p.IP;
+        const int vimg = q / p.IP;
+        const int rem = q - vimg * p.IP;
         const int py = rem / p.P;
         const int px = rem - py * p.P;
-        const bool valid = (q < p.q_end) && px >= 1 && px <= p.W && py >= 1 && py <= p.H;
-        const int x = px - 1, y = py - 1;
+        const int n = vimg / p.NJ;
+        const int x = (vimg - n * p.NJ) * p.Wb + px - p.pad, y = py - p.pad;
+        const bool valid = (q < p.q_end) && px >= p.pad && px < p.Wb + p.pad && x < p.W && py >= p.pad && py < p.H + p.pad;
         // sub-pixel / channel position of the unit's first output column, advanced incrementally (no divisions per chunk)
         int sub = (n_tile * block_n + c_lo) / p.cps;
         int cc = n_tile * block_n + c_lo - sub * p.cps;
@@ -426,12 +449,12 @@ bool strip_supported(const pssr_conv_desc_t& d) {
   if (getenv("PSSR_CONV_V1") != nullptr) return false;
   for (int s = 0; s < d.n_segs; ++s)
     if (d.segs[s].taps != 1 && d.segs[s].taps != 9) return false;
-  const int P = d.Wo + 2;
-  if (P > 256 && !(P % 2 == 0 && P / 2 <= 256)) return false;
   if (d.n % 32 != 0 || d.n < 32) return false;
   // small feature maps: the padded pixel space wastes (1 - HW/((H+2)(W+2))) of the MMAs (36 % at 8x8, 21 % at 16x16)
   // and the exact-tile kernel (conv_igemm.cu) is faster there
-  if (d.Wo < 32 && d.tail_z == nullptr && getenv("PSSR_STRIP_ALWAYS") == nullptr) return false;
+  bool any9 = false;
+  for (int s = 0; s < d.n_segs; ++s) any9 = any9 || d.segs[s].taps == 9;
+  if (any9 && d.Wo < 32 && d.tail_z == nullptr && getenv("PSSR_STRIP_ALWAYS") == nullptr) return false;
   return true;
 }
 
@@ -465,13 +488,18 @@ int strip_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
   p.n_valid = d.n_valid;
   p.n_total = d.n;
   p.H = d.Ho; p.W = d.Wo; p.B = d.B;
-  p.P = d.Wo + 2;
-  p.IP = (d.Ho + 2) * p.P;
-  p.boxes_per_row = p.P > 256 ? 2 : 1;
-  p.box_w = p.P / p.boxes_per_row;
-  p.q_begin = p.P + 1;
-  PSSR_REQUIRE((long long)d.B * p.IP < (1ll << 30), PSSR_EUNSUP, "conv: batch x padded image exceeds the 30-bit pixel index");
-  p.q_end = d.B * p.IP - p.P - 1;
+  p.NJ = (d.Wo + 127) / 128;
+  p.Wb = (d.Wo + p.NJ - 1) / p.NJ;
+  p.pad = 0;
+  for (int s2 = 0; s2 < d.n_segs; ++s2)
+    if (d.segs[s2].taps == 9) p.pad = 1;
+  if (!p.pad) { p.NJ = 1; p.Wb = d.Wo; }
+  p.P = p.Wb + 2 * p.pad;
+  p.HP = d.Ho + 2 * p.pad;
+  p.IP = p.HP * p.P;
+  p.q_begin = p.pad * (p.P + 1);
+  PSSR_REQUIRE((long long)d.B * p.NJ * p.IP < (1ll << 30), PSSR_EUNSUP, "conv: batch x padded image exceeds the 30-bit pixel index");
+  p.q_end = d.B * p.NJ * p.IP - p.pad * (p.P + 1);
 
   int num_kb = 0;
   p.n_segs = d.n_segs;
@@ -486,7 +514,8 @@ int strip_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
   // T: as many M tiles per unit as TMEM (512 columns) and shared memory allow, capped at 2 so the A halo
   // buffers can be double-buffered; TMEM is double-buffered when T * block_n <= 256.
   const int tailw_bytes = d.tail_z != nullptr ? 9 * cps * 4 : 0;
-  const int smem_cap = 226 * 1024 - 1024 - 8 * d.n - tailw_bytes;   // minus the staged bias / scale / tail-weight vectors
+  const int vec_bytes = 4 * d.n * (d.out_scale != nullptr ? 2 : 1);   // staged bias (+ scale) vectors
+  const int smem_cap = 226 * 1024 - 1024 - vec_bytes - tailw_bytes;
   // measured on B200 (scripts/dev_time_layer.py): keeping T * block_n <= 256 so that TMEM is double-buffered and the
   // epilogue of unit i overlaps the MMAs of unit i+1 beats the halved weight traffic of a larger T.
   int T = 256 / block_n;
@@ -500,7 +529,7 @@ int strip_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
   const char* envG = getenv("PSSR_STRIP_G");
   for (;; --T) {
     rmax = (128 * T + 1) / p.P + 4;   // rows [floor((qa-P-1)/P), floor((qb+P)/P)] plus the overhang a partial last tile may read
-    const long long a_bytes = (long long)rmax * p.P * 128;
+    const long long a_bytes = p.pad ? (long long)rmax * p.P * 128 : 128LL * T * 128;
     const long long a_total = ((2 * a_bytes + 1023) / 1024) * 1024;
     const long long left = smem_cap - a_total;
     // taps per B stage: as many as still leave two stages (a stage holds G weight blocks on one barrier)
@@ -521,7 +550,7 @@ int strip_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
   p.tap_bytes = (uint32_t)(block_n * 128);
   p.T = T;
   p.rmax = rmax;
-  p.a_bytes = (uint32_t)((((long long)rmax * p.P * 128 + 1023) / 1024) * 1024);
+  p.a_bytes = (uint32_t)((((p.pad ? (long long)rmax * p.P * 128 : 128LL * T * 128) + 1023) / 1024) * 1024);
   p.b_bytes = (uint32_t)(G * block_n * 128);
   p.b_stages = b_stages;
   p.tmem_bufs = (T * block_n <= 256) ? 2 : 1;
@@ -541,10 +570,20 @@ int strip_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
     PSSR_REQUIRE(src.H == d.Ho && src.W == d.Wo && src.B == d.B, PSSR_EINVAL, "conv: source %d geometry does not match the output", s);
     cuuint64_t gdim[4] = {(cuuint64_t)src.channels, (cuuint64_t)src.W, (cuuint64_t)src.H, (cuuint64_t)src.B};
     cuuint64_t gstr[3] = {(cuuint64_t)src.cstride * 2, (cuuint64_t)src.cstride * 2 * src.W, (cuuint64_t)src.cstride * 2 * src.W * src.H};
-    cuuint32_t box[4] = {64, (cuuint32_t)p.box_w, 1, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.P, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(&op.tmaps[s], tdt, 4, const_cast<void*>(src.base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r;
+    if (p.pad) {
+      r = enc(&op.tmaps[s], tdt, 4, const_cast<void*>(src.base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      cuuint64_t gdim2[2] = {(cuuint64_t)src.channels, (cuuint64_t)src.W * src.H * src.B};
+      cuuint64_t gstr2[1] = {(cuuint64_t)src.cstride * 2};
+      cuuint32_t box2[2] = {64, (cuuint32_t)(128 * T)};
+      cuuint32_t estr2[2] = {1, 1};
+      r = enc(&op.tmaps[s], tdt, 2, const_cast<void*>(src.base), gdim2, gstr2, box2, estr2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     PSSR_REQUIRE(r == CUDA_SUCCESS, PSSR_ECUDA, "cuTensorMapEncodeTiled(source %d) failed with %d", s, (int)r);
   }
   {
@@ -558,7 +597,7 @@ int strip_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PSSR_REQUIRE(r == CUDA_SUCCESS, PSSR_ECUDA, "cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
   }
-  op.smem_bytes = (int)(2 * p.a_bytes + (uint32_t)b_stages * p.b_bytes + 1024 + 8 * (uint32_t)d.n + (uint32_t)tailw_bytes);
+  op.smem_bytes = (int)(2 * p.a_bytes + (uint32_t)b_stages * p.b_bytes + 1024 + (uint32_t)vec_bytes + (uint32_t)tailw_bytes);
 
   p.bias = d.bias;
   p.out_scale = d.out_scale;

@@ -7,6 +7,8 @@
 //   dwln    : depthwise 7x7 conv + bias + LayerNorm2d (first two layers of Block / BlockESE)          :181-183
 //   ese     : EffectiveSEModule (global mean -> 1x1 fc -> hard-sigmoid gate) + layer-scale gamma     :172-174,200-202
 // One warp owns one pixel, lanes stride over 8-channel (16-byte) groups, LayerNorm statistics by warp shuffles.
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "plan.h"
 
@@ -33,31 +35,50 @@ static constexpr int kMaxGroupsPerLane = 6;   // channels <= 32 lanes * 6 groups
 
 // ------------------------------------------------------------------------------- stem
 __global__ void __launch_bounds__(256) stem_kernel(pssr_stem_desc_t d, int fp16) {
+  extern __shared__ float stem_sm[];            // [Cout][K] weights, bias, ln_w, ln_b
   const int Ho = d.H / d.patch, Wo = d.W / d.patch;
   const long long total = (long long)d.B * Ho * Wo;
   const int lane = threadIdx.x & 31;
   const int K = d.C * d.patch * d.patch;
+  float* w_s = stem_sm;
+  float* b_s = w_s + (size_t)d.Cout * K;
+  float* lw_s = b_s + d.Cout;
+  float* lb_s = lw_s + d.Cout;
+  for (int i = threadIdx.x; i < d.Cout * K; i += blockDim.x) w_s[(i % K) * d.Cout + i / K] = d.weight[i];   // [k][c]: 16-byte loads per lane
+  for (int i = threadIdx.x; i < d.Cout; i += blockDim.x) { b_s[i] = d.bias[i]; lw_s[i] = d.ln_w[i]; lb_s[i] = d.ln_b[i]; }
+  __syncthreads();
   for (long long pix = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; pix < total; pix += ((long long)gridDim.x * blockDim.x) >> 5) {
     const int x = (int)(pix % Wo), y = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
+    // the K = C*patch*patch normalised inputs of this patch: lane k loads element k, shuffles broadcast them
+    float vin = 0.f;
+    if (lane < K) {
+      const int ci = lane / (d.patch * d.patch), rem = lane % (d.patch * d.patch);
+      const int yy = y * d.patch + rem / d.patch, xx = x * d.patch + rem % d.patch;
+      const size_t idx = (((size_t)n * d.C + ci) * d.H + yy) * d.W + xx;
+      const float raw = d.x_u8 ? (float)reinterpret_cast<const uint8_t*>(d.x)[idx] : reinterpret_cast<const float*>(d.x)[idx];
+      vin = __fadd_rn(__fmul_rn(__fsub_rn(__fdiv_rn(raw, 128.f), 1.f), d.in_scale[ci]), d.in_shift[ci]);
+    }
     float vals[kMaxGroupsPerLane * 8];
     float s = 0.f;
     int cnt = 0;
     for (int c0 = lane * 8; c0 < d.Cout; c0 += 256, ++cnt) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int co = c0 + j;
-        float acc = d.bias[co];
-        for (int k = 0; k < K; ++k) {
-          const int ci = k / (d.patch * d.patch), rem = k % (d.patch * d.patch);
-          const int yy = y * d.patch + rem / d.patch, xx = x * d.patch + rem % d.patch;
-          const size_t idx = (((size_t)n * d.C + ci) * d.H + yy) * d.W + xx;
-          const float raw = d.x_u8 ? (float)reinterpret_cast<const uint8_t*>(d.x)[idx] : reinterpret_cast<const float*>(d.x)[idx];
-          const float v = __fadd_rn(__fmul_rn(__fsub_rn(__fdiv_rn(raw, 128.f), 1.f), d.in_scale[ci]), d.in_shift[ci]);
-          acc = fmaf(v, d.weight[(size_t)co * K + k], acc);
-        }
-        vals[cnt * 8 + j] = acc;
-        s += acc;
+      for (int j = 0; j < 8; ++j) vals[cnt * 8 + j] = b_s[c0 + j];
+    }
+    for (int k = 0; k < K; ++k) {
+      const float v = __shfl_sync(0xffffffffu, vin, k);
+      cnt = 0;
+      for (int c0 = lane * 8; c0 < d.Cout; c0 += 256, ++cnt) {
+        const float4 w0 = *reinterpret_cast<const float4*>(w_s + (size_t)k * d.Cout + c0), w1 = *reinterpret_cast<const float4*>(w_s + (size_t)k * d.Cout + c0 + 4);
+        float* vv = vals + cnt * 8;
+        vv[0] = fmaf(v, w0.x, vv[0]); vv[1] = fmaf(v, w0.y, vv[1]); vv[2] = fmaf(v, w0.z, vv[2]); vv[3] = fmaf(v, w0.w, vv[3]);
+        vv[4] = fmaf(v, w1.x, vv[4]); vv[5] = fmaf(v, w1.y, vv[5]); vv[6] = fmaf(v, w1.z, vv[6]); vv[7] = fmaf(v, w1.w, vv[7]);
       }
+    }
+    cnt = 0;
+    for (int c0 = lane * 8; c0 < d.Cout; c0 += 256, ++cnt) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += vals[cnt * 8 + j];
     }
     const float mean = warp_sum_f(s) / d.Cout;
     float q = 0.f;
@@ -68,7 +89,7 @@ __global__ void __launch_bounds__(256) stem_kernel(pssr_stem_desc_t d, int fp16)
     for (int c0 = lane * 8; c0 < d.Cout; c0 += 256, ++cnt) {
       float f[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = (vals[cnt * 8 + j] - mean) * rstd * d.ln_w[c0 + j] + d.ln_b[c0 + j];
+      for (int j = 0; j < 8; ++j) f[j] = (vals[cnt * 8 + j] - mean) * rstd * lw_s[c0 + j] + lb_s[c0 + j];
       *reinterpret_cast<uint4*>(out + c0) = pack8(f, fp16);
     }
   }
@@ -82,7 +103,11 @@ int stem_launch(const pssr_stem_desc_t& d, int dtype, cudaStream_t stream) {
   long long blocks = (total + 7) / 8;
   const long long cap = (long long)device_sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  stem_kernel<<<(int)blocks, 256, 0, stream>>>(d, dtype == PSSR_DT_FP16);
+  const int K = d.C * d.patch * d.patch;
+  PSSR_REQUIRE(K <= 32, PSSR_EUNSUP, "stem: C*patch^2 = %d must be <= 32", K);
+  const size_t smem = ((size_t)d.Cout * K + 3 * (size_t)d.Cout) * sizeof(float);
+  PSSR_REQUIRE(smem <= 48 * 1024, PSSR_EUNSUP, "stem: weights do not fit in shared memory");
+  stem_kernel<<<(int)blocks, 256, smem, stream>>>(d, dtype == PSSR_DT_FP16);
   count_launch();
   PSSR_CHECK_CUDA(cudaGetLastError());
   return PSSR_OK;
@@ -141,65 +166,187 @@ int ln_launch(const pssr_ln_desc_t& d, int dtype, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------- dwln
+// One warp produces TWO horizontally adjacent pixels: the 8 input columns x-3..x+4 of a filter row are loaded once and
+// feed both outputs, and each weight vector is loaded once per pair.
 __global__ void __launch_bounds__(256) dwln_kernel(pssr_dwln_desc_t d, int fp16) {
-  const long long total = (long long)d.B * d.H * d.W;
+  const int Wp = (d.W + 1) / 2;
+  const long long total = (long long)d.B * d.H * Wp;
   const int lane = threadIdx.x & 31;
   const uint16_t* in = reinterpret_cast<const uint16_t*>(d.in) + d.in_choff;
-  for (long long pix = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; pix < total; pix += ((long long)gridDim.x * blockDim.x) >> 5) {
-    const int x = (int)(pix % d.W), y = (int)((pix / d.W) % d.H), n = (int)(pix / ((long long)d.W * d.H));
-    float vals[kMaxGroupsPerLane * 8];
-    float s = 0.f;
+  for (long long pp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; pp < total; pp += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const int xp = (int)(pp % Wp), y = (int)((pp / Wp) % d.H), n = (int)(pp / ((long long)Wp * d.H));
+    const int x0 = 2 * xp;
+    const bool has1 = x0 + 1 < d.W;
+    float v0[kMaxGroupsPerLane * 8], v1[kMaxGroupsPerLane * 8];
+    float s0 = 0.f, s1 = 0.f;
     int cnt = 0;
     for (int c0 = lane * 8; c0 < d.C; c0 += 256, ++cnt) {
-      float acc[8];
+      float a0[8], a1[8];
       {
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(d.dw_b + c0)), b1 = __ldg(reinterpret_cast<const float4*>(d.dw_b + c0 + 4));
-        acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+        a0[0] = b0.x; a0[1] = b0.y; a0[2] = b0.z; a0[3] = b0.w; a0[4] = b1.x; a0[5] = b1.y; a0[6] = b1.z; a0[7] = b1.w;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a1[j] = a0[j];
       }
       for (int ky = 0; ky < 7; ++ky) {
         const int yy = y + ky - 3;
         if (yy < 0 || yy >= d.H) continue;
+        float wr[7][8];
+#pragma unroll
         for (int kx = 0; kx < 7; ++kx) {
-          const int xx = x + kx - 3;
-          if (xx < 0 || xx >= d.W) continue;
-          float f[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(in + (((size_t)n * d.H + yy) * d.W + xx) * d.in_cstride + c0)), f, fp16);
           const float* w = d.dw_w + (size_t)(ky * 7 + kx) * d.C + c0;
           const float4 w0 = __ldg(reinterpret_cast<const float4*>(w)), w1 = __ldg(reinterpret_cast<const float4*>(w + 4));
-          acc[0] = fmaf(f[0], w0.x, acc[0]); acc[1] = fmaf(f[1], w0.y, acc[1]); acc[2] = fmaf(f[2], w0.z, acc[2]); acc[3] = fmaf(f[3], w0.w, acc[3]);
-          acc[4] = fmaf(f[4], w1.x, acc[4]); acc[5] = fmaf(f[5], w1.y, acc[5]); acc[6] = fmaf(f[6], w1.z, acc[6]); acc[7] = fmaf(f[7], w1.w, acc[7]);
+          wr[kx][0] = w0.x; wr[kx][1] = w0.y; wr[kx][2] = w0.z; wr[kx][3] = w0.w; wr[kx][4] = w1.x; wr[kx][5] = w1.y; wr[kx][6] = w1.z; wr[kx][7] = w1.w;
+        }
+        const uint16_t* rowp = in + (((size_t)n * d.H + yy) * d.W) * d.in_cstride + c0;
+#pragma unroll
+        for (int cx = 0; cx < 8; ++cx) {           // input column x0 - 3 + cx : tap cx of pixel 0, tap cx-1 of pixel 1
+          const int xx = x0 - 3 + cx;
+          if (xx < 0 || xx >= d.W) continue;
+          float f[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(rowp + (size_t)xx * d.in_cstride)), f, fp16);
+          if (cx < 7) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a0[j] = fmaf(f[j], wr[cx][j], a0[j]);
+          }
+          if (cx >= 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a1[j] = fmaf(f[j], wr[cx - 1][j], a1[j]);
+          }
         }
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { vals[cnt * 8 + j] = acc[j]; s += acc[j]; }
+      for (int j = 0; j < 8; ++j) { v0[cnt * 8 + j] = a0[j]; v1[cnt * 8 + j] = a1[j]; s0 += a0[j]; s1 += a1[j]; }
     }
-    const float mean = warp_sum_f(s) / d.C;
-    float q = 0.f;
-    for (int i = 0; i < cnt * 8; ++i) { const float t = vals[i] - mean; q += t * t; }
-    const float rstd = rsqrtf(warp_sum_f(q) / d.C + d.eps);
-    uint16_t* out = reinterpret_cast<uint16_t*>(d.out) + (size_t)pix * d.out_cstride + d.out_choff;
+    const float m0 = warp_sum_f(s0) / d.C, m1 = warp_sum_f(s1) / d.C;
+    float q0 = 0.f, q1 = 0.f;
+    for (int i = 0; i < cnt * 8; ++i) { const float t0 = v0[i] - m0, t1 = v1[i] - m1; q0 += t0 * t0; q1 += t1 * t1; }
+    const float r0 = rsqrtf(warp_sum_f(q0) / d.C + d.eps), r1 = rsqrtf(warp_sum_f(q1) / d.C + d.eps);
+    const size_t pix0 = ((size_t)n * d.H + y) * d.W + x0;
+    uint16_t* out = reinterpret_cast<uint16_t*>(d.out) + pix0 * d.out_cstride + d.out_choff;
     cnt = 0;
     for (int c0 = lane * 8; c0 < d.C; c0 += 256, ++cnt) {
-      float f[8];
+      float f[8], g[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = (vals[cnt * 8 + j] - mean) * rstd * d.ln_w[c0 + j] + d.ln_b[c0 + j];
+      for (int j = 0; j < 8; ++j) {
+        const float lw = d.ln_w[c0 + j], lb = d.ln_b[c0 + j];
+        f[j] = (v0[cnt * 8 + j] - m0) * r0 * lw + lb;
+        g[j] = (v1[cnt * 8 + j] - m1) * r1 * lw + lb;
+      }
       *reinterpret_cast<uint4*>(out + c0) = pack8(f, fp16);
+      if (has1) *reinterpret_cast<uint4*>(out + d.out_cstride + c0) = pack8(g, fp16);
     }
   }
 }
+
+// Tiled depthwise 7x7: a CTA owns an 8x16 pixel tile x 64 channels.  The (14 x 22) halo tile and the 49x64 weights are
+// staged in shared memory; a thread computes 4 consecutive pixels of one row for 8 channels, so one filter row costs
+// 10 input + 14 weight 16-byte shared loads for 224 FMAs.  Output: pre-LayerNorm values, 16-bit NHWC.
+static constexpr int kDwTH = 8, kDwTW = 16, kDwC = 64;
+__global__ void __launch_bounds__(256) dwconv7_kernel(pssr_dwln_desc_t d, int fp16) {
+  extern __shared__ __align__(16) uint8_t dw_sm[];
+  uint4* tile = reinterpret_cast<uint4*>(dw_sm);                        // [row][col][8-ch group], 16 B each
+  float* wsm = reinterpret_cast<float*>(dw_sm + (kDwTH + 6) * (kDwTW + 6) * (kDwC / 8) * 16);   // [49][64]
+  float* bsm = wsm + 49 * kDwC;
+  const int tiles_x = (d.W + kDwTW - 1) / kDwTW, tiles_y = (d.H + kDwTH - 1) / kDwTH;
+  int bid = blockIdx.x;
+  const int tx = bid % tiles_x; bid /= tiles_x;
+  const int ty = bid % tiles_y; bid /= tiles_y;
+  const int slabs = (d.C + kDwC - 1) / kDwC;
+  const int sl = bid % slabs;
+  const int n = bid / slabs;
+  const int c_base = sl * kDwC;
+  const int cw = d.C - c_base < kDwC ? d.C - c_base : kDwC;   // channels in this slab (multiple of 8)
+  const int x0 = tx * kDwTW, y0 = ty * kDwTH;
+  const uint16_t* in = reinterpret_cast<const uint16_t*>(d.in) + d.in_choff + c_base;
+  for (int i = threadIdx.x; i < 49 * kDwC; i += 256) {
+    const int t = i / kDwC, c = i % kDwC;
+    wsm[i] = c < cw ? d.dw_w[(size_t)t * d.C + c_base + c] : 0.f;
+  }
+  if (threadIdx.x < kDwC) bsm[threadIdx.x] = threadIdx.x < cw ? d.dw_b[c_base + threadIdx.x] : 0.f;
+  for (int i = threadIdx.x; i < (kDwTH + 6) * (kDwTW + 6) * 8; i += 256) {
+    const int g = i & 7, pp = i >> 3;
+    const int yy = y0 + pp / (kDwTW + 6) - 3, xx = x0 + pp % (kDwTW + 6) - 3;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (yy >= 0 && yy < d.H && xx >= 0 && xx < d.W && g * 8 < cw)
+      v = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)n * d.H + yy) * d.W + xx) * d.in_cstride + g * 8));
+    tile[i] = v;
+  }
+  __syncthreads();
+  const int g = threadIdx.x & 7;             // channel group
+  const int xq = (threadIdx.x >> 3) & 3;     // which 4-pixel quad of the 16-wide row
+  const int row = threadIdx.x >> 5;          // 0..7
+  float acc[4][8];
+#pragma unroll
+  for (int p4 = 0; p4 < 4; ++p4)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[p4][j] = bsm[g * 8 + j];
+  for (int ky = 0; ky < 7; ++ky) {
+    float wr[7][8];
+#pragma unroll
+    for (int kx = 0; kx < 7; ++kx) {
+      const float4 w0 = *reinterpret_cast<const float4*>(wsm + (ky * 7 + kx) * kDwC + g * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(wsm + (ky * 7 + kx) * kDwC + g * 8 + 4);
+      wr[kx][0] = w0.x; wr[kx][1] = w0.y; wr[kx][2] = w0.z; wr[kx][3] = w0.w; wr[kx][4] = w1.x; wr[kx][5] = w1.y; wr[kx][6] = w1.z; wr[kx][7] = w1.w;
+    }
+    const uint4* trow = tile + ((row + ky) * (kDwTW + 6) + xq * 4) * 8 + g;
+#pragma unroll
+    for (int cx = 0; cx < 10; ++cx) {        // input column (xq*4 - 3 + cx): tap (cx - p4) of output pixel p4
+      float f[8];
+      unpack8(trow[cx * 8], f, fp16);
+#pragma unroll
+      for (int p4 = 0; p4 < 4; ++p4) {
+        const int kx = cx - p4;
+        if (kx >= 0 && kx < 7) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[p4][j] = fmaf(f[j], wr[kx][j], acc[p4][j]);
+        }
+      }
+    }
+  }
+  const int y = y0 + row;
+  if (y < d.H && g * 8 < cw) {
+    uint16_t* out = reinterpret_cast<uint16_t*>(d.out) + d.out_choff + c_base + g * 8;
+#pragma unroll
+    for (int p4 = 0; p4 < 4; ++p4) {
+      const int x = x0 + xq * 4 + p4;
+      if (x < d.W) *reinterpret_cast<uint4*>(out + (((size_t)n * d.H + y) * d.W + x) * d.out_cstride) = pack8(acc[p4], fp16);
+    }
+  }
+}
+
+int ln_launch(const pssr_ln_desc_t& d, int dtype, cudaStream_t stream);
 
 int dwln_launch(const pssr_dwln_desc_t& d, int dtype, cudaStream_t stream) {
   PSSR_REQUIRE(d.C % 8 == 0 && d.C <= 256 * kMaxGroupsPerLane, PSSR_EUNSUP, "dwconv: C=%d unsupported", d.C);
   PSSR_REQUIRE(d.in_cstride % 8 == 0 && d.in_choff % 8 == 0 && d.out_cstride % 8 == 0 && d.out_choff % 8 == 0, PSSR_EUNSUP, "dwconv: alignment");
   PSSR_REQUIRE(((uintptr_t)d.dw_w & 15) == 0 && ((uintptr_t)d.dw_b & 15) == 0, PSSR_EINVAL, "dwconv: weights misaligned");
-  const long long total = (long long)d.B * d.H * d.W;
-  long long blocks = (total + 7) / 8;
-  const long long cap = (long long)device_sm_count() * 16;
-  if (blocks > cap) blocks = cap;
-  dwln_kernel<<<(int)blocks, 256, 0, stream>>>(d, dtype == PSSR_DT_FP16);
+  if (getenv("PSSR_DWLN_FUSED") != nullptr) {      // single fused kernel (one warp per pixel pair), kept for comparison
+    const long long total = (long long)d.B * d.H * ((d.W + 1) / 2);
+    long long blocks = (total + 7) / 8;
+    const long long cap = (long long)device_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    dwln_kernel<<<(int)blocks, 256, 0, stream>>>(d, dtype == PSSR_DT_FP16);
+    count_launch();
+    PSSR_CHECK_CUDA(cudaGetLastError());
+    return PSSR_OK;
+  }
+  const long long blocks = (long long)d.B * ((d.C + kDwC - 1) / kDwC) * ((d.H + kDwTH - 1) / kDwTH) * ((d.W + kDwTW - 1) / kDwTW);
+  PSSR_REQUIRE(blocks < (1ll << 31), PSSR_EUNSUP, "dwconv: too many blocks");
+  const size_t smem = (size_t)(kDwTH + 6) * (kDwTW + 6) * (kDwC / 8) * 16 + (49 * kDwC + kDwC) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PSSR_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_set = true;
+  }
+  dwconv7_kernel<<<(unsigned)blocks, 256, smem, stream>>>(d, dtype == PSSR_DT_FP16);
   count_launch();
   PSSR_CHECK_CUDA(cudaGetLastError());
-  return PSSR_OK;
+  pssr_ln_desc_t ln;
+  memset(&ln, 0, sizeof(ln));
+  ln.in = d.out; ln.in_cstride = d.out_cstride; ln.in_choff = d.out_choff; ln.C = d.C; ln.B = d.B; ln.H = d.H; ln.W = d.W; ln.s2d = 1;
+  ln.w = d.ln_w; ln.b = d.ln_b; ln.eps = d.eps; ln.out = d.out; ln.out_cstride = d.out_cstride; ln.out_choff = d.out_choff;
+  return ln_launch(ln, dtype, stream);     // in place: a warp reads its whole pixel before writing it
 }
 
 // -------------------------------------------------------------------------------- ese

@@ -571,7 +571,9 @@ class RDResUNet(_PlanModule):
             return pack_weight([wt], plan.dtype, 1, n_pad), bias.contiguous(), (extra.contiguous() if extra is not None else None)
 
         def r32(v):
-            return ceil_div(v, 32) * 32
+            # GEMM N padding: wide layers get 128-column tiles (full-rate tcgen05 N), narrow ones waste as little as possible
+            q = 128 if v >= 512 else (64 if v > 128 else 32)
+            return ceil_div(v, q) * q
 
         for i, mods in enumerate(stage_mods):
             hh, ww = hw[i]
