@@ -36,6 +36,9 @@ const char* pssr_version(void);
 /* Number of kernels this library has launched so far in this process (bench.py's
  * gpu_launches counter). */
 int64_t pssr_launch_count(void);
+/* Developer diagnostic (no reference counterpart): copies the convolution kernels' per-CTA clock64 timeline
+ * (recorded only while the environment variable PSSR_DBG has bit 16 set) into `out` (n <= 148*128 int64). */
+int pssr_debug_trace(int64_t* out, int64_t n);
 
 /* ------------------------------------------------------------------------------------
  * Family 1: fused crappify  (pssr/data.py:471-495 `_gen_pair`, :629-638 `_sliding_window`,

@@ -13,7 +13,7 @@ from ctypes import (POINTER, Structure, Union, c_char_p, c_double, c_float, c_in
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libpssr_b200.so")
-SOURCES = ["api.cu", "conv_igemm.cu", "conv_strip.cu", "net_aux.cu", "rdnet.cu", "crappify.cu", "stitch.cu", "metrics.cu"]
+SOURCES = ["api.cu", "conv_igemm.cu", "conv_strip.cu", "conv_v3.cu", "net_aux.cu", "rdnet.cu", "crappify.cu", "stitch.cu", "metrics.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
@@ -161,6 +161,7 @@ SYMBOLS = {
     "pssr_last_error": (c_char_p, []),
     "pssr_version": (c_char_p, []),
     "pssr_launch_count": (c_int64, []),
+    "pssr_debug_trace": (c_int32, [c_void_p, c_int64]),
     "pssr_crappify": (c_int32, [POINTER(CrappifyArgs), c_void_p]),
     "pssr_noise_chain": (c_int32, [c_void_p, c_int32, c_void_p, c_int64, POINTER(NoiseStage), c_int32, c_int32, c_uint64, c_void_p]),
     "pssr_resize_bilinear": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),

@@ -36,6 +36,10 @@ extern "C" {
 const char* pssr_last_error(void) { return g_err; }
 const char* pssr_version(void) { return "pssr_b200 0.1 sm_100a"; }
 int64_t pssr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+int pssr_debug_trace(int64_t* out, int64_t n) {
+  PSSR_REQUIRE(out != nullptr && n > 0, PSSR_EINVAL, "debug_trace: bad arguments");
+  return strip_trace_fetch(reinterpret_cast<long long*>(out), (int)n);
+}
 
 int pssr_plan_create(const pssr_op_t* ops, int32_t n_ops, int32_t dtype, pssr_plan_t** out) {
   PSSR_REQUIRE(ops != nullptr && n_ops > 0 && out != nullptr, PSSR_EINVAL, "plan_create: bad arguments");
@@ -54,7 +58,9 @@ int pssr_plan_create(const pssr_op_t* ops, int32_t n_ops, int32_t dtype, pssr_pl
     switch (op.kind) {
       case PSSR_OP_CONV: {
         ConvOp c;
-        int rc = strip_supported(op.u.conv) ? strip_prepare(op.u.conv, dtype, c) : conv_prepare(op.u.conv, dtype, c);
+        int rc = v3_supported(op.u.conv)      ? v3_prepare(op.u.conv, dtype, c)
+                 : strip_supported(op.u.conv) ? strip_prepare(op.u.conv, dtype, c)
+                                              : conv_prepare(op.u.conv, dtype, c);
         if (rc != PSSR_OK) {
           char msg[400];
           snprintf(msg, sizeof(msg), "%s", g_err);
@@ -115,7 +121,8 @@ int pssr_plan_run_range(pssr_plan_t* plan, int32_t first, int32_t count, void* s
       case PSSR_OP_CONV: {
         const int ci = plan->conv_index[i];
         const void* tm = reinterpret_cast<uint8_t*>(plan->tmaps_dev) + (size_t)ci * 4 * sizeof(CUtensorMap);
-        rc = plan->convs[ci].variant == 2 ? strip_launch(plan->convs[ci], tm, st) : conv_launch(plan->convs[ci], tm, st);
+        const int variant = plan->convs[ci].variant;
+        rc = variant == 3 ? v3_launch(plan->convs[ci], tm, st) : variant == 2 ? strip_launch(plan->convs[ci], tm, st) : conv_launch(plan->convs[ci], tm, st);
         break;
       }
       case PSSR_OP_PREP:

@@ -67,9 +67,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.  The slow path is a
+// separate function so that the unrolled MMA-issue loops stay small.
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   long long t0 = clock64();
   uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -79,6 +79,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 
 // true in exactly one (converged) lane of the warp

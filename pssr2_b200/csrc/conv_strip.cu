@@ -62,6 +62,14 @@ struct StripKParams {
   float* tail_z;              // fp32 planar [B][r*r*9][H][W]
 };
 
+// developer timeline (PSSR_DBG bit 16): per CTA 128 clock64 stamps -- [0] entry, [1] setup done, [2+2u] unit u first MMA issued,
+// [3+2u] unit u committed, [64+2u] unit u accumulators ready (epilogue side), [65+2u] unit u epilogue done, [127] exit
+__device__ long long g_strip_trace[148 * 256];
+#define STRIP_TRACE(slot)                                                                                   \
+  do {                                                                                                      \
+    if ((p.dbg & 16) && lane == 0 && (slot) < 127) g_strip_trace[(blockIdx.x % 148) * 256 + (slot)] = clock64(); \
+  } while (0)
+
 __device__ __forceinline__ uint64_t strip_desc(uint32_t addr, int mode) {
   uint64_t d = (uint64_t)((addr >> 4) & 0x3FFFu);
   d |= (uint64_t)(1024u >> 4) << 32;
@@ -97,6 +105,7 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (warp == 1) STRIP_TRACE(0);
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + 2u * p.a_bytes;
@@ -132,6 +141,7 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  if (warp == 1) STRIP_TRACE(1);
   const int block_n = p.block_n;
   const int T = p.T;
   const int unit_q = 128 * T;
@@ -216,6 +226,7 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
     int as = 0, bs = 0;
     uint32_t aphase = 0, bphase = 0;
     int it = 0;
+    int trace_stage = 0;
     for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x, ++it) {
       const int um = unit / p.n_tiles;
       const int qa = p.q_begin + um * (128 * T);
@@ -235,12 +246,14 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
         for (int cb = 0; cb < p.seg_cblocks[sg]; ++cb) {
           mbar_wait(a_full(as), aphase);
           tc_fence_after();
+          if (first) STRIP_TRACE(2 + 2 * it);
           // descriptor of the unit's first pixel row in this A buffer; +8 per 128-byte row, +2 per 16 K elements
           const uint64_t adesc0 = strip_desc(a_base + (uint32_t)as * p.a_bytes + (uint32_t)row_off0 * 128u, 0);
           const int gs = taps == 9 ? p.G : 1;
           for (int t0 = 0; t0 < taps; t0 += gs) {
             mbar_wait(b_full(bs), bphase);
             tc_fence_after();
+            if ((p.dbg & 16) && it == 1 && lane == 0 && trace_stage < 128) g_strip_trace[(blockIdx.x % 148) * 256 + 128 + trace_stage++] = clock64();
             if (elect_one()) {
               for (int tt = 0; tt < gs; ++tt) {
                 const int t = t0 + tt;
@@ -270,6 +283,7 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
       }
       if (elect_one()) umma_commit(t_full(buf));
       __syncwarp();
+      STRIP_TRACE(3 + 2 * it);
     }
   } else if (warp >= 4) {
     // ==================================== epilogue ==========================================
@@ -290,6 +304,7 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
       const uint32_t use = p.tmem_bufs == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
       mbar_wait(t_full(buf), use & 1u);
       tc_fence_after();
+      if (warp == 4) STRIP_TRACE(64 + 2 * it);
       for (int item = eg; item < tv * npairs; item += 2) {
         const int mt = item / npairs;
         const int pi = item - mt * npairs;
@@ -418,6 +433,7 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(t_empty(buf));
+      if (warp == 4) STRIP_TRACE(65 + 2 * it);
     }
   }
 
@@ -426,7 +442,14 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+    if ((p.dbg & 16) && lane == 0) g_strip_trace[(blockIdx.x % 148) * 256 + 127] = clock64();
   }
+}
+
+int strip_trace_fetch(long long* host, int n) {
+  if (n > 148 * 256) n = 148 * 256;
+  PSSR_CHECK_CUDA(cudaMemcpyFromSymbol(host, g_strip_trace, sizeof(long long) * (size_t)n));
+  return PSSR_OK;
 }
 
 // --------------------------------------------------------------------------------- host

@@ -1,0 +1,827 @@
+// Lean-issue implicit-GEMM convolution (v3 of the tcgen05 path) -- runs every stride-1 3x3 / 1x1 convolution of the
+// network forward whose output is at least 32 pixels wide (pssr/models/_blocks.py:15-41, resunet.py:65-96,
+// rdresunet.py:104-130).
+//
+// What the B200 measurements behind this kernel say (scripts/ubench/*.cu, profiles/r01_ubench_mma.txt):
+//   * one warp issues tcgen05.mma into a SHALLOW queue: every instruction the issuing warp executes between two MMAs is
+//     on the critical path (~6 cycles each), and one mbarrier poll costs ~100 unhidden cycles unless the MMA is 128 cycles
+//     long.  The v2 loop (runtime tap arithmetic, ~100 instructions per 4 MMAs) ran N=256 MMAs at 163 cycles instead of
+//     128 and N=64 MMAs at 75-89 instead of 48.  Here the loop is a template: taps, tiles and K steps are unrolled,
+//     descriptors are base + compile-time constant, a stage holds G taps (up to the whole layer, "resident" weights).
+//   * M=128 x N=64 x K=16 costs 48 cycles (shared-memory operand reads), N=128 64, N=192 96, N=256 128.
+//   * the A operand in TMEM (TS mode) works with lane = row, column = k/2, low half = even k; the fused Reconstruction
+//     tail uses it: the epilogue writes relu(acc + bias) back to TMEM as 16-bit and the tensor core projects it on the
+//     nine tail taps (N = 16), instead of 9216 fp32 FMAs per pixel on the CUDA cores.
+//
+// Pixel space.  "flat" mode = v2's: the batch is one sequence of zero-padded pixels q = (v*(H+2) + y+1)*(W+2) + x+1 and a
+// unit is T consecutive 128-pixel tiles; its input pixels [q0-P-1, q0+128T+P+1) are staged by per-row TMA boxes at a FIXED
+// offset inside the stage buffer, so every MMA descriptor is a kernel-lifetime constant.  "rows" mode (W % 128 == 0: the
+// 128^2 / 256^2 layers, where the flat halo is 5x the tile) = a tile is one 128-pixel image row segment, a unit is T rows
+// of one image, staged with their two halo rows by ONE 4-D TMA box; no MMA is spent on padding columns.
+//
+// Warps: 0 = A producer, 1 = MMA issuer + TMEM owner, 2 = B producer, 3 idle, 4..11 = epilogue (two per TMEM lane quarter).
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+#include "common.cuh"
+#include "plan.h"
+
+namespace pssr {
+
+static constexpr int kV3Threads = 384;
+static constexpr int kV3MaxB = 8;
+
+struct V3Params {
+  const CUtensorMap* tmaps;   // device: [0..2] sources, [3] weights
+  int n_segs;
+  int seg_src[4], seg_taps[4], seg_cblocks[4], seg_kb0[4];
+  int num_kb;
+  int H, W, B, P, IP, pad, HP, NJ, Wb;
+  int rows_mode;              // 1: tile = one 128-pixel row segment (W % 128 == 0)
+  int total_vrows;            // rows mode: B * NJ * H
+  int q_begin, q_end;         // flat mode
+  int off_px;                 // pixel offset of a unit's first pixel inside an A stage buffer
+  uint32_t tile_step;         // descriptor units (16 B) between the A operands of consecutive tiles of a unit
+  uint32_t a_bytes, a_tx_bytes, b_bytes, tap_bytes;
+  int b_stages;
+  int units_m, n_tiles, total_units;
+  int block_n, n_valid, n_total, wide_store;
+  int dbg;
+  const float* bias;
+  const float* out_scale;
+  uint16_t* out;
+  float* out_f32;
+  int out_cstride, out_choff, shuffle, cps, act, fp16;
+  int Hout, Wout;
+  const float* tail_w;        // fused Reconstruction tail: fp32 [9][64]
+  float* tail_z;              // fp32 planar [B][r*r*9][H][W]
+};
+
+__device__ __forceinline__ uint64_t v3_desc(uint32_t addr) {
+  uint64_t d = (uint64_t)((addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// D (+)= A * B^T with the accumulate flag as an immediate / a register
+__device__ __forceinline__ void v3_mma_acc(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc) {
+  asm volatile("tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, 1;" ::"r"(d), "l"(a), "l"(b), "r"(idesc) : "memory");
+}
+__device__ __forceinline__ void v3_mma_p(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// A operand in TMEM (16-bit pairs: lane = row, column = k/2)
+__device__ __forceinline__ void v3_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void v3_tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void v3_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void v3_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void v3_st_global_v8(void* ptr, const uint32_t (&o)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
+               "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
+               : "memory");
+}
+// exact-erf GELU (nn.GELU(), _rdnet.py:186), erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 << 16-bit output rounding)
+__device__ __forceinline__ float v3_gelu(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = 1.0f - poly * t * __expf(-z * z);
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
+
+// T tiles per unit, G filter taps per weight stage (3x3 segments), RES: the whole layer's weights stay in shared memory,
+// TAIL: fused Reconstruction tail (block_n = 256, T = 1, 64 channels per pixel-shuffle sub-position)
+template <int T, int G, bool RES, bool TAIL>
+__global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_constant__ V3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bars[4 + 2 * kV3MaxB + 8];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + 2u * p.a_bytes;
+  const uint32_t b_total = RES ? (uint32_t)p.num_kb * p.tap_bytes : (uint32_t)p.b_stages * p.b_bytes;
+  const uint32_t tailw_off = 2u * p.a_bytes + b_total;                     // 16 x 128 B, 1024-aligned
+  const uint32_t vec_off = tailw_off + (TAIL ? 2048u : 0u);
+  float* bias_s = reinterpret_cast<float*>(smem_al + vec_off);
+  float* scale_s = bias_s + p.n_total;
+  for (int i = threadIdx.x; i < p.n_total; i += kV3Threads) {
+    bias_s[i] = p.bias[i];
+    if (p.out_scale != nullptr) scale_s[i] = p.out_scale[i];
+  }
+  if (TAIL) {
+    // tail weights [9][64] fp32 -> 16-bit K-major SWIZZLE_128B operand tile [16 taps x 64 channels] (rows 9..15 zero)
+    for (int i = threadIdx.x; i < 16 * 64; i += kV3Threads) {
+      const int t = i >> 6, c = i & 63;
+      const float w = t < 9 ? p.tail_w[t * 64 + c] : 0.f;
+      const int chunk = (c >> 3) ^ (t & 7);
+      reinterpret_cast<uint16_t*>(smem_al + tailw_off + t * 128 + chunk * 16)[c & 7] = pack1(w, p.fp16);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  const uint32_t bar0 = smem_u32(bars);
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 8u * (2 + s); };
+  auto b_full = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto b_empty = [&](int s) { return bar0 + 8u * (4 + kV3MaxB + s); };
+  auto t_full = [&](int b) { return bar0 + 8u * (4 + 2 * kV3MaxB + b); };
+  auto t_empty = [&](int b) { return bar0 + 8u * (4 + 2 * kV3MaxB + 2 + b); };
+  auto p_full = [&](int b) { return bar0 + 8u * (4 + 2 * kV3MaxB + 4 + b); };
+  auto z_full = [&](int b) { return bar0 + 8u * (4 + 2 * kV3MaxB + 6 + b); };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < kV3MaxB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(t_full(b), 1); mbar_init(t_empty(b), 8); mbar_init(p_full(b), 8); mbar_init(z_full(b), 1); }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  const int block_n = p.block_n;
+
+  if (warp == 0) {
+    // ============================ A producer ================================================
+    if (lane == 0) {
+      int as = 0;
+      uint32_t aphase = 0;
+      const int rows_total = p.B * p.NJ * p.HP;
+      for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
+        const int um = unit / p.n_tiles;
+        int c1 = 0, c2 = 0, c3 = 0, qa = 0, r0 = 0, nrows = 0;
+        if (p.rows_mode) {
+          const int vr0 = um * T;
+          const int v = vr0 / p.H;
+          const int n = v / p.NJ;
+          c1 = (v - n * p.NJ) * 128 - 1;
+          c2 = vr0 - v * p.H - 1;
+          c3 = n;
+        } else if (p.pad) {
+          qa = p.q_begin + um * (128 * T);
+          r0 = (qa - p.P - 1) / p.P;
+          int r1 = (qa + 128 * T + p.P) / p.P;
+          if (r1 > rows_total - 1) r1 = rows_total - 1;
+          nrows = r1 - r0 + 1;
+        } else {
+          qa = um * (128 * T);
+        }
+        for (int sg = 0; sg < p.n_segs; ++sg) {
+          const CUtensorMap* tm = p.tmaps + p.seg_src[sg];
+          for (int cb = 0; cb < p.seg_cblocks[sg]; ++cb) {
+            mbar_wait(a_empty(as), aphase ^ 1u);
+            const uint32_t dst0 = a_base + (uint32_t)as * p.a_bytes;
+            if (p.rows_mode) {
+              mbar_arrive_expect_tx(a_full(as), p.a_tx_bytes);
+              tma_load_4d(dst0, tm, a_full(as), cb * 64, c1, c2, c3);
+            } else if (p.pad) {
+              mbar_arrive_expect_tx(a_full(as), (uint32_t)nrows * (uint32_t)p.P * 128u);
+              for (int r = 0; r < nrows; ++r) {
+                const int rho = r0 + r;
+                const int v = rho / p.HP;
+                const int py = rho - v * p.HP;
+                const int n = v / p.NJ;
+                const int j = v - n * p.NJ;
+                const uint32_t dst = dst0 + (uint32_t)(rho * p.P - qa + p.off_px) * 128u;
+                tma_load_4d(dst, tm, a_full(as), cb * 64, j * p.Wb - 1, py - 1, n);
+              }
+            } else {
+              mbar_arrive_expect_tx(a_full(as), (uint32_t)(128 * T) * 128u);
+              tma_load_2d(dst0, tm, a_full(as), cb * 64, qa);
+            }
+            as ^= 1;
+            if (as == 0) aphase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ================================ B producer: weights ===================================
+    if (lane == 0) {
+      const CUtensorMap* tmB = p.tmaps + 3;
+      if (RES) {
+        mbar_arrive_expect_tx(b_full(0), (uint32_t)p.num_kb * p.tap_bytes);
+        for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(b_base + (uint32_t)kb * p.tap_bytes, tmB, b_full(0), kb * 64, 0);
+      } else {
+        int bs = 0;
+        uint32_t bphase = 0;
+        for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
+          const int n_tile = unit % p.n_tiles;
+          for (int sg = 0; sg < p.n_segs; ++sg) {
+            const int taps = p.seg_taps[sg], cbs = p.seg_cblocks[sg];
+            const int gs = taps == 9 ? G : 1;
+            for (int cb = 0; cb < cbs; ++cb) {
+              for (int t0 = 0; t0 < taps; t0 += gs) {
+                mbar_wait(b_empty(bs), bphase ^ 1u);
+                mbar_arrive_expect_tx(b_full(bs), (uint32_t)gs * p.tap_bytes);
+                for (int t = 0; t < gs; ++t) {
+                  const int kb = p.seg_kb0[sg] + (t0 + t) * cbs + cb;   // weights are packed tap-major, then channel block
+                  tma_load_2d(b_base + (uint32_t)bs * p.b_bytes + (uint32_t)t * p.tap_bytes, tmB, b_full(bs), kb * 64, n_tile * block_n);
+                }
+                if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================== MMA issuer ==========================================
+    // The whole warp walks the loops (warp-uniform control flow); one elected lane issues the tcgen05 instructions.
+    const uint32_t idesc = umma_idesc_f16(p.fp16 ? 0 : 1, block_n);
+    const uint32_t idesc_tail = umma_idesc_f16(p.fp16 ? 0 : 1, 16);
+    const uint64_t tdesc = v3_desc(smem_base + tailw_off);
+    const uint64_t adesc_s0 = v3_desc(a_base + (uint32_t)p.off_px * 128u);
+    const uint64_t adesc_s1 = adesc_s0 + (uint64_t)(p.a_bytes >> 4);
+    const uint64_t bdesc0 = v3_desc(b_base);
+    const uint32_t bstep = p.b_bytes >> 4, tapstep = p.tap_bytes >> 4;
+    const int64_t P8 = (int64_t)p.P * 8;
+    const uint64_t tile_step = p.tile_step;
+    int as = 0, bs = 0;
+    uint32_t aphase = 0, bphase = 0;
+    int it = 0;
+
+    auto issue_tail = [&](int pit) {
+      const int pbuf = pit & 1;
+      mbar_wait(p_full(pbuf), (uint32_t)(pit >> 1) & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t cbase = tmem_base + (uint32_t)(pbuf * 256);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          const uint32_t region = (uint32_t)((s >> 1) * 128);
+          const uint32_t a_col = cbase + region + (uint32_t)((s & 1) * 32);
+          const uint32_t d_col = cbase + region + 64u + (uint32_t)((s & 1) * 16);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v3_mma_ts(d_col, a_col + 8u * k, tdesc + 2u * k, idesc_tail, k ? 1u : 0u);
+        }
+        umma_commit(z_full(pbuf));
+      }
+      __syncwarp();
+    };
+
+    if (RES) {
+      mbar_wait(b_full(0), 0);
+      tc_fence_after();
+    }
+    for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(t_empty(buf), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + (uint32_t)(buf * 256);
+      uint32_t acc = 0;
+      bool tail_done = false;
+      for (int sg = 0; sg < p.n_segs; ++sg) {
+        const bool nine = p.seg_taps[sg] == 9;
+        const int cbs = p.seg_cblocks[sg];
+        for (int cb = 0; cb < cbs; ++cb) {
+          mbar_wait(a_full(as), aphase);
+          tc_fence_after();
+          const uint64_t ad0 = as ? adesc_s1 : adesc_s0;
+          if (nine) {
+#pragma unroll
+            for (int t0 = 0; t0 < 9; t0 += G) {
+              uint64_t bd;
+              if (RES) {
+                bd = bdesc0 + (uint64_t)((uint32_t)(p.seg_kb0[sg] + t0 * cbs + cb) * tapstep);
+              } else {
+                mbar_wait(b_full(bs), bphase);
+                tc_fence_after();
+                bd = bdesc0 + (uint64_t)((uint32_t)bs * bstep);
+              }
+              const uint64_t btap = RES ? (uint64_t)((uint32_t)cbs * tapstep) : (uint64_t)tapstep;
+              if (elect_one()) {
+#pragma unroll
+                for (int tt = 0; tt < G; ++tt) {
+                  const int t = t0 + tt;
+                  const int dy = t / 3 - 1, dx = t % 3 - 1;
+                  const uint64_t adt = ad0 + (uint64_t)(dy * P8 + dx * 8);
+                  const uint64_t bdt = bd + (uint64_t)tt * btap;
+#pragma unroll
+                  for (int mt = 0; mt < T; ++mt) {
+                    const uint64_t adm = adt + (uint64_t)mt * tile_step;
+                    const uint32_t dcol = d0 + (uint32_t)(mt * block_n);
+                    if (tt == 0) v3_mma_p(dcol, adm, bdt, idesc, acc);
+                    else v3_mma_acc(dcol, adm, bdt, idesc);
+                    v3_mma_acc(dcol, adm + 2, bdt + 2, idesc);
+                    v3_mma_acc(dcol, adm + 4, bdt + 4, idesc);
+                    v3_mma_acc(dcol, adm + 6, bdt + 6, idesc);
+                  }
+                }
+                if (!RES) umma_commit(b_empty(bs));
+              }
+              __syncwarp();
+              acc = 1;
+              if (!RES) { if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; } }
+              if (TAIL && t0 == 6 && !tail_done) {
+                // the previous unit's 16-bit activations are in TMEM by now: project them on the nine tail taps
+                if (it > 0) issue_tail(it - 1);
+                tail_done = true;
+              }
+            }
+          } else {
+            uint64_t bd;
+            if (RES) {
+              bd = bdesc0 + (uint64_t)((uint32_t)(p.seg_kb0[sg] + cb) * tapstep);
+            } else {
+              mbar_wait(b_full(bs), bphase);
+              tc_fence_after();
+              bd = bdesc0 + (uint64_t)((uint32_t)bs * bstep);
+            }
+            if (elect_one()) {
+#pragma unroll
+              for (int mt = 0; mt < T; ++mt) {
+                const uint64_t adm = ad0 + (uint64_t)mt * tile_step;
+                const uint32_t dcol = d0 + (uint32_t)(mt * block_n);
+                v3_mma_p(dcol, adm, bd, idesc, acc);
+                v3_mma_acc(dcol, adm + 2, bd + 2, idesc);
+                v3_mma_acc(dcol, adm + 4, bd + 4, idesc);
+                v3_mma_acc(dcol, adm + 6, bd + 6, idesc);
+              }
+              if (!RES) umma_commit(b_empty(bs));
+            }
+            __syncwarp();
+            acc = 1;
+            if (!RES) { if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; } }
+          }
+          if (elect_one()) umma_commit(a_empty(as));
+          __syncwarp();
+          as ^= 1;
+          if (as == 0) aphase ^= 1u;
+        }
+      }
+      if (TAIL && !tail_done && it > 0) issue_tail(it - 1);
+      if (elect_one()) umma_commit(t_full(buf));
+      __syncwarp();
+    }
+    if (TAIL && it > 0) issue_tail(it - 1);
+  } else if (warp >= 4) {
+    // ==================================== epilogue ==========================================
+    const int q4 = warp & 3;
+    const int eg = (warp - 4) >> 2;           // epilogue group 0 / 1
+    const int row = q4 * 32 + lane;
+    const int r = p.shuffle;
+    const int npairs = (block_n + 63) / 64;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    int it = 0;
+    for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x, ++it) {
+      const int n_tile = unit % p.n_tiles;
+      const int um = unit / p.n_tiles;
+      const int buf = it & 1;
+      const uint32_t par = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(t_full(buf), par);
+      tc_fence_after();
+      if (TAIL) {
+        // ---- phase 1: relu(acc + bias) -> 16-bit, written back over the accumulator's own columns ------------------
+        const uint32_t region = lane_addr + (uint32_t)(buf * 256 + eg * 128);
+        const int nb0 = n_tile * 256 + eg * 128;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(region + (uint32_t)(c * 32), v);
+          tmem_ld_wait();
+          uint32_t o[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 bb = *reinterpret_cast<const float4*>(bias_s + nb0 + c * 32 + 4 * j4);
+            const float f0 = fmaxf(__uint_as_float(v[4 * j4 + 0]) + bb.x, 0.f);
+            const float f1 = fmaxf(__uint_as_float(v[4 * j4 + 1]) + bb.y, 0.f);
+            const float f2 = fmaxf(__uint_as_float(v[4 * j4 + 2]) + bb.z, 0.f);
+            const float f3 = fmaxf(__uint_as_float(v[4 * j4 + 3]) + bb.w, 0.f);
+            o[2 * j4 + 0] = pack2(f0, f1, p.fp16);
+            o[2 * j4 + 1] = pack2(f2, f3, p.fp16);
+          }
+          v3_tmem_st16(region + (uint32_t)(c * 16), o);
+        }
+        v3_tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(buf));
+        // ---- phase 2: the nine per-tap projections of this thread's pixel, two sub-positions per warp -------------
+        int n, y, x;
+        bool valid;
+        if (p.rows_mode) {
+          const int vr = um;                      // T == 1
+          const int v = vr / p.H;
+          y = vr - v * p.H;
+          n = v / p.NJ;
+          x = (v - n * p.NJ) * 128 + row;
+          valid = vr < p.total_vrows;
+        } else {
+          const int q = p.q_begin + um * 128 + row;
+          const int vimg = q / p.IP;
+          const int rem = q - vimg * p.IP;
+          const int py = rem / p.P;
+          const int px = rem - py * p.P;
+          n = vimg / p.NJ;
+          x = (vimg - n * p.NJ) * p.Wb + px - 1;
+          y = py - 1;
+          valid = (q < p.q_end) && px >= 1 && px < p.Wb + 1 && x < p.W && py >= 1 && py < p.H + 1;
+        }
+        mbar_wait(z_full(buf), par);
+        tc_fence_after();
+        const int planes = r * r * 9;
+        const size_t plane = (size_t)p.H * p.W;
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          uint32_t zv[16];
+          v3_tmem_ld16(region + 64u + (uint32_t)(sl * 16), zv);
+          tmem_ld_wait();
+          if (valid && !(p.dbg & 1)) {
+            const int sub = n_tile * 4 + eg * 2 + sl;
+            float* zp = p.tail_z + (((size_t)n * planes + (size_t)sub * 9) * p.H + y) * p.W + x;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) zp[(size_t)t * plane] = __uint_as_float(zv[t]);
+          }
+        }
+      } else {
+        for (int item = eg; item < T * npairs; item += 2) {
+          const int mt = item / npairs;
+          const int pi = item - mt * npairs;
+          const int c_lo = pi * 64;
+          const int c_hi = c_lo + 64 < block_n ? c_lo + 64 : block_n;
+          int n, y, x;
+          bool valid;
+          if (p.rows_mode) {
+            const int vr = um * T + mt;
+            const int v = vr / p.H;
+            y = vr - v * p.H;
+            n = v / p.NJ;
+            x = (v - n * p.NJ) * 128 + row;
+            valid = vr < p.total_vrows;
+          } else if (p.pad) {
+            const int q = p.q_begin + (um * T + mt) * 128 + row;
+            const int vimg = q / p.IP;
+            const int rem = q - vimg * p.IP;
+            const int py = rem / p.P;
+            const int px = rem - py * p.P;
+            n = vimg / p.NJ;
+            x = (vimg - n * p.NJ) * p.Wb + px - 1;
+            y = py - 1;
+            valid = (q < p.q_end) && px >= 1 && px < p.Wb + 1 && x < p.W && py >= 1 && py < p.H + 1;
+          } else {
+            const int q = (um * T + mt) * 128 + row;
+            n = q / p.IP;
+            const int rem = q - n * p.IP;
+            y = rem / p.P;
+            x = rem - y * p.P;
+            valid = q < p.q_end;
+          }
+          // sub-pixel / channel position of the item's first output column, advanced incrementally
+          int sub = (n_tile * block_n + c_lo) / p.cps;
+          int cc = n_tile * block_n + c_lo - sub * p.cps;
+          int si = sub / r, sj = sub - si * r;
+          const size_t pix00 = ((size_t)n * p.Hout + (size_t)(y * r)) * p.Wout + (size_t)(x * r);
+          const uint32_t taddr = lane_addr + (uint32_t)(buf * 256 + mt * block_n);
+          for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + (uint32_t)c0, v);
+            tmem_ld_wait();
+            const int nbase = n_tile * block_n + c0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int nn = nbase + h * 16;
+              if (h == 1 || c0 > c_lo) {   // advance the (sub-pixel, channel) cursor by 16 columns
+                cc += 16;
+                if (cc >= p.cps) { cc -= p.cps; if (++sj == r) { sj = 0; ++si; } }
+              }
+              if (valid && !(p.dbg & 1) && nn < p.n_valid) {
+                float f[16];
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                  const float4 bb = *reinterpret_cast<const float4*>(bias_s + nn + 4 * j4);
+                  f[4 * j4 + 0] = __uint_as_float(v[h * 16 + 4 * j4 + 0]) + bb.x;
+                  f[4 * j4 + 1] = __uint_as_float(v[h * 16 + 4 * j4 + 1]) + bb.y;
+                  f[4 * j4 + 2] = __uint_as_float(v[h * 16 + 4 * j4 + 2]) + bb.z;
+                  f[4 * j4 + 3] = __uint_as_float(v[h * 16 + 4 * j4 + 3]) + bb.w;
+                }
+                if (p.act == PSSR_ACT_RELU) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+                } else if (p.act == PSSR_ACT_GELU) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) f[j] = v3_gelu(f[j]);
+                }
+                if (p.out_scale != nullptr) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) f[j] *= scale_s[nn + j];
+                }
+                uint32_t o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = pack2(f[2 * j], f[2 * j + 1], p.fp16);
+                if (p.wide_store) {
+                  const size_t pix = pix00 + (size_t)si * p.Wout + (size_t)sj;
+                  v3_st_global_v8(p.out + pix * p.out_cstride + p.out_choff + cc, o);
+                } else {
+#pragma unroll
+                  for (int g = 0; g < 2; ++g) {
+                    const int n8 = nn + g * 8;
+                    if (n8 < p.n_valid) {
+                      const int sub8 = n8 / p.cps;
+                      const int cc8 = n8 - sub8 * p.cps;
+                      const int si8 = sub8 / r, sj8 = sub8 - si8 * r;
+                      const size_t pix = ((size_t)n * p.Hout + (size_t)(y * r + si8)) * p.Wout + (size_t)(x * r + sj8);
+                      if (p.out != nullptr)
+                        *reinterpret_cast<uint4*>(p.out + pix * p.out_cstride + p.out_choff + cc8) = make_uint4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+                      if (p.out_f32 != nullptr) {
+                        float4* d = reinterpret_cast<float4*>(p.out_f32 + pix * p.out_cstride + p.out_choff + cc8);
+                        d[0] = make_float4(f[8 * g + 0], f[8 * g + 1], f[8 * g + 2], f[8 * g + 3]);
+                        d[1] = make_float4(f[8 * g + 4], f[8 * g + 5], f[8 * g + 6], f[8 * g + 7]);
+                      }
+                    }
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty(buf));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// --------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn v3_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || sym == nullptr)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+
+typedef void (*V3Kernel)(const V3Params);
+struct V3Variant { int T, G, RES, TAIL; V3Kernel fn; };
+static const V3Variant kV3Variants[] = {
+    {1, 1, 0, 0, conv_v3_kernel<1, 1, false, false>}, {1, 3, 0, 0, conv_v3_kernel<1, 3, false, false>},
+    {1, 9, 0, 0, conv_v3_kernel<1, 9, false, false>}, {1, 9, 1, 0, conv_v3_kernel<1, 9, true, false>},
+    {2, 1, 0, 0, conv_v3_kernel<2, 1, false, false>}, {2, 3, 0, 0, conv_v3_kernel<2, 3, false, false>},
+    {2, 9, 0, 0, conv_v3_kernel<2, 9, false, false>}, {2, 9, 1, 0, conv_v3_kernel<2, 9, true, false>},
+    {1, 1, 0, 1, conv_v3_kernel<1, 1, false, true>},  {1, 3, 0, 1, conv_v3_kernel<1, 3, false, true>},
+};
+static const int kV3NumVariants = (int)(sizeof(kV3Variants) / sizeof(kV3Variants[0]));
+
+bool v3_supported(const pssr_conv_desc_t& d) {
+  if (getenv("PSSR_CONV_V1") != nullptr || getenv("PSSR_CONV_V2") != nullptr) return false;
+  for (int s = 0; s < d.n_segs; ++s)
+    if (d.segs[s].taps != 1 && d.segs[s].taps != 9) return false;
+  if (d.n % 32 != 0 || d.n < 32) return false;
+  bool any9 = false;
+  for (int s = 0; s < d.n_segs; ++s) any9 = any9 || d.segs[s].taps == 9;
+  // small feature maps: the padded pixel space wastes (1 - HW/((H+2)(W+2))) of the MMAs (36 % at 8x8, 21 % at 16x16)
+  // and the exact-tile kernel (conv_igemm.cu) is faster there
+  if (any9 && d.Wo < 32 && d.tail_z == nullptr) return false;
+  if (d.tail_z != nullptr) {
+    const int cps = d.n_valid / (d.shuffle * d.shuffle);
+    if (cps != 64 || d.n % 256 != 0 || !any9) return false;   // other tail shapes: v2's CUDA-core tail
+  }
+  return true;
+}
+
+int v3_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
+  EncodeTiledFn enc = v3_encode_fn();
+  PSSR_REQUIRE(enc != nullptr, PSSR_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  PSSR_REQUIRE(d.n_srcs >= 1 && d.n_srcs <= 3 && d.n_segs >= 1 && d.n_segs <= 4, PSSR_EINVAL, "conv: n_srcs/n_segs out of range");
+  PSSR_REQUIRE(d.n_valid > 0 && d.n_valid <= d.n && d.n_valid % 8 == 0, PSSR_EUNSUP, "conv: n_valid=%d must be a multiple of 8 and <= n", d.n_valid);
+  PSSR_REQUIRE(d.shuffle >= 1 && d.n_valid % (d.shuffle * d.shuffle) == 0, PSSR_EUNSUP, "conv: n_valid %% shuffle^2 != 0");
+  const int cps = d.n_valid / (d.shuffle * d.shuffle);
+  PSSR_REQUIRE(cps % 8 == 0, PSSR_EUNSUP, "conv: channels after pixel shuffle (%d) must be a multiple of 8", cps);
+  PSSR_REQUIRE(d.shuffle == 1 || d.n == d.n_valid, PSSR_EUNSUP, "conv: padded N with pixel shuffle unsupported");
+  PSSR_REQUIRE(d.out_cstride % 8 == 0 && d.out_choff % 8 == 0, PSSR_EUNSUP, "conv: output channel stride/offset must be multiples of 8");
+  PSSR_REQUIRE(d.out != nullptr || d.out_f32 != nullptr || d.tail_z != nullptr, PSSR_EINVAL, "conv: no output buffer");
+  PSSR_REQUIRE(d.bias != nullptr && ((uintptr_t)d.bias & 15) == 0, PSSR_EINVAL, "conv: bias missing or misaligned");
+  const bool tail = d.tail_z != nullptr;
+  if (tail) {
+    PSSR_REQUIRE(d.tail_weight != nullptr && ((uintptr_t)d.tail_weight & 15) == 0, PSSR_EINVAL, "conv: tail_weight missing or misaligned");
+    PSSR_REQUIRE(cps == 64 && d.act == PSSR_ACT_RELU && d.n == d.n_valid && d.n % 256 == 0, PSSR_EUNSUP,
+                 "conv: the tensor-core tail needs C' = 64, ReLU and N %% 256 == 0");
+  }
+
+  V3Params& p = *reinterpret_cast<V3Params*>(op.kparams);
+  static_assert(sizeof(V3Params) <= sizeof(op.kparams), "ConvOp::kparams too small");
+  memset(&p, 0, sizeof(p));
+  memset(op.tmaps, 0, sizeof(op.tmaps));
+  op.variant = 3;
+
+  int block_n = 256;
+  while (d.n % block_n != 0) block_n >>= 1;
+  p.block_n = block_n;
+  p.n_tiles = d.n / block_n;
+  p.n_valid = d.n_valid;
+  p.n_total = d.n;
+  p.H = d.Ho; p.W = d.Wo; p.B = d.B;
+  p.pad = 0;
+  for (int s2 = 0; s2 < d.n_segs; ++s2)
+    if (d.segs[s2].taps == 9) p.pad = 1;
+  p.NJ = (d.Wo + 127) / 128;
+  p.Wb = (d.Wo + p.NJ - 1) / p.NJ;
+  p.rows_mode = (p.pad && d.Wo % 128 == 0 && getenv("PSSR_V3_FLAT") == nullptr) ? 1 : 0;
+  if (!p.pad) { p.NJ = 1; p.Wb = d.Wo; }
+  p.P = p.Wb + 2 * p.pad;
+  p.HP = d.Ho + 2 * p.pad;
+  p.IP = p.HP * p.P;
+  p.q_begin = p.pad * (p.P + 1);
+  PSSR_REQUIRE((long long)d.B * p.NJ * p.IP < (1ll << 30), PSSR_EUNSUP, "conv: batch x padded image exceeds the 30-bit pixel index");
+  p.q_end = d.B * p.NJ * p.IP - p.pad * (p.P + 1);
+  p.total_vrows = d.B * p.NJ * d.Ho;
+
+  int num_kb = 0;
+  p.n_segs = d.n_segs;
+  for (int s = 0; s < d.n_segs; ++s) {
+    const pssr_kseg_t& sg = d.segs[s];
+    PSSR_REQUIRE(sg.src >= 0 && sg.src < d.n_srcs && sg.cblocks >= 1, PSSR_EINVAL, "conv: bad K segment");
+    p.seg_src[s] = sg.src; p.seg_taps[s] = sg.taps; p.seg_cblocks[s] = sg.cblocks; p.seg_kb0[s] = num_kb;
+    num_kb += sg.taps * sg.cblocks;
+  }
+  p.num_kb = num_kb;
+  p.tap_bytes = (uint32_t)(block_n * 128);
+
+  // T tiles per unit with T * block_n <= 256 (TMEM double-buffered: the epilogue of unit i overlaps the MMAs of unit i+1)
+  int T = 256 / block_n;
+  if (T > 2) T = 2;
+  if (tail) T = 1;
+  if (p.rows_mode && d.Ho % T != 0) T = 1;
+  const char* envT = getenv("PSSR_V3_T");
+  if (envT && atoi(envT) == 1) T = 1;
+  const int tailw_bytes = tail ? 2048 : 0;
+  const int vec_bytes = 4 * d.n * (d.out_scale != nullptr ? 2 : 1);
+  const long long smem_cap = 226 * 1024 - 1024 - vec_bytes - tailw_bytes;
+  const char* envG = getenv("PSSR_V3_G");
+  int G = 1, RES = 0, b_stages = 0;
+  long long a_bytes = 0;
+  for (;; --T) {
+    long long a_raw;
+    if (p.rows_mode) a_raw = (long long)(T + 2) * p.P * 128;
+    else if (p.pad) a_raw = (long long)(128 * T + 4 * p.P + 1) * 128;
+    else a_raw = 128LL * T * 128;
+    a_bytes = ((a_raw + 1023) / 1024) * 1024;
+    const long long left = smem_cap - 2 * a_bytes;
+    G = 0; RES = 0; b_stages = 0;
+    if (!tail && p.n_tiles == 1 && (long long)num_kb * p.tap_bytes <= left && getenv("PSSR_V3_NORES") == nullptr) {
+      RES = 1; G = 9; b_stages = 1;
+    } else {
+      // small N: a stage must hold many MMAs (a barrier poll costs ~100 unhidden cycles); N = 256: finer stages, deeper prefetch
+      const int cand[3] = {9, 3, 1};
+      for (int ci = (block_n >= 256 ? 2 : 0); ci < 3; ++ci) {
+        const int g = cand[ci];
+        if (envG && atoi(envG) != g) continue;
+        if (tail && g == 9) continue;
+        if (!p.pad && g != 1) continue;
+        const long long stage = (long long)g * p.tap_bytes;
+        const int need = g == 1 ? 3 : 2;
+        if (left >= need * stage) { G = g; b_stages = (int)(left / stage); break; }
+      }
+      if (G == 0 && left >= 2LL * p.tap_bytes) { G = 1; b_stages = (int)(left / p.tap_bytes); }
+      if (b_stages > kV3MaxB) b_stages = kV3MaxB;
+    }
+    if (G != 0 || T == 1) break;
+  }
+  PSSR_REQUIRE(G != 0 && b_stages >= 1, PSSR_EUNSUP, "conv: image width %d needs more shared memory than available", d.Wo);
+  p.a_bytes = (uint32_t)a_bytes;
+  p.b_bytes = (uint32_t)(G * (int)p.tap_bytes);
+  p.b_stages = b_stages;
+  if (p.rows_mode) {
+    p.off_px = p.P + 1;
+    p.tile_step = (uint32_t)(p.P * 8);
+    p.a_tx_bytes = (uint32_t)((T + 2) * p.P * 128);
+    p.units_m = p.total_vrows / T;
+  } else if (p.pad) {
+    p.off_px = 2 * p.P + 1;
+    p.tile_step = 1024;
+    p.units_m = (p.q_end - p.q_begin + 128 * T - 1) / (128 * T);
+  } else {
+    p.off_px = 0;
+    p.tile_step = 1024;
+    p.units_m = (p.q_end + 128 * T - 1) / (128 * T);
+  }
+  p.total_units = p.units_m * p.n_tiles;
+  const char* envd = getenv("PSSR_DBG");
+  p.dbg = envd ? atoi(envd) : 0;
+
+  const CUtensorMapDataType tdt = dtype == PSSR_DT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  for (int s = 0; s < d.n_srcs; ++s) {
+    const pssr_src_t& src = d.srcs[s];
+    PSSR_REQUIRE(src.base != nullptr && ((uintptr_t)src.base & 15) == 0, PSSR_EINVAL, "conv: source %d base must be 16-byte aligned", s);
+    PSSR_REQUIRE(src.cstride % 8 == 0 && src.channels >= 1 && src.channels <= src.cstride, PSSR_EUNSUP, "conv: source %d bad channel stride", s);
+    PSSR_REQUIRE(src.H == d.Ho && src.W == d.Wo && src.B == d.B, PSSR_EINVAL, "conv: source %d geometry does not match the output", s);
+    CUresult r;
+    if (p.pad) {
+      cuuint64_t gdim[4] = {(cuuint64_t)src.channels, (cuuint64_t)src.W, (cuuint64_t)src.H, (cuuint64_t)src.B};
+      cuuint64_t gstr[3] = {(cuuint64_t)src.cstride * 2, (cuuint64_t)src.cstride * 2 * src.W, (cuuint64_t)src.cstride * 2 * src.W * src.H};
+      cuuint32_t box[4] = {64, (cuuint32_t)p.P, (cuuint32_t)(p.rows_mode ? T + 2 : 1), 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      r = enc(&op.tmaps[s], tdt, 4, const_cast<void*>(src.base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      cuuint64_t gdim2[2] = {(cuuint64_t)src.channels, (cuuint64_t)src.W * src.H * src.B};
+      cuuint64_t gstr2[1] = {(cuuint64_t)src.cstride * 2};
+      cuuint32_t box2[2] = {64, (cuuint32_t)(128 * T)};
+      cuuint32_t estr2[2] = {1, 1};
+      r = enc(&op.tmaps[s], tdt, 2, const_cast<void*>(src.base), gdim2, gstr2, box2, estr2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    PSSR_REQUIRE(r == CUDA_SUCCESS, PSSR_ECUDA, "cuTensorMapEncodeTiled(source %d) failed with %d", s, (int)r);
+  }
+  {
+    PSSR_REQUIRE(d.weights != nullptr && ((uintptr_t)d.weights & 15) == 0, PSSR_EINVAL, "conv: weights misaligned");
+    const cuuint64_t ktot = (cuuint64_t)num_kb * 64;
+    cuuint64_t gdim[2] = {ktot, (cuuint64_t)d.n};
+    cuuint64_t gstr[1] = {ktot * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)block_n};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&op.tmaps[3], tdt, 2, const_cast<void*>(d.weights), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PSSR_REQUIRE(r == CUDA_SUCCESS, PSSR_ECUDA, "cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
+  }
+  const uint32_t b_total = RES ? (uint32_t)num_kb * p.tap_bytes : (uint32_t)b_stages * p.b_bytes;
+  op.smem_bytes = (int)(2 * p.a_bytes + b_total + 1024 + (uint32_t)vec_bytes + (uint32_t)tailw_bytes);
+
+  p.bias = d.bias;
+  p.out_scale = d.out_scale;
+  p.out = reinterpret_cast<uint16_t*>(d.out);
+  p.out_f32 = d.out_f32;
+  p.tail_w = d.tail_weight;
+  p.tail_z = d.tail_z;
+  p.out_cstride = d.out_cstride;
+  p.out_choff = d.out_choff;
+  p.shuffle = d.shuffle;
+  p.cps = cps;
+  p.act = d.act;
+  p.fp16 = dtype == PSSR_DT_FP16 ? 1 : 0;
+  p.Hout = d.Ho * d.shuffle;
+  p.Wout = d.Wo * d.shuffle;
+  p.wide_store = (d.out != nullptr && d.out_f32 == nullptr && cps % 16 == 0 && d.out_choff % 16 == 0 && d.out_cstride % 16 == 0 &&
+                  d.n_valid % 16 == 0 && ((uintptr_t)d.out & 31) == 0) ? 1 : 0;
+  const int sms = device_sm_count();
+  op.grid = p.total_units < sms ? p.total_units : sms;
+  op.kernel_index = -1;
+  for (int i = 0; i < kV3NumVariants; ++i)
+    if (kV3Variants[i].T == T && kV3Variants[i].G == G && kV3Variants[i].RES == RES && kV3Variants[i].TAIL == (tail ? 1 : 0)) op.kernel_index = i;
+  PSSR_REQUIRE(op.kernel_index >= 0, PSSR_EUNSUP, "conv: no kernel variant for T=%d G=%d RES=%d TAIL=%d", T, G, RES, (int)tail);
+  static bool attr_set = false;
+  if (!attr_set) {
+    for (int i = 0; i < kV3NumVariants; ++i)
+      PSSR_CHECK_CUDA(cudaFuncSetAttribute(kV3Variants[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    attr_set = true;
+  }
+  if (getenv("PSSR_V3_VERBOSE") != nullptr)
+    fprintf(stderr, "v3: %dx%d n=%d kb=%d block_n=%d T=%d G=%d RES=%d TAIL=%d rows=%d b_stages=%d a_bytes=%u smem=%d units=%d\n", d.Ho, d.Wo, d.n,
+            num_kb, block_n, T, G, RES, (int)tail, p.rows_mode, b_stages, p.a_bytes, op.smem_bytes, p.total_units);
+  return PSSR_OK;
+}
+
+int v3_launch(const ConvOp& op, const void* tmaps_dev, cudaStream_t stream) {
+  V3Params p = *reinterpret_cast<const V3Params*>(op.kparams);
+  p.tmaps = reinterpret_cast<const CUtensorMap*>(tmaps_dev);
+  kV3Variants[op.kernel_index].fn<<<op.grid, kV3Threads, op.smem_bytes, stream>>>(p);
+  count_launch();
+  PSSR_CHECK_CUDA(cudaGetLastError());
+  return PSSR_OK;
+}
+
+}  // namespace pssr

@@ -12,7 +12,8 @@ struct ConvOp {
   alignas(16) uint8_t kparams[512];
   int grid = 0;
   int smem_bytes = 0;
-  int variant = 1;                // 1 = conv_igemm.cu (box per tap), 2 = conv_strip.cu (halo strips)
+  int variant = 1;                // 1 = conv_igemm.cu (box per tap), 2 = conv_strip.cu (halo strips), 3 = conv_v3.cu (lean issue)
+  int kernel_index = -1;          // variant 3: index of the template instantiation
 };
 
 int conv_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op);
@@ -20,6 +21,10 @@ int conv_launch(const ConvOp& op, const void* tmaps_dev, cudaStream_t stream);
 bool strip_supported(const pssr_conv_desc_t& d);
 int strip_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op);
 int strip_launch(const ConvOp& op, const void* tmaps_dev, cudaStream_t stream);
+int strip_trace_fetch(long long* host, int n);
+bool v3_supported(const pssr_conv_desc_t& d);
+int v3_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op);
+int v3_launch(const ConvOp& op, const void* tmaps_dev, cudaStream_t stream);
 
 int prep_launch(const pssr_prep_desc_t& d, int dtype, cudaStream_t stream);
 int pool_launch(const pssr_pool_desc_t& d, int dtype, cudaStream_t stream);

@@ -1,0 +1,2 @@
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+PSSR_V3_VERBOSE=1 timeout 300 python scripts/dev_time_net.py 64 fp16 2>&1 | tail -80
