@@ -38,7 +38,7 @@ const char* pssr_version(void) { return "pssr_b200 0.1 sm_100a"; }
 int64_t pssr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 int pssr_debug_trace(int64_t* out, int64_t n) {
   PSSR_REQUIRE(out != nullptr && n > 0, PSSR_EINVAL, "debug_trace: bad arguments");
-  return strip_trace_fetch(reinterpret_cast<long long*>(out), (int)n);
+  return v3_trace_fetch(reinterpret_cast<long long*>(out), (int)n);
 }
 
 int pssr_plan_create(const pssr_op_t* ops, int32_t n_ops, int32_t dtype, pssr_plan_t** out) {

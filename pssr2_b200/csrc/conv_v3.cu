@@ -30,6 +30,7 @@ namespace pssr {
 
 static constexpr int kV3Threads = 384;
 static constexpr int kV3MaxB = 8;
+static constexpr int kV3MaxR = 12;   // ring slots (row groups) in rows mode
 
 struct V3Params {
   const CUtensorMap* tmaps;   // device: [0..2] sources, [3] weights
@@ -39,6 +40,10 @@ struct V3Params {
   int H, W, B, P, IP, pad, HP, NJ, Wb;
   int rows_mode;              // 1: tile = one 128-pixel row segment (W % 128 == 0)
   int total_vrows;            // rows mode: B * NJ * H
+  int ring_R;                 // rows mode: row groups in the ring
+  uint32_t slot_bytes;        // rows mode: one row of one 64-channel plane = P * 128
+  uint32_t group_bytes;       // rows mode: all planes of one row
+  uint32_t ring_bytes;        // rows mode: ring_R * group_bytes rounded up to 1024
   int q_begin, q_end;         // flat mode
   int off_px;                 // pixel offset of a unit's first pixel inside an A stage buffer
   uint32_t tile_step;         // descriptor units (16 B) between the A operands of consecutive tiles of a unit
@@ -57,6 +62,15 @@ struct V3Params {
   float* tail_z;              // fp32 planar [B][r*r*9][H][W]
 };
 
+// developer timeline (PSSR_DBG bit 16): per CTA 256 clock64 stamps -- [0] entry, [1] setup done, [2+2u] unit u: accumulator buffer
+// free (MMA warp), [3+2u] unit u committed, [64+2u] unit u accumulators ready (epilogue warp 4), [65+2u] unit u epilogue done,
+// [127] exit, [128+2u] unit u: first A stage landed, [192+u] TAIL: tail MMAs of unit u issued
+__device__ long long g_v3_trace[148 * 256];
+#define V3_TRACE(slot)                                                                                   \
+  do {                                                                                                   \
+    if ((p.dbg & 16) && lane == 0 && (slot) >= 0 && (slot) < 256) g_v3_trace[(blockIdx.x % 148) * 256 + (slot)] = clock64(); \
+  } while (0)
+
 __device__ __forceinline__ uint64_t v3_desc(uint32_t addr) {
   uint64_t d = (uint64_t)((addr >> 4) & 0x3FFFu);
   d |= (uint64_t)(1024u >> 4) << 32;
@@ -64,22 +78,86 @@ __device__ __forceinline__ uint64_t v3_desc(uint32_t addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// D (+)= A * B^T with the accumulate flag as an immediate / a register
+// D (+)= A * B^T with the accumulate flag as an immediate / a register.  PAIR: cta_group::2 -- one instruction drives the
+// tensor cores of both SMs of the CTA pair (M = 256: each CTA's own 128 A rows, each CTA holds half of B's N rows).
+template <bool PAIR>
 __device__ __forceinline__ void v3_mma_acc(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc) {
-  asm volatile("tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, 1;" ::"r"(d), "l"(a), "l"(b), "r"(idesc) : "memory");
+  if (PAIR) asm volatile("tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, 1;" ::"r"(d), "l"(a), "l"(b), "r"(idesc) : "memory");
+  else asm volatile("tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, 1;" ::"r"(d), "l"(a), "l"(b), "r"(idesc) : "memory");
 }
+template <bool PAIR>
 __device__ __forceinline__ void v3_mma_p(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc)
-      : "memory");
+  if (PAIR)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc)
+        : "memory");
 }
 // A operand in TMEM (16-bit pairs: lane = row, column = k/2)
+template <bool PAIR>
 __device__ __forceinline__ void v3_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (PAIR)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// completion of all MMAs issued so far -> one arrival on the barrier (PAIR: on the barrier at this offset in BOTH CTAs)
+template <bool PAIR>
+__device__ __forceinline__ void v3_commit(uint32_t bar) {
+  if (PAIR)
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+  else
+    umma_commit(bar);
+}
+__device__ __forceinline__ uint32_t v3_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void v3_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (an address in this CTA's shared memory) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t v3_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void v3_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// TMA loads of a CTA pair: the data lands in this CTA's shared memory, the bytes are counted on the LEADER's barrier
+__device__ __forceinline__ void v3_tma_2d_pair(uint32_t dst, const void* tmap, uint32_t cluster_bar, int c0, int c1) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(cluster_bar), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void v3_tma_4d_pair(uint32_t dst, const void* tmap, uint32_t cluster_bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void v3_tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void v3_tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 __device__ __forceinline__ void v3_tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(
@@ -114,22 +192,45 @@ __device__ __forceinline__ float v3_gelu(float x) {
   return 0.5f * x * (1.0f + copysignf(e, x));
 }
 
-// T tiles per unit, G filter taps per weight stage (3x3 segments), RES: the whole layer's weights stay in shared memory,
-// TAIL: fused Reconstruction tail (block_n = 256, T = 1, 64 channels per pixel-shuffle sub-position)
-template <int T, int G, bool RES, bool TAIL>
+// 16-bit pack with saturation to the finite range (and optional ReLU) in one F2FP instruction
+__device__ __forceinline__ uint32_t v3_pack2(float lo, float hi, int fp16, bool relu) {
+  uint32_t d;
+  if (fp16) {
+    if (relu) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  } else {
+    if (relu) asm("cvt.rn.relu.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  }
+  return d;
+}
+
+// T tiles per CTA and unit, G filter taps per weight stage (3x3 segments), RES: the whole layer's weights stay in shared memory,
+// TAIL: fused Reconstruction tail (block_n = 256, T = 1, 64 channels per pixel-shuffle sub-position), PAIR: the kernel runs
+// as clusters of two CTAs; a unit is 2T tiles, the leader (cluster rank 0) issues cta_group::2 MMAs for both, each CTA stages
+// its own A tiles and half of the weight rows, and drains its own TMEM.  ROWS: rows mode -- a tile is a 128-pixel row segment,
+// every worker walks a CONTIGUOUS range of row groups and keeps the input rows in a shared-memory ring (each row is fetched
+// once and prefetched several units ahead; all N tiles of a row group run against the same staged rows).
+template <int T, int G, bool RES, bool TAIL, bool PAIR, bool ROWS>
 __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_constant__ V3Params p) {
+  constexpr int C = PAIR ? 2 : 1;
+  const uint32_t rank = PAIR ? v3_cluster_rank() : 0u;
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // persistent worker (CTA or CTA pair)
+  const int workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bars[4 + 2 * kV3MaxB + 8];
+  __shared__ uint64_t bars[4 + 2 * kV3MaxB + 8 + 2 * kV3MaxR];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (warp == 1) V3_TRACE(0);
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t a_base = smem_base;
-  const uint32_t b_base = smem_base + 2u * p.a_bytes;
+  const uint32_t a_base = smem_base;                                       // A stages (flat) or the row ring (ROWS)
+  const uint32_t a_total = ROWS ? p.ring_bytes : 2u * p.a_bytes;
+  const uint32_t b_base = smem_base + a_total;
   const uint32_t b_total = RES ? (uint32_t)p.num_kb * p.tap_bytes : (uint32_t)p.b_stages * p.b_bytes;
-  const uint32_t tailw_off = 2u * p.a_bytes + b_total;                     // 16 x 128 B, 1024-aligned
+  const uint32_t tailw_off = a_total + b_total;                            // 16 x 128 B, 1024-aligned
   const uint32_t vec_off = tailw_off + (TAIL ? 2048u : 0u);
   float* bias_s = reinterpret_cast<float*>(smem_al + vec_off);
   float* scale_s = bias_s + p.n_total;
@@ -138,10 +239,12 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
     if (p.out_scale != nullptr) scale_s[i] = p.out_scale[i];
   }
   if (TAIL) {
-    // tail weights [9][64] fp32 -> 16-bit K-major SWIZZLE_128B operand tile [16 taps x 64 channels] (rows 9..15 zero)
-    for (int i = threadIdx.x; i < 16 * 64; i += kV3Threads) {
+    // tail weights [9][64] fp32 -> 16-bit K-major SWIZZLE_128B operand tile [16 taps x 64 channels] (rows 9..15 zero);
+    // a CTA pair splits the N = 16 rows: local row t of rank r is tap r*8 + t
+    for (int i = threadIdx.x; i < (16 / C) * 64; i += kV3Threads) {
       const int t = i >> 6, c = i & 63;
-      const float w = t < 9 ? p.tail_w[t * 64 + c] : 0.f;
+      const int tap = t + (int)rank * (16 / C);
+      const float w = tap < 9 ? p.tail_w[tap * 64 + c] : 0.f;
       const int chunk = (c >> 3) ^ (t & 7);
       reinterpret_cast<uint16_t*>(smem_al + tailw_off + t * 128 + chunk * 16)[c & 7] = pack1(w, p.fp16);
     }
@@ -156,96 +259,174 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
   auto t_empty = [&](int b) { return bar0 + 8u * (4 + 2 * kV3MaxB + 2 + b); };
   auto p_full = [&](int b) { return bar0 + 8u * (4 + 2 * kV3MaxB + 4 + b); };
   auto z_full = [&](int b) { return bar0 + 8u * (4 + 2 * kV3MaxB + 6 + b); };
+  auto r_full = [&](int s) { return bar0 + 8u * (4 + 2 * kV3MaxB + 8 + s); };
+  auto r_empty = [&](int s) { return bar0 + 8u * (4 + 2 * kV3MaxB + 8 + kV3MaxR + s); };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < kV3MaxB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(t_full(b), 1); mbar_init(t_empty(b), 8); mbar_init(p_full(b), 8); mbar_init(z_full(b), 1); }
+    for (int s = 0; s < kV3MaxR; ++s) { mbar_init(r_full(s), 1); mbar_init(r_empty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(t_full(b), 1); mbar_init(t_empty(b), 8 * C); mbar_init(p_full(b), 8 * C); mbar_init(z_full(b), 1); }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), 512);
+  if (warp == 1) {
+    if (PAIR) v3_tmem_alloc_pair(smem_u32(&tmem_base_smem), 512);
+    else tmem_alloc(smem_u32(&tmem_base_smem), 512);
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) v3_cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   const int block_n = p.block_n;
+  if (warp == 1) V3_TRACE(1);
+
+  // ---- ROWS: this worker's contiguous range of row groups (a group = T rows of one virtual image) -----------------------
+  // groups [g_lo, g_hi); a pair splits the range in two halves walked in lockstep (rank r: g_lo + r*msteps + ms).  The ring
+  // advances identically in both CTAs of a pair (one MMA descriptor addresses both): a step is "fresh" (all T+2 rows
+  // fetched) when either CTA starts a new image, else only the T new rows are fetched.
+  const int groups = ROWS ? p.total_vrows / T : 0;
+  const int g_lo = ROWS ? (int)((long long)worker * groups / workers) : 0;
+  const int g_hi = ROWS ? (int)((long long)(worker + 1) * groups / workers) : 0;
+  const int msteps = ROWS ? (PAIR ? (g_hi - g_lo + 1) / 2 : g_hi - g_lo) : 0;
+  auto group_of = [&](int ms, int rk, bool& valid) {
+    int g = g_lo + (PAIR ? rk * msteps : 0) + ms;
+    valid = g < g_hi;
+    if (!valid) g = g_hi - 1;
+    return g;
+  };
+  auto step_fresh = [&](int ms) {
+    if (ms == 0) return true;
+    bool fresh = false;
+#pragma unroll
+    for (int rk = 0; rk < C; ++rk) {
+      bool valid;
+      const int g = group_of(ms, rk, valid);
+      fresh = fresh || !valid || ((g * T) % p.H == 0);
+    }
+    return fresh;
+  };
 
   if (warp == 0) {
     // ============================ A producer ================================================
+    // every CTA stages its own tiles; in a pair the bytes of both CTAs are counted on the leader's barrier
     if (lane == 0) {
-      int as = 0;
-      uint32_t aphase = 0;
-      const int rows_total = p.B * p.NJ * p.HP;
-      for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
-        const int um = unit / p.n_tiles;
-        int c1 = 0, c2 = 0, c3 = 0, qa = 0, r0 = 0, nrows = 0;
-        if (p.rows_mode) {
-          const int vr0 = um * T;
+      if (ROWS) {
+        int slot = 0;
+        uint32_t phase = 0;
+        for (int ms = 0; ms < msteps; ++ms) {
+          bool valid;
+          const int g = group_of(ms, (int)rank, valid);
+          const int vr0 = g * T;
           const int v = vr0 / p.H;
+          const int y0 = vr0 - v * p.H;
           const int n = v / p.NJ;
-          c1 = (v - n * p.NJ) * 128 - 1;
-          c2 = vr0 - v * p.H - 1;
-          c3 = n;
-        } else if (p.pad) {
-          qa = p.q_begin + um * (128 * T);
-          r0 = (qa - p.P - 1) / p.P;
-          int r1 = (qa + 128 * T + p.P) / p.P;
-          if (r1 > rows_total - 1) r1 = rows_total - 1;
-          nrows = r1 - r0 + 1;
-        } else {
-          qa = um * (128 * T);
-        }
-        for (int sg = 0; sg < p.n_segs; ++sg) {
-          const CUtensorMap* tm = p.tmaps + p.seg_src[sg];
-          for (int cb = 0; cb < p.seg_cblocks[sg]; ++cb) {
-            mbar_wait(a_empty(as), aphase ^ 1u);
-            const uint32_t dst0 = a_base + (uint32_t)as * p.a_bytes;
-            if (p.rows_mode) {
-              mbar_arrive_expect_tx(a_full(as), p.a_tx_bytes);
-              tma_load_4d(dst0, tm, a_full(as), cb * 64, c1, c2, c3);
-            } else if (p.pad) {
-              mbar_arrive_expect_tx(a_full(as), (uint32_t)nrows * (uint32_t)p.P * 128u);
-              for (int r = 0; r < nrows; ++r) {
-                const int rho = r0 + r;
-                const int v = rho / p.HP;
-                const int py = rho - v * p.HP;
-                const int n = v / p.NJ;
-                const int j = v - n * p.NJ;
-                const uint32_t dst = dst0 + (uint32_t)(rho * p.P - qa + p.off_px) * 128u;
-                tma_load_4d(dst, tm, a_full(as), cb * 64, j * p.Wb - 1, py - 1, n);
+          const int x0 = (v - n * p.NJ) * 128 - 1;
+          const bool fresh = step_fresh(ms);
+          const int first_row = fresh ? y0 - 1 : y0 + 1;
+          const int count = fresh ? T + 2 : T;
+          for (int i = 0; i < count; ++i) {
+            mbar_wait(r_empty(slot), phase ^ 1u);
+            const uint32_t fbar = PAIR ? v3_mapa(r_full(slot), 0) : r_full(slot);
+            if (rank == 0) mbar_arrive_expect_tx(r_full(slot), p.group_bytes * C);
+            uint32_t dst = a_base + (uint32_t)slot * p.group_bytes;
+            for (int sg = 0; sg < p.n_segs; ++sg) {
+              const CUtensorMap* tm = p.tmaps + p.seg_src[sg];
+              for (int cb = 0; cb < p.seg_cblocks[sg]; ++cb) {
+                if (PAIR) v3_tma_4d_pair(dst, tm, fbar, cb * 64, x0, first_row + i, n);
+                else tma_load_4d(dst, tm, fbar, cb * 64, x0, first_row + i, n);
+                dst += p.slot_bytes;
               }
-            } else {
-              mbar_arrive_expect_tx(a_full(as), (uint32_t)(128 * T) * 128u);
-              tma_load_2d(dst0, tm, a_full(as), cb * 64, qa);
             }
-            as ^= 1;
-            if (as == 0) aphase ^= 1u;
+            if (++slot == p.ring_R) { slot = 0; phase ^= 1u; }
+          }
+        }
+      } else {
+        int as = 0;
+        uint32_t aphase = 0;
+        const int rows_total = p.B * p.NJ * p.HP;
+        for (int unit = worker; unit < p.total_units; unit += workers) {
+          const int um = unit / p.n_tiles;
+          int qa = 0, r0 = 0, nrows = 0;
+          uint32_t tx = 0;
+          if (p.pad) {
+#pragma unroll
+            for (int rk = 0; rk < C; ++rk) {        // row range of each CTA of the pair (the leader needs both byte counts)
+              const int qa_r = p.q_begin + (um * C + rk) * (128 * T);
+              const int r0_r = (qa_r - p.P - 1) / p.P;
+              int r1_r = (qa_r + 128 * T + p.P) / p.P;
+              if (r1_r > rows_total - 1) r1_r = rows_total - 1;
+              int nr = r1_r - r0_r + 1;
+              if (nr < 0) nr = 0;
+              tx += (uint32_t)nr * (uint32_t)p.P * 128u;
+              if (rk == (int)rank) { qa = qa_r; r0 = r0_r; nrows = nr; }
+            }
+          } else {
+            qa = (um * C + (int)rank) * (128 * T);
+            tx = (uint32_t)(128 * T) * 128u * C;
+          }
+          for (int sg = 0; sg < p.n_segs; ++sg) {
+            const CUtensorMap* tm = p.tmaps + p.seg_src[sg];
+            for (int cb = 0; cb < p.seg_cblocks[sg]; ++cb) {
+              mbar_wait(a_empty(as), aphase ^ 1u);
+              const uint32_t dst0 = a_base + (uint32_t)as * p.a_bytes;
+              const uint32_t fbar = PAIR ? v3_mapa(a_full(as), 0) : a_full(as);
+              if (rank == 0) mbar_arrive_expect_tx(a_full(as), tx);
+              if (p.pad) {
+                for (int r = 0; r < nrows; ++r) {
+                  const int rho = r0 + r;
+                  const int v = rho / p.HP;
+                  const int py = rho - v * p.HP;
+                  const int n = v / p.NJ;
+                  const int j = v - n * p.NJ;
+                  const uint32_t dst = dst0 + (uint32_t)(rho * p.P - qa + p.off_px) * 128u;
+                  if (PAIR) v3_tma_4d_pair(dst, tm, fbar, cb * 64, j * p.Wb - 1, py - 1, n);
+                  else tma_load_4d(dst, tm, fbar, cb * 64, j * p.Wb - 1, py - 1, n);
+                }
+              } else {
+                if (PAIR) v3_tma_2d_pair(dst0, tm, fbar, cb * 64, qa);
+                else tma_load_2d(dst0, tm, fbar, cb * 64, qa);
+              }
+              as ^= 1;
+              if (as == 0) aphase ^= 1u;
+            }
           }
         }
       }
     }
   } else if (warp == 2) {
     // ================================ B producer: weights ===================================
+    // p.tap_bytes = bytes of one tap's weight block held by ONE CTA (a pair splits the N rows); bytes counted on the leader
     if (lane == 0) {
       const CUtensorMap* tmB = p.tmaps + 3;
+      const int nrow0 = (int)rank * (block_n / C);
       if (RES) {
-        mbar_arrive_expect_tx(b_full(0), (uint32_t)p.num_kb * p.tap_bytes);
-        for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(b_base + (uint32_t)kb * p.tap_bytes, tmB, b_full(0), kb * 64, 0);
+        const uint32_t fbar = PAIR ? v3_mapa(b_full(0), 0) : b_full(0);
+        if (rank == 0) mbar_arrive_expect_tx(b_full(0), (uint32_t)p.num_kb * p.tap_bytes * C);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          if (PAIR) v3_tma_2d_pair(b_base + (uint32_t)kb * p.tap_bytes, tmB, fbar, kb * 64, nrow0);
+          else tma_load_2d(b_base + (uint32_t)kb * p.tap_bytes, tmB, fbar, kb * 64, nrow0);
+        }
       } else {
         int bs = 0;
         uint32_t bphase = 0;
-        for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
-          const int n_tile = unit % p.n_tiles;
+        const int steps = ROWS ? msteps * p.n_tiles : 0;
+        int k = 0;
+        for (int unit = worker; ROWS ? k < steps : unit < p.total_units; unit += workers, ++k) {
+          const int n_tile = ROWS ? k % p.n_tiles : unit % p.n_tiles;
           for (int sg = 0; sg < p.n_segs; ++sg) {
             const int taps = p.seg_taps[sg], cbs = p.seg_cblocks[sg];
             const int gs = taps == 9 ? G : 1;
             for (int cb = 0; cb < cbs; ++cb) {
               for (int t0 = 0; t0 < taps; t0 += gs) {
                 mbar_wait(b_empty(bs), bphase ^ 1u);
-                mbar_arrive_expect_tx(b_full(bs), (uint32_t)gs * p.tap_bytes);
+                const uint32_t fbar = PAIR ? v3_mapa(b_full(bs), 0) : b_full(bs);
+                if (rank == 0) mbar_arrive_expect_tx(b_full(bs), (uint32_t)gs * p.tap_bytes * C);
                 for (int t = 0; t < gs; ++t) {
                   const int kb = p.seg_kb0[sg] + (t0 + t) * cbs + cb;   // weights are packed tap-major, then channel block
-                  tma_load_2d(b_base + (uint32_t)bs * p.b_bytes + (uint32_t)t * p.tap_bytes, tmB, b_full(bs), kb * 64, n_tile * block_n);
+                  const uint32_t dst = b_base + (uint32_t)bs * p.b_bytes + (uint32_t)t * p.tap_bytes;
+                  if (PAIR) v3_tma_2d_pair(dst, tmB, fbar, kb * 64, n_tile * block_n + nrow0);
+                  else tma_load_2d(dst, tmB, fbar, kb * 64, n_tile * block_n + nrow0);
                 }
                 if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; }
               }
@@ -254,11 +435,12 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && rank == 0) {
     // ================================== MMA issuer ==========================================
     // The whole warp walks the loops (warp-uniform control flow); one elected lane issues the tcgen05 instructions.
-    const uint32_t idesc = umma_idesc_f16(p.fp16 ? 0 : 1, block_n);
-    const uint32_t idesc_tail = umma_idesc_f16(p.fp16 ? 0 : 1, 16);
+    // PAIR: M = 256 in the instruction descriptor (bits 24..28 hold M >> 4)
+    const uint32_t idesc = umma_idesc_f16(p.fp16 ? 0 : 1, block_n) + (PAIR ? (8u << 24) : 0u);
+    const uint32_t idesc_tail = umma_idesc_f16(p.fp16 ? 0 : 1, 16) + (PAIR ? (8u << 24) : 0u);
     const uint64_t tdesc = v3_desc(smem_base + tailw_off);
     const uint64_t adesc_s0 = v3_desc(a_base + (uint32_t)p.off_px * 128u);
     const uint64_t adesc_s1 = adesc_s0 + (uint64_t)(p.a_bytes >> 4);
@@ -266,6 +448,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
     const uint32_t bstep = p.b_bytes >> 4, tapstep = p.tap_bytes >> 4;
     const int64_t P8 = (int64_t)p.P * 8;
     const uint64_t tile_step = p.tile_step;
+    const uint64_t slot_desc = (uint64_t)(p.slot_bytes >> 4);
     int as = 0, bs = 0;
     uint32_t aphase = 0, bphase = 0;
     int it = 0;
@@ -282,31 +465,36 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
           const uint32_t a_col = cbase + region + (uint32_t)((s & 1) * 32);
           const uint32_t d_col = cbase + region + 64u + (uint32_t)((s & 1) * 16);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) v3_mma_ts(d_col, a_col + 8u * k, tdesc + 2u * k, idesc_tail, k ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) v3_mma_ts<PAIR>(d_col, a_col + 8u * k, tdesc + 2u * k, idesc_tail, k ? 1u : 0u);
         }
-        umma_commit(z_full(pbuf));
+        v3_commit<PAIR>(z_full(pbuf));
       }
       __syncwarp();
+      if (pit < 60) V3_TRACE(192 + pit);
     };
 
-    if (RES) {
-      mbar_wait(b_full(0), 0);
-      tc_fence_after();
-    }
-    for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x, ++it) {
+    // one accumulator tile set: all K segments of (n_tile) against the staged A.  ea[i] (ROWS): descriptor of ring row i of
+    // the current group (row y0-1+i, pixel x0 = -1), plane 0.
+    auto run_k = [&](const uint64_t (&ea)[T + 2]) {
       const int buf = it & 1;
       mbar_wait(t_empty(buf), ((uint32_t)(it >> 1) & 1u) ^ 1u);
       tc_fence_after();
+      if (it < 31) V3_TRACE(2 + 2 * it);
       const uint32_t d0 = tmem_base + (uint32_t)(buf * 256);
       uint32_t acc = 0;
       bool tail_done = false;
+      uint64_t plane_desc = 0;
       for (int sg = 0; sg < p.n_segs; ++sg) {
         const bool nine = p.seg_taps[sg] == 9;
         const int cbs = p.seg_cblocks[sg];
-        for (int cb = 0; cb < cbs; ++cb) {
-          mbar_wait(a_full(as), aphase);
-          tc_fence_after();
-          const uint64_t ad0 = as ? adesc_s1 : adesc_s0;
+        for (int cb = 0; cb < cbs; ++cb, plane_desc += slot_desc) {
+          uint64_t ad0 = 0;
+          if (!ROWS) {
+            mbar_wait(a_full(as), aphase);
+            tc_fence_after();
+            ad0 = as ? adesc_s1 : adesc_s0;
+          }
+          if (acc == 0 && it < 31) V3_TRACE(128 + 2 * it);
           if (nine) {
 #pragma unroll
             for (int t0 = 0; t0 < 9; t0 += G) {
@@ -324,20 +512,20 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
                 for (int tt = 0; tt < G; ++tt) {
                   const int t = t0 + tt;
                   const int dy = t / 3 - 1, dx = t % 3 - 1;
-                  const uint64_t adt = ad0 + (uint64_t)(dy * P8 + dx * 8);
                   const uint64_t bdt = bd + (uint64_t)tt * btap;
 #pragma unroll
                   for (int mt = 0; mt < T; ++mt) {
-                    const uint64_t adm = adt + (uint64_t)mt * tile_step;
+                    const uint64_t adm = ROWS ? ea[mt + 1 + dy] + plane_desc + (uint64_t)((1 + dx) * 8)
+                                              : ad0 + (uint64_t)(dy * P8 + dx * 8) + (uint64_t)mt * tile_step;
                     const uint32_t dcol = d0 + (uint32_t)(mt * block_n);
-                    if (tt == 0) v3_mma_p(dcol, adm, bdt, idesc, acc);
-                    else v3_mma_acc(dcol, adm, bdt, idesc);
-                    v3_mma_acc(dcol, adm + 2, bdt + 2, idesc);
-                    v3_mma_acc(dcol, adm + 4, bdt + 4, idesc);
-                    v3_mma_acc(dcol, adm + 6, bdt + 6, idesc);
+                    if (tt == 0) v3_mma_p<PAIR>(dcol, adm, bdt, idesc, acc);
+                    else v3_mma_acc<PAIR>(dcol, adm, bdt, idesc);
+                    v3_mma_acc<PAIR>(dcol, adm + 2, bdt + 2, idesc);
+                    v3_mma_acc<PAIR>(dcol, adm + 4, bdt + 4, idesc);
+                    v3_mma_acc<PAIR>(dcol, adm + 6, bdt + 6, idesc);
                   }
                 }
-                if (!RES) umma_commit(b_empty(bs));
+                if (!RES) v3_commit<PAIR>(b_empty(bs));
               }
               __syncwarp();
               acc = 1;
@@ -360,28 +548,79 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
             if (elect_one()) {
 #pragma unroll
               for (int mt = 0; mt < T; ++mt) {
-                const uint64_t adm = ad0 + (uint64_t)mt * tile_step;
+                const uint64_t adm = ROWS ? ea[mt + 1] + plane_desc + 8u : ad0 + (uint64_t)mt * tile_step;
                 const uint32_t dcol = d0 + (uint32_t)(mt * block_n);
-                v3_mma_p(dcol, adm, bd, idesc, acc);
-                v3_mma_acc(dcol, adm + 2, bd + 2, idesc);
-                v3_mma_acc(dcol, adm + 4, bd + 4, idesc);
-                v3_mma_acc(dcol, adm + 6, bd + 6, idesc);
+                v3_mma_p<PAIR>(dcol, adm, bd, idesc, acc);
+                v3_mma_acc<PAIR>(dcol, adm + 2, bd + 2, idesc);
+                v3_mma_acc<PAIR>(dcol, adm + 4, bd + 4, idesc);
+                v3_mma_acc<PAIR>(dcol, adm + 6, bd + 6, idesc);
               }
-              if (!RES) umma_commit(b_empty(bs));
+              if (!RES) v3_commit<PAIR>(b_empty(bs));
             }
             __syncwarp();
             acc = 1;
             if (!RES) { if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; } }
           }
-          if (elect_one()) umma_commit(a_empty(as));
-          __syncwarp();
-          as ^= 1;
-          if (as == 0) aphase ^= 1u;
+          if (!ROWS) {
+            if (elect_one()) v3_commit<PAIR>(a_empty(as));
+            __syncwarp();
+            as ^= 1;
+            if (as == 0) aphase ^= 1u;
+          }
         }
       }
       if (TAIL && !tail_done && it > 0) issue_tail(it - 1);
-      if (elect_one()) umma_commit(t_full(buf));
+      if (elect_one()) v3_commit<PAIR>(t_full(buf));
       __syncwarp();
+      if (it < 31) V3_TRACE(3 + 2 * it);
+      ++it;
+    };
+
+    if (RES) {
+      mbar_wait(b_full(0), 0);
+      tc_fence_after();
+    }
+    if (ROWS) {
+      const uint64_t ring_desc0 = v3_desc(a_base);
+      const uint64_t group_desc = (uint64_t)(p.group_bytes >> 4);
+      int cslot = 0;                // next ring slot to be consumed
+      uint32_t cphase = 0;
+      bool fresh = true;
+      for (int ms = 0; ms < msteps; ++ms) {
+        const int count = fresh ? T + 2 : T;
+        int first = fresh ? cslot : cslot - 2;
+        if (first < 0) first += p.ring_R;
+        for (int i = 0; i < count; ++i) {
+          mbar_wait(r_full(cslot), cphase);
+          if (++cslot == p.ring_R) { cslot = 0; cphase ^= 1u; }
+        }
+        tc_fence_after();
+        uint64_t ea[T + 2];
+        int sl[T + 2];
+#pragma unroll
+        for (int i = 0; i < T + 2; ++i) {
+          int s_i = first + i;
+          if (s_i >= p.ring_R) s_i -= p.ring_R;
+          sl[i] = s_i;
+          ea[i] = ring_desc0 + (uint64_t)s_i * group_desc;
+        }
+        for (int nt = 0; nt < p.n_tiles; ++nt) run_k(ea);
+        // rows that no later group of this worker needs go back to the producer
+        const bool last = ms + 1 == msteps;
+        const bool next_fresh = last ? true : step_fresh(ms + 1);
+        if (!last) {
+          if (elect_one()) {
+#pragma unroll
+            for (int i = 0; i < T + 2; ++i)
+              if (i < T || next_fresh) v3_commit<PAIR>(r_empty(sl[i]));
+          }
+          __syncwarp();
+        }
+        fresh = next_fresh;
+      }
+    } else {
+      const uint64_t ea[T + 2] = {};
+      for (int unit = worker; unit < p.total_units; unit += workers) run_k(ea);
     }
     if (TAIL && it > 0) issue_tail(it - 1);
   } else if (warp >= 4) {
@@ -392,14 +631,28 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
     const int r = p.shuffle;
     const int npairs = (block_n + 63) / 64;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    const bool relu = p.act == PSSR_ACT_RELU;
+    const int steps = ROWS ? msteps * p.n_tiles : 0;
     int it = 0;
-    for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x, ++it) {
-      const int n_tile = unit % p.n_tiles;
-      const int um = unit / p.n_tiles;
+    for (int unit = worker; ROWS ? it < steps : unit < p.total_units; unit += workers, ++it) {
+      const int n_tile = ROWS ? it % p.n_tiles : unit % p.n_tiles;
+      const int um = ROWS ? 0 : (unit / p.n_tiles) * C + (int)rank;     // flat: this CTA's group of T tiles
+      // ROWS: this CTA's row group
+      int gn = 0, gy0 = 0, gx0 = 0;
+      bool gvalid = true;
+      if (ROWS) {
+        const int g = group_of(it / p.n_tiles, (int)rank, gvalid);
+        const int vr0 = g * T;
+        const int v = vr0 / p.H;
+        gy0 = vr0 - v * p.H;
+        gn = v / p.NJ;
+        gx0 = (v - gn * p.NJ) * 128;
+      }
       const int buf = it & 1;
       const uint32_t par = (uint32_t)(it >> 1) & 1u;
       mbar_wait(t_full(buf), par);
       tc_fence_after();
+      if (warp == 4 && it < 31) V3_TRACE(64 + 2 * it);
       if (TAIL) {
         // ---- phase 1: relu(acc + bias) -> 16-bit, written back over the accumulator's own columns ------------------
         const uint32_t region = lane_addr + (uint32_t)(buf * 256 + eg * 128);
@@ -413,29 +666,23 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 bb = *reinterpret_cast<const float4*>(bias_s + nb0 + c * 32 + 4 * j4);
-            const float f0 = fmaxf(__uint_as_float(v[4 * j4 + 0]) + bb.x, 0.f);
-            const float f1 = fmaxf(__uint_as_float(v[4 * j4 + 1]) + bb.y, 0.f);
-            const float f2 = fmaxf(__uint_as_float(v[4 * j4 + 2]) + bb.z, 0.f);
-            const float f3 = fmaxf(__uint_as_float(v[4 * j4 + 3]) + bb.w, 0.f);
-            o[2 * j4 + 0] = pack2(f0, f1, p.fp16);
-            o[2 * j4 + 1] = pack2(f2, f3, p.fp16);
+            o[2 * j4 + 0] = v3_pack2(__uint_as_float(v[4 * j4 + 0]) + bb.x, __uint_as_float(v[4 * j4 + 1]) + bb.y, p.fp16, true);
+            o[2 * j4 + 1] = v3_pack2(__uint_as_float(v[4 * j4 + 2]) + bb.z, __uint_as_float(v[4 * j4 + 3]) + bb.w, p.fp16, true);
           }
           v3_tmem_st16(region + (uint32_t)(c * 16), o);
         }
         v3_tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_full(buf));
+        if (lane == 0) {
+          if (rank == 0) mbar_arrive(p_full(buf));
+          else v3_arrive_cluster(v3_mapa(p_full(buf), 0));
+        }
         // ---- phase 2: the nine per-tap projections of this thread's pixel, two sub-positions per warp -------------
         int n, y, x;
         bool valid;
-        if (p.rows_mode) {
-          const int vr = um;                      // T == 1
-          const int v = vr / p.H;
-          y = vr - v * p.H;
-          n = v / p.NJ;
-          x = (v - n * p.NJ) * 128 + row;
-          valid = vr < p.total_vrows;
+        if (ROWS) {
+          n = gn; y = gy0; x = gx0 + row; valid = gvalid;      // T == 1
         } else {
           const int q = p.q_begin + um * 128 + row;
           const int vimg = q / p.IP;
@@ -471,13 +718,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
           const int c_hi = c_lo + 64 < block_n ? c_lo + 64 : block_n;
           int n, y, x;
           bool valid;
-          if (p.rows_mode) {
-            const int vr = um * T + mt;
-            const int v = vr / p.H;
-            y = vr - v * p.H;
-            n = v / p.NJ;
-            x = (v - n * p.NJ) * 128 + row;
-            valid = vr < p.total_vrows;
+          if (ROWS) {
+            n = gn; y = gy0 + mt; x = gx0 + row; valid = gvalid;
           } else if (p.pad) {
             const int q = p.q_begin + (um * T + mt) * 128 + row;
             const int vimg = q / p.IP;
@@ -502,10 +744,12 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
           int si = sub / r, sj = sub - si * r;
           const size_t pix00 = ((size_t)n * p.Hout + (size_t)(y * r)) * p.Wout + (size_t)(x * r);
           const uint32_t taddr = lane_addr + (uint32_t)(buf * 256 + mt * block_n);
+          if (warp == 4 && it == 2) V3_TRACE(224);
           for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
             uint32_t v[32];
             tmem_ld_32x32(taddr + (uint32_t)c0, v);
             tmem_ld_wait();
+            if (warp == 4 && it == 2) V3_TRACE(225 + 2 * ((c0 - c_lo) >> 5));
             const int nbase = n_tile * block_n + c0;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -524,24 +768,31 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
                   f[4 * j4 + 2] = __uint_as_float(v[h * 16 + 4 * j4 + 2]) + bb.z;
                   f[4 * j4 + 3] = __uint_as_float(v[h * 16 + 4 * j4 + 3]) + bb.w;
                 }
-                if (p.act == PSSR_ACT_RELU) {
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-                } else if (p.act == PSSR_ACT_GELU) {
+                if (p.act == PSSR_ACT_GELU) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) f[j] = v3_gelu(f[j]);
                 }
                 if (p.out_scale != nullptr) {
+                  if (relu) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+                  }
 #pragma unroll
                   for (int j = 0; j < 16; ++j) f[j] *= scale_s[nn + j];
                 }
+                const bool relu_pack = relu && p.out_scale == nullptr;      // ReLU folded into the 16-bit conversion
                 uint32_t o[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = pack2(f[2 * j], f[2 * j + 1], p.fp16);
+                for (int j = 0; j < 8; ++j) o[j] = v3_pack2(f[2 * j], f[2 * j + 1], p.fp16, relu_pack);
                 if (p.wide_store) {
                   const size_t pix = pix00 + (size_t)si * p.Wout + (size_t)sj;
                   v3_st_global_v8(p.out + pix * p.out_cstride + p.out_choff + cc, o);
+                  if (warp == 4 && it == 2 && h == 1) V3_TRACE(226 + 2 * ((c0 - c_lo) >> 5));
                 } else {
+                  if (relu_pack && p.out_f32 != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+                  }
 #pragma unroll
                   for (int g = 0; g < 2; ++g) {
                     const int n8 = nn + g * 8;
@@ -565,18 +816,35 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
           }
         }
       }
+      // the accumulator buffer goes back to the MMA issuer.  Only the TMEM reads must be ordered before this arrival (they
+      // are: tcgen05.wait::ld + the fence); a cluster-scope RELEASE would also wait for this thread's global stores.
+      if (warp == 4 && it == 2) V3_TRACE(230);
       tc_fence_before();
+      if (warp == 4 && it == 2) V3_TRACE(231);
       __syncwarp();
-      if (lane == 0) mbar_arrive(t_empty(buf));
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(t_empty(buf));
+        else v3_arrive_cluster(v3_mapa(t_empty(buf), 0));
+      }
+      if (warp == 4 && it < 31) V3_TRACE(65 + 2 * it);
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) v3_cluster_sync();     // the peer's shared memory and barriers stay alive until the leader's MMAs are done
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) v3_tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
+    V3_TRACE(127);
   }
+}
+
+int v3_trace_fetch(long long* host, int n) {
+  if (n > 148 * 256) n = 148 * 256;
+  PSSR_CHECK_CUDA(cudaMemcpyFromSymbol(host, g_v3_trace, sizeof(long long) * (size_t)n));
+  return PSSR_OK;
 }
 
 // --------------------------------------------------------------------------------- host
@@ -596,14 +864,13 @@ static EncodeTiledFn v3_encode_fn() {
 }
 
 typedef void (*V3Kernel)(const V3Params);
-struct V3Variant { int T, G, RES, TAIL; V3Kernel fn; };
-static const V3Variant kV3Variants[] = {
-    {1, 1, 0, 0, conv_v3_kernel<1, 1, false, false>}, {1, 3, 0, 0, conv_v3_kernel<1, 3, false, false>},
-    {1, 9, 0, 0, conv_v3_kernel<1, 9, false, false>}, {1, 9, 1, 0, conv_v3_kernel<1, 9, true, false>},
-    {2, 1, 0, 0, conv_v3_kernel<2, 1, false, false>}, {2, 3, 0, 0, conv_v3_kernel<2, 3, false, false>},
-    {2, 9, 0, 0, conv_v3_kernel<2, 9, false, false>}, {2, 9, 1, 0, conv_v3_kernel<2, 9, true, false>},
-    {1, 1, 0, 1, conv_v3_kernel<1, 1, false, true>},  {1, 3, 0, 1, conv_v3_kernel<1, 3, false, true>},
-};
+struct V3Variant { int T, G, RES, TAIL, PAIR, ROWS; V3Kernel fn; };
+#define V3_VARIANT(T, G, RES, TAIL, PAIR, ROWS) {T, G, RES, TAIL, PAIR, ROWS, conv_v3_kernel<T, G, RES != 0, TAIL != 0, PAIR != 0, ROWS != 0>}
+#define V3_VARIANTS_PR(PAIR, ROWS)                                                                                             \
+  V3_VARIANT(1, 1, 0, 0, PAIR, ROWS), V3_VARIANT(1, 3, 0, 0, PAIR, ROWS), V3_VARIANT(1, 9, 1, 0, PAIR, ROWS),                  \
+  V3_VARIANT(2, 1, 0, 0, PAIR, ROWS), V3_VARIANT(2, 3, 0, 0, PAIR, ROWS), V3_VARIANT(2, 9, 1, 0, PAIR, ROWS),                  \
+  V3_VARIANT(1, 1, 0, 1, PAIR, ROWS), V3_VARIANT(1, 3, 0, 1, PAIR, ROWS)
+static const V3Variant kV3Variants[] = {V3_VARIANTS_PR(0, 0), V3_VARIANTS_PR(1, 0), V3_VARIANTS_PR(0, 1), V3_VARIANTS_PR(1, 1)};
 static const int kV3NumVariants = (int)(sizeof(kV3Variants) / sizeof(kV3Variants[0]));
 
 bool v3_supported(const pssr_conv_desc_t& d) {
@@ -615,7 +882,7 @@ bool v3_supported(const pssr_conv_desc_t& d) {
   for (int s = 0; s < d.n_segs; ++s) any9 = any9 || d.segs[s].taps == 9;
   // small feature maps: the padded pixel space wastes (1 - HW/((H+2)(W+2))) of the MMAs (36 % at 8x8, 21 % at 16x16)
   // and the exact-tile kernel (conv_igemm.cu) is faster there
-  if (any9 && d.Wo < 32 && d.tail_z == nullptr) return false;
+  if (any9 && d.Wo < 32 && d.tail_z == nullptr && getenv("PSSR_V3_SMALL") == nullptr) return false;
   if (d.tail_z != nullptr) {
     const int cps = d.n_valid / (d.shuffle * d.shuffle);
     if (cps != 64 || d.n % 256 != 0 || !any9) return false;   // other tail shapes: v2's CUDA-core tail
@@ -679,9 +946,13 @@ int v3_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
     num_kb += sg.taps * sg.cblocks;
   }
   p.num_kb = num_kb;
-  p.tap_bytes = (uint32_t)(block_n * 128);
+  // CTA pairs (cta_group::2): each CTA holds half of the weight rows, one MMA instruction drives both SMs
+  const int sms = device_sm_count();
+  int PAIR = (getenv("PSSR_V3_NOPAIR") == nullptr && sms % 2 == 0 && block_n >= 32) ? 1 : 0;
+  const int C = PAIR ? 2 : 1;
+  p.tap_bytes = (uint32_t)(block_n / C * 128);
 
-  // T tiles per unit with T * block_n <= 256 (TMEM double-buffered: the epilogue of unit i overlaps the MMAs of unit i+1)
+  // T tiles per CTA and unit with T * block_n <= 256 (TMEM double-buffered: the epilogue of unit i overlaps the MMAs of unit i+1)
   int T = 256 / block_n;
   if (T > 2) T = 2;
   if (tail) T = 1;
@@ -692,29 +963,42 @@ int v3_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
   const int vec_bytes = 4 * d.n * (d.out_scale != nullptr ? 2 : 1);
   const long long smem_cap = 226 * 1024 - 1024 - vec_bytes - tailw_bytes;
   const char* envG = getenv("PSSR_V3_G");
-  int G = 1, RES = 0, b_stages = 0;
-  long long a_bytes = 0;
+  int planes = 0;
+  for (int s2 = 0; s2 < d.n_segs; ++s2) planes += d.segs[s2].cblocks;
+  p.slot_bytes = (uint32_t)(p.P * 128);
+  p.group_bytes = p.slot_bytes * (uint32_t)planes;
+  int G = 1, RES = 0, b_stages = 0, ring_R = 0;
+  long long a_total = 0, a_bytes = 0;
   for (;; --T) {
-    long long a_raw;
-    if (p.rows_mode) a_raw = (long long)(T + 2) * p.P * 128;
-    else if (p.pad) a_raw = (long long)(128 * T + 4 * p.P + 1) * 128;
-    else a_raw = 128LL * T * 128;
-    a_bytes = ((a_raw + 1023) / 1024) * 1024;
-    const long long left = smem_cap - 2 * a_bytes;
+    long long a_min;        // smallest A staging that works; rows mode: the ring grows into whatever the weights leave
+    if (p.rows_mode) {
+      a_min = (long long)(T + 2 + T) * p.group_bytes;          // the current group and one group of prefetch
+    } else {
+      const long long a_raw = p.pad ? (long long)(128 * T + 4 * p.P + 1) * 128 : 128LL * T * 128;
+      a_bytes = ((a_raw + 1023) / 1024) * 1024;
+      a_min = 2 * a_bytes;
+    }
+    a_min = ((a_min + 1023) / 1024) * 1024;
+    const long long left = smem_cap - a_min;
     G = 0; RES = 0; b_stages = 0;
-    if (!tail && p.n_tiles == 1 && (long long)num_kb * p.tap_bytes <= left && getenv("PSSR_V3_NORES") == nullptr) {
+    if (p.n_tiles == 1 && (long long)num_kb * p.tap_bytes <= left && getenv("PSSR_V3_NORES") == nullptr && !tail) {
       RES = 1; G = 9; b_stages = 1;
     } else {
       // small N: a stage must hold many MMAs (a barrier poll costs ~100 unhidden cycles); N = 256: finer stages, deeper prefetch
-      const int cand[3] = {9, 3, 1};
-      for (int ci = (block_n >= 256 ? 2 : 0); ci < 3; ++ci) {
+      const int cand[2] = {3, 1};
+      for (int ci = (block_n >= 256 ? 1 : 0); ci < 2; ++ci) {
         const int g = cand[ci];
         if (envG && atoi(envG) != g) continue;
-        if (tail && g == 9) continue;
         if (!p.pad && g != 1) continue;
         const long long stage = (long long)g * p.tap_bytes;
         const int need = g == 1 ? 3 : 2;
-        if (left >= need * stage) { G = g; b_stages = (int)(left / stage); break; }
+        if (left >= need * stage) {
+          G = g;
+          b_stages = (int)(left / stage);
+          const int want = g == 1 ? 6 : 3;                      // rows mode: the rest goes to the ring
+          if (p.rows_mode && b_stages > want) b_stages = want;
+          break;
+        }
       }
       if (G == 0 && left >= 2LL * p.tap_bytes) { G = 1; b_stages = (int)(left / p.tap_bytes); }
       if (b_stages > kV3MaxB) b_stages = kV3MaxB;
@@ -722,22 +1006,34 @@ int v3_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
     if (G != 0 || T == 1) break;
   }
   PSSR_REQUIRE(G != 0 && b_stages >= 1, PSSR_EUNSUP, "conv: image width %d needs more shared memory than available", d.Wo);
-  p.a_bytes = (uint32_t)a_bytes;
   p.b_bytes = (uint32_t)(G * (int)p.tap_bytes);
   p.b_stages = b_stages;
+  const long long b_total_ll = RES ? (long long)num_kb * p.tap_bytes : (long long)b_stages * p.b_bytes;
   if (p.rows_mode) {
-    p.off_px = p.P + 1;
-    p.tile_step = (uint32_t)(p.P * 8);
-    p.a_tx_bytes = (uint32_t)((T + 2) * p.P * 128);
-    p.units_m = p.total_vrows / T;
-  } else if (p.pad) {
-    p.off_px = 2 * p.P + 1;
-    p.tile_step = 1024;
-    p.units_m = (p.q_end - p.q_begin + 128 * T - 1) / (128 * T);
-  } else {
+    ring_R = (int)((smem_cap - b_total_ll) / p.group_bytes);
+    if (ring_R > kV3MaxR) ring_R = kV3MaxR;
+    PSSR_REQUIRE(ring_R >= T + 2, PSSR_EUNSUP, "conv: the row ring does not fit in shared memory");
+    p.ring_R = ring_R;
+    p.ring_bytes = (uint32_t)((((long long)ring_R * p.group_bytes + 1023) / 1024) * 1024);
+    if ((long long)p.ring_bytes + b_total_ll > smem_cap) { p.ring_R = --ring_R; p.ring_bytes = (uint32_t)((((long long)ring_R * p.group_bytes + 1023) / 1024) * 1024); }
+    PSSR_REQUIRE(ring_R >= T + 2, PSSR_EUNSUP, "conv: the row ring does not fit in shared memory");
+    a_total = p.ring_bytes;
+    p.a_bytes = 0;
     p.off_px = 0;
-    p.tile_step = 1024;
-    p.units_m = (p.q_end + 128 * T - 1) / (128 * T);
+    p.tile_step = 0;
+    p.units_m = p.total_vrows / T;       // row groups
+  } else {
+    p.a_bytes = (uint32_t)a_bytes;
+    a_total = 2 * a_bytes;
+    if (p.pad) {
+      p.off_px = 2 * p.P + 1;
+      p.tile_step = 1024;
+      p.units_m = (p.q_end - p.q_begin + 128 * T * C - 1) / (128 * T * C);
+    } else {
+      p.off_px = 0;
+      p.tile_step = 1024;
+      p.units_m = (p.q_end + 128 * T * C - 1) / (128 * T * C);
+    }
   }
   p.total_units = p.units_m * p.n_tiles;
   const char* envd = getenv("PSSR_DBG");
@@ -753,7 +1049,7 @@ int v3_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
     if (p.pad) {
       cuuint64_t gdim[4] = {(cuuint64_t)src.channels, (cuuint64_t)src.W, (cuuint64_t)src.H, (cuuint64_t)src.B};
       cuuint64_t gstr[3] = {(cuuint64_t)src.cstride * 2, (cuuint64_t)src.cstride * 2 * src.W, (cuuint64_t)src.cstride * 2 * src.W * src.H};
-      cuuint32_t box[4] = {64, (cuuint32_t)p.P, (cuuint32_t)(p.rows_mode ? T + 2 : 1), 1};
+      cuuint32_t box[4] = {64, (cuuint32_t)p.P, 1, 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
       r = enc(&op.tmaps[s], tdt, 4, const_cast<void*>(src.base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -772,14 +1068,13 @@ int v3_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
     const cuuint64_t ktot = (cuuint64_t)num_kb * 64;
     cuuint64_t gdim[2] = {ktot, (cuuint64_t)d.n};
     cuuint64_t gstr[1] = {ktot * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)block_n};
+    cuuint32_t box[2] = {64, (cuuint32_t)(block_n / C)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&op.tmaps[3], tdt, 2, const_cast<void*>(d.weights), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PSSR_REQUIRE(r == CUDA_SUCCESS, PSSR_ECUDA, "cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
   }
-  const uint32_t b_total = RES ? (uint32_t)num_kb * p.tap_bytes : (uint32_t)b_stages * p.b_bytes;
-  op.smem_bytes = (int)(2 * p.a_bytes + b_total + 1024 + (uint32_t)vec_bytes + (uint32_t)tailw_bytes);
+  op.smem_bytes = (int)(a_total + b_total_ll + 1024 + vec_bytes + tailw_bytes);
 
   p.bias = d.bias;
   p.out_scale = d.out_scale;
@@ -797,12 +1092,22 @@ int v3_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
   p.Wout = d.Wo * d.shuffle;
   p.wide_store = (d.out != nullptr && d.out_f32 == nullptr && cps % 16 == 0 && d.out_choff % 16 == 0 && d.out_cstride % 16 == 0 &&
                   d.n_valid % 16 == 0 && ((uintptr_t)d.out & 31) == 0) ? 1 : 0;
-  const int sms = device_sm_count();
-  op.grid = p.total_units < sms ? p.total_units : sms;
+  int workers = sms / C;
+  if (p.rows_mode) {
+    int gmax = p.units_m / C;          // every worker gets at least one row group per CTA
+    if (gmax < 1) gmax = 1;
+    if (workers > gmax) workers = gmax;
+  } else if (workers > p.total_units) {
+    workers = p.total_units;
+  }
+  op.grid = workers * C;
+  op.cluster = C;
   op.kernel_index = -1;
   for (int i = 0; i < kV3NumVariants; ++i)
-    if (kV3Variants[i].T == T && kV3Variants[i].G == G && kV3Variants[i].RES == RES && kV3Variants[i].TAIL == (tail ? 1 : 0)) op.kernel_index = i;
-  PSSR_REQUIRE(op.kernel_index >= 0, PSSR_EUNSUP, "conv: no kernel variant for T=%d G=%d RES=%d TAIL=%d", T, G, RES, (int)tail);
+    if (kV3Variants[i].T == T && kV3Variants[i].G == G && kV3Variants[i].RES == RES && kV3Variants[i].TAIL == (tail ? 1 : 0) &&
+        kV3Variants[i].PAIR == PAIR && kV3Variants[i].ROWS == p.rows_mode)
+      op.kernel_index = i;
+  PSSR_REQUIRE(op.kernel_index >= 0, PSSR_EUNSUP, "conv: no kernel variant for T=%d G=%d RES=%d TAIL=%d PAIR=%d", T, G, RES, (int)tail, PAIR);
   static bool attr_set = false;
   if (!attr_set) {
     for (int i = 0; i < kV3NumVariants; ++i)
@@ -810,17 +1115,30 @@ int v3_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
     attr_set = true;
   }
   if (getenv("PSSR_V3_VERBOSE") != nullptr)
-    fprintf(stderr, "v3: %dx%d n=%d kb=%d block_n=%d T=%d G=%d RES=%d TAIL=%d rows=%d b_stages=%d a_bytes=%u smem=%d units=%d\n", d.Ho, d.Wo, d.n,
-            num_kb, block_n, T, G, RES, (int)tail, p.rows_mode, b_stages, p.a_bytes, op.smem_bytes, p.total_units);
+    fprintf(stderr, "v3: %dx%d n=%d kb=%d block_n=%d T=%d G=%d RES=%d TAIL=%d PAIR=%d rows=%d ring=%d b_stages=%d a_bytes=%u smem=%d units=%d grid=%d\n",
+            d.Ho, d.Wo, d.n, num_kb, block_n, T, G, RES, (int)tail, PAIR, p.rows_mode, p.ring_R, b_stages, p.a_bytes, op.smem_bytes, p.total_units,
+            op.grid);
   return PSSR_OK;
 }
 
 int v3_launch(const ConvOp& op, const void* tmaps_dev, cudaStream_t stream) {
   V3Params p = *reinterpret_cast<const V3Params*>(op.kparams);
   p.tmaps = reinterpret_cast<const CUtensorMap*>(tmaps_dev);
-  kV3Variants[op.kernel_index].fn<<<op.grid, kV3Threads, op.smem_bytes, stream>>>(p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)op.grid, 1, 1);
+  cfg.blockDim = dim3(kV3Threads, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)op.smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)op.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = op.cluster > 1 ? 1 : 0;
+  PSSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kV3Variants[op.kernel_index].fn, p));
   count_launch();
-  PSSR_CHECK_CUDA(cudaGetLastError());
   return PSSR_OK;
 }
 

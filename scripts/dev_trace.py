@@ -17,12 +17,15 @@ for ci in [int(a) for a in sys.argv[1:]] or [2]:
     rc = _lib.lib().pssr_debug_trace(buf.ctypes.data, buf.size)
     assert rc == 0
     tr = buf.reshape(148, 256)
-    print("DBG", os.environ["PSSR_DBG"], "cfg", cfg)
-    st = tr[0][128:256]; st = st[st > 0]
-    print("  cta 0 unit 1 per-stage b_full-wait-done deltas:", np.diff(st)[:60].tolist())
-    for cta in (0, 73):
+    print("DBG", os.environ["PSSR_DBG"], "NOPAIR", os.environ.get("PSSR_V3_NOPAIR"), "cfg", cfg)
+    t = tr[0]
+    print("  cta0 warp4 unit2 epilogue: ready->idx %d, ->ld0 %d, ->st0 %d, ->ld1 %d, ->st1 %d, ->loopend %d, ->fence %d, ->arrived %d" % (
+        t[224]-t[64+4], t[225]-t[224], t[226]-t[225], t[227]-t[226], t[228]-t[227], t[230]-t[228], t[231]-t[230], t[65+4]-t[231]))
+    for cta in (0, 1):
         t = tr[cta]; t0 = t[0]
-        units = [u for u in range(30) if t[2 + 2 * u] > 0 and t[2 + 2 * u] >= t0]
-        print(f" cta {cta}: setup {t[1]-t0} cyc; exit at {t[127]-t0}; units {len(units)}")
-        for u in units:
-            print(f"   unit {u}: mma first-issue {t[2+2*u]-t0:7d} commit-issued {t[3+2*u]-t0:7d} | acc ready {t[64+2*u]-t0:7d} epi done {t[65+2*u]-t0:7d}  (epi {t[65+2*u]-t[64+2*u]})")
+        print(f" cta {cta}: setup {t[1]-t0} cyc; exit at {t[127]-t0}")
+        for u in range(8):
+            if t[64 + 2 * u] <= 0:
+                continue
+            m = f"buffer free {t[2+2*u]-t0:7d} A landed {t[128+2*u]-t0:7d} committed {t[3+2*u]-t0:7d}" if t[2 + 2 * u] > 0 else " " * 60
+            print(f"   unit {u}: {m} | acc ready {t[64+2*u]-t0:7d} epi done {t[65+2*u]-t0:7d} (epi {t[65+2*u]-t[64+2*u]})")
