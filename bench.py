@@ -221,25 +221,28 @@ def run_ours(args):
         return
 
     # ---- e2e through the public API from pinned host buffers ---------------------------------
+    # ONE predict_images call over a dataset of `e2e_steps` batches (one pinned host stack of 64 tiles per step): the timed
+    # region holds the dataset construction (host -> device upload of every stack), crappify, forward, and the device -> host
+    # read of every uint8 prediction; uploads and read-backs overlap the kernels of neighbouring batches.
+    e2e_steps = max(2, min(args.steps, 10))
     host = [b.cpu().pin_memory() for b in batches[:2]]
+    stacks = [host[i % 2] for i in range(e2e_steps)]
 
-    def e2e_step(i):
-        ds = ImageDataset([host[i % 2]], hr_res=TILE, lr_scale=SCALE, crappifier=crap, n_frames=1, val_split=1, device=dev)
-        preds = predict_images(model, ds, device=str(dev), batch_size=BATCH, out_dir=None)
-        return preds
+    def e2e_run():
+        ds = ImageDataset(list(stacks), hr_res=TILE, lr_scale=SCALE, crappifier=crap, n_frames=1, val_split=1, device=dev)
+        return predict_images(model, ds, device=str(dev), batch_size=BATCH, out_dir=None)
 
     import contextlib
     import io
     with contextlib.redirect_stderr(io.StringIO()), contextlib.redirect_stdout(io.StringIO()):
-        for i in range(2):
-            e2e_step(i)
+        preds = e2e_run()
+        del preds
         barrier()
         t0 = time.perf_counter()
-        e2e_steps = max(2, min(args.steps, 10))
-        for i in range(e2e_steps):
-            preds = e2e_step(i)
+        preds = e2e_run()
         torch.cuda.synchronize()
         e2e_dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+        assert len(preds) == e2e_steps * BATCH
     if world > 1:
         dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
     e2e_value = world * BATCH * TILE * TILE / float(e2e_dt) / 1e6
@@ -293,7 +296,7 @@ def run_ours(args):
                        "l2": f"inputs rotate over {NB} resident batches ({NB * h2d / 1e6:.0f} MB) and each step streams >4 GB of "
                              "activations, both > 126 MB L2"},
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "ImageDataset(pinned host stack) + predict_images(out_dir=None)"},
+                    "api": "ImageDataset(pinned host stacks, one per step) + one predict_images(batch_size=64, out_dir=None) call over all steps"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "metric_check": {"mean_psnr_db": None}}
     s = sums.cpu()

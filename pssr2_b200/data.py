@@ -146,11 +146,31 @@ class _DeviceDataset(Dataset):
             raise NotImplementedError("all images of one dataset must share height, width and dtype on the device path")
         self.device = torch.device(device)
         self._sheets = []
-        for a in arrays:
+        self._sheet_events = {}     # sheet index -> upload-complete event not yet waited for by the compute stream
+        # sheets go up on a side stream, one event per sheet: batch() waits only for the sheets it gathers from, so the
+        # upload of later sheets overlaps the first batches (pinned host tensors make the copies truly asynchronous)
+        up = torch.cuda.Stream(device=self.device)
+        for i, a in enumerate(arrays):
             t = a if isinstance(a, torch.Tensor) else torch.as_tensor(a.view(np.int16) if a.dtype == np.uint16 else a)
-            self._sheets.append(t.to(self.device, non_blocking=True))
+            with torch.cuda.stream(up):
+                d = t.to(self.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(up)
+            self._sheets.append(d)
+            self._sheet_events[i] = ev
+        self._upload_stream = up
         self._frames_total = [a.shape[0] for a in arrays]
         self._shape = next(iter(shapes))
+
+    def _wait_sheets(self, sheet_ids):
+        """Orders the current stream after the upload of the given sheets (each event is waited for once)."""
+        if not self._sheet_events:
+            return
+        cur = torch.cuda.current_stream(self.device)
+        for i in set(sheet_ids):
+            ev = self._sheet_events.pop(i, None)
+            if ev is not None:
+                cur.wait_event(ev)
 
     # per-item geometry, implemented by subclasses: (sheet, frame0, y, x, vh, vw)
     def _locate(self, idx):
@@ -162,6 +182,7 @@ class _DeviceDataset(Dataset):
     def _table(self, indices):
         locs = [self._locate(i) for i in indices]
         cols = list(zip(*locs))
+        self._wait_sheets(cols[0])
         return ops.TileTable(self._sheets, *cols)
 
     def batch(self, indices, want_hr=True, want_hr_u8=False, want_lr=True, tile_index0=None, seed=None):

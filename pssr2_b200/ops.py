@@ -42,9 +42,9 @@ class TileTable:
             raise TypeError(f"sheets must be uint8 or uint16, got {s0.dtype}")
         self.sheet_h, self.sheet_w = int(s0.shape[1]), int(s0.shape[2])
         self.ptrs = torch.tensor([s.data_ptr() for s in self.sheets], dtype=torch.int64, device=dev)
-        mk = lambda a: torch.as_tensor(np.asarray(a, dtype=np.int32), device=dev)
-        self.tile_sheet, self.tile_frame, self.tile_y, self.tile_x = mk(tile_sheet), mk(tile_frame), mk(tile_y), mk(tile_x)
-        self.tile_vh, self.tile_vw = mk(tile_vh), mk(tile_vw)
+        # one host->device copy for the six index columns
+        cols = torch.as_tensor(np.asarray([tile_sheet, tile_frame, tile_y, tile_x, tile_vh, tile_vw], dtype=np.int32)).to(dev)
+        self.tile_sheet, self.tile_frame, self.tile_y, self.tile_x, self.tile_vh, self.tile_vw = (cols[i] for i in range(6))
         self.n_tiles = int(self.tile_sheet.numel())
         self.device = dev
 

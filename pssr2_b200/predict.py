@@ -53,6 +53,14 @@ def _batch(dataset, idxs, device, want_hr_u8, tile_index0=None):
     return lr, (hr[:, c:c + 1].clamp(0, 255).to(torch.uint8) if want_hr_u8 else None)
 
 
+def _to_device(model, device):
+    """model.to(device) without walking every parameter when the model already lives there."""
+    want, p = torch.device(device), next(model.parameters(), None)
+    same = p is not None and p.device.type == want.type and (want.index is None or p.device.index == want.index)
+    if not same:
+        model.to(device)
+
+
 def _save_tif(path, arr):
     from PIL import Image
     Image.fromarray(np.asarray(arr).reshape(arr.shape[-2:])).save(path, format="TIFF")
@@ -74,14 +82,36 @@ def predict_images(model: nn.Module, dataset, device: str = "cuda", batch_size=N
     if out_dir:
         os.makedirs(out_dir, exist_ok=True)
     callbacks, callback_locals = _get_callbacks(callbacks)
-    model.to(device)
+    _to_device(model, device)
     model.eval()
 
     val_idx = list(dataset.val_idx)
     lo, hi = D.shard_range(len(val_idx))
     outs = {}
+    dev = torch.device(device)
+    cur = torch.cuda.current_stream(dev)
+    down = torch.cuda.Stream(device=dev)          # device -> pinned host copies run beside the next batch's kernels
+    pending = None                                # (done event, pinned uint8 batch, positions, device buffer)
+
+    def finish(item):
+        done, host, pos, _keep = item
+        done.synchronize()
+        hr_hat = host.numpy()                     # zero-copy view of the pinned batch; the dict entries keep it alive
+        for batch_idx, image_idx in enumerate(pos):
+            name = dataset._get_name(image_idx)   # reference quirk: the POSITION in val_idx names the file (predict.py:69-73)
+            if out_dir:
+                _save_tif(f"{out_dir}/{prefix + '_' if prefix else ''}{name}.tif", hr_hat[batch_idx])
+            else:
+                outs[name] = hr_hat[batch_idx]
+            for idx, callback in enumerate(callbacks):
+                if callback_locals[idx]:
+                    callback(locals())
+                else:
+                    callback()
+
+    starts = range(lo, hi, batch_size)
     with torch.no_grad():
-        for start in _progress(range(lo, hi, batch_size)):
+        for start in (_progress(starts) if len(starts) > 1 else starts):
             pos = list(range(start, min(start + batch_size, hi)))
             idxs = [val_idx[p] for p in pos]
             lr, hr8 = _batch(dataset, idxs, device, want_hr_u8=norm)
@@ -90,18 +120,21 @@ def predict_images(model: nn.Module, dataset, device: str = "cuda", batch_size=N
                 _, hr_hat = ops.normalize_preds_u8(hr8[:, 0], hr_hat[:, 0])
                 hr_hat = hr_hat[:, None]
             crop_res = dataset.crop_res if not dataset.is_lr else dataset.crop_res * (hr_hat.shape[-1] // lr.shape[-1])
-            hr_hat = hr_hat[:, :, :crop_res, :crop_res].contiguous().cpu().numpy()
-            for batch_idx, image_idx in enumerate(pos):
-                name = dataset._get_name(image_idx)   # reference quirk: the POSITION in val_idx names the file (predict.py:69-73)
-                if out_dir:
-                    _save_tif(f"{out_dir}/{prefix + '_' if prefix else ''}{name}.tif", hr_hat[batch_idx])
-                else:
-                    outs[name] = hr_hat[batch_idx]
-                for idx, callback in enumerate(callbacks):
-                    if callback_locals[idx]:
-                        callback(locals())
-                    else:
-                        callback()
+            # own copy of the batch: the plan's output buffer is overwritten by the next forward while this one travels
+            dbuf = hr_hat[:, :, :crop_res, :crop_res].clone(memory_format=torch.contiguous_format)
+            host = torch.empty(dbuf.shape, dtype=torch.uint8, pin_memory=True)
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            done = torch.cuda.Event()
+            with torch.cuda.stream(down):
+                down.wait_event(ready)
+                host.copy_(dbuf, non_blocking=True)
+                done.record(down)
+            if pending is not None:
+                finish(pending)                   # the previous batch reaches the host while this one computes
+            pending = (done, host, pos, dbuf)
+        if pending is not None:
+            finish(pending)
     if out_dir is None:
         return D.gather_dict(outs)
 
@@ -120,15 +153,42 @@ def test_metrics(model: nn.Module, dataset, device: str = "cuda", metrics=["mse"
     names = list(metrics)
     if not str(device).startswith("cuda"):
         raise RuntimeError("pssr2_b200.test_metrics runs on CUDA devices only (no CPU fallback); pass device='cuda'")
-    model.to(device)
+    _to_device(model, device)
     model.eval()
 
     val_idx = list(dataset.val_idx)
     lo, hi = D.shard_range(len(val_idx))
     per_image = {m: [] for m in names}
     want_ssim = "ssim" in names
+    dev = torch.device(device)
+    cur = torch.cuda.current_stream(dev)
+    pending = None                                # (done event, pinned sums [2, n] float64, n, pixels, ssim pixels)
+
+    def finish(item):
+        done, host, n, n_px, n_win = item
+        done.synchronize()
+        sq, ss = host[0].numpy(), host[1].numpy()
+        for i in range(n):
+            # mean((h/255 - h_hat/255)^2) in float64 == sum d^2 / N / 255^2 up to 1e-16 relative
+            mse = float(sq[i]) / n_px / float(image_range) ** 2
+            if "mse" in per_image:
+                per_image["mse"].append(mse)
+            if "pixel" in per_image:
+                per_image["pixel"].append(pixel_metric(mse, image_range))
+            if "psnr" in per_image:
+                err = float(sq[i]) / n_px
+                per_image["psnr"].append(10 * math.log10(image_range ** 2 / err) if err > 0 else float("inf"))
+            if "ssim" in per_image:
+                per_image["ssim"].append(float(ss[i]) / n_win)
+        for idx, callback in enumerate(callbacks):
+            if callback_locals[idx]:
+                callback(locals())
+            else:
+                callback()
+
+    starts = range(lo, hi, batch_size)
     with torch.no_grad():
-        for start in _progress(range(lo, hi, batch_size)):
+        for start in (_progress(starts) if len(starts) > 1 else starts):
             pos = list(range(start, min(start + batch_size, hi)))
             idxs = [0] * len(pos) if item0_quirk else [val_idx[p] for p in pos]
             lr, hr8 = _batch(dataset, idxs, device, want_hr_u8=True, tile_index0=pos[0])
@@ -138,26 +198,17 @@ def test_metrics(model: nn.Module, dataset, device: str = "cuda", metrics=["mse"
             if norm:
                 hr, hr_hat = ops.normalize_preds_u8(hr, hr_hat)
             sq, ss = ops.metric_sums(hr, hr_hat, want_ssim=want_ssim)
-            sq = sq.cpu().numpy()
-            ss = ss.cpu().numpy() if ss is not None else None
-            n_px = hr.shape[-1] * hr.shape[-2]
-            for i in range(len(pos)):
-                # mean((h/255 - h_hat/255)^2) in float64 == sum d^2 / N / 255^2 up to 1e-16 relative
-                mse = float(sq[i]) / n_px / float(image_range) ** 2
-                if "mse" in per_image:
-                    per_image["mse"].append(mse)
-                if "pixel" in per_image:
-                    per_image["pixel"].append(pixel_metric(mse, image_range))
-                if "psnr" in per_image:
-                    err = float(sq[i]) / n_px
-                    per_image["psnr"].append(10 * math.log10(image_range ** 2 / err) if err > 0 else float("inf"))
-                if "ssim" in per_image:
-                    per_image["ssim"].append(float(ss[i]) / ((hr.shape[-2] - 6) * (hr.shape[-1] - 6)))
-            for idx, callback in enumerate(callbacks):
-                if callback_locals[idx]:
-                    callback(locals())
-                else:
-                    callback()
+            # the two small sum vectors travel to pinned memory asynchronously; they are read one batch later
+            both = torch.stack([sq.to(torch.float64), (ss if ss is not None else torch.zeros_like(sq)).to(torch.float64)])
+            host = torch.empty(both.shape, dtype=torch.float64, pin_memory=True)
+            host.copy_(both, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(cur)
+            if pending is not None:
+                finish(pending)
+            pending = (done, host, len(pos), hr.shape[-1] * hr.shape[-2], (hr.shape[-2] - 6) * (hr.shape[-1] - 6))
+        if pending is not None:
+            finish(pending)
     per_image = D.gather_metric_lists(per_image, names)
     return {m: (sum(v) / len(v) if avg else v) for m, v in per_image.items()}
 

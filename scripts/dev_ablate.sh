@@ -1,1 +1,2 @@
-PSSR_V3_SMALL=1 PSSR_V3_VERBOSE=1 timeout 300 python scripts/dev_time_net.py 64 fp16 2>&1 | grep "16x16\|8x8\|forward"
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+python bench.py --steps 20 --warmup 3 > gpurun_out/bench5.json 2> gpurun_out/bench5.err; tail -c 1800 gpurun_out/bench5.json; tail -3 gpurun_out/bench5.err
