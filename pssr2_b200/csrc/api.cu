@@ -88,7 +88,7 @@ int pssr_plan_create(const pssr_op_t* ops, int32_t n_ops, int32_t dtype, pssr_pl
     }
   }
   if (!plan->convs.empty()) {
-    const size_t bytes = plan->convs.size() * 4 * sizeof(CUtensorMap);
+    const size_t bytes = plan->convs.size() * kTmapsPerConv * sizeof(CUtensorMap);
     cudaError_t e = cudaMalloc(&plan->tmaps_dev, bytes);
     if (e != cudaSuccess) {
       set_error("plan_create: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
@@ -96,8 +96,8 @@ int pssr_plan_create(const pssr_op_t* ops, int32_t n_ops, int32_t dtype, pssr_pl
       return PSSR_ECUDA;
     }
     for (size_t i = 0; i < plan->convs.size(); ++i) {
-      e = cudaMemcpy(reinterpret_cast<uint8_t*>(plan->tmaps_dev) + i * 4 * sizeof(CUtensorMap), plan->convs[i].tmaps,
-                     4 * sizeof(CUtensorMap), cudaMemcpyHostToDevice);
+      e = cudaMemcpy(reinterpret_cast<uint8_t*>(plan->tmaps_dev) + i * kTmapsPerConv * sizeof(CUtensorMap), plan->convs[i].tmaps,
+                     kTmapsPerConv * sizeof(CUtensorMap), cudaMemcpyHostToDevice);
       if (e != cudaSuccess) {
         set_error("plan_create: tensor-map upload failed: %s", cudaGetErrorString(e));
         cudaFree(plan->tmaps_dev);
@@ -120,7 +120,7 @@ int pssr_plan_run_range(pssr_plan_t* plan, int32_t first, int32_t count, void* s
     switch (op.kind) {
       case PSSR_OP_CONV: {
         const int ci = plan->conv_index[i];
-        const void* tm = reinterpret_cast<uint8_t*>(plan->tmaps_dev) + (size_t)ci * 4 * sizeof(CUtensorMap);
+        const void* tm = reinterpret_cast<uint8_t*>(plan->tmaps_dev) + (size_t)ci * kTmapsPerConv * sizeof(CUtensorMap);
         const int variant = plan->convs[ci].variant;
         rc = variant == 3 ? v3_launch(plan->convs[ci], tm, st) : variant == 2 ? strip_launch(plan->convs[ci], tm, st) : conv_launch(plan->convs[ci], tm, st);
         break;

@@ -58,6 +58,8 @@ struct V3Params {
   float* out_f32;
   int out_cstride, out_choff, shuffle, cps, act, fp16;
   int Hout, Wout;
+  int tma_store;              // 1: the epilogue stages 16-bit tiles in shared memory and writes them with TMA (tmaps[4])
+  uint32_t stage_off;         // byte offset of the 8 x 4 KB store staging tiles inside the aligned dynamic shared memory
   const float* tail_w;        // fused Reconstruction tail: fp32 [9][64]
   float* tail_z;              // fp32 planar [B][r*r*9][H][W]
 };
@@ -192,6 +194,19 @@ __device__ __forceinline__ float v3_gelu(float x) {
   return 0.5f * x * (1.0f + copysignf(e, x));
 }
 
+// TMA stores of the epilogue: shared memory tile -> global, out-of-range coordinates are clipped by the TMA unit
+__device__ __forceinline__ void v3_tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void v3_tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tmap), "r"(src), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void v3_st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // 16-bit pack with saturation to the finite range (and optional ReLU) in one F2FP instruction
 __device__ __forceinline__ uint32_t v3_pack2(float lo, float hi, int fp16, bool relu) {
   uint32_t d;
@@ -280,6 +295,11 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
   const uint32_t tmem_base = tmem_base_smem;
   const int block_n = p.block_n;
   if (warp == 1) V3_TRACE(1);
+  // Programmatic dependent launch: the next kernel of the stream may start its own prologue (barriers, TMEM, bias, weight
+  // prefetch) on SMs this grid has left; this grid's own prologue above ran the same way while its predecessor drained.
+  // Everything that reads the predecessor's output (A loads) or overwrites buffers it may still read (epilogue stores)
+  // first waits for the predecessor to finish (griddepcontrol.wait); weights / bias are constants and do not wait.
+  if (threadIdx.x == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // ---- ROWS: this worker's contiguous range of row groups (a group = T rows of one virtual image) -----------------------
   // groups [g_lo, g_hi); a pair splits the range in two halves walked in lockstep (rank r: g_lo + r*msteps + ms).  The ring
@@ -311,6 +331,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
     // ============================ A producer ================================================
     // every CTA stages its own tiles; in a pair the bytes of both CTAs are counted on the leader's barrier
     if (lane == 0) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");
       if (ROWS) {
         int slot = 0;
         uint32_t phase = 0;
@@ -452,6 +473,13 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
     int as = 0, bs = 0;
     uint32_t aphase = 0, bphase = 0;
     int it = 0;
+    // K segments packed into registers (bit 0: 3x3, bits 1..8: channel blocks, bits 9..: first K block): an indexed load from
+    // the constant bank per segment would sit on the issue path of every unit
+    uint32_t segw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      segw[i] = i < p.n_segs ? ((p.seg_taps[i] == 9 ? 1u : 0u) | ((uint32_t)p.seg_cblocks[i] << 1) | ((uint32_t)p.seg_kb0[i] << 9)) : 0u;
+    const int n_segs = p.n_segs;
 
     auto issue_tail = [&](int pit) {
       const int pbuf = pit & 1;
@@ -484,9 +512,11 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
       uint32_t acc = 0;
       bool tail_done = false;
       uint64_t plane_desc = 0;
-      for (int sg = 0; sg < p.n_segs; ++sg) {
-        const bool nine = p.seg_taps[sg] == 9;
-        const int cbs = p.seg_cblocks[sg];
+      for (int sg = 0; sg < n_segs; ++sg) {
+        const uint32_t sw = sg == 0 ? segw[0] : sg == 1 ? segw[1] : sg == 2 ? segw[2] : segw[3];
+        const bool nine = (sw & 1u) != 0;
+        const int cbs = (int)((sw >> 1) & 0xffu);
+        const int kb0 = (int)(sw >> 9);
         for (int cb = 0; cb < cbs; ++cb, plane_desc += slot_desc) {
           uint64_t ad0 = 0;
           if (!ROWS) {
@@ -500,7 +530,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
             for (int t0 = 0; t0 < 9; t0 += G) {
               uint64_t bd;
               if (RES) {
-                bd = bdesc0 + (uint64_t)((uint32_t)(p.seg_kb0[sg] + t0 * cbs + cb) * tapstep);
+                bd = bdesc0 + (uint64_t)((uint32_t)(kb0 + t0 * cbs + cb) * tapstep);
               } else {
                 mbar_wait(b_full(bs), bphase);
                 tc_fence_after();
@@ -539,7 +569,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
           } else {
             uint64_t bd;
             if (RES) {
-              bd = bdesc0 + (uint64_t)((uint32_t)(p.seg_kb0[sg] + cb) * tapstep);
+              bd = bdesc0 + (uint64_t)((uint32_t)(kb0 + cb) * tapstep);
             } else {
               mbar_wait(b_full(bs), bphase);
               tc_fence_after();
@@ -586,6 +616,15 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
       int cslot = 0;                // next ring slot to be consumed
       uint32_t cphase = 0;
       bool fresh = true;
+      // first row of each CTA's current group, advanced by T per step (no divisions on the issue path); must reproduce
+      // step_fresh(): a step is fresh when a CTA enters a new image or the pair's second half has run out of groups
+      int y0r[C];
+#pragma unroll
+      for (int rk = 0; rk < C; ++rk) {
+        bool v;
+        y0r[rk] = (group_of(0, rk, v) * T) % p.H;
+      }
+      const bool odd_tail = PAIR && (((g_hi - g_lo) & 1) != 0);
       for (int ms = 0; ms < msteps; ++ms) {
         const int count = fresh ? T + 2 : T;
         int first = fresh ? cslot : cslot - 2;
@@ -607,7 +646,13 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
         for (int nt = 0; nt < p.n_tiles; ++nt) run_k(ea);
         // rows that no later group of this worker needs go back to the producer
         const bool last = ms + 1 == msteps;
-        const bool next_fresh = last ? true : step_fresh(ms + 1);
+        bool next_fresh = odd_tail && ms + 2 == msteps;
+#pragma unroll
+        for (int rk = 0; rk < C; ++rk) {
+          y0r[rk] += T;
+          if (y0r[rk] >= p.H) y0r[rk] -= p.H;
+          next_fresh = next_fresh || y0r[rk] == 0;
+        }
         if (!last) {
           if (elect_one()) {
 #pragma unroll
@@ -633,6 +678,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
     const bool relu = p.act == PSSR_ACT_RELU;
     const int steps = ROWS ? msteps * p.n_tiles : 0;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     int it = 0;
     for (int unit = worker; ROWS ? it < steps : unit < p.total_units; unit += workers, ++it) {
       const int n_tile = ROWS ? it % p.n_tiles : unit % p.n_tiles;
@@ -738,6 +784,73 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
             x = rem - y * p.P;
             valid = q < p.q_end;
           }
+          if (p.tma_store) {
+            // ---- 16-bit tile [32 pixels x 64 channels] -> swizzled shared memory -> one TMA store (two when the 32 flat
+            // pixels wrap to the next image row); padding / out-of-range positions are clipped by the TMA unit ----------
+            const uint32_t stg = smem_base + p.stage_off + (uint32_t)(warp - 4) * 4096u;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous tile has left the buffer
+            __syncwarp();
+            const uint32_t taddr2 = lane_addr + (uint32_t)(buf * 256 + mt * block_n + c_lo);
+            const int nb = n_tile * block_n + c_lo;
+#pragma unroll
+            for (int cq = 0; cq < 2; ++cq) {
+              uint32_t v[32];
+              tmem_ld_32x32(taddr2 + (uint32_t)(cq * 32), v);
+              tmem_ld_wait();
+              float f[32];
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 bb = *reinterpret_cast<const float4*>(bias_s + nb + cq * 32 + 4 * j4);
+                f[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) + bb.x;
+                f[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + bb.y;
+                f[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + bb.z;
+                f[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + bb.w;
+              }
+              if (p.act == PSSR_ACT_GELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = v3_gelu(f[j]);
+              }
+              if (p.out_scale != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = (relu ? fmaxf(f[j], 0.f) : f[j]) * scale_s[nb + cq * 32 + j];
+              }
+              const bool relu_pack = relu && p.out_scale == nullptr;
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const uint32_t chunk = (uint32_t)(cq * 4 + j4) ^ (uint32_t)(lane & 7);
+                v3_st_shared_v4(stg + (uint32_t)lane * 128u + chunk * 16u, v3_pack2(f[8 * j4 + 0], f[8 * j4 + 1], p.fp16, relu_pack),
+                                v3_pack2(f[8 * j4 + 2], f[8 * j4 + 3], p.fp16, relu_pack), v3_pack2(f[8 * j4 + 4], f[8 * j4 + 5], p.fp16, relu_pack),
+                                v3_pack2(f[8 * j4 + 6], f[8 * j4 + 7], p.fp16, relu_pack));
+              }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0 && !(p.dbg & 1)) {
+              const CUtensorMap* tmo = p.tmaps + 4;
+              if (ROWS) {
+                if (gvalid) v3_tma_store_4d(tmo, stg, nb, gx0 + q4 * 32, gy0 + mt, gn);
+              } else if (p.pad) {
+                const int q0 = p.q_begin + (um * T + mt) * 128 + q4 * 32;
+                const int vimg = q0 / p.IP;
+                const int rem = q0 - vimg * p.IP;
+                const int py = rem / p.P;
+                const int px = rem - py * p.P;
+                // a box is issued only when it covers real pixels (rows of the zero halo / beyond the batch are skipped);
+                // its columns left of x = 0 or right of x = W - 1 are clipped by the TMA unit
+                if (py >= 1 && py <= p.H && vimg < p.B && px <= p.W) v3_tma_store_4d(tmo, stg, nb, px - 1, py - 1, vimg);
+                if (px + 32 > p.P) {              // the tail of the 32 pixels lies in the next padded row (maybe the next image)
+                  const int q1 = q0 + (p.P - px);
+                  const int vimg1 = q1 / p.IP;
+                  const int py1 = (q1 - vimg1 * p.IP) / p.P;
+                  if (py1 >= 1 && py1 <= p.H && vimg1 < p.B) v3_tma_store_4d(tmo, stg, nb, -1 - (p.P - px), py1 - 1, vimg1);
+                }
+              } else {
+                if ((um * T + mt) * 128 + q4 * 32 < p.q_end) v3_tma_store_2d(tmo, stg, nb, (um * T + mt) * 128 + q4 * 32);
+              }
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            continue;
+          }
           // sub-pixel / channel position of the item's first output column, advanced incrementally
           int sub = (n_tile * block_n + c_lo) / p.cps;
           int cc = n_tile * block_n + c_lo - sub * p.cps;
@@ -830,6 +943,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
     }
   }
 
+  if (warp >= 4 && lane == 0 && p.tma_store) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staging tiles fully written out
   tc_fence_before();
   __syncthreads();
   if (PAIR) v3_cluster_sync();     // the peer's shared memory and barriers stay alive until the leader's MMAs are done
@@ -960,8 +1074,13 @@ int v3_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
   const char* envT = getenv("PSSR_V3_T");
   if (envT && atoi(envT) == 1) T = 1;
   const int tailw_bytes = tail ? 2048 : 0;
-  const int vec_bytes = 4 * d.n * (d.out_scale != nullptr ? 2 : 1);
-  const long long smem_cap = 226 * 1024 - 1024 - vec_bytes - tailw_bytes;
+  const int vec_bytes = ((4 * d.n * (d.out_scale != nullptr ? 2 : 1) + 1023) / 1024) * 1024;
+  // epilogue through shared memory + TMA stores (full 128-byte lines, asynchronous) where the output is a plain 16-bit NHWC view
+  // and every 32-pixel box lies inside the image (rows mode, 1x1 layers).  Measured on B200: store boxes with out-of-range
+  // coordinates on several sides raise an illegal-instruction fault, so the flat 3x3 mode keeps its direct stores.
+  p.tma_store = (!tail && d.shuffle == 1 && d.out != nullptr && d.out_f32 == nullptr && d.n_valid % 64 == 0 && block_n % 64 == 0 &&
+                 (p.rows_mode || !p.pad || getenv("PSSR_V3_TMA_STORE_FLAT") != nullptr) && getenv("PSSR_V3_NO_TMA_STORE") == nullptr) ? 1 : 0;
+  const long long smem_cap0 = 226 * 1024 - 1024 - vec_bytes - tailw_bytes;
   const char* envG = getenv("PSSR_V3_G");
   int planes = 0;
   for (int s2 = 0; s2 < d.n_segs; ++s2) planes += d.segs[s2].cblocks;
@@ -969,7 +1088,11 @@ int v3_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
   p.group_bytes = p.slot_bytes * (uint32_t)planes;
   int G = 1, RES = 0, b_stages = 0, ring_R = 0;
   long long a_total = 0, a_bytes = 0;
-  for (;; --T) {
+  const int T_first = T;
+  int stage_bytes = p.tma_store ? 8 * 4096 : 0;
+  long long smem_cap = smem_cap0 - stage_bytes;
+retry_sizes:
+  for (T = T_first;; --T) {
     long long a_min;        // smallest A staging that works; rows mode: the ring grows into whatever the weights leave
     if (p.rows_mode) {
       a_min = (long long)(T + 2 + T) * p.group_bytes;          // the current group and one group of prefetch
@@ -1004,6 +1127,13 @@ int v3_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
       if (b_stages > kV3MaxB) b_stages = kV3MaxB;
     }
     if (G != 0 || T == 1) break;
+  }
+  if ((G == 0 || (p.rows_mode && (smem_cap - (RES ? (long long)num_kb * p.tap_bytes : (long long)b_stages * G * p.tap_bytes)) / p.group_bytes < T + 2)) &&
+      p.tma_store) {
+    p.tma_store = 0;            // not enough shared memory for the store staging tiles: direct stores
+    stage_bytes = 0;
+    smem_cap = smem_cap0;
+    goto retry_sizes;
   }
   PSSR_REQUIRE(G != 0 && b_stages >= 1, PSSR_EUNSUP, "conv: image width %d needs more shared memory than available", d.Wo);
   p.b_bytes = (uint32_t)(G * (int)p.tap_bytes);
@@ -1074,7 +1204,29 @@ int v3_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PSSR_REQUIRE(r == CUDA_SUCCESS, PSSR_ECUDA, "cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
   }
-  op.smem_bytes = (int)(a_total + b_total_ll + 1024 + vec_bytes + tailw_bytes);
+  op.smem_bytes = (int)(a_total + b_total_ll + 1024 + vec_bytes + tailw_bytes + stage_bytes);
+  p.stage_off = (uint32_t)(a_total + b_total_ll + tailw_bytes + vec_bytes);
+  if (p.tma_store) {
+    // output view [pixels][channels]: channel 0 of the view at out + choff, n_valid channels visible, pixel pitch out_cstride
+    uint8_t* obase = reinterpret_cast<uint8_t*>(d.out) + (size_t)d.out_choff * 2;
+    CUresult r;
+    if (p.pad) {
+      cuuint64_t gdim[4] = {(cuuint64_t)d.n_valid, (cuuint64_t)d.Wo, (cuuint64_t)d.Ho, (cuuint64_t)d.B};
+      cuuint64_t gstr[3] = {(cuuint64_t)d.out_cstride * 2, (cuuint64_t)d.out_cstride * 2 * d.Wo, (cuuint64_t)d.out_cstride * 2 * d.Wo * d.Ho};
+      cuuint32_t box[4] = {64, 32, 1, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      r = enc(&op.tmaps[4], tdt, 4, obase, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      cuuint64_t gdim[2] = {(cuuint64_t)d.n_valid, (cuuint64_t)d.Wo * d.Ho * d.B};
+      cuuint64_t gstr[1] = {(cuuint64_t)d.out_cstride * 2};
+      cuuint32_t box[2] = {64, 32};
+      cuuint32_t estr[2] = {1, 1};
+      r = enc(&op.tmaps[4], tdt, 2, obase, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    PSSR_REQUIRE(r == CUDA_SUCCESS, PSSR_ECUDA, "cuTensorMapEncodeTiled(output) failed with %d", (int)r);
+  }
 
   p.bias = d.bias;
   p.out_scale = d.out_scale;
@@ -1130,13 +1282,23 @@ int v3_launch(const ConvOp& op, const void* tmaps_dev, cudaStream_t stream) {
   cfg.blockDim = dim3(kV3Threads, 1, 1);
   cfg.dynamicSmemBytes = (size_t)op.smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)op.cluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (op.cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)op.cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  static const bool pdl = getenv("PSSR_V3_NO_PDL") == nullptr;
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = op.cluster > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   PSSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kV3Variants[op.kernel_index].fn, p));
   count_launch();
   return PSSR_OK;

@@ -5,6 +5,7 @@
 //   tail  : Reconstruction.conv (3x3, hidden -> out channels) + x*128+128, with the fused
 //           clip -> uint8 truncation -> centre channel of `_pred_array`
 //           pssr/models/_blocks.py:17, resunet.py:95, pssr/predict.py:245-246
+#include <stdlib.h>
 #include "common.cuh"
 #include "plan.h"
 
@@ -247,11 +248,87 @@ __global__ void __launch_bounds__(256) tailsum_kernel(pssr_tailsum_desc_t d, int
   }
 }
 
+// Row-coalesced variant (r = 2, 4, 8): a thread owns the r outputs (Y = r*y + si, X = r*x .. r*x + r-1) of one LR pixel and one
+// sub-row; every one of its 9r loads is coalesced along the LR x axis (consecutive threads = consecutive x in one z plane),
+// the r outputs leave as one vector store.  Each z value is read exactly once: HBM traffic = |z| + |out|.
+template <int R>
+__global__ void __launch_bounds__(256) tailsum_rows_kernel(pssr_tailsum_desc_t d) {
+  const int Hh = d.H * R, Wh = d.W * R;
+  const size_t plane = (size_t)d.H * d.W;
+  const long long total = (long long)d.B * d.H * R * d.W;       // (n, y, si, x), x fastest
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % d.W);
+    long long rest = i / d.W;
+    const int si = (int)(rest % R);
+    rest /= R;
+    const int y = (int)(rest % d.H);
+    const int n = (int)(rest / d.H);
+    const float* zb = d.z + (size_t)n * (R * R * 9) * plane;
+    float acc[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) acc[j] = d.bias;
+#pragma unroll
+    for (int ty = -1; ty <= 1; ++ty) {
+      const int sy = si + ty;                                   // source sub-row relative to LR row y
+      const int ys = y + (sy < 0 ? -1 : (sy >= R ? 1 : 0));
+      const int sis = sy < 0 ? sy + R : (sy >= R ? sy - R : sy);
+      if (ys < 0 || ys >= d.H) continue;
+#pragma unroll
+      for (int c = -1; c <= R; ++c) {                           // source HR column relative to R*x
+        const int xs = x + (c < 0 ? -1 : (c >= R ? 1 : 0));
+        const int sjs = c < 0 ? c + R : (c >= R ? c - R : c);
+        if (xs < 0 || xs >= d.W) continue;
+        const float* zp = zb + ((size_t)(sis * R + sjs) * 9 + (size_t)(ty + 1) * 3) * plane + (size_t)ys * d.W + xs;
+#pragma unroll
+        for (int tx = -1; tx <= 1; ++tx) {
+          const int sj = c - tx;                                // the output column this (source, tap) pair belongs to
+          if (sj >= 0 && sj < R) acc[sj] += __ldg(zp + (size_t)(tx + 1) * plane);
+        }
+      }
+    }
+    const size_t o = ((size_t)n * Hh + (size_t)(y * R + si)) * Wh + (size_t)x * R;
+    float yv[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) yv[j] = acc[j] * d.mul + d.add;
+    if (d.out_f32 != nullptr) {
+      if (R % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < R; j += 4) *reinterpret_cast<float4*>(d.out_f32 + o + j) = make_float4(yv[j], yv[j + 1], yv[j + 2], yv[j + 3]);
+      } else {
+        *reinterpret_cast<float2*>(d.out_f32 + o) = make_float2(yv[0], yv[1]);
+      }
+    }
+    if (d.out_u8 != nullptr) {
+      uint8_t b[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) b[j] = (uint8_t)(int)fminf(fmaxf(yv[j], 0.f), 255.f);
+      if (R % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < R; j += 4) *reinterpret_cast<uchar4*>(d.out_u8 + o + j) = make_uchar4(b[j], b[j + 1], b[j + 2], b[j + 3]);
+      } else {
+        *reinterpret_cast<uchar2*>(d.out_u8 + o) = make_uchar2(b[0], b[1]);
+      }
+    }
+  }
+}
+
 int tailsum_launch(const pssr_tailsum_desc_t& d, cudaStream_t stream) {
   PSSR_REQUIRE(d.z != nullptr && d.B >= 1 && d.H >= 1 && d.W >= 1 && d.r >= 1, PSSR_EINVAL, "tailsum: bad arguments");
+  const long long cap = (long long)device_sm_count() * 32;
+  const bool aligned = (d.out_f32 == nullptr || ((uintptr_t)d.out_f32 & 15) == 0) && (d.out_u8 == nullptr || ((uintptr_t)d.out_u8 & 3) == 0);
+  if ((d.r == 2 || d.r == 4 || d.r == 8) && aligned && getenv("PSSR_TAILSUM_V1") == nullptr) {
+    const long long total = (long long)d.B * d.H * d.r * d.W;
+    long long blocks = (total + 255) / 256;
+    if (blocks > cap) blocks = cap;
+    if (d.r == 2) tailsum_rows_kernel<2><<<(int)blocks, 256, 0, stream>>>(d);
+    else if (d.r == 4) tailsum_rows_kernel<4><<<(int)blocks, 256, 0, stream>>>(d);
+    else tailsum_rows_kernel<8><<<(int)blocks, 256, 0, stream>>>(d);
+    count_launch();
+    PSSR_CHECK_CUDA(cudaGetLastError());
+    return PSSR_OK;
+  }
   const long long total = (long long)d.B * d.H * d.r * d.W * d.r;
   long long blocks = (total + 255) / 256;
-  const long long cap = (long long)device_sm_count() * 32;
   if (blocks > cap) blocks = cap;
   int lg = 0;
   while ((1 << lg) < d.r) ++lg;

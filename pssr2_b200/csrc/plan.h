@@ -7,8 +7,10 @@
 
 namespace pssr {
 
+static constexpr int kTmapsPerConv = 5;
+
 struct ConvOp {
-  CUtensorMap tmaps[4];           // host copies; uploaded into the plan's device table
+  CUtensorMap tmaps[5];           // host copies ([0..2] sources, [3] weights, [4] output); uploaded into the plan's device table
   alignas(16) uint8_t kparams[512];
   int grid = 0;
   int smem_bytes = 0;
