@@ -40,6 +40,22 @@ def _peaks():
         return 1590.0, 6650.0, "fallback"
 
 
+def _peak_sustained(burst_tf):
+    """bf16_tflops_sustained of MEASURED_PEAKS.json (cuBLAS back to back for seconds under the power cap); the profiling
+    recipe's stated fallback (1.4 PFLOP/s) when the file is absent."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops_sustained"])
+    except Exception:
+        return 1400.0
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum summed over the conv launches of ONE step, from the ncu capture named below
+# (None until a capture of the current kernels is committed)
+CONV_DRAM_BYTES_PER_STEP = None
+CONV_DRAM_SOURCE = None
+
+
 def _synthetic_tiles(n, seed, device):
     """Microscopy-like uint16 tiles in a 0..255 range: smooth structure + shot noise."""
     import torch
@@ -201,11 +217,15 @@ def run_ours(args):
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if args.kernels_only:
+        torch.cuda.profiler.start()     # ncu --profile-from-start off: the launch list holds exactly the timed steps
     e0.record()
     for i in range(args.steps):
         step(100 + i)
     e1.record()
     barrier()
+    if args.kernels_only:
+        torch.cuda.profiler.stop()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     launches = _lib.launch_count() - launches0
     if world > 1:
@@ -275,12 +295,19 @@ def run_ours(args):
     other_ms = sum(t for t, (kind, _) in zip(acc, plan.records) if kind != "conv")
     n_conv = sum(1 for kind, _ in plan.records if kind == "conv")
     peak_tf, peak_hbm, peak_src = _peaks()
+    peak_sus = _peak_sustained(peak_tf)
     conv_flops = (ALG_FLOPS_PER_TILE - TAIL_FLOPS_PER_TILE) * BATCH
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "conv_strip_kernel + conv_igemm_kernel (tcgen05 implicit GEMM, all conv launches of the step)", "achieved": round(achieved, 1), "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4), "traffic": None, "peak_source": peak_src,
-                "launches_per_step": n_conv, "kernel_ms_per_step": round(conv_ms, 3), "other_net_ms_per_step": round(other_ms, 3),
-                "step_frac_of_peak": round(ALG_FLOPS_PER_TILE * BATCH / (ms_step * 1e-3) / 1e12 / peak_tf, 4)}
+    # The conv launches are timed inside the step sequence (tens of milliseconds of back-to-back tensor work under the 1 kW
+    # cap), so the denominator is the SUSTAINED cuBLAS figure of MEASURED_PEAKS.json; the burst figure is reported beside it.
+    roofline = {"bound": "tensor",
+                "kernel": "conv_v3_kernel (tcgen05 cta_group::2 implicit GEMM; the 16x16 / 8x8 levels run conv_igemm_kernel): all conv launches of the step",
+                "achieved": round(achieved, 1), "peak": peak_sus, "unit": "TFLOP/s", "frac": round(achieved / peak_sus, 4),
+                "traffic": CONV_DRAM_BYTES_PER_STEP, "traffic_source": CONV_DRAM_SOURCE,
+                "peak_source": peak_src + " (bf16_tflops_sustained)", "peak_burst": peak_tf, "frac_of_burst": round(achieved / peak_tf, 4),
+                "algorithmic_flops_per_step": conv_flops, "launches_per_step": n_conv, "kernel_ms_per_step": round(conv_ms, 3),
+                "other_net_ms_per_step": round(other_ms, 3),
+                "step_frac_of_peak": round(ALG_FLOPS_PER_TILE * BATCH / (ms_step * 1e-3) / 1e12 / peak_sus, 4)}
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ------------------------
     cpu_mp, cpu_dt, threads = _cpu_reference_steps(2, 1, 2)
