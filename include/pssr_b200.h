@@ -192,12 +192,21 @@ typedef struct {
   /* Fused Reconstruction tail (pssr/models/_blocks.py:15-18): when tail_z != NULL the epilogue does not
    * store the activation (out may be NULL).  Instead, per output pixel and per pixel-shuffle sub-position
    * s = i*r+j it reduces the C' = n/r^2 post-ReLU channels against the 3x3 tail weights in fp32:
-   *     z[b][s*9 + t][y][x] = sum_c tail_weight[t][c] * act(acc[s*C' + c] + bias)        t = 0..8
+   *     z[b][y][s*9 + t][x] = sum_c tail_weight[t][c] * act(acc[s*C' + c] + bias)        t = 0..8
    * (a 1x1 "per-tap" projection; PSSR_OP_TAILSUM then gathers the 9 shifted taps at HR resolution).
    * The r^2*C'-channel HR feature map -- 2 GB per 64-tile batch -- never exists in memory.            */
   const float* tail_weight; /* fp32 [9][C'] (single output channel)                               */
-  float* tail_z;            /* fp32 planar [B][r*r*9][Ho][Wo]                                     */
+  float* tail_z;            /* fp32 [B][Ho][r*r*9][Wo]: plane rows of one LR row are contiguous   */
+  /* tail_layout = PSSR_TAIL_WINDOW48 (r = 4, Wo % 128 == 0 only): the epilogue also pre-sums the projections of the 16
+   * sub-positions of an LR pixel by the HR OUTPUT position they feed.  (s = (i', j'), tap (dy, dx)) feeds the output at
+   * (oi, oj) = (i' - dy, j' - dx) in [-1, 4]^2 relative to the pixel's 4x4 HR block; sources with j' < 2 and j' >= 2 are
+   * summed by different threads and stored separately (two 6 x 4 windows):
+   *     z[b][y][e*24 + (oi+1)*4 + (oj+1-2e)][x],  e = j' / 2        -- 48 floats per LR pixel instead of 144.          */
+  int32_t tail_layout;
+  int32_t reserved2;
 } pssr_conv_desc_t;
+#define PSSR_TAIL_TAPS 0
+#define PSSR_TAIL_WINDOW48 1
 
 typedef struct {
   const void* x;         /* [B][C][H][W] float32 (0..255) or uint8 if x_u8                   */
@@ -230,13 +239,13 @@ typedef struct {
 } pssr_tail_desc_t;
 
 /* Second half of the fused tail: out[b][0][Y][X] = (bias + sum_t zHR[(Y+dy, X+dx)][t]) * mul + add with
- * zHR[(Y,X)][t] = z[b][((Y%r)*r + X%r)*9 + t][Y/r][X/r] and zero outside the HR image
+ * zHR[(Y,X)][t] = z[b][Y/r][((Y%r)*r + X%r)*9 + t][X/r] and zero outside the HR image
  * (= Reconstruction.conv's zero padding), plus the fused `_pred_array` uint8 output.               */
 typedef struct {
-  const float* z;        /* [B][r*r*9][H][W]                                                  */
+  const float* z;        /* [B][H][r*r*9][W], or [B][H][48][W] with layout PSSR_TAIL_WINDOW48  */
   int32_t B, H, W, r;    /* LR geometry and pixel-shuffle factor; output is [B][1][H*r][W*r]  */
   float bias, mul, add;
-  int32_t reserved;
+  int32_t layout;        /* PSSR_TAIL_TAPS / PSSR_TAIL_WINDOW48 (must match the producing conv) */
   float* out_f32;        /* [B][1][H*r][W*r] or NULL                                          */
   uint8_t* out_u8;       /* [B][H*r][W*r] or NULL                                             */
 } pssr_tailsum_desc_t;

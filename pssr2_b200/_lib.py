@@ -89,7 +89,8 @@ class ConvDesc(Structure):
                 ("weights", c_void_p), ("bias", c_void_p), ("n", c_int32), ("n_valid", c_int32),
                 ("Ho", c_int32), ("Wo", c_int32), ("B", c_int32), ("out", c_void_p),
                 ("out_cstride", c_int32), ("out_choff", c_int32), ("shuffle", c_int32), ("act", c_int32),
-                ("out_scale", c_void_p), ("out_f32", c_void_p), ("tail_weight", c_void_p), ("tail_z", c_void_p)]
+                ("out_scale", c_void_p), ("out_f32", c_void_p), ("tail_weight", c_void_p), ("tail_z", c_void_p),
+                ("tail_layout", c_int32), ("reserved2", c_int32)]
 
 
 class PrepDesc(Structure):
@@ -112,7 +113,7 @@ class TailDesc(Structure):
 
 class TailSumDesc(Structure):
     _fields_ = [("z", c_void_p), ("B", c_int32), ("H", c_int32), ("W", c_int32), ("r", c_int32), ("bias", c_float),
-                ("mul", c_float), ("add", c_float), ("reserved", c_int32), ("out_f32", c_void_p), ("out_u8", c_void_p)]
+                ("mul", c_float), ("add", c_float), ("layout", c_int32), ("out_f32", c_void_p), ("out_u8", c_void_p)]
 
 
 class StemDesc(Structure):

@@ -59,7 +59,7 @@ struct StripKParams {
   int out_cstride, out_choff, shuffle, cps, act, fp16;
   int Hout, Wout;
   const float* tail_w;        // fused Reconstruction tail: fp32 [9][cps] or nullptr
-  float* tail_z;              // fp32 planar [B][r*r*9][H][W]
+  float* tail_z;              // fp32 [B][H][r*r*9][W]
 };
 
 // developer timeline (PSSR_DBG bit 16): per CTA 128 clock64 stamps -- [0] entry, [1] setup done, [2+2u] unit u first MMA issued,
@@ -363,10 +363,9 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_strip_kernel(const __grid_c
               }
               if (ccb + 32 == p.cps) {
                 const int planes = r * r * 9;
-                float* zp = p.tail_z + (((size_t)n * planes + (size_t)sub_t * 9) * p.H + y) * p.W + x;
-                const size_t plane = (size_t)p.H * p.W;
+                float* zp = p.tail_z + (((size_t)n * p.H + y) * planes + (size_t)sub_t * 9) * p.W + x;
 #pragma unroll
-                for (int t = 0; t < 9; ++t) zp[(size_t)t * plane] = zacc[t];
+                for (int t = 0; t < 9; ++t) zp[(size_t)t * p.W] = zacc[t];
               }
             }
           } else {
@@ -628,6 +627,7 @@ int strip_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
   p.out_f32 = d.out_f32;
   p.tail_w = d.tail_weight;
   p.tail_z = d.tail_z;
+  PSSR_REQUIRE(d.tail_z == nullptr || d.tail_layout == PSSR_TAIL_TAPS, PSSR_EUNSUP, "conv: this kernel only writes the per-tap tail layout");
   p.out_cstride = d.out_cstride;
   p.out_choff = d.out_choff;
   p.shuffle = d.shuffle;

@@ -61,7 +61,8 @@ struct V3Params {
   int tma_store;              // 1: the epilogue stages 16-bit tiles in shared memory and writes them with TMA (tmaps[4])
   uint32_t stage_off;         // byte offset of the 8 x 4 KB store staging tiles inside the aligned dynamic shared memory
   const float* tail_w;        // fused Reconstruction tail: fp32 [9][64]
-  float* tail_z;              // fp32 planar [B][r*r*9][H][W]
+  float* tail_z;              // fp32 [B][H][r*r*9][W]: the r*r*9 plane rows of one LR row are contiguous
+  int tail_win48;             // PSSR_TAIL_WINDOW48: [B][H][48][W], the projections pre-summed by HR output position (r = 4, rows mode)
 };
 
 // developer timeline (PSSR_DBG bit 16): per CTA 256 clock64 stamps -- [0] entry, [1] setup done, [2+2u] unit u: accumulator buffer
@@ -218,6 +219,18 @@ __device__ __forceinline__ uint32_t v3_pack2(float lo, float hi, int fp16, bool 
     else asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   }
   return d;
+}
+
+// PSSR_TAIL_WINDOW48: add the nine projections of source sub-position (i' = I, j' = 2*eg + SL) to the 6 x 4 window of HR output
+// positions this epilogue group owns: tap (dy, dx) feeds (oi, oj) = (I - dy, j' - dx); window row = oi + 1, column = oj + 1 - 2*eg
+// = SL - dx + 1.  All indices are compile-time constants: the window lives in registers.
+template <int I, int SL>
+__device__ __forceinline__ void v3_tail_window_add(float (&win)[24], const uint32_t (&zv)[16]) {
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int dy = t / 3 - 1, dx = t % 3 - 1;
+    win[(I - dy + 1) * 4 + (SL - dx + 1)] += __uint_as_float(zv[t]);
+  }
 }
 
 // T tiles per CTA and unit, G filter taps per weight stage (3x3 segments), RES: the whole layer's weights stay in shared memory,
@@ -680,6 +693,9 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
     const int steps = ROWS ? msteps * p.n_tiles : 0;
     asm volatile("griddepcontrol.wait;" ::: "memory");
     int it = 0;
+    float win[24];                  // TAIL + window layout: this thread's pixel, persistent over the four N tiles of a row group
+#pragma unroll
+    for (int k = 0; k < 24; ++k) win[k] = 0.f;
     for (int unit = worker; ROWS ? it < steps : unit < p.total_units; unit += workers, ++it) {
       const int n_tile = ROWS ? it % p.n_tiles : unit % p.n_tiles;
       const int um = ROWS ? 0 : (unit / p.n_tiles) * C + (int)rank;     // flat: this CTA's group of T tiles
@@ -743,7 +759,27 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
         mbar_wait(z_full(buf), par);
         tc_fence_after();
         const int planes = r * r * 9;
-        const size_t plane = (size_t)p.H * p.W;
+        if (ROWS && p.tail_win48) {
+          uint32_t zv0[16], zv1[16];
+          v3_tmem_ld16(region + 64u, zv0);
+          v3_tmem_ld16(region + 64u + 16u, zv1);
+          tmem_ld_wait();
+          switch (n_tile) {
+            case 0: v3_tail_window_add<0, 0>(win, zv0); v3_tail_window_add<0, 1>(win, zv1); break;
+            case 1: v3_tail_window_add<1, 0>(win, zv0); v3_tail_window_add<1, 1>(win, zv1); break;
+            case 2: v3_tail_window_add<2, 0>(win, zv0); v3_tail_window_add<2, 1>(win, zv1); break;
+            default: v3_tail_window_add<3, 0>(win, zv0); v3_tail_window_add<3, 1>(win, zv1); break;
+          }
+          if (n_tile == 3) {
+            if (valid && !(p.dbg & 1)) {
+              float* zp = p.tail_z + (((size_t)n * p.H + y) * 48 + (size_t)(eg * 24)) * p.W + x;
+#pragma unroll
+              for (int k = 0; k < 24; ++k) zp[(size_t)k * p.W] = win[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 24; ++k) win[k] = 0.f;
+          }
+        } else
 #pragma unroll
         for (int sl = 0; sl < 2; ++sl) {
           uint32_t zv[16];
@@ -751,9 +787,9 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
           tmem_ld_wait();
           if (valid && !(p.dbg & 1)) {
             const int sub = n_tile * 4 + eg * 2 + sl;
-            float* zp = p.tail_z + (((size_t)n * planes + (size_t)sub * 9) * p.H + y) * p.W + x;
+            float* zp = p.tail_z + (((size_t)n * p.H + y) * planes + (size_t)sub * 9) * p.W + x;
 #pragma unroll
-            for (int t = 0; t < 9; ++t) zp[(size_t)t * plane] = __uint_as_float(zv[t]);
+            for (int t = 0; t < 9; ++t) zp[(size_t)t * p.W] = __uint_as_float(zv[t]);
           }
         }
       } else {
@@ -1234,6 +1270,9 @@ retry_sizes:
   p.out_f32 = d.out_f32;
   p.tail_w = d.tail_weight;
   p.tail_z = d.tail_z;
+  p.tail_win48 = (tail && d.tail_layout == PSSR_TAIL_WINDOW48) ? 1 : 0;
+  PSSR_REQUIRE(!p.tail_win48 || (p.rows_mode && d.shuffle == 4 && p.n_tiles == 4), PSSR_EUNSUP,
+               "conv: PSSR_TAIL_WINDOW48 needs scale 4, 64 channels per sub-position and Wo %% 128 == 0");
   p.out_cstride = d.out_cstride;
   p.out_choff = d.out_choff;
   p.shuffle = d.shuffle;

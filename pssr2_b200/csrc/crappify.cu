@@ -14,6 +14,7 @@
 // uint16 uses Pillow's sequential double accumulation (explicit __dmul_rn/__dadd_rn: an FMA would
 // change the bits).
 #include <math.h>
+#include <stdlib.h>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -125,24 +126,53 @@ __device__ __forceinline__ double u01d(uint32_t hi, uint32_t lo) {
 
 // Poisson(lam): Knuth's product method below 10, Hoermann's PTRS above (the pair NumPy's legacy
 // generator uses; the stream of uniforms differs, so free-running mode is validated statistically).
-__device__ double poisson_sample(const Philox& ph, uint32_t pix, uint32_t stage, double lam) {
-  if (!(lam > 0.0)) return 0.0;
+// lam < 1024 (every 8-bit pipeline value) runs in float32 -- the sampler's arithmetic is ours to choose, only its
+// distribution is specified, and B200's fp64 transcendental path (log, lgamma) made the fp64 version 90 % of the kernel;
+// the squeeze inequality is evaluated with ~1e-4 absolute error on terms of O(1e3), i.e. it changes the acceptance of a
+// vanishing fraction of borderline draws.  One Philox block feeds two PTRS attempts.
+__device__ float poisson_sample_f32(const Philox& ph, uint32_t pix, uint32_t stage, float lam) {
   uint32_t draw = 0;
-  if (lam < 10.0) {
-    const double enlam = exp(-lam);
-    double prod = 1.0;
+  if (lam < 10.0f) {
+    const float enlam = expf(-lam);
+    float prod = 1.0f;
     int k = 0;
     while (true) {
       const uint4 r = ph(pix, stage, draw++, 0x504F4953u);
       const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        prod *= (double)u01f(w[j]);
-        if (prod <= enlam) return (double)k;
+        prod *= u01f(w[j]);
+        if (prod <= enlam) return (float)k;
         ++k;
       }
     }
   }
+  const float slam = sqrtf(lam), loglam = logf(lam);
+  const float b = 0.931f + 2.53f * slam;
+  const float a = -0.059f + 0.02483f * b;
+  const float invalpha = 1.1239f + 1.1328f / (b - 3.4f);
+  const float vr = 0.9277f - 3.6224f / (b - 2.0f);
+  const float log_invalpha = logf(invalpha);
+  while (true) {
+    const uint4 r = ph(pix, stage, draw++, 0x50545253u);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float U = u01f(w[2 * j]) - 0.5f;
+      const float V = u01f(w[2 * j + 1]);
+      const float us = 0.5f - fabsf(U);
+      const float k = floorf((2.0f * a / us + b) * U + lam + 0.43f);
+      if (us >= 0.07f && V <= vr) return k;
+      if (k < 0.0f || (us < 0.013f && V > us)) continue;
+      if ((logf(V) + log_invalpha - logf(a / (us * us) + b)) <= (-lam + k * loglam - lgammaf(k + 1.0f))) return k;
+    }
+  }
+}
+
+__device__ double poisson_sample(const Philox& ph, uint32_t pix, uint32_t stage, double lam) {
+  if (!(lam > 0.0)) return 0.0;
+  if (lam < 1024.0) return (double)poisson_sample_f32(ph, pix, stage, (float)lam);
+  uint32_t draw = 0;
   const double slam = sqrt(lam), loglam = log(lam);
   const double b = 0.931 + 2.53 * slam;
   const double a = -0.059 + 0.02483 * b;
@@ -234,6 +264,10 @@ struct CrapK {
   uint32_t seed_lo, seed_hi;
   unsigned long long tile_index0;
   float* lr_out;
+  // HR tiles emitted from the staged window (fused path: hr_res % scale == 0 and the HR frame window inside the LR one)
+  float* hr_out;
+  uint8_t* hr_u8;
+  int hr_frame0, hr_frames, scale;
 };
 
 template <typename T>
@@ -297,6 +331,47 @@ __global__ void __launch_bounds__(kCrapThreads) crappify_kernel(const CrapK p) {
     for (int r = threadIdx.x; r < nrows; r += kCrapThreads) lead[r] = 0;
   }
   __syncthreads();
+
+  // ---- stage 1b: the HR tile itself (dataset HR output, data.py:495; `_pred_array` view, predict.py:245-246), from the
+  // staged window: this CTA owns HR rows [yy0*s, yy1*s) x cols [xx0*s, xx1*s) -- no second pass over the sheet ----------
+  if (p.hr_out != nullptr || p.hr_u8 != nullptr) {
+    const int hf = f - p.hr_frame0;
+    const bool want_f32 = p.hr_out != nullptr && hf >= 0 && hf < p.hr_frames;
+    const bool want_u8 = p.hr_u8 != nullptr && hf == p.hr_frames / 2;      // _slice_center(x, 1) keeps index shape//2
+    if (want_f32 || want_u8) {
+      const int s = p.scale;
+      const int X0 = xx0 * s, Y0 = yy0 * s, wown = (xx1 - xx0) * s, hown = (yy1 - yy0) * s;
+      const int groups = (wown + 3) >> 2;
+      const size_t n_hr = (size_t)p.hr_res * p.hr_res;
+      const bool vec_st = (p.hr_res & 3) == 0 && (X0 & 3) == 0;
+      for (int i = threadIdx.x; i < hown * groups; i += kCrapThreads) {
+        const int ry = i / groups, g = i - ry * groups;
+        const int Y = Y0 + ry, X = X0 + 4 * g;
+        const int r = Y - row0;
+        const T* src = reinterpret_cast<const T*>(raw + (size_t)r * p.raw_pitch + lead[r]) + (X - col0);
+        const int cnt = min(4, wown - 4 * g);
+        int v[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < cnt) v[j] = (int)src[j];
+        const size_t o = (size_t)Y * p.hr_res + X;
+        if (want_u8) {
+          uint8_t* d = p.hr_u8 + (size_t)tile * n_hr + o;
+          if (vec_st && cnt == 4)
+            *reinterpret_cast<uint32_t*>(d) = (uint32_t)min(v[0], 255) | ((uint32_t)min(v[1], 255) << 8) | ((uint32_t)min(v[2], 255) << 16) |
+                                              ((uint32_t)min(v[3], 255) << 24);
+          else
+            for (int j = 0; j < cnt; ++j) d[j] = (uint8_t)min(v[j], 255);
+        }
+        if (want_f32) {
+          float* d = p.hr_out + ((size_t)tile * p.hr_frames + hf) * n_hr + o;
+          if (vec_st && cnt == 4) *reinterpret_cast<float4*>(d) = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+          else
+            for (int j = 0; j < cnt; ++j) d[j] = (float)v[j];
+        }
+      }
+    }
+  }
 
   // ---- stage 2: horizontal pass, rounded to the image dtype ------------------------------
   const int nx = xx1 - xx0, ny = yy1 - yy0;
@@ -450,6 +525,15 @@ extern "C" int pssr_crappify(const pssr_crappify_args_t* a, void* stream) {
   const int lr_res = a->hr_res / a->lr_scale;
   PSSR_REQUIRE(lr_res >= 1, PSSR_EINVAL, "crappify: lr_scale larger than hr_res");
 
+  const bool want_hr = a->hr_out != nullptr || a->hr_u8_out != nullptr;
+  if (want_hr)
+    PSSR_REQUIRE(a->hr_frames >= 1 && a->hr_frame0 >= 0 && a->hr_frame0 + a->hr_frames <= a->frames, PSSR_EINVAL,
+                 "crappify: HR frame window outside the tile");
+  // the crappify CTAs emit the HR tile from their staged window when every wanted HR frame is one of the LR frames and the
+  // HR grid is an integer multiple of the LR grid; otherwise a separate gather pass runs
+  const bool hr_fused = want_hr && a->lr_out != nullptr && a->hr_res % a->lr_scale == 0 && a->hr_frame0 >= a->lr_frame0 &&
+                        a->hr_frame0 + a->hr_frames <= a->lr_frame0 + a->lr_frames && getenv("PSSR_NO_HR_FUSE") == nullptr &&
+                        ((uintptr_t)a->hr_out & 15) == 0 && ((uintptr_t)a->hr_u8_out & 3) == 0;
   if (a->lr_out != nullptr) {
     const ResampleTable* tab = nullptr;
     int rc = get_table(a->hr_res, lr_res, &tab);
@@ -492,6 +576,8 @@ extern "C" int pssr_crappify(const pssr_crappify_args_t* a, void* stream) {
     p.seed_lo = (uint32_t)a->seed; p.seed_hi = (uint32_t)(a->seed >> 32);
     p.tile_index0 = a->tile_index0;
     p.lr_out = a->lr_out;
+    p.scale = a->lr_scale;
+    if (hr_fused) { p.hr_out = a->hr_out; p.hr_u8 = a->hr_u8_out; p.hr_frame0 = a->hr_frame0; p.hr_frames = a->hr_frames; }
     const size_t smem = (size_t)p.max_rows * p.raw_pitch + (size_t)p.max_rows * TL * a->elem_bytes + (size_t)p.max_rows * 4 + 32;
     PSSR_REQUIRE(smem <= 200 * 1024, PSSR_EUNSUP, "crappify: staging needs %zu bytes of shared memory (scale %d too large)", smem, a->lr_scale);
     const long long blocks = (long long)a->n_tiles * a->lr_frames * p.tiles_per_side * p.tiles_per_side;
@@ -508,9 +594,7 @@ extern "C" int pssr_crappify(const pssr_crappify_args_t* a, void* stream) {
     count_launch();
     PSSR_CHECK_CUDA(cudaGetLastError());
   }
-  if (a->hr_out != nullptr || a->hr_u8_out != nullptr) {
-    PSSR_REQUIRE(a->hr_frames >= 1 && a->hr_frame0 >= 0 && a->hr_frame0 + a->hr_frames <= a->frames, PSSR_EINVAL,
-                 "crappify: HR frame window outside the tile");
+  if (want_hr && !hr_fused) {
     dim3 grid(64, a->hr_frames, a->n_tiles);
     if (a->elem_bytes == 1)
       hr_gather_kernel<uint8_t><<<grid, 256, 0, st>>>(a->sheets, a->tile_sheet, a->tile_frame, a->tile_y, a->tile_x, a->tile_vh,

@@ -25,75 +25,139 @@ __device__ __forceinline__ long long warp_sum(long long v) {
 }
 
 // -------------------------------------------------------------------------- SSIM + SSE
-static constexpr int kSsimT = 32;            // centres per CTA edge
-static constexpr int kSsimW = kSsimT + 6;    // staged pixels per edge
+// Row-streaming design.  A CTA of 128 threads owns a strip of 512 input columns (4 per thread, one 32-bit load per image and
+// row) and a chunk of output rows.  Per input row every thread updates the VERTICAL 7-row running sums of a, b, a^2, b^2, ab
+// of its four columns (add the new row, subtract the row seven above: 8 integer instructions per column), publishes them
+// to shared memory (double-buffered, one barrier per row), slides the HORIZONTAL 7-window over its own four columns and the
+// six to the right, and evaluates the SSIM expression for four window positions.  Every input byte is read from HBM once
+// (the row seven above comes from L1/L2), all window sums are exact integers:
+//   S = (2 s0 s1 + c1)(2 (49 s4 - s0 s1) + c2) / ((s0^2 + s1^2 + c1)(49 (s2 + s3) - s0^2 - s1^2 + c2))
+// with s0..s4 the 49-pixel sums of a, b, a^2, b^2, ab, c1 = 49^2 C1, c2 = 49*48 C2 (skimage structural_similarity with
+// sample covariance: the 1/49^2 and 1/(49*48) factors cancel) -- two int->double conversions per factor pair and ONE
+// double division per window position instead of six.
+static constexpr int kMetThreads = 128;
+static constexpr int kMetCols = kMetThreads * 4;     // input columns per strip
+static constexpr int kMetStep = kMetCols - 8;        // output columns a strip owns (multiple of 4; the last strip takes up to +2 more)
 
-__global__ void __launch_bounds__(256) metric_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int h, int w,
-                                                     int tiles_x, int tiles_y, long long* __restrict__ sse_part,
-                                                     double* __restrict__ ssim_part) {
-  __shared__ uint8_t sa[kSsimW][kSsimW + 2], sb[kSsimW][kSsimW + 2];
-  __shared__ int hs[5][kSsimW][kSsimT + 1];  // horizontal 7-sums of a, b, a^2, b^2, ab
-  __shared__ double red_d[8];
-  __shared__ long long red_l[8];
-  const int img = blockIdx.y;
-  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
-  const int x0 = tx * kSsimT, y0 = ty * kSsimT;  // top-left of the staged window (= centre - 3)
+struct MetGeom { int strips, chunks, rows_per_chunk; };
+static MetGeom metric_geom(int n, int h, int w) {
+  MetGeom g;
+  const int ow = w - 6 > 0 ? w - 6 : 1, oh = h - 6 > 0 ? h - 6 : 1;
+  g.strips = ow <= kMetStep + 2 ? 1 : (ow - 2 + kMetStep - 1) / kMetStep;
+  // enough CTAs for ~10 per SM, at least 8 output rows per chunk (6 halo rows are re-read per chunk)
+  long long want = (148LL * 10 + (long long)n * g.strips - 1) / ((long long)n * g.strips);
+  if (want < 1) want = 1;
+  int max_chunks = (oh + 7) / 8;
+  if (max_chunks < 1) max_chunks = 1;
+  g.chunks = (int)(want < max_chunks ? want : max_chunks);
+  g.rows_per_chunk = (oh + g.chunks - 1) / g.chunks;
+  g.chunks = (oh + g.rows_per_chunk - 1) / g.rows_per_chunk;
+  return g;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kMetThreads) metric_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int h, int w,
+                                                             int rows_per_chunk, int want_ssim, long long* __restrict__ sse_part,
+                                                             double* __restrict__ ssim_part) {
+  __shared__ __align__(16) int vs[2][5][kMetCols + 8];
+  __shared__ double red_d[kMetThreads / 32];
+  __shared__ long long red_l[kMetThreads / 32];
+  const int strip = blockIdx.x, chunk = blockIdx.y, img = blockIdx.z;
+  const int strips = gridDim.x, chunks = gridDim.y;
+  const int tid = threadIdx.x;
+  const int ow = w - 6, oh = h - 6;
+  const int x0 = strip * kMetStep + 4 * tid;                // this thread's four input columns / window left edges
+  const int own_x_end = strip + 1 == strips ? w : (strip + 1) * kMetStep;      // SSE ownership of input columns
+  const int out_x_end = strip + 1 == strips ? ow : (strip + 1) * kMetStep;     // window positions this strip scores
+  const int oy0 = chunk * rows_per_chunk;
+  const int oy1 = min(oy0 + rows_per_chunk, oh);
+  const int own_y_end = chunk + 1 == chunks ? h : oy0 + rows_per_chunk;        // SSE ownership of input rows
+  const int y_begin = oy0, y_end = (want_ssim && oh > 0) ? max(oy1 + 6, own_y_end) : own_y_end;
   const uint8_t* pa = a + (size_t)img * h * w;
   const uint8_t* pb = b + (size_t)img * h * w;
+  if (tid < 8) {
+#pragma unroll
+    for (int q = 0; q < 5; ++q) { vs[0][q][kMetCols + tid] = 0; vs[1][q][kMetCols + tid] = 0; }
+  }
+  auto load4 = [&](const uint8_t* p, int y) -> uint32_t {
+    if (VEC) {
+      if (x0 + 3 < w) return __ldg(reinterpret_cast<const uint32_t*>(p + (size_t)y * w + x0));
+    }
+    uint32_t v = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (x0 + j < w) v |= (uint32_t)__ldg(p + (size_t)y * w + x0 + j) << (8 * j);
+    return v;
+  };
+  int V[5][4];
+#pragma unroll
+  for (int q = 0; q < 5; ++q)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) V[q][j] = 0;
   long long sse = 0;
-  for (int i = threadIdx.x; i < kSsimW * kSsimW; i += blockDim.x) {
-    const int r = i / kSsimW, c = i % kSsimW;
-    const int y = y0 + r, x = x0 + c;
-    int va = 0, vb = 0;
-    if (y < h && x < w) {
-      va = pa[(size_t)y * w + x];
-      vb = pb[(size_t)y * w + x];
-      // every pixel belongs to exactly one CTA's top-left kSsimT x kSsimT block for the SSE
-      if (r < kSsimT && c < kSsimT) sse += (long long)((va - vb) * (va - vb));
-    }
-    sa[r][c] = (uint8_t)va;
-    sb[r][c] = (uint8_t)vb;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < kSsimW * kSsimT; i += blockDim.x) {
-    const int r = i / kSsimT, c = i % kSsimT;
-    int s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) {
-      const int va = sa[r][c + k], vb = sb[r][c + k];
-      s0 += va; s1 += vb; s2 += va * va; s3 += vb * vb; s4 += va * vb;
-    }
-    hs[0][r][c] = s0; hs[1][r][c] = s1; hs[2][r][c] = s2; hs[3][r][c] = s3; hs[4][r][c] = s4;
-  }
-  __syncthreads();
   double acc = 0.0;
-  const double C1 = (0.01 * 255.0) * (0.01 * 255.0), C2 = (0.03 * 255.0) * (0.03 * 255.0);
-  const double cov_norm = 49.0 / 48.0;
-  for (int i = threadIdx.x; i < kSsimT * kSsimT; i += blockDim.x) {
-    const int r = i / kSsimT, c = i % kSsimT;
-    // centre (y0+r+3, x0+c+3) must satisfy 3 <= cy <= h-4  <=>  window fully inside the image
-    if (y0 + r + 6 < h && x0 + c + 6 < w) {
-      int s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+  const double c1 = 2401.0 * (0.01 * 255.0) * (0.01 * 255.0), c2 = 2352.0 * (0.03 * 255.0) * (0.03 * 255.0);
+  for (int y = y_begin; y < y_end; ++y) {
+    const uint32_t na = load4(pa, y), nb = load4(pb, y);
+    uint32_t oa = 0, ob = 0;
+    const bool has_old = y - 7 >= y_begin;
+    if (has_old) { oa = load4(pa, y - 7); ob = load4(pb, y - 7); }
+    int sq_row = 0;
 #pragma unroll
-      for (int k = 0; k < 7; ++k) {
-        s0 += hs[0][r + k][c]; s1 += hs[1][r + k][c]; s2 += hs[2][r + k][c]; s3 += hs[3][r + k][c]; s4 += hs[4][r + k][c];
+    for (int j = 0; j < 4; ++j) {
+      const int an = (int)((na >> (8 * j)) & 255u), bn = (int)((nb >> (8 * j)) & 255u);
+      const int ao = (int)((oa >> (8 * j)) & 255u), bo = (int)((ob >> (8 * j)) & 255u);
+      V[0][j] += an - ao;
+      V[1][j] += bn - bo;
+      V[2][j] += an * an - ao * ao;
+      V[3][j] += bn * bn - bo * bo;
+      V[4][j] += an * bn - ao * bo;
+      if (x0 + j < own_x_end) sq_row += (an - bn) * (an - bn);
+    }
+    if (y < own_y_end) sse += sq_row;
+    const int oy = y - 6;                       // window rows [oy, oy+6] are summed in V now
+    if (!want_ssim || oy < oy0 || oy >= oy1) continue;      // uniform across the CTA
+    const int pbuf = y & 1;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) *reinterpret_cast<int4*>(&vs[pbuf][q][4 * tid]) = make_int4(V[q][0], V[q][1], V[q][2], V[q][3]);
+    __syncthreads();
+    int H[5][4];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const int4 r0 = *reinterpret_cast<const int4*>(&vs[pbuf][q][4 * tid + 4]);
+      const int2 r1 = *reinterpret_cast<const int2*>(&vs[pbuf][q][4 * tid + 8]);
+      const int v0 = V[q][0], v1 = V[q][1], v2 = V[q][2], v3 = V[q][3];
+      const int h0 = v0 + v1 + v2 + v3 + r0.x + r0.y + r0.z;
+      const int h1 = h0 - v0 + r0.w;
+      const int h2 = h1 - v1 + r1.x;
+      const int h3 = h2 - v2 + r1.y;
+      H[q][0] = h0; H[q][1] = h1; H[q][2] = h2; H[q][3] = h3;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (x0 + j < out_x_end) {
+        const int s0 = H[0][j], s1 = H[1][j];
+        const int s01 = s0 * s1;
+        const int sq = s0 * s0 + s1 * s1;
+        const int cv = 49 * H[4][j] - s01;
+        const int vr = 49 * (H[2][j] + H[3][j]) - sq;
+        const double A1 = (double)(2 * s01) + c1, A2 = (double)(2 * cv) + c2;
+        const double B1 = (double)sq + c1, B2 = (double)vr + c2;
+        acc += (A1 * A2) / (B1 * B2);
       }
-      const double ux = s0 / 49.0, uy = s1 / 49.0, uxx = s2 / 49.0, uyy = s3 / 49.0, uxy = s4 / 49.0;
-      const double vx = cov_norm * (uxx - ux * ux), vy = cov_norm * (uyy - uy * uy), vxy = cov_norm * (uxy - ux * uy);
-      const double A1 = 2.0 * ux * uy + C1, A2 = 2.0 * vxy + C2, B1 = ux * ux + uy * uy + C1, B2 = vx + vy + C2;
-      acc += (A1 * A2) / (B1 * B2);
     }
   }
   acc = warp_sum(acc);
   sse = warp_sum(sse);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tid >> 5, lane = tid & 31;
   if (lane == 0) { red_d[warp] = acc; red_l[warp] = sse; }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     double d = 0.0; long long l = 0;
-    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { d += red_d[k]; l += red_l[k]; }
-    ssim_part[(size_t)img * gridDim.x + blockIdx.x] = d;
-    sse_part[(size_t)img * gridDim.x + blockIdx.x] = l;
+    for (int k = 0; k < kMetThreads / 32; ++k) { d += red_d[k]; l += red_l[k]; }
+    const size_t part = ((size_t)img * chunks + chunk) * strips + strip;
+    ssim_part[part] = d;
+    sse_part[part] = l;
   }
 }
 
@@ -235,8 +299,9 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const uint8_t* __restri
 using namespace pssr;
 
 extern "C" int64_t pssr_metric_workspace_bytes(int32_t n, int32_t h, int32_t w) {
-  const int64_t parts = (int64_t)((w + kSsimT - 1) / kSsimT) * ((h + kSsimT - 1) / kSsimT);
-  return (int64_t)(n > 0 ? n : 0) * parts * 16;
+  if (n <= 0 || h <= 0 || w <= 0) return 0;
+  const MetGeom g = metric_geom(n, h, w);
+  return (int64_t)n * g.strips * g.chunks * 16;
 }
 
 extern "C" int pssr_metric_sums(const uint8_t* a, const uint8_t* b, int32_t n, int32_t h, int32_t w, int64_t* sq_err,
@@ -245,12 +310,16 @@ extern "C" int pssr_metric_sums(const uint8_t* a, const uint8_t* b, int32_t n, i
   PSSR_REQUIRE(ssim_sum == nullptr || (h >= 7 && w >= 7), PSSR_EINVAL, "win_size exceeds image extent.");
   PSSR_REQUIRE(n <= 65535, PSSR_EUNSUP, "metric_sums: at most 65535 images per call");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int tiles_x = (w + kSsimT - 1) / kSsimT, tiles_y = (h + kSsimT - 1) / kSsimT;
-  const int parts = tiles_x * tiles_y;
+  const MetGeom g = metric_geom(n, h, w);
+  const int parts = g.strips * g.chunks;
+  PSSR_REQUIRE(g.chunks <= 65535, PSSR_EUNSUP, "metric_sums: image too tall");
   PSSR_REQUIRE(workspace != nullptr && ((uintptr_t)workspace & 15) == 0, PSSR_EINVAL, "metric_sums: workspace missing or misaligned");
   long long* sse_part = reinterpret_cast<long long*>(workspace);
   double* ssim_part = reinterpret_cast<double*>(sse_part + (size_t)n * parts);
-  metric_kernel<<<dim3(parts, n), 256, 0, st>>>(a, b, h, w, tiles_x, tiles_y, sse_part, ssim_part);
+  const dim3 grid(g.strips, g.chunks, n);
+  const bool vec = (w % 4 == 0) && (((uintptr_t)a | (uintptr_t)b) & 3) == 0;
+  if (vec) metric_kernel<true><<<grid, kMetThreads, 0, st>>>(a, b, h, w, g.rows_per_chunk, ssim_sum != nullptr, sse_part, ssim_part);
+  else metric_kernel<false><<<grid, kMetThreads, 0, st>>>(a, b, h, w, g.rows_per_chunk, ssim_sum != nullptr, sse_part, ssim_part);
   metric_finish_kernel<<<n, 32, 0, st>>>(sse_part, ssim_part, parts, reinterpret_cast<long long*>(sq_err), ssim_sum);
   count_launch(2);
   PSSR_CHECK_CUDA(cudaGetLastError());

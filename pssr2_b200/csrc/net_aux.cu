@@ -12,39 +12,55 @@
 namespace pssr {
 
 // ------------------------------------------------------------------------------ prep
-// One thread per pixel writes its 64-channel (128 B) im2col row.  Zero padding is applied AFTER
+// One thread per pixel builds its 64-channel (128 B) im2col row in registers; the warp then transposes its 32 rows through
+// shared memory (16-byte chunks XOR-swizzled by pixel: conflict-free both ways) so that every store instruction writes
+// 512 contiguous bytes (four whole pixel rows) instead of 32 scattered 16-byte pieces.  Zero padding is applied AFTER
 // normalisation (reference quirk: BN acts before the conv's padding), so out-of-image taps are 0.
-__global__ void prep_im2col_kernel(pssr_prep_desc_t d, int fp16) {
+static constexpr int kPrepThreads = 128;
+__global__ void __launch_bounds__(kPrepThreads) prep_im2col_kernel(pssr_prep_desc_t d, int fp16) {
+  __shared__ uint4 tr[kPrepThreads / 32][32 * 8];
   const long long total = (long long)d.B * d.H * d.W;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % d.W);
-    const int y = (int)((i / d.W) % d.H);
-    const int n = (int)(i / ((long long)d.W * d.H));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long base = blockIdx.x * (long long)blockDim.x + warp * 32; base < total; base += stride) {   // warp-uniform
+    const long long i = base + lane;
     uint32_t row[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) row[k] = 0u;
-    uint16_t* r16 = reinterpret_cast<uint16_t*>(row);
-    for (int c = 0; c < d.C; ++c) {
-      const float s = d.scale[c], t = d.shift[c];
-      const size_t plane = ((size_t)n * d.C + c) * d.H * (size_t)d.W;
+    if (i < total) {
+      const int x = (int)(i % d.W);
+      const int y = (int)((i / d.W) % d.H);
+      const int n = (int)(i / ((long long)d.W * d.H));
+      uint16_t* r16 = reinterpret_cast<uint16_t*>(row);
+      for (int c = 0; c < d.C; ++c) {
+        const float s = d.scale[c], t = d.shift[c];
+        const size_t plane = ((size_t)n * d.C + c) * d.H * (size_t)d.W;
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-        float v = 0.f;
-        if (yy >= 0 && yy < d.H && xx >= 0 && xx < d.W) {
-          const size_t idx = plane + (size_t)yy * d.W + xx;
-          const float raw = d.x_u8 ? (float)reinterpret_cast<const uint8_t*>(d.x)[idx]
-                                   : reinterpret_cast<const float*>(d.x)[idx];
-          v = __fadd_rn(__fmul_rn(__fsub_rn(__fdiv_rn(raw, 128.f), 1.f), s), t);  // no FMA contraction: same bits as the unfused ops
-          if (tap == 4 && d.xnorm_f32 != nullptr) d.xnorm_f32[idx] = v;
+        for (int tap = 0; tap < 9; ++tap) {
+          const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+          float v = 0.f;
+          if (yy >= 0 && yy < d.H && xx >= 0 && xx < d.W) {
+            const size_t idx = plane + (size_t)yy * d.W + xx;
+            const float raw = d.x_u8 ? (float)reinterpret_cast<const uint8_t*>(d.x)[idx]
+                                     : reinterpret_cast<const float*>(d.x)[idx];
+            v = __fadd_rn(__fmul_rn(__fsub_rn(__fdiv_rn(raw, 128.f), 1.f), s), t);  // no FMA contraction: same bits as the unfused ops
+            if (tap == 4 && d.xnorm_f32 != nullptr) d.xnorm_f32[idx] = v;
+          }
+          r16[c * 9 + tap] = pack1(v, fp16);
         }
-        r16[c * 9 + tap] = pack1(v, fp16);
       }
     }
-    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(d.im2col) + (size_t)i * 64);
+    uint4* my = tr[warp];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) dst[k] = make_uint4(row[4 * k], row[4 * k + 1], row[4 * k + 2], row[4 * k + 3]);
+    for (int k = 0; k < 8; ++k) my[lane * 8 + (k ^ (lane & 7))] = make_uint4(row[4 * k], row[4 * k + 1], row[4 * k + 2], row[4 * k + 3]);
+    __syncwarp();
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(d.im2col) + (size_t)base * 64);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int pix = k * 4 + (lane >> 3), chunk = lane & 7;
+      if (base + pix < total) dst[pix * 8 + chunk] = my[pix * 8 + (chunk ^ (pix & 7))];
+    }
+    __syncwarp();
   }
 }
 
@@ -52,7 +68,7 @@ int prep_launch(const pssr_prep_desc_t& d, int dtype, cudaStream_t stream) {
   PSSR_REQUIRE(d.C >= 1 && d.C * 9 <= 64, PSSR_EUNSUP, "prep: %d input channels unsupported (9*C must be <= 64)", d.C);
   PSSR_REQUIRE(d.x && d.im2col && d.scale && d.shift, PSSR_EINVAL, "prep: null pointer");
   const long long total = (long long)d.B * d.H * d.W;
-  const int threads = 128;
+  const int threads = kPrepThreads;
   long long blocks = (total + threads - 1) / threads;
   const long long cap = (long long)device_sm_count() * 32;
   if (blocks > cap) blocks = cap;
@@ -218,7 +234,7 @@ int tail_launch(const pssr_tail_desc_t& d, int dtype, cudaStream_t stream) {
 
 // --------------------------------------------------------------------------- tailsum
 // Second half of the fused Reconstruction tail: gather the nine per-tap projections the conv epilogue
-// left at LR resolution (planar z[b][s*9+t][y][x]) at their shifted HR positions, add the bias, apply
+// left at LR resolution (z[b][y][s*9+t][x]: the r*r*9 plane rows of one LR row are contiguous, 74 KB at r = 4, W = 128) at their shifted HR positions, add the bias, apply
 // x*128+128 (resunet.py:95) and emit fp32 + `_pred_array` uint8.  Pure streaming: ~r^2*9*4 B read and 5 B
 // written per LR pixel.
 template <bool POW2>
@@ -239,7 +255,7 @@ __global__ void __launch_bounds__(256) tailsum_kernel(pssr_tailsum_desc_t d, int
       if (Yt >= 0 && Yt < Hh && Xt >= 0 && Xt < Wh) {
         const int y = POW2 ? (Yt >> lg) : Yt / d.r, x = POW2 ? (Xt >> lg) : Xt / d.r;
         const int s = (Yt - y * d.r) * d.r + (Xt - x * d.r);
-        acc += __ldg(zb + (size_t)(s * 9 + t) * plane + (size_t)y * d.W + x);
+        acc += __ldg(zb + ((size_t)y * planes + (size_t)(s * 9 + t)) * d.W + x);       // z[b][y][s*9+t][x]
       }
     }
     const float yv = acc * d.mul + d.add;
@@ -278,11 +294,11 @@ __global__ void __launch_bounds__(256) tailsum_rows_kernel(pssr_tailsum_desc_t d
         const int xs = x + (c < 0 ? -1 : (c >= R ? 1 : 0));
         const int sjs = c < 0 ? c + R : (c >= R ? c - R : c);
         if (xs < 0 || xs >= d.W) continue;
-        const float* zp = zb + ((size_t)(sis * R + sjs) * 9 + (size_t)(ty + 1) * 3) * plane + (size_t)ys * d.W + xs;
+        const float* zp = zb + ((size_t)ys * (R * R * 9) + (size_t)(sis * R + sjs) * 9 + (size_t)(ty + 1) * 3) * d.W + xs;
 #pragma unroll
         for (int tx = -1; tx <= 1; ++tx) {
           const int sj = c - tx;                                // the output column this (source, tap) pair belongs to
-          if (sj >= 0 && sj < R) acc[sj] += __ldg(zp + (size_t)(tx + 1) * plane);
+          if (sj >= 0 && sj < R) acc[sj] += __ldg(zp + (size_t)(tx + 1) * d.W);
         }
       }
     }
@@ -312,10 +328,64 @@ __global__ void __launch_bounds__(256) tailsum_rows_kernel(pssr_tailsum_desc_t d
   }
 }
 
+// PSSR_TAIL_WINDOW48 (r = 4): z[b][y][e*24 + oi*4 + ojl][x] holds, per LR pixel, the sums of its own projections by HR output
+// position: window row oi = 0..5 is HR row 4y + oi - 1, window column ojg = ojl + 2e = 0..5 is HR column 4x + ojg - 1.  A
+// thread owns the 4 outputs (4y + si, 4x .. 4x+3): from its own pixel the window row si + 1 (columns 1..4: e = 0 holds
+// 0..3, e = 1 holds 2..5), from the pixel left / right the columns 5 / 0, and for si = 0 / 3 the rows 5 / 0 of the pixel
+// above / below -- 8 or 16 coalesced loads per thread instead of 36, every z value read exactly once.
+__global__ void __launch_bounds__(256) tailsum_win48_kernel(pssr_tailsum_desc_t d) {
+  const int Hh = d.H * 4, Wh = d.W * 4;
+  const long long total = (long long)d.B * d.H * 4 * d.W;       // (n, y, si, x), x fastest
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % d.W);
+    long long rest = i / d.W;
+    const int si = (int)(rest & 3);
+    rest >>= 2;
+    const int y = (int)(rest % d.H);
+    const int n = (int)(rest / d.H);
+    float a0 = d.bias, a1 = d.bias, a2 = d.bias, a3 = d.bias;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      // k = 0: own LR row, window row si + 1;  k = 1: the neighbouring LR row whose window reaches this HR row
+      int ys = y, oi = si + 1;
+      if (k == 1) {
+        if (si == 0) { ys = y - 1; oi = 5; }
+        else if (si == 3) { ys = y + 1; oi = 0; }
+        else continue;
+        if (ys < 0 || ys >= d.H) continue;
+      }
+      const float* zr = d.z + (((size_t)n * d.H + ys) * 48 + (size_t)oi * 4) * d.W + x;     // e = 0, ojl = 0
+      const size_t e1 = (size_t)24 * d.W;
+      a0 += __ldg(zr + 1 * d.W);
+      a1 += __ldg(zr + 2 * d.W) + __ldg(zr + e1);
+      a2 += __ldg(zr + 3 * d.W) + __ldg(zr + e1 + d.W);
+      a3 += __ldg(zr + e1 + 2 * d.W);
+      if (x > 0) a0 += __ldg(zr + e1 + 3 * d.W - 1);          // left pixel, window column 5
+      if (x + 1 < d.W) a3 += __ldg(zr + 1);                  // right pixel, window column 0
+    }
+    const size_t o = ((size_t)n * Hh + (size_t)(y * 4 + si)) * Wh + (size_t)x * 4;
+    const float y0 = a0 * d.mul + d.add, y1 = a1 * d.mul + d.add, y2 = a2 * d.mul + d.add, y3 = a3 * d.mul + d.add;
+    if (d.out_f32 != nullptr) *reinterpret_cast<float4*>(d.out_f32 + o) = make_float4(y0, y1, y2, y3);
+    if (d.out_u8 != nullptr)
+      *reinterpret_cast<uchar4*>(d.out_u8 + o) = make_uchar4((uint8_t)(int)fminf(fmaxf(y0, 0.f), 255.f), (uint8_t)(int)fminf(fmaxf(y1, 0.f), 255.f),
+                                                             (uint8_t)(int)fminf(fmaxf(y2, 0.f), 255.f), (uint8_t)(int)fminf(fmaxf(y3, 0.f), 255.f));
+  }
+}
+
 int tailsum_launch(const pssr_tailsum_desc_t& d, cudaStream_t stream) {
   PSSR_REQUIRE(d.z != nullptr && d.B >= 1 && d.H >= 1 && d.W >= 1 && d.r >= 1, PSSR_EINVAL, "tailsum: bad arguments");
   const long long cap = (long long)device_sm_count() * 32;
   const bool aligned = (d.out_f32 == nullptr || ((uintptr_t)d.out_f32 & 15) == 0) && (d.out_u8 == nullptr || ((uintptr_t)d.out_u8 & 3) == 0);
+  if (d.layout == PSSR_TAIL_WINDOW48) {
+    PSSR_REQUIRE(d.r == 4 && aligned, PSSR_EUNSUP, "tailsum: the window layout needs r = 4 and aligned outputs");
+    const long long total = (long long)d.B * d.H * 4 * d.W;
+    long long blocks = (total + 255) / 256;
+    if (blocks > cap) blocks = cap;
+    tailsum_win48_kernel<<<(int)blocks, 256, 0, stream>>>(d);
+    count_launch();
+    PSSR_CHECK_CUDA(cudaGetLastError());
+    return PSSR_OK;
+  }
   if ((d.r == 2 || d.r == 4 || d.r == 8) && aligned && getenv("PSSR_TAILSUM_V1") == nullptr) {
     const long long total = (long long)d.B * d.H * d.r * d.W;
     long long blocks = (total + 255) / 256;

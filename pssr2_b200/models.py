@@ -158,10 +158,15 @@ class _PlanModule(nn.Module):
             # fused tail: relu(pre) is reduced against the 3x3 tail weights inside the conv epilogue (fp32), the
             # scale^2*hidden-channel HR map is never written; PSSR_OP_TAILSUM gathers the 9 taps (see include/pssr_b200.h)
             tw = wc[0].permute(1, 2, 0).reshape(9, hid0).contiguous()      # [tap][c]
-            zbuf = torch.zeros(B, s * s * 9, H, W, dtype=torch.float32, device=dev)
+            # scale 4 on row-mode geometry (W % 128 == 0): the epilogue pre-sums the 144 projections of an LR pixel into the
+            # 2 x 24 HR output positions they feed (PSSR_TAIL_WINDOW48), 3x less z traffic
+            import os
+            win48 = 1 if (s == 4 and hid0 == 64 and W % 128 == 0 and not any(os.environ.get(k) for k in (
+                "PSSR_TAIL_TAPS", "PSSR_V3_FLAT", "PSSR_CONV_V1", "PSSR_CONV_V2"))) else 0
+            zbuf = torch.zeros(B, H, 48 if win48 else s * s * 9, W, dtype=torch.float32, device=dev)
             plan.conv(srcs, segs, wpk, permute_n(bp, s).contiguous(), None, Ho=H, Wo=W, B=B, shuffle=s, act=ACT_RELU,
-                      tail_weight=tw, tail_z=zbuf)
-            plan.tailsum(zbuf, s, float(bc[0]), 128.0, 128.0, out, out_u8)    # x*128+128 (resunet.py:95)
+                      tail_weight=tw, tail_z=zbuf, tail_layout=win48)
+            plan.tailsum(zbuf, s, float(bc[0]), 128.0, 128.0, out, out_u8, layout=win48)    # x*128+128 (resunet.py:95)
         else:
             ps_out = z(B, H * s, W * s, hid0)
             plan.conv(srcs, segs, wpk, permute_n(bp, s).contiguous(), View(ps_out), Ho=H, Wo=W, B=B, shuffle=s, act=ACT_RELU)

@@ -101,7 +101,7 @@ class Plan:
 
     # ---- op builders -----------------------------------------------------------------
     def conv(self, srcs, segs, weight, bias, out: View, *, Ho, Wo, B, n=None, n_valid=None, shuffle=1, act=ACT_NONE,
-             out_scale=None, out_f32=None, tail_weight=None, tail_z=None):
+             out_scale=None, out_f32=None, tail_weight=None, tail_z=None, tail_layout=0):
         """srcs: list[View]; segs: list[(src_index, taps, cblocks)]; weight [n, Ktot] 16-bit; bias [n] fp32."""
         d = ConvDesc()
         d.n_srcs = len(srcs)
@@ -129,6 +129,7 @@ class Plan:
         d.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
         d.tail_weight = tail_weight.data_ptr() if tail_weight is not None else None
         d.tail_z = tail_z.data_ptr() if tail_z is not None else None
+        d.tail_layout = tail_layout
         op = Op()
         op.kind = OP_CONV
         op.u.conv = d
@@ -136,7 +137,8 @@ class Plan:
         self.keep += [weight, bias, out_scale, out_f32, tail_weight, tail_z] + [s.buf for s in srcs] + ([out.buf] if out is not None else [])
         self.records.append(("conv", dict(srcs=list(srcs), segs=list(segs), weight=weight, bias=bias, out=out, Ho=Ho, Wo=Wo, B=B,
                                           n=n, n_valid=d.n_valid, shuffle=shuffle, act=act, out_scale=out_scale, out_f32=out_f32,
-                                          issued_flops=2 * B * Ho * Wo * n * ktot, tail_weight=tail_weight, tail_z=tail_z)))
+                                          issued_flops=2 * B * Ho * Wo * n * ktot, tail_weight=tail_weight, tail_z=tail_z,
+                                          tail_layout=tail_layout)))
 
     def prep(self, x, scale, shift, im2col, xnorm=None):
         B, C, H, W = x.shape
@@ -171,17 +173,17 @@ class Plan:
         self.keep += [src.buf, weight, bias, out_f32, out_u8]
         self.records.append(("tail", dict(src=src, weight=weight, bias=bias, mul=mul, add=add, out_f32=out_f32, out_u8=out_u8)))
 
-    def tailsum(self, z, r, bias, mul, add, out_f32=None, out_u8=None):
-        B, planes, H, W = z.shape
-        assert planes == r * r * 9 and z.dtype == torch.float32 and z.is_contiguous()
-        d = TailSumDesc(z.data_ptr(), B, H, W, r, float(bias), mul, add, 0, out_f32.data_ptr() if out_f32 is not None else None,
+    def tailsum(self, z, r, bias, mul, add, out_f32=None, out_u8=None, layout=0):
+        B, H, planes, W = z.shape            # z[b][y][s*9+t][x]  (layout 1: 48 window sums per LR pixel, include/pssr_b200.h)
+        assert planes == (48 if layout == 1 else r * r * 9) and z.dtype == torch.float32 and z.is_contiguous()
+        d = TailSumDesc(z.data_ptr(), B, H, W, r, float(bias), mul, add, layout, out_f32.data_ptr() if out_f32 is not None else None,
                         out_u8.data_ptr() if out_u8 is not None else None)
         op = Op()
         op.kind = OP_TAILSUM
         op.u.tailsum = d
         self.ops.append(op)
         self.keep += [z, out_f32, out_u8]
-        self.records.append(("tailsum", dict(z=z, r=r, bias=float(bias), mul=mul, add=add, out_f32=out_f32, out_u8=out_u8)))
+        self.records.append(("tailsum", dict(z=z, r=r, bias=float(bias), mul=mul, add=add, out_f32=out_f32, out_u8=out_u8, layout=layout)))
 
     def stem(self, x, in_scale, in_shift, patch, weight, bias, ln_w, ln_b, eps, out: View):
         B, C, H, W = x.shape

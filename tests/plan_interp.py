@@ -69,12 +69,26 @@ def run_records(plan):
                 acc = acc.view(B, rr, rr, cps, H, Wd).permute(0, 3, 4, 1, 5, 2).reshape(B, cps, H * rr, Wd * rr)
             if r.get("tail_z") is not None:
                 # acc is the pixel-shuffled post-activation map [B, C', H*r, W*r] (fp32): per-tap 1x1 projection, stored
-                # planar per sub-pixel:  z[b][s*9+t][y][x]
+                # per LR row and sub-pixel:  z[b][y][s*9+t][x]
                 tw = r["tail_weight"]                                   # [9][C']
                 zt = torch.einsum("bchw,tc->bthw", acc, tw)             # [B, 9, H*r, W*r]
                 B_, _, Hh, Wh = zt.shape
                 zt = zt.view(B_, 9, Hh // rr, rr, Wh // rr, rr).permute(0, 3, 5, 1, 2, 4).reshape(B_, rr * rr * 9, Hh // rr, Wh // rr)
-                r["tail_z"].copy_(zt)
+                if r.get("tail_layout", 0) == 1:
+                    # PSSR_TAIL_WINDOW48: zHR[b][t][4y+i'][4x+j'] feeds the output at (i'-dy, j'-dx) relative to the LR pixel;
+                    # plane e*24 + (oi+1)*4 + (oj+1-2e), e = j' // 2
+                    assert rr == 4
+                    zh = zt.view(B_, rr, rr, 9, Hh // rr, Wh // rr)             # [b][i'][j'][t][y][x]
+                    z48 = torch.zeros(B_, Hh // rr, 48, Wh // rr)
+                    for i_ in range(4):
+                        for j_ in range(4):
+                            for t in range(9):
+                                dy, dx = t // 3 - 1, t % 3 - 1
+                                e = j_ // 2
+                                z48[:, :, e * 24 + (i_ - dy + 1) * 4 + (j_ - dx + 1 - 2 * e), :] += zh[:, i_, j_, t]
+                    r["tail_z"].copy_(z48)
+                    continue
+                r["tail_z"].copy_(zt.permute(0, 2, 1, 3))
                 continue
             o = r["out"]
             if o is not None:
@@ -116,8 +130,21 @@ def run_records(plan):
             if r["gamma"] is not None:
                 y = y * r["gamma"].view(1, -1, 1, 1)
             o.buf[..., o.choff:o.choff + C] = y.permute(0, 2, 3, 1).to(o.buf.dtype)
+        elif kind == "tailsum" and r.get("layout", 0) == 1:
+            z48, rr = r["z"], r["r"]
+            B_, H, _, W = z48.shape
+            canvas = torch.zeros(B_, H * 4 + 2, W * 4 + 2)
+            for e in range(2):
+                for oi in range(6):
+                    for ojl in range(4):
+                        canvas[:, oi:oi + 4 * H:4, ojl + 2 * e:ojl + 2 * e + 4 * W:4] += z48[:, :, e * 24 + oi * 4 + ojl, :]
+            y = (canvas[:, None, 1:-1, 1:-1] + r["bias"]) * r["mul"] + r["add"]
+            if r["out_f32"] is not None:
+                r["out_f32"].copy_(y)
+            if r["out_u8"] is not None:
+                r["out_u8"].copy_(y.clamp(0, 255).to(torch.uint8))
         elif kind == "tailsum":
-            z, rr = r["z"], r["r"]
+            z, rr = r["z"].permute(0, 2, 1, 3).contiguous(), r["r"]
             B_, _, H, W = z.shape
             zh = z.view(B_, rr, rr, 9, H, W).permute(0, 3, 4, 1, 5, 2).reshape(B_, 9, H * rr, W * rr)   # zHR[b][t][Y][X]
             zp = F.pad(zh, (1, 1, 1, 1))

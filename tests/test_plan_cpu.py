@@ -42,6 +42,23 @@ def test_resunet_plan_matches_oracle_on_cpu(dry_run, cfg):
     assert torch.equal(st["out_u8"], got[:, c:c + 1].clamp(0, 255).to(torch.uint8))
 
 
+def test_resunet_plan_window48_tail_on_cpu(dry_run):
+    """W % 128 == 0 and scale 4: the fused tail uses the PSSR_TAIL_WINDOW48 layout (include/pssr_b200.h); its CPU statement in
+    tests/plan_interp.py must reproduce the oracle forward as well."""
+    from pssr2_b200.models import ResUNet
+    torch.manual_seed(3)
+    model = ResUNet(hidden=[64, 128], depth=0).eval()
+    _randomise_bn(model)
+    x = torch.tensor(np.random.default_rng(3).integers(0, 256, (2, 1, 4, 128)).astype(np.float32))
+    want = resunet_forward(model.state_dict(), x)
+    model.precision = "fp16"
+    st = model._build(x.shape, x.dtype, torch.device("cpu"))
+    assert any(k == "tailsum" and r["layout"] == 1 for k, r in st["plan"].records)
+    st["x"].copy_(x)
+    run_records(st["plan"])
+    assert float((st["out"] - want).abs().max()) < 3e-2
+
+
 @pytest.mark.parametrize("cfg", [dict(), dict(hidden=[128, 64], growth_rates=[32, 40, 64], ds_blocks=[False, True, False],
                                                 ese_blocks=[False, True, True], n_blocks=[2, 1, 2], rdnet_init=64, scale=2, depth=1)])
 def test_rdresunet_plan_matches_oracle_on_cpu(dry_run, cfg):
