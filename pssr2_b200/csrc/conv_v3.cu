@@ -41,6 +41,7 @@ struct V3Params {
   int rows_mode;              // 1: tile = one 128-pixel row segment (W % 128 == 0)
   int total_vrows;            // rows mode: B * NJ * H
   int ring_R;                 // rows mode: row groups in the ring
+  int row_major;              // rows mode: filter-row-major K order with early release / late acquire of ring rows (shallow ring)
   uint32_t slot_bytes;        // rows mode: one row of one 64-channel plane = P * 128
   uint32_t group_bytes;       // rows mode: all planes of one row
   uint32_t ring_bytes;        // rows mode: ring_R * group_bytes rounded up to 1024
@@ -448,11 +449,17 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
         int k = 0;
         for (int unit = worker; ROWS ? k < steps : unit < p.total_units; unit += workers, ++k) {
           const int n_tile = ROWS ? k % p.n_tiles : unit % p.n_tiles;
+          // ROWS: filter-row-major order (dy = -1, 0, +1; 1x1 segments ride with dy = 0), the order the MMA issuer walks so that
+          // the top input row can be released after the first third of a unit.  Flat: channel-block-major (A is staged per block).
+          const bool rm = ROWS && p.row_major;
+          for (int g = 0; g < (rm ? 3 : 1); ++g)
           for (int sg = 0; sg < p.n_segs; ++sg) {
             const int taps = p.seg_taps[sg], cbs = p.seg_cblocks[sg];
             const int gs = taps == 9 ? G : 1;
+            if (rm && taps != 9 && g != 1) continue;
+            const int t_lo = (rm && taps == 9) ? 3 * g : 0, t_hi = (rm && taps == 9) ? 3 * g + 3 : taps;
             for (int cb = 0; cb < cbs; ++cb) {
-              for (int t0 = 0; t0 < taps; t0 += gs) {
+              for (int t0 = t_lo; t0 < t_hi; t0 += gs) {
                 mbar_wait(b_empty(bs), bphase ^ 1u);
                 const uint32_t fbar = PAIR ? v3_mapa(b_full(bs), 0) : b_full(bs);
                 if (rank == 0) mbar_arrive_expect_tx(b_full(bs), (uint32_t)gs * p.tap_bytes * C);
@@ -619,6 +626,121 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
       ++it;
     };
 
+    // ROWS: one accumulator tile set in filter-row-major order.  rows[i] = ring row y0-1+i of the current group: descriptor ea[i],
+    // slot sl[i], barrier parity ph[i].  Row i is first read by filter row dy = max(-1, i-T) and last by dy = min(1, i-1), so it
+    // is awaited just before its first use (bit i of newmask: the row was fetched for this step) and handed back to the producer
+    // right after its last (bit i of relmask) -- with a ring of only T+2 rows the next rows load while this unit computes.
+    auto run_k_rows = [&](const uint64_t (&ea)[T + 2], const int (&sl)[T + 2], const uint32_t (&ph)[T + 2], uint32_t newmask, uint32_t relmask) {
+      const int buf = it & 1;
+      mbar_wait(t_empty(buf), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      if (it < 31) V3_TRACE(2 + 2 * it);
+      const uint32_t d0 = tmem_base + (uint32_t)(buf * 256);
+      uint32_t acc = 0;
+      bool tail_done = false;
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        const int dy = g - 1;
+#pragma unroll
+        for (int i = 0; i < T + 2; ++i) {
+          const int need = (i - T) > -1 ? (i - T) : -1;
+          if (need == dy && ((newmask >> i) & 1u)) mbar_wait(r_full(sl[i]), ph[i]);
+        }
+        tc_fence_after();
+        if (g == 0 && it < 31) V3_TRACE(128 + 2 * it);
+        uint64_t plane_desc = 0;
+        for (int sg = 0; sg < n_segs; ++sg) {
+          const uint32_t sw = sg == 0 ? segw[0] : sg == 1 ? segw[1] : sg == 2 ? segw[2] : segw[3];
+          const bool nine = (sw & 1u) != 0;
+          const int cbs = (int)((sw >> 1) & 0xffu);
+          const int kb0 = (int)(sw >> 9);
+          if (!nine && g != 1) { plane_desc += (uint64_t)cbs * slot_desc; continue; }
+          for (int cb = 0; cb < cbs; ++cb, plane_desc += slot_desc) {
+            if (nine) {
+              constexpr int GS = G == 9 ? 3 : G;          // taps per weight stage inside one filter row
+#pragma unroll
+              for (int x0 = 0; x0 < 3; x0 += GS) {
+                uint64_t bd;
+                if (RES) {
+                  bd = bdesc0 + (uint64_t)((uint32_t)(kb0 + (3 * g + x0) * cbs + cb) * tapstep);
+                } else {
+                  mbar_wait(b_full(bs), bphase);
+                  tc_fence_after();
+                  bd = bdesc0 + (uint64_t)((uint32_t)bs * bstep);
+                }
+                const uint64_t btap = RES ? (uint64_t)((uint32_t)cbs * tapstep) : (uint64_t)tapstep;
+                if (elect_one()) {
+#pragma unroll
+                  for (int tt = 0; tt < GS; ++tt) {
+                    const int dx = x0 + tt - 1;
+                    const uint64_t bdt = bd + (uint64_t)tt * btap;
+#pragma unroll
+                    for (int mt = 0; mt < T; ++mt) {
+                      const uint64_t adm = ea[mt + 1 + dy] + plane_desc + (uint64_t)((1 + dx) * 8);
+                      const uint32_t dcol = d0 + (uint32_t)(mt * block_n);
+                      if (tt == 0) v3_mma_p<PAIR>(dcol, adm, bdt, idesc, acc);
+                      else v3_mma_acc<PAIR>(dcol, adm, bdt, idesc);
+                      v3_mma_acc<PAIR>(dcol, adm + 2, bdt + 2, idesc);
+                      v3_mma_acc<PAIR>(dcol, adm + 4, bdt + 4, idesc);
+                      v3_mma_acc<PAIR>(dcol, adm + 6, bdt + 6, idesc);
+                    }
+                  }
+                  if (!RES) v3_commit<PAIR>(b_empty(bs));
+                }
+                __syncwarp();
+                acc = 1;
+                if (!RES) { if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; } }
+                if (TAIL && g == 2 && !tail_done) {
+                  // the previous unit's 16-bit activations are in TMEM by now: project them on the nine tail taps
+                  if (it > 0) issue_tail(it - 1);
+                  tail_done = true;
+                }
+              }
+            } else {
+              uint64_t bd;
+              if (RES) {
+                bd = bdesc0 + (uint64_t)((uint32_t)(kb0 + cb) * tapstep);
+              } else {
+                mbar_wait(b_full(bs), bphase);
+                tc_fence_after();
+                bd = bdesc0 + (uint64_t)((uint32_t)bs * bstep);
+              }
+              if (elect_one()) {
+#pragma unroll
+                for (int mt = 0; mt < T; ++mt) {
+                  const uint64_t adm = ea[mt + 1] + plane_desc + 8u;
+                  const uint32_t dcol = d0 + (uint32_t)(mt * block_n);
+                  v3_mma_p<PAIR>(dcol, adm, bd, idesc, acc);
+                  v3_mma_acc<PAIR>(dcol, adm + 2, bd + 2, idesc);
+                  v3_mma_acc<PAIR>(dcol, adm + 4, bd + 4, idesc);
+                  v3_mma_acc<PAIR>(dcol, adm + 6, bd + 6, idesc);
+                }
+                if (!RES) v3_commit<PAIR>(b_empty(bs));
+              }
+              __syncwarp();
+              acc = 1;
+              if (!RES) { if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; } }
+            }
+          }
+        }
+        if (relmask != 0u) {
+          if (elect_one()) {
+#pragma unroll
+            for (int i = 0; i < T + 2; ++i) {
+              const int last_use = (i - 1) < 1 ? (i - 1) : 1;
+              if (last_use == dy && ((relmask >> i) & 1u)) v3_commit<PAIR>(r_empty(sl[i]));
+            }
+          }
+          __syncwarp();
+        }
+      }
+      if (TAIL && !tail_done && it > 0) issue_tail(it - 1);
+      if (elect_one()) v3_commit<PAIR>(t_full(buf));
+      __syncwarp();
+      if (it < 31) V3_TRACE(3 + 2 * it);
+      ++it;
+    };
+
     if (RES) {
       mbar_wait(b_full(0), 0);
       tc_fence_after();
@@ -639,24 +761,26 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
       }
       const bool odd_tail = PAIR && (((g_hi - g_lo) & 1) != 0);
       for (int ms = 0; ms < msteps; ++ms) {
-        const int count = fresh ? T + 2 : T;
+        // ring slots of the T+2 rows of this group; the rows fetched for this step (all of them after a fresh start, else the
+        // last T) are consumed in slot order, each with the barrier parity of its own lap around the ring
         int first = fresh ? cslot : cslot - 2;
         if (first < 0) first += p.ring_R;
-        for (int i = 0; i < count; ++i) {
-          mbar_wait(r_full(cslot), cphase);
-          if (++cslot == p.ring_R) { cslot = 0; cphase ^= 1u; }
-        }
-        tc_fence_after();
         uint64_t ea[T + 2];
         int sl[T + 2];
+        uint32_t ph[T + 2];
 #pragma unroll
         for (int i = 0; i < T + 2; ++i) {
           int s_i = first + i;
           if (s_i >= p.ring_R) s_i -= p.ring_R;
           sl[i] = s_i;
           ea[i] = ring_desc0 + (uint64_t)s_i * group_desc;
+          ph[i] = 0;
+          if (fresh || i >= 2) {
+            ph[i] = cphase;
+            if (++cslot == p.ring_R) { cslot = 0; cphase ^= 1u; }
+          }
         }
-        for (int nt = 0; nt < p.n_tiles; ++nt) run_k(ea);
+        const uint32_t newmask = fresh ? ((1u << (T + 2)) - 1u) : (((1u << (T + 2)) - 1u) & ~3u);
         // rows that no later group of this worker needs go back to the producer
         const bool last = ms + 1 == msteps;
         bool next_fresh = odd_tail && ms + 2 == msteps;
@@ -666,13 +790,24 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
           if (y0r[rk] >= p.H) y0r[rk] -= p.H;
           next_fresh = next_fresh || y0r[rk] == 0;
         }
-        if (!last) {
-          if (elect_one()) {
+        const uint32_t relmask = last ? 0u : (next_fresh ? ((1u << (T + 2)) - 1u) : ((1u << T) - 1u));
+        if (p.row_major) {
+          for (int nt = 0; nt < p.n_tiles; ++nt)
+            run_k_rows(ea, sl, ph, nt == 0 ? newmask : 0u, nt + 1 == p.n_tiles ? relmask : 0u);
+        } else {
 #pragma unroll
-            for (int i = 0; i < T + 2; ++i)
-              if (i < T || next_fresh) v3_commit<PAIR>(r_empty(sl[i]));
+          for (int i = 0; i < T + 2; ++i)
+            if ((newmask >> i) & 1u) mbar_wait(r_full(sl[i]), ph[i]);
+          tc_fence_after();
+          for (int nt = 0; nt < p.n_tiles; ++nt) run_k(ea);
+          if (relmask != 0u) {
+            if (elect_one()) {
+#pragma unroll
+              for (int i = 0; i < T + 2; ++i)
+                if ((relmask >> i) & 1u) v3_commit<PAIR>(r_empty(sl[i]));
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
         fresh = next_fresh;
       }
@@ -1125,24 +1260,29 @@ int v3_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
   int G = 1, RES = 0, b_stages = 0, ring_R = 0;
   long long a_total = 0, a_bytes = 0;
   const int T_first = T;
-  int stage_bytes = p.tma_store ? 8 * 4096 : 0;
-  long long smem_cap = smem_cap0 - stage_bytes;
-retry_sizes:
-  for (T = T_first;; --T) {
-    long long a_min;        // smallest A staging that works; rows mode: the ring grows into whatever the weights leave
+  const int want_stage = p.tma_store;
+  int stage_bytes = 0;
+  long long smem_cap = smem_cap0;
+  // Shared-memory budget.  Candidates in order of preference: resident weights before streamed ones (rows mode), T = 2 before
+  // T = 1, a deep ring (2T+2 rows: plain K order, all nine taps of a block issued in one go) before a shallow one (T+2 rows:
+  // filter-row-major order, the issuer releases the top rows early and awaits the bottom rows late so that the next rows load
+  // while the unit computes), TMA-store staging before direct stores.  Whatever is left after the weights deepens the ring.
+  auto try_config = [&](int Tc, bool staged, bool res_only, bool deep) -> bool {
+    const long long cap = smem_cap0 - (staged ? 8 * 4096 : 0);
+    long long a_min, ab = 0;
     if (p.rows_mode) {
-      a_min = (long long)(T + 2 + T) * p.group_bytes;          // the current group and one group of prefetch
+      a_min = (long long)(deep ? 2 * Tc + 2 : Tc + 2) * p.group_bytes;      // deep: the current group and one group of prefetch
     } else {
-      const long long a_raw = p.pad ? (long long)(128 * T + 4 * p.P + 1) * 128 : 128LL * T * 128;
-      a_bytes = ((a_raw + 1023) / 1024) * 1024;
-      a_min = 2 * a_bytes;
+      const long long a_raw = p.pad ? (long long)(128 * Tc + 4 * p.P + 1) * 128 : 128LL * Tc * 128;
+      ab = ((a_raw + 1023) / 1024) * 1024;
+      a_min = 2 * ab;
     }
     a_min = ((a_min + 1023) / 1024) * 1024;
-    const long long left = smem_cap - a_min;
-    G = 0; RES = 0; b_stages = 0;
+    const long long left = cap - a_min;
+    int g_ = 0, res_ = 0, bst_ = 0;
     if (p.n_tiles == 1 && (long long)num_kb * p.tap_bytes <= left && getenv("PSSR_V3_NORES") == nullptr && !tail) {
-      RES = 1; G = 9; b_stages = 1;
-    } else {
+      res_ = 1; g_ = 9; bst_ = 1;
+    } else if (!res_only) {
       // small N: a stage must hold many MMAs (a barrier poll costs ~100 unhidden cycles); N = 256: finer stages, deeper prefetch
       const int cand[2] = {3, 1};
       for (int ci = (block_n >= 256 ? 1 : 0); ci < 2; ++ci) {
@@ -1152,24 +1292,31 @@ retry_sizes:
         const long long stage = (long long)g * p.tap_bytes;
         const int need = g == 1 ? 3 : 2;
         if (left >= need * stage) {
-          G = g;
-          b_stages = (int)(left / stage);
+          g_ = g;
+          bst_ = (int)(left / stage);
           const int want = g == 1 ? 6 : 3;                      // rows mode: the rest goes to the ring
-          if (p.rows_mode && b_stages > want) b_stages = want;
+          if (p.rows_mode && bst_ > want) bst_ = want;
           break;
         }
       }
-      if (G == 0 && left >= 2LL * p.tap_bytes) { G = 1; b_stages = (int)(left / p.tap_bytes); }
-      if (b_stages > kV3MaxB) b_stages = kV3MaxB;
+      if (g_ == 0 && left >= 2LL * p.tap_bytes) { g_ = 1; bst_ = (int)(left / p.tap_bytes); }
+      if (bst_ > kV3MaxB) bst_ = kV3MaxB;
     }
-    if (G != 0 || T == 1) break;
-  }
-  if ((G == 0 || (p.rows_mode && (smem_cap - (RES ? (long long)num_kb * p.tap_bytes : (long long)b_stages * G * p.tap_bytes)) / p.group_bytes < T + 2)) &&
-      p.tma_store) {
-    p.tma_store = 0;            // not enough shared memory for the store staging tiles: direct stores
-    stage_bytes = 0;
-    smem_cap = smem_cap0;
-    goto retry_sizes;
+    if (g_ == 0) return false;
+    T = Tc; G = g_; RES = res_; b_stages = bst_; a_bytes = ab;
+    p.row_major = (p.rows_mode && !deep) ? 1 : 0;
+    p.tma_store = staged ? 1 : 0;
+    stage_bytes = staged ? 8 * 4096 : 0;
+    smem_cap = cap;
+    return true;
+  };
+  {
+    bool found = false;
+    for (int pass = (p.rows_mode ? 0 : 1); pass < 2 && !found; ++pass)
+      for (int Tc = T_first; Tc >= 1 && !found; --Tc)
+        for (int deep = 1; deep >= (p.rows_mode ? 0 : 1) && !found; --deep)
+          for (int st = want_stage; st >= 0 && !found; --st) found = try_config(Tc, st != 0, pass == 0, deep != 0);
+    if (!found) G = 0;
   }
   PSSR_REQUIRE(G != 0 && b_stages >= 1, PSSR_EUNSUP, "conv: image width %d needs more shared memory than available", d.Wo);
   p.b_bytes = (uint32_t)(G * (int)p.tap_bytes);
@@ -1306,8 +1453,8 @@ retry_sizes:
     attr_set = true;
   }
   if (getenv("PSSR_V3_VERBOSE") != nullptr)
-    fprintf(stderr, "v3: %dx%d n=%d kb=%d block_n=%d T=%d G=%d RES=%d TAIL=%d PAIR=%d rows=%d ring=%d b_stages=%d a_bytes=%u smem=%d units=%d grid=%d\n",
-            d.Ho, d.Wo, d.n, num_kb, block_n, T, G, RES, (int)tail, PAIR, p.rows_mode, p.ring_R, b_stages, p.a_bytes, op.smem_bytes, p.total_units,
+    fprintf(stderr, "v3: %dx%d n=%d kb=%d block_n=%d T=%d G=%d RES=%d TAIL=%d PAIR=%d rows=%d/%d ring=%d b_stages=%d a_bytes=%u smem=%d units=%d grid=%d\n",
+            d.Ho, d.Wo, d.n, num_kb, block_n, T, G, RES, (int)tail, PAIR, p.rows_mode, p.row_major, p.ring_R, b_stages, p.a_bytes, op.smem_bytes, p.total_units,
             op.grid);
   return PSSR_OK;
 }
