@@ -52,8 +52,12 @@ def _peak_sustained(burst_tf):
 
 # dram__bytes_read.sum + dram__bytes_write.sum summed over the conv launches of ONE step, from the ncu capture named below
 # (None until a capture of the current kernels is committed)
-CONV_DRAM_BYTES_PER_STEP = None
-CONV_DRAM_SOURCE = None
+CONV_DRAM_BYTES_PER_STEP = 4232002048
+CONV_DRAM_SOURCE = "profiles/r01_launches_v3_summary.txt (ncu launch list of `bench.py --kernels-only`, 37 conv launches of one step: 3132.5 MB read + 1099.5 MB written)"
+# the single largest launch: Reconstruction.pre (65 -> 1024 channels @128^2, 19.629 GFLOP per tile) with the fused tail
+RECON_FLOPS_PER_TILE = 19.629e9
+RECON_DRAM_BYTES = 440600000
+RECON_DRAM_SOURCE = "profiles/r01_launches_v3_summary.txt launch #42 (279.3 MB read + 161.3 MB written)"
 
 
 def _synthetic_tiles(n, seed, device):
@@ -297,6 +301,7 @@ def run_ours(args):
     n_conv = sum(1 for kind, _ in plan.records if kind == "conv")
     peak_tf, peak_hbm, peak_src = _peaks()
     peak_sus = _peak_sustained(peak_tf)
+    recon_ms = max((t for t, (kind, r) in zip(acc, plan.records) if kind == "conv" and r.get("tail_z") is not None), default=None)
     conv_flops = (ALG_FLOPS_PER_TILE - TAIL_FLOPS_PER_TILE) * BATCH
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12
     # The conv launches are timed inside the step sequence (tens of milliseconds of back-to-back tensor work under the 1 kW
@@ -308,6 +313,12 @@ def run_ours(args):
                 "peak_source": peak_src + " (bf16_tflops_sustained)", "peak_burst": peak_tf, "frac_of_burst": round(achieved / peak_tf, 4),
                 "algorithmic_flops_per_step": conv_flops, "launches_per_step": n_conv, "kernel_ms_per_step": round(conv_ms, 3),
                 "other_net_ms_per_step": round(other_ms, 3),
+                "dominant_launch": None if not recon_ms else {
+                    "kernel": "conv_v3_kernel<T=1,G=1,TAIL,PAIR,ROWS>: Reconstruction.pre 65->1024 @128^2 + tensor-core tail projection",
+                    "ms": round(recon_ms, 3), "achieved": round(RECON_FLOPS_PER_TILE * BATCH / (recon_ms * 1e-3) / 1e12, 1),
+                    "peak": peak_sus, "frac": round(RECON_FLOPS_PER_TILE * BATCH / (recon_ms * 1e-3) / 1e12 / peak_sus, 4),
+                    "frac_of_burst": round(RECON_FLOPS_PER_TILE * BATCH / (recon_ms * 1e-3) / 1e12 / peak_tf, 4),
+                    "traffic": RECON_DRAM_BYTES, "traffic_source": RECON_DRAM_SOURCE},
                 "step_frac_of_peak": round(ALG_FLOPS_PER_TILE * BATCH / (ms_step * 1e-3) / 1e12 / peak_sus, 4)}
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ------------------------

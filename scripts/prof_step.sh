@@ -8,3 +8,8 @@ ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.s
     --clock-control none --csv --log-file gpurun_out/r01_launches_v3.csv $CMD > gpurun_out/prof_ncu1.log 2>&1
 cat gpurun_out/prof_plain.log
 tail -n 3 gpurun_out/prof_ncu1.log
+# full captures of the dominant launches (one capture each; ncu replays the kernel ~40 times)
+ncu --profile-from-start off --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:conv_v3_kernelILi1ELi1ELb0ELb1E -c 1 -f -o gpurun_out/r01_v3_recon_pre $CMD > gpurun_out/prof_ncu2.log 2>&1
+ncu --profile-from-start off --set full --clock-control none -k regex:metric_kernel -c 1 -f -o gpurun_out/r01_metric $CMD > gpurun_out/prof_ncu3.log 2>&1
+ncu --profile-from-start off --set full --clock-control none -k regex:crappify_kernel -c 1 -f -o gpurun_out/r01_crappify $CMD > gpurun_out/prof_ncu4.log 2>&1
+ncu --profile-from-start off --set full --clock-control none -k regex:tailsum -c 1 -f -o gpurun_out/r01_tailsum $CMD > gpurun_out/prof_ncu5.log 2>&1
