@@ -214,9 +214,12 @@ typedef struct {
   int32_t B, C, H, W;
   const float* scale;    /* [C] BN scale  s  (1 if no norm)                                  */
   const float* shift;    /* [C] BN shift  t                                                   */
-  void* im2col;          /* NHWC 16-bit [B][H][W][64]: channel (c*9+tap) = norm(x) at the tap,
+  void* im2col;          /* NHWC 16-bit [B][H][W][cols]: channel (c*9+tap) = norm(x) at the tap,
                             zero outside the image and for channels >= 9*C                   */
   float* xnorm_f32;      /* [B][C][H][W] fp32 normalised input (the final skip), may be NULL */
+  int32_t cols;          /* channels per pixel of im2col: 64 (0 = 64) or 16 when 9*C <= 16 -- the consuming
+                            convolutions' TMA boxes zero-fill channels >= cols, 4x less HBM traffic         */
+  int32_t reserved;
 } pssr_prep_desc_t;
 
 typedef struct {

@@ -43,7 +43,10 @@ struct V3Params {
   int ring_R;                 // rows mode: row groups in the ring
   int row_major;              // rows mode: filter-row-major K order with early release / late acquire of ring rows (shallow ring)
   uint32_t slot_bytes;        // rows mode: one row of one 64-channel plane = P * 128
-  uint32_t group_bytes;       // rows mode: all planes of one row
+  uint32_t slot16_bytes;      // rows mode: one row of a narrow (16-channel, SWIZZLE_32B) plane = P * 32 rounded up to 128
+  uint32_t group_bytes;       // rows mode: all planes of one row (layout stride of a ring slot)
+  uint32_t group_tx;          // rows mode: bytes the TMA unit writes per ring slot
+  int seg_k16[4];             // rows mode: the segment's source is a 16-channel tensor staged as a narrow plane (one K = 16 MMA)
   uint32_t ring_bytes;        // rows mode: ring_R * group_bytes rounded up to 1024
   int q_begin, q_end;         // flat mode
   int off_px;                 // pixel offset of a unit's first pixel inside an A stage buffer
@@ -363,14 +366,14 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
           for (int i = 0; i < count; ++i) {
             mbar_wait(r_empty(slot), phase ^ 1u);
             const uint32_t fbar = PAIR ? v3_mapa(r_full(slot), 0) : r_full(slot);
-            if (rank == 0) mbar_arrive_expect_tx(r_full(slot), p.group_bytes * C);
+            if (rank == 0) mbar_arrive_expect_tx(r_full(slot), p.group_tx * C);
             uint32_t dst = a_base + (uint32_t)slot * p.group_bytes;
             for (int sg = 0; sg < p.n_segs; ++sg) {
               const CUtensorMap* tm = p.tmaps + p.seg_src[sg];
               for (int cb = 0; cb < p.seg_cblocks[sg]; ++cb) {
                 if (PAIR) v3_tma_4d_pair(dst, tm, fbar, cb * 64, x0, first_row + i, n);
                 else tma_load_4d(dst, tm, fbar, cb * 64, x0, first_row + i, n);
-                dst += p.slot_bytes;
+                dst += p.seg_k16[sg] ? p.slot16_bytes : p.slot_bytes;
               }
             }
             if (++slot == p.ring_R) { slot = 0; phase ^= 1u; }
@@ -490,6 +493,9 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
     const int64_t P8 = (int64_t)p.P * 8;
     const uint64_t tile_step = p.tile_step;
     const uint64_t slot_desc = (uint64_t)(p.slot_bytes >> 4);
+    const uint64_t slot16_desc = (uint64_t)(p.slot16_bytes >> 4);
+    // narrow plane: same start-address field, SWIZZLE_32B layout (type 6) and 256-byte stride between 8-row groups
+    const uint64_t k16_fix = (((uint64_t)(256u >> 4) << 32) | ((uint64_t)6 << 61)) - (((uint64_t)(1024u >> 4) << 32) | ((uint64_t)2 << 61));
     int as = 0, bs = 0;
     uint32_t aphase = 0, bphase = 0;
     int it = 0;
@@ -498,7 +504,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
     uint32_t segw[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      segw[i] = i < p.n_segs ? ((p.seg_taps[i] == 9 ? 1u : 0u) | ((uint32_t)p.seg_cblocks[i] << 1) | ((uint32_t)p.seg_kb0[i] << 9)) : 0u;
+      segw[i] = i < p.n_segs ? ((p.seg_taps[i] == 9 ? 1u : 0u) | ((uint32_t)p.seg_cblocks[i] << 1) | ((uint32_t)p.seg_kb0[i] << 9) |
+                                (p.seg_k16[i] ? 0x80000000u : 0u)) : 0u;
     const int n_segs = p.n_segs;
 
     auto issue_tail = [&](int pit) {
@@ -535,9 +542,10 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
       for (int sg = 0; sg < n_segs; ++sg) {
         const uint32_t sw = sg == 0 ? segw[0] : sg == 1 ? segw[1] : sg == 2 ? segw[2] : segw[3];
         const bool nine = (sw & 1u) != 0;
+        const bool k16 = ROWS && (sw >> 31) != 0;
         const int cbs = (int)((sw >> 1) & 0xffu);
-        const int kb0 = (int)(sw >> 9);
-        for (int cb = 0; cb < cbs; ++cb, plane_desc += slot_desc) {
+        const int kb0 = (int)((sw >> 9) & 0x3fffffu);
+        for (int cb = 0; cb < cbs; ++cb, plane_desc += (k16 ? slot16_desc : slot_desc)) {
           uint64_t ad0 = 0;
           if (!ROWS) {
             mbar_wait(a_full(as), aphase);
@@ -598,12 +606,16 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
             if (elect_one()) {
 #pragma unroll
               for (int mt = 0; mt < T; ++mt) {
-                const uint64_t adm = ROWS ? ea[mt + 1] + plane_desc + 8u : ad0 + (uint64_t)mt * tile_step;
                 const uint32_t dcol = d0 + (uint32_t)(mt * block_n);
-                v3_mma_p<PAIR>(dcol, adm, bd, idesc, acc);
-                v3_mma_acc<PAIR>(dcol, adm + 2, bd + 2, idesc);
-                v3_mma_acc<PAIR>(dcol, adm + 4, bd + 4, idesc);
-                v3_mma_acc<PAIR>(dcol, adm + 6, bd + 6, idesc);
+                if (k16) {     // one K = 16 step: pixel x0 + 1 of the narrow plane (32 bytes per pixel)
+                  v3_mma_p<PAIR>(dcol, ea[mt + 1] + plane_desc + 2u + k16_fix, bd, idesc, acc);
+                } else {
+                  const uint64_t adm = ROWS ? ea[mt + 1] + plane_desc + 8u : ad0 + (uint64_t)mt * tile_step;
+                  v3_mma_p<PAIR>(dcol, adm, bd, idesc, acc);
+                  v3_mma_acc<PAIR>(dcol, adm + 2, bd + 2, idesc);
+                  v3_mma_acc<PAIR>(dcol, adm + 4, bd + 4, idesc);
+                  v3_mma_acc<PAIR>(dcol, adm + 6, bd + 6, idesc);
+                }
               }
               if (!RES) v3_commit<PAIR>(b_empty(bs));
             }
@@ -652,10 +664,11 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
         for (int sg = 0; sg < n_segs; ++sg) {
           const uint32_t sw = sg == 0 ? segw[0] : sg == 1 ? segw[1] : sg == 2 ? segw[2] : segw[3];
           const bool nine = (sw & 1u) != 0;
+          const bool k16 = (sw >> 31) != 0;
           const int cbs = (int)((sw >> 1) & 0xffu);
-          const int kb0 = (int)(sw >> 9);
-          if (!nine && g != 1) { plane_desc += (uint64_t)cbs * slot_desc; continue; }
-          for (int cb = 0; cb < cbs; ++cb, plane_desc += slot_desc) {
+          const int kb0 = (int)((sw >> 9) & 0x3fffffu);
+          if (!nine && g != 1) { plane_desc += (uint64_t)cbs * (k16 ? slot16_desc : slot_desc); continue; }
+          for (int cb = 0; cb < cbs; ++cb, plane_desc += (k16 ? slot16_desc : slot_desc)) {
             if (nine) {
               constexpr int GS = G == 9 ? 3 : G;          // taps per weight stage inside one filter row
 #pragma unroll
@@ -708,12 +721,16 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
               if (elect_one()) {
 #pragma unroll
                 for (int mt = 0; mt < T; ++mt) {
-                  const uint64_t adm = ea[mt + 1] + plane_desc + 8u;
                   const uint32_t dcol = d0 + (uint32_t)(mt * block_n);
-                  v3_mma_p<PAIR>(dcol, adm, bd, idesc, acc);
-                  v3_mma_acc<PAIR>(dcol, adm + 2, bd + 2, idesc);
-                  v3_mma_acc<PAIR>(dcol, adm + 4, bd + 4, idesc);
-                  v3_mma_acc<PAIR>(dcol, adm + 6, bd + 6, idesc);
+                  if (k16) {
+                    v3_mma_p<PAIR>(dcol, ea[mt + 1] + plane_desc + 2u + k16_fix, bd, idesc, acc);
+                  } else {
+                    const uint64_t adm = ea[mt + 1] + plane_desc + 8u;
+                    v3_mma_p<PAIR>(dcol, adm, bd, idesc, acc);
+                    v3_mma_acc<PAIR>(dcol, adm + 2, bd + 2, idesc);
+                    v3_mma_acc<PAIR>(dcol, adm + 4, bd + 4, idesc);
+                    v3_mma_acc<PAIR>(dcol, adm + 6, bd + 6, idesc);
+                  }
                 }
                 if (!RES) v3_commit<PAIR>(b_empty(bs));
               }
@@ -1256,7 +1273,24 @@ int v3_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
   int planes = 0;
   for (int s2 = 0; s2 < d.n_segs; ++s2) planes += d.segs[s2].cblocks;
   p.slot_bytes = (uint32_t)(p.P * 128);
-  p.group_bytes = p.slot_bytes * (uint32_t)planes;
+  p.slot16_bytes = (uint32_t)(((p.P * 32 + 127) / 128) * 128);
+  // narrow planes (rows mode): a 1x1 segment over a 16-channel tensor (the im2col of a 1-channel input) is staged with 32-byte
+  // pixels and multiplied with ONE K = 16 MMA instead of four (3 of the 40 K steps of Reconstruction.pre were zeros)
+  bool src_k16[3] = {false, false, false};
+  p.group_bytes = 0;
+  p.group_tx = 0;
+  for (int s2 = 0; s2 < d.n_segs; ++s2) {
+    const pssr_kseg_t& sg = d.segs[s2];
+    const pssr_src_t& src = d.srcs[sg.src];
+    const bool k16 = p.rows_mode && sg.taps == 1 && sg.cblocks == 1 && src.cstride == 16 && src.channels <= 16 && getenv("PSSR_V3_NO_K16") == nullptr;
+    p.seg_k16[s2] = k16 ? 1 : 0;
+    if (k16) src_k16[sg.src] = true;
+    p.group_bytes += (uint32_t)sg.cblocks * (k16 ? p.slot16_bytes : p.slot_bytes);
+    p.group_tx += (uint32_t)sg.cblocks * (uint32_t)p.P * (k16 ? 32u : 128u);
+  }
+  for (int s2 = 0; s2 < d.n_segs; ++s2)
+    PSSR_REQUIRE(p.seg_k16[s2] || !src_k16[d.segs[s2].src], PSSR_EUNSUP, "conv: a 16-channel source must be read by 1x1 segments only");
+  (void)planes;
   int G = 1, RES = 0, b_stages = 0, ring_R = 0;
   long long a_total = 0, a_bytes = 0;
   const int T_first = T;
@@ -1362,10 +1396,11 @@ int v3_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
     if (p.pad) {
       cuuint64_t gdim[4] = {(cuuint64_t)src.channels, (cuuint64_t)src.W, (cuuint64_t)src.H, (cuuint64_t)src.B};
       cuuint64_t gstr[3] = {(cuuint64_t)src.cstride * 2, (cuuint64_t)src.cstride * 2 * src.W, (cuuint64_t)src.cstride * 2 * src.W * src.H};
-      cuuint32_t box[4] = {64, (cuuint32_t)p.P, 1, 1};
+      cuuint32_t box[4] = {src_k16[s] ? 16u : 64u, (cuuint32_t)p.P, 1, 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
       r = enc(&op.tmaps[s], tdt, 4, const_cast<void*>(src.base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+              src_k16[s] ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
       cuuint64_t gdim2[2] = {(cuuint64_t)src.channels, (cuuint64_t)src.W * src.H * src.B};
       cuuint64_t gstr2[1] = {(cuuint64_t)src.cstride * 2};

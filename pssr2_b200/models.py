@@ -292,9 +292,9 @@ class ResUNet(_PlanModule):
         bn = self.norm
         sc = (bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + bn.eps)).contiguous()
         sh = (bn.bias.detach().float() - bn.running_mean.float() * sc).contiguous()
-        im2col = z(B, H, W, 64)
+        im2col = z(B, H, W, 16 if C * 9 <= 16 else 64)      # narrow im2col: the convs' TMA boxes zero-fill channels >= 16
         plan.prep(x_in, sc, sh, im2col)
-        xcol = View(im2col, 0, 64)
+        xcol = View(im2col)
 
         # level l lives at H/2^l; cat[l] = [pixel_shuffle(decoder input), encoder skip l]
         up = [hid[l + 1] // 4 for l in range(L - 1)]
@@ -513,9 +513,9 @@ class RDResUNet(_PlanModule):
         bn = self.norm
         sc = (bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + bn.eps)).contiguous()
         sh = (bn.bias.detach().float() - bn.running_mean.float() * sc).contiguous()
-        im2col = z(B, H, W, 64)
+        im2col = z(B, H, W, 16 if C * 9 <= 16 else 64)      # narrow im2col: the convs' TMA boxes zero-fill channels >= 16
         plan.prep(x_in, sc, sh, im2col)
-        xcol = View(im2col, 0, 64)
+        xcol = View(im2col)
 
         # ---- encoder geometry: which stage outputs are decoder skips, and where they live -----------------
         n_st = len(enc.dense_stages)

@@ -143,7 +143,8 @@ class Plan:
     def prep(self, x, scale, shift, im2col, xnorm=None):
         B, C, H, W = x.shape
         d = PrepDesc(x.data_ptr(), 1 if x.dtype == torch.uint8 else 0, B, C, H, W, scale.data_ptr(), shift.data_ptr(),
-                     im2col.data_ptr(), xnorm.data_ptr() if xnorm is not None else None)
+                     im2col.data_ptr(), xnorm.data_ptr() if xnorm is not None else None, im2col.shape[3], 0)
+        assert im2col.shape[3] in (16, 64) and C * 9 <= im2col.shape[3]
         op = Op()
         op.kind = OP_PREP
         op.u.prep = d
