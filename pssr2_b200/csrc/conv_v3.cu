@@ -1192,7 +1192,17 @@ bool v3_supported(const pssr_conv_desc_t& d) {
   return true;
 }
 
+static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, bool force_flat);
+
 int v3_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
+  // rows mode keeps ALL source planes of T+2 image rows in shared memory; layers with many planes (e.g. a 3x3 over 128 channels
+  // plus a 1x1 over 192 at width 128: 5 planes, 81 KB per row) do not fit and run in flat mode, which stages one plane at a time
+  int rc = v3_prepare_impl(d, dtype, op, false);
+  if (rc == PSSR_EUNSUP && d.Wo % 128 == 0 && d.tail_layout != PSSR_TAIL_WINDOW48) rc = v3_prepare_impl(d, dtype, op, true);
+  return rc;
+}
+
+static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, bool force_flat) {
   EncodeTiledFn enc = v3_encode_fn();
   PSSR_REQUIRE(enc != nullptr, PSSR_ECUDA, "cuTensorMapEncodeTiled entry point not available");
   PSSR_REQUIRE(d.n_srcs >= 1 && d.n_srcs <= 3 && d.n_segs >= 1 && d.n_segs <= 4, PSSR_EINVAL, "conv: n_srcs/n_segs out of range");
@@ -1229,7 +1239,7 @@ int v3_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
     if (d.segs[s2].taps == 9) p.pad = 1;
   p.NJ = (d.Wo + 127) / 128;
   p.Wb = (d.Wo + p.NJ - 1) / p.NJ;
-  p.rows_mode = (p.pad && d.Wo % 128 == 0 && getenv("PSSR_V3_FLAT") == nullptr) ? 1 : 0;
+  p.rows_mode = (p.pad && d.Wo % 128 == 0 && !force_flat && getenv("PSSR_V3_FLAT") == nullptr) ? 1 : 0;
   if (!p.pad) { p.NJ = 1; p.Wb = d.Wo; }
   p.P = p.Wb + 2 * p.pad;
   p.HP = d.Ho + 2 * p.pad;

@@ -30,6 +30,8 @@ struct ResampleTable {
   int2* bounds = nullptr;    // device [out] (xmin, count)
   int32_t* kq = nullptr;     // device [out][ksize] 8 bpc fixed-point coefficients
   double* kd = nullptr;      // device [out][ksize] double coefficients
+  int32_t* ki = nullptr;     // device [out][ksize] k * 2^shift where every coefficient of the output is dyadic, see dshift
+  int32_t* dshift = nullptr; // device [out] shift (0..14), or -1: the output needs the double path
   std::vector<int2> h_bounds;
 };
 
@@ -97,6 +99,32 @@ static int get_table(int in_size, int out_size, const ResampleTable** out) {
   PSSR_CHECK_CUDA(cudaMemcpy(t.bounds, t.h_bounds.data(), sizeof(int2) * out_size, cudaMemcpyHostToDevice));
   PSSR_CHECK_CUDA(cudaMemcpy(t.kq, kq.data(), sizeof(int32_t) * kq.size(), cudaMemcpyHostToDevice));
   PSSR_CHECK_CUDA(cudaMemcpy(t.kd, kk.data(), sizeof(double) * kk.size(), cudaMemcpyHostToDevice));
+  // Integer fast path of the 16-bit (double) resample.  Pillow accumulates pixel * k sequentially in double and takes
+  // (int)(ss + 0.5).  When every coefficient of an output is k = m / 2^s with s <= 14 (integer scales: all interior outputs,
+  // e.g. [1,3,5,7,7,5,3,1]/32), every product and partial sum is an exactly representable dyadic rational (< 2^31 / 2^s,
+  // far inside 53 bits), so  (sum pixel*m + 2^(s-1)) >> s  is the same number bit for bit.  Edge outputs (renormalised by a
+  // non-power-of-two window weight) keep the double path.
+  std::vector<int32_t> ki(kk.size(), 0), dsh(out_size, -1);
+  for (int xx = 0; xx < out_size; ++xx) {
+    for (int sft = 0; sft <= 14; ++sft) {
+      bool ok = true;
+      long long tot = 0;
+      for (int x = 0; x < t.ksize && ok; ++x) {
+        const double v = kk[(size_t)xx * t.ksize + x] * (double)(1 << sft);
+        ok = v == floor(v) && v >= 0.0 && v <= 2147483647.0;
+        tot += (long long)v;
+      }
+      if (ok && tot * 65535ll < (1ll << 31)) {
+        dsh[xx] = sft;
+        for (int x = 0; x < t.ksize; ++x) ki[(size_t)xx * t.ksize + x] = (int32_t)(kk[(size_t)xx * t.ksize + x] * (double)(1 << sft));
+        break;
+      }
+    }
+  }
+  PSSR_CHECK_CUDA(cudaMalloc(&t.ki, sizeof(int32_t) * ki.size()));
+  PSSR_CHECK_CUDA(cudaMalloc(&t.dshift, sizeof(int32_t) * out_size));
+  PSSR_CHECK_CUDA(cudaMemcpy(t.ki, ki.data(), sizeof(int32_t) * ki.size(), cudaMemcpyHostToDevice));
+  PSSR_CHECK_CUDA(cudaMemcpy(t.dshift, dsh.data(), sizeof(int32_t) * out_size, cudaMemcpyHostToDevice));
   auto ins = g_tables.emplace(key, std::move(t));
   *out = &ins.first->second;
   return PSSR_OK;
@@ -259,6 +287,8 @@ struct CrapK {
   const int2* bounds;
   const int32_t* kq;
   const double* kd;
+  const int32_t* ki;
+  const int32_t* dshift;
   StageK stages[4];
   int n_stages, clip_between;
   uint32_t seed_lo, seed_hi;
@@ -278,7 +308,8 @@ __device__ __forceinline__ T load_reflect(const T* frame_base, int sheet_w, int 
   return frame_base[(size_t)(ty + rr) * sheet_w + tx + cc];
 }
 
-template <typename T>
+// KS: compile-time bound of the filter window (9: scales <= 4, 17: scales <= 8; 0: generic loops)
+template <typename T, int KS>
 __global__ void __launch_bounds__(kCrapThreads) crappify_kernel(const CrapK p) {
   extern __shared__ __align__(16) uint8_t csm[];
   const int TL = p.TL;
@@ -375,22 +406,52 @@ __global__ void __launch_bounds__(kCrapThreads) crappify_kernel(const CrapK p) {
 
   // ---- stage 2: horizontal pass, rounded to the image dtype ------------------------------
   const int nx = xx1 - xx0, ny = yy1 - yy0;
-  for (int i = threadIdx.x; i < nrows * nx; i += kCrapThreads) {
-    const int r = i / nx, xo = i - r * nx;
+  if (KS > 0 && (kCrapThreads % nx) == 0) {
+    // a thread keeps one output column for all rows: window bounds and the (integer) coefficients stay in registers
+    const int xo = threadIdx.x % nx;
     const int2 b = p.bounds[xx0 + xo];
-    const T* src = reinterpret_cast<const T*>(raw + (size_t)r * p.raw_pitch + lead[r]) + (b.x - col0);
-    if (sizeof(T) == 1) {
-      const int32_t* k = p.kq + (size_t)(xx0 + xo) * p.ksize;
-      int32_t ss = 1 << (kPrecisionBits - 1);
-      for (int x = 0; x < b.y; ++x) ss += (int32_t)src[x] * __ldg(k + x);
-      ss >>= kPrecisionBits;
-      inter[r * TL + xo] = (T)min(max(ss, 0), 255);
-    } else {
-      const double* k = p.kd + (size_t)(xx0 + xo) * p.ksize;
-      double ss = 0.0;
-      for (int x = 0; x < b.y; ++x) ss = __dadd_rn(ss, __dmul_rn((double)src[x], __ldg(k + x)));
-      const int si = (int)(ss + 0.5);
-      inter[r * TL + xo] = (T)((si & 255) | (min(max(si >> 8, 0), 255) << 8));
+    const int sft = sizeof(T) == 1 ? kPrecisionBits : p.dshift[xx0 + xo];
+    const int32_t* kp = (sizeof(T) == 1 ? p.kq : p.ki) + (size_t)(xx0 + xo) * p.ksize;
+    int32_t kr[KS > 0 ? KS : 1];
+#pragma unroll
+    for (int x = 0; x < KS; ++x) kr[x] = (x < b.y && sft >= 0) ? __ldg(kp + x) : 0;
+    const int32_t half = sft > 0 ? (1 << (sft - 1)) : 0;
+    const int coff = b.x - col0;
+    for (int r = threadIdx.x / nx; r < nrows; r += kCrapThreads / nx) {
+      const T* src = reinterpret_cast<const T*>(raw + (size_t)r * p.raw_pitch + lead[r]) + coff;
+      if (sft >= 0) {
+        int32_t ss = half;
+#pragma unroll
+        for (int x = 0; x < KS; ++x)
+          if (x < b.y) ss += (int32_t)src[x] * kr[x];
+        ss >>= sft;
+        inter[r * TL + xo] = sizeof(T) == 1 ? (T)min(max(ss, 0), 255) : (T)((ss & 255) | (min(max(ss >> 8, 0), 255) << 8));
+      } else {
+        const double* k = p.kd + (size_t)(xx0 + xo) * p.ksize;
+        double ss = 0.0;
+        for (int x = 0; x < b.y; ++x) ss = __dadd_rn(ss, __dmul_rn((double)src[x], __ldg(k + x)));
+        const int si = (int)(ss + 0.5);
+        inter[r * TL + xo] = (T)((si & 255) | (min(max(si >> 8, 0), 255) << 8));
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < nrows * nx; i += kCrapThreads) {
+      const int r = i / nx, xo = i - r * nx;
+      const int2 b = p.bounds[xx0 + xo];
+      const T* src = reinterpret_cast<const T*>(raw + (size_t)r * p.raw_pitch + lead[r]) + (b.x - col0);
+      if (sizeof(T) == 1) {
+        const int32_t* k = p.kq + (size_t)(xx0 + xo) * p.ksize;
+        int32_t ss = 1 << (kPrecisionBits - 1);
+        for (int x = 0; x < b.y; ++x) ss += (int32_t)src[x] * __ldg(k + x);
+        ss >>= kPrecisionBits;
+        inter[r * TL + xo] = (T)min(max(ss, 0), 255);
+      } else {
+        const double* k = p.kd + (size_t)(xx0 + xo) * p.ksize;
+        double ss = 0.0;
+        for (int x = 0; x < b.y; ++x) ss = __dadd_rn(ss, __dmul_rn((double)src[x], __ldg(k + x)));
+        const int si = (int)(ss + 0.5);
+        inter[r * TL + xo] = (T)((si & 255) | (min(max(si >> 8, 0), 255) << 8));
+      }
     }
   }
   __syncthreads();
@@ -409,10 +470,19 @@ __global__ void __launch_bounds__(kCrapThreads) crappify_kernel(const CrapK p) {
       ss >>= kPrecisionBits;
       val = (double)min(max(ss, 0), 255);
     } else {
-      const double* k = p.kd + (size_t)(yy0 + yo) * p.ksize;
-      double ss = 0.0;
-      for (int y = 0; y < b.y; ++y) ss = __dadd_rn(ss, __dmul_rn((double)src[(size_t)y * TL], __ldg(k + y)));
-      const int si = (int)(ss + 0.5);
+      const int sft = p.dshift[yy0 + yo];
+      int si;
+      if (sft >= 0) {
+        const int32_t* k = p.ki + (size_t)(yy0 + yo) * p.ksize;
+        int32_t ss = sft > 0 ? (1 << (sft - 1)) : 0;
+        for (int y = 0; y < b.y; ++y) ss += (int32_t)src[(size_t)y * TL] * __ldg(k + y);
+        si = ss >> sft;
+      } else {
+        const double* k = p.kd + (size_t)(yy0 + yo) * p.ksize;
+        double ss = 0.0;
+        for (int y = 0; y < b.y; ++y) ss = __dadd_rn(ss, __dmul_rn((double)src[(size_t)y * TL], __ldg(k + y)));
+        si = (int)(ss + 0.5);
+      }
       val = (double)((si & 255) | (min(max(si >> 8, 0), 255) << 8));
     }
     // `.astype(np.float32)`: exact for values <= 65535 (data.py:483)
@@ -563,7 +633,7 @@ extern "C" int pssr_crappify(const pssr_crappify_args_t* a, void* stream) {
     }
     p.max_rows = max_span;
     p.raw_pitch = ((max_span * a->elem_bytes + 15 + 15) / 16) * 16;  // + worst-case 15-byte lead
-    p.bounds = tab->bounds; p.kq = tab->kq; p.kd = tab->kd;
+    p.bounds = tab->bounds; p.kq = tab->kq; p.kd = tab->kd; p.ki = tab->ki; p.dshift = tab->dshift;
     p.n_stages = a->n_stages;
     p.clip_between = a->clip_between;
     for (int s = 0; s < a->n_stages; ++s) {
@@ -582,15 +652,19 @@ extern "C" int pssr_crappify(const pssr_crappify_args_t* a, void* stream) {
     PSSR_REQUIRE(smem <= 200 * 1024, PSSR_EUNSUP, "crappify: staging needs %zu bytes of shared memory (scale %d too large)", smem, a->lr_scale);
     const long long blocks = (long long)a->n_tiles * a->lr_frames * p.tiles_per_side * p.tiles_per_side;
     PSSR_REQUIRE(blocks < (1ll << 31), PSSR_EUNSUP, "crappify: too many blocks");
+    const int ks = getenv("PSSR_CRAP_GENERIC") != nullptr ? 0 : (p.ksize <= 9 ? 9 : (p.ksize <= 17 ? 17 : 0));
+#define PSSR_CRAP_LAUNCH(TT, KK)                                                                                              \
+  do {                                                                                                                        \
+    static bool attr = false;                                                                                                 \
+    if (!attr) { PSSR_CHECK_CUDA(cudaFuncSetAttribute(crappify_kernel<TT, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; } \
+    crappify_kernel<TT, KK><<<(unsigned)blocks, kCrapThreads, smem, st>>>(p);                                                 \
+  } while (0)
     if (a->elem_bytes == 1) {
-      static bool attr1 = false;
-      if (!attr1) { PSSR_CHECK_CUDA(cudaFuncSetAttribute(crappify_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr1 = true; }
-      crappify_kernel<uint8_t><<<(unsigned)blocks, kCrapThreads, smem, st>>>(p);
+      if (ks == 9) PSSR_CRAP_LAUNCH(uint8_t, 9); else if (ks == 17) PSSR_CRAP_LAUNCH(uint8_t, 17); else PSSR_CRAP_LAUNCH(uint8_t, 0);
     } else {
-      static bool attr2 = false;
-      if (!attr2) { PSSR_CHECK_CUDA(cudaFuncSetAttribute(crappify_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr2 = true; }
-      crappify_kernel<uint16_t><<<(unsigned)blocks, kCrapThreads, smem, st>>>(p);
+      if (ks == 9) PSSR_CRAP_LAUNCH(uint16_t, 9); else if (ks == 17) PSSR_CRAP_LAUNCH(uint16_t, 17); else PSSR_CRAP_LAUNCH(uint16_t, 0);
     }
+#undef PSSR_CRAP_LAUNCH
     count_launch();
     PSSR_CHECK_CUDA(cudaGetLastError());
   }

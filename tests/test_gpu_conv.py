@@ -51,6 +51,12 @@ CASES = [
     (8, 64, 64, 64, 64, 1, "bf16"),      # 256 tiles > 148 SMs: persistent loop + TMEM double buffering
     (2, 32, 32, 64, 64, 1, "fp16"),
     (2, 16, 16, 128, 256, 2, "fp16"),
+    # rows mode (W % 128 == 0): row ring, CTA pairs, TMA-store epilogue
+    (2, 8, 128, 64, 64, 1, "fp16"),      # one plane, resident weights, deep ring
+    (3, 6, 128, 96, 64, 1, "fp16"),      # two planes (ragged K), odd number of row groups per pair
+    (1, 5, 256, 64, 64, 1, "bf16"),      # two 128-pixel segments per image row, odd height (T falls back to 1)
+    (1, 4, 128, 64, 256, 2, "fp16"),     # pixel shuffle from rows mode (direct stores)
+    (2, 130, 128, 64, 64, 1, "fp16"),    # more row groups than workers: persistent walk across images
 ]
 
 
@@ -79,12 +85,15 @@ def test_conv3x3(B, H, W, Cin, Cout, shuffle, prec):
     assert bool((out[..., :8].float() == 7.0).all()), "conv wrote outside its channel slice"
 
 
-def test_conv_residual_two_sources():
+@pytest.mark.parametrize("B,H,W,C,Cx", [(2, 16, 16, 128, 192),
+                                       (2, 9, 128, 64, 96),      # rows mode, 3 planes: shallow ring, filter-row-major K order
+                                       (1, 6, 128, 128, 192),    # 5 planes at width 128: the row ring does not fit -> flat mode
+                                       (2, 40, 64, 64, 96)])     # flat mode with a respass segment
+def test_conv_residual_two_sources(B, H, W, C, Cx):
     """relu(conv3x3(h) + conv1x1(x) + bias): the fused ResBlock tail (pssr/models/_blocks.py:39-41)."""
     P = _setup()
     plan = P.Plan("bf16")
     dt = plan.tdtype
-    B, H, W, C, Cx = 2, 16, 16, 128, 192
     h = _rand_act(B, H, W, C, dt, 3)
     xbuf = _rand_act(B, H, W, Cx + 64, dt, 4)          # x is a channel slice [64, 64+Cx) of a wider buffer
     g = torch.Generator(device="cuda").manual_seed(5)
@@ -93,12 +102,42 @@ def test_conv_residual_two_sources():
     b = torch.randn(C, device="cuda", generator=g)
     wp = P.pack_weight([w3, w1], plan.dtype)
     out = torch.zeros(B, H, W, C, dtype=dt, device="cuda")
-    plan.conv([P.View(h), P.View(xbuf, 64, Cx)], [(0, 9, 2), (1, 1, 3)], wp, b, P.View(out), Ho=H, Wo=W, B=B, act=P.ACT_RELU)
+    plan.conv([P.View(h), P.View(xbuf, 64, Cx)], [(0, 9, P.ceil_div(C, 64)), (1, 1, P.ceil_div(Cx, 64))], wp, b, P.View(out), Ho=H, Wo=W,
+              B=B, act=P.ACT_RELU)
     plan.finalize()
     plan.run()
     torch.cuda.synchronize()
     ref = F.relu(F.conv2d(_nchw(h), w3.to(dt).float(), None, padding=1) + F.conv2d(_nchw(xbuf[..., 64:]), w1.to(dt).float(), b))
     _check(_nchw(out), ref, "bf16", "conv+respass")
+
+
+@pytest.mark.parametrize("H,W", [(7, 128), (12, 64)])
+def test_conv_narrow_im2col_source(H, W):
+    """3x3 over 64 channels + 1x1 over the 16-channel im2col of a 1-channel input (the ResUNet input skip, resunet.py:90):
+    rows mode stages the narrow source as a K = 16 SWIZZLE_32B plane, flat mode zero-fills channels 16..63 in the TMA box."""
+    P = _setup()
+    plan = P.Plan("fp16")
+    dt = plan.tdtype
+    B, C = 2, 64
+    h = _rand_act(B, H, W, C, dt, 11)
+    g = torch.Generator(device="cuda").manual_seed(12)
+    x = torch.randint(0, 256, (B, 1, H, W), device="cuda", generator=g).float()
+    sc, sh = torch.tensor([0.9], device="cuda"), torch.tensor([0.1], device="cuda")
+    im2col = torch.zeros(B, H, W, 16, dtype=dt, device="cuda")
+    plan.prep(x, sc, sh, im2col)
+    w3 = torch.randn(C, C, 3, 3, device="cuda", generator=g) / (3.0 * C ** 0.5)
+    wx = torch.randn(C, 1, 3, 3, device="cuda", generator=g) / 3.0
+    b = torch.randn(C, device="cuda", generator=g)
+    from pssr2_b200.models import _im2col_parts
+    wp = P.pack_weight([w3, _im2col_parts(wx)], plan.dtype)
+    out = torch.zeros(B, H, W, C, dtype=dt, device="cuda")
+    plan.conv([P.View(h), P.View(im2col)], [(0, 9, 1), (1, 1, 1)], wp, b, P.View(out), Ho=H, Wo=W, B=B, act=P.ACT_RELU)
+    plan.finalize()
+    plan.run()
+    torch.cuda.synchronize()
+    xn = ((x / 128 - 1) * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)).to(dt).float()
+    ref = F.relu(F.conv2d(_nchw(h), w3.to(dt).float(), None, padding=1) + F.conv2d(xn, wx.to(dt).float(), b, padding=1))
+    _check(_nchw(out), ref, "fp16", f"conv + narrow im2col skip {H}x{W}")
 
 
 def test_prep_pool_tail():
