@@ -49,6 +49,15 @@ struct V3Params {
   int seg_k16[4];             // rows mode: the segment's source is a 16-channel tensor staged as a narrow plane (one K = 16 MMA)
   uint32_t ring_bytes;        // rows mode: ring_R * group_bytes rounded up to 1024
   int q_begin, q_end;         // flat mode
+  // cols mode (small feature maps, W % 8 == 0, W < 32): a tile = 16 groups of 8 pixels = cR image rows x 8 columns of cG images
+  // (16x16 maps: 16 rows of one image half; 8x8 maps: 8 rows of two images, rows interleaved).  One TMA box {64 ch, 10 px, cG,
+  // cR+2 rows} stages the tile with its halo; the 8-pixel groups sit 10 pixels apart, so the UMMA descriptors use a 1280-byte
+  // group stride and NO padded pixel is multiplied (flat mode wastes 21 % / 36 % of the MMAs at 16^2 / 8^2).
+  int cols_mode, cR, cG, c_strips, c_yblocks, tiles_total;
+  uint32_t tile_bytes;        // cols mode: staged bytes per tile (box bytes rounded up to 1024)
+  uint32_t box_bytes;         // cols mode: bytes one tile box transfers
+  uint32_t dy_units;          // descriptor units (16 B) between consecutive filter rows of the staged A operand
+  uint32_t a_sbo;             // byte stride between 8-row groups of the A operand (1024; 1280 in cols mode)
   int off_px;                 // pixel offset of a unit's first pixel inside an A stage buffer
   uint32_t tile_step;         // descriptor units (16 B) between the A operands of consecutive tiles of a unit
   uint32_t a_bytes, a_tx_bytes, b_bytes, tap_bytes;
@@ -387,7 +396,9 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
           const int um = unit / p.n_tiles;
           int qa = 0, r0 = 0, nrows = 0;
           uint32_t tx = 0;
-          if (p.pad) {
+          if (p.cols_mode) {
+            tx = (uint32_t)T * p.box_bytes * C;
+          } else if (p.pad) {
 #pragma unroll
             for (int rk = 0; rk < C; ++rk) {        // row range of each CTA of the pair (the leader needs both byte counts)
               const int qa_r = p.q_begin + (um * C + rk) * (128 * T);
@@ -410,7 +421,20 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
               const uint32_t dst0 = a_base + (uint32_t)as * p.a_bytes;
               const uint32_t fbar = PAIR ? v3_mapa(a_full(as), 0) : a_full(as);
               if (rank == 0) mbar_arrive_expect_tx(a_full(as), tx);
-              if (p.pad) {
+              if (p.cols_mode) {
+                for (int mt = 0; mt < T; ++mt) {
+                  int t = (um * C + (int)rank) * T + mt;
+                  if (t >= p.tiles_total) t = p.tiles_total - 1;       // overhanging tiles re-read the last one; the epilogue drops them
+                  const int sx = t % p.c_strips;
+                  const int t2 = t / p.c_strips;
+                  const int yb = t2 % p.c_yblocks;
+                  const int ng = t2 / p.c_yblocks;
+                  const uint32_t dst = dst0 + (uint32_t)mt * p.tile_bytes;
+                  // tensor map dims: (channel, x, image, y)
+                  if (PAIR) v3_tma_4d_pair(dst, tm, fbar, cb * 64, sx * 8 - 1, ng * p.cG, yb * p.cR - 1);
+                  else tma_load_4d(dst, tm, fbar, cb * 64, sx * 8 - 1, ng * p.cG, yb * p.cR - 1);
+                }
+              } else if (p.pad) {
                 for (int r = 0; r < nrows; ++r) {
                   const int rho = r0 + r;
                   const int v = rho / p.HP;
@@ -486,11 +510,11 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
     const uint32_t idesc = umma_idesc_f16(p.fp16 ? 0 : 1, block_n) + (PAIR ? (8u << 24) : 0u);
     const uint32_t idesc_tail = umma_idesc_f16(p.fp16 ? 0 : 1, 16) + (PAIR ? (8u << 24) : 0u);
     const uint64_t tdesc = v3_desc(smem_base + tailw_off);
-    const uint64_t adesc_s0 = v3_desc(a_base + (uint32_t)p.off_px * 128u);
+    const uint64_t adesc_s0 = v3_desc(a_base + (uint32_t)p.off_px * 128u) + ((uint64_t)((p.a_sbo - 1024u) >> 4) << 32);
     const uint64_t adesc_s1 = adesc_s0 + (uint64_t)(p.a_bytes >> 4);
     const uint64_t bdesc0 = v3_desc(b_base);
     const uint32_t bstep = p.b_bytes >> 4, tapstep = p.tap_bytes >> 4;
-    const int64_t P8 = (int64_t)p.P * 8;
+    const int64_t P8 = (int64_t)p.dy_units;
     const uint64_t tile_step = p.tile_step;
     const uint64_t slot_desc = (uint64_t)(p.slot_bytes >> 4);
     const uint64_t slot16_desc = (uint64_t)(p.slot16_bytes >> 4);
@@ -954,6 +978,18 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
           bool valid;
           if (ROWS) {
             n = gn; y = gy0 + mt; x = gx0 + row; valid = gvalid;
+          } else if (p.cols_mode) {
+            const int t = um * T + mt;
+            const int sx = t % p.c_strips;
+            const int t2 = t / p.c_strips;
+            const int yb = t2 % p.c_yblocks;
+            const int ng = t2 / p.c_yblocks;
+            const int g = row >> 3;
+            const int rr = p.cG == 2 ? (g >> 1) : g, img = p.cG == 2 ? (g & 1) : 0;
+            n = ng * p.cG + img;
+            y = yb * p.cR + rr;
+            x = sx * 8 + (row & 7);
+            valid = t < p.tiles_total && n < p.B;
           } else if (p.pad) {
             const int q = p.q_begin + (um * T + mt) * 128 + row;
             const int vimg = q / p.IP;
@@ -1175,6 +1211,22 @@ struct V3Variant { int T, G, RES, TAIL, PAIR, ROWS; V3Kernel fn; };
 static const V3Variant kV3Variants[] = {V3_VARIANTS_PR(0, 0), V3_VARIANTS_PR(1, 0), V3_VARIANTS_PR(0, 1), V3_VARIANTS_PR(1, 1)};
 static const int kV3NumVariants = (int)(sizeof(kV3Variants) / sizeof(kV3Variants[0]));
 
+// cols mode applies to 3x3 layers on small maps that split into 16 groups of 8 pixels: H % 16 == 0 (16 rows x 8 columns of one
+// image) or H == 8 (8 rows x 8 columns of two images)
+static bool v3_cols_geometry(const pssr_conv_desc_t& d, int* cR, int* cG) {
+  if (getenv("PSSR_V3_NO_COLS") != nullptr) return false;
+  bool any9 = false;
+  for (int s = 0; s < d.n_segs; ++s) any9 = any9 || d.segs[s].taps == 9;
+  if (!any9 || d.tail_z != nullptr || d.Wo >= 32 || d.Wo % 8 != 0) return false;
+  int r, g;
+  if (d.Ho % 16 == 0) { r = 16; g = 1; }
+  else if (d.Ho == 8) { r = 8; g = 2; }
+  else return false;
+  if (cR) *cR = r;
+  if (cG) *cG = g;
+  return true;
+}
+
 bool v3_supported(const pssr_conv_desc_t& d) {
   if (getenv("PSSR_CONV_V1") != nullptr || getenv("PSSR_CONV_V2") != nullptr) return false;
   for (int s = 0; s < d.n_segs; ++s)
@@ -1184,7 +1236,8 @@ bool v3_supported(const pssr_conv_desc_t& d) {
   for (int s = 0; s < d.n_segs; ++s) any9 = any9 || d.segs[s].taps == 9;
   // small feature maps: the padded pixel space wastes (1 - HW/((H+2)(W+2))) of the MMAs (36 % at 8x8, 21 % at 16x16)
   // and the exact-tile kernel (conv_igemm.cu) is faster there
-  if (any9 && d.Wo < 32 && d.tail_z == nullptr && getenv("PSSR_V3_SMALL") == nullptr) return false;
+  // ... unless the map tiles exactly into 8-pixel column groups (cols mode, v3_cols_geometry)
+  if (any9 && d.Wo < 32 && d.tail_z == nullptr && getenv("PSSR_V3_SMALL") == nullptr && !v3_cols_geometry(d, nullptr, nullptr)) return false;
   if (d.tail_z != nullptr) {
     const int cps = d.n_valid / (d.shuffle * d.shuffle);
     if (cps != 64 || d.n % 256 != 0 || !any9) return false;   // other tail shapes: v2's CUDA-core tail
@@ -1240,6 +1293,14 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
   p.NJ = (d.Wo + 127) / 128;
   p.Wb = (d.Wo + p.NJ - 1) / p.NJ;
   p.rows_mode = (p.pad && d.Wo % 128 == 0 && !force_flat && getenv("PSSR_V3_FLAT") == nullptr) ? 1 : 0;
+  p.cols_mode = (p.pad && v3_cols_geometry(d, &p.cR, &p.cG)) ? 1 : 0;
+  if (p.cols_mode) {
+    p.c_strips = d.Wo / 8;
+    p.c_yblocks = d.Ho / p.cR;
+    p.tiles_total = ((d.B + p.cG - 1) / p.cG) * p.c_yblocks * p.c_strips;
+    p.box_bytes = (uint32_t)(128 * 10 * p.cG * (p.cR + 2));
+    p.tile_bytes = ((p.box_bytes + 1023u) / 1024u) * 1024u;
+  }
   if (!p.pad) { p.NJ = 1; p.Wb = d.Wo; }
   p.P = p.Wb + 2 * p.pad;
   p.HP = d.Ho + 2 * p.pad;
@@ -1317,7 +1378,7 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
     if (p.rows_mode) {
       a_min = (long long)(deep ? 2 * Tc + 2 : Tc + 2) * p.group_bytes;      // deep: the current group and one group of prefetch
     } else {
-      const long long a_raw = p.pad ? (long long)(128 * Tc + 4 * p.P + 1) * 128 : 128LL * Tc * 128;
+      const long long a_raw = p.cols_mode ? (long long)Tc * p.tile_bytes : (p.pad ? (long long)(128 * Tc + 4 * p.P + 1) * 128 : 128LL * Tc * 128);
       ab = ((a_raw + 1023) / 1024) * 1024;
       a_min = 2 * ab;
     }
@@ -1382,7 +1443,11 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
   } else {
     p.a_bytes = (uint32_t)a_bytes;
     a_total = 2 * a_bytes;
-    if (p.pad) {
+    if (p.cols_mode) {
+      p.off_px = p.cG * 10 + 1;                       // staged (row 0, pixel 0) of the tile: one halo row of all cG images + one halo pixel
+      p.tile_step = p.tile_bytes >> 4;
+      p.units_m = (p.tiles_total + T * C - 1) / (T * C);
+    } else if (p.pad) {
       p.off_px = 2 * p.P + 1;
       p.tile_step = 1024;
       p.units_m = (p.q_end - p.q_begin + 128 * T * C - 1) / (128 * T * C);
@@ -1393,6 +1458,8 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
     }
   }
   p.total_units = p.units_m * p.n_tiles;
+  p.dy_units = p.cols_mode ? (uint32_t)(p.cG * 10 * 8) : (uint32_t)(p.P * 8);
+  p.a_sbo = p.cols_mode ? 1280u : 1024u;
   const char* envd = getenv("PSSR_DBG");
   p.dbg = envd ? atoi(envd) : 0;
 
@@ -1403,7 +1470,15 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
     PSSR_REQUIRE(src.cstride % 8 == 0 && src.channels >= 1 && src.channels <= src.cstride, PSSR_EUNSUP, "conv: source %d bad channel stride", s);
     PSSR_REQUIRE(src.H == d.Ho && src.W == d.Wo && src.B == d.B, PSSR_EINVAL, "conv: source %d geometry does not match the output", s);
     CUresult r;
-    if (p.pad) {
+    if (p.cols_mode) {
+      // dims (channel, x, image, y): the box lands as [y][image][x][channel], rows of the cG images interleaved
+      cuuint64_t gdim[4] = {(cuuint64_t)src.channels, (cuuint64_t)src.W, (cuuint64_t)src.B, (cuuint64_t)src.H};
+      cuuint64_t gstr[3] = {(cuuint64_t)src.cstride * 2, (cuuint64_t)src.cstride * 2 * src.W * src.H, (cuuint64_t)src.cstride * 2 * src.W};
+      cuuint32_t box[4] = {64, 10, (cuuint32_t)p.cG, (cuuint32_t)(p.cR + 2)};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      r = enc(&op.tmaps[s], tdt, 4, const_cast<void*>(src.base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else if (p.pad) {
       cuuint64_t gdim[4] = {(cuuint64_t)src.channels, (cuuint64_t)src.W, (cuuint64_t)src.H, (cuuint64_t)src.B};
       cuuint64_t gstr[3] = {(cuuint64_t)src.cstride * 2, (cuuint64_t)src.cstride * 2 * src.W, (cuuint64_t)src.cstride * 2 * src.W * src.H};
       cuuint32_t box[4] = {src_k16[s] ? 16u : 64u, (cuuint32_t)p.P, 1, 1};
@@ -1498,8 +1573,8 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
     attr_set = true;
   }
   if (getenv("PSSR_V3_VERBOSE") != nullptr)
-    fprintf(stderr, "v3: %dx%d n=%d kb=%d block_n=%d T=%d G=%d RES=%d TAIL=%d PAIR=%d rows=%d/%d ring=%d b_stages=%d a_bytes=%u smem=%d units=%d grid=%d\n",
-            d.Ho, d.Wo, d.n, num_kb, block_n, T, G, RES, (int)tail, PAIR, p.rows_mode, p.row_major, p.ring_R, b_stages, p.a_bytes, op.smem_bytes, p.total_units,
+    fprintf(stderr, "v3: %dx%d n=%d kb=%d block_n=%d T=%d G=%d RES=%d TAIL=%d PAIR=%d rows=%d/%d cols=%d ring=%d b_stages=%d a_bytes=%u smem=%d units=%d grid=%d\n",
+            d.Ho, d.Wo, d.n, num_kb, block_n, T, G, RES, (int)tail, PAIR, p.rows_mode, p.row_major, p.cols_mode, p.ring_R, b_stages, p.a_bytes, op.smem_bytes, p.total_units,
             op.grid);
   return PSSR_OK;
 }
