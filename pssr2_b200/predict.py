@@ -86,7 +86,10 @@ def predict_images(model: nn.Module, dataset, device: str = "cuda", batch_size=N
     model.eval()
 
     val_idx = list(dataset.val_idx)
-    lo, hi = D.shard_range(len(val_idx))
+    # `dataset.rank_local = True`: the dataset already holds only this rank's share (pre-sharded ingest, weak scaling): no
+    # sharding of val_idx and no gather -- every rank returns / writes its own images
+    rank_local = bool(getattr(dataset, "rank_local", False))
+    lo, hi = (0, len(val_idx)) if rank_local else D.shard_range(len(val_idx))
     outs = {}
     dev = torch.device(device)
     cur = torch.cuda.current_stream(dev)
@@ -136,7 +139,7 @@ def predict_images(model: nn.Module, dataset, device: str = "cuda", batch_size=N
         if pending is not None:
             finish(pending)
     if out_dir is None:
-        return D.gather_dict(outs)
+        return outs if rank_local else D.gather_dict(outs)
 
 
 def test_metrics(model: nn.Module, dataset, device: str = "cuda", metrics=["mse", "pixel", "psnr", "ssim"], avg: bool = True,
