@@ -322,6 +322,44 @@ def run_ours(args):
                     "traffic": RECON_DRAM_BYTES, "traffic_source": RECON_DRAM_SOURCE},
                 "step_frac_of_peak": round(ALG_FLOPS_PER_TILE * BATCH / (ms_step * 1e-3) / 1e12 / peak_sus, 4)}
 
+    # ---- the HBM-side kernel families (crappify / tail gather / metrics / stitch), timed alone with CUDA events ---------
+    # algorithmic bytes: DESIGN.md section 3 (every input byte read once + every output byte written once); peak = measured copy
+    def ev_ms(fn, reps=10):
+        for _ in range(3):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for k in range(reps):
+            fn(k)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    lr_b, _, hr8_b = ops.crappify(tables[0], TILE, SCALE, specs, clip_between=True, seed=1, want_hr_u8=True)
+    _, out8_b = model.forward_u8(lr_b)
+    out8_b = out8_b.clone()
+    n_px = BATCH * TILE * TILE
+    lr_px = n_px // (SCALE * SCALE)
+    t_crap = ev_ms(lambda k=0: ops.crappify(tables[k % NB], TILE, SCALE, specs, clip_between=True, seed=k, want_hr_u8=True))
+    t_met = ev_ms(lambda k=0: ops.metric_sums(hr8_b[:, 0], out8_b[:, 0]))
+    t_stitch = ev_ms(lambda k=0: ops.stitch(out8_b[:, 0], 8, 8, 128, 32))
+    tail_ms = sum(t for t, (kind, _) in zip(acc, plan.records) if kind == "tailsum")
+    zbytes = sum(r["z"].numel() * 4 for kind, r in plan.records if kind == "tailsum")
+
+    def hbm(ms, nbytes, what):
+        return {"ms": round(ms, 4), "algorithmic_bytes": int(nbytes), "achieved_gbs": round(nbytes / (ms * 1e-3) / 1e9, 1),
+                "frac_of_hbm_peak": round(nbytes / (ms * 1e-3) / 1e9 / peak_hbm, 4), "what": what}
+
+    hbm_kernels = {
+        "peak_gbs": peak_hbm, "peak_source": peak_src,
+        "crappify": hbm(t_crap, n_px * 2 + lr_px * 4 + n_px, "64 uint16 HR tiles 512^2 read, float32 LR + uint8 HR written; Poisson+Gaussian Philox "
+                                                                 "noise (bound by integer ALU / RNG, DESIGN 3.4)"),
+        "tailsum": hbm(tail_ms, zbytes + n_px * 5, "window sums read once, fp32 + uint8 prediction written"),
+        "metric_sums": hbm(t_met, n_px * 2, "two uint8 images read; SSIM window arithmetic bound (DESIGN 3.6)"),
+        "stitch": hbm(t_stitch, n_px + (8 * 384 + 128) ** 2, "64 uint8 tiles 512^2 (8x8 grid, overlap 128, margin 32) -> 3200^2 sheet"),
+    }
+
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ------------------------
     if world == 1:
         cpu_mp, cpu_dt, threads = _cpu_reference_steps(2, 1, 2)
@@ -341,7 +379,7 @@ def run_ours(args):
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "ImageDataset(pinned host stacks, one per step) + one predict_images(batch_size=64, out_dir=None) call over all steps"
                            + (" per rank (rank_local datasets: no gather)" if world > 1 else "")},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "hbm_kernels": hbm_kernels, "cpu_baseline": cpu,
             "metric_check": {"mean_psnr_db": None}}
     s = [float(sums[0].sum()), float(sums[1].sum()), float(n_scored[0])]
     mse = float(s[0]) / max(float(s[2]), 1) / (TILE * TILE)

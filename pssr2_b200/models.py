@@ -136,12 +136,13 @@ class _PlanModule(nn.Module):
         return st["out"], st["out_u8"]
 
     # helpers used by subclasses ---------------------------------------------------------
-    def _emit_reconstruction(self, plan, final, xcol, B, H, W, dev):
+    def _emit_reconstruction(self, plan, final, xcol, B, H, W, dev, out=None, out_u8=None, zbuf=None):
         """Reconstruction (resunet.py:90-95, _blocks.py:15-18): cat([x, xnorm]) -> pre -> relu -> shuffle(s) -> conv -> *128+128."""
         dt = plan.tdtype
         z = lambda *sh: torch.zeros(*sh, dtype=dt, device=dev)
         s = self.scale
         hid0 = final.shape[3]
+        self._zbuf = None
         rec = self.reconstruction
         wp = rec.pre.weight.detach().float()
         bp = rec.pre.bias.detach().float()
@@ -150,8 +151,9 @@ class _PlanModule(nn.Module):
         wc = rec.conv.weight.detach().float()
         bc = rec.conv.bias.detach().float().contiguous()
         cout = wc.shape[0]
-        out = torch.empty(B, cout, H * s, W * s, dtype=torch.float32, device=dev)
-        out_u8 = torch.empty(B, 1, H * s, W * s, dtype=torch.uint8, device=dev)
+        if out is None:
+            out = torch.empty(B, cout, H * s, W * s, dtype=torch.float32, device=dev)
+            out_u8 = torch.empty(B, 1, H * s, W * s, dtype=torch.uint8, device=dev)
         srcs, segs = [View(final), xcol], [(0, 9, ceil_div(hid0, 64)), (1, 1, 1)]
         plan.flops += 2 * wp.numel() * B * H * W + 2 * wc.numel() * B * H * s * W * s
         if cout == 1 and hid0 % 32 == 0 and W >= 1 and self.fuse_tail:
@@ -163,10 +165,14 @@ class _PlanModule(nn.Module):
             import os
             win48 = 1 if (s == 4 and hid0 == 64 and W % 128 == 0 and not any(os.environ.get(k) for k in (
                 "PSSR_TAIL_TAPS", "PSSR_V3_FLAT", "PSSR_CONV_V1", "PSSR_CONV_V2"))) else 0
-            zbuf = torch.zeros(B, H, 48 if win48 else s * s * 9, W, dtype=torch.float32, device=dev)
+            if zbuf is None:
+                zbuf = torch.zeros(B, H, 48 if win48 else s * s * 9, W, dtype=torch.float32, device=dev)
+            zbuf = zbuf[:B]
+            assert zbuf.shape == (B, H, 48 if win48 else s * s * 9, W)
             plan.conv(srcs, segs, wpk, permute_n(bp, s).contiguous(), None, Ho=H, Wo=W, B=B, shuffle=s, act=ACT_RELU,
                       tail_weight=tw, tail_z=zbuf, tail_layout=win48)
             plan.tailsum(zbuf, s, float(bc[0]), 128.0, 128.0, out, out_u8, layout=win48)    # x*128+128 (resunet.py:95)
+            self._zbuf = zbuf
         else:
             ps_out = z(B, H * s, W * s, hid0)
             plan.conv(srcs, segs, wpk, permute_n(bp, s).contiguous(), View(ps_out), Ho=H, Wo=W, B=B, shuffle=s, act=ACT_RELU)
@@ -278,6 +284,8 @@ class ResUNet(_PlanModule):
         hid, L, s = self.hidden, len(self.hidden), self.scale
         if C != self.channels[0]:
             raise ValueError(f"expected {self.channels[0]} input channels, got {C}")
+        if L < 2:
+            raise NotImplementedError("ResUNet needs at least two levels (hidden) in the plan builder")
         if H % (1 << (L - 1)) or W % (1 << (L - 1)):
             raise ValueError(f"input size {H}x{W} must be divisible by {1 << (L - 1)}")
         for i in range(1, L):
@@ -293,8 +301,18 @@ class ResUNet(_PlanModule):
         sc = (bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + bn.eps)).contiguous()
         sh = (bn.bias.detach().float() - bn.running_mean.float() * sc).contiguous()
         im2col = z(B, H, W, 16 if C * 9 <= 16 else 64)      # narrow im2col: the convs' TMA boxes zero-fill channels >= 16
-        plan.prep(x_in, sc, sh, im2col)
         xcol = View(im2col)
+        # Optional sub-batches at level 0 (PSSR_SUBBATCH_MB > 0): the level-0 encoder block and the last decoder block +
+        # Reconstruction run chunk by chunk so that a layer finds its input (<= that many MB per tensor) in the 126 MB L2 instead
+        # of HBM.  MEASURED on B200 (batch 64, 128^2): forward 3.27 ms without, 3.38 / 3.50 / 3.86 ms with 64 / 32 / 16 MB chunks --
+        # the extra launches (pipeline fill + drain of a persistent kernel is ~5 us) cost more than the HBM reads they save,
+        # so it is off by default and kept as a measured negative result.
+        import os
+        sub_mb = float(os.environ.get("PSSR_SUBBATCH_MB", "0"))
+        nb = B
+        if sub_mb > 0:
+            nb = max(1, min(B, int(sub_mb * 2 ** 20) // (H * W * hid[0] * 2)))
+        chunks = [(b0, min(b0 + nb, B)) for b0 in range(0, B, nb)]
 
         # level l lives at H/2^l; cat[l] = [pixel_shuffle(decoder input), encoder skip l]
         up = [hid[l + 1] // 4 for l in range(L - 1)]
@@ -320,7 +338,16 @@ class ResUNet(_PlanModule):
                 srcs, segs = [cur], [(0, 9, ceil_div(cin, 64))]
                 w0f = lambda wt: [wt]
                 wrf = (lambda cin: (lambda wt: ([wt], [(0, 1, ceil_div(cin, 64))])))(cin)
-            if l + 1 < L:
+            if l == 0:
+                pooled = z(B, h // 2, w // 2, hid[l])
+                for b0, b1 in chunks:
+                    plan.prep(x_in[b0:b1], sc, sh, im2col[b0:b1])
+                    dst = View(cat[l][b0:b1], up[l], hid[l])
+                    self._emit_resblock(plan, blk, [View(im2col[b0:b1])], segs, w0f, wrf, [sv[:b1 - b0] for sv in scratch(l)], dst, 1,
+                                        b1 - b0, h, w)
+                    plan.maxpool(dst, View(pooled[b0:b1]))
+                cur = View(pooled)
+            elif l + 1 < L:
                 dst = View(cat[l], up[l], hid[l])
                 self._emit_resblock(plan, blk, srcs, segs, w0f, wrf, scratch(l), dst, 1, B, h, w)
                 pooled = z(B, h // 2, w // 2, hid[l])
@@ -331,23 +358,30 @@ class ResUNet(_PlanModule):
                 dst = View(cat[l - 1], 0, up[l - 1])
                 self._emit_resblock(plan, blk, srcs, segs, w0f, wrf, scratch(l), dst, 2, B, h, w)
         # decoder (resunet.py:81-85): block j works at level l = L-2-j on cat[l]
-        final = z(B, H, W, hid[0])
+        final = z(nb, H, W, hid[0])           # one chunk of the last decoder output; every chunk reuses it (stays in L2)
+        cout_final = self.reconstruction.conv.weight.shape[0]
+        out = torch.empty(B, cout_final, H * s, W * s, dtype=torch.float32, device=dev)
+        out_u8 = torch.empty(B, 1, H * s, W * s, dtype=torch.uint8, device=dev)
+        zshared = [None]
         for j in range(L - 1):
             l = L - 2 - j
             blk = self.decoder[j]
             h, w = H >> l, W >> l
             cin = up[l] + hid[l]
-            srcs, segs = [View(cat[l], 0, cin)], [(0, 9, ceil_div(cin, 64))]
+            segs = [(0, 9, ceil_div(cin, 64))]
             w0f = lambda wt: [wt]
             wrf = (lambda cin: (lambda wt: ([wt], [(0, 1, ceil_div(cin, 64))])))(cin)
             if l > 0:
-                dst, shf = View(cat[l - 1], 0, up[l - 1]), 2
+                self._emit_resblock(plan, blk, [View(cat[l], 0, cin)], segs, w0f, wrf, scratch(l), View(cat[l - 1], 0, up[l - 1]), 2, B, h, w)
             else:
-                dst, shf = View(final), 1
-            self._emit_resblock(plan, blk, srcs, segs, w0f, wrf, scratch(l), dst, shf, B, h, w)
+                for b0, b1 in chunks:
+                    fin = final[:b1 - b0]
+                    self._emit_resblock(plan, blk, [View(cat[l][b0:b1], 0, cin)], segs, w0f, wrf, [sv[:b1 - b0] for sv in scratch(l)],
+                                        View(fin), 1, b1 - b0, h, w)
+                    self._emit_reconstruction(plan, fin, View(im2col[b0:b1]), b1 - b0, H, W, dev, out[b0:b1], out_u8[b0:b1],
+                                              zshared[0])
+                    zshared[0] = self._zbuf
 
-        self._emit_reconstruction(plan, final, xcol, B, H, W, dev)
-        out, out_u8 = self._out, self._out_u8
         plan.finalize()
         return {"plan": plan, "x": x_in, "out": out, "out_u8": out_u8}
 
