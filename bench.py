@@ -148,7 +148,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    tiles = 2
+    tiles = 4
     warm = min(args.warmup, 1)
     mp, dt, threads = _cpu_reference_steps(args.steps, warm, tiles)
     sample = f"{tiles} tiles/step x {args.steps} steps of the same workload on the host CPU (oracle port, torch fp32 + NumPy/Pillow-exact)"
@@ -362,9 +362,10 @@ def run_ours(args):
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ------------------------
     if world == 1:
-        cpu_mp, cpu_dt, threads = _cpu_reference_steps(2, 1, 2)
+        cpu_mp, cpu_dt, threads = _cpu_reference_steps(3, 1, 8)
         cpu = {"value": round(cpu_mp, 4), "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "2 steps x 2 tiles of the same workload (oracle port: Pillow-exact resize + NumPy noise + torch fp32 forward + SSIM)"}
+               "sample": "3 steps x 8 tiles of the same workload after 1 warm-up step (oracle port: Pillow-exact resize + NumPy noise + "
+                         "torch fp32 forward + SSIM), %.1f s of CPU work" % (3 * cpu_dt)}
     else:
         cpu = None      # reported at N = 1 only
 

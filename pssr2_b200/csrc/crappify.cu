@@ -158,6 +158,15 @@ __device__ __forceinline__ double u01d(uint32_t hi, uint32_t lo) {
 // distribution is specified, and B200's fp64 transcendental path (log, lgamma) made the fp64 version 90 % of the kernel;
 // the squeeze inequality is evaluated with ~1e-4 absolute error on terms of O(1e3), i.e. it changes the acceptance of a
 // vanishing fraction of borderline draws.  One Philox block feeds two PTRS attempts.
+// log(k!) for integer-valued k >= 0: table below 8, Stirling series above (|error| < 1.3e-8 at k + 1 >= 9) -- lgammaf() costs
+// ~100 instructions and every warp takes the squeeze branch that needs it
+__constant__ float kLogFact[8] = {0.f, 0.f, 0.69314718f, 1.79175947f, 3.17805383f, 4.78749174f, 6.57925121f, 8.52516136f};
+__device__ __forceinline__ float log_factorial(float k) {
+  if (k < 8.f) return kLogFact[(int)k];
+  const float x = k + 1.0f, rx = __frcp_rn(x);
+  return fmaf(x - 0.5f, logf(x), -x) + 0.91893853f + rx * (0.083333333f - 0.0027777778f * rx * rx);
+}
+
 __device__ float poisson_sample_f32(const Philox& ph, uint32_t pix, uint32_t stage, float lam) {
   uint32_t draw = 0;
   if (lam < 10.0f) {
@@ -192,7 +201,7 @@ __device__ float poisson_sample_f32(const Philox& ph, uint32_t pix, uint32_t sta
       const float k = floorf((2.0f * a / us + b) * U + lam + 0.43f);
       if (us >= 0.07f && V <= vr) return k;
       if (k < 0.0f || (us < 0.013f && V > us)) continue;
-      if ((logf(V) + log_invalpha - logf(a / (us * us) + b)) <= (-lam + k * loglam - lgammaf(k + 1.0f))) return k;
+      if ((__logf(V) + log_invalpha - __logf(a / (us * us) + b)) <= (-lam + k * loglam - log_factorial(k))) return k;
     }
   }
 }
@@ -379,12 +388,24 @@ __global__ void __launch_bounds__(kCrapThreads) crappify_kernel(const CrapK p) {
         const int ry = i / groups, g = i - ry * groups;
         const int Y = Y0 + ry, X = X0 + 4 * g;
         const int r = Y - row0;
-        const T* src = reinterpret_cast<const T*>(raw + (size_t)r * p.raw_pitch + lead[r]) + (X - col0);
+        const uint8_t* sb = raw + (size_t)r * p.raw_pitch + lead[r] + (size_t)(X - col0) * sizeof(T);
+        const T* src = reinterpret_cast<const T*>(sb);
         const int cnt = min(4, wown - 4 * g);
         int v[4] = {0, 0, 0, 0};
+        if (cnt == 4 && (reinterpret_cast<uintptr_t>(sb) & 3) == 0) {          // 4 pixels in one / two 32-bit shared-memory reads
+          const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sb);
+          if (sizeof(T) == 1) {
+            const uint32_t w = s32[0];
+            v[0] = w & 255u; v[1] = (w >> 8) & 255u; v[2] = (w >> 16) & 255u; v[3] = w >> 24;
+          } else {
+            const uint32_t w0 = s32[0], w1 = s32[1];
+            v[0] = w0 & 0xffffu; v[1] = w0 >> 16; v[2] = w1 & 0xffffu; v[3] = w1 >> 16;
+          }
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j < cnt) v[j] = (int)src[j];
+          for (int j = 0; j < 4; ++j)
+            if (j < cnt) v[j] = (int)src[j];
+        }
         const size_t o = (size_t)Y * p.hr_res + X;
         if (want_u8) {
           uint8_t* d = p.hr_u8 + (size_t)tile * n_hr + o;

@@ -143,7 +143,12 @@ __global__ void __launch_bounds__(kMetThreads) metric_kernel(const uint8_t* __re
         const int vr = 49 * (H[2][j] + H[3][j]) - sq;
         const double A1 = (double)(2 * s01) + c1, A2 = (double)(2 * cv) + c2;
         const double B1 = (double)sq + c1, B2 = (double)vr + c2;
-        acc += (A1 * A2) / (B1 * B2);
+        // N / D with one float reciprocal and one Newton step in double (relative error ~1e-14) instead of a full IEEE
+        // double division (~20 fp64-pipe instructions): the quotient is a mean over >= 10^5 windows, tolerance 1e-3
+        const double N = A1 * A2, D = B1 * B2;
+        const double r0 = (double)__frcp_rn((float)D);
+        const double r1 = fma(fma(-D, r0, 1.0), r0, r0);
+        acc += N * r1;
       }
     }
   }
