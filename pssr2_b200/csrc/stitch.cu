@@ -5,6 +5,7 @@
 // integer sum / integer count, truncated, equals the reference's float64 quotient truncated to uint8.
 // Inner tiles drop `margin` pixels on interior edges (util.py:131); pixels nobody covers stay 0
 // (count forced to 1, util.py:136).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace pssr {
@@ -41,6 +42,44 @@ __global__ void stitch_kernel(const uint8_t* __restrict__ tiles, uint8_t* __rest
   }
 }
 
+// Vector path (T, step, margin, sheet width all multiples of 4 and 4-byte aligned buffers): every boundary of a kept span is a
+// multiple of 4, so the four pixels of an aligned group share their contributors -- one 32-bit load per contributor, one
+// 32-bit store per group, no per-pixel division (count is 1, 2 or 4 except for overlaps > T/2).
+__global__ void __launch_bounds__(256) stitch_vec4_kernel(const uint8_t* __restrict__ tiles, uint8_t* __restrict__ sheets, int n_rows,
+                                                          int n_cols, int T, int step, int margin, int out_h, int out_w) {
+  const int stack = blockIdx.y;
+  const size_t tile_px = (size_t)T * T;
+  const uint8_t* tb = tiles + (size_t)stack * n_rows * n_cols * tile_px;
+  uint8_t* ob = sheets + (size_t)stack * out_h * out_w;
+  const int G = out_w >> 2;
+  const long long total = (long long)out_h * G;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int Y = (int)(i / G), X = (int)(i - (long long)Y * G) << 2;
+    const int r_lo = Y - T + 1 <= 0 ? 0 : (Y - T + step) / step;
+    const int r_hi = min(Y / step, n_rows - 1);
+    const int c_lo = X - T + 1 <= 0 ? 0 : (X - T + step) / step;
+    const int c_hi = min(X / step, n_cols - 1);
+    int s0 = 0, s1 = 0, s2 = 0, s3 = 0, cnt = 0;
+    for (int r = r_lo; r <= r_hi; ++r) {
+      const int ly = Y - r * step;
+      const int m0 = r != 0 ? margin : 0, m1 = r != n_rows - 1 ? margin : 0;
+      if (ly < m0 || ly >= T - m1) continue;
+      for (int c = c_lo; c <= c_hi; ++c) {
+        const int lx = X - c * step;
+        const int n0 = c != 0 ? margin : 0, n1 = c != n_cols - 1 ? margin : 0;
+        if (lx < n0 || lx >= T - n1) continue;
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(tb + (size_t)(r * n_cols + c) * tile_px + (size_t)ly * T + lx));
+        s0 += w & 255u; s1 += (w >> 8) & 255u; s2 += (w >> 16) & 255u; s3 += w >> 24;
+        ++cnt;
+      }
+    }
+    if (cnt == 2) { s0 >>= 1; s1 >>= 1; s2 >>= 1; s3 >>= 1; }
+    else if (cnt == 4) { s0 >>= 2; s1 >>= 2; s2 >>= 2; s3 >>= 2; }
+    else if (cnt > 1) { s0 /= cnt; s1 /= cnt; s2 /= cnt; s3 /= cnt; }
+    *reinterpret_cast<uint32_t*>(ob + (size_t)Y * out_w + X) = (uint32_t)s0 | ((uint32_t)s1 << 8) | ((uint32_t)s2 << 16) | ((uint32_t)s3 << 24);
+  }
+}
+
 }  // namespace pssr
 
 using namespace pssr;
@@ -55,8 +94,19 @@ extern "C" int pssr_stitch(const uint8_t* tiles, uint8_t* sheets, int32_t n_stac
   const int step = tile - overlap;
   const int out_h = n_rows * step + overlap, out_w = n_cols * step + overlap;
   PSSR_REQUIRE(n_stacks <= 65535 && out_h <= 65535, PSSR_EUNSUP, "stitch: sheet too large for the launch grid");
-  dim3 grid((out_w + 255) / 256, out_h, n_stacks);
-  stitch_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tiles, sheets, n_rows, n_cols, tile, step, margin, out_h, out_w);
+  const bool vec = tile % 4 == 0 && step % 4 == 0 && margin % 4 == 0 && out_w % 4 == 0 &&
+                   (((uintptr_t)tiles | (uintptr_t)sheets) & 3) == 0 && getenv("PSSR_STITCH_SCALAR") == nullptr;
+  if (vec) {
+    const long long total = (long long)out_h * (out_w / 4);
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)device_sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    stitch_vec4_kernel<<<dim3((unsigned)blocks, n_stacks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tiles, sheets, n_rows, n_cols, tile,
+                                                                                                                 step, margin, out_h, out_w);
+  } else {
+    dim3 grid((out_w + 255) / 256, out_h, n_stacks);
+    stitch_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tiles, sheets, n_rows, n_cols, tile, step, margin, out_h, out_w);
+  }
   count_launch();
   PSSR_CHECK_CUDA(cudaGetLastError());
   return PSSR_OK;
