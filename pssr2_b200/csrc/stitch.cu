@@ -45,38 +45,50 @@ __global__ void stitch_kernel(const uint8_t* __restrict__ tiles, uint8_t* __rest
 // Vector path (T, step, margin, sheet width all multiples of 4 and 4-byte aligned buffers): every boundary of a kept span is a
 // multiple of 4, so the four pixels of an aligned group share their contributors -- one 32-bit load per contributor, one
 // 32-bit store per group, no per-pixel division (count is 1, 2 or 4 except for overlaps > T/2).
-__global__ void __launch_bounds__(256) stitch_vec4_kernel(const uint8_t* __restrict__ tiles, uint8_t* __restrict__ sheets, int n_rows,
+__device__ __forceinline__ uint32_t stitch_group(const uint8_t* __restrict__ tb, int n_rows, int n_cols, int T, int step, int margin,
+                                                 size_t tile_px, int Y, int X, int r_lo, int r_hi) {
+  const int c_lo = X - T + 1 <= 0 ? 0 : (X - T + step) / step;
+  const int c_hi = min(X / step, n_cols - 1);
+  int s0 = 0, s1 = 0, s2 = 0, s3 = 0, cnt = 0;
+  for (int r = r_lo; r <= r_hi; ++r) {
+    const int ly = Y - r * step;
+    const int m0 = r != 0 ? margin : 0, m1 = r != n_rows - 1 ? margin : 0;
+    if (ly < m0 || ly >= T - m1) continue;
+    for (int c = c_lo; c <= c_hi; ++c) {
+      const int lx = X - c * step;
+      const int n0 = c != 0 ? margin : 0, n1 = c != n_cols - 1 ? margin : 0;
+      if (lx < n0 || lx >= T - n1) continue;
+      const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(tb + (size_t)(r * n_cols + c) * tile_px + (size_t)ly * T + lx));
+      s0 += w & 255u; s1 += (w >> 8) & 255u; s2 += (w >> 16) & 255u; s3 += w >> 24;
+      ++cnt;
+    }
+  }
+  if (cnt == 2) { s0 >>= 1; s1 >>= 1; s2 >>= 1; s3 >>= 1; }
+  else if (cnt == 4) { s0 >>= 2; s1 >>= 2; s2 >>= 2; s3 >>= 2; }
+  else if (cnt > 1) { s0 /= cnt; s1 /= cnt; s2 /= cnt; s3 /= cnt; }
+  return (uint32_t)s0 | ((uint32_t)s1 << 8) | ((uint32_t)s2 << 16) | ((uint32_t)s3 << 24);
+}
+
+// grid (x: 16-pixel column blocks, y: output rows, z: stacks); a thread produces 4 groups = 16 pixels (their loads are independent)
+__global__ void __launch_bounds__(128) stitch_vec4_kernel(const uint8_t* __restrict__ tiles, uint8_t* __restrict__ sheets, int n_rows,
                                                           int n_cols, int T, int step, int margin, int out_h, int out_w) {
-  const int stack = blockIdx.y;
+  const int stack = blockIdx.z, Y = blockIdx.y;
   const size_t tile_px = (size_t)T * T;
   const uint8_t* tb = tiles + (size_t)stack * n_rows * n_cols * tile_px;
-  uint8_t* ob = sheets + (size_t)stack * out_h * out_w;
-  const int G = out_w >> 2;
-  const long long total = (long long)out_h * G;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int Y = (int)(i / G), X = (int)(i - (long long)Y * G) << 2;
-    const int r_lo = Y - T + 1 <= 0 ? 0 : (Y - T + step) / step;
-    const int r_hi = min(Y / step, n_rows - 1);
-    const int c_lo = X - T + 1 <= 0 ? 0 : (X - T + step) / step;
-    const int c_hi = min(X / step, n_cols - 1);
-    int s0 = 0, s1 = 0, s2 = 0, s3 = 0, cnt = 0;
-    for (int r = r_lo; r <= r_hi; ++r) {
-      const int ly = Y - r * step;
-      const int m0 = r != 0 ? margin : 0, m1 = r != n_rows - 1 ? margin : 0;
-      if (ly < m0 || ly >= T - m1) continue;
-      for (int c = c_lo; c <= c_hi; ++c) {
-        const int lx = X - c * step;
-        const int n0 = c != 0 ? margin : 0, n1 = c != n_cols - 1 ? margin : 0;
-        if (lx < n0 || lx >= T - n1) continue;
-        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(tb + (size_t)(r * n_cols + c) * tile_px + (size_t)ly * T + lx));
-        s0 += w & 255u; s1 += (w >> 8) & 255u; s2 += (w >> 16) & 255u; s3 += w >> 24;
-        ++cnt;
-      }
-    }
-    if (cnt == 2) { s0 >>= 1; s1 >>= 1; s2 >>= 1; s3 >>= 1; }
-    else if (cnt == 4) { s0 >>= 2; s1 >>= 2; s2 >>= 2; s3 >>= 2; }
-    else if (cnt > 1) { s0 /= cnt; s1 /= cnt; s2 /= cnt; s3 /= cnt; }
-    *reinterpret_cast<uint32_t*>(ob + (size_t)Y * out_w + X) = (uint32_t)s0 | ((uint32_t)s1 << 8) | ((uint32_t)s2 << 16) | ((uint32_t)s3 << 24);
+  uint8_t* orow = sheets + ((size_t)stack * out_h + Y) * out_w;
+  const int r_lo = Y - T + 1 <= 0 ? 0 : (Y - T + step) / step;
+  const int r_hi = min(Y / step, n_rows - 1);
+  const int X0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (X0 >= out_w) return;
+  uint32_t o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) o[k] = X0 + 4 * k < out_w ? stitch_group(tb, n_rows, n_cols, T, step, margin, tile_px, Y, X0 + 4 * k, r_lo, r_hi) : 0u;
+  if (X0 + 16 <= out_w && ((reinterpret_cast<uintptr_t>(orow) + X0) & 15) == 0) {
+    *reinterpret_cast<uint4*>(orow + X0) = make_uint4(o[0], o[1], o[2], o[3]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (X0 + 4 * k < out_w) *reinterpret_cast<uint32_t*>(orow + X0 + 4 * k) = o[k];
   }
 }
 
@@ -97,12 +109,8 @@ extern "C" int pssr_stitch(const uint8_t* tiles, uint8_t* sheets, int32_t n_stac
   const bool vec = tile % 4 == 0 && step % 4 == 0 && margin % 4 == 0 && out_w % 4 == 0 &&
                    (((uintptr_t)tiles | (uintptr_t)sheets) & 3) == 0 && getenv("PSSR_STITCH_SCALAR") == nullptr;
   if (vec) {
-    const long long total = (long long)out_h * (out_w / 4);
-    long long blocks = (total + 255) / 256;
-    const long long cap = (long long)device_sm_count() * 32;
-    if (blocks > cap) blocks = cap;
-    stitch_vec4_kernel<<<dim3((unsigned)blocks, n_stacks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tiles, sheets, n_rows, n_cols, tile,
-                                                                                                                 step, margin, out_h, out_w);
+    dim3 grid((out_w + 16 * 128 - 1) / (16 * 128), out_h, n_stacks);
+    stitch_vec4_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tiles, sheets, n_rows, n_cols, tile, step, margin, out_h, out_w);
   } else {
     dim3 grid((out_w + 255) / 256, out_h, n_stacks);
     stitch_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tiles, sheets, n_rows, n_cols, tile, step, margin, out_h, out_w);
