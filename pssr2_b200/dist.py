@@ -85,6 +85,30 @@ def gather_dict(outs: dict):
     return outs
 
 
+def gather_images_nccl(local: torch.Tensor, n_items: int):
+    """NCCL path of predict_images: every rank holds the uint8 predictions of its contiguous block of the validation items as
+    ONE device tensor [n_local, ...]; rank 0 receives all blocks with one `gather` over NVLink and returns
+    [n_items, ...] in validation order (other ranks return None).  Blocks are padded to the largest share."""
+    w, r = world_size(), rank()
+    counts = [shard_bounds(n_items, k, w)[1] - shard_bounds(n_items, k, w)[0] for k in range(w)]
+    mx = max(counts)
+    if min(counts) == 0:        # fewer items than ranks: an empty rank does not know the image shape
+        shapes = [None] * w
+        dist.all_gather_object(shapes, tuple(local.shape[1:]) if local.shape[0] else None)
+        shape = next(sh for sh in shapes if sh is not None)
+        if local.shape[0] == 0:
+            local = torch.zeros((0,) + tuple(shape), dtype=local.dtype, device=local.device)
+    buf = local
+    if local.shape[0] < mx:
+        buf = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        buf[:local.shape[0]] = local
+    bufs = [torch.empty_like(buf) for _ in range(w)] if r == 0 else None
+    dist.gather(buf.contiguous(), bufs, dst=0)
+    if r != 0:
+        return None
+    return torch.cat([b[:c] for b, c in zip(bufs, counts)], 0)
+
+
 def gather_tensor_to_rank0(t: torch.Tensor):
     """Gather equally-shaped device tensors (e.g. stitched uint8 sheets) on rank 0 with one collective."""
     if not is_dist():

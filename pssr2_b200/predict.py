@@ -112,6 +112,11 @@ def predict_images(model: nn.Module, dataset, device: str = "cuda", batch_size=N
                 else:
                     callback()
 
+    # under torchrun with NCCL the predicted tiles travel GPU -> GPU: every rank keeps its uint8 batches on the device, rank 0
+    # gathers them with one collective over NVLink and reads them back once (no pickling of host arrays)
+    nccl_gather = (out_dir is None and not rank_local and D.is_dist() and torch.distributed.get_backend() == "nccl"
+                   and D.world_size() > 1 and not callbacks)
+    kept = []
     starts = range(lo, hi, batch_size)
     with torch.no_grad():
         for start in (_progress(starts) if len(starts) > 1 else starts):
@@ -125,6 +130,9 @@ def predict_images(model: nn.Module, dataset, device: str = "cuda", batch_size=N
             crop_res = dataset.crop_res if not dataset.is_lr else dataset.crop_res * (hr_hat.shape[-1] // lr.shape[-1])
             # own copy of the batch: the plan's output buffer is overwritten by the next forward while this one travels
             dbuf = hr_hat[:, :, :crop_res, :crop_res].clone(memory_format=torch.contiguous_format)
+            if nccl_gather:
+                kept.append(dbuf)
+                continue
             host = torch.empty(dbuf.shape, dtype=torch.uint8, pin_memory=True)
             ready = torch.cuda.Event()
             ready.record(cur)
@@ -138,6 +146,13 @@ def predict_images(model: nn.Module, dataset, device: str = "cuda", batch_size=N
             pending = (done, host, pos, dbuf)
         if pending is not None:
             finish(pending)
+    if nccl_gather:
+        shape = kept[0].shape[1:] if kept else (1, dataset.crop_res, dataset.crop_res)
+        local = torch.cat(kept, 0) if kept else torch.zeros((0,) + tuple(shape), dtype=torch.uint8, device=dev)
+        allp = D.gather_images_nccl(local, len(val_idx))
+        src, base = (allp, 0) if allp is not None else (local, lo)          # rank 0: everything; others: their own share
+        arr = src.cpu().numpy()
+        return {dataset._get_name(base + k): arr[k] for k in range(arr.shape[0])}
     if out_dir is None:
         return outs if rank_local else D.gather_dict(outs)
 

@@ -126,3 +126,48 @@ def test_dataset_shapes_like_reference_tests():
     assert tuple(hr.shape) == (1, 512, 512) and tuple(lr.shape) == (1, 128, 128)
     ds = SlidingDataset([s[:, :256, :256] for s in sheets], hr_res=128, lr_scale=-1, extension="tif", overlap=None, val_split=1)
     assert ds.is_lr and len(ds) == 8 and tuple(ds[0].shape) == (1, 128, 128)
+
+
+def test_error_behaviour_callbacks_and_file_output(tmp_path):
+    """Reference error contract (pssr/predict.py:40, pssr/util.py:76-77), the callback protocol (pssr/util.py:228-231,
+    predict.py:75-79: called after every image, with locals() iff it takes one argument; raising aborts the run), the TIFF
+    output path (predict.py:66-73) and the no-fallback rule."""
+    from PIL import Image
+    from pssr2_b200.data import ImageDataset, SlidingDataset
+    from pssr2_b200.predict import predict_images
+    from pssr2_b200.util import reassemble_sheets
+    model, _ = _model()
+    rng = np.random.default_rng(9)
+    lr_only = ImageDataset([rng.integers(0, 256, (1, 64, 64)).astype(np.uint8) for _ in range(3)], hr_res=256, lr_scale=4, val_split=1)
+    assert lr_only.is_lr
+    with pytest.raises(ValueError):
+        predict_images(model, lr_only, device="cuda", norm=True, out_dir=None)
+    with pytest.raises(RuntimeError):
+        predict_images(model, lr_only, device="cpu", out_dir=None)
+    with pytest.raises(ValueError):
+        reassemble_sheets({}, {"s": (1, 64, 64)}, lr_scale=4, overlap=8, margin=9, out_dir=None)
+    # LR-mode prediction: 64^2 -> 256^2, crop = crop_res * scale (predict.py:66)
+    seen, seen_locals = [], []
+    preds = predict_images(model, lr_only, device="cuda", batch_size=2, out_dir=None,
+                           callbacks=[lambda: seen.append(1), lambda loc: seen_locals.append(sorted(loc)[:1])])
+    assert len(preds) == 3 and all(v.shape == (1, 256, 256) and v.dtype == np.uint8 for v in preds.values())
+    assert len(seen) == 3 and len(seen_locals) == 3
+
+    class Abort(Exception):
+        pass
+
+    def stop():
+        raise Abort()
+    with pytest.raises(Abort):
+        predict_images(model, lr_only, device="cuda", out_dir=None, callbacks=[stop])
+    # file output: {out_dir}/{prefix_}{name}.tif, identical pixels to the dict path
+    sheet = _sheet(np.uint8, (1, 320, 320), seed=5)
+    ds = SlidingDataset({"a": sheet}, hr_res=256, lr_scale=4, overlap=192, val_split=1, crappifier=None)
+    want = predict_images(model, ds, device="cuda", batch_size=3, out_dir=None)
+    predict_images(model, ds, device="cuda", batch_size=3, out_dir=str(tmp_path / "p"), prefix="run")
+    for name, arr in want.items():
+        got = np.asarray(Image.open(tmp_path / "p" / f"run_{name}.tif"))
+        assert np.array_equal(got, arr[0])
+    # an empty validation split predicts nothing
+    ds.val_idx = []
+    assert predict_images(model, ds, device="cuda", out_dir=None) == {}
