@@ -19,6 +19,8 @@ namespace pssr {
 static constexpr int kPrepThreads = 128;
 __global__ void __launch_bounds__(kPrepThreads) prep_im2col_kernel(pssr_prep_desc_t d, int fp16) {
   __shared__ uint4 tr[kPrepThreads / 32][32 * 8];
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = (long long)d.B * d.H * d.W;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool cols16 = d.cols == 16;
@@ -87,9 +89,8 @@ int prep_launch(const pssr_prep_desc_t& d, int dtype, cudaStream_t stream) {
   long long blocks = (total + threads - 1) / threads;
   const long long cap = (long long)device_sm_count() * 32;
   if (blocks > cap) blocks = cap;
-  prep_im2col_kernel<<<(int)blocks, threads, 0, stream>>>(d, dtype == PSSR_DT_FP16);
+  PSSR_CHECK_CUDA(launch_pdl(prep_im2col_kernel, dim3((unsigned)blocks), dim3(threads), 0, stream, d, (int)(dtype == PSSR_DT_FP16)));
   count_launch();
-  PSSR_CHECK_CUDA(cudaGetLastError());
   return PSSR_OK;
 }
 
@@ -108,6 +109,8 @@ __device__ __forceinline__ uint4 max4(uint4 a, uint4 b, int fp16) {
 
 // One thread per (output pixel, 8-channel group): 4 x 16-byte loads, 1 x 16-byte store.
 __global__ void maxpool2_kernel(pssr_pool_desc_t d, int fp16) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int groups = d.C / 8;
   const int Ho = d.H / 2, Wo = d.W / 2;
   const long long total = (long long)d.B * Ho * Wo * groups;
@@ -142,9 +145,8 @@ int pool_launch(const pssr_pool_desc_t& d, int dtype, cudaStream_t stream) {
   const long long cap = (long long)device_sm_count() * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  maxpool2_kernel<<<(int)blocks, threads, 0, stream>>>(d, dtype == PSSR_DT_FP16);
+  PSSR_CHECK_CUDA(launch_pdl(maxpool2_kernel, dim3((unsigned)blocks), dim3(threads), 0, stream, d, (int)(dtype == PSSR_DT_FP16)));
   count_launch();
-  PSSR_CHECK_CUDA(cudaGetLastError());
   return PSSR_OK;
 }
 
@@ -349,6 +351,8 @@ __global__ void __launch_bounds__(256) tailsum_rows_kernel(pssr_tailsum_desc_t d
 // 0..3, e = 1 holds 2..5), from the pixel left / right the columns 5 / 0, and for si = 0 / 3 the rows 5 / 0 of the pixel
 // above / below -- 8 or 16 coalesced loads per thread instead of 36, every z value read exactly once.
 __global__ void __launch_bounds__(256) tailsum_win48_kernel(pssr_tailsum_desc_t d) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Hh = d.H * 4, Wh = d.W * 4;
   const long long total = (long long)d.B * d.H * 4 * d.W;       // (n, y, si, x), x fastest
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -396,9 +400,8 @@ int tailsum_launch(const pssr_tailsum_desc_t& d, cudaStream_t stream) {
     const long long total = (long long)d.B * d.H * 4 * d.W;
     long long blocks = (total + 255) / 256;
     if (blocks > cap) blocks = cap;
-    tailsum_win48_kernel<<<(int)blocks, 256, 0, stream>>>(d);
+    PSSR_CHECK_CUDA(launch_pdl(tailsum_win48_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, d));
     count_launch();
-    PSSR_CHECK_CUDA(cudaGetLastError());
     return PSSR_OK;
   }
   if ((d.r == 2 || d.r == 4 || d.r == 8) && aligned && getenv("PSSR_TAILSUM_V1") == nullptr) {
