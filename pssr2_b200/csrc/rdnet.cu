@@ -58,39 +58,55 @@ __global__ void __launch_bounds__(256) stem_kernel(pssr_stem_desc_t d, int fp16)
       const float raw = d.x_u8 ? (float)reinterpret_cast<const uint8_t*>(d.x)[idx] : reinterpret_cast<const float*>(d.x)[idx];
       vin = __fadd_rn(__fmul_rn(__fsub_rn(__fdiv_rn(raw, 128.f), 1.f), d.in_scale[ci]), d.in_shift[ci]);
     }
+    // channel groups unrolled with compile-time indices: vals[] stays in registers (a runtime group counter put it in local
+    // memory); groups beyond Cout are predicated off
     float vals[kMaxGroupsPerLane * 8];
     float s = 0.f;
-    int cnt = 0;
-    for (int c0 = lane * 8; c0 < d.Cout; c0 += 256, ++cnt) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) vals[cnt * 8 + j] = b_s[c0 + j];
+    for (int g = 0; g < kMaxGroupsPerLane; ++g) {
+      const int c0 = lane * 8 + g * 256;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) vals[g * 8 + j] = c0 < d.Cout ? b_s[c0 + j] : 0.f;
     }
     for (int k = 0; k < K; ++k) {
       const float v = __shfl_sync(0xffffffffu, vin, k);
-      cnt = 0;
-      for (int c0 = lane * 8; c0 < d.Cout; c0 += 256, ++cnt) {
-        const float4 w0 = *reinterpret_cast<const float4*>(w_s + (size_t)k * d.Cout + c0), w1 = *reinterpret_cast<const float4*>(w_s + (size_t)k * d.Cout + c0 + 4);
-        float* vv = vals + cnt * 8;
-        vv[0] = fmaf(v, w0.x, vv[0]); vv[1] = fmaf(v, w0.y, vv[1]); vv[2] = fmaf(v, w0.z, vv[2]); vv[3] = fmaf(v, w0.w, vv[3]);
-        vv[4] = fmaf(v, w1.x, vv[4]); vv[5] = fmaf(v, w1.y, vv[5]); vv[6] = fmaf(v, w1.z, vv[6]); vv[7] = fmaf(v, w1.w, vv[7]);
+#pragma unroll
+      for (int g = 0; g < kMaxGroupsPerLane; ++g) {
+        const int c0 = lane * 8 + g * 256;
+        if (c0 < d.Cout) {
+          const float4 w0 = *reinterpret_cast<const float4*>(w_s + (size_t)k * d.Cout + c0), w1 = *reinterpret_cast<const float4*>(w_s + (size_t)k * d.Cout + c0 + 4);
+          vals[g * 8 + 0] = fmaf(v, w0.x, vals[g * 8 + 0]); vals[g * 8 + 1] = fmaf(v, w0.y, vals[g * 8 + 1]);
+          vals[g * 8 + 2] = fmaf(v, w0.z, vals[g * 8 + 2]); vals[g * 8 + 3] = fmaf(v, w0.w, vals[g * 8 + 3]);
+          vals[g * 8 + 4] = fmaf(v, w1.x, vals[g * 8 + 4]); vals[g * 8 + 5] = fmaf(v, w1.y, vals[g * 8 + 5]);
+          vals[g * 8 + 6] = fmaf(v, w1.z, vals[g * 8 + 6]); vals[g * 8 + 7] = fmaf(v, w1.w, vals[g * 8 + 7]);
+        }
       }
     }
-    cnt = 0;
-    for (int c0 = lane * 8; c0 < d.Cout; c0 += 256, ++cnt) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += vals[cnt * 8 + j];
-    }
+    for (int g = 0; g < kMaxGroupsPerLane; ++g)
+      if (lane * 8 + g * 256 < d.Cout) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += vals[g * 8 + j];
+      }
     const float mean = warp_sum_f(s) / d.Cout;
     float q = 0.f;
-    for (int i = 0; i < cnt * 8; ++i) { const float t = vals[i] - mean; q += t * t; }
+#pragma unroll
+    for (int g = 0; g < kMaxGroupsPerLane; ++g)
+      if (lane * 8 + g * 256 < d.Cout) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float t = vals[g * 8 + j] - mean; q += t * t; }
+      }
     const float rstd = rsqrtf(warp_sum_f(q) / d.Cout + d.eps);
     uint16_t* out = reinterpret_cast<uint16_t*>(d.out) + (size_t)pix * d.out_cstride + d.out_choff;
-    cnt = 0;
-    for (int c0 = lane * 8; c0 < d.Cout; c0 += 256, ++cnt) {
-      float f[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = (vals[cnt * 8 + j] - mean) * rstd * lw_s[c0 + j] + lb_s[c0 + j];
-      *reinterpret_cast<uint4*>(out + c0) = pack8(f, fp16);
+    for (int g = 0; g < kMaxGroupsPerLane; ++g) {
+      const int c0 = lane * 8 + g * 256;
+      if (c0 < d.Cout) {
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = (vals[g * 8 + j] - mean) * rstd * lw_s[c0 + j] + lb_s[c0 + j];
+        *reinterpret_cast<uint4*>(out + c0) = pack8(f, fp16);
+      }
     }
   }
 }
@@ -120,18 +136,27 @@ __global__ void __launch_bounds__(256) ln_kernel(pssr_ln_desc_t d, int fp16) {
   const uint16_t* in = reinterpret_cast<const uint16_t*>(d.in) + d.in_choff;
   for (long long pix = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; pix < total; pix += ((long long)gridDim.x * blockDim.x) >> 5) {
     const uint16_t* src = in + (size_t)pix * d.in_cstride;
+    // channel groups unrolled with compile-time indices: vals[] stays in registers (see stem_kernel)
     float vals[kMaxGroupsPerLane * 8];
     float s = 0.f;
-    int cnt = 0;
-    for (int c0 = lane * 8; c0 < d.C; c0 += 256, ++cnt) {
-      float f[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(src + c0)), f, fp16);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { vals[cnt * 8 + j] = f[j]; s += f[j]; }
+    for (int g = 0; g < kMaxGroupsPerLane; ++g) {
+      const int c0 = lane * 8 + g * 256;
+      if (c0 < d.C) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(src + c0)), f, fp16);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { vals[g * 8 + j] = f[j]; s += f[j]; }
+      }
     }
     const float mean = warp_sum_f(s) / d.C;
     float q = 0.f;
-    for (int i = 0; i < cnt * 8; ++i) { const float t = vals[i] - mean; q += t * t; }
+#pragma unroll
+    for (int g = 0; g < kMaxGroupsPerLane; ++g)
+      if (lane * 8 + g * 256 < d.C) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float t = vals[g * 8 + j] - mean; q += t * t; }
+      }
     const float rstd = rsqrtf(warp_sum_f(q) / d.C + d.eps);
     size_t opix = (size_t)pix;
     int coff = 0;
@@ -141,12 +166,18 @@ __global__ void __launch_bounds__(256) ln_kernel(pssr_ln_desc_t d, int fp16) {
       coff = ((y & 1) * 2 + (x & 1)) * d.C;
     }
     uint16_t* out = reinterpret_cast<uint16_t*>(d.out) + opix * d.out_cstride + d.out_choff + coff;
-    cnt = 0;
-    for (int c0 = lane * 8; c0 < d.C; c0 += 256, ++cnt) {
-      float f[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = (vals[cnt * 8 + j] - mean) * rstd * d.w[c0 + j] + d.b[c0 + j];
-      *reinterpret_cast<uint4*>(out + c0) = pack8(f, fp16);
+    for (int g = 0; g < kMaxGroupsPerLane; ++g) {
+      const int c0 = lane * 8 + g * 256;
+      if (c0 < d.C) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(d.w + c0)), w1 = __ldg(reinterpret_cast<const float4*>(d.w + c0 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(d.b + c0)), b1 = __ldg(reinterpret_cast<const float4*>(d.b + c0 + 4));
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w}, bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = (vals[g * 8 + j] - mean) * rstd * wv[j] + bv[j];
+        *reinterpret_cast<uint4*>(out + c0) = pack8(f, fp16);
+      }
     }
   }
 }
@@ -315,6 +346,112 @@ __global__ void __launch_bounds__(256) dwconv7_kernel(pssr_dwln_desc_t d, int fp
   }
 }
 
+// Pipelined variant for large maps: a CTA owns one 8x16 spatial tile and walks ALL 64-channel slabs of it; the halo tile and the
+// filter of slab s+1 arrive by cp.async (zero-filled outside the image / beyond C) while slab s is computed, so the staging
+// latency that the one-slab kernel exposes on every CTA is hidden behind the FMAs.
+__device__ __forceinline__ void dw_cp16(uint32_t dst, const void* src, bool valid) {
+  const int nbytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+}
+static constexpr int kDwTileBytes = (kDwTH + 6) * (kDwTW + 6) * (kDwC / 8) * 16;
+static constexpr int kDwBufBytes = kDwTileBytes + (49 * kDwC + kDwC) * 4;
+
+__global__ void __launch_bounds__(256, 2) dwconv7_pipe_kernel(pssr_dwln_desc_t d, int fp16) {
+  extern __shared__ __align__(16) uint8_t dw_sm[];
+  const int tiles_x = (d.W + kDwTW - 1) / kDwTW, tiles_y = (d.H + kDwTH - 1) / kDwTH;
+  int bid = blockIdx.x;
+  const int tx = bid % tiles_x; bid /= tiles_x;
+  const int ty = bid % tiles_y;
+  const int n = bid / tiles_y;
+  const int slabs = (d.C + kDwC - 1) / kDwC;
+  const int x0 = tx * kDwTW, y0 = ty * kDwTH;
+  const uint16_t* in0 = reinterpret_cast<const uint16_t*>(d.in) + d.in_choff;
+  const uint32_t sm0 = smem_u32(dw_sm);
+
+  auto stage = [&](int sl, int buf) {
+    const int c_base = sl * kDwC;
+    const int cw = d.C - c_base < kDwC ? d.C - c_base : kDwC;
+    const uint32_t tile_s = sm0 + (uint32_t)buf * kDwBufBytes;
+    const uint32_t w_s = tile_s + kDwTileBytes;
+    for (int i = threadIdx.x; i < (kDwTH + 6) * (kDwTW + 6) * 8; i += 256) {
+      const int g = i & 7, pp = i >> 3;
+      const int yy = y0 + pp / (kDwTW + 6) - 3, xx = x0 + pp % (kDwTW + 6) - 3;
+      const bool ok = yy >= 0 && yy < d.H && xx >= 0 && xx < d.W && g * 8 < cw;
+      const uint16_t* src = ok ? in0 + (((size_t)n * d.H + yy) * d.W + xx) * d.in_cstride + c_base + g * 8 : in0;
+      dw_cp16(tile_s + (uint32_t)i * 16u, src, ok);
+    }
+    for (int i = threadIdx.x; i < 49 * (kDwC / 4); i += 256) {          // filter taps: 16 chunks of 4 floats per tap
+      const int t = i / (kDwC / 4), c4 = (i % (kDwC / 4)) * 4;
+      const bool ok = c4 < cw;
+      dw_cp16(w_s + (uint32_t)(t * kDwC + c4) * 4u, ok ? d.dw_w + (size_t)t * d.C + c_base + c4 : d.dw_w, ok);
+    }
+    if (threadIdx.x < kDwC / 4) {
+      const int c4 = threadIdx.x * 4;
+      const bool ok = c4 < cw;
+      dw_cp16(w_s + (uint32_t)(49 * kDwC + c4) * 4u, ok ? d.dw_b + c_base + c4 : d.dw_b, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const int g = threadIdx.x & 7;             // channel group
+  const int xq = (threadIdx.x >> 3) & 3;     // which 4-pixel quad of the 16-wide row
+  const int row = threadIdx.x >> 5;          // 0..7
+  stage(0, 0);
+  for (int sl = 0; sl < slabs; ++sl) {
+    const int buf = sl & 1;
+    if (sl + 1 < slabs) {
+      stage(sl + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const uint4* tile = reinterpret_cast<const uint4*>(dw_sm + (size_t)buf * kDwBufBytes);
+    const float* wsm = reinterpret_cast<const float*>(dw_sm + (size_t)buf * kDwBufBytes + kDwTileBytes);
+    const float* bsm = wsm + 49 * kDwC;
+    const int c_base = sl * kDwC;
+    const int cw = d.C - c_base < kDwC ? d.C - c_base : kDwC;
+    float acc[4][8];
+#pragma unroll
+    for (int p4 = 0; p4 < 4; ++p4)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[p4][j] = bsm[g * 8 + j];
+    for (int ky = 0; ky < 7; ++ky) {
+      float wr[7][8];
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) {
+        const float4 w0 = *reinterpret_cast<const float4*>(wsm + (ky * 7 + kx) * kDwC + g * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(wsm + (ky * 7 + kx) * kDwC + g * 8 + 4);
+        wr[kx][0] = w0.x; wr[kx][1] = w0.y; wr[kx][2] = w0.z; wr[kx][3] = w0.w; wr[kx][4] = w1.x; wr[kx][5] = w1.y; wr[kx][6] = w1.z; wr[kx][7] = w1.w;
+      }
+      const uint4* trow = tile + ((row + ky) * (kDwTW + 6) + xq * 4) * 8 + g;
+#pragma unroll
+      for (int cx = 0; cx < 10; ++cx) {
+        float f[8];
+        unpack8(trow[cx * 8], f, fp16);
+#pragma unroll
+        for (int p4 = 0; p4 < 4; ++p4) {
+          const int kx = cx - p4;
+          if (kx >= 0 && kx < 7) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[p4][j] = fmaf(f[j], wr[kx][j], acc[p4][j]);
+          }
+        }
+      }
+    }
+    const int y = y0 + row;
+    if (y < d.H && g * 8 < cw) {
+      uint16_t* out = reinterpret_cast<uint16_t*>(d.out) + d.out_choff + c_base + g * 8;
+#pragma unroll
+      for (int p4 = 0; p4 < 4; ++p4) {
+        const int x = x0 + xq * 4 + p4;
+        if (x < d.W) *reinterpret_cast<uint4*>(out + (((size_t)n * d.H + y) * d.W + x) * d.out_cstride) = pack8(acc[p4], fp16);
+      }
+    }
+    __syncthreads();           // every thread is done with buffer `buf` before the stage after next overwrites it
+  }
+}
+
 int ln_launch(const pssr_ln_desc_t& d, int dtype, cudaStream_t stream);
 
 int dwln_launch(const pssr_dwln_desc_t& d, int dtype, cudaStream_t stream) {
@@ -330,6 +467,25 @@ int dwln_launch(const pssr_dwln_desc_t& d, int dtype, cudaStream_t stream) {
     count_launch();
     PSSR_CHECK_CUDA(cudaGetLastError());
     return PSSR_OK;
+  }
+  const long long sp_tiles = (long long)d.B * ((d.H + kDwTH - 1) / kDwTH) * ((d.W + kDwTW - 1) / kDwTW);
+  const int slabs_all = (d.C + kDwC - 1) / kDwC;
+  // enough spatial tiles to fill the machine twice over and at least two slabs to pipeline: the slab-walking kernel
+  if (sp_tiles >= 4LL * device_sm_count() && slabs_all >= 2 && ((uintptr_t)d.dw_w & 15) == 0 && d.C % 4 == 0 && getenv("PSSR_DW_NOPIPE") == nullptr) {
+    static bool attr_pipe = false;
+    if (!attr_pipe) {
+      PSSR_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kDwBufBytes));
+      attr_pipe = true;
+    }
+    PSSR_REQUIRE(sp_tiles < (1ll << 31), PSSR_EUNSUP, "dwconv: too many blocks");
+    dwconv7_pipe_kernel<<<(unsigned)sp_tiles, 256, 2 * kDwBufBytes, stream>>>(d, dtype == PSSR_DT_FP16);
+    count_launch();
+    PSSR_CHECK_CUDA(cudaGetLastError());
+    pssr_ln_desc_t lnp;
+    memset(&lnp, 0, sizeof(lnp));
+    lnp.in = d.out; lnp.in_cstride = d.out_cstride; lnp.in_choff = d.out_choff; lnp.C = d.C; lnp.B = d.B; lnp.H = d.H; lnp.W = d.W; lnp.s2d = 1;
+    lnp.w = d.ln_w; lnp.b = d.ln_b; lnp.eps = d.eps; lnp.out = d.out; lnp.out_cstride = d.out_cstride; lnp.out_choff = d.out_choff;
+    return ln_launch(lnp, dtype, stream);
   }
   const long long blocks = (long long)d.B * ((d.C + kDwC - 1) / kDwC) * ((d.H + kDwTH - 1) / kDwTH) * ((d.W + kDwTW - 1) / kDwTW);
   PSSR_REQUIRE(blocks < (1ll << 31), PSSR_EUNSUP, "dwconv: too many blocks");
@@ -351,23 +507,54 @@ int dwln_launch(const pssr_dwln_desc_t& d, int dtype, cudaStream_t stream) {
 
 // -------------------------------------------------------------------------------- ese
 // gate[b][c] = relu6(fc(mean_yx in[b]) + 3) / 6 * gamma[c]; one CTA per image.
+// One CTA per image.  Phase 1: global mean per channel -- thread = (8-channel group, pixel subset), 16-byte loads, partial sums
+// reduced through shared memory in a fixed order (deterministic).  Phase 2: the C x C squeeze-excite fc as one warp per output
+// channel (coalesced weight rows, shuffle reduction) -> hard-sigmoid gate x layer scale.
 __global__ void __launch_bounds__(256) ese_gate_kernel(pssr_ese_desc_t d, int fp16) {
-  extern __shared__ float ese_mean[];
+  extern __shared__ float ese_sm[];          // [C] means, then [nsets][C] partial sums
+  float* ese_mean = ese_sm;
+  float* part = ese_sm + d.C;
   const int b = blockIdx.x;
   const int HW = d.H * d.W;
+  const int groups = d.C / 8;
   const uint16_t* in = reinterpret_cast<const uint16_t*>(d.in) + (size_t)b * HW * d.in_cstride;
-  for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
-    float s = 0.f;
-    for (int p = 0; p < HW; ++p) s += unpack1(in[(size_t)p * d.in_cstride + c], fp16);
-    ese_mean[c] = s / HW;
+  if (groups <= 256 && 256 % groups == 0) {
+    const int nsets = 256 / groups;
+    const int g = threadIdx.x % groups, ps = threadIdx.x / groups;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int p = ps; p < HW; p += nsets) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(in + (size_t)p * d.in_cstride + g * 8)), f, fp16);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[(size_t)ps * d.C + g * 8 + j] = acc[j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
+      float s = 0.f;
+      for (int k = 0; k < nsets; ++k) s += part[(size_t)k * d.C + c];
+      ese_mean[c] = s / HW;
+    }
+  } else {
+    for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
+      float s = 0.f;
+      for (int p = 0; p < HW; ++p) s += unpack1(in[(size_t)p * d.in_cstride + c], fp16);
+      ese_mean[c] = s / HW;
+    }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
-    float a = d.fc_b[c];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = warp; c < d.C; c += 8) {
     const float* w = d.fc_w + (size_t)c * d.C;
-    for (int k = 0; k < d.C; ++k) a = fmaf(w[k], ese_mean[k], a);
-    const float g = fminf(fmaxf(a + 3.f, 0.f), 6.f) / 6.f;
-    d.gate_ws[(size_t)b * d.C + c] = g * (d.gamma != nullptr ? d.gamma[c] : 1.f);
+    float a = 0.f;
+    for (int k = lane; k < d.C; k += 32) a = fmaf(__ldg(w + k), ese_mean[k], a);
+    a = warp_sum_f(a);
+    if (lane == 0) {
+      a += d.fc_b[c];
+      const float gte = fminf(fmaxf(a + 3.f, 0.f), 6.f) / 6.f;
+      d.gate_ws[(size_t)b * d.C + c] = gte * (d.gamma != nullptr ? d.gamma[c] : 1.f);
+    }
   }
 }
 
@@ -391,7 +578,11 @@ int ese_launch(const pssr_ese_desc_t& d, int dtype, cudaStream_t stream) {
   PSSR_REQUIRE(d.C % 8 == 0 && d.C <= 4096, PSSR_EUNSUP, "ese: C=%d unsupported", d.C);
   PSSR_REQUIRE(d.in_cstride % 8 == 0 && d.out_cstride % 8 == 0 && d.out_choff % 8 == 0, PSSR_EUNSUP, "ese: alignment");
   PSSR_REQUIRE(d.gate_ws != nullptr && d.fc_w != nullptr && d.fc_b != nullptr, PSSR_EINVAL, "ese: null pointer");
-  ese_gate_kernel<<<d.B, 256, d.C * sizeof(float), stream>>>(d, dtype == PSSR_DT_FP16);
+  const int groups = d.C / 8;
+  const int nsets = (groups > 0 && groups <= 256 && 256 % groups == 0) ? 256 / groups : 0;
+  const size_t ese_smem = ((size_t)d.C + (size_t)nsets * d.C) * sizeof(float);
+  PSSR_REQUIRE(d.C % 8 == 0 && ese_smem <= 48 * 1024, PSSR_EUNSUP, "ese: C=%d unsupported", d.C);
+  ese_gate_kernel<<<d.B, 256, ese_smem, stream>>>(d, dtype == PSSR_DT_FP16);
   const long long total = (long long)d.B * d.H * d.W * (d.C / 8);
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)device_sm_count() * 16;
