@@ -92,6 +92,57 @@ __global__ void __launch_bounds__(128) stitch_vec4_kernel(const uint8_t* __restr
   }
 }
 
+// 16-pixel path (T, step, margin, sheet width all multiples of 16, 16-byte aligned buffers): every span boundary is a multiple
+// of 16, so an aligned 16-pixel vector shares its contributors.  One 16-byte load per contributor; the byte sums are kept in
+// 16-bit lanes (two per 32-bit word, <= 9 * 255), the division is a shift for 1 / 2 / 4 contributors.
+__device__ __forceinline__ void stitch_acc16(uint32_t (&lo)[4], uint32_t (&hi)[4], const uint4& v) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { lo[k] += w[k] & 0x00FF00FFu; hi[k] += (w[k] >> 8) & 0x00FF00FFu; }
+}
+__global__ void __launch_bounds__(128) stitch_vec16_kernel(const uint8_t* __restrict__ tiles, uint8_t* __restrict__ sheets, int n_rows,
+                                                           int n_cols, int T, int step, int margin, int out_h, int out_w) {
+  const int stack = blockIdx.z, Y = blockIdx.y;
+  const int X = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (X >= out_w) return;
+  const size_t tile_px = (size_t)T * T;
+  const uint8_t* tb = tiles + (size_t)stack * n_rows * n_cols * tile_px;
+  const int r_lo = Y - T + 1 <= 0 ? 0 : (Y - T + step) / step;
+  const int r_hi = min(Y / step, n_rows - 1);
+  const int c_lo = X - T + 1 <= 0 ? 0 : (X - T + step) / step;
+  const int c_hi = min(X / step, n_cols - 1);
+  uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+  int cnt = 0;
+  for (int r = r_lo; r <= r_hi; ++r) {
+    const int ly = Y - r * step;
+    const int m0 = r != 0 ? margin : 0, m1 = r != n_rows - 1 ? margin : 0;
+    if (ly < m0 || ly >= T - m1) continue;
+    for (int c = c_lo; c <= c_hi; ++c) {
+      const int lx = X - c * step;
+      const int n0 = c != 0 ? margin : 0, n1 = c != n_cols - 1 ? margin : 0;
+      if (lx < n0 || lx >= T - n1) continue;
+      stitch_acc16(lo, hi, __ldg(reinterpret_cast<const uint4*>(tb + (size_t)(r * n_cols + c) * tile_px + (size_t)ly * T + lx)));
+      ++cnt;
+    }
+  }
+  uint32_t o[4];
+  if (cnt <= 1 || cnt == 2 || cnt == 4) {
+    const int sh = cnt == 2 ? 1 : (cnt == 4 ? 2 : 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = ((lo[k] >> sh) & 0x00FF00FFu) | (((hi[k] >> sh) & 0x00FF00FFu) << 8);
+  } else {
+    // floor(s / cnt) = (s * ceil(2^16 / cnt)) >> 16 exactly for s <= 9 * 255, cnt <= 9
+    const uint32_t m = (65536u + (uint32_t)cnt - 1u) / (uint32_t)cnt;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t a = ((lo[k] & 0xFFFFu) * m) >> 16, b = ((lo[k] >> 16) * m) >> 16;
+      const uint32_t c2 = ((hi[k] & 0xFFFFu) * m) >> 16, d2 = ((hi[k] >> 16) * m) >> 16;
+      o[k] = a | (c2 << 8) | (b << 16) | (d2 << 24);
+    }
+  }
+  *reinterpret_cast<uint4*>(sheets + ((size_t)stack * out_h + Y) * out_w + X) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 }  // namespace pssr
 
 using namespace pssr;
@@ -108,7 +159,12 @@ extern "C" int pssr_stitch(const uint8_t* tiles, uint8_t* sheets, int32_t n_stac
   PSSR_REQUIRE(n_stacks <= 65535 && out_h <= 65535, PSSR_EUNSUP, "stitch: sheet too large for the launch grid");
   const bool vec = tile % 4 == 0 && step % 4 == 0 && margin % 4 == 0 && out_w % 4 == 0 &&
                    (((uintptr_t)tiles | (uintptr_t)sheets) & 3) == 0 && getenv("PSSR_STITCH_SCALAR") == nullptr;
-  if (vec) {
+  const bool vec16 = vec && tile % 16 == 0 && step % 16 == 0 && margin % 16 == 0 && out_w % 16 == 0 &&
+                     (((uintptr_t)tiles | (uintptr_t)sheets) & 15) == 0 && tile / step < 3 && getenv("PSSR_STITCH_VEC4") == nullptr;
+  if (vec16) {
+    dim3 grid((out_w / 16 + 127) / 128, out_h, n_stacks);
+    stitch_vec16_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tiles, sheets, n_rows, n_cols, tile, step, margin, out_h, out_w);
+  } else if (vec) {
     dim3 grid((out_w + 16 * 128 - 1) / (16 * 128), out_h, n_stacks);
     stitch_vec4_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tiles, sheets, n_rows, n_cols, tile, step, margin, out_h, out_w);
   } else {

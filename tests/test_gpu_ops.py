@@ -116,7 +116,9 @@ def test_crappify_philox_statistics():
 @pytest.mark.parametrize("n_rows,n_cols,T,ov,margin,stacks", [(3, 4, 64, 16, 0, 2), (3, 3, 64, 16, 8, 1), (2, 5, 64, 16, 12, 1),
                                                                (4, 4, 32, 20, 4, 1), (1, 1, 64, 0, 0, 3), (10, 10, 512, 128, 32, 1),
                                                                (3, 4, 64, 18, 5, 2),      # step / margin not multiples of 4: scalar path
-                                                               (3, 3, 64, 40, 12, 1)])    # overlap > T/2: up to 9 contributors per pixel
+                                                               (3, 3, 64, 40, 12, 1),     # overlap > T/2: up to 9 contributors per pixel
+                                                               (4, 5, 80, 48, 16, 2),     # 16-pixel path with 3 / 6 / 9 contributors (reciprocal division)
+                                                               (3, 3, 128, 32, 16, 1)])   # 16-pixel path, 1 / 2 / 4 contributors
 def test_stitch_bit_exact(n_rows, n_cols, T, ov, margin, stacks):
     ops = _ops()
     rng = np.random.default_rng(n_rows * 100 + n_cols)
