@@ -167,48 +167,83 @@ __device__ __forceinline__ float log_factorial(float k) {
   return fmaf(x - 0.5f, logf(x), -x) + 0.91893853f + rx * (0.083333333f - 0.0027777778f * rx * rx);
 }
 
-__device__ float poisson_sample_f32(const Philox& ph, uint32_t pix, uint32_t stage, float lam) {
-  uint32_t draw = 0;
+// Per-pixel pool of Philox words shared by all noise stages of the pixel: one Philox4x32-10 block (~70 instructions) yields two
+// pairs; a PTRS attempt, a Box-Muller normal and a salt-and-pepper draw take one pair each, so the usual Poisson + Gaussian
+// chain costs ONE block per pixel instead of two or three.  Counter = (pixel, block index), key = (seed, tile).
+struct RngPool {
+  const Philox& ph;
+  uint32_t pix, blk;
+  uint4 w;
+  int have;
+  __device__ __forceinline__ RngPool(const Philox& p, uint32_t px) : ph(p), pix(px), blk(0), w(make_uint4(0, 0, 0, 0)), have(0) {}
+  __device__ __forceinline__ void next2(uint32_t& a, uint32_t& b) {
+    if (have == 0) { w = ph(pix, 0x504F4F4Cu, blk++, 0x50535352u); have = 2; a = w.x; b = w.y; }
+    else { have = 0; a = w.z; b = w.w; }
+  }
+};
+
+// PTRS constants of integer rates 0..255 (every LR pixel of an 8-bit pipeline before the first noise stage): filled once per
+// device by ptrs_table_kernel with the same float expressions the sampler uses, so a table hit and the inline path agree.
+struct PtrsConst { float slam, loglam, b, a, invalpha, vr, log_invalpha, enlam; };
+__device__ PtrsConst g_ptrs_tab[256];
+__device__ __forceinline__ PtrsConst ptrs_const(float lam) {
+  PtrsConst c;
+  c.slam = sqrtf(lam);
+  c.loglam = logf(lam);
+  c.b = 0.931f + 2.53f * c.slam;
+  c.a = -0.059f + 0.02483f * c.b;
+  c.invalpha = 1.1239f + 1.1328f / (c.b - 3.4f);
+  c.vr = 0.9277f - 3.6224f / (c.b - 2.0f);
+  c.log_invalpha = logf(c.invalpha);
+  c.enlam = expf(-lam);
+  return c;
+}
+__global__ void ptrs_table_kernel() {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 256) g_ptrs_tab[i] = ptrs_const((float)(i > 0 ? i : 1));
+}
+
+__device__ float poisson_sample_f32(RngPool& rng, float lam) {
+  PtrsConst c;
+  if (lam < 256.0f && lam == floorf(lam)) {
+    const float4* t = reinterpret_cast<const float4*>(&g_ptrs_tab[(int)lam]);
+    const float4 t0 = __ldg(t), t1 = __ldg(t + 1);
+    c.slam = t0.x; c.loglam = t0.y; c.b = t0.z; c.a = t0.w; c.invalpha = t1.x; c.vr = t1.y; c.log_invalpha = t1.z; c.enlam = t1.w;
+  } else {
+    c = ptrs_const(lam);
+  }
   if (lam < 10.0f) {
-    const float enlam = expf(-lam);
     float prod = 1.0f;
     int k = 0;
     while (true) {
-      const uint4 r = ph(pix, stage, draw++, 0x504F4953u);
-      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        prod *= u01f(w[j]);
-        if (prod <= enlam) return (float)k;
-        ++k;
-      }
+      uint32_t u0, u1;
+      rng.next2(u0, u1);
+      prod *= u01f(u0);
+      if (prod <= c.enlam) return (float)k;
+      ++k;
+      prod *= u01f(u1);
+      if (prod <= c.enlam) return (float)k;
+      ++k;
     }
   }
-  const float slam = sqrtf(lam), loglam = logf(lam);
-  const float b = 0.931f + 2.53f * slam;
-  const float a = -0.059f + 0.02483f * b;
-  const float invalpha = 1.1239f + 1.1328f / (b - 3.4f);
-  const float vr = 0.9277f - 3.6224f / (b - 2.0f);
-  const float log_invalpha = logf(invalpha);
   while (true) {
-    const uint4 r = ph(pix, stage, draw++, 0x50545253u);
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const float U = u01f(w[2 * j]) - 0.5f;
-      const float V = u01f(w[2 * j + 1]);
-      const float us = 0.5f - fabsf(U);
-      const float k = floorf((2.0f * a / us + b) * U + lam + 0.43f);
-      if (us >= 0.07f && V <= vr) return k;
-      if (k < 0.0f || (us < 0.013f && V > us)) continue;
-      if ((__logf(V) + log_invalpha - __logf(a / (us * us) + b)) <= (-lam + k * loglam - log_factorial(k))) return k;
-    }
+    uint32_t u0, u1;
+    rng.next2(u0, u1);
+    const float U = u01f(u0) - 0.5f;
+    const float V = u01f(u1);
+    const float us = 0.5f - fabsf(U);
+    const float k = floorf((2.0f * c.a / us + c.b) * U + lam + 0.43f);
+    if (us >= 0.07f && V <= c.vr) return k;
+    if (k < 0.0f || (us < 0.013f && V > us)) continue;
+    if ((__logf(V) + c.log_invalpha - __logf(c.a / (us * us) + c.b)) <= (-lam + k * c.loglam - log_factorial(k))) return k;
   }
 }
 
-__device__ double poisson_sample(const Philox& ph, uint32_t pix, uint32_t stage, double lam) {
+__device__ double poisson_sample(RngPool& rng, double lam) {
   if (!(lam > 0.0)) return 0.0;
-  if (lam < 1024.0) return (double)poisson_sample_f32(ph, pix, stage, (float)lam);
+  if (lam < 1024.0) return (double)poisson_sample_f32(rng, (float)lam);
+  const Philox& ph = rng.ph;
+  const uint32_t pix = rng.pix, stage = 0x4C415247u;
   uint32_t draw = 0;
   const double slam = sqrt(lam), loglam = log(lam);
   const double b = 0.931 + 2.53 * slam;
@@ -227,6 +262,21 @@ __device__ double poisson_sample(const Philox& ph, uint32_t pix, uint32_t stage,
   }
 }
 
+// one-time fill of g_ptrs_tab on the current device (synchronous on first use so that every stream sees it)
+static int ensure_ptrs_table() {
+  static std::mutex mu;
+  static bool done[64] = {false};
+  int dev = 0;
+  PSSR_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev < 64 && done[dev]) return PSSR_OK;
+  ptrs_table_kernel<<<1, 256>>>();
+  PSSR_CHECK_CUDA(cudaGetLastError());
+  PSSR_CHECK_CUDA(cudaDeviceSynchronize());
+  if (dev < 64) done[dev] = true;
+  return PSSR_OK;
+}
+
 // ------------------------------------------------------------------------------ kernel
 struct StageK {
   int kind, rng, mix_in_f32, pad;
@@ -238,6 +288,7 @@ struct StageK {
 // carries either a float32 or a float64 quantity exactly; casts reproduce NumPy's dtype flow.
 __device__ __forceinline__ double noise_chain(double val, const StageK* stages, int n_stages, int clip_between,
                                               const Philox& ph, uint32_t pix, size_t inj) {
+  RngPool rng(ph, pix);
   for (int s = 0; s < n_stages; ++s) {
     const StageK& st = stages[s];
     if (st.kind == PSSR_NOISE_POISSON) {
@@ -245,7 +296,7 @@ __device__ __forceinline__ double noise_chain(double val, const StageK* stages, 
       const float xf = (float)val;
       double y;
       if (st.rng == PSSR_RNG_INJECTED) y = (double)reinterpret_cast<const long long*>(st.injected)[inj];
-      else y = poisson_sample(ph, pix, (uint32_t)s, fmax(val, 0.0));
+      else y = poisson_sample(rng, fmax(val, 0.0));
       double t;
       if (st.mix_in_f32) t = (double)__fmul_rn(xf, (float)(1.0 - st.intensity));
       else t = __dmul_rn((double)xf, 1.0 - st.intensity);
@@ -256,9 +307,10 @@ __device__ __forceinline__ double noise_chain(double val, const StageK* stages, 
       double g;
       if (st.rng == PSSR_RNG_INJECTED) g = reinterpret_cast<const double*>(st.injected)[inj];
       else {
-        const uint4 r = ph(pix, (uint32_t)s, 0u, 0x47415553u);
-        const float rad = sqrtf(-2.0f * logf(u01f(r.x)));
-        const float z = rad * cospif(2.0f * u01f(r.y));
+        uint32_t u0, u1;
+        rng.next2(u0, u1);
+        const float rad = sqrtf(-2.0f * logf(u01f(u0)));
+        const float z = rad * cospif(2.0f * u01f(u1));
         g = __dadd_rn(st.gain, __dmul_rn(st.intensity, (double)z));
       }
       val = __dadd_rn((double)xf, g);
@@ -273,9 +325,10 @@ __device__ __forceinline__ double noise_chain(double val, const StageK* stages, 
         flipped = m & 1;
         salted = m & 2;
       } else {
-        const uint4 r = ph(pix, (uint32_t)s, 0u, 0x53414C54u);
-        flipped = u01d(r.x, r.y) <= st.intensity;
-        salted = u01d(r.z, r.w) <= 0.5;
+        uint32_t u0, u1;
+        rng.next2(u0, u1);
+        flipped = (double)u01f(u0) <= st.intensity;          // 24-bit uniforms: the rates are reproduced to 6e-8
+        salted = u01f(u1) <= 0.5f;
       }
       if (flipped) v = salted ? 1.f : 0.f;
       v = fminf(fmaxf(v, 0.f), 1.f);
@@ -319,7 +372,7 @@ __device__ __forceinline__ T load_reflect(const T* frame_base, int sheet_w, int 
 
 // KS: compile-time bound of the filter window (9: scales <= 4, 17: scales <= 8; 0: generic loops)
 template <typename T, int KS>
-__global__ void __launch_bounds__(kCrapThreads) crappify_kernel(const CrapK p) {
+__global__ void __launch_bounds__(kCrapThreads, 3) crappify_kernel(const CrapK p) {
   extern __shared__ __align__(16) uint8_t csm[];
   const int TL = p.TL;
   int* lead = reinterpret_cast<int*>(csm);                         // [max_rows] byte offset of each staged row
@@ -626,6 +679,10 @@ extern "C" int pssr_crappify(const pssr_crappify_args_t* a, void* stream) {
                         a->hr_frame0 + a->hr_frames <= a->lr_frame0 + a->lr_frames && getenv("PSSR_NO_HR_FUSE") == nullptr &&
                         ((uintptr_t)a->hr_out & 15) == 0 && ((uintptr_t)a->hr_u8_out & 3) == 0;
   if (a->lr_out != nullptr) {
+    if (a->n_stages > 0) {
+      const int rct = ensure_ptrs_table();
+      if (rct != PSSR_OK) return rct;
+    }
     const ResampleTable* tab = nullptr;
     int rc = get_table(a->hr_res, lr_res, &tab);
     if (rc != PSSR_OK) return rc;
@@ -709,6 +766,10 @@ extern "C" int pssr_noise_chain(const void* in, int32_t in_is_f64, double* out, 
                                 int32_t n_stages, int32_t clip_between, uint64_t seed, void* stream) {
   PSSR_REQUIRE(in && out && n >= 0 && stages && n_stages >= 1 && n_stages <= 4, PSSR_EINVAL, "noise_chain: bad arguments");
   if (n == 0) return PSSR_OK;
+  {
+    const int rct = ensure_ptrs_table();
+    if (rct != PSSR_OK) return rct;
+  }
   NoiseK p;
   memset(&p, 0, sizeof(p));
   for (int s = 0; s < n_stages; ++s) {
