@@ -182,10 +182,14 @@ struct RngPool {
   }
 };
 
-// PTRS constants of integer rates 0..255 (every LR pixel of an 8-bit pipeline before the first noise stage): filled once per
-// device by ptrs_table_kernel with the same float expressions the sampler uses, so a table hit and the inline path agree.
+// Integer rates 1..255 (every LR pixel of an 8-bit pipeline before the first noise stage) are sampled with Walker/Vose ALIAS
+// tables built on the host in double precision: per rate 256 outcomes k = kmin .. kmin+255 (kmin = max(0, rate - 7.5 sqrt(rate)
+// - 4): > 7.5 sigma on both sides, truncated mass < 1e-13, renormalised), thresholds quantised to 2^-32.  One pair of Philox
+// words per draw, two loads, no rejection loop -- a warp running PTRS repeats the attempt until its slowest lane accepts
+// (~3.5 rounds, ~500 instructions per pixel).  Other rates (non-integer after an earlier stage, > 255) keep Knuth / PTRS.
 struct PtrsConst { float slam, loglam, b, a, invalpha, vr, log_invalpha, enlam; };
-__device__ PtrsConst g_ptrs_tab[256];
+__device__ const uint2* g_alias_tab;      // [256][256] (threshold, alias)
+__device__ const int* g_alias_kmin;       // [256]
 __device__ __forceinline__ PtrsConst ptrs_const(float lam) {
   PtrsConst c;
   c.slam = sqrtf(lam);
@@ -198,20 +202,16 @@ __device__ __forceinline__ PtrsConst ptrs_const(float lam) {
   c.enlam = expf(-lam);
   return c;
 }
-__global__ void ptrs_table_kernel() {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 256) g_ptrs_tab[i] = ptrs_const((float)(i > 0 ? i : 1));
-}
 
 __device__ float poisson_sample_f32(RngPool& rng, float lam) {
-  PtrsConst c;
-  if (lam < 256.0f && lam == floorf(lam)) {
-    const float4* t = reinterpret_cast<const float4*>(&g_ptrs_tab[(int)lam]);
-    const float4 t0 = __ldg(t), t1 = __ldg(t + 1);
-    c.slam = t0.x; c.loglam = t0.y; c.b = t0.z; c.a = t0.w; c.invalpha = t1.x; c.vr = t1.y; c.log_invalpha = t1.z; c.enlam = t1.w;
-  } else {
-    c = ptrs_const(lam);
+  if (lam < 256.0f && lam >= 1.0f && lam == floorf(lam)) {
+    uint32_t u0, u1;
+    rng.next2(u0, u1);
+    const int il = (int)lam, j = (int)(u0 >> 24);
+    const uint2 e = __ldg(g_alias_tab + il * 256 + j);
+    return (float)(__ldg(g_alias_kmin + il) + (u1 < e.x ? j : (int)e.y));
   }
+  const PtrsConst c = ptrs_const(lam);
   if (lam < 10.0f) {
     float prod = 1.0f;
     int k = 0;
@@ -262,7 +262,7 @@ __device__ double poisson_sample(RngPool& rng, double lam) {
   }
 }
 
-// one-time fill of g_ptrs_tab on the current device (synchronous on first use so that every stream sees it)
+// one-time build + upload of the alias tables on the current device (synchronous on first use so that every stream sees them)
 static int ensure_ptrs_table() {
   static std::mutex mu;
   static bool done[64] = {false};
@@ -270,8 +270,44 @@ static int ensure_ptrs_table() {
   PSSR_CHECK_CUDA(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lock(mu);
   if (dev < 64 && done[dev]) return PSSR_OK;
-  ptrs_table_kernel<<<1, 256>>>();
-  PSSR_CHECK_CUDA(cudaGetLastError());
+  std::vector<uint2> tab(256 * 256, make_uint2(0xFFFFFFFFu, 0u));
+  std::vector<int> kmin(256, 0);
+  std::vector<double> q(256);
+  std::vector<int> small, large;
+  for (int lam = 1; lam < 256; ++lam) {
+    int k0 = (int)floor((double)lam - 7.5 * sqrt((double)lam) - 4.0);
+    if (k0 < 0) k0 = 0;
+    kmin[lam] = k0;
+    double tot = 0.0;
+    for (int j = 0; j < 256; ++j) {
+      const double k = (double)(k0 + j);
+      q[j] = exp(-(double)lam + k * log((double)lam) - lgamma(k + 1.0));
+      tot += q[j];
+    }
+    small.clear(); large.clear();
+    for (int j = 0; j < 256; ++j) {
+      q[j] = q[j] / tot * 256.0;
+      (q[j] < 1.0 ? small : large).push_back(j);
+    }
+    uint2* row = &tab[(size_t)lam * 256];
+    for (int j = 0; j < 256; ++j) row[j] = make_uint2(0xFFFFFFFFu, (unsigned)j);
+    while (!small.empty() && !large.empty()) {          // Vose's alias construction
+      const int sidx = small.back(); small.pop_back();
+      const int lidx = large.back(); large.pop_back();
+      const double thr = q[sidx] * 4294967296.0;
+      row[sidx] = make_uint2(thr >= 4294967295.0 ? 0xFFFFFFFFu : (unsigned)thr, (unsigned)lidx);
+      q[lidx] = (q[lidx] + q[sidx]) - 1.0;
+      (q[lidx] < 1.0 ? small : large).push_back(lidx);
+    }
+  }
+  uint2* d_tab = nullptr;
+  int* d_kmin = nullptr;
+  PSSR_CHECK_CUDA(cudaMalloc(&d_tab, tab.size() * sizeof(uint2)));
+  PSSR_CHECK_CUDA(cudaMalloc(&d_kmin, kmin.size() * sizeof(int)));
+  PSSR_CHECK_CUDA(cudaMemcpy(d_tab, tab.data(), tab.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+  PSSR_CHECK_CUDA(cudaMemcpy(d_kmin, kmin.data(), kmin.size() * sizeof(int), cudaMemcpyHostToDevice));
+  PSSR_CHECK_CUDA(cudaMemcpyToSymbol(g_alias_tab, &d_tab, sizeof(d_tab)));
+  PSSR_CHECK_CUDA(cudaMemcpyToSymbol(g_alias_kmin, &d_kmin, sizeof(d_kmin)));
   PSSR_CHECK_CUDA(cudaDeviceSynchronize());
   if (dev < 64) done[dev] = true;
   return PSSR_OK;
