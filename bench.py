@@ -182,10 +182,23 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        D.init_from_env("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if world > 1:
+        # NCCL announces its version on STDOUT when the first communicator is created; the contract is ONE JSON line on stdout,
+        # so stdout points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            D.init_from_env("nccl")
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     _lib.lib()   # fails loudly if the CUDA extension is missing
 
     torch.manual_seed(0)
