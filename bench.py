@@ -52,8 +52,8 @@ def _peak_sustained(burst_tf):
 
 # dram__bytes_read.sum + dram__bytes_write.sum summed over the conv launches of ONE step, from the ncu capture named below
 # (None until a capture of the current kernels is committed)
-CONV_DRAM_BYTES_PER_STEP = 3873050880
-CONV_DRAM_SOURCE = "profiles/r01_launches_v3_summary.txt (ncu launch list of `bench.py --kernels-only`, 37 conv launches of one step: 2823.8 MB read + 1049.2 MB written)"
+CONV_DRAM_BYTES_PER_STEP = 3876322304
+CONV_DRAM_SOURCE = "profiles/r01_launches_v3_summary.txt (ncu launch list of `bench.py --kernels-only`, 37 conv launches of one step: 2823.8 MB read + 1052.6 MB written)"
 # the single largest launch: Reconstruction.pre (65 -> 1024 channels @128^2, 19.629 GFLOP per tile) with the fused tail
 RECON_FLOPS_PER_TILE = 19.629e9
 RECON_DRAM_BYTES = 325600000
