@@ -113,6 +113,10 @@ typedef struct {
   int32_t hr_frames;     /* the HR frames kept by _slice_center (data.py:489-491)          */
   int32_t lr_frame0;     /* first LR frame kept by _slice_center (data.py:492-493) ...     */
   int32_t lr_frames;     /* ... and how many (= frames when n_frames[0] == n_frames[1])    */
+  /* heterogeneous sheets: optional DEVICE int32 arrays [n_sheets] with each sheet's height / width; when NULL every sheet
+   * is sheet_h x sheet_w (the reference datasets accept images of different sizes, data.py:536-551) */
+  const int32_t* sheet_hs;
+  const int32_t* sheet_ws;
 } pssr_crappify_args_t;
 
 int pssr_crappify(const pssr_crappify_args_t* args, void* stream);

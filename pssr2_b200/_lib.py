@@ -72,7 +72,8 @@ class CrappifyArgs(Structure):
                 ("stages", NoiseStage * 4), ("n_stages", c_int32), ("clip_between", c_int32),
                 ("seed", c_uint64), ("tile_index0", c_uint64),
                 ("lr_out", c_void_p), ("hr_out", c_void_p), ("hr_u8_out", c_void_p),
-                ("hr_frame0", c_int32), ("hr_frames", c_int32), ("lr_frame0", c_int32), ("lr_frames", c_int32)]
+                ("hr_frame0", c_int32), ("hr_frames", c_int32), ("lr_frame0", c_int32), ("lr_frames", c_int32),
+                ("sheet_hs", c_void_p), ("sheet_ws", c_void_p)]
 
 
 class Src(Structure):

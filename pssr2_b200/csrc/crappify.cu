@@ -378,6 +378,7 @@ __device__ __forceinline__ double noise_chain(double val, const StageK* stages, 
 struct CrapK {
   const void* const* sheets;
   int elem_bytes, sheet_h, sheet_w;
+  const int32_t *sheet_hs, *sheet_ws;      // optional per-sheet dimensions
   const int32_t *tile_sheet, *tile_frame, *tile_y, *tile_x, *tile_vh, *tile_vw;
   int n_tiles, frames, lr_frame0, lr_frames, hr_res, lr_res;
   int TL, tiles_per_side, ksize;
@@ -432,8 +433,11 @@ __global__ void __launch_bounds__(kCrapThreads, 3) crappify_kernel(const CrapK p
   const int row0 = by0.x, nrows = by1.x + by1.y - row0;
 
   const int ty = p.tile_y[tile], tx = p.tile_x[tile], vh = p.tile_vh[tile], vw = p.tile_vw[tile];
-  const size_t frame_elems = (size_t)p.sheet_h * p.sheet_w;
-  const T* sheet = reinterpret_cast<const T*>(p.sheets[p.tile_sheet[tile]]);
+  const int sheet_idx = p.tile_sheet[tile];
+  const int sheet_h = p.sheet_hs != nullptr ? p.sheet_hs[sheet_idx] : p.sheet_h;
+  const int sheet_w = p.sheet_ws != nullptr ? p.sheet_ws[sheet_idx] : p.sheet_w;
+  const size_t frame_elems = (size_t)sheet_h * sheet_w;
+  const T* sheet = reinterpret_cast<const T*>(p.sheets[sheet_idx]);
   const T* fbase = sheet + (size_t)(p.tile_frame[tile] + f) * frame_elems;
 
   // ---- stage 1: HR window -> shared (16-byte vectors on the aligned fast path) ----------
@@ -443,7 +447,7 @@ __global__ void __launch_bounds__(kCrapThreads, 3) crappify_kernel(const CrapK p
     const int vec_per_row = p.raw_pitch / 16;
     for (int i = threadIdx.x; i < nrows * vec_per_row; i += kCrapThreads) {
       const int r = i / vec_per_row, v = i - r * vec_per_row;
-      const uint8_t* g = reinterpret_cast<const uint8_t*>(fbase + (size_t)(ty + row0 + r) * p.sheet_w + tx + col0);
+      const uint8_t* g = reinterpret_cast<const uint8_t*>(fbase + (size_t)(ty + row0 + r) * sheet_w + tx + col0);
       const int ld = (int)(reinterpret_cast<uintptr_t>(g) & 15);
       if (v == 0) lead[r] = ld;
       const uint8_t* src = g - ld + (size_t)v * 16;
@@ -455,7 +459,7 @@ __global__ void __launch_bounds__(kCrapThreads, 3) crappify_kernel(const CrapK p
   } else {
     for (int i = threadIdx.x; i < nrows * ncols; i += kCrapThreads) {
       const int r = i / ncols, c = i - r * ncols;
-      reinterpret_cast<T*>(raw + (size_t)r * p.raw_pitch)[c] = load_reflect<T>(fbase, p.sheet_w, ty, tx, row0 + r, col0 + c, vh, vw);
+      reinterpret_cast<T*>(raw + (size_t)r * p.raw_pitch)[c] = load_reflect<T>(fbase, sheet_w, ty, tx, row0 + r, col0 + c, vh, vw);
     }
     for (int r = threadIdx.x; r < nrows; r += kCrapThreads) lead[r] = 0;
   }
@@ -611,9 +615,10 @@ template <typename T>
 __global__ void hr_gather_kernel(const void* const* sheets, const int32_t* tile_sheet, const int32_t* tile_frame,
                                  const int32_t* tile_y, const int32_t* tile_x, const int32_t* tile_vh,
                                  const int32_t* tile_vw, int sheet_h, int sheet_w, int hr_res, int hr_frame0,
-                                 int hr_frames, float* hr_out, uint8_t* hr_u8) {
+                                 int hr_frames, float* hr_out, uint8_t* hr_u8, const int32_t* sheet_hs, const int32_t* sheet_ws) {
   const int tile = blockIdx.z;
   const int fo = blockIdx.y;
+  if (sheet_hs != nullptr) { sheet_h = sheet_hs[tile_sheet[tile]]; sheet_w = sheet_ws[tile_sheet[tile]]; }
   const T* sheet = reinterpret_cast<const T*>(sheets[tile_sheet[tile]]);
   const T* fbase = sheet + (size_t)(tile_frame[tile] + hr_frame0 + fo) * sheet_h * sheet_w;
   const int ty = tile_y[tile], tx = tile_x[tile], vh = tile_vh[tile], vw = tile_vw[tile];
@@ -728,6 +733,9 @@ extern "C" int pssr_crappify(const pssr_crappify_args_t* a, void* stream) {
     p.elem_bytes = a->elem_bytes;
     p.sheet_h = a->sheet_h;
     p.sheet_w = a->sheet_w;
+    PSSR_REQUIRE((a->sheet_hs == nullptr) == (a->sheet_ws == nullptr), PSSR_EINVAL, "crappify: sheet_hs and sheet_ws go together");
+    p.sheet_hs = a->sheet_hs;
+    p.sheet_ws = a->sheet_ws;
     p.tile_sheet = a->tile_sheet; p.tile_frame = a->tile_frame; p.tile_y = a->tile_y; p.tile_x = a->tile_x;
     p.tile_vh = a->tile_vh; p.tile_vw = a->tile_vw;
     p.n_tiles = a->n_tiles; p.frames = a->frames; p.lr_frame0 = a->lr_frame0; p.lr_frames = a->lr_frames;
@@ -787,11 +795,11 @@ extern "C" int pssr_crappify(const pssr_crappify_args_t* a, void* stream) {
     if (a->elem_bytes == 1)
       hr_gather_kernel<uint8_t><<<grid, 256, 0, st>>>(a->sheets, a->tile_sheet, a->tile_frame, a->tile_y, a->tile_x, a->tile_vh,
                                                       a->tile_vw, a->sheet_h, a->sheet_w, a->hr_res, a->hr_frame0, a->hr_frames,
-                                                      a->hr_out, a->hr_u8_out);
+                                                      a->hr_out, a->hr_u8_out, a->sheet_hs, a->sheet_ws);
     else
       hr_gather_kernel<uint16_t><<<grid, 256, 0, st>>>(a->sheets, a->tile_sheet, a->tile_frame, a->tile_y, a->tile_x, a->tile_vh,
                                                        a->tile_vw, a->sheet_h, a->sheet_w, a->hr_res, a->hr_frame0, a->hr_frames,
-                                                       a->hr_out, a->hr_u8_out);
+                                                       a->hr_out, a->hr_u8_out, a->sheet_hs, a->sheet_ws);
     count_launch();
     PSSR_CHECK_CUDA(cudaGetLastError());
   }

@@ -142,8 +142,8 @@ class _DeviceDataset(Dataset):
     def _upload(self, arrays, device):
         shapes = {tuple(a.shape[1:]) for a in arrays}
         dtypes = {str(a.dtype).replace("torch.", "").replace("int16", "uint16").replace("uuint16", "uint16") for a in arrays}
-        if len(shapes) != 1 or len(dtypes) != 1:
-            raise NotImplementedError("all images of one dataset must share height, width and dtype on the device path")
+        if len(dtypes) != 1:
+            raise NotImplementedError("all images of one dataset must share their dtype on the device path")
         self.device = torch.device(device)
         self._sheets = []
         self._sheet_events = {}     # sheet index -> upload-complete event not yet waited for by the compute stream
@@ -166,7 +166,7 @@ class _DeviceDataset(Dataset):
             self._sheet_events[i] = ev
         self._upload_stream = up
         self._frames_total = [a.shape[0] for a in arrays]
-        self._shape = next(iter(shapes))
+        self._shapes = [tuple(a.shape[1:]) for a in arrays]          # per image (heights / widths may differ)
 
     def _wait_sheets(self, sheet_ids):
         """Orders the current stream after the upload of the given sheets (each event is waited for once)."""
@@ -338,7 +338,7 @@ class ImageDataset(_DeviceDataset):
 
     def _locate(self, idx):
         image_idx, local = _get_image_idx(idx, self.slices)
-        h, w = self._shape
+        h, w = self._shapes[image_idx]
         res = self._lr_mode_res if self.is_lr else self.hr_res
         if [h, w] == [res] * 2:                                   # _square_crop, data.py:536-546
             y = x = 0

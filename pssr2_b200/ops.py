@@ -32,8 +32,8 @@ class TileTable:
         self.sheets = [_cuda(s, "sheet").contiguous() for s in sheets]
         s0 = self.sheets[0]
         for s in self.sheets:
-            if s.dim() != 3 or s.shape[1:] != s0.shape[1:] or s.dtype != s0.dtype:
-                raise ValueError("all sheets must be [frames, H, W] with one shape and dtype")
+            if s.dim() != 3 or s.dtype != s0.dtype:
+                raise ValueError("all sheets must be [frames, H, W] with one dtype")
         if s0.dtype == torch.uint8:
             self.elem_bytes = 1
         elif s0.dtype in (torch.uint16, torch.int16):
@@ -42,6 +42,11 @@ class TileTable:
             raise TypeError(f"sheets must be uint8 or uint16, got {s0.dtype}")
         self.sheet_h, self.sheet_w = int(s0.shape[1]), int(s0.shape[2])
         self.ptrs = torch.tensor([s.data_ptr() for s in self.sheets], dtype=torch.int64, device=dev)
+        # sheets of different sizes: per-sheet dimension arrays travel with the table
+        self.sheet_dims = None
+        if any(s.shape[1:] != s0.shape[1:] for s in self.sheets):
+            self.sheet_dims = torch.tensor([[int(s.shape[1]) for s in self.sheets], [int(s.shape[2]) for s in self.sheets]],
+                                           dtype=torch.int32, device=dev)
         # one host->device copy for the six index columns
         cols = torch.as_tensor(np.asarray([tile_sheet, tile_frame, tile_y, tile_x, tile_vh, tile_vw], dtype=np.int32)).to(dev)
         self.tile_sheet, self.tile_frame, self.tile_y, self.tile_x, self.tile_vh, self.tile_vw = (cols[i] for i in range(6))
@@ -72,6 +77,8 @@ def crappify(table: TileTable, hr_res, lr_scale, stages, *, frames=1, lr_frame0=
     a.n_sheets = len(table.sheets)
     a.elem_bytes = table.elem_bytes
     a.sheet_h, a.sheet_w = table.sheet_h, table.sheet_w
+    if table.sheet_dims is not None:
+        a.sheet_hs, a.sheet_ws = table.sheet_dims[0].data_ptr(), table.sheet_dims[1].data_ptr()
     a.tile_sheet, a.tile_frame = table.tile_sheet.data_ptr(), table.tile_frame.data_ptr()
     a.tile_y, a.tile_x = table.tile_y.data_ptr(), table.tile_x.data_ptr()
     a.tile_vh, a.tile_vw = table.tile_vh.data_ptr(), table.tile_vw.data_ptr()

@@ -171,3 +171,33 @@ def test_error_behaviour_callbacks_and_file_output(tmp_path):
     # an empty validation split predicts nothing
     ds.val_idx = []
     assert predict_images(model, ds, device="cuda", out_dir=None) == {}
+
+
+def test_heterogeneous_image_sizes():
+    """Images / sheets of different sizes in one dataset (the reference crops / pads / tiles each image on its own,
+    pssr/data.py:100-120, :236-256, :536-551): per-sheet dimensions travel to the gather kernel."""
+    from pssr2_b200.data import ImageDataset, SlidingDataset
+    from pssr2_b200.predict import predict_images
+    rng = np.random.default_rng(21)
+    ims = [rng.integers(0, 256, (1, h, w)).astype(np.uint8) for h, w in ((256, 256), (200, 240), (300, 280), (131, 256))]
+    ds = ImageDataset(ims, hr_res=256, lr_scale=4, n_frames=1, val_split=1, crappifier=None)
+    assert len(ds) == 4 and ds.crop_res == 256
+    for i, im in enumerate(ims):
+        hr, lr = ds[i]
+        want_hr, want_lr = OP.gen_pair(im, 256, 4, None)
+        assert np.array_equal(hr.cpu().numpy(), want_hr) and np.array_equal(lr.cpu().numpy(), want_lr), f"image {i}"
+    sheets = {"a": rng.integers(0, 256, (1, 320, 448)).astype(np.uint16), "b": rng.integers(0, 256, (1, 448, 256)).astype(np.uint16)}
+    sd = SlidingDataset(sheets, hr_res=128, lr_scale=4, overlap=32, val_split=1, crappifier=None)
+    counts = [OP.n_tiles(s.shape[-2:], 128, 96) for s in sheets.values()]
+    assert len(sd) == sum(a * b for a, b in counts)
+    idx = 0
+    for name, s in sheets.items():
+        ta, tb = OP.n_tiles(s.shape[-2:], 128, 96)
+        for t in range(ta * tb):
+            hr, lr = sd[idx]
+            want_hr, want_lr = OP.gen_pair(OP.sliding_window(s, 128, 96, None, 1, t), 128, 4, None)
+            assert np.array_equal(hr.cpu().numpy(), want_hr) and np.array_equal(lr.cpu().numpy(), want_lr), (name, t)
+            idx += 1
+    model, _ = _model()
+    preds = predict_images(model, sd, device="cuda", batch_size=5, out_dir=None)
+    assert len(preds) == len(sd) and all(v.shape == (1, 128, 128) for v in preds.values())
