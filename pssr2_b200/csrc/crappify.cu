@@ -402,8 +402,10 @@ struct CrapK {
 template <typename T>
 __device__ __forceinline__ T load_reflect(const T* frame_base, int sheet_w, int ty, int tx, int r, int c, int vh,
                                           int vw) {
-  const int rr = r < vh ? r : 2 * vh - 2 - r;   // np.pad(mode="reflect")
-  const int cc = c < vw ? c : 2 * vw - 2 - c;
+  // np.pad(mode="reflect"): period 2n-2, repeated when the pad is wider than the image (n == 1: the single value)
+  int rr = r, cc = c;
+  if (r >= vh) { const int per = 2 * vh - 2; rr = per > 0 ? r % per : 0; if (rr >= vh) rr = per - rr; }
+  if (c >= vw) { const int per = 2 * vw - 2; cc = per > 0 ? c % per : 0; if (cc >= vw) cc = per - cc; }
   return frame_base[(size_t)(ty + rr) * sheet_w + tx + cc];
 }
 

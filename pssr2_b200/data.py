@@ -346,8 +346,6 @@ class ImageDataset(_DeviceDataset):
         else:
             size = min(h, w, res)
             y, x = (h - size) // 2, (w - size) // 2
-        if res - size > size - 1:
-            raise NotImplementedError("reflect padding wider than the image itself is not supported")
         f0 = 0 if self.n_frames is None else (local % self.slices[image_idx]) * max(self.n_frames)
         return image_idx, f0, y, x, size, size
 

@@ -179,9 +179,10 @@ def test_heterogeneous_image_sizes():
     from pssr2_b200.data import ImageDataset, SlidingDataset
     from pssr2_b200.predict import predict_images
     rng = np.random.default_rng(21)
-    ims = [rng.integers(0, 256, (1, h, w)).astype(np.uint8) for h, w in ((256, 256), (200, 240), (300, 280), (131, 256))]
+    # (100, 90): the reflect pad (166) is wider than the image, np.pad repeats the reflection
+    ims = [rng.integers(0, 256, (1, h, w)).astype(np.uint8) for h, w in ((256, 256), (200, 240), (300, 280), (131, 256), (100, 90))]
     ds = ImageDataset(ims, hr_res=256, lr_scale=4, n_frames=1, val_split=1, crappifier=None)
-    assert len(ds) == 4 and ds.crop_res == 256
+    assert len(ds) == 5 and ds.crop_res == 256
     for i, im in enumerate(ims):
         hr, lr = ds[i]
         want_hr, want_lr = OP.gen_pair(im, 256, 4, None)
