@@ -223,7 +223,9 @@ typedef struct {
   float* xnorm_f32;      /* [B][C][H][W] fp32 normalised input (the final skip), may be NULL */
   int32_t cols;          /* channels per pixel of im2col: 64 (0 = 64) or 16 when 9*C <= 16 -- the consuming
                             convolutions' TMA boxes zero-fill channels >= cols, 4x less HBM traffic         */
-  int32_t reserved;
+  int32_t centre_only;   /* 1: no taps -- im2col is the normalised input itself, NHWC [B][H][W][cols] with cols a multiple
+                            of 8 >= C (inputs with more than 7 channels: the first convolution is then an ordinary 3x3
+                            segment over this tensor, whose TMA zero fill IS the post-normalisation padding)            */
 } pssr_prep_desc_t;
 
 typedef struct {

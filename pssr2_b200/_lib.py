@@ -97,7 +97,7 @@ class ConvDesc(Structure):
 class PrepDesc(Structure):
     _fields_ = [("x", c_void_p), ("x_u8", c_int32), ("B", c_int32), ("C", c_int32), ("H", c_int32),
                 ("W", c_int32), ("scale", c_void_p), ("shift", c_void_p), ("im2col", c_void_p),
-                ("xnorm_f32", c_void_p), ("cols", c_int32), ("reserved", c_int32)]
+                ("xnorm_f32", c_void_p), ("cols", c_int32), ("centre_only", c_int32)]
 
 
 class PoolDesc(Structure):

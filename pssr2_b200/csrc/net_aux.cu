@@ -80,7 +80,47 @@ __global__ void __launch_bounds__(kPrepThreads) prep_im2col_kernel(pssr_prep_des
   }
 }
 
+// Inputs with more than 7 channels: the normalised input itself as an NHWC 16-bit tensor (one thread per pixel and 8-channel group)
+__global__ void prep_nhwc_kernel(pssr_prep_desc_t d, int fp16) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int groups = d.cols / 8;
+  const long long total = (long long)d.B * d.H * d.W * groups;
+  const size_t hw = (size_t)d.H * d.W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const long long pix = i / groups;
+    const int n = (int)(pix / (long long)hw);
+    const size_t rem = (size_t)(pix - (long long)n * (long long)hw);
+    uint32_t o[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      float v = 0.f;
+      if (c < d.C) {
+        const size_t idx = ((size_t)n * d.C + c) * hw + rem;
+        const float raw = d.x_u8 ? (float)reinterpret_cast<const uint8_t*>(d.x)[idx] : reinterpret_cast<const float*>(d.x)[idx];
+        v = __fadd_rn(__fmul_rn(__fsub_rn(__fdiv_rn(raw, 128.f), 1.f), d.scale[c]), d.shift[c]);
+        if (d.xnorm_f32 != nullptr) d.xnorm_f32[idx] = v;
+      }
+      o[j >> 1] |= (uint32_t)pack1(v, fp16) << (16 * (j & 1));
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(d.im2col) + (size_t)pix * d.cols + g * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 int prep_launch(const pssr_prep_desc_t& d, int dtype, cudaStream_t stream) {
+  if (d.centre_only) {
+    PSSR_REQUIRE(d.x && d.im2col && d.scale && d.shift, PSSR_EINVAL, "prep: null pointer");
+    PSSR_REQUIRE(d.C >= 1 && d.cols % 8 == 0 && d.cols >= d.C && d.cols <= 64, PSSR_EUNSUP, "prep: NHWC mode needs C <= cols <= 64, cols %% 8 == 0");
+    const long long total = (long long)d.B * d.H * d.W * (d.cols / 8);
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)device_sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    PSSR_CHECK_CUDA(launch_pdl(prep_nhwc_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, d, (int)(dtype == PSSR_DT_FP16)));
+    count_launch();
+    return PSSR_OK;
+  }
   PSSR_REQUIRE(d.C >= 1 && d.C * 9 <= 64, PSSR_EUNSUP, "prep: %d input channels unsupported (9*C must be <= 64)", d.C);
   PSSR_REQUIRE(d.x && d.im2col && d.scale && d.shift, PSSR_EINVAL, "prep: null pointer");
   PSSR_REQUIRE(d.cols == 0 || d.cols == 64 || (d.cols == 16 && d.C * 9 <= 16), PSSR_EUNSUP, "prep: im2col width %d unsupported", d.cols);

@@ -146,7 +146,8 @@ class _PlanModule(nn.Module):
         rec = self.reconstruction
         wp = rec.pre.weight.detach().float()
         bp = rec.pre.bias.detach().float()
-        parts = [wp[:, :hid0], _im2col_parts(wp[:, hid0:])]
+        wide = bool(getattr(xcol, "wide_input", False))          # > 7 input channels: xcol is the normalised input, a 3x3 segment
+        parts = [wp[:, :hid0], wp[:, hid0:] if wide else _im2col_parts(wp[:, hid0:])]
         wpk = pack_weight(parts, plan.dtype, s)
         wc = rec.conv.weight.detach().float()
         bc = rec.conv.bias.detach().float().contiguous()
@@ -154,7 +155,7 @@ class _PlanModule(nn.Module):
         if out is None:
             out = torch.empty(B, cout, H * s, W * s, dtype=torch.float32, device=dev)
             out_u8 = torch.empty(B, 1, H * s, W * s, dtype=torch.uint8, device=dev)
-        srcs, segs = [View(final), xcol], [(0, 9, ceil_div(hid0, 64)), (1, 1, 1)]
+        srcs, segs = [View(final), xcol], [(0, 9, ceil_div(hid0, 64)), (1, 9 if wide else 1, 1)]
         plan.flops += 2 * wp.numel() * B * H * W + 2 * wc.numel() * B * H * s * W * s
         if cout == 1 and hid0 % 32 == 0 and W >= 1 and self.fuse_tail:
             # fused tail: relu(pre) is reduced against the 3x3 tail weights inside the conv epilogue (fp32), the
@@ -300,8 +301,12 @@ class ResUNet(_PlanModule):
         bn = self.norm
         sc = (bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + bn.eps)).contiguous()
         sh = (bn.bias.detach().float() - bn.running_mean.float() * sc).contiguous()
-        im2col = z(B, H, W, 16 if C * 9 <= 16 else 64)      # narrow im2col: the convs' TMA boxes zero-fill channels >= 16
-        xcol = View(im2col)
+        wide_in = C * 9 > 64          # more than 7 input channels: no im2col, the normalised input is an ordinary 3x3 source
+        if C > 64:
+            raise NotImplementedError(f"{C} input channels: at most 64 are supported")
+        im2col = z(B, H, W, ((C + 7) // 8) * 8 if wide_in else (16 if C * 9 <= 16 else 64))      # narrow im2col: TMA boxes zero-fill channels >= 16
+        xcol = View(im2col, 0, C) if wide_in else View(im2col)
+        xcol.wide_input = wide_in
         # Optional sub-batches at level 0 (PSSR_SUBBATCH_MB > 0): the level-0 encoder block and the last decoder block +
         # Reconstruction run chunk by chunk so that a layer finds its input (<= that many MB per tensor) in the 126 MB L2 instead
         # of HBM.  MEASURED on B200 (batch 64, 128^2): forward 3.27 ms without, 3.38 / 3.50 / 3.86 ms with 64 / 32 / 16 MB chunks --
@@ -329,7 +334,11 @@ class ResUNet(_PlanModule):
         for l in range(L):
             blk = self.encoder[l]
             h, w = H >> l, W >> l
-            if l == 0:
+            if l == 0 and wide_in:
+                srcs, segs = [xcol], [(0, 9, 1)]
+                w0f = lambda wt: [wt]
+                wrf = lambda wt: ([wt], [(0, 1, 1)])
+            elif l == 0:
                 srcs, segs = [xcol], [(0, 1, 1)]
                 w0f = lambda wt: [_im2col_parts(wt)]
                 wrf = lambda wt: ([_im2col_centre(wt)], [(0, 1, 1)])
@@ -341,9 +350,10 @@ class ResUNet(_PlanModule):
             if l == 0:
                 pooled = z(B, h // 2, w // 2, hid[l])
                 for b0, b1 in chunks:
-                    plan.prep(x_in[b0:b1], sc, sh, im2col[b0:b1])
+                    plan.prep(x_in[b0:b1], sc, sh, im2col[b0:b1], centre_only=wide_in)
                     dst = View(cat[l][b0:b1], up[l], hid[l])
-                    self._emit_resblock(plan, blk, [View(im2col[b0:b1])], segs, w0f, wrf, [sv[:b1 - b0] for sv in scratch(l)], dst, 1,
+                    xc = View(im2col[b0:b1], 0, C) if wide_in else View(im2col[b0:b1])
+                    self._emit_resblock(plan, blk, [xc], segs, w0f, wrf, [sv[:b1 - b0] for sv in scratch(l)], dst, 1,
                                         b1 - b0, h, w)
                     plan.maxpool(dst, View(pooled[b0:b1]))
                 cur = View(pooled)
@@ -378,8 +388,9 @@ class ResUNet(_PlanModule):
                     fin = final[:b1 - b0]
                     self._emit_resblock(plan, blk, [View(cat[l][b0:b1], 0, cin)], segs, w0f, wrf, [sv[:b1 - b0] for sv in scratch(l)],
                                         View(fin), 1, b1 - b0, h, w)
-                    self._emit_reconstruction(plan, fin, View(im2col[b0:b1]), b1 - b0, H, W, dev, out[b0:b1], out_u8[b0:b1],
-                                              zshared[0])
+                    xc = View(im2col[b0:b1], 0, C) if wide_in else View(im2col[b0:b1])
+                    xc.wide_input = wide_in
+                    self._emit_reconstruction(plan, fin, xc, b1 - b0, H, W, dev, out[b0:b1], out_u8[b0:b1], zshared[0])
                     zshared[0] = self._zbuf
 
         plan.finalize()
@@ -547,9 +558,13 @@ class RDResUNet(_PlanModule):
         bn = self.norm
         sc = (bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + bn.eps)).contiguous()
         sh = (bn.bias.detach().float() - bn.running_mean.float() * sc).contiguous()
-        im2col = z(B, H, W, 16 if C * 9 <= 16 else 64)      # narrow im2col: the convs' TMA boxes zero-fill channels >= 16
-        plan.prep(x_in, sc, sh, im2col)
-        xcol = View(im2col)
+        wide_in = C * 9 > 64          # more than 7 input channels: no im2col, the normalised input is an ordinary 3x3 source
+        if C > 64:
+            raise NotImplementedError(f"{C} input channels: at most 64 are supported")
+        im2col = z(B, H, W, ((C + 7) // 8) * 8 if wide_in else (16 if C * 9 <= 16 else 64))      # narrow im2col: TMA boxes zero-fill channels >= 16
+        plan.prep(x_in, sc, sh, im2col, centre_only=wide_in)
+        xcol = View(im2col, 0, C) if wide_in else View(im2col)
+        xcol.wide_input = wide_in
 
         # ---- encoder geometry: which stage outputs are decoder skips, and where they live -----------------
         n_st = len(enc.dense_stages)

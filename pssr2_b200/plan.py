@@ -140,17 +140,21 @@ class Plan:
                                           issued_flops=2 * B * Ho * Wo * n * ktot, tail_weight=tail_weight, tail_z=tail_z,
                                           tail_layout=tail_layout)))
 
-    def prep(self, x, scale, shift, im2col, xnorm=None):
+    def prep(self, x, scale, shift, im2col, xnorm=None, centre_only=False):
+        """centre_only: im2col is the normalised input itself, NHWC [B, H, W, cols] (inputs with more than 7 channels)."""
         B, C, H, W = x.shape
         d = PrepDesc(x.data_ptr(), 1 if x.dtype == torch.uint8 else 0, B, C, H, W, scale.data_ptr(), shift.data_ptr(),
-                     im2col.data_ptr(), xnorm.data_ptr() if xnorm is not None else None, im2col.shape[3], 0)
-        assert im2col.shape[3] in (16, 64) and C * 9 <= im2col.shape[3]
+                     im2col.data_ptr(), xnorm.data_ptr() if xnorm is not None else None, im2col.shape[3], 1 if centre_only else 0)
+        if centre_only:
+            assert im2col.shape[3] % 8 == 0 and C <= im2col.shape[3] <= 64
+        else:
+            assert im2col.shape[3] in (16, 64) and C * 9 <= im2col.shape[3]
         op = Op()
         op.kind = OP_PREP
         op.u.prep = d
         self.ops.append(op)
         self.keep += [x, scale, shift, im2col, xnorm]
-        self.records.append(("prep", dict(x=x, scale=scale, shift=shift, im2col=im2col, xnorm=xnorm)))
+        self.records.append(("prep", dict(x=x, scale=scale, shift=shift, im2col=im2col, xnorm=xnorm, centre_only=centre_only)))
 
     def maxpool(self, src: View, dst: View):
         d = PoolDesc(src.buf.data_ptr(), src.cstride, src.choff, dst.buf.data_ptr(), dst.cstride, dst.choff, src.B, src.H,

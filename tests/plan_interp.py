@@ -20,6 +20,10 @@ def run_records(plan):
             x = r["x"].float()
             B, C, H, W = x.shape
             xn = (x / 128 - 1) * r["scale"].view(1, -1, 1, 1) + r["shift"].view(1, -1, 1, 1)
+            if r.get("centre_only"):
+                r["im2col"].zero_()
+                r["im2col"][..., :C] = xn.permute(0, 2, 3, 1).to(r["im2col"].dtype)
+                continue
             cols = F.unfold(xn, 3, padding=1).view(B, C * 9, H, W)
             r["im2col"].zero_()
             r["im2col"][..., :C * 9] = cols.permute(0, 2, 3, 1).to(r["im2col"].dtype)

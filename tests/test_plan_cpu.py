@@ -19,7 +19,8 @@ def dry_run():
 
 
 @pytest.mark.parametrize("cfg", [dict(), dict(channels=[3, 3], hidden=[64, 128, 256], scale=2, depth=1),
-                                 dict(channels=[5, 1], hidden=[64, 128], scale=8, depth=0)])
+                                 dict(channels=[5, 1], hidden=[64, 128], scale=8, depth=0),
+                                 dict(channels=[9, 1], hidden=[64, 128], scale=2, depth=1)])   # > 7 channels: no im2col, 3x3 over the input
 def test_resunet_plan_matches_oracle_on_cpu(dry_run, cfg):
     from pssr2_b200.models import ResUNet
     torch.manual_seed(0)
