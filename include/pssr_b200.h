@@ -11,8 +11,9 @@
  *  - every function returns 0 on success, a negative PSSR_E* code on failure; the message
  *    is available (thread-local) from pssr_last_error().
  *  - all pointers are DEVICE pointers owned by the caller unless the name says host_;
- *    the library never frees caller memory and never allocates behind the caller's back
- *    except inside an opaque plan (pssr_plan_create / pssr_plan_destroy).
+ *    the library never frees caller memory and allocates only inside an opaque plan
+ *    (pssr_plan_create / pssr_plan_destroy) and, once per device, a few constant tables
+ *    (resample coefficients per geometry, Poisson alias tables: < 1 MB).
  *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous w.r.t. the host.
  *  - images are row-major, innermost dimension last; shapes are explicit.
  */
