@@ -30,6 +30,17 @@ if r == 0:
 bufs = D.gather_tensor_to_rank0(torch.full((3,), r, dtype=torch.uint8))
 if r == 0:
     assert [int(b[0]) for b in bufs] == [0, 1]
+# image gather (the NCCL path of predict_images; the logic is backend-agnostic): uneven shares, then an empty rank
+for n_items in (11, 1):
+    lo2, hi2 = D.shard_range(n_items)
+    local = torch.arange(lo2, hi2, dtype=torch.uint8).view(-1, 1, 1, 1).expand(-1, 1, 2, 3).contiguous()
+    if hi2 == lo2:
+        local = torch.zeros(0, dtype=torch.uint8)
+    allp = D.gather_images_nccl(local, n_items)
+    if r == 0:
+        assert allp.shape == (n_items, 1, 2, 3) and allp[:, 0, 0, 0].tolist() == list(range(n_items)), allp.shape
+    else:
+        assert allp is None
 dist.barrier()
 sys.stdout.write("rank" + str(r) + "-ok\n"); sys.stdout.flush()
 '''
