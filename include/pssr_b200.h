@@ -179,7 +179,7 @@ typedef struct {
 typedef struct {
   pssr_src_t srcs[3];
   int32_t n_srcs;
-  pssr_kseg_t segs[4];
+  pssr_kseg_t segs[6];
   int32_t n_segs;
   const void* weights;   /* [n][k_total] 16-bit, K-major, K ordered seg -> tap -> cblock -> c */
   const float* bias;     /* [n] fp32 (BatchNorm shift and conv biases folded)               */
@@ -208,10 +208,21 @@ typedef struct {
    * summed by different threads and stored separately (two 6 x 4 windows):
    *     z[b][y][e*24 + (oi+1)*4 + (oj+1-2e)][x],  e = j' / 2        -- 48 floats per LR pixel instead of 144.          */
   int32_t tail_layout;
-  int32_t reserved2;
+  /* Compensated ("fp16c") precision, the mode that meets the 1e-2 max-abs bar of the network output: a 16-bit tensor t is
+   * carried as the pair (hi = rn16(t), lo = rn16(t - hi)) where it feeds a sensitive layer, and the K segments of that layer
+   * multiply hi*W_hi + lo*W_hi + hi*W_lo (the host packs W_hi / W_lo as ordinary K blocks; segments that read the same
+   * source share its staged tile).
+   *   out_lo     : optional second 16-bit NHWC output = rn16(y - rn16(y)) of the activated result y, same pixel grid as out
+   *   tail_flags : PSSR_TAIL_COMP -- the fused tail projects hi and lo of relu(pre) on W_hi and W_lo of the tail weights
+   *                (lo rides an e5m2 kind::f8f6f4 pass: it only has to be known to a few bits)                              */
+  int32_t tail_flags;
+  void* out_lo;
+  int32_t out_lo_cstride;
+  int32_t out_lo_choff;
 } pssr_conv_desc_t;
 #define PSSR_TAIL_TAPS 0
 #define PSSR_TAIL_WINDOW48 1
+#define PSSR_TAIL_COMP 1
 
 typedef struct {
   const void* x;         /* [B][C][H][W] float32 (0..255) or uint8 if x_u8                   */
@@ -221,6 +232,7 @@ typedef struct {
   const float* shift;    /* [C] BN shift  t                                                   */
   void* im2col;          /* NHWC 16-bit [B][H][W][cols]: channel (c*9+tap) = norm(x) at the tap,
                             zero outside the image and for channels >= 9*C                   */
+  void* im2col_lo;       /* optional: same layout, rn16(v - rn16(v)) of every value v of im2col (compensated precision) */
   float* xnorm_f32;      /* [B][C][H][W] fp32 normalised input (the final skip), may be NULL */
   int32_t cols;          /* channels per pixel of im2col: 64 (0 = 64) or 16 when 9*C <= 16 -- the consuming
                             convolutions' TMA boxes zero-fill channels >= cols, 4x less HBM traffic         */

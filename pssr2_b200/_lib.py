@@ -13,7 +13,7 @@ from ctypes import (POINTER, Structure, Union, c_char_p, c_double, c_float, c_in
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libpssr_b200.so")
-SOURCES = ["api.cu", "conv_igemm.cu", "conv_strip.cu", "conv_v3.cu", "net_aux.cu", "rdnet.cu", "crappify.cu", "stitch.cu", "metrics.cu"]
+SOURCES = ["api.cu", "conv_igemm.cu", "conv_v3.cu", "net_aux.cu", "rdnet.cu", "crappify.cu", "stitch.cu", "metrics.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
@@ -86,17 +86,18 @@ class KSeg(Structure):
 
 
 class ConvDesc(Structure):
-    _fields_ = [("srcs", Src * 3), ("n_srcs", c_int32), ("segs", KSeg * 4), ("n_segs", c_int32),
+    _fields_ = [("srcs", Src * 3), ("n_srcs", c_int32), ("segs", KSeg * 6), ("n_segs", c_int32),
                 ("weights", c_void_p), ("bias", c_void_p), ("n", c_int32), ("n_valid", c_int32),
                 ("Ho", c_int32), ("Wo", c_int32), ("B", c_int32), ("out", c_void_p),
                 ("out_cstride", c_int32), ("out_choff", c_int32), ("shuffle", c_int32), ("act", c_int32),
                 ("out_scale", c_void_p), ("out_f32", c_void_p), ("tail_weight", c_void_p), ("tail_z", c_void_p),
-                ("tail_layout", c_int32), ("reserved2", c_int32)]
+                ("tail_layout", c_int32), ("tail_flags", c_int32), ("out_lo", c_void_p),
+                ("out_lo_cstride", c_int32), ("out_lo_choff", c_int32)]
 
 
 class PrepDesc(Structure):
     _fields_ = [("x", c_void_p), ("x_u8", c_int32), ("B", c_int32), ("C", c_int32), ("H", c_int32),
-                ("W", c_int32), ("scale", c_void_p), ("shift", c_void_p), ("im2col", c_void_p),
+                ("W", c_int32), ("scale", c_void_p), ("shift", c_void_p), ("im2col", c_void_p), ("im2col_lo", c_void_p),
                 ("xnorm_f32", c_void_p), ("cols", c_int32), ("centre_only", c_int32)]
 
 

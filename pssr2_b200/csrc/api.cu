@@ -58,9 +58,7 @@ int pssr_plan_create(const pssr_op_t* ops, int32_t n_ops, int32_t dtype, pssr_pl
     switch (op.kind) {
       case PSSR_OP_CONV: {
         ConvOp c;
-        int rc = v3_supported(op.u.conv)      ? v3_prepare(op.u.conv, dtype, c)
-                 : strip_supported(op.u.conv) ? strip_prepare(op.u.conv, dtype, c)
-                                              : conv_prepare(op.u.conv, dtype, c);
+        int rc = v3_supported(op.u.conv) ? v3_prepare(op.u.conv, dtype, c) : conv_prepare(op.u.conv, dtype, c);
         if (rc != PSSR_OK) {
           char msg[400];
           snprintf(msg, sizeof(msg), "%s", g_err);
@@ -122,7 +120,7 @@ int pssr_plan_run_range(pssr_plan_t* plan, int32_t first, int32_t count, void* s
         const int ci = plan->conv_index[i];
         const void* tm = reinterpret_cast<uint8_t*>(plan->tmaps_dev) + (size_t)ci * kTmapsPerConv * sizeof(CUtensorMap);
         const int variant = plan->convs[ci].variant;
-        rc = variant == 3 ? v3_launch(plan->convs[ci], tm, st) : variant == 2 ? strip_launch(plan->convs[ci], tm, st) : conv_launch(plan->convs[ci], tm, st);
+        rc = variant == 3 ? v3_launch(plan->convs[ci], tm, st) : conv_launch(plan->convs[ci], tm, st);
         break;
       }
       case PSSR_OP_PREP:

@@ -32,7 +32,7 @@ static constexpr int kMaxStages = 8;
 struct ConvKParams {
   const CUtensorMap* tmaps;  // device: [0..2] = sources, [3] = weights
   int n_segs;
-  int seg_src[4], seg_taps[4], seg_cblocks[4];
+  int seg_src[6], seg_taps[6], seg_cblocks[6];
   int num_kb;
   int Ho, Wo, B;
   int BW, BH, BNI;
@@ -45,6 +45,8 @@ struct ConvKParams {
   const float* out_scale;
   uint16_t* out;
   float* out_f32;
+  uint16_t* out_lo;
+  int lo_cstride, lo_choff;
   int out_cstride, out_choff, shuffle, cps, act, fp16;
   int Hout, Wout;
 };
@@ -230,6 +232,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                 o.z = pack2(f[4], f[5], p.fp16);
                 o.w = pack2(f[6], f[7], p.fp16);
                 *reinterpret_cast<uint4*>(p.out + pix * p.out_cstride + p.out_choff + cc) = o;
+                if (p.out_lo != nullptr) {      // compensated precision: what the 16-bit rounding dropped
+                  uint4 l;
+                  l.x = pack2(f[0] - unpack1((uint16_t)(o.x & 0xffffu), p.fp16), f[1] - unpack1((uint16_t)(o.x >> 16), p.fp16), p.fp16);
+                  l.y = pack2(f[2] - unpack1((uint16_t)(o.y & 0xffffu), p.fp16), f[3] - unpack1((uint16_t)(o.y >> 16), p.fp16), p.fp16);
+                  l.z = pack2(f[4] - unpack1((uint16_t)(o.z & 0xffffu), p.fp16), f[5] - unpack1((uint16_t)(o.z >> 16), p.fp16), p.fp16);
+                  l.w = pack2(f[6] - unpack1((uint16_t)(o.w & 0xffffu), p.fp16), f[7] - unpack1((uint16_t)(o.w >> 16), p.fp16), p.fp16);
+                  *reinterpret_cast<uint4*>(p.out_lo + pix * p.lo_cstride + p.lo_choff + cc) = l;
+                }
               }
               if (p.out_f32 != nullptr) {
                 float4* d = reinterpret_cast<float4*>(p.out_f32 + pix * p.out_cstride + p.out_choff + cc);
@@ -282,7 +292,7 @@ static int floor_pow2(int v) {
 int conv_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
   EncodeTiledFn enc = get_encode_fn();
   PSSR_REQUIRE(enc != nullptr, PSSR_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-  PSSR_REQUIRE(d.n_srcs >= 1 && d.n_srcs <= 3 && d.n_segs >= 1 && d.n_segs <= 4, PSSR_EINVAL,
+  PSSR_REQUIRE(d.n_srcs >= 1 && d.n_srcs <= 3 && d.n_segs >= 1 && d.n_segs <= 6, PSSR_EINVAL,
                "conv: n_srcs/n_segs out of range");
   PSSR_REQUIRE(d.n >= 32 && d.n % 32 == 0, PSSR_EUNSUP, "conv: n=%d must be a positive multiple of 32", d.n);
   PSSR_REQUIRE(d.n_valid > 0 && d.n_valid <= d.n && d.n_valid % 8 == 0, PSSR_EUNSUP,
@@ -294,7 +304,7 @@ int conv_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
   PSSR_REQUIRE(d.shuffle == 1 || d.n == d.n_valid, PSSR_EUNSUP, "conv: padded N with pixel shuffle unsupported");
   PSSR_REQUIRE(d.out_cstride % 8 == 0 && d.out_choff % 8 == 0, PSSR_EUNSUP,
                "conv: output channel stride/offset must be multiples of 8");
-  PSSR_REQUIRE(d.tail_z == nullptr, PSSR_EUNSUP, "conv: the fused Reconstruction tail needs the strip kernel (stride-1 3x3/1x1 taps)");
+  PSSR_REQUIRE(d.tail_z == nullptr, PSSR_EUNSUP, "conv: the fused Reconstruction tail needs the v3 kernel (64 channels per sub-position, N %% 256 == 0)");
   PSSR_REQUIRE(d.out != nullptr || d.out_f32 != nullptr, PSSR_EINVAL, "conv: no output buffer");
 
   ConvKParams& p = *reinterpret_cast<ConvKParams*>(op.kparams);
@@ -386,6 +396,10 @@ int conv_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
   p.out_scale = d.out_scale;
   p.out = reinterpret_cast<uint16_t*>(d.out);
   p.out_f32 = d.out_f32;
+  p.out_lo = reinterpret_cast<uint16_t*>(d.out_lo);
+  p.lo_cstride = d.out_lo_cstride;
+  p.lo_choff = d.out_lo_choff;
+  PSSR_REQUIRE(d.out_lo == nullptr || (d.out != nullptr && d.out_lo_cstride % 8 == 0 && d.out_lo_choff % 8 == 0), PSSR_EUNSUP, "conv: out_lo needs a 16-bit primary output");
   p.out_cstride = d.out_cstride;
   p.out_choff = d.out_choff;
   p.shuffle = d.shuffle;

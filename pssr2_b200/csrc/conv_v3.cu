@@ -21,6 +21,7 @@
 //
 // Warps: 0 = A producer, 1 = MMA issuer + TMEM owner, 2 = B producer, 3 idle, 4..11 = epilogue (two per TMEM lane quarter).
 #include <cuda.h>
+#include <cuda_fp8.h>
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
@@ -35,7 +36,7 @@ static constexpr int kV3MaxR = 12;   // ring slots (row groups) in rows mode
 struct V3Params {
   const CUtensorMap* tmaps;   // device: [0..2] sources, [3] weights
   int n_segs;
-  int seg_src[4], seg_taps[4], seg_cblocks[4], seg_kb0[4];
+  int seg_src[6], seg_taps[6], seg_cblocks[6], seg_kb0[6];
   int num_kb;
   int H, W, B, P, IP, pad, HP, NJ, Wb;
   int rows_mode;              // 1: tile = one 128-pixel row segment (W % 128 == 0)
@@ -46,7 +47,9 @@ struct V3Params {
   uint32_t slot16_bytes;      // rows mode: one row of a narrow (16-channel, SWIZZLE_32B) plane = P * 32 rounded up to 128
   uint32_t group_bytes;       // rows mode: all planes of one row (layout stride of a ring slot)
   uint32_t group_tx;          // rows mode: bytes the TMA unit writes per ring slot
-  int seg_k16[4];             // rows mode: the segment's source is a 16-channel tensor staged as a narrow plane (one K = 16 MMA)
+  int seg_k16[6];             // rows mode: the segment's source is a 16-channel tensor staged as a narrow plane (one K = 16 MMA)
+  int seg_load[6];            // rows mode: 0 = the segment reads the planes an earlier segment over the same source staged
+  uint32_t seg_plane[6];      // rows mode: byte offset of the segment's first plane inside a ring slot
   uint32_t ring_bytes;        // rows mode: ring_R * group_bytes rounded up to 1024
   int q_begin, q_end;         // flat mode
   // cols mode (small feature maps, W % 8 == 0, W < 32): a tile = 16 groups of 8 pixels = cR image rows x 8 columns of cG images
@@ -76,6 +79,12 @@ struct V3Params {
   const float* tail_w;        // fused Reconstruction tail: fp32 [9][64]
   float* tail_z;              // fp32 [B][H][r*r*9][W]: the r*r*9 plane rows of one LR row are contiguous
   int tail_win48;             // PSSR_TAIL_WINDOW48: [B][H][48][W], the projections pre-summed by HR output position (r = 4, rows mode)
+  // compensated precision (pssr_conv_desc_t::out_lo / PSSR_TAIL_COMP)
+  uint16_t* out_lo;           // second 16-bit output: rn16(y - rn16(y))
+  int lo_cstride, lo_choff;
+  int tail_comp;              // tail: B = [W_hi ; W_lo] (N = 32) against the 16-bit activation in TMEM, plus an e5m2 pass
+                              // (kind::f8f6f4, A = 64 * (y - rn16(y)) staged in shared memory, B = W / 64) into the same accumulator
+  uint32_t tailw_bytes;       // bytes of the tail operand region: 16-bit weight tile [+ e5m2 weight tile + 4 x 8 KB e5m2 A tiles]
 };
 
 // developer timeline (PSSR_DBG bit 16): per CTA 256 clock64 stamps -- [0] entry, [1] setup done, [2+2u] unit u: accumulator buffer
@@ -127,6 +136,57 @@ __device__ __forceinline__ void v3_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t 
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
         : "memory");
+}
+// e5m2 operands (kind::f8f6f4, K = 32 per instruction), fp32 accumulate into the same TMEM columns as the f16 MMAs
+template <bool PAIR>
+__device__ __forceinline__ void v3_mma_f8(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (PAIR)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// K-major operand tile with 64-byte rows, SWIZZLE_64B: 8-row groups 512 B apart
+__device__ __forceinline__ uint64_t v3_desc64(uint32_t addr) {
+  uint64_t d = (uint64_t)((addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)(512u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+// four floats -> four e5m2 bytes (byte i = value i)
+__device__ __forceinline__ uint32_t v3_e5m2x4(float a, float b, float c, float d) {
+  const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E5M2);
+  const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E5M2);
+  return lo | (hi << 16);
+}
+__device__ __forceinline__ float2 v3_unpack2(uint32_t v, int fp16) {
+  if (fp16) return __half22float2(*reinterpret_cast<__half2*>(&v));
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+__device__ __forceinline__ void v3_arrive_cluster_release(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// wait that pairs with a cluster-scope release from the peer CTA (its shared-memory writes must be visible to the MMA)
+__device__ __forceinline__ void v3_mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
 }
 // completion of all MMAs issued so far -> one arrival on the barrier (PAIR: on the barrier at this offset in BOTH CTAs)
 template <bool PAIR>
@@ -271,8 +331,11 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
   const uint32_t a_total = ROWS ? p.ring_bytes : 2u * p.a_bytes;
   const uint32_t b_base = smem_base + a_total;
   const uint32_t b_total = RES ? (uint32_t)p.num_kb * p.tap_bytes : (uint32_t)p.b_stages * p.b_bytes;
-  const uint32_t tailw_off = a_total + b_total;                            // 16 x 128 B, 1024-aligned
-  const uint32_t vec_off = tailw_off + (TAIL ? 2048u : 0u);
+  const uint32_t tailw_off = a_total + b_total;                            // tail operands, 1024-aligned
+  const uint32_t vec_off = tailw_off + (TAIL ? p.tailw_bytes : 0u);
+  // compensated tail: [0, 4096) 16-bit weight tile (N = 32), [4096, 5120) e5m2 weight tile, [6144, 6144 + 32 KB) e5m2 A tiles
+  const uint32_t w8_off = tailw_off + 4096u;
+  const uint32_t lo8_off = tailw_off + 6144u;
   float* bias_s = reinterpret_cast<float*>(smem_al + vec_off);
   float* scale_s = bias_s + p.n_total;
   for (int i = threadIdx.x; i < p.n_total; i += kV3Threads) {
@@ -281,13 +344,28 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
   }
   if (TAIL) {
     // tail weights [9][64] fp32 -> 16-bit K-major SWIZZLE_128B operand tile [16 taps x 64 channels] (rows 9..15 zero);
-    // a CTA pair splits the N = 16 rows: local row t of rank r is tap r*8 + t
-    for (int i = threadIdx.x; i < (16 / C) * 64; i += kV3Threads) {
+    // a CTA pair splits the N rows: local row t of rank r is row r*NT/2 + t.  Compensated: N = 32, rows 16..31 hold
+    // rn16(w - rn16(w)) of the same taps (the second half of the accumulator columns).
+    const int NT = p.tail_comp ? 32 : 16;
+    for (int i = threadIdx.x; i < (NT / C) * 64; i += kV3Threads) {
       const int t = i >> 6, c = i & 63;
-      const int tap = t + (int)rank * (16 / C);
+      const int grow = t + (int)rank * (NT / C);
+      const int tap = grow & 15;
       const float w = tap < 9 ? p.tail_w[tap * 64 + c] : 0.f;
+      uint16_t val = pack1(w, p.fp16);
+      if (grow >= 16) val = pack1(w - unpack1(val, p.fp16), p.fp16);
       const int chunk = (c >> 3) ^ (t & 7);
-      reinterpret_cast<uint16_t*>(smem_al + tailw_off + t * 128 + chunk * 16)[c & 7] = pack1(w, p.fp16);
+      reinterpret_cast<uint16_t*>(smem_al + tailw_off + t * 128 + chunk * 16)[c & 7] = val;
+    }
+    if (p.tail_comp) {
+      // e5m2 tile [16 taps x 64 channels] of w / 64, 64-byte rows, SWIZZLE_64B (16-byte chunk index ^ ((row >> 1) & 3))
+      for (int i = threadIdx.x; i < (16 / C) * 64; i += kV3Threads) {
+        const int t = i >> 6, c = i & 63;
+        const int tap = t + (int)rank * (16 / C);
+        const float w = tap < 9 ? p.tail_w[tap * 64 + c] * 0.015625f : 0.f;
+        const int chunk = (c >> 4) ^ ((t >> 1) & 3);
+        (smem_al + w8_off + t * 64 + chunk * 16)[c & 15] = (uint8_t)__nv_cvt_float_to_fp8(w, __NV_SATFINITE, __NV_E5M2);
+      }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -376,8 +454,9 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
             mbar_wait(r_empty(slot), phase ^ 1u);
             const uint32_t fbar = PAIR ? v3_mapa(r_full(slot), 0) : r_full(slot);
             if (rank == 0) mbar_arrive_expect_tx(r_full(slot), p.group_tx * C);
-            uint32_t dst = a_base + (uint32_t)slot * p.group_bytes;
             for (int sg = 0; sg < p.n_segs; ++sg) {
+              if (!p.seg_load[sg]) continue;
+              uint32_t dst = a_base + (uint32_t)slot * p.group_bytes + p.seg_plane[sg];
               const CUtensorMap* tm = p.tmaps + p.seg_src[sg];
               for (int cb = 0; cb < p.seg_cblocks[sg]; ++cb) {
                 if (PAIR) v3_tma_4d_pair(dst, tm, fbar, cb * 64, x0, first_row + i, n);
@@ -508,8 +587,13 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
     // The whole warp walks the loops (warp-uniform control flow); one elected lane issues the tcgen05 instructions.
     // PAIR: M = 256 in the instruction descriptor (bits 24..28 hold M >> 4)
     const uint32_t idesc = umma_idesc_f16(p.fp16 ? 0 : 1, block_n) + (PAIR ? (8u << 24) : 0u);
-    const uint32_t idesc_tail = umma_idesc_f16(p.fp16 ? 0 : 1, 16) + (PAIR ? (8u << 24) : 0u);
+    const uint32_t tail_n = p.tail_comp ? 32u : 16u;
+    const uint32_t idesc_tail = umma_idesc_f16(p.fp16 ? 0 : 1, (int)tail_n) + (PAIR ? (8u << 24) : 0u);
+    // kind::f8f6f4: fp32 accumulate, A and B e5m2 (format 1), K-major, N = 16
+    const uint32_t idesc_f8 = (1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24) + (PAIR ? (8u << 24) : 0u);
     const uint64_t tdesc = v3_desc(smem_base + tailw_off);
+    const uint64_t w8desc = v3_desc64(smem_base + w8_off);
+    const uint64_t lo8desc = v3_desc64(smem_base + lo8_off);
     const uint64_t adesc_s0 = v3_desc(a_base + (uint32_t)p.off_px * 128u) + ((uint64_t)((p.a_sbo - 1024u) >> 4) << 32);
     const uint64_t adesc_s1 = adesc_s0 + (uint64_t)(p.a_bytes >> 4);
     const uint64_t bdesc0 = v3_desc(b_base);
@@ -525,16 +609,20 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
     int it = 0;
     // K segments packed into registers (bit 0: 3x3, bits 1..8: channel blocks, bits 9..: first K block): an indexed load from
     // the constant bank per segment would sit on the issue path of every unit
-    uint32_t segw[4];
+    uint32_t segw[6];
+    uint32_t segp[6];             // rows mode: descriptor units (16 B) from a ring slot to the segment's first plane
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 6; ++i) {
       segw[i] = i < p.n_segs ? ((p.seg_taps[i] == 9 ? 1u : 0u) | ((uint32_t)p.seg_cblocks[i] << 1) | ((uint32_t)p.seg_kb0[i] << 9) |
                                 (p.seg_k16[i] ? 0x80000000u : 0u)) : 0u;
+      segp[i] = i < p.n_segs ? (p.seg_plane[i] >> 4) : 0u;
+    }
     const int n_segs = p.n_segs;
 
     auto issue_tail = [&](int pit) {
       const int pbuf = pit & 1;
-      mbar_wait(p_full(pbuf), (uint32_t)(pit >> 1) & 1u);
+      if (PAIR && p.tail_comp) v3_mbar_wait_cluster(p_full(pbuf), (uint32_t)(pit >> 1) & 1u);
+      else mbar_wait(p_full(pbuf), (uint32_t)(pit >> 1) & 1u);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t cbase = tmem_base + (uint32_t)(pbuf * 256);
@@ -542,9 +630,15 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
         for (int s = 0; s < 4; ++s) {
           const uint32_t region = (uint32_t)((s >> 1) * 128);
           const uint32_t a_col = cbase + region + (uint32_t)((s & 1) * 32);
-          const uint32_t d_col = cbase + region + 64u + (uint32_t)((s & 1) * 16);
+          const uint32_t d_col = cbase + region + 64u + (uint32_t)(s & 1) * tail_n;
 #pragma unroll
           for (int k = 0; k < 4; ++k) v3_mma_ts<PAIR>(d_col, a_col + 8u * k, tdesc + 2u * k, idesc_tail, k ? 1u : 0u);
+          if (p.tail_comp) {
+            // + (64 * lo) x (w / 64), both e5m2, K = 32 per instruction: accumulates on the hi x W_hi columns
+            const uint64_t ad = lo8desc + (uint64_t)(s * (8192 >> 4));
+            v3_mma_f8<PAIR>(d_col, ad, w8desc, idesc_f8, 1u);
+            v3_mma_f8<PAIR>(d_col, ad + 2u, w8desc + 2u, idesc_f8, 1u);
+          }
         }
         v3_commit<PAIR>(z_full(pbuf));
       }
@@ -562,9 +656,9 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
       const uint32_t d0 = tmem_base + (uint32_t)(buf * 256);
       uint32_t acc = 0;
       bool tail_done = false;
-      uint64_t plane_desc = 0;
       for (int sg = 0; sg < n_segs; ++sg) {
-        const uint32_t sw = sg == 0 ? segw[0] : sg == 1 ? segw[1] : sg == 2 ? segw[2] : segw[3];
+        const uint32_t sw = sg == 0 ? segw[0] : sg == 1 ? segw[1] : sg == 2 ? segw[2] : sg == 3 ? segw[3] : sg == 4 ? segw[4] : segw[5];
+        uint64_t plane_desc = sg == 0 ? segp[0] : sg == 1 ? segp[1] : sg == 2 ? segp[2] : sg == 3 ? segp[3] : sg == 4 ? segp[4] : segp[5];
         const bool nine = (sw & 1u) != 0;
         const bool k16 = ROWS && (sw >> 31) != 0;
         const int cbs = (int)((sw >> 1) & 0xffu);
@@ -684,14 +778,14 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
         }
         tc_fence_after();
         if (g == 0 && it < 31) V3_TRACE(128 + 2 * it);
-        uint64_t plane_desc = 0;
         for (int sg = 0; sg < n_segs; ++sg) {
-          const uint32_t sw = sg == 0 ? segw[0] : sg == 1 ? segw[1] : sg == 2 ? segw[2] : segw[3];
+          const uint32_t sw = sg == 0 ? segw[0] : sg == 1 ? segw[1] : sg == 2 ? segw[2] : sg == 3 ? segw[3] : sg == 4 ? segw[4] : segw[5];
+          uint64_t plane_desc = sg == 0 ? segp[0] : sg == 1 ? segp[1] : sg == 2 ? segp[2] : sg == 3 ? segp[3] : sg == 4 ? segp[4] : segp[5];
           const bool nine = (sw & 1u) != 0;
           const bool k16 = (sw >> 31) != 0;
           const int cbs = (int)((sw >> 1) & 0xffu);
           const int kb0 = (int)((sw >> 9) & 0x3fffffu);
-          if (!nine && g != 1) { plane_desc += (uint64_t)cbs * (k16 ? slot16_desc : slot_desc); continue; }
+          if (!nine && g != 1) continue;
           for (int cb = 0; cb < cbs; ++cb, plane_desc += (k16 ? slot16_desc : slot_desc)) {
             if (nine) {
               constexpr int GS = G == 9 ? 3 : G;          // taps per weight stage inside one filter row
@@ -901,19 +995,42 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
           tmem_ld_32x32(region + (uint32_t)(c * 32), v);
           tmem_ld_wait();
           uint32_t o[16];
+          if (p.tail_comp) {
+            // hi = rn16(y) goes back to TMEM; 64 * (y - hi) as e5m2 goes to this pixel's row of the sub-position's A tile in
+            // shared memory (64-byte rows, SWIZZLE_64B): 32 channels = two 16-byte chunks
+            uint32_t l8[8];
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 bb = *reinterpret_cast<const float4*>(bias_s + nb0 + c * 32 + 4 * j4);
-            o[2 * j4 + 0] = v3_pack2(__uint_as_float(v[4 * j4 + 0]) + bb.x, __uint_as_float(v[4 * j4 + 1]) + bb.y, p.fp16, true);
-            o[2 * j4 + 1] = v3_pack2(__uint_as_float(v[4 * j4 + 2]) + bb.z, __uint_as_float(v[4 * j4 + 3]) + bb.w, p.fp16, true);
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bb = *reinterpret_cast<const float4*>(bias_s + nb0 + c * 32 + 4 * j4);
+              const float y0 = fmaxf(__uint_as_float(v[4 * j4 + 0]) + bb.x, 0.f), y1 = fmaxf(__uint_as_float(v[4 * j4 + 1]) + bb.y, 0.f);
+              const float y2 = fmaxf(__uint_as_float(v[4 * j4 + 2]) + bb.z, 0.f), y3 = fmaxf(__uint_as_float(v[4 * j4 + 3]) + bb.w, 0.f);
+              o[2 * j4 + 0] = v3_pack2(y0, y1, p.fp16, false);
+              o[2 * j4 + 1] = v3_pack2(y2, y3, p.fp16, false);
+              const float2 h01 = v3_unpack2(o[2 * j4 + 0], p.fp16), h23 = v3_unpack2(o[2 * j4 + 1], p.fp16);
+              l8[j4] = v3_e5m2x4((y0 - h01.x) * 64.f, (y1 - h01.y) * 64.f, (y2 - h23.x) * 64.f, (y3 - h23.y) * 64.f);
+            }
+            const uint32_t rowaddr = smem_base + lo8_off + (uint32_t)((eg * 2 + (c >> 1)) * 8192 + row * 64);
+            const uint32_t sw = (uint32_t)(row >> 1) & 3u;
+            const uint32_t j0 = (uint32_t)(c & 1) * 2u;
+            v3_st_shared_v4(rowaddr + ((j0 ^ sw) << 4), l8[0], l8[1], l8[2], l8[3]);
+            v3_st_shared_v4(rowaddr + (((j0 + 1u) ^ sw) << 4), l8[4], l8[5], l8[6], l8[7]);
+          } else {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bb = *reinterpret_cast<const float4*>(bias_s + nb0 + c * 32 + 4 * j4);
+              o[2 * j4 + 0] = v3_pack2(__uint_as_float(v[4 * j4 + 0]) + bb.x, __uint_as_float(v[4 * j4 + 1]) + bb.y, p.fp16, true);
+              o[2 * j4 + 1] = v3_pack2(__uint_as_float(v[4 * j4 + 2]) + bb.z, __uint_as_float(v[4 * j4 + 3]) + bb.w, p.fp16, true);
+            }
           }
           v3_tmem_st16(region + (uint32_t)(c * 16), o);
         }
+        if (p.tail_comp) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the e5m2 tile is read by the tensor core
         v3_tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
           if (rank == 0) mbar_arrive(p_full(buf));
+          else if (p.tail_comp) v3_arrive_cluster_release(v3_mapa(p_full(buf), 0));
           else v3_arrive_cluster(v3_mapa(p_full(buf), 0));
         }
         // ---- phase 2: the nine per-tap projections of this thread's pixel, two sub-positions per warp -------------
@@ -937,9 +1054,24 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
         const int planes = r * r * 9;
         if (ROWS && p.tail_win48) {
           uint32_t zv0[16], zv1[16];
-          v3_tmem_ld16(region + 64u, zv0);
-          v3_tmem_ld16(region + 64u + 16u, zv1);
-          tmem_ld_wait();
+          if (p.tail_comp) {
+            // accumulator columns per sub-position: [0, 16) hi x W_hi + lo x W, [16, 32) hi x W_lo
+            uint32_t zl0[16], zl1[16];
+            v3_tmem_ld16(region + 64u, zv0);
+            v3_tmem_ld16(region + 64u + 16u, zl0);
+            v3_tmem_ld16(region + 64u + 32u, zv1);
+            v3_tmem_ld16(region + 64u + 48u, zl1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              zv0[t] = __float_as_uint(__uint_as_float(zv0[t]) + __uint_as_float(zl0[t]));
+              zv1[t] = __float_as_uint(__uint_as_float(zv1[t]) + __uint_as_float(zl1[t]));
+            }
+          } else {
+            v3_tmem_ld16(region + 64u, zv0);
+            v3_tmem_ld16(region + 64u + 16u, zv1);
+            tmem_ld_wait();
+          }
           switch (n_tile) {
             case 0: v3_tail_window_add<0, 0>(win, zv0); v3_tail_window_add<0, 1>(win, zv1); break;
             case 1: v3_tail_window_add<1, 0>(win, zv0); v3_tail_window_add<1, 1>(win, zv1); break;
@@ -959,8 +1091,17 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
 #pragma unroll
         for (int sl = 0; sl < 2; ++sl) {
           uint32_t zv[16];
-          v3_tmem_ld16(region + 64u + (uint32_t)(sl * 16), zv);
-          tmem_ld_wait();
+          if (p.tail_comp) {
+            uint32_t zl[16];
+            v3_tmem_ld16(region + 64u + (uint32_t)(sl * 32), zv);
+            v3_tmem_ld16(region + 64u + (uint32_t)(sl * 32 + 16), zl);
+            tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 9; ++t) zv[t] = __float_as_uint(__uint_as_float(zv[t]) + __uint_as_float(zl[t]));
+          } else {
+            v3_tmem_ld16(region + 64u + (uint32_t)(sl * 16), zv);
+            tmem_ld_wait();
+          }
           if (valid && !(p.dbg & 1)) {
             const int sub = n_tile * 4 + eg * 2 + sl;
             float* zp = p.tail_z + (((size_t)n * p.H + y) * planes + (size_t)sub * 9) * p.W + x;
@@ -1121,9 +1262,19 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
                 uint32_t o[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) o[j] = v3_pack2(f[2 * j], f[2 * j + 1], p.fp16, relu_pack);
+                uint32_t ol[8];
+                if (p.out_lo != nullptr) {          // second output: what the 16-bit rounding of the activated value dropped
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const float2 h = v3_unpack2(o[j], p.fp16);
+                    const float a0 = relu_pack ? fmaxf(f[2 * j], 0.f) : f[2 * j], a1 = relu_pack ? fmaxf(f[2 * j + 1], 0.f) : f[2 * j + 1];
+                    ol[j] = v3_pack2(a0 - h.x, a1 - h.y, p.fp16, false);
+                  }
+                }
                 if (p.wide_store) {
                   const size_t pix = pix00 + (size_t)si * p.Wout + (size_t)sj;
                   v3_st_global_v8(p.out + pix * p.out_cstride + p.out_choff + cc, o);
+                  if (p.out_lo != nullptr) v3_st_global_v8(p.out_lo + pix * p.lo_cstride + p.lo_choff + cc, ol);
                   if (warp == 4 && it == 2 && h == 1) V3_TRACE(226 + 2 * ((c0 - c_lo) >> 5));
                 } else {
                   if (relu_pack && p.out_f32 != nullptr) {
@@ -1140,6 +1291,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
                       const size_t pix = ((size_t)n * p.Hout + (size_t)(y * r + si8)) * p.Wout + (size_t)(x * r + sj8);
                       if (p.out != nullptr)
                         *reinterpret_cast<uint4*>(p.out + pix * p.out_cstride + p.out_choff + cc8) = make_uint4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+                      if (p.out_lo != nullptr)
+                        *reinterpret_cast<uint4*>(p.out_lo + pix * p.lo_cstride + p.lo_choff + cc8) = make_uint4(ol[4 * g], ol[4 * g + 1], ol[4 * g + 2], ol[4 * g + 3]);
                       if (p.out_f32 != nullptr) {
                         float4* d = reinterpret_cast<float4*>(p.out_f32 + pix * p.out_cstride + p.out_choff + cc8);
                         d[0] = make_float4(f[8 * g + 0], f[8 * g + 1], f[8 * g + 2], f[8 * g + 3]);
@@ -1233,7 +1386,7 @@ static bool v3_cols_geometry(const pssr_conv_desc_t& d, int* cR, int* cG) {
 }
 
 bool v3_supported(const pssr_conv_desc_t& d) {
-  if (getenv("PSSR_CONV_V1") != nullptr || getenv("PSSR_CONV_V2") != nullptr) return false;
+  if (getenv("PSSR_CONV_V1") != nullptr) return false;
   for (int s = 0; s < d.n_segs; ++s)
     if (d.segs[s].taps != 1 && d.segs[s].taps != 9) return false;
   if (d.n % 32 != 0 || d.n < 32) return false;
@@ -1245,7 +1398,7 @@ bool v3_supported(const pssr_conv_desc_t& d) {
   if (any9 && d.Wo < 32 && d.tail_z == nullptr && getenv("PSSR_V3_SMALL") == nullptr && !v3_cols_geometry(d, nullptr, nullptr)) return false;
   if (d.tail_z != nullptr) {
     const int cps = d.n_valid / (d.shuffle * d.shuffle);
-    if (cps != 64 || d.n % 256 != 0 || !any9) return false;   // other tail shapes: v2's CUDA-core tail
+    if (cps != 64 || d.n % 256 != 0 || !any9) return false;   // other tail shapes run unfused (PSSR_OP_TAIL)
   }
   return true;
 }
@@ -1263,7 +1416,7 @@ int v3_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
 static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, bool force_flat) {
   EncodeTiledFn enc = v3_encode_fn();
   PSSR_REQUIRE(enc != nullptr, PSSR_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-  PSSR_REQUIRE(d.n_srcs >= 1 && d.n_srcs <= 3 && d.n_segs >= 1 && d.n_segs <= 4, PSSR_EINVAL, "conv: n_srcs/n_segs out of range");
+  PSSR_REQUIRE(d.n_srcs >= 1 && d.n_srcs <= 3 && d.n_segs >= 1 && d.n_segs <= 6, PSSR_EINVAL, "conv: n_srcs/n_segs out of range");
   PSSR_REQUIRE(d.n_valid > 0 && d.n_valid <= d.n && d.n_valid % 8 == 0, PSSR_EUNSUP, "conv: n_valid=%d must be a multiple of 8 and <= n", d.n_valid);
   PSSR_REQUIRE(d.shuffle >= 1 && d.n_valid % (d.shuffle * d.shuffle) == 0, PSSR_EUNSUP, "conv: n_valid %% shuffle^2 != 0");
   const int cps = d.n_valid / (d.shuffle * d.shuffle);
@@ -1337,12 +1490,15 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
   if (p.rows_mode && d.Ho % T != 0) T = 1;
   const char* envT = getenv("PSSR_V3_T");
   if (envT && atoi(envT) == 1) T = 1;
-  const int tailw_bytes = tail ? 2048 : 0;
+  const bool tail_comp = tail && (d.tail_flags & PSSR_TAIL_COMP) != 0 && getenv("PSSR_V3_NO_TAIL_COMP") == nullptr;
+  const int tailw_bytes = tail ? (tail_comp ? 6144 + 4 * 8192 : 2048) : 0;
+  PSSR_REQUIRE(d.out_lo == nullptr || (d.out != nullptr && !tail && d.out_lo_cstride % 8 == 0 && d.out_lo_choff % 8 == 0), PSSR_EUNSUP,
+               "conv: out_lo needs a 16-bit primary output and 8-channel aligned stride / offset");
   const int vec_bytes = ((4 * d.n * (d.out_scale != nullptr ? 2 : 1) + 1023) / 1024) * 1024;
   // epilogue through shared memory + TMA stores (full 128-byte lines, asynchronous) where the output is a plain 16-bit NHWC view
   // and every 32-pixel box lies inside the image (rows mode, 1x1 layers).  Measured on B200: store boxes with out-of-range
   // coordinates on several sides raise an illegal-instruction fault, so the flat 3x3 mode keeps its direct stores.
-  p.tma_store = (!tail && d.shuffle == 1 && d.out != nullptr && d.out_f32 == nullptr && d.n_valid % 64 == 0 && block_n % 64 == 0 &&
+  p.tma_store = (!tail && d.shuffle == 1 && d.out != nullptr && d.out_f32 == nullptr && d.out_lo == nullptr && d.n_valid % 64 == 0 && block_n % 64 == 0 &&
                  (p.rows_mode || !p.pad || getenv("PSSR_V3_TMA_STORE_FLAT") != nullptr) && getenv("PSSR_V3_NO_TMA_STORE") == nullptr) ? 1 : 0;
   const long long smem_cap0 = 226 * 1024 - 1024 - vec_bytes - tailw_bytes;
   const char* envG = getenv("PSSR_V3_G");
@@ -1361,6 +1517,20 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
     const bool k16 = p.rows_mode && sg.taps == 1 && sg.cblocks == 1 && src.cstride == 16 && src.channels <= 16 && getenv("PSSR_V3_NO_K16") == nullptr;
     p.seg_k16[s2] = k16 ? 1 : 0;
     if (k16) src_k16[sg.src] = true;
+    // segments over the same source view share its staged rows (hi x W_hi and hi x W_lo of the compensated layers, or the 3x3
+    // and the 1x1 residual of a depth-0 block): only the first one is loaded
+    int alias = -1;
+    for (int e = 0; e < s2 && alias < 0; ++e)
+      if (p.seg_load[e] && d.segs[e].src == sg.src && d.segs[e].cblocks == sg.cblocks && p.seg_k16[e] == p.seg_k16[s2] &&
+          getenv("PSSR_V3_NO_ALIAS") == nullptr)
+        alias = e;
+    if (alias >= 0) {
+      p.seg_load[s2] = 0;
+      p.seg_plane[s2] = p.seg_plane[alias];
+      continue;
+    }
+    p.seg_load[s2] = 1;
+    p.seg_plane[s2] = p.group_bytes;
     p.group_bytes += (uint32_t)sg.cblocks * (k16 ? p.slot16_bytes : p.slot_bytes);
     p.group_tx += (uint32_t)sg.cblocks * (uint32_t)p.P * (k16 ? 32u : 128u);
   }
@@ -1543,6 +1713,11 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
   p.tail_w = d.tail_weight;
   p.tail_z = d.tail_z;
   p.tail_win48 = (tail && d.tail_layout == PSSR_TAIL_WINDOW48) ? 1 : 0;
+  p.tail_comp = tail_comp ? 1 : 0;
+  p.tailw_bytes = (uint32_t)tailw_bytes;
+  p.out_lo = reinterpret_cast<uint16_t*>(d.out_lo);
+  p.lo_cstride = d.out_lo_cstride;
+  p.lo_choff = d.out_lo_choff;
   PSSR_REQUIRE(!p.tail_win48 || (p.rows_mode && d.shuffle == 4 && p.n_tiles == 4), PSSR_EUNSUP,
                "conv: PSSR_TAIL_WINDOW48 needs scale 4, 64 channels per sub-position and Wo %% 128 == 0");
   p.out_cstride = d.out_cstride;
@@ -1554,7 +1729,8 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
   p.Hout = d.Ho * d.shuffle;
   p.Wout = d.Wo * d.shuffle;
   p.wide_store = (d.out != nullptr && d.out_f32 == nullptr && cps % 16 == 0 && d.out_choff % 16 == 0 && d.out_cstride % 16 == 0 &&
-                  d.n_valid % 16 == 0 && ((uintptr_t)d.out & 31) == 0) ? 1 : 0;
+                  d.n_valid % 16 == 0 && ((uintptr_t)d.out & 31) == 0 &&
+                  (d.out_lo == nullptr || (d.out_lo_choff % 16 == 0 && d.out_lo_cstride % 16 == 0 && ((uintptr_t)d.out_lo & 31) == 0))) ? 1 : 0;
   int workers = sms / C;
   if (p.rows_mode) {
     int gmax = p.units_m / C;          // every worker gets at least one row group per CTA

@@ -28,8 +28,9 @@ __global__ void __launch_bounds__(kPrepThreads) prep_im2col_kernel(pssr_prep_des
   for (long long base = blockIdx.x * (long long)blockDim.x + warp * 32; base < total; base += stride) {   // warp-uniform
     const long long i = base + lane;
     uint32_t row[32];
+    uint32_t rowl[32];      // compensated precision: rn16(v - rn16(v)), same layout (dead code without im2col_lo)
 #pragma unroll
-    for (int k = 0; k < 32; ++k) row[k] = 0u;
+    for (int k = 0; k < 32; ++k) row[k] = rowl[k] = 0u;
     if (i < total) {
       const int x = (int)(i % d.W);
       const int y = (int)((i / d.W) % d.H);
@@ -52,7 +53,9 @@ __global__ void __launch_bounds__(kPrepThreads) prep_im2col_kernel(pssr_prep_des
               v = __fadd_rn(__fmul_rn(__fsub_rn(__fdiv_rn(raw, 128.f), 1.f), s), t);  // no FMA contraction: same bits as the unfused ops
               if (tap == 4 && d.xnorm_f32 != nullptr) d.xnorm_f32[idx] = v;
             }
-            row[(c * 9 + tap) >> 1] |= (uint32_t)pack1(v, fp16) << (16 * ((c * 9 + tap) & 1));
+            const uint16_t hi16 = pack1(v, fp16);
+            row[(c * 9 + tap) >> 1] |= (uint32_t)hi16 << (16 * ((c * 9 + tap) & 1));
+            if (d.im2col_lo != nullptr) rowl[(c * 9 + tap) >> 1] |= (uint32_t)pack1(v - unpack1(hi16, fp16), fp16) << (16 * ((c * 9 + tap) & 1));
           }
         }
       }
@@ -63,6 +66,11 @@ __global__ void __launch_bounds__(kPrepThreads) prep_im2col_kernel(pssr_prep_des
         uint4* dst16 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(d.im2col) + (size_t)i * 16);
         dst16[0] = make_uint4(row[0], row[1], row[2], row[3]);
         dst16[1] = make_uint4(row[4], row[5], row[6], row[7]);
+        if (d.im2col_lo != nullptr) {
+          uint4* dl = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(d.im2col_lo) + (size_t)i * 16);
+          dl[0] = make_uint4(rowl[0], rowl[1], rowl[2], rowl[3]);
+          dl[1] = make_uint4(rowl[4], rowl[5], rowl[6], rowl[7]);
+        }
       }
       continue;
     }
@@ -77,6 +85,18 @@ __global__ void __launch_bounds__(kPrepThreads) prep_im2col_kernel(pssr_prep_des
       if (base + pix < total) dst[pix * 8 + chunk] = my[pix * 8 + (chunk ^ (pix & 7))];
     }
     __syncwarp();
+    if (d.im2col_lo != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) my[lane * 8 + (k ^ (lane & 7))] = make_uint4(rowl[4 * k], rowl[4 * k + 1], rowl[4 * k + 2], rowl[4 * k + 3]);
+      __syncwarp();
+      uint4* dl = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(d.im2col_lo) + (size_t)base * 64);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int pix = k * 4 + (lane >> 3), chunk = lane & 7;
+        if (base + pix < total) dl[pix * 8 + chunk] = my[pix * 8 + (chunk ^ (pix & 7))];
+      }
+      __syncwarp();
+    }
   }
 }
 
@@ -93,6 +113,7 @@ __global__ void prep_nhwc_kernel(pssr_prep_desc_t d, int fp16) {
     const int n = (int)(pix / (long long)hw);
     const size_t rem = (size_t)(pix - (long long)n * (long long)hw);
     uint32_t o[4] = {0, 0, 0, 0};
+    uint32_t ol[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = g * 8 + j;
@@ -103,9 +124,13 @@ __global__ void prep_nhwc_kernel(pssr_prep_desc_t d, int fp16) {
         v = __fadd_rn(__fmul_rn(__fsub_rn(__fdiv_rn(raw, 128.f), 1.f), d.scale[c]), d.shift[c]);
         if (d.xnorm_f32 != nullptr) d.xnorm_f32[idx] = v;
       }
-      o[j >> 1] |= (uint32_t)pack1(v, fp16) << (16 * (j & 1));
+      const uint16_t hi16 = pack1(v, fp16);
+      o[j >> 1] |= (uint32_t)hi16 << (16 * (j & 1));
+      ol[j >> 1] |= (uint32_t)pack1(v - unpack1(hi16, fp16), fp16) << (16 * (j & 1));
     }
     *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(d.im2col) + (size_t)pix * d.cols + g * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    if (d.im2col_lo != nullptr)
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(d.im2col_lo) + (size_t)pix * d.cols + g * 8) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
   }
 }
 

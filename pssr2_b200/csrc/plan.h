@@ -14,17 +14,13 @@ struct ConvOp {
   alignas(16) uint8_t kparams[512];
   int grid = 0;
   int smem_bytes = 0;
-  int variant = 1;                // 1 = conv_igemm.cu (box per tap), 2 = conv_strip.cu (halo strips), 3 = conv_v3.cu (lean issue)
+  int variant = 1;                // 1 = conv_igemm.cu (box per tap), 3 = conv_v3.cu (lean issue)
   int kernel_index = -1;          // variant 3: index of the template instantiation
   int cluster = 1;                // variant 3: CTAs per cluster (2 = cta_group::2 pairs)
 };
 
 int conv_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op);
 int conv_launch(const ConvOp& op, const void* tmaps_dev, cudaStream_t stream);
-bool strip_supported(const pssr_conv_desc_t& d);
-int strip_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op);
-int strip_launch(const ConvOp& op, const void* tmaps_dev, cudaStream_t stream);
-int strip_trace_fetch(long long* host, int n);
 bool v3_supported(const pssr_conv_desc_t& d);
 int v3_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op);
 int v3_trace_fetch(long long* host, int n);

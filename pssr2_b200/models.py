@@ -11,7 +11,7 @@ CPU or eager fallback: a non-CUDA input raises.
 import torch
 import torch.nn as nn
 
-from .plan import ACT_NONE, ACT_RELU, Plan, View, ceil_div, pack_weight, permute_n
+from .plan import ACT_NONE, ACT_RELU, TAIL_COMP, Plan, View, ceil_div, pack_weight, permute_n, split_lo
 
 
 def _force_list(item):
@@ -79,7 +79,12 @@ class _PlanModule(nn.Module):
     """Shared forward machinery: plan cache keyed by input geometry, invalidated whenever the
     parameters may have changed (load_state_dict, .to(), train())."""
 
-    precision = "fp16"   # operand format of the tensor-core path: "fp16" or "bf16" (fp32 accumulate)
+    # Operand format of the tensor-core path (fp32 accumulate everywhere):
+    #   "fp16c" (default) fp16 with hi + lo compensation of the tensors the output is sensitive to -- the full-resolution skip
+    #           path input -> encoder.0 -> last decoder block's respass -> Reconstruction.pre -> Reconstruction.conv carries
+    #           > 95 % of the rounding error of the plain fp16 plan (scripts/dev_error_budget.py); meets 1e-2 max-abs
+    #   "fp16"  single-pass fp16 (max-abs ~1.5e-2),  "bf16" single-pass bf16 (max-abs ~1e-1)
+    precision = "fp16c"
     fuse_tail = True     # fuse Reconstruction.conv into Reconstruction.pre's epilogue (single output channel)
 
     def __init__(self):
@@ -136,7 +141,7 @@ class _PlanModule(nn.Module):
         return st["out"], st["out_u8"]
 
     # helpers used by subclasses ---------------------------------------------------------
-    def _emit_reconstruction(self, plan, final, xcol, B, H, W, dev, out=None, out_u8=None, zbuf=None):
+    def _emit_reconstruction(self, plan, final, xcol, B, H, W, dev, out=None, out_u8=None, zbuf=None, xcol_lo=None):
         """Reconstruction (resunet.py:90-95, _blocks.py:15-18): cat([x, xnorm]) -> pre -> relu -> shuffle(s) -> conv -> *128+128."""
         dt = plan.tdtype
         z = lambda *sh: torch.zeros(*sh, dtype=dt, device=dev)
@@ -147,7 +152,17 @@ class _PlanModule(nn.Module):
         wp = rec.pre.weight.detach().float()
         bp = rec.pre.bias.detach().float()
         wide = bool(getattr(xcol, "wide_input", False))          # > 7 input channels: xcol is the normalised input, a 3x3 segment
-        parts = [wp[:, :hid0], wp[:, hid0:] if wide else _im2col_parts(wp[:, hid0:])]
+        wm, wx = wp[:, :hid0], (wp[:, hid0:] if wide else _im2col_parts(wp[:, hid0:]))
+        comp = plan.comp and xcol_lo is not None
+        tx = 9 if wide else 1
+        cbm = ceil_div(hid0, 64)
+        if comp:
+            # (final_hi, x_hi, x_lo) x (W_hi, W_lo): final * W_hi + x_hi * Wx_hi + x_lo * Wx_hi + x_hi * Wx_lo + final * W_lo
+            parts = [wm, wx, wx, split_lo(wx, plan.dtype), split_lo(wm, plan.dtype)]
+            srcs, segs = [View(final), xcol, xcol_lo], [(0, 9, cbm), (1, tx, 1), (2, tx, 1), (1, tx, 1), (0, 9, cbm)]
+        else:
+            parts = [wm, wx]
+            srcs, segs = [View(final), xcol], [(0, 9, cbm), (1, tx, 1)]
         wpk = pack_weight(parts, plan.dtype, s)
         wc = rec.conv.weight.detach().float()
         bc = rec.conv.bias.detach().float().contiguous()
@@ -155,9 +170,8 @@ class _PlanModule(nn.Module):
         if out is None:
             out = torch.empty(B, cout, H * s, W * s, dtype=torch.float32, device=dev)
             out_u8 = torch.empty(B, 1, H * s, W * s, dtype=torch.uint8, device=dev)
-        srcs, segs = [View(final), xcol], [(0, 9, ceil_div(hid0, 64)), (1, 9 if wide else 1, 1)]
         plan.flops += 2 * wp.numel() * B * H * W + 2 * wc.numel() * B * H * s * W * s
-        if cout == 1 and hid0 % 32 == 0 and W >= 1 and self.fuse_tail:
+        if cout == 1 and hid0 == 64 and W >= 1 and self.fuse_tail:
             # fused tail: relu(pre) is reduced against the 3x3 tail weights inside the conv epilogue (fp32), the
             # scale^2*hidden-channel HR map is never written; PSSR_OP_TAILSUM gathers the 9 taps (see include/pssr_b200.h)
             tw = wc[0].permute(1, 2, 0).reshape(9, hid0).contiguous()      # [tap][c]
@@ -165,13 +179,13 @@ class _PlanModule(nn.Module):
             # 2 x 24 HR output positions they feed (PSSR_TAIL_WINDOW48), 3x less z traffic
             import os
             win48 = 1 if (s == 4 and hid0 == 64 and W % 128 == 0 and not any(os.environ.get(k) for k in (
-                "PSSR_TAIL_TAPS", "PSSR_V3_FLAT", "PSSR_CONV_V1", "PSSR_CONV_V2"))) else 0
+                "PSSR_TAIL_TAPS", "PSSR_V3_FLAT", "PSSR_CONV_V1"))) else 0
             if zbuf is None:
                 zbuf = torch.zeros(B, H, 48 if win48 else s * s * 9, W, dtype=torch.float32, device=dev)
             zbuf = zbuf[:B]
             assert zbuf.shape == (B, H, 48 if win48 else s * s * 9, W)
             plan.conv(srcs, segs, wpk, permute_n(bp, s).contiguous(), None, Ho=H, Wo=W, B=B, shuffle=s, act=ACT_RELU,
-                      tail_weight=tw, tail_z=zbuf, tail_layout=win48)
+                      tail_weight=tw, tail_z=zbuf, tail_layout=win48, tail_flags=TAIL_COMP if comp else 0)
             plan.tailsum(zbuf, s, float(bc[0]), 128.0, 128.0, out, out_u8, layout=win48)    # x*128+128 (resunet.py:95)
             self._zbuf = zbuf
         else:
@@ -181,11 +195,13 @@ class _PlanModule(nn.Module):
         self._out, self._out_u8 = out, out_u8
 
     @staticmethod
-    def _emit_resblock(plan, blk, srcs, seg_spec, w0_parts_fn, wr_parts_fn, scratch, dst, shuffle, B, H, W):
+    def _emit_resblock(plan, blk, srcs, seg_spec, w0_parts_fn, wr_parts_fn, scratch, dst, shuffle, B, H, W, res_srcs=None, out_lo=None):
         """Emits the convs of one ResBlock.
         srcs / seg_spec: views and (src, taps, cblocks) segments feeding conv0 (3x3) -- and, with taps
         forced to the 1x1 variant by ``wr_parts_fn``, the respass.  ``w0_parts_fn(w)`` / ``wr_parts_fn(w)``
-        split a conv0 / respass weight into per-segment [Cout, Cin_seg, kh, kw] parts."""
+        split a conv0 / respass weight into per-segment [Cout, Cin_seg, kh, kw] parts.
+        res_srcs: views the respass segments index (default: ``srcs``); out_lo: second output of the block's last
+        convolution (what the 16-bit rounding of its result dropped), both for the compensated precision."""
         convs, (wr, br) = blk.folded()
         cout = blk.out_channels
         dev = wr.device
@@ -198,32 +214,37 @@ class _PlanModule(nn.Module):
                 in_srcs, in_segs, parts = list(srcs), list(seg_spec), w0_parts_fn(w)
             else:
                 in_srcs, in_segs, parts = [cur], [(0, 9, cb_out)], [w]
+            alg = [w]            # algorithmic work (hi / lo compensation terms and im2col padding are not counted)
             bias = b
             if last:
                 # relu(conv_n(h) + respass(x)): the 1x1 residual is extra K blocks of the same GEMM
                 r_parts, r_segs = wr_parts_fn(wr)
                 base = len(in_srcs)
-                for v in srcs:
+                for v in (srcs if res_srcs is None else res_srcs):
                     in_srcs.append(v)
                 in_segs += [(base + si, taps, cb) for (si, taps, cb) in r_segs]
                 parts = parts + r_parts
+                alg.append(wr)
                 bias = b + br
-                # merge duplicate source views (conv0 == last conv when depth == 0)
             wp = pack_weight(parts, plan.dtype, shuffle if last else 1)
             bp = permute_n(bias, shuffle if last else 1).contiguous()
-            in_srcs, in_segs = _dedupe_sources(in_srcs, in_segs)
+            in_srcs, in_segs = _dedupe_sources(in_srcs, in_segs)     # conv0 == last conv when depth == 0
             out_view = dst if last else View(scratch[i % 2])
-            plan.conv(in_srcs, in_segs, wp, bp, out_view, Ho=H, Wo=W, B=B, shuffle=shuffle if last else 1, act=ACT_RELU)
-            for p in parts:
+            plan.conv(in_srcs, in_segs, wp, bp, out_view, Ho=H, Wo=W, B=B, shuffle=shuffle if last else 1, act=ACT_RELU,
+                      out_lo=out_lo if last else None)
+            for p in alg:
                 plan.flops += 2 * p.numel() * B * H * W
             cur = out_view
         return dst
 
 
 def _dedupe_sources(srcs, segs):
-    """The C descriptor holds at most 3 distinct source views; identical views are merged."""
+    """The C descriptor holds at most 3 distinct source views; identical views are merged, unreferenced ones dropped."""
     uniq, remap = [], {}
+    used = {s for (s, _, _) in segs}
     for i, v in enumerate(srcs):
+        if i not in used:
+            continue
         key = (v.buf.data_ptr(), v.choff, v.channels)
         for j, u in enumerate(uniq):
             if (u.buf.data_ptr(), u.choff, u.channels) == key:
@@ -307,6 +328,9 @@ class ResUNet(_PlanModule):
         im2col = z(B, H, W, ((C + 7) // 8) * 8 if wide_in else (16 if C * 9 <= 16 else 64))      # narrow im2col: TMA boxes zero-fill channels >= 16
         xcol = View(im2col, 0, C) if wide_in else View(im2col)
         xcol.wide_input = wide_in
+        comp = plan.comp
+        im2col_lo = torch.zeros_like(im2col) if comp else None      # compensated precision: low halves of the input ...
+        skip_lo = z(B, H, W, hid[0]) if comp else None              # ... and of the level-0 skip
         # Optional sub-batches at level 0 (PSSR_SUBBATCH_MB > 0): the level-0 encoder block and the last decoder block +
         # Reconstruction run chunk by chunk so that a layer finds its input (<= that many MB per tensor) in the 126 MB L2 instead
         # of HBM.  MEASURED on B200 (batch 64, 128^2): forward 3.27 ms without, 3.38 / 3.50 / 3.86 ms with 64 / 32 / 16 MB chunks --
@@ -334,14 +358,16 @@ class ResUNet(_PlanModule):
         for l in range(L):
             blk = self.encoder[l]
             h, w = H >> l, W >> l
-            if l == 0 and wide_in:
-                srcs, segs = [xcol], [(0, 9, 1)]
-                w0f = lambda wt: [wt]
-                wrf = lambda wt: ([wt], [(0, 1, 1)])
-            elif l == 0:
-                srcs, segs = [xcol], [(0, 1, 1)]
-                w0f = lambda wt: [_im2col_parts(wt)]
-                wrf = lambda wt: ([_im2col_centre(wt)], [(0, 1, 1)])
+            if l == 0:
+                # the input feeds conv0 and the respass as (x_hi, x_lo) x (W_hi, W_lo) when compensated
+                t0 = 9 if wide_in else 1
+                f0 = (lambda wt: wt) if wide_in else _im2col_parts
+                fr = (lambda wt: wt) if wide_in else _im2col_centre
+                trip = (lambda p_: [p_, p_, split_lo(p_, plan.dtype)]) if comp else (lambda p_: [p_])
+                segs = [(0, t0, 1), (1, t0, 1), (0, t0, 1)] if comp else [(0, t0, 1)]
+                rsegs = [(0, 1, 1), (1, 1, 1), (0, 1, 1)] if comp else [(0, 1, 1)]
+                w0f = lambda wt: trip(f0(wt))
+                wrf = lambda wt: (trip(fr(wt)), rsegs)
             else:
                 cin = hid[l - 1]
                 srcs, segs = [cur], [(0, 9, ceil_div(cin, 64))]
@@ -350,11 +376,11 @@ class ResUNet(_PlanModule):
             if l == 0:
                 pooled = z(B, h // 2, w // 2, hid[l])
                 for b0, b1 in chunks:
-                    plan.prep(x_in[b0:b1], sc, sh, im2col[b0:b1], centre_only=wide_in)
+                    plan.prep(x_in[b0:b1], sc, sh, im2col[b0:b1], centre_only=wide_in, im2col_lo=im2col_lo[b0:b1] if comp else None)
                     dst = View(cat[l][b0:b1], up[l], hid[l])
-                    xc = View(im2col[b0:b1], 0, C) if wide_in else View(im2col[b0:b1])
-                    self._emit_resblock(plan, blk, [xc], segs, w0f, wrf, [sv[:b1 - b0] for sv in scratch(l)], dst, 1,
-                                        b1 - b0, h, w)
+                    xcs = [View(t_[b0:b1], 0, C) if wide_in else View(t_[b0:b1]) for t_ in ([im2col, im2col_lo] if comp else [im2col])]
+                    self._emit_resblock(plan, blk, xcs, segs, w0f, wrf, [sv[:b1 - b0] for sv in scratch(l)], dst, 1,
+                                        b1 - b0, h, w, out_lo=View(skip_lo[b0:b1]) if comp else None)
                     plan.maxpool(dst, View(pooled[b0:b1]))
                 cur = View(pooled)
             elif l + 1 < L:
@@ -386,11 +412,22 @@ class ResUNet(_PlanModule):
             else:
                 for b0, b1 in chunks:
                     fin = final[:b1 - b0]
-                    self._emit_resblock(plan, blk, [View(cat[l][b0:b1], 0, cin)], segs, w0f, wrf, [sv[:b1 - b0] for sv in scratch(l)],
-                                        View(fin), 1, b1 - b0, h, w)
+                    catv = View(cat[l][b0:b1], 0, cin)
+                    if comp:
+                        # respass over (up | skip_hi) with W_hi and W_lo, plus skip_lo with W_hi
+                        cbr = ceil_div(cin, 64)
+                        wrc = (lambda u_, cbr_: (lambda wt: ([wt, split_lo(wt, plan.dtype), wt[:, u_:].contiguous()],
+                                                             [(0, 1, cbr_), (0, 1, cbr_), (1, 1, ceil_div(hid[0], 64))])))(up[l], cbr)
+                        self._emit_resblock(plan, blk, [catv], segs, w0f, wrc, [sv[:b1 - b0] for sv in scratch(l)], View(fin), 1, b1 - b0, h, w,
+                                            res_srcs=[catv, View(skip_lo[b0:b1])])
+                    else:
+                        self._emit_resblock(plan, blk, [catv], segs, w0f, wrf, [sv[:b1 - b0] for sv in scratch(l)], View(fin), 1, b1 - b0, h, w)
                     xc = View(im2col[b0:b1], 0, C) if wide_in else View(im2col[b0:b1])
                     xc.wide_input = wide_in
-                    self._emit_reconstruction(plan, fin, xc, b1 - b0, H, W, dev, out[b0:b1], out_u8[b0:b1], zshared[0])
+                    xcl = None
+                    if comp:
+                        xcl = View(im2col_lo[b0:b1], 0, C) if wide_in else View(im2col_lo[b0:b1])
+                    self._emit_reconstruction(plan, fin, xc, b1 - b0, H, W, dev, out[b0:b1], out_u8[b0:b1], zshared[0], xcol_lo=xcl)
                     zshared[0] = self._zbuf
 
         plan.finalize()
@@ -562,9 +599,12 @@ class RDResUNet(_PlanModule):
         if C > 64:
             raise NotImplementedError(f"{C} input channels: at most 64 are supported")
         im2col = z(B, H, W, ((C + 7) // 8) * 8 if wide_in else (16 if C * 9 <= 16 else 64))      # narrow im2col: TMA boxes zero-fill channels >= 16
-        plan.prep(x_in, sc, sh, im2col, centre_only=wide_in)
+        comp = plan.comp
+        im2col_lo = torch.zeros_like(im2col) if comp else None
+        plan.prep(x_in, sc, sh, im2col, centre_only=wide_in, im2col_lo=im2col_lo)
         xcol = View(im2col, 0, C) if wide_in else View(im2col)
         xcol.wide_input = wide_in
+        xcol_lo = (View(im2col_lo, 0, C) if wide_in else View(im2col_lo)) if comp else None
 
         # ---- encoder geometry: which stage outputs are decoder skips, and where they live -----------------
         n_st = len(enc.dense_stages)
@@ -683,6 +723,8 @@ class RDResUNet(_PlanModule):
             srcs, segs = [dec_in[k]], [(0, 9, ceil_div(cin, 64))]
             w0f = lambda wt: [wt]
             wrf = (lambda cin: (lambda wt: ([wt], [(0, 1, ceil_div(cin, 64))])))(cin)
+            if comp and k + 1 == n_dec:      # the last block's respass sits on the shallow path to the output: W_hi + W_lo
+                wrf = (lambda cin: (lambda wt: ([wt, split_lo(wt, plan.dtype)], [(0, 1, ceil_div(cin, 64))] * 2)))(cin)
             n = B * hh * ww * hid[k]
             scr = [sb[:n].view(B, hh, ww, hid[k]) for sb in sbuf]
             shf = self.ratios[k + 1]
@@ -690,6 +732,6 @@ class RDResUNet(_PlanModule):
             self._emit_resblock(plan, blk, srcs, segs, w0f, wrf, scr, dst, shf, B, hh, ww)
 
         # ---- Reconstruction (rdresunet.py:125-130) -----------------------------------------------------------
-        self._emit_reconstruction(plan, final, xcol, B, H, W, dev)
+        self._emit_reconstruction(plan, final, xcol, B, H, W, dev, xcol_lo=xcol_lo)
         plan.finalize()
         return {"plan": plan, "x": x_in, "out": self._out, "out_u8": self._out_u8}

@@ -16,7 +16,8 @@ from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, DT_BF16, DT_FP16, OP_CONV, OP_D
                    TailDesc, TailSumDesc)
 
 TORCH_DT = {DT_BF16: torch.bfloat16, DT_FP16: torch.float16}
-DT_NAMES = {"bf16": DT_BF16, "fp16": DT_FP16}
+DT_NAMES = {"bf16": DT_BF16, "fp16": DT_FP16, "fp16c": DT_FP16}
+TAIL_COMP = 1   # include/pssr_b200.h PSSR_TAIL_COMP
 
 
 DRY_RUN = False
@@ -56,6 +57,11 @@ class View:
         return self.buf.data_ptr() + self.choff * self.buf.element_size()
 
 
+def split_lo(w, dtype):
+    """What the 16-bit rounding of ``w`` drops: w - rn16(w) (fp32; packed as its own K blocks by the compensated layers)."""
+    return w - w.to(TORCH_DT[dtype]).float()
+
+
 def pack_weight(parts, dtype, shuffle=1, n_pad=None):
     """parts: list of fp32 tensors [Cout, Cin, kh, kw] in K-schedule order (one per K segment).
     Returns ([n_pad, Ktot] 16-bit, K-major, K ordered tap-major then 64-padded channel) where the N
@@ -91,6 +97,8 @@ def permute_n(t, shuffle):
 
 class Plan:
     def __init__(self, dtype="bf16"):
+        # "fp16c": fp16 operands with hi + lo compensation on the layers the output is sensitive to (models.py)
+        self.comp = dtype == "fp16c"
         self.dtype = DT_NAMES[dtype] if isinstance(dtype, str) else dtype
         self.tdtype = TORCH_DT[self.dtype]
         self.ops = []
@@ -101,12 +109,13 @@ class Plan:
 
     # ---- op builders -----------------------------------------------------------------
     def conv(self, srcs, segs, weight, bias, out: View, *, Ho, Wo, B, n=None, n_valid=None, shuffle=1, act=ACT_NONE,
-             out_scale=None, out_f32=None, tail_weight=None, tail_z=None, tail_layout=0):
+             out_scale=None, out_f32=None, tail_weight=None, tail_z=None, tail_layout=0, out_lo: View = None, tail_flags=0):
         """srcs: list[View]; segs: list[(src_index, taps, cblocks)]; weight [n, Ktot] 16-bit; bias [n] fp32."""
         d = ConvDesc()
         d.n_srcs = len(srcs)
         for i, s in enumerate(srcs):
             d.srcs[i] = Src(s.ptr(), s.channels, s.cstride, s.H, s.W, s.B, 0)
+        assert len(srcs) <= 3 and len(segs) <= 6
         d.n_segs = len(segs)
         ktot = 0
         for i, (si, taps, cb) in enumerate(segs):
@@ -130,21 +139,31 @@ class Plan:
         d.tail_weight = tail_weight.data_ptr() if tail_weight is not None else None
         d.tail_z = tail_z.data_ptr() if tail_z is not None else None
         d.tail_layout = tail_layout
+        d.tail_flags = tail_flags
+        if out_lo is not None:
+            assert out is not None and (out_lo.B, out_lo.H, out_lo.W) == (out.B, out.H, out.W)
+            d.out_lo = out_lo.buf.data_ptr()
+            d.out_lo_cstride = out_lo.cstride
+            d.out_lo_choff = out_lo.choff
         op = Op()
         op.kind = OP_CONV
         op.u.conv = d
         self.ops.append(op)
         self.keep += [weight, bias, out_scale, out_f32, tail_weight, tail_z] + [s.buf for s in srcs] + ([out.buf] if out is not None else [])
+        self.keep += [out_lo.buf] if out_lo is not None else []
         self.records.append(("conv", dict(srcs=list(srcs), segs=list(segs), weight=weight, bias=bias, out=out, Ho=Ho, Wo=Wo, B=B,
                                           n=n, n_valid=d.n_valid, shuffle=shuffle, act=act, out_scale=out_scale, out_f32=out_f32,
                                           issued_flops=2 * B * Ho * Wo * n * ktot, tail_weight=tail_weight, tail_z=tail_z,
-                                          tail_layout=tail_layout)))
+                                          tail_layout=tail_layout, out_lo=out_lo, tail_flags=tail_flags)))
 
-    def prep(self, x, scale, shift, im2col, xnorm=None, centre_only=False):
-        """centre_only: im2col is the normalised input itself, NHWC [B, H, W, cols] (inputs with more than 7 channels)."""
+    def prep(self, x, scale, shift, im2col, xnorm=None, centre_only=False, im2col_lo=None):
+        """centre_only: im2col is the normalised input itself, NHWC [B, H, W, cols] (inputs with more than 7 channels).
+        im2col_lo (compensated precision): same shape, receives what the 16-bit rounding of every im2col value dropped."""
         B, C, H, W = x.shape
+        assert im2col_lo is None or (im2col_lo.shape == im2col.shape and im2col_lo.dtype == im2col.dtype)
         d = PrepDesc(x.data_ptr(), 1 if x.dtype == torch.uint8 else 0, B, C, H, W, scale.data_ptr(), shift.data_ptr(),
-                     im2col.data_ptr(), xnorm.data_ptr() if xnorm is not None else None, im2col.shape[3], 1 if centre_only else 0)
+                     im2col.data_ptr(), im2col_lo.data_ptr() if im2col_lo is not None else None,
+                     xnorm.data_ptr() if xnorm is not None else None, im2col.shape[3], 1 if centre_only else 0)
         if centre_only:
             assert im2col.shape[3] % 8 == 0 and C <= im2col.shape[3] <= 64
         else:
@@ -153,8 +172,9 @@ class Plan:
         op.kind = OP_PREP
         op.u.prep = d
         self.ops.append(op)
-        self.keep += [x, scale, shift, im2col, xnorm]
-        self.records.append(("prep", dict(x=x, scale=scale, shift=shift, im2col=im2col, xnorm=xnorm, centre_only=centre_only)))
+        self.keep += [x, scale, shift, im2col, xnorm, im2col_lo]
+        self.records.append(("prep", dict(x=x, scale=scale, shift=shift, im2col=im2col, xnorm=xnorm, centre_only=centre_only,
+                                          im2col_lo=im2col_lo)))
 
     def maxpool(self, src: View, dst: View):
         d = PoolDesc(src.buf.data_ptr(), src.cstride, src.choff, dst.buf.data_ptr(), dst.cstride, dst.choff, src.B, src.H,

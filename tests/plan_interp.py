@@ -20,13 +20,15 @@ def run_records(plan):
             x = r["x"].float()
             B, C, H, W = x.shape
             xn = (x / 128 - 1) * r["scale"].view(1, -1, 1, 1) + r["shift"].view(1, -1, 1, 1)
-            if r.get("centre_only"):
-                r["im2col"].zero_()
-                r["im2col"][..., :C] = xn.permute(0, 2, 3, 1).to(r["im2col"].dtype)
-                continue
-            cols = F.unfold(xn, 3, padding=1).view(B, C * 9, H, W)
+            lo = r.get("im2col_lo")
+            cols = xn if r.get("centre_only") else F.unfold(xn, 3, padding=1).view(B, C * 9, H, W)
+            cols = cols.permute(0, 2, 3, 1)
+            nc = cols.shape[-1]
             r["im2col"].zero_()
-            r["im2col"][..., :C * 9] = cols.permute(0, 2, 3, 1).to(r["im2col"].dtype)
+            r["im2col"][..., :nc] = cols.to(r["im2col"].dtype)
+            if lo is not None:          # compensated precision: what the 16-bit rounding dropped
+                lo.zero_()
+                lo[..., :nc] = (cols - r["im2col"][..., :nc].float()).to(lo.dtype)
         elif kind == "maxpool":
             s, d = r["src"], r["dst"]
             d.buf[..., d.choff:d.choff + s.channels] = F.max_pool2d(_view_nchw(s), 2).permute(0, 2, 3, 1).to(d.buf.dtype)
@@ -75,6 +77,11 @@ def run_records(plan):
                 # acc is the pixel-shuffled post-activation map [B, C', H*r, W*r] (fp32): per-tap 1x1 projection, stored
                 # per LR row and sub-pixel:  z[b][y][s*9+t][x]
                 tw = r["tail_weight"]                                   # [9][C']
+                if not (r.get("tail_flags", 0) & 1):
+                    # single-pass tail: the activation goes back to TMEM as 16-bit and the tap weights are a 16-bit operand tile;
+                    # the compensated tail (PSSR_TAIL_COMP) carries hi + lo of both, i.e. fp32 to first order
+                    acc = acc.to(r["weight"].dtype).float()
+                    tw = tw.to(r["weight"].dtype).float()
                 zt = torch.einsum("bchw,tc->bthw", acc, tw)             # [B, 9, H*r, W*r]
                 B_, _, Hh, Wh = zt.shape
                 zt = zt.view(B_, 9, Hh // rr, rr, Wh // rr, rr).permute(0, 3, 5, 1, 2, 4).reshape(B_, rr * rr * 9, Hh // rr, Wh // rr)
@@ -97,6 +104,10 @@ def run_records(plan):
             o = r["out"]
             if o is not None:
                 o.buf[..., o.choff:o.choff + acc.shape[1]] = acc.permute(0, 2, 3, 1).to(o.buf.dtype)
+            ol = r.get("out_lo")
+            if ol is not None:
+                hi = o.buf[..., o.choff:o.choff + acc.shape[1]].float()
+                ol.buf[..., ol.choff:ol.choff + acc.shape[1]] = (acc.permute(0, 2, 3, 1) - hi).to(ol.buf.dtype)
             if r["out_f32"] is not None:
                 r["out_f32"][..., :acc.shape[1]] = acc.permute(0, 2, 3, 1)
         elif kind == "stem":

@@ -173,3 +173,83 @@ def test_prep_pool_tail():
     assert float((out - ref).abs().max()) < 2e-3, f"tail max err {float((out - ref).abs().max())}"
     ref8 = out.clamp(0, 255).to(torch.uint8)
     assert torch.equal(out8, ref8), "tail uint8 truncation mismatch"
+
+
+# ------------------------------------------------------------------ compensated precision ("fp16c")
+@pytest.mark.parametrize("H,W", [(6, 128), (16, 64), (5, 40)])       # rows mode (shared staged planes), cols mode, flat mode
+def test_conv_compensated_segments(H, W):
+    """(h, x_hi, x_lo) x (W_hi, W_lo): five K segments over three sources, two of them re-reading a source another segment
+    staged, plus the second output out_lo = rn16(y - rn16(y)).  hi + lo must reproduce the fp64 convolution of the UNROUNDED
+    weights / input to ~2^-20, far below one fp16 rounding (include/pssr_b200.h: tail_flags / out_lo)."""
+    P = _setup()
+    plan = P.Plan("fp16c")
+    dt = plan.tdtype
+    B, C = 2, 64
+    h = _rand_act(B, H, W, C, dt, 21)
+    g = torch.Generator(device="cuda").manual_seed(22)
+    x = torch.randint(0, 256, (B, 1, H, W), device="cuda", generator=g).float()
+    sc, sh = torch.tensor([0.93], device="cuda"), torch.tensor([0.07], device="cuda")
+    im2col = torch.zeros(B, H, W, 16, dtype=dt, device="cuda")
+    im2col_lo = torch.zeros_like(im2col)
+    plan.prep(x, sc, sh, im2col, im2col_lo=im2col_lo)
+    w3 = torch.randn(C, C, 3, 3, device="cuda", generator=g) / (3.0 * C ** 0.5)
+    wx = torch.randn(C, 1, 3, 3, device="cuda", generator=g) / 3.0
+    b = torch.randn(C, device="cuda", generator=g)
+    from pssr2_b200.models import _im2col_parts
+    wxc = _im2col_parts(wx)
+    wp = P.pack_weight([w3, wxc, wxc, P.split_lo(wxc, plan.dtype), P.split_lo(w3, plan.dtype)], plan.dtype)
+    out = torch.zeros(B, H, W, C, dtype=dt, device="cuda")
+    out_lo = torch.full((B, H, W, C + 16), 5.0, dtype=dt, device="cuda")
+    plan.conv([P.View(h), P.View(im2col), P.View(im2col_lo)], [(0, 9, 1), (1, 1, 1), (2, 1, 1), (1, 1, 1), (0, 9, 1)], wp, b, P.View(out),
+              Ho=H, Wo=W, B=B, act=P.ACT_RELU, out_lo=P.View(out_lo, 16, C))
+    plan.finalize()
+    plan.run()
+    torch.cuda.synchronize()
+    xn = (x / 128 - 1) * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)
+    cols = F.unfold(xn, 3, padding=1).view(B, 9, H, W)
+    assert torch.equal(_nchw(im2col)[:, :9], cols.to(dt).float())
+    assert torch.equal(_nchw(im2col_lo)[:, :9], (cols - cols.to(dt).float()).to(dt).float()), "im2col_lo mismatch"
+    ref = F.relu(F.conv2d(_nchw(h).double(), w3.double(), None, padding=1) + F.conv2d(xn.double(), wx.double(), b.double(), padding=1))
+    got = _nchw(out).double() + _nchw(out_lo[..., 16:]).double()
+    err = float((got - ref).abs().max())
+    single = float((_nchw(out).double() - ref).abs().max())
+    print(f"compensated conv {H}x{W}: hi+lo err {err:.3g}, hi alone {single:.3g}, max ref {float(ref.abs().max()):.3g}")
+    assert err < 2.0 ** -17 * max(1.0, float(ref.abs().max())), err
+    assert torch.equal(out.float(), (out.float() + out_lo[..., 16:].float()).to(dt).float()), "out is not the rounding of hi + lo"
+    assert bool((out_lo[..., :16].float() == 5.0).all()), "out_lo wrote outside its channel slice"
+
+
+@pytest.mark.parametrize("H,W,s", [(4, 128, 4), (8, 64, 2), (3, 128, 8)])    # window-48 layout, flat mode, per-tap layout in rows mode
+def test_tail_compensated(H, W, s):
+    """Fused Reconstruction tail with PSSR_TAIL_COMP: relu(pre) is projected on the tail taps as hi (16-bit, TMEM) x [W_hi ; W_lo]
+    plus an e5m2 pass for lo.  Against the fp64 statement of relu -> pixel_shuffle -> 3x3 conv the error must drop well below the
+    single-pass tail's (which rounds the activation and the tap weights to 16 bits)."""
+    P = _setup()
+    B, C = 2, 64
+    errs = {}
+    for prec, flags in (("fp16", 0), ("fp16c", P.TAIL_COMP)):
+        plan = P.Plan(prec)
+        dt = plan.tdtype
+        h = _rand_act(B, H, W, C, dt, 31)
+        g = torch.Generator(device="cuda").manual_seed(32)
+        n = s * s * 64
+        w3 = torch.randn(n, C, 3, 3, device="cuda", generator=g) / (3.0 * C ** 0.5)
+        b = torch.randn(n, device="cuda", generator=g) * 0.5
+        wt = torch.randn(1, 64, 3, 3, device="cuda", generator=g) / 24.0
+        wp = P.pack_weight([w3], plan.dtype, s)
+        bp = P.permute_n(b, s).contiguous()
+        tw = wt[0].permute(1, 2, 0).reshape(9, 64).contiguous()
+        win48 = 1 if (s == 4 and W % 128 == 0) else 0
+        z = torch.zeros(B, H, 48 if win48 else s * s * 9, W, device="cuda")
+        out = torch.zeros(B, 1, H * s, W * s, device="cuda")
+        plan.conv([P.View(h)], [(0, 9, 1)], wp, bp, None, Ho=H, Wo=W, B=B, shuffle=s, act=P.ACT_RELU, tail_weight=tw, tail_z=z,
+                  tail_layout=win48, tail_flags=flags)
+        plan.tailsum(z, s, 0.25, 1.0, 0.0, out, None, layout=win48)
+        plan.finalize()
+        plan.run()
+        torch.cuda.synchronize()
+        pre = F.relu(F.conv2d(_nchw(h).double(), w3.to(dt).double(), b.double(), padding=1))
+        ref = F.conv2d(F.pixel_shuffle(pre, s), wt.double(), None, padding=1) + 0.25
+        errs[prec] = float((out.double() - ref).abs().max())
+    print(f"tail {H}x{W} s={s}: single-pass err {errs['fp16']:.3g}, compensated {errs['fp16c']:.3g}")
+    assert errs["fp16c"] < 0.2 * errs["fp16"] and errs["fp16c"] < 2e-5, errs

@@ -1,13 +1,13 @@
-"""GPU parity of the ResUNet plan (tcgen05 convolutions + fused epilogues) against the fp32 CPU oracle
+"""GPU parity of the ResUNet / RDResUNet plans (tcgen05 convolutions + fused epilogues) against the fp32 CPU oracle
 (oracle/models.py, itself pinned to the reference modules).
 
 Tolerances (0..255 output scale), from BASELINE.json north_star: <= 1e-2 max-abs / >= 50 dB PSNR vs
-the reference fp32 output.  With 16-bit tensor-core operands the measured/emulated budget is
-  fp16 operands: max-abs ~1.3e-2 (the 16-bit round trip of Reconstruction.pre's output dominates),
-  bf16 operands: max-abs ~1e-1, PSNR ~82 dB,
-so the tests assert PSNR >= 50 dB for both and max-abs <= 3e-2 for fp16 / <= 0.3 for bf16 (an
-indexing or packing bug produces O(1..100) errors; tests/test_plan_cpu.py checks the emitted plan
-against the oracle on CPU independently of the kernels).
+the reference fp32 output.  Measured / emulated budget of the three operand modes (scripts/dev_error_budget.py):
+  "fp16c" (default)  fp16 operands with hi + lo compensation of the full-resolution skip path: max-abs ~6e-3 -> asserted <= 1e-2
+  "fp16"             single-pass fp16: max-abs ~1.5e-2 (asserted <= 3e-2)
+  "bf16"             single-pass bf16: max-abs ~1e-1, PSNR ~82 dB (asserted <= 0.3)
+An indexing or packing bug produces O(1..100) errors; tests/test_plan_cpu.py checks the emitted plan
+against the oracle on CPU independently of the kernels.
 """
 import numpy as np
 import pytest
@@ -33,7 +33,10 @@ def _psnr(a, b):
     return 10 * np.log10(255.0 ** 2 / max(mse, 1e-30))
 
 
-@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+TOL = {"fp16c": 1e-2, "fp16": 3e-2, "bf16": 0.3}
+
+
+@pytest.mark.parametrize("prec", ["fp16c", "fp16", "bf16"])
 def test_resunet_matches_oracle(prec):
     from pssr2_b200.models import ResUNet
     torch.manual_seed(0)
@@ -43,7 +46,7 @@ def test_resunet_matches_oracle(prec):
     rng = np.random.default_rng(0)
     x = torch.tensor(rng.integers(0, 256, (2, 1, 128, 128)).astype(np.float32))
     want = resunet_forward(sd, x)
-    emu = resunet_forward(sd, x, emulate=prec)
+    emu = resunet_forward(sd, x, emulate="fp16" if prec == "fp16c" else prec)
     model.precision = prec
     model = model.cuda()
     got = model(x.cuda()).cpu()
@@ -52,10 +55,44 @@ def test_resunet_matches_oracle(prec):
     d_emu = float((got - emu).abs().max())
     print(f"[{prec}] max-abs vs fp32 oracle {d_ref:.5f}, vs emulation {d_emu:.5f}, PSNR {_psnr(got, want):.1f} dB")
     assert _psnr(got, want) >= 50.0
-    assert d_ref <= (3e-2 if prec == "fp16" else 0.3)
+    assert d_ref <= TOL[prec]
     # fused `_pred_array`: uint8 truncation of the same fp32 values
     out, out8 = model.forward_u8(x.cuda())
     assert torch.equal(out8.cpu(), out.clamp(0, 255).to(torch.uint8).cpu())
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_resunet_default_meets_north_star_tolerance(seed):
+    """Default model, default precision, other seeds / batch: <= 1e-2 max-abs and >= 50 dB (north star)."""
+    from pssr2_b200.models import ResUNet
+    torch.manual_seed(seed)
+    model = ResUNet().eval()
+    _randomise_bn(model, seed + 10)
+    assert model.precision == "fp16c"
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x = torch.tensor(np.random.default_rng(seed).integers(0, 256, (3, 1, 128, 128)).astype(np.float32))
+    want = resunet_forward(sd, x)
+    got = model.cuda()(x.cuda()).cpu()
+    d = float((got - want).abs().max())
+    print(f"[default ResUNet seed {seed}] max-abs {d:.5f}, PSNR {_psnr(got, want):.1f} dB")
+    assert d <= 1e-2 and _psnr(got, want) >= 50.0
+
+
+def test_resunet_scale8_multiframe_meets_tolerance():
+    """BASELINE config 5's model, ResUNet(channels=[5, 1], scale=8) (reference kwargs grid tests/test_models.py:5-12), at a
+    small spatial size: 64-wide 5-channel im2col blocks (hi / lo), 16 N tiles in the fused tail, per-tap z layout."""
+    from pssr2_b200.models import ResUNet
+    torch.manual_seed(4)
+    model = ResUNet(channels=[5, 1], scale=8).eval()
+    _randomise_bn(model, 5)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x = torch.tensor(np.random.default_rng(4).integers(0, 256, (2, 5, 64, 64)).astype(np.float32))
+    want = resunet_forward(sd, x)
+    got = model.cuda()(x.cuda()).cpu()
+    d = float((got - want).abs().max())
+    print(f"[ResUNet [5,1] scale 8] max-abs {d:.5f}, PSNR {_psnr(got, want):.1f} dB")
+    assert got.shape == want.shape == (2, 1, 512, 512)
+    assert d <= 1e-2 and _psnr(got, want) >= 50.0
 
 
 def test_resunet_small_variant_multichannel():
@@ -128,4 +165,6 @@ def test_rdresunet_matches_oracle(cfg, shape):
     d = float((got - want).abs().max())
     print(f"[rdresunet {shape}] max-abs vs fp32 oracle {d:.5f}, PSNR {_psnr(got, want):.1f} dB")
     assert got.shape == want.shape
-    assert _psnr(got, want) >= 50.0 and d <= 6e-2
+    # the RDNet encoder's first stage (stem, LayerNorm, GELU expand / project at half resolution) sits on the same shallow path
+    # to the output and is not compensated yet: emulated 1.2e-2 with the default layer scale, 2e-2 with the randomised one
+    assert _psnr(got, want) >= 50.0 and d <= 3e-2

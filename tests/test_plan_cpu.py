@@ -21,7 +21,8 @@ def dry_run():
 @pytest.mark.parametrize("cfg", [dict(), dict(channels=[3, 3], hidden=[64, 128, 256], scale=2, depth=1),
                                  dict(channels=[5, 1], hidden=[64, 128], scale=8, depth=0),
                                  dict(channels=[9, 1], hidden=[64, 128], scale=2, depth=1)])   # > 7 channels: no im2col, 3x3 over the input
-def test_resunet_plan_matches_oracle_on_cpu(dry_run, cfg):
+@pytest.mark.parametrize("prec", ["fp16", "fp16c"])
+def test_resunet_plan_matches_oracle_on_cpu(dry_run, cfg, prec):
     from pssr2_b200.models import ResUNet
     torch.manual_seed(0)
     model = ResUNet(**cfg).eval()
@@ -31,14 +32,19 @@ def test_resunet_plan_matches_oracle_on_cpu(dry_run, cfg):
     B, H, W = (2, 32, 48) if small else (1, 32, 32)
     x = torch.tensor(np.random.default_rng(0).integers(0, 256, (B, cin, H, W)).astype(np.float32))
     want = resunet_forward(model.state_dict(), x)
-    model.precision = "fp16"
+    model.precision = prec
     st = model._build(x.shape, x.dtype, torch.device("cpu"))
     st["x"].copy_(x)
     run_records(st["plan"])
     got = st["out"]
     assert got.shape == want.shape
-    # 16-bit operand rounding only (fp16: ~1e-2 on the 0..255 scale); an indexing / packing bug gives O(1..100)
-    assert float((got - want).abs().max()) < 3e-2
+    # 16-bit operand rounding only (fp16: ~1e-2 on the 0..255 scale); an indexing / packing bug gives O(1..100).
+    # The compensated plan (hi + lo on the shallow full-resolution path) must land below the 1e-2 bar of the north star.
+    err = float((got - want).abs().max())
+    print(f"{cfg} {prec}: max-abs {err:.5f}")
+    # (the reduced test nets put relatively more weight on the one uncompensated term left, the last decoder output feeding
+    # Reconstruction.pre; the default-depth models the 1e-2 bar is stated for are asserted in tests/test_gpu_net.py)
+    assert err < ((1e-2 if not cfg else 1.5e-2) if prec == "fp16c" else 3e-2)
     c = got.shape[1] // 2
     assert torch.equal(st["out_u8"], got[:, c:c + 1].clamp(0, 255).to(torch.uint8))
 
@@ -52,12 +58,13 @@ def test_resunet_plan_window48_tail_on_cpu(dry_run):
     _randomise_bn(model)
     x = torch.tensor(np.random.default_rng(3).integers(0, 256, (2, 1, 4, 128)).astype(np.float32))
     want = resunet_forward(model.state_dict(), x)
-    model.precision = "fp16"
-    st = model._build(x.shape, x.dtype, torch.device("cpu"))
-    assert any(k == "tailsum" and r["layout"] == 1 for k, r in st["plan"].records)
-    st["x"].copy_(x)
-    run_records(st["plan"])
-    assert float((st["out"] - want).abs().max()) < 3e-2
+    for prec, tol in (("fp16", 3e-2), ("fp16c", 2e-2)):      # two levels, depth 0: a packing test, not a precision claim
+        model.precision = prec
+        st = model._build(x.shape, x.dtype, torch.device("cpu"))
+        assert any(k == "tailsum" and r["layout"] == 1 for k, r in st["plan"].records)
+        st["x"].copy_(x)
+        run_records(st["plan"])
+        assert float((st["out"] - want).abs().max()) < tol
 
 
 @pytest.mark.parametrize("cfg", [dict(), dict(hidden=[128, 64], growth_rates=[32, 40, 64], ds_blocks=[False, True, False],
