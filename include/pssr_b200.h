@@ -156,6 +156,7 @@ int pssr_resize_bilinear(const void* src, void* dst, int32_t n, int32_t h, int32
 #define PSSR_OP_COPY 8        /* channel-slice copy between NHWC buffers                    */
 #define PSSR_OP_TAILSUM 9     /* 9-tap gather of the fused Reconstruction tail + *128+128   */
 #define PSSR_OP_STEM 10       /* RDNet PatchifyStem: normalise + patch conv + LayerNorm2d   */
+#define PSSR_OP_CAST8 11      /* 16-bit NHWC view * scale -> e5m2 NHWC (operand of PSSR_SEG_E5M2 segments) */
 
 /* One NHWC source view of an implicit-GEMM op. */
 typedef struct {
@@ -173,11 +174,17 @@ typedef struct {
   int32_t src;           /* index into srcs[]                                              */
   int32_t taps;          /* 1: 1x1,  9: 3x3 pad 1,  4: 2x2 stride 2                        */
   int32_t cblocks;       /* 64-channel blocks per tap                                      */
-  int32_t reserved;
+  int32_t fmt;           /* PSSR_SEG_F16: 16-bit source x `weights`;  PSSR_SEG_E5M2: the source is an e5m2 NHWC tensor
+                            (1-byte elements; channels / cstride in elements) multiplied with `weights8` by kind::f8f6f4
+                            MMAs (K = 32, twice the 16-bit rate) into the same fp32 accumulator -- the low-order terms of
+                            the compensated precision only have to be known to a few bits.  3x3 segments of layers whose
+                            width is a multiple of 128 only.                                                          */
 } pssr_kseg_t;
+#define PSSR_SEG_F16 0
+#define PSSR_SEG_E5M2 1
 
 typedef struct {
-  pssr_src_t srcs[3];
+  pssr_src_t srcs[4];
   int32_t n_srcs;
   pssr_kseg_t segs[6];
   int32_t n_segs;
@@ -219,6 +226,7 @@ typedef struct {
   void* out_lo;
   int32_t out_lo_cstride;
   int32_t out_lo_choff;
+  const void* weights8;  /* [n][k8_total] e5m2, K-major, K ordered like `weights` over the PSSR_SEG_E5M2 segments only */
 } pssr_conv_desc_t;
 #define PSSR_TAIL_TAPS 0
 #define PSSR_TAIL_WINDOW48 1
@@ -272,6 +280,14 @@ typedef struct {
   uint8_t* out_u8;       /* [B][H*r][W*r] or NULL                                             */
 } pssr_tailsum_desc_t;
 
+/* PSSR_OP_CAST8: out[b][y][x][c] = e5m2(in[b][y][x][c] * scale), round to nearest, saturating (C % 16 == 0). */
+typedef struct {
+  const void* in; int32_t in_cstride, in_choff, C;
+  int32_t B, H, W;
+  float scale;
+  void* out; int32_t out_cstride, out_choff;
+} pssr_cast8_desc_t;
+
 /* ---- RDNet encoder ops (pssr/models/_rdnet.py) ---------------------------------------------- */
 /* PSSR_OP_STEM: x/128-1 -> BatchNorm(eval) -> PatchifyStem conv (kernel = stride = patch, _rdnet.py:106-116)
  * -> LayerNorm2d over channels (timm, eps 1e-6).  Output NHWC 16-bit [B][H/patch][W/patch][.].        */
@@ -324,6 +340,7 @@ typedef struct {
     pssr_ln_desc_t ln;
     pssr_dwln_desc_t dwln;
     pssr_ese_desc_t ese;
+    pssr_cast8_desc_t cast8;
     uint8_t pad[512];
   } u;
 } pssr_op_t;

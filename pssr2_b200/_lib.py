@@ -82,17 +82,22 @@ class Src(Structure):
 
 
 class KSeg(Structure):
-    _fields_ = [("src", c_int32), ("taps", c_int32), ("cblocks", c_int32), ("reserved", c_int32)]
+    _fields_ = [("src", c_int32), ("taps", c_int32), ("cblocks", c_int32), ("fmt", c_int32)]
 
 
 class ConvDesc(Structure):
-    _fields_ = [("srcs", Src * 3), ("n_srcs", c_int32), ("segs", KSeg * 6), ("n_segs", c_int32),
+    _fields_ = [("srcs", Src * 4), ("n_srcs", c_int32), ("segs", KSeg * 6), ("n_segs", c_int32),
                 ("weights", c_void_p), ("bias", c_void_p), ("n", c_int32), ("n_valid", c_int32),
                 ("Ho", c_int32), ("Wo", c_int32), ("B", c_int32), ("out", c_void_p),
                 ("out_cstride", c_int32), ("out_choff", c_int32), ("shuffle", c_int32), ("act", c_int32),
                 ("out_scale", c_void_p), ("out_f32", c_void_p), ("tail_weight", c_void_p), ("tail_z", c_void_p),
                 ("tail_layout", c_int32), ("tail_flags", c_int32), ("out_lo", c_void_p),
-                ("out_lo_cstride", c_int32), ("out_lo_choff", c_int32)]
+                ("out_lo_cstride", c_int32), ("out_lo_choff", c_int32), ("weights8", c_void_p)]
+
+
+class Cast8Desc(Structure):
+    _fields_ = [("in_", c_void_p), ("in_cstride", c_int32), ("in_choff", c_int32), ("C", c_int32), ("B", c_int32), ("H", c_int32),
+                ("W", c_int32), ("scale", c_float), ("out", c_void_p), ("out_cstride", c_int32), ("out_choff", c_int32)]
 
 
 class PrepDesc(Structure):
@@ -144,7 +149,7 @@ class EseDesc(Structure):
 
 
 class _OpU(Union):
-    _fields_ = [("conv", ConvDesc), ("prep", PrepDesc), ("pool", PoolDesc), ("tail", TailDesc), ("tailsum", TailSumDesc), ("stem", StemDesc), ("ln", LnDesc), ("dwln", DwLnDesc), ("ese", EseDesc),
+    _fields_ = [("conv", ConvDesc), ("prep", PrepDesc), ("pool", PoolDesc), ("tail", TailDesc), ("tailsum", TailSumDesc), ("stem", StemDesc), ("ln", LnDesc), ("dwln", DwLnDesc), ("ese", EseDesc), ("cast8", Cast8Desc),
                 ("pad", c_uint8 * 512)]
 
 
@@ -153,7 +158,8 @@ class Op(Structure):
 
 
 OP_CONV, OP_PREP, OP_MAXPOOL, OP_TAIL, OP_TAILSUM = 1, 2, 3, 4, 9
-OP_DWCONV_LN, OP_LAYERNORM, OP_ESE, OP_STEM = 5, 6, 7, 10
+OP_DWCONV_LN, OP_LAYERNORM, OP_ESE, OP_STEM, OP_CAST8 = 5, 6, 7, 10, 11
+SEG_F16, SEG_E5M2 = 0, 1
 DT_BF16, DT_FP16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 NOISE_POISSON, NOISE_GAUSSIAN, NOISE_SALTPEPPER = 1, 2, 3

@@ -78,6 +78,7 @@ int pssr_plan_create(const pssr_op_t* ops, int32_t n_ops, int32_t dtype, pssr_pl
       case PSSR_OP_LAYERNORM:
       case PSSR_OP_DWCONV_LN:
       case PSSR_OP_ESE:
+      case PSSR_OP_CAST8:
         break;
       default:
         set_error("plan_create: op %d has unsupported kind %d", i, op.kind);
@@ -146,6 +147,9 @@ int pssr_plan_run_range(pssr_plan_t* plan, int32_t first, int32_t count, void* s
         break;
       case PSSR_OP_ESE:
         rc = ese_launch(op.u.ese, plan->dtype, st);
+        break;
+      case PSSR_OP_CAST8:
+        rc = cast8_launch(op.u.cast8, plan->dtype, st);
         break;
       default:
         set_error("plan_run: op %d has unsupported kind %d", i, op.kind);

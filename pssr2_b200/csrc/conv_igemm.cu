@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   if (warp == 0) {
     // ================================ TMA producer ==================================
     if (lane == 0) {
-      const CUtensorMap* tmB = p.tmaps + 3;
+      const CUtensorMap* tmB = p.tmaps + kTmW;
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -292,7 +292,7 @@ static int floor_pow2(int v) {
 int conv_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
   EncodeTiledFn enc = get_encode_fn();
   PSSR_REQUIRE(enc != nullptr, PSSR_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-  PSSR_REQUIRE(d.n_srcs >= 1 && d.n_srcs <= 3 && d.n_segs >= 1 && d.n_segs <= 6, PSSR_EINVAL,
+  PSSR_REQUIRE(d.n_srcs >= 1 && d.n_srcs <= 4 && d.n_segs >= 1 && d.n_segs <= 6, PSSR_EINVAL,
                "conv: n_srcs/n_segs out of range");
   PSSR_REQUIRE(d.n >= 32 && d.n % 32 == 0, PSSR_EUNSUP, "conv: n=%d must be a positive multiple of 32", d.n);
   PSSR_REQUIRE(d.n_valid > 0 && d.n_valid <= d.n && d.n_valid % 8 == 0, PSSR_EUNSUP,
@@ -334,12 +334,13 @@ int conv_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
 
   const CUtensorMapDataType tdt = dtype == PSSR_DT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   int num_kb = 0;
-  bool src_stride2[3] = {false, false, false};
+  bool src_stride2[4] = {false, false, false, false};
   p.n_segs = d.n_segs;
   for (int s = 0; s < d.n_segs; ++s) {
     const pssr_kseg_t& sg = d.segs[s];
     PSSR_REQUIRE(sg.src >= 0 && sg.src < d.n_srcs, PSSR_EINVAL, "conv: segment source index out of range");
     PSSR_REQUIRE(sg.taps == 1 || sg.taps == 9 || sg.taps == 4, PSSR_EUNSUP, "conv: taps must be 1, 4 or 9");
+    PSSR_REQUIRE(sg.fmt == PSSR_SEG_F16, PSSR_EUNSUP, "conv: e5m2 segments need the rows-mode kernel (3x3, width %% 128 == 0)");
     PSSR_REQUIRE(sg.cblocks >= 1, PSSR_EINVAL, "conv: cblocks must be >= 1");
     p.seg_src[s] = sg.src;
     p.seg_taps[s] = sg.taps;
@@ -377,7 +378,7 @@ int conv_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
     cuuint64_t gstr[1] = {ktot * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)block_n};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&op.tmaps[3], tdt, 2, const_cast<void*>(d.weights), gdim, gstr, box, estr,
+    CUresult r = enc(&op.tmaps[kTmW], tdt, 2, const_cast<void*>(d.weights), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PSSR_REQUIRE(r == CUDA_SUCCESS, PSSR_ECUDA, "cuTensorMapEncodeTiled(weights) failed with %d", (int)r);

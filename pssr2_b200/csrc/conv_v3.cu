@@ -34,7 +34,7 @@ static constexpr int kV3MaxB = 8;
 static constexpr int kV3MaxR = 12;   // ring slots (row groups) in rows mode
 
 struct V3Params {
-  const CUtensorMap* tmaps;   // device: [0..2] sources, [3] weights
+  const CUtensorMap* tmaps;   // device: [0..3] sources, [kTmW] weights, [kTmOut] output, [kTmW8] e5m2 weights
   int n_segs;
   int seg_src[6], seg_taps[6], seg_cblocks[6], seg_kb0[6];
   int num_kb;
@@ -48,6 +48,8 @@ struct V3Params {
   uint32_t group_bytes;       // rows mode: all planes of one row (layout stride of a ring slot)
   uint32_t group_tx;          // rows mode: bytes the TMA unit writes per ring slot
   int seg_k16[6];             // rows mode: the segment's source is a 16-channel tensor staged as a narrow plane (one K = 16 MMA)
+  int seg_f8[6];              // rows mode: e5m2 source (64-byte pixels, SWIZZLE_64B) x e5m2 weights, kind::f8f6f4 (K = 32)
+  uint32_t slot8_bytes;       // rows mode: one row of an e5m2 plane = P * 64 rounded up to 128
   int seg_load[6];            // rows mode: 0 = the segment reads the planes an earlier segment over the same source staged
   uint32_t seg_plane[6];      // rows mode: byte offset of the segment's first plane inside a ring slot
   uint32_t ring_bytes;        // rows mode: ring_R * group_bytes rounded up to 1024
@@ -74,7 +76,7 @@ struct V3Params {
   float* out_f32;
   int out_cstride, out_choff, shuffle, cps, act, fp16;
   int Hout, Wout;
-  int tma_store;              // 1: the epilogue stages 16-bit tiles in shared memory and writes them with TMA (tmaps[4])
+  int tma_store;              // 1: the epilogue stages 16-bit tiles in shared memory and writes them with TMA (tmaps[kTmOut])
   uint32_t stage_off;         // byte offset of the 8 x 4 KB store staging tiles inside the aligned dynamic shared memory
   const float* tail_w;        // fused Reconstruction tail: fp32 [9][64]
   float* tail_z;              // fp32 [B][H][r*r*9][W]: the r*r*9 plane rows of one LR row are contiguous
@@ -461,7 +463,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
               for (int cb = 0; cb < p.seg_cblocks[sg]; ++cb) {
                 if (PAIR) v3_tma_4d_pair(dst, tm, fbar, cb * 64, x0, first_row + i, n);
                 else tma_load_4d(dst, tm, fbar, cb * 64, x0, first_row + i, n);
-                dst += p.seg_k16[sg] ? p.slot16_bytes : p.slot_bytes;
+                dst += p.seg_k16[sg] ? p.slot16_bytes : p.seg_f8[sg] ? p.slot8_bytes : p.slot_bytes;
               }
             }
             if (++slot == p.ring_R) { slot = 0; phase ^= 1u; }
@@ -539,7 +541,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
     // ================================ B producer: weights ===================================
     // p.tap_bytes = bytes of one tap's weight block held by ONE CTA (a pair splits the N rows); bytes counted on the leader
     if (lane == 0) {
-      const CUtensorMap* tmB = p.tmaps + 3;
+      const CUtensorMap* tmB16 = p.tmaps + kTmW;
+      const CUtensorMap* tmB = tmB16;
       const int nrow0 = (int)rank * (block_n / C);
       if (RES) {
         const uint32_t fbar = PAIR ? v3_mapa(b_full(0), 0) : b_full(0);
@@ -562,16 +565,20 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
           for (int sg = 0; sg < p.n_segs; ++sg) {
             const int taps = p.seg_taps[sg], cbs = p.seg_cblocks[sg];
             const int gs = taps == 9 ? G : 1;
+            // e5m2 segments: 64-byte weight rows from their own matrix, half a 16-bit tap block per tap
+            const bool f8 = ROWS && p.seg_f8[sg] != 0;
+            tmB = f8 ? p.tmaps + kTmW8 : tmB16;
+            const uint32_t tapb = f8 ? (p.tap_bytes >> 1) : p.tap_bytes;
             if (rm && taps != 9 && g != 1) continue;
             const int t_lo = (rm && taps == 9) ? 3 * g : 0, t_hi = (rm && taps == 9) ? 3 * g + 3 : taps;
             for (int cb = 0; cb < cbs; ++cb) {
               for (int t0 = t_lo; t0 < t_hi; t0 += gs) {
                 mbar_wait(b_empty(bs), bphase ^ 1u);
                 const uint32_t fbar = PAIR ? v3_mapa(b_full(bs), 0) : b_full(bs);
-                if (rank == 0) mbar_arrive_expect_tx(b_full(bs), (uint32_t)gs * p.tap_bytes * C);
+                if (rank == 0) mbar_arrive_expect_tx(b_full(bs), (uint32_t)gs * tapb * C);
                 for (int t = 0; t < gs; ++t) {
                   const int kb = p.seg_kb0[sg] + (t0 + t) * cbs + cb;   // weights are packed tap-major, then channel block
-                  const uint32_t dst = b_base + (uint32_t)bs * p.b_bytes + (uint32_t)t * p.tap_bytes;
+                  const uint32_t dst = b_base + (uint32_t)bs * p.b_bytes + (uint32_t)t * tapb;
                   if (PAIR) v3_tma_2d_pair(dst, tmB, fbar, kb * 64, n_tile * block_n + nrow0);
                   else tma_load_2d(dst, tmB, fbar, kb * 64, n_tile * block_n + nrow0);
                 }
@@ -591,6 +598,10 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
     const uint32_t idesc_tail = umma_idesc_f16(p.fp16 ? 0 : 1, (int)tail_n) + (PAIR ? (8u << 24) : 0u);
     // kind::f8f6f4: fp32 accumulate, A and B e5m2 (format 1), K-major, N = 16
     const uint32_t idesc_f8 = (1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24) + (PAIR ? (8u << 24) : 0u);
+    const uint32_t idesc_m8 = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)block_n >> 3) << 17) | ((128u >> 4) << 24) + (PAIR ? (8u << 24) : 0u);
+    // e5m2 planes / weight tiles: same start-address field, SWIZZLE_64B layout (type 4), 512 bytes between 8-row groups
+    const uint64_t f8_fix = (((uint64_t)(512u >> 4) << 32) | ((uint64_t)4 << 61)) - (((uint64_t)(1024u >> 4) << 32) | ((uint64_t)2 << 61));
+    const uint64_t slot8_desc = (uint64_t)(p.slot8_bytes >> 4);
     const uint64_t tdesc = v3_desc(smem_base + tailw_off);
     const uint64_t w8desc = v3_desc64(smem_base + w8_off);
     const uint64_t lo8desc = v3_desc64(smem_base + lo8_off);
@@ -614,7 +625,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       segw[i] = i < p.n_segs ? ((p.seg_taps[i] == 9 ? 1u : 0u) | ((uint32_t)p.seg_cblocks[i] << 1) | ((uint32_t)p.seg_kb0[i] << 9) |
-                                (p.seg_k16[i] ? 0x80000000u : 0u)) : 0u;
+                                (p.seg_k16[i] ? 0x80000000u : 0u) | (p.seg_f8[i] ? 0x40000000u : 0u)) : 0u;
       segp[i] = i < p.n_segs ? (p.seg_plane[i] >> 4) : 0u;
     }
     const int n_segs = p.n_segs;
@@ -661,9 +672,10 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
         uint64_t plane_desc = sg == 0 ? segp[0] : sg == 1 ? segp[1] : sg == 2 ? segp[2] : sg == 3 ? segp[3] : sg == 4 ? segp[4] : segp[5];
         const bool nine = (sw & 1u) != 0;
         const bool k16 = ROWS && (sw >> 31) != 0;
+        const bool f8 = ROWS && ((sw >> 30) & 1u) != 0;
         const int cbs = (int)((sw >> 1) & 0xffu);
-        const int kb0 = (int)((sw >> 9) & 0x3fffffu);
-        for (int cb = 0; cb < cbs; ++cb, plane_desc += (k16 ? slot16_desc : slot_desc)) {
+        const int kb0 = (int)((sw >> 9) & 0x1fffffu);
+        for (int cb = 0; cb < cbs; ++cb, plane_desc += (k16 ? slot16_desc : f8 ? slot8_desc : slot_desc)) {
           uint64_t ad0 = 0;
           if (!ROWS) {
             mbar_wait(a_full(as), aphase);
@@ -671,7 +683,34 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
             ad0 = as ? adesc_s1 : adesc_s0;
           }
           if (acc == 0 && it < 31) V3_TRACE(128 + 2 * it);
-          if (nine) {
+          if (ROWS && f8) {
+            // e5m2 3x3 segment (streamed weights): two K = 32 MMAs per tap and 64-channel block
+#pragma unroll
+            for (int t0 = 0; t0 < 9; t0 += G) {
+              mbar_wait(b_full(bs), bphase);
+              tc_fence_after();
+              const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)bs * bstep) + f8_fix;
+              if (elect_one()) {
+#pragma unroll
+                for (int tt = 0; tt < G; ++tt) {
+                  const int t = t0 + tt;
+                  const int dy = t / 3 - 1, dx = t % 3 - 1;
+                  const uint64_t bdt = bd + (uint64_t)tt * (uint64_t)(tapstep >> 1);
+#pragma unroll
+                  for (int mt = 0; mt < T; ++mt) {
+                    const uint64_t adm = ea[mt + 1 + dy] + plane_desc + (uint64_t)((1 + dx) * 4) + f8_fix;
+                    const uint32_t dcol = d0 + (uint32_t)(mt * block_n);
+                    v3_mma_f8<PAIR>(dcol, adm, bdt, idesc_m8, (tt == 0) ? acc : 1u);
+                    v3_mma_f8<PAIR>(dcol, adm + 2, bdt + 2, idesc_m8, 1u);
+                  }
+                }
+                v3_commit<PAIR>(b_empty(bs));
+              }
+              __syncwarp();
+              acc = 1;
+              if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; }
+            }
+          } else if (nine) {
 #pragma unroll
             for (int t0 = 0; t0 < 9; t0 += G) {
               uint64_t bd;
@@ -783,11 +822,38 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
           uint64_t plane_desc = sg == 0 ? segp[0] : sg == 1 ? segp[1] : sg == 2 ? segp[2] : sg == 3 ? segp[3] : sg == 4 ? segp[4] : segp[5];
           const bool nine = (sw & 1u) != 0;
           const bool k16 = (sw >> 31) != 0;
+          const bool f8 = ((sw >> 30) & 1u) != 0;
           const int cbs = (int)((sw >> 1) & 0xffu);
-          const int kb0 = (int)((sw >> 9) & 0x3fffffu);
+          const int kb0 = (int)((sw >> 9) & 0x1fffffu);
           if (!nine && g != 1) continue;
-          for (int cb = 0; cb < cbs; ++cb, plane_desc += (k16 ? slot16_desc : slot_desc)) {
-            if (nine) {
+          for (int cb = 0; cb < cbs; ++cb, plane_desc += (k16 ? slot16_desc : f8 ? slot8_desc : slot_desc)) {
+            if (f8) {
+              constexpr int GS = G == 9 ? 3 : G;
+#pragma unroll
+              for (int x0 = 0; x0 < 3; x0 += GS) {
+                mbar_wait(b_full(bs), bphase);
+                tc_fence_after();
+                const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)bs * bstep) + f8_fix;
+                if (elect_one()) {
+#pragma unroll
+                  for (int tt = 0; tt < GS; ++tt) {
+                    const int dx = x0 + tt - 1;
+                    const uint64_t bdt = bd + (uint64_t)tt * (uint64_t)(tapstep >> 1);
+#pragma unroll
+                    for (int mt = 0; mt < T; ++mt) {
+                      const uint64_t adm = ea[mt + 1 + dy] + plane_desc + (uint64_t)((1 + dx) * 4) + f8_fix;
+                      const uint32_t dcol = d0 + (uint32_t)(mt * block_n);
+                      v3_mma_f8<PAIR>(dcol, adm, bdt, idesc_m8, (tt == 0) ? acc : 1u);
+                      v3_mma_f8<PAIR>(dcol, adm + 2, bdt + 2, idesc_m8, 1u);
+                    }
+                  }
+                  v3_commit<PAIR>(b_empty(bs));
+                }
+                __syncwarp();
+                acc = 1;
+                if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; }
+              }
+            } else if (nine) {
               constexpr int GS = G == 9 ? 3 : G;          // taps per weight stage inside one filter row
 #pragma unroll
               for (int x0 = 0; x0 < 3; x0 += GS) {
@@ -1191,7 +1257,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0 && !(p.dbg & 1)) {
-              const CUtensorMap* tmo = p.tmaps + 4;
+              const CUtensorMap* tmo = p.tmaps + kTmOut;
               if (ROWS) {
                 if (gvalid) v3_tma_store_4d(tmo, stg, nb, gx0 + q4 * 32, gy0 + mt, gn);
               } else if (p.pad) {
@@ -1416,7 +1482,7 @@ int v3_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
 static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, bool force_flat) {
   EncodeTiledFn enc = v3_encode_fn();
   PSSR_REQUIRE(enc != nullptr, PSSR_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-  PSSR_REQUIRE(d.n_srcs >= 1 && d.n_srcs <= 3 && d.n_segs >= 1 && d.n_segs <= 6, PSSR_EINVAL, "conv: n_srcs/n_segs out of range");
+  PSSR_REQUIRE(d.n_srcs >= 1 && d.n_srcs <= 4 && d.n_segs >= 1 && d.n_segs <= 6, PSSR_EINVAL, "conv: n_srcs/n_segs out of range");
   PSSR_REQUIRE(d.n_valid > 0 && d.n_valid <= d.n && d.n_valid % 8 == 0, PSSR_EUNSUP, "conv: n_valid=%d must be a multiple of 8 and <= n", d.n_valid);
   PSSR_REQUIRE(d.shuffle >= 1 && d.n_valid % (d.shuffle * d.shuffle) == 0, PSSR_EUNSUP, "conv: n_valid %% shuffle^2 != 0");
   const int cps = d.n_valid / (d.shuffle * d.shuffle);
@@ -1468,14 +1534,30 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
   p.q_end = d.B * p.NJ * p.IP - p.pad * (p.P + 1);
   p.total_vrows = d.B * p.NJ * d.Ho;
 
-  int num_kb = 0;
+  int num_kb = 0, num_kb8 = 0;
+  bool src_f8[4] = {false, false, false, false};
   p.n_segs = d.n_segs;
   for (int s = 0; s < d.n_segs; ++s) {
     const pssr_kseg_t& sg = d.segs[s];
     PSSR_REQUIRE(sg.src >= 0 && sg.src < d.n_srcs && sg.cblocks >= 1, PSSR_EINVAL, "conv: bad K segment");
-    p.seg_src[s] = sg.src; p.seg_taps[s] = sg.taps; p.seg_cblocks[s] = sg.cblocks; p.seg_kb0[s] = num_kb;
-    num_kb += sg.taps * sg.cblocks;
+    p.seg_src[s] = sg.src; p.seg_taps[s] = sg.taps; p.seg_cblocks[s] = sg.cblocks;
+    if (sg.fmt == PSSR_SEG_E5M2) {
+      // low-order correction terms as e5m2 x e5m2 (kind::f8f6f4): their own weight matrix and K-block numbering
+      PSSR_REQUIRE(p.rows_mode && sg.taps == 9 && d.weights8 != nullptr && ((uintptr_t)d.weights8 & 15) == 0, PSSR_EUNSUP,
+                   "conv: e5m2 segments need rows mode (width %% 128 == 0), 3x3 taps and weights8");
+      p.seg_f8[s] = 1;
+      src_f8[sg.src] = true;
+      p.seg_kb0[s] = num_kb8;
+      num_kb8 += sg.taps * sg.cblocks;
+    } else {
+      PSSR_REQUIRE(sg.fmt == PSSR_SEG_F16, PSSR_EINVAL, "conv: unknown segment format %d", sg.fmt);
+      p.seg_kb0[s] = num_kb;
+      num_kb += sg.taps * sg.cblocks;
+    }
   }
+  for (int s = 0; s < d.n_segs; ++s)
+    PSSR_REQUIRE((p.seg_f8[s] != 0) == src_f8[d.segs[s].src], PSSR_EINVAL, "conv: a source is read both as 16-bit and as e5m2");
+  PSSR_REQUIRE(num_kb >= 1, PSSR_EINVAL, "conv: no 16-bit K segment");
   p.num_kb = num_kb;
   // CTA pairs (cta_group::2): each CTA holds half of the weight rows, one MMA instruction drives both SMs
   const int sms = device_sm_count();
@@ -1506,9 +1588,10 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
   for (int s2 = 0; s2 < d.n_segs; ++s2) planes += d.segs[s2].cblocks;
   p.slot_bytes = (uint32_t)(p.P * 128);
   p.slot16_bytes = (uint32_t)(((p.P * 32 + 127) / 128) * 128);
+  p.slot8_bytes = (uint32_t)(((p.P * 64 + 127) / 128) * 128);
   // narrow planes (rows mode): a 1x1 segment over a 16-channel tensor (the im2col of a 1-channel input) is staged with 32-byte
   // pixels and multiplied with ONE K = 16 MMA instead of four (3 of the 40 K steps of Reconstruction.pre were zeros)
-  bool src_k16[3] = {false, false, false};
+  bool src_k16[4] = {false, false, false, false};
   p.group_bytes = 0;
   p.group_tx = 0;
   for (int s2 = 0; s2 < d.n_segs; ++s2) {
@@ -1521,7 +1604,7 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
     // and the 1x1 residual of a depth-0 block): only the first one is loaded
     int alias = -1;
     for (int e = 0; e < s2 && alias < 0; ++e)
-      if (p.seg_load[e] && d.segs[e].src == sg.src && d.segs[e].cblocks == sg.cblocks && p.seg_k16[e] == p.seg_k16[s2] &&
+      if (p.seg_load[e] && d.segs[e].src == sg.src && d.segs[e].cblocks == sg.cblocks && p.seg_k16[e] == p.seg_k16[s2] && p.seg_f8[e] == p.seg_f8[s2] &&
           getenv("PSSR_V3_NO_ALIAS") == nullptr)
         alias = e;
     if (alias >= 0) {
@@ -1531,8 +1614,8 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
     }
     p.seg_load[s2] = 1;
     p.seg_plane[s2] = p.group_bytes;
-    p.group_bytes += (uint32_t)sg.cblocks * (k16 ? p.slot16_bytes : p.slot_bytes);
-    p.group_tx += (uint32_t)sg.cblocks * (uint32_t)p.P * (k16 ? 32u : 128u);
+    p.group_bytes += (uint32_t)sg.cblocks * (k16 ? p.slot16_bytes : p.seg_f8[s2] ? p.slot8_bytes : p.slot_bytes);
+    p.group_tx += (uint32_t)sg.cblocks * (uint32_t)p.P * (k16 ? 32u : p.seg_f8[s2] ? 64u : 128u);
   }
   for (int s2 = 0; s2 < d.n_segs; ++s2)
     PSSR_REQUIRE(p.seg_k16[s2] || !src_k16[d.segs[s2].src], PSSR_EUNSUP, "conv: a 16-channel source must be read by 1x1 segments only");
@@ -1560,7 +1643,7 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
     a_min = ((a_min + 1023) / 1024) * 1024;
     const long long left = cap - a_min;
     int g_ = 0, res_ = 0, bst_ = 0;
-    if (p.n_tiles == 1 && (long long)num_kb * p.tap_bytes <= left && getenv("PSSR_V3_NORES") == nullptr && !tail) {
+    if (p.n_tiles == 1 && num_kb8 == 0 && (long long)num_kb * p.tap_bytes <= left && getenv("PSSR_V3_NORES") == nullptr && !tail) {
       res_ = 1; g_ = 9; bst_ = 1;
     } else if (!res_only) {
       // small N: a stage must hold many MMAs (a barrier poll costs ~100 unhidden cycles); N = 256: finer stages, deeper prefetch
@@ -1645,7 +1728,16 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
     PSSR_REQUIRE(src.cstride % 8 == 0 && src.channels >= 1 && src.channels <= src.cstride, PSSR_EUNSUP, "conv: source %d bad channel stride", s);
     PSSR_REQUIRE(src.H == d.Ho && src.W == d.Wo && src.B == d.B, PSSR_EINVAL, "conv: source %d geometry does not match the output", s);
     CUresult r;
-    if (p.cols_mode) {
+    if (src_f8[s]) {
+      // e5m2 source (rows mode only): one byte per element, 64-byte pixels
+      PSSR_REQUIRE(src.cstride % 16 == 0, PSSR_EUNSUP, "conv: e5m2 source %d needs a channel stride that is a multiple of 16", s);
+      cuuint64_t gdim[4] = {(cuuint64_t)src.channels, (cuuint64_t)src.W, (cuuint64_t)src.H, (cuuint64_t)src.B};
+      cuuint64_t gstr[3] = {(cuuint64_t)src.cstride, (cuuint64_t)src.cstride * src.W, (cuuint64_t)src.cstride * src.W * src.H};
+      cuuint32_t box[4] = {64u, (cuuint32_t)p.P, 1, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      r = enc(&op.tmaps[s], CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(src.base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else if (p.cols_mode) {
       // dims (channel, x, image, y): the box lands as [y][image][x][channel], rows of the cG images interleaved
       cuuint64_t gdim[4] = {(cuuint64_t)src.channels, (cuuint64_t)src.W, (cuuint64_t)src.B, (cuuint64_t)src.H};
       cuuint64_t gstr[3] = {(cuuint64_t)src.cstride * 2, (cuuint64_t)src.cstride * 2 * src.W * src.H, (cuuint64_t)src.cstride * 2 * src.W};
@@ -1678,9 +1770,19 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
     cuuint64_t gstr[1] = {ktot * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)(block_n / C)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&op.tmaps[3], tdt, 2, const_cast<void*>(d.weights), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(&op.tmaps[kTmW], tdt, 2, const_cast<void*>(d.weights), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PSSR_REQUIRE(r == CUDA_SUCCESS, PSSR_ECUDA, "cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
+  }
+  if (num_kb8 > 0) {
+    const cuuint64_t ktot = (cuuint64_t)num_kb8 * 64;
+    cuuint64_t gdim[2] = {ktot, (cuuint64_t)d.n};
+    cuuint64_t gstr[1] = {ktot};
+    cuuint32_t box[2] = {64, (cuuint32_t)(block_n / C)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&op.tmaps[kTmW8], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(d.weights8), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PSSR_REQUIRE(r == CUDA_SUCCESS, PSSR_ECUDA, "cuTensorMapEncodeTiled(weights8) failed with %d", (int)r);
   }
   op.smem_bytes = (int)(a_total + b_total_ll + 1024 + vec_bytes + tailw_bytes + stage_bytes);
   p.stage_off = (uint32_t)(a_total + b_total_ll + tailw_bytes + vec_bytes);
@@ -1693,14 +1795,14 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
       cuuint64_t gstr[3] = {(cuuint64_t)d.out_cstride * 2, (cuuint64_t)d.out_cstride * 2 * d.Wo, (cuuint64_t)d.out_cstride * 2 * d.Wo * d.Ho};
       cuuint32_t box[4] = {64, 32, 1, 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
-      r = enc(&op.tmaps[4], tdt, 4, obase, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+      r = enc(&op.tmaps[kTmOut], tdt, 4, obase, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
       cuuint64_t gdim[2] = {(cuuint64_t)d.n_valid, (cuuint64_t)d.Wo * d.Ho * d.B};
       cuuint64_t gstr[1] = {(cuuint64_t)d.out_cstride * 2};
       cuuint32_t box[2] = {64, 32};
       cuuint32_t estr[2] = {1, 1};
-      r = enc(&op.tmaps[4], tdt, 2, obase, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+      r = enc(&op.tmaps[kTmOut], tdt, 2, obase, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     PSSR_REQUIRE(r == CUDA_SUCCESS, PSSR_ECUDA, "cuTensorMapEncodeTiled(output) failed with %d", (int)r);

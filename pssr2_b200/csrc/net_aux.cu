@@ -6,6 +6,7 @@
 //           clip -> uint8 truncation -> centre channel of `_pred_array`
 //           pssr/models/_blocks.py:17, resunet.py:95, pssr/predict.py:245-246
 #include <stdlib.h>
+#include <cuda_fp8.h>
 #include "common.cuh"
 #include "plan.h"
 
@@ -155,6 +156,46 @@ int prep_launch(const pssr_prep_desc_t& d, int dtype, cudaStream_t stream) {
   const long long cap = (long long)device_sm_count() * 32;
   if (blocks > cap) blocks = cap;
   PSSR_CHECK_CUDA(launch_pdl(prep_im2col_kernel, dim3((unsigned)blocks), dim3(threads), 0, stream, d, (int)(dtype == PSSR_DT_FP16)));
+  count_launch();
+  return PSSR_OK;
+}
+
+// ------------------------------------------------------------------------------ cast8
+// 16-bit NHWC view * scale -> e5m2 NHWC: the operand of the e5m2 correction segments of the compensated precision
+// (include/pssr_b200.h PSSR_SEG_E5M2).  One thread per 16 channels: 32 bytes in, 16 bytes out.
+__global__ void cast8_kernel(pssr_cast8_desc_t d, int fp16) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int groups = d.C / 16;
+  const long long total = (long long)d.B * d.H * d.W * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const long long pix = i / groups;
+    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(d.in) + (size_t)pix * d.in_cstride + d.in_choff + g * 16);
+    const uint4 a = src[0], b = src[1];
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float f0 = unpack1((uint16_t)(w[2 * j] & 0xffffu), fp16) * d.scale, f1 = unpack1((uint16_t)(w[2 * j] >> 16), fp16) * d.scale;
+      const float f2 = unpack1((uint16_t)(w[2 * j + 1] & 0xffffu), fp16) * d.scale, f3 = unpack1((uint16_t)(w[2 * j + 1] >> 16), fp16) * d.scale;
+      const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(f0, f1), __NV_SATFINITE, __NV_E5M2);
+      const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(f2, f3), __NV_SATFINITE, __NV_E5M2);
+      o[j] = lo | (hi << 16);
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(d.out) + (size_t)pix * d.out_cstride + d.out_choff + g * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+int cast8_launch(const pssr_cast8_desc_t& d, int dtype, cudaStream_t stream) {
+  PSSR_REQUIRE(d.in && d.out, PSSR_EINVAL, "cast8: null pointer");
+  PSSR_REQUIRE(d.C >= 16 && d.C % 16 == 0 && d.in_cstride % 8 == 0 && d.in_choff % 8 == 0 && d.out_cstride % 16 == 0 && d.out_choff % 16 == 0 &&
+               ((uintptr_t)d.in & 15) == 0 && ((uintptr_t)d.out & 15) == 0, PSSR_EUNSUP, "cast8: channels must come in aligned groups of 16");
+  const long long total = (long long)d.B * d.H * d.W * (d.C / 16);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)device_sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  PSSR_CHECK_CUDA(launch_pdl(cast8_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, d, (int)(dtype == PSSR_DT_FP16)));
   count_launch();
   return PSSR_OK;
 }

@@ -7,10 +7,12 @@
 
 namespace pssr {
 
-static constexpr int kTmapsPerConv = 5;
+// tensor-map table of one convolution: sources, 16-bit weights, 16-bit output, e5m2 weights, spare
+static constexpr int kTmapsPerConv = 8;
+static constexpr int kTmW = 4, kTmOut = 5, kTmW8 = 6;
 
 struct ConvOp {
-  CUtensorMap tmaps[5];           // host copies ([0..2] sources, [3] weights, [4] output); uploaded into the plan's device table
+  CUtensorMap tmaps[kTmapsPerConv];   // host copies ([0..3] sources, [kTmW] weights, [kTmOut] output, [kTmW8] e5m2 weights); uploaded into the plan's device table
   alignas(16) uint8_t kparams[512];
   int grid = 0;
   int smem_bytes = 0;
@@ -34,6 +36,7 @@ int stem_launch(const pssr_stem_desc_t& d, int dtype, cudaStream_t stream);
 int ln_launch(const pssr_ln_desc_t& d, int dtype, cudaStream_t stream);
 int dwln_launch(const pssr_dwln_desc_t& d, int dtype, cudaStream_t stream);
 int ese_launch(const pssr_ese_desc_t& d, int dtype, cudaStream_t stream);
+int cast8_launch(const pssr_cast8_desc_t& d, int dtype, cudaStream_t stream);
 
 }  // namespace pssr
 

@@ -11,13 +11,14 @@ import math
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, DT_BF16, DT_FP16, OP_CONV, OP_DWCONV_LN, OP_ESE, OP_LAYERNORM, OP_MAXPOOL, OP_PREP,
-                   OP_STEM, OP_TAIL, OP_TAILSUM, ConvDesc, DwLnDesc, EseDesc, KSeg, LnDesc, Op, PoolDesc, PrepDesc, Src, StemDesc,
-                   TailDesc, TailSumDesc)
+from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, DT_BF16, DT_FP16, OP_CAST8, OP_CONV, OP_DWCONV_LN, OP_ESE, OP_LAYERNORM, OP_MAXPOOL,
+                   OP_PREP, OP_STEM, OP_TAIL, OP_TAILSUM, SEG_E5M2, SEG_F16, Cast8Desc, ConvDesc, DwLnDesc, EseDesc, KSeg, LnDesc, Op,
+                   PoolDesc, PrepDesc, Src, StemDesc, TailDesc, TailSumDesc)
 
 TORCH_DT = {DT_BF16: torch.bfloat16, DT_FP16: torch.float16}
 DT_NAMES = {"bf16": DT_BF16, "fp16": DT_FP16, "fp16c": DT_FP16}
 TAIL_COMP = 1   # include/pssr_b200.h PSSR_TAIL_COMP
+__all_seg__ = (SEG_F16, SEG_E5M2)
 
 
 DRY_RUN = False
@@ -84,6 +85,19 @@ def pack_weight(parts, dtype, shuffle=1, n_pad=None):
     return W.to(TORCH_DT[dtype]).contiguous()
 
 
+def pack_weight8(parts, scale, shuffle=1):
+    """e5m2 twin of ``pack_weight`` for the PSSR_SEG_E5M2 segments: [n, K8tot] uint8 holding e5m2(w * scale), same K / N order."""
+    cols = []
+    for w in parts:
+        co, ci, kh, kw = w.shape
+        cb = ceil_div(ci, 64)
+        wp = torch.zeros(co, kh * kw, cb * 64, dtype=torch.float32, device=w.device)
+        wp[:, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, kh * kw, ci)
+        cols.append(wp.reshape(co, -1))
+    W = permute_n(torch.cat(cols, 1) * scale, shuffle)
+    return W.clamp(-57344.0, 57344.0).to(torch.float8_e5m2).view(torch.uint8).contiguous()
+
+
 def permute_n(t, shuffle):
     """Reorders dim 0 (output channels) for the pixel-shuffle epilogue."""
     if shuffle == 1:
@@ -109,20 +123,30 @@ class Plan:
 
     # ---- op builders -----------------------------------------------------------------
     def conv(self, srcs, segs, weight, bias, out: View, *, Ho, Wo, B, n=None, n_valid=None, shuffle=1, act=ACT_NONE,
-             out_scale=None, out_f32=None, tail_weight=None, tail_z=None, tail_layout=0, out_lo: View = None, tail_flags=0):
-        """srcs: list[View]; segs: list[(src_index, taps, cblocks)]; weight [n, Ktot] 16-bit; bias [n] fp32."""
+             out_scale=None, out_f32=None, tail_weight=None, tail_z=None, tail_layout=0, out_lo: View = None, tail_flags=0, weight8=None):
+        """srcs: list[View]; segs: list[(src_index, taps, cblocks[, fmt])]; weight [n, Ktot] 16-bit; bias [n] fp32;
+        weight8 [n, K8tot] uint8 (e5m2) for the segments with fmt == SEG_E5M2, whose sources are uint8 (e5m2) NHWC views."""
         d = ConvDesc()
         d.n_srcs = len(srcs)
         for i, s in enumerate(srcs):
             d.srcs[i] = Src(s.ptr(), s.channels, s.cstride, s.H, s.W, s.B, 0)
-        assert len(srcs) <= 3 and len(segs) <= 6
+        assert len(srcs) <= 4 and len(segs) <= 6
         d.n_segs = len(segs)
-        ktot = 0
-        for i, (si, taps, cb) in enumerate(segs):
-            d.segs[i] = KSeg(si, taps, cb, 0)
-            ktot += taps * cb * 64
+        segs = [tuple(sg) + (SEG_F16,) * (4 - len(sg)) for sg in segs]
+        ktot = k8tot = 0
+        for i, (si, taps, cb, fmt) in enumerate(segs):
+            d.segs[i] = KSeg(si, taps, cb, fmt)
+            assert (srcs[si].buf.dtype == torch.uint8) == (fmt == SEG_E5M2)
+            if fmt == SEG_E5M2:
+                k8tot += taps * cb * 64
+            else:
+                ktot += taps * cb * 64
         n = weight.shape[0] if n is None else n
         assert weight.shape == (n, ktot) and weight.dtype == self.tdtype and weight.is_contiguous()
+        assert (weight8 is None) == (k8tot == 0)
+        if weight8 is not None:
+            assert weight8.shape == (n, k8tot) and weight8.dtype == torch.uint8 and weight8.is_contiguous()
+            d.weights8 = weight8.data_ptr()
         assert bias.shape == (n,) and bias.dtype == torch.float32
         d.weights = weight.data_ptr()
         d.bias = bias.data_ptr()
@@ -151,10 +175,11 @@ class Plan:
         self.ops.append(op)
         self.keep += [weight, bias, out_scale, out_f32, tail_weight, tail_z] + [s.buf for s in srcs] + ([out.buf] if out is not None else [])
         self.keep += [out_lo.buf] if out_lo is not None else []
+        self.keep += [weight8]
         self.records.append(("conv", dict(srcs=list(srcs), segs=list(segs), weight=weight, bias=bias, out=out, Ho=Ho, Wo=Wo, B=B,
                                           n=n, n_valid=d.n_valid, shuffle=shuffle, act=act, out_scale=out_scale, out_f32=out_f32,
                                           issued_flops=2 * B * Ho * Wo * n * ktot, tail_weight=tail_weight, tail_z=tail_z,
-                                          tail_layout=tail_layout, out_lo=out_lo, tail_flags=tail_flags)))
+                                          tail_layout=tail_layout, out_lo=out_lo, tail_flags=tail_flags, weight8=weight8)))
 
     def prep(self, x, scale, shift, im2col, xnorm=None, centre_only=False, im2col_lo=None):
         """centre_only: im2col is the normalised input itself, NHWC [B, H, W, cols] (inputs with more than 7 channels).
@@ -175,6 +200,18 @@ class Plan:
         self.keep += [x, scale, shift, im2col, xnorm, im2col_lo]
         self.records.append(("prep", dict(x=x, scale=scale, shift=shift, im2col=im2col, xnorm=xnorm, centre_only=centre_only,
                                           im2col_lo=im2col_lo)))
+
+    def cast8(self, src: View, dst: View, scale):
+        """dst (uint8 NHWC, e5m2 bit patterns) = e5m2(src * scale): the operand of SEG_E5M2 segments."""
+        assert dst.buf.dtype == torch.uint8 and src.channels == dst.channels and src.channels % 16 == 0
+        d = Cast8Desc(src.buf.data_ptr(), src.cstride, src.choff, src.channels, src.B, src.H, src.W, float(scale), dst.buf.data_ptr(),
+                      dst.cstride, dst.choff)
+        op = Op()
+        op.kind = OP_CAST8
+        op.u.cast8 = d
+        self.ops.append(op)
+        self.keep += [src.buf, dst.buf]
+        self.records.append(("cast8", dict(src=src, dst=dst, scale=float(scale))))
 
     def maxpool(self, src: View, dst: View):
         d = PoolDesc(src.buf.data_ptr(), src.cstride, src.choff, dst.buf.data_ptr(), dst.cstride, dst.choff, src.B, src.H,

@@ -29,6 +29,10 @@ def run_records(plan):
             if lo is not None:          # compensated precision: what the 16-bit rounding dropped
                 lo.zero_()
                 lo[..., :nc] = (cols - r["im2col"][..., :nc].float()).to(lo.dtype)
+        elif kind == "cast8":
+            s, d = r["src"], r["dst"]
+            y = s.buf[..., s.choff:s.choff + s.channels].float() * r["scale"]
+            d.buf[..., d.choff:d.choff + s.channels] = y.clamp(-57344.0, 57344.0).to(torch.float8_e5m2).view(torch.uint8)
         elif kind == "maxpool":
             s, d = r["src"], r["dst"]
             d.buf[..., d.choff:d.choff + s.channels] = F.max_pool2d(_view_nchw(s), 2).permute(0, 2, 3, 1).to(d.buf.dtype)
@@ -43,15 +47,23 @@ def run_records(plan):
                 r["out_u8"].copy_(y[:, c:c + 1].clamp(0, 255).to(torch.uint8))
         elif kind == "conv":
             W = r["weight"].float()
+            W8 = r["weight8"].view(torch.float8_e5m2).float() if r.get("weight8") is not None else None
             n = W.shape[0]
             acc = None
-            k0 = 0
-            for (si, taps, cb) in r["segs"]:
+            k0 = k8 = 0
+            for sg in r["segs"]:
+                si, taps, cb = sg[:3]
                 v = r["srcs"][si]
                 kw = taps * cb * 64
-                wseg = W[:, k0:k0 + kw].reshape(n, taps, cb * 64)
-                k0 += kw
-                x = _view_nchw(v, cb * 64)
+                if len(sg) > 3 and sg[3] == 1:     # e5m2 source x e5m2 weights (fp32 accumulate)
+                    wseg = W8[:, k8:k8 + kw].reshape(n, taps, cb * 64)
+                    k8 += kw
+                    x = v.buf[..., v.choff:v.choff + v.channels].view(torch.float8_e5m2).float().permute(0, 3, 1, 2)
+                    x = F.pad(x, (0, 0, 0, 0, 0, cb * 64 - v.channels))
+                else:
+                    wseg = W[:, k0:k0 + kw].reshape(n, taps, cb * 64)
+                    k0 += kw
+                    x = _view_nchw(v, cb * 64)
                 if taps == 9:
                     y = F.conv2d(x, wseg.permute(0, 2, 1).reshape(n, cb * 64, 3, 3), padding=1)
                 elif taps == 1:
