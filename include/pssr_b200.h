@@ -227,6 +227,14 @@ typedef struct {
   int32_t out_lo_cstride;
   int32_t out_lo_choff;
   const void* weights8;  /* [n][k8_total] e5m2, K-major, K ordered like `weights` over the PSSR_SEG_E5M2 segments only */
+  /* optional residual added in the epilogue before the activation: y = act(acc + bias + resid_scale * resid[pixel][n])
+   * (16-bit NHWC on the output pixel grid, shuffle == 1).  The compensated ResBlock tail adds the low-order terms of its
+   * 1x1 residual this way: a separate small GEMM computes them scaled by 2^10, so the main launch keeps its three source planes. */
+  const void* resid;
+  int32_t resid_cstride;
+  int32_t resid_choff;
+  float resid_scale;
+  int32_t reserved3;
 } pssr_conv_desc_t;
 #define PSSR_TAIL_TAPS 0
 #define PSSR_TAIL_WINDOW48 1

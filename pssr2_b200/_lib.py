@@ -92,7 +92,8 @@ class ConvDesc(Structure):
                 ("out_cstride", c_int32), ("out_choff", c_int32), ("shuffle", c_int32), ("act", c_int32),
                 ("out_scale", c_void_p), ("out_f32", c_void_p), ("tail_weight", c_void_p), ("tail_z", c_void_p),
                 ("tail_layout", c_int32), ("tail_flags", c_int32), ("out_lo", c_void_p),
-                ("out_lo_cstride", c_int32), ("out_lo_choff", c_int32), ("weights8", c_void_p)]
+                ("out_lo_cstride", c_int32), ("out_lo_choff", c_int32), ("weights8", c_void_p),
+                ("resid", c_void_p), ("resid_cstride", c_int32), ("resid_choff", c_int32), ("resid_scale", c_float), ("reserved3", c_int32)]
 
 
 class Cast8Desc(Structure):

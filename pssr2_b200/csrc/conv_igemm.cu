@@ -306,6 +306,7 @@ int conv_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
                "conv: output channel stride/offset must be multiples of 8");
   PSSR_REQUIRE(d.tail_z == nullptr, PSSR_EUNSUP, "conv: the fused Reconstruction tail needs the v3 kernel (64 channels per sub-position, N %% 256 == 0)");
   PSSR_REQUIRE(d.out != nullptr || d.out_f32 != nullptr, PSSR_EINVAL, "conv: no output buffer");
+  PSSR_REQUIRE(d.resid == nullptr, PSSR_EUNSUP, "conv: the epilogue residual needs the v3 kernel");
 
   ConvKParams& p = *reinterpret_cast<ConvKParams*>(op.kparams);
   static_assert(sizeof(ConvKParams) <= sizeof(op.kparams), "ConvOp::kparams too small");

@@ -86,6 +86,9 @@ struct V3Params {
   int lo_cstride, lo_choff;
   int tail_comp;              // tail: B = [W_hi ; W_lo] (N = 32) against the 16-bit activation in TMEM, plus an e5m2 pass
                               // (kind::f8f6f4, A = 64 * (y - rn16(y)) staged in shared memory, B = W / 64) into the same accumulator
+  const uint16_t* resid;      // epilogue residual: y = act(acc + bias + resid_scale * resid[pixel][n]) (shuffle == 1)
+  int resid_cstride, resid_choff;
+  float resid_scale;
   uint32_t tailw_bytes;       // bytes of the tail operand region: 16-bit weight tile [+ e5m2 weight tile + 4 x 8 KB e5m2 A tiles]
 };
 
@@ -571,12 +574,14 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
             const uint32_t tapb = f8 ? (p.tap_bytes >> 1) : p.tap_bytes;
             if (rm && taps != 9 && g != 1) continue;
             const int t_lo = (rm && taps == 9) ? 3 * g : 0, t_hi = (rm && taps == 9) ? 3 * g + 3 : taps;
+            const int gsf = f8 ? 2 * gs : gs;       // e5m2 taps are half as large: two per 16-bit tap slot of a stage
             for (int cb = 0; cb < cbs; ++cb) {
-              for (int t0 = t_lo; t0 < t_hi; t0 += gs) {
+              for (int t0 = t_lo; t0 < t_hi; t0 += gsf) {
+                const int cnt = t_hi - t0 < gsf ? t_hi - t0 : gsf;
                 mbar_wait(b_empty(bs), bphase ^ 1u);
                 const uint32_t fbar = PAIR ? v3_mapa(b_full(bs), 0) : b_full(bs);
-                if (rank == 0) mbar_arrive_expect_tx(b_full(bs), (uint32_t)gs * tapb * C);
-                for (int t = 0; t < gs; ++t) {
+                if (rank == 0) mbar_arrive_expect_tx(b_full(bs), (uint32_t)cnt * tapb * C);
+                for (int t = 0; t < cnt; ++t) {
                   const int kb = p.seg_kb0[sg] + (t0 + t) * cbs + cb;   // weights are packed tap-major, then channel block
                   const uint32_t dst = b_base + (uint32_t)bs * p.b_bytes + (uint32_t)t * tapb;
                   if (PAIR) v3_tma_2d_pair(dst, tmB, fbar, kb * 64, n_tile * block_n + nrow0);
@@ -684,16 +689,17 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
           }
           if (acc == 0 && it < 31) V3_TRACE(128 + 2 * it);
           if (ROWS && f8) {
-            // e5m2 3x3 segment (streamed weights): two K = 32 MMAs per tap and 64-channel block
+            // e5m2 3x3 segment (streamed weights): two K = 32 MMAs per tap and 64-channel block, 2G taps per weight stage
 #pragma unroll
-            for (int t0 = 0; t0 < 9; t0 += G) {
+            for (int t0 = 0; t0 < 9; t0 += 2 * G) {
               mbar_wait(b_full(bs), bphase);
               tc_fence_after();
               const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)bs * bstep) + f8_fix;
               if (elect_one()) {
 #pragma unroll
-                for (int tt = 0; tt < G; ++tt) {
+                for (int tt = 0; tt < 2 * G; ++tt) {
                   const int t = t0 + tt;
+                  if (t >= 9) break;
                   const int dy = t / 3 - 1, dx = t % 3 - 1;
                   const uint64_t bdt = bd + (uint64_t)tt * (uint64_t)(tapstep >> 1);
 #pragma unroll
@@ -830,13 +836,14 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
             if (f8) {
               constexpr int GS = G == 9 ? 3 : G;
 #pragma unroll
-              for (int x0 = 0; x0 < 3; x0 += GS) {
+              for (int x0 = 0; x0 < 3; x0 += 2 * GS) {
                 mbar_wait(b_full(bs), bphase);
                 tc_fence_after();
                 const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)bs * bstep) + f8_fix;
                 if (elect_one()) {
 #pragma unroll
-                  for (int tt = 0; tt < GS; ++tt) {
+                  for (int tt = 0; tt < 2 * GS; ++tt) {
+                    if (x0 + tt >= 3) break;
                     const int dx = x0 + tt - 1;
                     const uint64_t bdt = bd + (uint64_t)tt * (uint64_t)(tapstep >> 1);
 #pragma unroll
@@ -1237,6 +1244,20 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
                 f[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + bb.z;
                 f[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + bb.w;
               }
+              if (p.resid != nullptr && valid) {
+                const uint4* rp = reinterpret_cast<const uint4*>(p.resid + (((size_t)n * p.H + y) * p.W + x) * p.resid_cstride + p.resid_choff + nb + cq * 32);
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) {
+                  const uint4 rv = rp[j8];
+                  const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const float2 r2 = v3_unpack2(rw[k], p.fp16);
+                    f[8 * j8 + 2 * k] = fmaf(p.resid_scale, r2.x, f[8 * j8 + 2 * k]);
+                    f[8 * j8 + 2 * k + 1] = fmaf(p.resid_scale, r2.y, f[8 * j8 + 2 * k + 1]);
+                  }
+                }
+              }
               if (p.act == PSSR_ACT_GELU) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = v3_gelu(f[j]);
@@ -1311,6 +1332,20 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
                   f[4 * j4 + 1] = __uint_as_float(v[h * 16 + 4 * j4 + 1]) + bb.y;
                   f[4 * j4 + 2] = __uint_as_float(v[h * 16 + 4 * j4 + 2]) + bb.z;
                   f[4 * j4 + 3] = __uint_as_float(v[h * 16 + 4 * j4 + 3]) + bb.w;
+                }
+                if (p.resid != nullptr) {
+                  const uint4* rp = reinterpret_cast<const uint4*>(p.resid + (((size_t)n * p.H + y) * p.W + x) * p.resid_cstride + p.resid_choff + nn);
+#pragma unroll
+                  for (int j8 = 0; j8 < 2; ++j8) {
+                    const uint4 rv = rp[j8];
+                    const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                      const float2 r2 = v3_unpack2(rw[k], p.fp16);
+                      f[8 * j8 + 2 * k] = fmaf(p.resid_scale, r2.x, f[8 * j8 + 2 * k]);
+                      f[8 * j8 + 2 * k + 1] = fmaf(p.resid_scale, r2.y, f[8 * j8 + 2 * k + 1]);
+                    }
+                  }
                 }
                 if (p.act == PSSR_ACT_GELU) {
 #pragma unroll
@@ -1817,6 +1852,13 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
   p.tail_win48 = (tail && d.tail_layout == PSSR_TAIL_WINDOW48) ? 1 : 0;
   p.tail_comp = tail_comp ? 1 : 0;
   p.tailw_bytes = (uint32_t)tailw_bytes;
+  PSSR_REQUIRE(d.resid == nullptr || (!tail && d.shuffle == 1 && d.n == d.n_valid && d.n_valid % 16 == 0 && d.resid_cstride % 8 == 0 &&
+                                      d.resid_choff % 8 == 0 && ((uintptr_t)d.resid & 15) == 0),
+               PSSR_EUNSUP, "conv: the epilogue residual needs shuffle == 1, unpadded N and 16-byte aligned channel slices");
+  p.resid = reinterpret_cast<const uint16_t*>(d.resid);
+  p.resid_cstride = d.resid_cstride;
+  p.resid_choff = d.resid_choff;
+  p.resid_scale = d.resid_scale;
   p.out_lo = reinterpret_cast<uint16_t*>(d.out_lo);
   p.lo_cstride = d.out_lo_cstride;
   p.lo_choff = d.out_lo_choff;

@@ -13,7 +13,7 @@ static constexpr int kTmW = 4, kTmOut = 5, kTmW8 = 6;
 
 struct ConvOp {
   CUtensorMap tmaps[kTmapsPerConv];   // host copies ([0..3] sources, [kTmW] weights, [kTmOut] output, [kTmW8] e5m2 weights); uploaded into the plan's device table
-  alignas(16) uint8_t kparams[512];
+  alignas(16) uint8_t kparams[640];
   int grid = 0;
   int smem_bytes = 0;
   int variant = 1;                // 1 = conv_igemm.cu (box per tap), 3 = conv_v3.cu (lean issue)

@@ -156,15 +156,19 @@ class _PlanModule(nn.Module):
         bp = rec.pre.bias.detach().float()
         wide = bool(getattr(xcol, "wide_input", False))          # > 7 input channels: xcol is the normalised input, a 3x3 segment
         wm, wx = wp[:, :hid0], (wp[:, hid0:] if wide else _im2col_parts(wp[:, hid0:]))
-        comp = plan.comp and xcol_lo is not None
+        comp = plan.comp
         tx = 9 if wide else 1
         cbm = ceil_div(hid0, 64)
         w8 = None
         if comp:
             # (final_hi, x_hi, x_lo) x (W_hi, W_lo): final * W_hi + x_hi * Wx_hi + x_lo * Wx_hi + x_hi * Wx_lo + final * W_lo
             wlo = split_lo(wm, plan.dtype)
-            parts = [wm, wx, wx, split_lo(wx, plan.dtype)]
-            srcs, segs = [View(final), xcol, xcol_lo], [(0, 9, cbm), (1, tx, 1), (2, tx, 1), (1, tx, 1)]
+            if xcol_lo is not None:
+                parts = [wm, wx, wx, split_lo(wx, plan.dtype)]
+                srcs, segs = [View(final), xcol, xcol_lo], [(0, 9, cbm), (1, tx, 1), (2, tx, 1), (1, tx, 1)]
+            else:
+                parts = [wm, wx]
+                srcs, segs = [View(final), xcol], [(0, 9, cbm), (1, tx, 1)]
             mx = float(wlo.abs().max())
             if W % 128 == 0 and hid0 % 16 == 0 and mx > 0 and not os.environ.get("PSSR_NO_F8"):
                 # the last term only has to be known to a few bits: e5m2 x e5m2 at twice the 16-bit MMA rate (rows-mode layers).
@@ -175,7 +179,7 @@ class _PlanModule(nn.Module):
                 plan.cast8(View(final), View(final8), 2.0 ** -e)
                 w8 = pack_weight8([wlo], 2.0 ** e, s)
                 srcs.append(View(final8))
-                segs.append((3, 9, cbm, SEG_E5M2))
+                segs.append((len(srcs) - 1, 9, cbm, SEG_E5M2))
             else:
                 parts.append(wlo)
                 segs.append((0, 9, cbm))
@@ -213,13 +217,15 @@ class _PlanModule(nn.Module):
         self._out, self._out_u8 = out, out_u8
 
     @staticmethod
-    def _emit_resblock(plan, blk, srcs, seg_spec, w0_parts_fn, wr_parts_fn, scratch, dst, shuffle, B, H, W, res_srcs=None, out_lo=None):
+    def _emit_resblock(plan, blk, srcs, seg_spec, w0_parts_fn, wr_parts_fn, scratch, dst, shuffle, B, H, W, res_srcs=None, out_lo=None,
+                       resid=None, resid_scale=1.0):
         """Emits the convs of one ResBlock.
         srcs / seg_spec: views and (src, taps, cblocks) segments feeding conv0 (3x3) -- and, with taps
         forced to the 1x1 variant by ``wr_parts_fn``, the respass.  ``w0_parts_fn(w)`` / ``wr_parts_fn(w)``
         split a conv0 / respass weight into per-segment [Cout, Cin_seg, kh, kw] parts.
         res_srcs: views the respass segments index (default: ``srcs``); out_lo: second output of the block's last
-        convolution (what the 16-bit rounding of its result dropped), both for the compensated precision."""
+        convolution (what the 16-bit rounding of its result dropped); resid: view added (times resid_scale) in the last
+        convolution's epilogue before the ReLU -- all three for the compensated precision."""
         convs, (wr, br) = blk.folded()
         cout = blk.out_channels
         dev = wr.device
@@ -249,7 +255,7 @@ class _PlanModule(nn.Module):
             in_srcs, in_segs = _dedupe_sources(in_srcs, in_segs)     # conv0 == last conv when depth == 0
             out_view = dst if last else View(scratch[i % 2])
             plan.conv(in_srcs, in_segs, wp, bp, out_view, Ho=H, Wo=W, B=B, shuffle=shuffle if last else 1, act=ACT_RELU,
-                      out_lo=out_lo if last else None)
+                      out_lo=out_lo if last else None, resid=resid if last else None, resid_scale=resid_scale)
             for p in alg:
                 plan.flops += 2 * p.numel() * B * H * W
             cur = out_view
@@ -413,6 +419,7 @@ class ResUNet(_PlanModule):
                 self._emit_resblock(plan, blk, srcs, segs, w0f, wrf, scratch(l), dst, 2, B, h, w)
         # decoder (resunet.py:81-85): block j works at level l = L-2-j on cat[l]
         final = z(nb, H, W, hid[0])           # one chunk of the last decoder output; every chunk reuses it (stays in L2)
+        corr = z(nb, H, W, hid[0]) if comp else None
         cout_final = self.reconstruction.conv.weight.shape[0]
         out = torch.empty(B, cout_final, H * s, W * s, dtype=torch.float32, device=dev)
         out_u8 = torch.empty(B, 1, H * s, W * s, dtype=torch.uint8, device=dev)
@@ -432,19 +439,23 @@ class ResUNet(_PlanModule):
                     fin = final[:b1 - b0]
                     catv = View(cat[l][b0:b1], 0, cin)
                     if comp:
-                        # respass over (up | skip_hi) with W_hi and W_lo, plus skip_lo with W_hi
-                        cbr = ceil_div(cin, 64)
-                        wrc = (lambda u_, cbr_: (lambda wt: ([wt, split_lo(wt, plan.dtype), wt[:, u_:].contiguous()],
-                                                             [(0, 1, cbr_), (0, 1, cbr_), (1, 1, ceil_div(hid[0], 64))])))(up[l], cbr)
-                        self._emit_resblock(plan, blk, [catv], segs, w0f, wrc, [sv[:b1 - b0] for sv in scratch(l)], View(fin), 1, b1 - b0, h, w,
-                                            res_srcs=[catv, View(skip_lo[b0:b1])])
+                        # low-order terms of the respass, (up | skip_hi) x W_lo + skip_lo x W_hi, as their own small GEMM scaled by
+                        # 2^10 (fp16 normal range); the block's last convolution adds them in its epilogue and keeps its three
+                        # source planes (a fourth one would halve the row ring of the 128-pixel-wide layers)
+                        wr_ = blk.respass.weight.detach().float()
+                        wpc = pack_weight([split_lo(wr_, plan.dtype) * 1024.0, wr_[:, up[l]:].contiguous() * 1024.0], plan.dtype)
+                        cv = View(corr[:b1 - b0])
+                        plan.conv([catv, View(skip_lo[b0:b1])], [(0, 1, ceil_div(cin, 64)), (1, 1, ceil_div(hid[0], 64))], wpc,
+                                  torch.zeros(hid[0], device=dev), cv, Ho=h, Wo=w, B=b1 - b0)
+                        self._emit_resblock(plan, blk, [catv], segs, w0f, wrf, [sv[:b1 - b0] for sv in scratch(l)], View(fin), 1, b1 - b0, h, w,
+                                            resid=cv, resid_scale=2.0 ** -10)
                     else:
                         self._emit_resblock(plan, blk, [catv], segs, w0f, wrf, [sv[:b1 - b0] for sv in scratch(l)], View(fin), 1, b1 - b0, h, w)
                     xc = View(im2col[b0:b1], 0, C) if wide_in else View(im2col[b0:b1])
                     xc.wide_input = wide_in
                     xcl = None
-                    if comp:
-                        xcl = View(im2col_lo[b0:b1], 0, C) if wide_in else View(im2col_lo[b0:b1])
+                    if comp and not wide_in:     # (a wide input's two extra full-width planes do not fit next to the fused tail's operands)
+                        xcl = View(im2col_lo[b0:b1])
                     self._emit_reconstruction(plan, fin, xc, b1 - b0, H, W, dev, out[b0:b1], out_u8[b0:b1], zshared[0], xcol_lo=xcl)
                     zshared[0] = self._zbuf
 
@@ -622,7 +633,7 @@ class RDResUNet(_PlanModule):
         plan.prep(x_in, sc, sh, im2col, centre_only=wide_in, im2col_lo=im2col_lo)
         xcol = View(im2col, 0, C) if wide_in else View(im2col)
         xcol.wide_input = wide_in
-        xcol_lo = (View(im2col_lo, 0, C) if wide_in else View(im2col_lo)) if comp else None
+        xcol_lo = View(im2col_lo) if comp and not wide_in else None
 
         # ---- encoder geometry: which stage outputs are decoder skips, and where they live -----------------
         n_st = len(enc.dense_stages)

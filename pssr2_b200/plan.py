@@ -123,7 +123,8 @@ class Plan:
 
     # ---- op builders -----------------------------------------------------------------
     def conv(self, srcs, segs, weight, bias, out: View, *, Ho, Wo, B, n=None, n_valid=None, shuffle=1, act=ACT_NONE,
-             out_scale=None, out_f32=None, tail_weight=None, tail_z=None, tail_layout=0, out_lo: View = None, tail_flags=0, weight8=None):
+             out_scale=None, out_f32=None, tail_weight=None, tail_z=None, tail_layout=0, out_lo: View = None, tail_flags=0, weight8=None,
+             resid: View = None, resid_scale=1.0):
         """srcs: list[View]; segs: list[(src_index, taps, cblocks[, fmt])]; weight [n, Ktot] 16-bit; bias [n] fp32;
         weight8 [n, K8tot] uint8 (e5m2) for the segments with fmt == SEG_E5M2, whose sources are uint8 (e5m2) NHWC views."""
         d = ConvDesc()
@@ -169,17 +170,24 @@ class Plan:
             d.out_lo = out_lo.buf.data_ptr()
             d.out_lo_cstride = out_lo.cstride
             d.out_lo_choff = out_lo.choff
+        if resid is not None:
+            assert shuffle == 1 and (resid.B, resid.H, resid.W) == (B, Ho, Wo) and resid.buf.dtype == self.tdtype
+            d.resid = resid.ptr()
+            d.resid_cstride = resid.cstride
+            d.resid_choff = 0
+            d.resid_scale = float(resid_scale)
         op = Op()
         op.kind = OP_CONV
         op.u.conv = d
         self.ops.append(op)
         self.keep += [weight, bias, out_scale, out_f32, tail_weight, tail_z] + [s.buf for s in srcs] + ([out.buf] if out is not None else [])
         self.keep += [out_lo.buf] if out_lo is not None else []
-        self.keep += [weight8]
+        self.keep += [weight8, resid.buf if resid is not None else None]
         self.records.append(("conv", dict(srcs=list(srcs), segs=list(segs), weight=weight, bias=bias, out=out, Ho=Ho, Wo=Wo, B=B,
                                           n=n, n_valid=d.n_valid, shuffle=shuffle, act=act, out_scale=out_scale, out_f32=out_f32,
                                           issued_flops=2 * B * Ho * Wo * n * ktot, tail_weight=tail_weight, tail_z=tail_z,
-                                          tail_layout=tail_layout, out_lo=out_lo, tail_flags=tail_flags, weight8=weight8)))
+                                          tail_layout=tail_layout, out_lo=out_lo, tail_flags=tail_flags, weight8=weight8, resid=resid,
+                                          resid_scale=float(resid_scale))))
 
     def prep(self, x, scale, shift, im2col, xnorm=None, centre_only=False, im2col_lo=None):
         """centre_only: im2col is the normalised input itself, NHWC [B, H, W, cols] (inputs with more than 7 channels).

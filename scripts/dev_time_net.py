@@ -41,6 +41,6 @@ for i, (kind, r) in enumerate(plan.records):
     extra = ""
     if kind == "conv":
         segs = r["segs"]
-        extra = f"n={r['n']} {r['Ho']}x{r['Wo']} kb={sum(t_*c for _,t_,c in segs)} shuffle={r['shuffle']} issued {r['issued_flops']/t/1e9:.0f} TF/s"
+        extra = f"n={r['n']} {r['Ho']}x{r['Wo']} kb={sum(sg[1]*sg[2] for sg in segs)} shuffle={r['shuffle']} issued {r['issued_flops']/t/1e9:.0f} TF/s"
     print(f"  op{i:02d} {kind:8s} {t*1000:8.1f} us  {extra}")
 print(f"sum of ops {tot:.3f} ms")

@@ -73,6 +73,8 @@ def run_records(plan):
                 acc = y if acc is None else acc + y
             assert k0 == W.shape[1]
             acc = acc + r["bias"].view(1, -1, 1, 1)
+            if r.get("resid") is not None:
+                acc = acc + r["resid_scale"] * _view_nchw(r["resid"])
             if r["act"] == 1:
                 acc = F.relu(acc)
             elif r["act"] == 2:
