@@ -382,15 +382,15 @@ class ResUNet(_PlanModule):
             blk = self.encoder[l]
             h, w = H >> l, W >> l
             if l == 0:
-                # compensated: the input feeds the respass (the shallow path) as (x_hi, x_lo) x (W_hi, W_lo); conv0 heads the deep
-                # path, whose rounding is damped by the BatchNorm chain behind it (error budget: 0.05 % of the variance)
+                # compensated: the input feeds the respass (the shallow path) as (x_hi, x_lo) x (W_hi, W_lo) and conv0 as
+                # (x_hi, x_lo) x W_hi -- conv0's weight rounding is 0.05 % of the error variance, its input's rounding is not
                 t0 = 9 if wide_in else 1
                 f0 = (lambda wt: wt) if wide_in else _im2col_parts
                 fr = (lambda wt: wt) if wide_in else _im2col_centre
                 trip = (lambda p_: [p_, p_, split_lo(p_, plan.dtype)]) if comp else (lambda p_: [p_])
-                segs = [(0, t0, 1)]
+                segs = [(0, t0, 1), (1, t0, 1)] if comp else [(0, t0, 1)]
                 rsegs = [(0, 1, 1), (1, 1, 1), (0, 1, 1)] if comp else [(0, 1, 1)]
-                w0f = lambda wt: [f0(wt)]
+                w0f = lambda wt: [f0(wt)] * (2 if comp else 1)
                 wrf = lambda wt: (trip(fr(wt)), rsegs)
             else:
                 cin = hid[l - 1]
@@ -439,14 +439,16 @@ class ResUNet(_PlanModule):
                     fin = final[:b1 - b0]
                     catv = View(cat[l][b0:b1], 0, cin)
                     if comp:
-                        # low-order terms of the respass, (up | skip_hi) x W_lo + skip_lo x W_hi, as their own small GEMM scaled by
-                        # 2^10 (fp16 normal range); the block's last convolution adds them in its epilogue and keeps its three
-                        # source planes (a fourth one would halve the row ring of the 128-pixel-wide layers)
-                        wr_ = blk.respass.weight.detach().float()
-                        wpc = pack_weight([split_lo(wr_, plan.dtype) * 1024.0, wr_[:, up[l]:].contiguous() * 1024.0], plan.dtype)
+                        # low-order terms of the respass over the level-0 skip, skip_hi x W_lo + skip_lo x W_hi, as their own small GEMM
+                        # scaled by 2^10 (fp16 normal range); the block's last convolution adds them in its epilogue and keeps its
+                        # three source planes (a fourth one would halve the row ring of the 128-pixel-wide layers).  The up-sampled
+                        # half of the concat carries 4 % of the term's error (scripts/dev_error_budget.py) and stays single-pass.
+                        wr_ = blk.respass.weight.detach().float()[:, up[l]:].contiguous()
+                        wpc = pack_weight([split_lo(wr_, plan.dtype) * 1024.0, wr_ * 1024.0], plan.dtype)
                         cv = View(corr[:b1 - b0])
-                        plan.conv([catv, View(skip_lo[b0:b1])], [(0, 1, ceil_div(cin, 64)), (1, 1, ceil_div(hid[0], 64))], wpc,
-                                  torch.zeros(hid[0], device=dev), cv, Ho=h, Wo=w, B=b1 - b0)
+                        cbs_ = ceil_div(hid[0], 64)
+                        plan.conv([View(cat[l][b0:b1], up[l], hid[l]), View(skip_lo[b0:b1])], [(0, 1, cbs_), (1, 1, cbs_)],
+                                  wpc, torch.zeros(hid[0], device=dev), cv, Ho=h, Wo=w, B=b1 - b0)
                         self._emit_resblock(plan, blk, [catv], segs, w0f, wrf, [sv[:b1 - b0] for sv in scratch(l)], View(fin), 1, b1 - b0, h, w,
                                             resid=cv, resid_scale=2.0 ** -10)
                     else:
@@ -454,7 +456,9 @@ class ResUNet(_PlanModule):
                     xc = View(im2col[b0:b1], 0, C) if wide_in else View(im2col[b0:b1])
                     xc.wide_input = wide_in
                     xcl = None
-                    if comp and not wide_in:     # (a wide input's two extra full-width planes do not fit next to the fused tail's operands)
+                    # (rows-mode layers keep every source plane of three image rows in shared memory: a second full-width input
+                    # plane does not fit next to the fused tail's operands there -- narrow planes always do)
+                    if comp and not wide_in and (im2col.shape[3] == 16 or W % 128 != 0):
                         xcl = View(im2col_lo[b0:b1])
                     self._emit_reconstruction(plan, fin, xc, b1 - b0, H, W, dev, out[b0:b1], out_u8[b0:b1], zshared[0], xcol_lo=xcl)
                     zshared[0] = self._zbuf
@@ -633,7 +637,7 @@ class RDResUNet(_PlanModule):
         plan.prep(x_in, sc, sh, im2col, centre_only=wide_in, im2col_lo=im2col_lo)
         xcol = View(im2col, 0, C) if wide_in else View(im2col)
         xcol.wide_input = wide_in
-        xcol_lo = View(im2col_lo) if comp and not wide_in else None
+        xcol_lo = View(im2col_lo) if comp and not wide_in and (im2col.shape[3] == 16 or W % 128 != 0) else None
 
         # ---- encoder geometry: which stage outputs are decoder skips, and where they live -----------------
         n_st = len(enc.dense_stages)

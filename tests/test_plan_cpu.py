@@ -44,7 +44,7 @@ def test_resunet_plan_matches_oracle_on_cpu(dry_run, cfg, prec):
     print(f"{cfg} {prec}: max-abs {err:.5f}")
     # (the reduced test nets put relatively more weight on the one uncompensated term left, the last decoder output feeding
     # Reconstruction.pre; the default-depth models the 1e-2 bar is stated for are asserted in tests/test_gpu_net.py)
-    assert err < ((1e-2 if not cfg else 1.5e-2) if prec == "fp16c" else 3e-2)
+    assert err < ((1e-2 if not cfg else 2e-2) if prec == "fp16c" else 3e-2)
     c = got.shape[1] // 2
     assert torch.equal(st["out_u8"], got[:, c:c + 1].clamp(0, 255).to(torch.uint8))
 
