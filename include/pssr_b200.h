@@ -392,6 +392,19 @@ int pssr_normalize_preds(const uint8_t* hr, const uint8_t* hr_hat, uint8_t* hr_o
                          uint8_t* hr_hat_out, int32_t n, int32_t h, int32_t w, double pmin,
                          double pmax, void* workspace, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * File I/O edges: the reference reads sheets with tifffile.imread (pssr/data.py:566-571, :621-625) and
+ * writes predictions / stitched sheets with tifffile.imwrite (pssr/predict.py:71, pssr/util.py:103).  These entry points
+ * decode a grayscale 8 / 16-bit TIFF stack (uncompressed strips, one IFD per frame or a contiguous ImageJ hyperstack,
+ * classic or BigTIFF, either byte order) straight into caller-owned -- normally pinned -- host memory, so the upload can
+ * follow without a staging copy, and encode uint8 / uint16 stacks.  Host functions: no stream, callable from any thread.
+ * ------------------------------------------------------------------------------------ */
+/* native = 1: pssr_tiff_read can decode the file; 0: compressed / tiled / colour (the host mirror falls back to Pillow). */
+int pssr_tiff_probe(const char* path, int32_t* frames, int32_t* h, int32_t* w, int32_t* bits, int32_t* native);
+/* dst: [frames][h][w] in the file's bit depth, native byte order; dst_bytes >= frames*h*w*bits/8. */
+int pssr_tiff_read(const char* path, void* dst, int64_t dst_bytes);
+int pssr_tiff_write(const char* path, const void* src, int32_t frames, int32_t h, int32_t w, int32_t bits);
+
 #ifdef __cplusplus
 }
 #endif

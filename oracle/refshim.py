@@ -1,7 +1,7 @@
 """Import the *unmodified* reference (``/root/reference/pssr``) in the build container.
 
-TEST INFRASTRUCTURE ONLY, and only usable where ``/root/reference`` exists (the build
-container, never the GPU box).  The reference imports several third-party packages that
+TEST INFRASTRUCTURE ONLY, usable where ``/root/reference`` exists (the build container) or where
+``baseline/_ref`` holds the install of the reference's own wheel (``__graft_entry__.build()``).  The reference imports several third-party packages that
 are not installed here (tifffile, czifile, scikit-image, timm, pytorch_msssim, skopt);
 this module registers stand-ins in ``sys.modules`` -- real restatements for the routines
 on the hot path (``oracle/thirdparty.py``), inert stubs for file I/O and training-only
@@ -13,7 +13,19 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("PSSR_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root():
+    """The unmodified reference: $PSSR_REFERENCE_ROOT, the source checkout in the build container, or the copy installed from the
+    reference's own wheel into baseline/_ref (git-ignored; it travels to the GPU box with the snapshot)."""
+    for cand in (os.environ.get("PSSR_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "pssr")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:

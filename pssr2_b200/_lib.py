@@ -13,7 +13,7 @@ from ctypes import (POINTER, Structure, Union, c_char_p, c_double, c_float, c_in
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libpssr_b200.so")
-SOURCES = ["api.cu", "conv_igemm.cu", "conv_v3.cu", "net_aux.cu", "rdnet.cu", "crappify.cu", "stitch.cu", "metrics.cu"]
+SOURCES = ["api.cu", "conv_igemm.cu", "conv_v3.cu", "tiff_io.cu", "net_aux.cu", "rdnet.cu", "crappify.cu", "stitch.cu", "metrics.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
@@ -172,6 +172,9 @@ SYMBOLS = {
     "pssr_version": (c_char_p, []),
     "pssr_launch_count": (c_int64, []),
     "pssr_debug_trace": (c_int32, [c_void_p, c_int64]),
+    "pssr_tiff_probe": (c_int32, [c_char_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
+    "pssr_tiff_read": (c_int32, [c_char_p, c_void_p, c_int64]),
+    "pssr_tiff_write": (c_int32, [c_char_p, c_void_p, c_int32, c_int32, c_int32, c_int32]),
     "pssr_crappify": (c_int32, [POINTER(CrappifyArgs), c_void_p]),
     "pssr_noise_chain": (c_int32, [c_void_p, c_int32, c_void_p, c_int64, POINTER(NoiseStage), c_int32, c_int32, c_uint64, c_void_p]),
     "pssr_resize_bilinear": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
@@ -214,9 +217,26 @@ def check(rc: int, what: str = ""):
         raise RuntimeError(f"libpssr_b200 {what} failed ({rc}): {msg}")
 
 
-def current_stream_ptr():
+def current_stream_ptr(device=None):
+    """cudaStream_t of torch's current stream on ``device`` (default: the current device).  The C side keys its per-device state
+    on cudaGetDevice(), so callers also enter ``on_device(device)`` around every library call."""
     import torch
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def on_device(device):
+    """Context manager making ``device`` the current CUDA device for the duration of a library call (tensors on cuda:1 must be
+    processed with device 1 current: kernels launch into the current device's context)."""
+    import torch
+    return torch.cuda.device(device)
+
+
+def same_device(*tensors):
+    """The common device of the given CUDA tensors (None entries ignored); inputs that span devices are rejected."""
+    devs = {t.device for t in tensors if t is not None}
+    if len(devs) != 1:
+        raise ValueError(f"all tensors of one call must live on one CUDA device, got {sorted(str(d) for d in devs)}")
+    return next(iter(devs))
 
 
 def launch_count() -> int:

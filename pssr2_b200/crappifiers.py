@@ -40,6 +40,10 @@ class Crappifier(ABC):
 
     clip_between = False
 
+    def has_spread(self):
+        """True if the crappifier redraws its intensity on every call (spread > 0): datasets then resolve it per item."""
+        return float(getattr(self, "spread", 0) or 0) > 0
+
 
 def _resolve_intensity(intensity, spread):
     # max(np.random.normal(intensity, spread), 0) if spread > 0 else intensity  (crappifiers.py:63,85,104)
@@ -49,9 +53,9 @@ def _resolve_intensity(intensity, spread):
 
 
 class _DeviceCrappifier(Crappifier):
-    def crappify(self, image: np.ndarray):
+    def crappify(self, image: np.ndarray, _specs=None):
         image = np.asarray(image)
-        specs = self.noise_specs()
+        specs = self.noise_specs() if _specs is None else _specs
         x = torch.as_tensor(np.ascontiguousarray(image if image.dtype in (np.float32, np.float64) else image.astype(np.float64)))
         out = run_noise_chain(x.cuda(), specs, self.clip_between, _fresh_seed())
         res = out.cpu().numpy().reshape(image.shape)
@@ -72,8 +76,10 @@ def run_noise_chain(x: torch.Tensor, specs, clip_between, seed):
         arr[i].kind, arr[i].rng = s.kind, _lib.RNG_PHILOX
         arr[i].intensity, arr[i].gain, arr[i].mix_in_f32 = s.intensity, s.gain, 1 if s.mix_in_f32 else 0
         arr[i].injected = None
-    _lib.check(_lib.lib().pssr_noise_chain(x.data_ptr(), 1 if x.dtype == torch.float64 else 0, out.data_ptr(), x.numel(), arr,
-                                           len(specs), 1 if clip_between else 0, seed, _lib.current_stream_ptr()), "pssr_noise_chain")
+    with _lib.on_device(x.device):
+        _lib.check(_lib.lib().pssr_noise_chain(x.data_ptr(), 1 if x.dtype == torch.float64 else 0, out.data_ptr(), x.numel(), arr,
+                                               len(specs), 1 if clip_between else 0, seed, _lib.current_stream_ptr(x.device)),
+                   "pssr_noise_chain")
     return out
 
 
@@ -87,23 +93,37 @@ class MultiCrappifier(_DeviceCrappifier):
     def clip_between(self):
         return self.clip
 
+    def has_spread(self):
+        return any(isinstance(c, Crappifier) and c.has_spread() for c in self.crappifiers)
+
+    def _device_chain(self):
+        """True if the chain can run as one device noise chain: device crappifiers only; a nested MultiCrappifier must clip
+        like this one (the kernel has ONE clip-between flag per chain)."""
+        for c in self.crappifiers:
+            if not isinstance(c, _DeviceCrappifier):
+                return False
+            if isinstance(c, MultiCrappifier) and (c.clip != self.clip or not c._device_chain()):
+                return False
+        return True
+
     def noise_specs(self):
+        """One resolution of every stage, in chain order (each stage draws its ``spread`` exactly once per call)."""
+        if not self._device_chain():
+            return None
         specs = []
         for c in self.crappifiers:
-            s = c.noise_specs() if isinstance(c, Crappifier) else None
-            if s is None:
-                return None
-            specs += s
+            specs += c.noise_specs()
         return specs
 
     def crappify(self, image: np.ndarray):
-        if self.noise_specs() is None:  # contains a custom host crappifier: chain on the host like the reference
+        specs = self.noise_specs()          # resolved ONCE: a second call would consume extra np.random draws with spread > 0
+        if specs is None or len(specs) > 4:  # custom host crappifier / nested clip / long chain: chain on the host like the reference
             for c in self.crappifiers:
                 image = c.crappify(image)
                 if self.clip:
                     image = np.clip(image, 0, 255)
             return image
-        return super().crappify(image)
+        return super().crappify(image, _specs=specs)
 
 
 class AdditiveGaussian(_DeviceCrappifier):

@@ -36,6 +36,19 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 
 int device_sm_count();
 
+// One-time per-DEVICE setup (cudaFuncSetAttribute is a per-device property: a second GPU used by the same process needs its own
+// opt-in to large dynamic shared memory).  first() is true the first time it is called with a given current device.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 #ifdef __CUDACC__
 // Programmatic dependent launch for the small kernels between the convolutions: the kernel may be scheduled while its
 // predecessor drains (pdl_wait() orders every memory access after the predecessor's completion) and lets its successor

@@ -413,10 +413,9 @@ int conv_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
   const int sms = device_sm_count();
   op.grid = p.total_tiles < sms ? p.total_tiles : sms;
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     PSSR_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
-    attr_set = true;
   }
   return PSSR_OK;
 }

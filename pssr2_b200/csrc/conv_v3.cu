@@ -1891,11 +1891,10 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
         kV3Variants[i].PAIR == PAIR && kV3Variants[i].ROWS == p.rows_mode)
       op.kernel_index = i;
   PSSR_REQUIRE(op.kernel_index >= 0, PSSR_EUNSUP, "conv: no kernel variant for T=%d G=%d RES=%d TAIL=%d PAIR=%d", T, G, RES, (int)tail, PAIR);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     for (int i = 0; i < kV3NumVariants; ++i)
       PSSR_CHECK_CUDA(cudaFuncSetAttribute(kV3Variants[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-    attr_set = true;
   }
   if (getenv("PSSR_V3_VERBOSE") != nullptr)
     fprintf(stderr, "v3: %dx%d n=%d kb=%d block_n=%d T=%d G=%d RES=%d TAIL=%d PAIR=%d rows=%d/%d cols=%d ring=%d b_stages=%d a_bytes=%u smem=%d units=%d grid=%d\n",

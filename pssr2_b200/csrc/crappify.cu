@@ -779,8 +779,8 @@ extern "C" int pssr_crappify(const pssr_crappify_args_t* a, void* stream) {
     const int ks = getenv("PSSR_CRAP_GENERIC") != nullptr ? 0 : (p.ksize <= 9 ? 9 : (p.ksize <= 17 ? 17 : 0));
 #define PSSR_CRAP_LAUNCH(TT, KK)                                                                                              \
   do {                                                                                                                        \
-    static bool attr = false;                                                                                                 \
-    if (!attr) { PSSR_CHECK_CUDA(cudaFuncSetAttribute(crappify_kernel<TT, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; } \
+    static PerDeviceOnce attr;                                                                                                \
+    if (attr.first()) PSSR_CHECK_CUDA(cudaFuncSetAttribute(crappify_kernel<TT, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
     crappify_kernel<TT, KK><<<(unsigned)blocks, kCrapThreads, smem, st>>>(p);                                                 \
   } while (0)
     if (a->elem_bytes == 1) {

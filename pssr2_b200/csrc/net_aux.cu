@@ -343,10 +343,9 @@ int tail_launch(const pssr_tail_desc_t& d, int dtype, cudaStream_t stream) {
                PSSR_EUNSUP, "tail: C=%d unsupported", d.C);
   PSSR_REQUIRE(d.cstride % 8 == 0 && d.cstride >= d.C, PSSR_EUNSUP, "tail: bad channel stride");
   const size_t smem = (size_t)(kTailTW + 2) * (kTailTH + 2) * chunks * 16 + (size_t)d.Cout * 9 * d.C * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     PSSR_CHECK_CUDA(cudaFuncSetAttribute(tail_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
   }
   const int tiles = ((d.W + kTailTW - 1) / kTailTW) * ((d.H + kTailTH - 1) / kTailTH);
   tail_conv_kernel<<<d.B * tiles, kTailTW * kTailTH, smem, stream>>>(d, dtype == PSSR_DT_FP16);

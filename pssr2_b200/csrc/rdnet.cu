@@ -497,11 +497,8 @@ int dwln_launch(const pssr_dwln_desc_t& d, int dtype, cudaStream_t stream) {
   const int slabs_all = (d.C + kDwC - 1) / kDwC;
   // enough spatial tiles to fill the machine twice over and at least two slabs to pipeline: the slab-walking kernel
   if (sp_tiles >= 4LL * device_sm_count() && slabs_all >= 2 && ((uintptr_t)d.dw_w & 15) == 0 && d.C % 4 == 0 && getenv("PSSR_DW_NOPIPE") == nullptr) {
-    static bool attr_pipe = false;
-    if (!attr_pipe) {
-      PSSR_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kDwBufBytes));
-      attr_pipe = true;
-    }
+    static PerDeviceOnce attr_pipe;
+    if (attr_pipe.first()) PSSR_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kDwBufBytes));
     PSSR_REQUIRE(sp_tiles < (1ll << 31), PSSR_EUNSUP, "dwconv: too many blocks");
     dwconv7_pipe_kernel<<<(unsigned)sp_tiles, 256, 2 * kDwBufBytes, stream>>>(d, dtype == PSSR_DT_FP16);
     count_launch();
@@ -515,10 +512,9 @@ int dwln_launch(const pssr_dwln_desc_t& d, int dtype, cudaStream_t stream) {
   const long long blocks = (long long)d.B * ((d.C + kDwC - 1) / kDwC) * ((d.H + kDwTH - 1) / kDwTH) * ((d.W + kDwTW - 1) / kDwTW);
   PSSR_REQUIRE(blocks < (1ll << 31), PSSR_EUNSUP, "dwconv: too many blocks");
   const size_t smem = (size_t)(kDwTH + 6) * (kDwTW + 6) * (kDwC / 8) * 16 + (49 * kDwC + kDwC) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     PSSR_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_set = true;
   }
   dwconv7_kernel<<<(unsigned)blocks, 256, smem, stream>>>(d, dtype == PSSR_DT_FP16);
   count_launch();

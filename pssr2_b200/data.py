@@ -88,8 +88,8 @@ def _slice_center_range(total, n):
     return (center - half, 2 * half) if n % 2 == 0 else (center - half, 2 * half + 1)
 
 
-def _load_sources(path, extension):
-    """-> (names, arrays [F,H,W] uint8/uint16)."""
+def _load_sources(path, extension, stack="TZ", mode="L"):
+    """-> (names, arrays [F,H,W] uint8/uint16 or lazy ``io.SheetFile`` sources)."""
     if isinstance(path, dict):
         names, arrays = list(path.keys()), list(path.values())
     elif isinstance(path, (list, tuple)):
@@ -102,20 +102,20 @@ def _load_sources(path, extension):
         files = sorted(glob.glob(f"{p}/**/*.{extension}", recursive=True))
         if not len(files) > 0:
             raise FileNotFoundError(f'No .{extension} files exist in path "{p}".')
-        if extension.lower() == "czi":
-            raise NotImplementedError("czi decoding is outside the accelerated hot path; convert sheets to TIFF or pass arrays")
-        from PIL import Image
-        names, arrays = [], []
-        for f in files:
-            im = Image.open(f)
-            frames = []
-            for i in range(getattr(im, "n_frames", 1)):
-                im.seek(i)
-                frames.append(np.asarray(im))
-            arrays.append(np.stack(frames))
-            names.append(os.path.relpath(f, p))
+        # lazy sources (pssr2_b200/io.py): TIFF geometry from a header probe, pixels decoded into pinned memory on a reader
+        # thread when a batch first needs the sheet (tifffile.imread keeps the native 8 / 16-bit depth, data.py:621-625);
+        # CZI: axis selection / channel mean / max-normalisation to uint8 (data.py:585-619); other formats: Pillow,
+        # converted to mode "L" (data.py:640-647)
+        from .io import SheetFile
+        names = [os.path.relpath(f, p) for f in files]
+        arrays = [SheetFile(f, stack=stack, mode=mode) for f in files]
     out = []
     for a in arrays:
+        if hasattr(a, "read_pinned"):
+            if a.dtype not in (np.uint8, np.uint16) or len(a.shape) != 3:
+                raise TypeError(f"{a.path}: images must decode to [frames, H, W] uint8 / uint16")
+            out.append(a)
+            continue
         if isinstance(a, torch.Tensor):   # e.g. a pinned host stack: uploaded as is (int16 = uint16 container)
             if a.dim() == 2:
                 a = a[None]
@@ -137,23 +137,56 @@ def _load_sources(path, extension):
 
 
 class _DeviceDataset(Dataset):
-    """Shared machinery: resident sheets, tile table, fused batch generation."""
+    """Shared machinery: sheets resident in HBM, tile table, fused batch generation.
 
-    def _upload(self, arrays, device):
-        shapes = {tuple(a.shape[1:]) for a in arrays}
+    Residency.  ``_sources[i]`` is the host side of sheet i (a NumPy array, a -- preferably pinned -- torch tensor, or a lazy
+    ``io.SheetFile`` that decodes into a pinned staging buffer on a reader thread); ``_sheets[i]`` is its device copy or None.
+    Sheets go up on a side stream the first time a batch touches them, the next one is prefetched while the current one is
+    being predicted, and -- when ``max_resident_bytes`` is set -- the least recently used ones are dropped again, so a dataset
+    larger than HBM streams through (the reference's ``preload=False`` analogue, pssr/data.py:553-564).  Without a process
+    group and with everything fitting the budget the whole dataset is uploaded at construction (``preload=True``)."""
+
+    max_resident_bytes = None      # None: keep every sheet that was uploaded
+
+    def _upload(self, arrays, device, preload=True):
         dtypes = {str(a.dtype).replace("torch.", "").replace("int16", "uint16").replace("uuint16", "uint16") for a in arrays}
         if len(dtypes) != 1:
             raise NotImplementedError("all images of one dataset must share their dtype on the device path")
         self.device = torch.device(device)
-        self._sheets = []
+        if self.device.type != "cuda":
+            raise RuntimeError("pssr2_b200 datasets live on CUDA devices (no CPU path); pass device='cuda'")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self._sources = list(arrays)
+        self._sheets = [None] * len(arrays)
         self._sheet_events = {}     # sheet index -> upload-complete event not yet waited for by the compute stream
-        # sheets go up on a side stream, one event per sheet: batch() waits only for the sheets it gathers from, so the
-        # upload of later sheets overlaps the first batches (pinned host tensors make the copies truly asynchronous)
-        up = torch.cuda.Stream(device=self.device)
-        cur = torch.cuda.current_stream(self.device)
-        up.wait_stream(cur)         # the destination blocks may be recycled memory still in use by kernels queued on `cur`
-        for i, a in enumerate(arrays):
-            t = a if isinstance(a, torch.Tensor) else torch.as_tensor(a.view(np.int16) if a.dtype == np.uint16 else a)
+        self._lru = []              # resident sheet indices, least recently used first
+        self._upload_stream = torch.cuda.Stream(device=self.device)
+        self._frames_total = [a.shape[0] for a in arrays]
+        self._shapes = [tuple(a.shape[1:]) for a in arrays]          # per image (heights / widths may differ)
+        from . import dist as D
+        if preload and not D.is_dist():
+            for i in range(len(arrays)):
+                self._ensure(i)
+
+    def _sheet_bytes(self, i):
+        f, (h, w) = self._frames_total[i], self._shapes[i]
+        return f * h * w * (1 if str(self._sources[i].dtype).endswith("uint8") else 2)
+
+    def _ensure(self, i):
+        """Starts the upload of sheet i on the side stream unless it is resident; returns immediately."""
+        if self._sheets[i] is not None:
+            return
+        src = self._sources[i]
+        if hasattr(src, "read_pinned"):                  # lazy file source (pssr2_b200/io.py): decoded into pinned staging
+            if i + 1 < len(self._sources) and hasattr(self._sources[i + 1], "prefetch"):
+                self._sources[i + 1].prefetch()          # the next sheet decodes on the reader thread meanwhile
+            src = src.read_pinned()
+        t = src if isinstance(src, torch.Tensor) else torch.as_tensor(src.view(np.int16) if src.dtype == np.uint16 else src)
+        up = self._upload_stream
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream(self.device)
+            up.wait_stream(cur)     # the destination block may be recycled memory still in use by kernels queued on `cur`
             # destination from the CURRENT stream's pool: a block allocated under a fresh side stream can never be served from
             # the allocator's cache, i.e. every sheet would cost a synchronous cudaMalloc (measured 0.4 ms per 33 MB sheet)
             d = torch.empty(t.shape, dtype=t.dtype, device=self.device)
@@ -162,21 +195,64 @@ class _DeviceDataset(Dataset):
                 ev = torch.cuda.Event()
                 ev.record(up)
             d.record_stream(up)
-            self._sheets.append(d)
-            self._sheet_events[i] = ev
-        self._upload_stream = up
-        self._frames_total = [a.shape[0] for a in arrays]
-        self._shapes = [tuple(a.shape[1:]) for a in arrays]          # per image (heights / widths may differ)
+        self._sheets[i] = d
+        self._sheet_events[i] = ev
+        self._lru.append(i)
+
+    def _evict(self, keep):
+        if self.max_resident_bytes is None:
+            return
+        total = sum(self._sheet_bytes(i) for i in self._lru)
+        for i in list(self._lru):
+            if total <= self.max_resident_bytes:
+                break
+            if i in keep:
+                continue
+            self._lru.remove(i)
+            self._sheet_events.pop(i, None)
+            self._sheets[i] = None      # the caching allocator frees the block once the kernels queued on it are done
+            total -= self._sheet_bytes(i)
 
     def _wait_sheets(self, sheet_ids):
-        """Orders the current stream after the upload of the given sheets (each event is waited for once)."""
-        if not self._sheet_events:
-            return
+        """Makes the given sheets resident, orders the current stream after their upload (each event is waited for once) and
+        prefetches the sheet after the last one."""
+        ids = sorted(set(int(i) for i in sheet_ids))
+        for i in ids:
+            self._ensure(i)
+            if i in self._lru:
+                self._lru.remove(i)
+                self._lru.append(i)
+        nxt = ids[-1] + 1
+        keep = set(ids)
+        if nxt < len(self._sheets) and (self.max_resident_bytes is None or
+                                         sum(self._sheet_bytes(i) for i in keep | {nxt}) <= self.max_resident_bytes):
+            src = self._sources[nxt]
+            if not hasattr(src, "read_pinned") or src.ready():
+                self._ensure(nxt)            # upload ahead (a file source only once its decode has finished: never block here)
+                keep.add(nxt)
+            else:
+                src.prefetch()
+        self._evict(keep)
         cur = torch.cuda.current_stream(self.device)
-        for i in set(sheet_ids):
+        for i in ids:
             ev = self._sheet_events.pop(i, None)
             if ev is not None:
                 cur.wait_event(ev)
+
+    def sheet_item_counts(self):
+        """Validation items per source image, in ``val_idx`` order (the unit of sheet-aligned sharding): a list of
+        (image index, count) runs, or None when the validation items of an image are not contiguous."""
+        runs = []
+        tiles = getattr(self, "tiles", None)
+        for v in self.val_idx:
+            img = _get_image_idx(v, self.slices, tiles)[0]
+            if runs and runs[-1][0] == img:
+                runs[-1][1] += 1
+            elif any(r[0] == img for r in runs):
+                return None
+            else:
+                runs.append([img, 1])
+        return [(i, c) for i, c in runs]
 
     # per-item geometry, implemented by subclasses: (sheet, frame0, y, x, vh, vw)
     def _locate(self, idx):
@@ -195,7 +271,20 @@ class _DeviceDataset(Dataset):
         """One fused launch for many items.  Returns dict(lr=[n,f_lr,h,w] f32, hr=[n,f_hr,H,W] f32 | None,
         hr_u8=[n,1,H,W] u8 | None), all on the device.  (pssr/data.py:100-120 / :236-256 + _gen_pair :471-495)"""
         indices = list(indices)
-        frames = self._frames_window(_get_image_idx(indices[0], self.slices, getattr(self, "tiles", None))[0])
+        tiles_ = getattr(self, "tiles", None)
+        windows = {self._frames_window(_get_image_idx(i, self.slices, tiles_)[0]) for i in indices}
+        crap_ = self.crappifier
+        per_item = len(indices) > 1 and (len(windows) > 1 or (isinstance(crap_, Crappifier) and crap_.has_spread()))
+        if per_item:
+            # items whose frame windows differ (n_frames=-1 over stacks of different depth) cannot share a launch, and a
+            # crappifier with spread > 0 redraws its intensity for EVERY item (pssr/crappifiers.py:63,85,104): one launch each
+            t0 = indices[0] if tile_index0 is None else tile_index0
+            parts = [self.batch([i], want_hr, want_hr_u8, want_lr, t0 + k, seed) for k, i in enumerate(indices)]
+            if len(windows) > 1 and not self.is_lr and any(p["lr"].shape != parts[0]["lr"].shape for p in parts):
+                raise ValueError("the items of one batch have different frame counts (n_frames=-1 over stacks of different depth); "
+                                 "use batch_size=1 or a fixed n_frames")
+            return {k: (torch.cat([p[k] for p in parts]) if parts[0][k] is not None else None) for k in ("lr", "hr", "hr_u8")}
+        frames = self._frames_window(_get_image_idx(indices[0], self.slices, tiles_)[0])
         table = self._table(indices)
         lr_res_scale = self.lr_scale
         if self.is_lr:
@@ -216,6 +305,8 @@ class _DeviceDataset(Dataset):
                 host_crap = crap
             else:
                 clip_between = bool(getattr(crap, "clip_between", False))
+                if len(specs) > 4:
+                    host_crap, specs = crap, None      # longer chains than the kernel's four stages run on the host path
         seed = _fresh_seed() if seed is None else seed
         t0 = indices[0] if tile_index0 is None else tile_index0
         if host_crap is None:
@@ -255,7 +346,7 @@ class SlidingDataset(_DeviceDataset):
         if extra_path is not None or transforms is not None:
             raise NotImplementedError("extra_path / transforms are training-time options outside the accelerated predict path")
         self.path = path
-        names, arrays = _load_sources(path, extension)
+        names, arrays = _load_sources(path, extension, stack=stack.upper())
         self.hr_files = names
         overlap = 0 if overlap is None else overlap
         if not hr_res > overlap:
@@ -265,7 +356,7 @@ class SlidingDataset(_DeviceDataset):
         lr_scale = None if lr_scale == -1 else lr_scale
         self.n_frames = _get_n_frames(n_frames)
         self.slide = slide
-        self.preload = True
+        self.preload = preload
         self.tiles, self.slices, self._tiles_y = [], [], []
         for a in arrays:
             tx, ty = _n_tiles(a.shape[-2:], hr_res, self.stride)
@@ -283,7 +374,7 @@ class SlidingDataset(_DeviceDataset):
         self.hr_res, self.lr_scale = hr_res, lr_scale
         self._lr_mode_res = hr_res
         self.crappifier, self.rotation, self.extra_scale, self.transforms = crappifier, rotation, extra_scale, transforms
-        self._upload(arrays, device)
+        self._upload(arrays, device, preload=preload)
 
     def _locate(self, idx):
         image_idx, local = _get_image_idx(idx, self.slices, self.tiles)

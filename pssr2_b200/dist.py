@@ -48,6 +48,60 @@ def shard_range(n_items: int):
     return shard_bounds(n_items, rank(), world_size())
 
 
+def shard_groups(counts, r: int, w: int):
+    """Group-aligned sharding ("aligned to whole sheets where possible so each rank stitches its own sheets").
+    ``counts[g]`` items belong to group g (a sheet), groups are contiguous in item order.  Returns (first group, end group,
+    first item, end item) of rank r: contiguous runs of whole groups, balanced by item count with a greedy prefix split."""
+    total = sum(counts)
+    bounds, acc, g = [0], 0, 0
+    for k in range(1, w):
+        target = total * k / w
+        while g < len(counts) and acc + counts[g] / 2 <= target:
+            acc += counts[g]
+            g += 1
+        bounds.append(g)
+    bounds.append(len(counts))
+    g0, g1 = bounds[r], bounds[r + 1]
+    return g0, g1, sum(counts[:g0]), sum(counts[:g1])
+
+
+def allreduce_vector(t: torch.Tensor) -> torch.Tensor:
+    """In-place SUM of a small tensor over ranks on its own device (NCCL) or via the CPU (gloo)."""
+    if not is_dist():
+        return t
+    if dist.get_backend() == "nccl":
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t
+    c = t.cpu()
+    dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    t.copy_(c)
+    return t
+
+
+def gather_sheets(local, owners, shapes, device):
+    """Stitched uint8 sheets to rank 0 (the path's second collective).  ``local``: {sheet index: device tensor} of
+    this rank; ``owners[s]``: the rank that holds sheet s; ``shapes[s]``: its shape.  Point-to-point sends over NCCL (NVLink) /
+    gloo, all posted at once; rank 0 returns the full list in sheet order, the others their own sheets (None elsewhere)."""
+    n = len(owners)
+    if not is_dist() or world_size() == 1:
+        return [local.get(s) for s in range(n)]
+    cpu = dist.get_backend() != "nccl"
+    ops_, out = [], [local.get(s) for s in range(n)]
+    for s in range(n):
+        if owners[s] == 0:
+            continue
+        if rank() == 0:
+            out[s] = torch.empty(tuple(shapes[s]), dtype=torch.uint8, device="cpu" if cpu else device)
+            ops_.append(dist.P2POp(dist.irecv, out[s], owners[s]))
+        elif rank() == owners[s]:
+            t = local[s].contiguous()
+            ops_.append(dist.P2POp(dist.isend, t.cpu() if cpu else t, 0))
+    if ops_:
+        for req in dist.batch_isend_irecv(ops_):
+            req.wait()
+    return out
+
+
 def _device():
     return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
 
@@ -85,12 +139,14 @@ def gather_dict(outs: dict):
     return outs
 
 
-def gather_images_nccl(local: torch.Tensor, n_items: int):
+def gather_images_nccl(local: torch.Tensor, n_items: int, counts=None):
     """NCCL path of predict_images: every rank holds the uint8 predictions of its contiguous block of the validation items as
     ONE device tensor [n_local, ...]; rank 0 receives all blocks with one `gather` over NVLink and returns
-    [n_items, ...] in validation order (other ranks return None).  Blocks are padded to the largest share."""
+    [n_items, ...] in validation order (other ranks return None).  Blocks are padded to the largest share.
+    ``counts``: items per rank when the shares are not the balanced ``shard_bounds`` split (sheet-aligned sharding)."""
     w, r = world_size(), rank()
-    counts = [shard_bounds(n_items, k, w)[1] - shard_bounds(n_items, k, w)[0] for k in range(w)]
+    if counts is None:
+        counts = [shard_bounds(n_items, k, w)[1] - shard_bounds(n_items, k, w)[0] for k in range(w)]
     mx = max(counts)
     if min(counts) == 0:        # fewer items than ranks: an empty rank does not know the image shape
         shapes = [None] * w

@@ -25,11 +25,18 @@ class NoiseSpec:
 
 
 class TileTable:
-    """Device-resident description of where each HR tile lives inside the resident sheets."""
+    """Device-resident description of where each HR tile lives inside the resident sheets.
+
+    ``sheets`` may hold ``None`` for sheets that are not resident; only the sheets the tiles reference are used (their indices
+    are remapped), and the pointer table, the per-sheet dimensions and the six index columns travel in ONE pinned-host ->
+    device copy on the current stream."""
 
     def __init__(self, sheets, tile_sheet, tile_frame, tile_y, tile_x, tile_vh, tile_vw):
-        dev = sheets[0].device
-        self.sheets = [_cuda(s, "sheet").contiguous() for s in sheets]
+        tile_sheet = np.asarray(tile_sheet, dtype=np.int64)
+        used = sorted(set(int(i) for i in tile_sheet))
+        remap = {g: k for k, g in enumerate(used)}
+        self.sheets = [_cuda(sheets[g], "sheet").contiguous() for g in used]
+        dev = _lib.same_device(*self.sheets)
         s0 = self.sheets[0]
         for s in self.sheets:
             if s.dim() != 3 or s.dtype != s0.dtype:
@@ -41,16 +48,28 @@ class TileTable:
         else:
             raise TypeError(f"sheets must be uint8 or uint16, got {s0.dtype}")
         self.sheet_h, self.sheet_w = int(s0.shape[1]), int(s0.shape[2])
-        self.ptrs = torch.tensor([s.data_ptr() for s in self.sheets], dtype=torch.int64, device=dev)
+        n, ns = int(tile_sheet.size), len(used)
+        local = np.asarray([remap[int(i)] for i in tile_sheet], dtype=np.int32)
+        self.frames_of_tile = np.asarray([int(self.sheets[k].shape[0]) for k in local], dtype=np.int64)   # host copy: frame-range checks
+        self.tile_frame_host = np.asarray(tile_frame, dtype=np.int64)
+        # packed header: [ns] int64 pointers | [2*ns] int32 sheet dims | [6*n] int32 columns
+        host = torch.empty(8 * ns + 4 * (2 * ns + 6 * n), dtype=torch.uint8, pin_memory=True)
+        hv = host.numpy()
+        hv[:8 * ns].view(np.int64)[:] = [s.data_ptr() for s in self.sheets]
+        i32 = hv[8 * ns:].view(np.int32)
+        i32[:ns] = [int(s.shape[1]) for s in self.sheets]
+        i32[ns:2 * ns] = [int(s.shape[2]) for s in self.sheets]
+        i32[2 * ns:] = np.asarray([local, tile_frame, tile_y, tile_x, tile_vh, tile_vw], dtype=np.int32).reshape(-1)
+        with _lib.on_device(dev):
+            packed = host.to(dev, non_blocking=True)
+        self._packed, self._host = packed, host            # the pinned source must outlive the asynchronous copy
+        self.ptrs = packed[:8 * ns].view(torch.int64)
+        d32 = packed[8 * ns:].view(torch.int32)
         # sheets of different sizes: per-sheet dimension arrays travel with the table
-        self.sheet_dims = None
-        if any(s.shape[1:] != s0.shape[1:] for s in self.sheets):
-            self.sheet_dims = torch.tensor([[int(s.shape[1]) for s in self.sheets], [int(s.shape[2]) for s in self.sheets]],
-                                           dtype=torch.int32, device=dev)
-        # one host->device copy for the six index columns
-        cols = torch.as_tensor(np.asarray([tile_sheet, tile_frame, tile_y, tile_x, tile_vh, tile_vw], dtype=np.int32)).to(dev)
+        self.sheet_dims = d32[:2 * ns].view(2, ns) if any(s.shape[1:] != s0.shape[1:] for s in self.sheets) else None
+        cols = d32[2 * ns:].view(6, n)
         self.tile_sheet, self.tile_frame, self.tile_y, self.tile_x, self.tile_vh, self.tile_vw = (cols[i] for i in range(6))
-        self.n_tiles = int(self.tile_sheet.numel())
+        self.n_tiles = n
         self.device = dev
 
     def slice(self, start, count):
@@ -58,6 +77,8 @@ class TileTable:
         t.__dict__.update(self.__dict__)
         for k in ("tile_sheet", "tile_frame", "tile_y", "tile_x", "tile_vh", "tile_vw"):
             setattr(t, k, getattr(self, k)[start:start + count])
+        t.frames_of_tile = self.frames_of_tile[start:start + count]
+        t.tile_frame_host = self.tile_frame_host[start:start + count]
         t.n_tiles = count
         return t
 
@@ -72,6 +93,13 @@ def crappify(table: TileTable, hr_res, lr_scale, stages, *, frames=1, lr_frame0=
     lr_frames = frames if lr_frames is None else lr_frames
     hr_frames = frames if hr_frames is None else hr_frames
     dev = table.device
+    # the kernel reads frames [tile_frame, tile_frame + frames) of each tile's sheet: a window that runs past a (shorter) sheet
+    # would be an out-of-bounds device read, so it is rejected here
+    bad = np.nonzero((table.tile_frame_host < 0) | (table.tile_frame_host + frames > table.frames_of_tile))[0]
+    if bad.size:
+        k = int(bad[0])
+        raise ValueError(f"tile {k}: frames [{int(table.tile_frame_host[k])}, {int(table.tile_frame_host[k]) + frames}) exceed its sheet's "
+                         f"{int(table.frames_of_tile[k])} frames (one batch must not mix sheets with different frame windows)")
     a = CrappifyArgs()
     a.sheets = table.ptrs.data_ptr()
     a.n_sheets = len(table.sheets)
@@ -112,7 +140,8 @@ def crappify(table: TileTable, hr_res, lr_scale, stages, *, frames=1, lr_frame0=
     a.lr_out = lr.data_ptr() if lr is not None else None
     a.hr_out = hr.data_ptr() if hr is not None else None
     a.hr_u8_out = hr8.data_ptr() if hr8 is not None else None
-    _lib.check(_lib.lib().pssr_crappify(ctypes.byref(a), _lib.current_stream_ptr()), "pssr_crappify")
+    with _lib.on_device(dev):
+        _lib.check(_lib.lib().pssr_crappify(ctypes.byref(a), _lib.current_stream_ptr(dev)), "pssr_crappify")
     return lr, hr, hr8
 
 
@@ -122,8 +151,9 @@ def resize_bilinear(img: torch.Tensor, scale: int) -> torch.Tensor:
     n, h, w = img.shape
     eb = img.element_size()
     out = torch.empty(n, h // scale, w // scale, dtype=img.dtype, device=img.device)
-    _lib.check(_lib.lib().pssr_resize_bilinear(img.data_ptr(), out.data_ptr(), n, h, w, scale, eb, _lib.current_stream_ptr()),
-               "pssr_resize_bilinear")
+    with _lib.on_device(img.device):
+        _lib.check(_lib.lib().pssr_resize_bilinear(img.data_ptr(), out.data_ptr(), n, h, w, scale, eb, _lib.current_stream_ptr(img.device)),
+                   "pssr_resize_bilinear")
     return out
 
 
@@ -137,7 +167,9 @@ def stitch(tiles: torch.Tensor, n_rows, n_cols, overlap, margin) -> torch.Tensor
     T = int(tiles.shape[1])
     step = T - overlap
     out = torch.empty(stacks, n_rows * step + overlap, n_cols * step + overlap, dtype=torch.uint8, device=tiles.device)
-    rc = _lib.lib().pssr_stitch(tiles.data_ptr(), out.data_ptr(), stacks, n_rows, n_cols, T, overlap, margin, _lib.current_stream_ptr())
+    with _lib.on_device(tiles.device):
+        rc = _lib.lib().pssr_stitch(tiles.data_ptr(), out.data_ptr(), stacks, n_rows, n_cols, T, overlap, margin,
+                                    _lib.current_stream_ptr(tiles.device))
     if rc == -1 and b"margin" in _lib.lib().pssr_last_error():
         raise ValueError(_lib.lib().pssr_last_error().decode())
     _lib.check(rc, "pssr_stitch")
@@ -147,14 +179,16 @@ def stitch(tiles: torch.Tensor, n_rows, n_cols, overlap, margin) -> torch.Tensor
 def metric_sums(a: torch.Tensor, b: torch.Tensor, want_ssim=True):
     """Exact per-image sums for uint8 pairs [n, h, w]: (sum (a-b)^2 int64 [n], SSIM-map sum float64 [n] | None)."""
     a, b = _cuda(a, "a").contiguous(), _cuda(b, "b").contiguous()
+    _lib.same_device(a, b)
     if a.dtype != torch.uint8 or b.dtype != torch.uint8 or a.shape != b.shape or a.dim() != 3:
         raise ValueError("metric_sums expects two uint8 tensors of identical shape [n, h, w]")
     n, h, w = a.shape
     sq = torch.empty(n, dtype=torch.int64, device=a.device)
     ss = torch.empty(n, dtype=torch.float64, device=a.device) if want_ssim else None
     ws = torch.empty(max(16, int(_lib.lib().pssr_metric_workspace_bytes(n, h, w))), dtype=torch.uint8, device=a.device)
-    rc = _lib.lib().pssr_metric_sums(a.data_ptr(), b.data_ptr(), n, h, w, sq.data_ptr(), ss.data_ptr() if ss is not None else None,
-                                     ws.data_ptr(), _lib.current_stream_ptr())
+    with _lib.on_device(a.device):
+        rc = _lib.lib().pssr_metric_sums(a.data_ptr(), b.data_ptr(), n, h, w, sq.data_ptr(), ss.data_ptr() if ss is not None else None,
+                                         ws.data_ptr(), _lib.current_stream_ptr(a.device))
     if rc == -1 and b"win_size" in _lib.lib().pssr_last_error():
         raise ValueError(_lib.lib().pssr_last_error().decode())
     _lib.check(rc, "pssr_metric_sums")
@@ -164,11 +198,13 @@ def metric_sums(a: torch.Tensor, b: torch.Tensor, want_ssim=True):
 def normalize_preds_u8(hr: torch.Tensor, hr_hat: torch.Tensor, pmin=0.1, pmax=99.9):
     """`normalize_preds` (pssr/util.py:139-191) on device for uint8 pairs [n, h, w] of equal shape."""
     hr, hr_hat = _cuda(hr, "hr").contiguous(), _cuda(hr_hat, "hr_hat").contiguous()
+    _lib.same_device(hr, hr_hat)
     if hr.dtype != torch.uint8 or hr_hat.dtype != torch.uint8 or hr.shape != hr_hat.shape or hr.dim() != 3:
         raise ValueError("normalize_preds_u8 expects two uint8 tensors of identical shape [n, h, w]")
     n, h, w = hr.shape
     ws = torch.empty(int(_lib.lib().pssr_normalize_workspace_bytes(n)), dtype=torch.uint8, device=hr.device)
     oa, ob = torch.empty_like(hr), torch.empty_like(hr_hat)
-    _lib.check(_lib.lib().pssr_normalize_preds(hr.data_ptr(), hr_hat.data_ptr(), oa.data_ptr(), ob.data_ptr(), n, h, w, pmin, pmax,
-                                               ws.data_ptr(), _lib.current_stream_ptr()), "pssr_normalize_preds")
+    with _lib.on_device(hr.device):
+        _lib.check(_lib.lib().pssr_normalize_preds(hr.data_ptr(), hr_hat.data_ptr(), oa.data_ptr(), ob.data_ptr(), n, h, w, pmin, pmax,
+                                                   ws.data_ptr(), _lib.current_stream_ptr(hr.device)), "pssr_normalize_preds")
     return oa, ob

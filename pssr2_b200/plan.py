@@ -304,18 +304,22 @@ class Plan:
             return self
         arr = (Op * len(self.ops))(*self.ops)
         h = ctypes.c_void_p()
-        _lib.check(_lib.lib().pssr_plan_create(arr, len(self.ops), self.dtype, ctypes.byref(h)), "pssr_plan_create")
+        # the plan belongs to the device its buffers live on: created and run with that device current
+        self.device = _lib.same_device(*[t for t in self.keep if isinstance(t, torch.Tensor)])
+        with _lib.on_device(self.device):
+            _lib.check(_lib.lib().pssr_plan_create(arr, len(self.ops), self.dtype, ctypes.byref(h)), "pssr_plan_create")
         self.handle = h
         return self
 
     def run(self, first=None, count=None):
         if self.handle is None:
             raise RuntimeError("plan not finalized")
-        st = _lib.current_stream_ptr()
-        if first is None:
-            _lib.check(_lib.lib().pssr_plan_run(self.handle, st), "pssr_plan_run")
-        else:
-            _lib.check(_lib.lib().pssr_plan_run_range(self.handle, first, count, st), "pssr_plan_run_range")
+        with _lib.on_device(self.device):
+            st = _lib.current_stream_ptr(self.device)
+            if first is None:
+                _lib.check(_lib.lib().pssr_plan_run(self.handle, st), "pssr_plan_run")
+            else:
+                _lib.check(_lib.lib().pssr_plan_run_range(self.handle, first, count, st), "pssr_plan_run_range")
 
     def __len__(self):
         return len(self.ops)

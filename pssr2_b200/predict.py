@@ -8,6 +8,7 @@ validation items are sharded tile-wise across ranks.
 """
 import math
 import os
+from collections.abc import Mapping
 
 import numpy as np
 import torch
@@ -53,6 +54,58 @@ def _batch(dataset, idxs, device, want_hr_u8, tile_index0=None):
     return lr, (hr[:, c:c + 1].clamp(0, 255).to(torch.uint8) if want_hr_u8 else None)
 
 
+def _shares(dataset, n_items):
+    """Item range [lo, hi) of this rank and the item count of every rank.  Sliding datasets are split at sheet boundaries when
+    there are at least as many sheets as ranks, so that a rank only uploads, predicts and stitches its own sheets (SURVEY.md
+    8e); otherwise contiguous balanced blocks of tiles."""
+    w, r = D.world_size(), D.rank()
+    runs = dataset.sheet_item_counts() if (w > 1 and hasattr(dataset, "sheet_item_counts") and hasattr(dataset, "tiles")) else None
+    if runs is not None and len(runs) >= w and sum(c for _, c in runs) == n_items:
+        counts = [c for _, c in runs]
+        spans = [D.shard_groups(counts, k, w) for k in range(w)]
+        return spans[r][2], spans[r][3], [sp[3] - sp[2] for sp in spans]
+    spans = [D.shard_bounds(n_items, k, w) for k in range(w)]
+    return spans[r][0], spans[r][1], [hi - lo for lo, hi in spans]
+
+
+class TilePreds(Mapping):
+    """What ``predict_images(..., keep_on_device=True)`` returns: the reference's ``dict[name -> uint8 [1, H, W]]`` view of
+    predictions that stay in HBM.  ``reassemble_sheets`` reads the device batches directly (no tile ever visits the host);
+    indexing by name copies that batch to the host on first use."""
+
+    def __init__(self):
+        self.names = []            # validation order
+        self.batches = []          # device uint8 [n, 1, H, W]
+        self._where = {}           # name -> (batch index, row)
+        self._host = {}
+
+    def append(self, names, batch):
+        for k, nme in enumerate(names):
+            self._where[nme] = (len(self.batches), k)
+        self.names += list(names)
+        self.batches.append(batch)
+
+    def device_tiles(self, names):
+        """uint8 [len(names), H, W] on the device, in the given order (one gather, or a view when the names are one batch run)."""
+        loc = [self._where[nme] for nme in names]
+        b0 = loc[0][0]
+        if all(b == b0 for b, _ in loc) and [k for _, k in loc] == list(range(loc[0][1], loc[0][1] + len(loc))):
+            return self.batches[b0][loc[0][1]:loc[0][1] + len(loc), 0]
+        return torch.stack([self.batches[b][k, 0] for b, k in loc])
+
+    def __getitem__(self, name):
+        b, k = self._where[name]
+        if b not in self._host:
+            self._host[b] = self.batches[b].cpu().numpy()
+        return self._host[b][k]
+
+    def __iter__(self):
+        return iter(self.names)
+
+    def __len__(self):
+        return len(self.names)
+
+
 def _to_device(model, device):
     """model.to(device) without walking every parameter when the model already lives there."""
     want, p = torch.device(device), next(model.parameters(), None)
@@ -61,26 +114,26 @@ def _to_device(model, device):
         model.to(device)
 
 
-def _save_tif(path, arr):
-    from PIL import Image
-    Image.fromarray(np.asarray(arr).reshape(arr.shape[-2:])).save(path, format="TIFF")
-
-
 def predict_images(model: nn.Module, dataset, device: str = "cuda", batch_size=None, out_dir: str = "preds", norm: bool = False,
-                   prefix: str = None, dataloader_kwargs=None, callbacks=None):
+                   prefix: str = None, dataloader_kwargs=None, callbacks=None, keep_on_device: bool = False):
     r"""Predicts high-resolution images from low-resolution images (pssr/predict.py:11-83).
 
     Same arguments and return value as the reference (``dict[name -> uint8 [1,H,W]]`` iff ``out_dir`` is None,
     else ``{out_dir}/{prefix_}{name}.tif`` files).  ``device`` must be a CUDA device; ``dataloader_kwargs`` is
     accepted for compatibility (there is no DataLoader: batches are generated on the device).
-    Under torchrun each rank predicts a contiguous share of ``dataset.val_idx`` and rank 0 receives all images."""
+    Under torchrun each rank predicts a contiguous share of ``dataset.val_idx`` (whole sheets of a sliding dataset where
+    possible) and rank 0 receives all images.  ``keep_on_device=True`` (with ``out_dir=None``) returns a :class:`TilePreds`
+    mapping whose tiles stay in HBM -- every rank its own share -- for :func:`pssr2_b200.util.reassemble_sheets`."""
     batch_size = 1 if batch_size is None else batch_size
     if norm and dataset.is_lr:
         raise ValueError("Dataset must be paired with high-low-resolution images for normalization.")
     if not str(device).startswith("cuda"):
         raise RuntimeError("pssr2_b200.predict_images runs on CUDA devices only (no CPU fallback); pass device='cuda'")
+    writer = None
     if out_dir:
         os.makedirs(out_dir, exist_ok=True)
+        from .io import TiffWriter
+        writer = TiffWriter()
     callbacks, callback_locals = _get_callbacks(callbacks)
     _to_device(model, device)
     model.eval()
@@ -89,8 +142,11 @@ def predict_images(model: nn.Module, dataset, device: str = "cuda", batch_size=N
     # `dataset.rank_local = True`: the dataset already holds only this rank's share (pre-sharded ingest, weak scaling): no
     # sharding of val_idx and no gather -- every rank returns / writes its own images
     rank_local = bool(getattr(dataset, "rank_local", False))
-    lo, hi = (0, len(val_idx)) if rank_local else D.shard_range(len(val_idx))
+    lo, hi, counts = (0, len(val_idx), [len(val_idx)]) if rank_local else _shares(dataset, len(val_idx))
     outs = {}
+    if keep_on_device and (out_dir or callbacks):
+        raise ValueError("keep_on_device=True returns device-resident tiles: it needs out_dir=None and no callbacks")
+    dpreds = TilePreds() if keep_on_device else None
     dev = torch.device(device)
     cur = torch.cuda.current_stream(dev)
     down = torch.cuda.Stream(device=dev)          # device -> pinned host copies run beside the next batch's kernels
@@ -103,7 +159,7 @@ def predict_images(model: nn.Module, dataset, device: str = "cuda", batch_size=N
         for batch_idx, image_idx in enumerate(pos):
             name = dataset._get_name(image_idx)   # reference quirk: the POSITION in val_idx names the file (predict.py:69-73)
             if out_dir:
-                _save_tif(f"{out_dir}/{prefix + '_' if prefix else ''}{name}.tif", hr_hat[batch_idx])
+                writer.write(f"{out_dir}/{prefix + '_' if prefix else ''}{name}.tif", hr_hat[batch_idx])   # encoded off-thread
             else:
                 outs[name] = hr_hat[batch_idx]
             for idx, callback in enumerate(callbacks):
@@ -114,7 +170,7 @@ def predict_images(model: nn.Module, dataset, device: str = "cuda", batch_size=N
 
     # under torchrun with NCCL the predicted tiles travel GPU -> GPU: every rank keeps its uint8 batches on the device, rank 0
     # gathers them with one collective over NVLink and reads them back once (no pickling of host arrays)
-    nccl_gather = (out_dir is None and not rank_local and D.is_dist() and torch.distributed.get_backend() == "nccl"
+    nccl_gather = (out_dir is None and not rank_local and not keep_on_device and D.is_dist() and torch.distributed.get_backend() == "nccl"
                    and D.world_size() > 1 and not callbacks)
     kept = []
     starts = range(lo, hi, batch_size)
@@ -130,6 +186,9 @@ def predict_images(model: nn.Module, dataset, device: str = "cuda", batch_size=N
             crop_res = dataset.crop_res if not dataset.is_lr else dataset.crop_res * (hr_hat.shape[-1] // lr.shape[-1])
             # own copy of the batch: the plan's output buffer is overwritten by the next forward while this one travels
             dbuf = hr_hat[:, :, :crop_res, :crop_res].clone(memory_format=torch.contiguous_format)
+            if keep_on_device:
+                dpreds.append([dataset._get_name(p) for p in pos], dbuf)
+                continue
             if nccl_gather:
                 kept.append(dbuf)
                 continue
@@ -146,10 +205,14 @@ def predict_images(model: nn.Module, dataset, device: str = "cuda", batch_size=N
             pending = (done, host, pos, dbuf)
         if pending is not None:
             finish(pending)
+    if writer is not None:
+        writer.close()                    # every file is on disk when the call returns
+    if keep_on_device:
+        return dpreds
     if nccl_gather:
         shape = kept[0].shape[1:] if kept else (1, dataset.crop_res, dataset.crop_res)
         local = torch.cat(kept, 0) if kept else torch.zeros((0,) + tuple(shape), dtype=torch.uint8, device=dev)
-        allp = D.gather_images_nccl(local, len(val_idx))
+        allp = D.gather_images_nccl(local, len(val_idx), counts)
         src, base = (allp, 0) if allp is not None else (local, lo)          # rank 0: everything; others: their own share
         arr = src.cpu().numpy()
         return {dataset._get_name(base + k): arr[k] for k in range(arr.shape[0])}
@@ -175,7 +238,7 @@ def test_metrics(model: nn.Module, dataset, device: str = "cuda", metrics=["mse"
     model.eval()
 
     val_idx = list(dataset.val_idx)
-    lo, hi = D.shard_range(len(val_idx))
+    lo, hi = D.shard_range(len(val_idx))      # item-0 quirk / per-tile metrics: sheets play no role, balanced blocks
     per_image = {m: [] for m in names}
     want_ssim = "ssim" in names
     dev = torch.device(device)
@@ -227,8 +290,115 @@ def test_metrics(model: nn.Module, dataset, device: str = "cuda", metrics=["mse"
             pending = (done, host, len(pos), hr.shape[-1] * hr.shape[-2], (hr.shape[-2] - 6) * (hr.shape[-1] - 6))
         if pending is not None:
             finish(pending)
+    if avg:
+        # the path's first collective: one all-reduce of [sum per metric ..., count] in float64
+        vec = torch.tensor([sum(per_image[m]) for m in names] + [float(hi - lo)], dtype=torch.float64, device=dev)
+        vec = D.allreduce_vector(vec).cpu()
+        return {m: float(vec[i]) / float(vec[-1]) for i, m in enumerate(names)}
     per_image = D.gather_metric_lists(per_image, names)
-    return {m: (sum(v) / len(v) if avg else v) for m, v in per_image.items()}
+    return {m: v for m, v in per_image.items()}
 
 
 test_metrics.__test__ = False  # "This guy is NOT a test." (reference tests/conftest.py:1-2)
+
+
+def predict_sheets(model: nn.Module, dataset, device: str = "cuda", batch_size: int = None, overlap: int = None, margin: int = 0,
+                   out_dir: str = None, norm: bool = False, prefix: str = None):
+    r"""``predict_images`` + ``reassemble_sheets`` (pssr/predict.py:11-83, pssr/util.py:54-108) as ONE device-resident pipeline
+    for sliding datasets: every rank uploads, predicts and stitches its own sheets -- the tiles never leave HBM -- and only the
+    stitched uint8 sheets travel (device -> pinned host on a side stream; under torchrun rank 0 receives every sheet over NCCL).
+
+    ``overlap`` / ``margin``: as in ``reassemble_sheets`` with ``lr_scale=1`` on the predicted tiles, in pixels of the
+    PREDICTION (default overlap: the dataset's own tile overlap, scaled in LR mode).  Returns the list of stitched sheets
+    ``uint8 [stacks, rows*step+overlap, cols*step+overlap]`` in sheet order (rank 0: all sheets; other ranks: their own, None
+    elsewhere) or writes ``{out_dir}/{prefix_}{sheet}.tif``."""
+    if not hasattr(dataset, "tiles") or not hasattr(dataset, "_tiles_y"):
+        raise TypeError("predict_sheets needs a SlidingDataset (tiled sheets)")
+    if not str(device).startswith("cuda"):
+        raise RuntimeError("pssr2_b200.predict_sheets runs on CUDA devices only (no CPU fallback); pass device='cuda'")
+    if norm and dataset.is_lr:
+        raise ValueError("Dataset must be paired with high-low-resolution images for normalization.")
+    runs = dataset.sheet_item_counts()
+    n_val = len(dataset.val_idx)
+    if runs is None or any(c != dataset.tiles[i] * dataset.slices[i] for i, c in runs):
+        raise ValueError("predict_sheets stitches whole sheets: construct the dataset with val_split=1")
+    batch_size = 1 if batch_size is None else batch_size
+    if out_dir:
+        os.makedirs(out_dir, exist_ok=True)
+    _to_device(model, device)
+    model.eval()
+    dev = torch.device(device)
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    w, r = D.world_size(), D.rank()
+    counts = [c for _, c in runs]
+    spans = [D.shard_groups(counts, k, w) for k in range(w)] if len(runs) >= w else None
+    if spans is None:
+        raise ValueError(f"predict_sheets shards by whole sheets: {len(runs)} sheets cannot feed {w} ranks")
+    owners = [next(k for k in range(w) if spans[k][0] <= g < spans[k][1]) for g in range(len(runs))]
+    g0, g1, lo, _ = spans[r]
+    val_idx = list(dataset.val_idx)
+    down = torch.cuda.Stream(device=dev)
+    local, shapes, hosts = {}, [None] * len(runs), {}
+    pos = lo
+    with torch.no_grad(), torch.cuda.device(dev):
+        cur = torch.cuda.current_stream(dev)
+        for g in range(len(runs)):
+            img, cnt = runs[g]
+            n_sl = dataset.slices[img]
+            ty = dataset._tiles_y[img]
+            tx = dataset.tiles[img] // ty
+            scale_out = 1
+            if g0 <= g < g1:
+                tiles_dev = None
+                for start in range(pos, pos + cnt, batch_size):
+                    ps = list(range(start, min(start + batch_size, pos + cnt)))
+                    lr, hr8 = _batch(dataset, [val_idx[p] for p in ps], device, want_hr_u8=norm)
+                    hr_hat = _pred_u8(model, lr)
+                    if norm:
+                        _, hh = ops.normalize_preds_u8(hr8[:, 0], hr_hat[:, 0])
+                        hr_hat = hh[:, None]
+                    crop_res = dataset.crop_res if not dataset.is_lr else dataset.crop_res * (hr_hat.shape[-1] // lr.shape[-1])
+                    if tiles_dev is None:
+                        tiles_dev = torch.empty(cnt, crop_res, crop_res, dtype=torch.uint8, device=dev)
+                        scale_out = hr_hat.shape[-1] // lr.shape[-1] if dataset.is_lr else 1
+                    tiles_dev[start - pos:start - pos + len(ps)] = hr_hat[:, 0, :crop_res, :crop_res]
+                pos += cnt
+                # item order inside a sheet is tile-major, slice-minor (data.py:236-256); the stitch wants [slice][tile]
+                if n_sl > 1:
+                    tiles_dev = tiles_dev.view(tx * ty, n_sl, *tiles_dev.shape[1:]).transpose(0, 1).reshape(cnt, *tiles_dev.shape[1:])
+                ov = (dataset.hr_res - dataset.stride) * scale_out if overlap is None else overlap
+                sheet = ops.stitch(tiles_dev, tx, ty, ov, margin)
+                local[g] = sheet
+                if r == 0 or not D.is_dist():
+                    # rank 0's own sheets go to pinned host memory beside the next sheet's kernels
+                    host = torch.empty(sheet.shape, dtype=torch.uint8, pin_memory=True)
+                    ready = torch.cuda.Event()
+                    ready.record(cur)
+                    with torch.cuda.stream(down):
+                        down.wait_event(ready)
+                        host.copy_(sheet, non_blocking=True)
+                    sheet.record_stream(down)
+                    hosts[g] = host
+            # every rank knows every sheet's stitched shape (needed to post the receives)
+            T = dataset.crop_res * (1 if not dataset.is_lr else max(1, getattr(model, "scale", 1)))
+            ovg = (dataset.hr_res - dataset.stride) * (T // dataset.crop_res) if overlap is None else overlap
+            shapes[g] = (n_sl, tx * (T - ovg) + ovg, ty * (T - ovg) + ovg)
+    gathered = D.gather_sheets(local, owners, shapes, dev) if D.is_dist() and w > 1 else None
+    down.synchronize()
+    out = []
+    for g in range(len(runs)):
+        if g in hosts:
+            out.append(hosts[g].numpy())
+        elif gathered is not None and gathered[g] is not None:
+            out.append(gathered[g].cpu().numpy())
+        else:
+            out.append(None)
+    if out_dir:
+        from .io import write_tiff
+        for g, arr in enumerate(out):
+            if arr is not None:
+                name = dataset.hr_files[runs[g][0]].split("/")[-1].split(".")[0]
+                write_tiff(f"{out_dir}/{prefix + '_' if prefix else ''}{name}.tif", arr)
+        return None
+    return out

@@ -74,25 +74,23 @@ def _sheet_shapes(lr_path):
     dataset from pssr2_b200.data (in-memory sheets)."""
     if isinstance(lr_path, dict):
         return {k: (tuple(v) if isinstance(v, (tuple, list)) else tuple(np.asarray(v).shape)) for k, v in lr_path.items()}
-    if hasattr(lr_path, "hr_files") and hasattr(lr_path, "_sheets"):
-        return {n.split("/")[-1].split(".")[0]: tuple(s.shape) for n, s in zip(lr_path.hr_files, lr_path._sheets)}
+    if hasattr(lr_path, "hr_files") and hasattr(lr_path, "_shapes"):
+        return {n.split("/")[-1].split(".")[0]: (f,) + tuple(hw) for n, f, hw in zip(lr_path.hr_files, lr_path._frames_total, lr_path._shapes)}
     files = glob.glob(f"{lr_path}/*.tif", recursive=True)
     if len(files) == 0:
         raise FileExistsError("No files exist in lr_path.")
-    from PIL import Image
-    out = {}
-    for f in files:
-        im = Image.open(f)
-        out[f.split("/")[-1].split(".")[0]] = (getattr(im, "n_frames", 1), im.height, im.width)
-    return out
+    from .io import tiff_probe
+    return {f.split("/")[-1].split(".")[0]: tiff_probe(f)[:3] for f in files}
 
 
 def reassemble_sheets(pred_path, lr_path, lr_scale: int, overlap: int = 0, margin: int = 0, out_dir: str = "sheets"):
     r"""Reassembles image sheets from predicted tiles (pssr/util.py:54-108) with the CUDA stitch kernel.
 
-    ``pred_path``: dict of named tiles from :func:`predict_images` (or a directory of tile TIFFs);
+    ``pred_path``: dict of named tiles from :func:`predict_images` (or a directory of tile TIFFs), or the device-resident
+    ``TilePreds`` of ``predict_images(..., keep_on_device=True)`` -- then no tile visits the host, only the stitched sheets do;
     ``lr_path``: directory of low-resolution sheets, or -- for in-memory work -- a dict
-    ``{sheet_name: shape}`` / the dataset itself.  Returns the list of uint8 sheets if ``out_dir`` is None."""
+    ``{sheet_name: shape}`` / the dataset itself.  Returns the list of uint8 sheets if ``out_dir`` is None (sheets without
+    tiles in ``pred_path`` -- another rank's share -- are skipped, as in the reference)."""
     if margin > overlap:
         raise ValueError(f"The value of margin cannot be greater than overlap. Given {margin} and {overlap} respectively.")
     shapes = _sheet_shapes(lr_path)
@@ -100,7 +98,12 @@ def reassemble_sheets(pred_path, lr_path, lr_scale: int, overlap: int = 0, margi
         os.makedirs(out_dir, exist_ok=True)
     outs = []
     for sheet, lr_shape in shapes.items():
-        if type(pred_path) is dict:
+        if hasattr(pred_path, "device_tiles"):
+            files = sorted([f for f in pred_path.keys() if "_".join(f.split("_")[:-2]) == sheet], key=_sort_tiles)
+            if len(files) == 0:
+                continue
+            batched = pred_path.device_tiles(files)
+        elif isinstance(pred_path, dict):
             files = sorted([f for f in pred_path.keys() if "_".join(f.split("_")[:-2]) == sheet], key=_sort_tiles)
             tiles = [pred_path[f] for f in files]
             if len(tiles) == 0:
@@ -110,18 +113,17 @@ def reassemble_sheets(pred_path, lr_path, lr_scale: int, overlap: int = 0, margi
             else:
                 batched = torch.as_tensor(np.asarray([np.asarray(t).squeeze() for t in tiles])).cuda()
         else:
-            from PIL import Image
+            from .io import read_tiff
             files = sorted(glob.glob(f"{pred_path}/{sheet}*"), key=_sort_tiles)
-            batched = torch.as_tensor(np.asarray([np.asarray(Image.open(f)).squeeze() for f in files])).cuda()
+            batched = torch.as_tensor(np.asarray([read_tiff(f).squeeze() for f in files])).cuda()
         T = batched.shape[1]
         n_rows = (lr_shape[1] * lr_scale - T) // (T - overlap * lr_scale) + 1          # util.py:96
         n_cols = (lr_shape[2] * lr_scale - batched.shape[2]) // (batched.shape[2] - overlap * lr_scale) + 1
         stacks = batched.shape[0] // n_rows // n_cols
         image = ops.stitch(batched[:stacks * n_rows * n_cols], n_rows, n_cols, overlap * lr_scale, margin).cpu().numpy()
         if out_dir:
-            from PIL import Image
-            ims = [Image.fromarray(p) for p in image]
-            ims[0].save(f"{out_dir}/{sheet}.tif", format="TIFF", save_all=True, append_images=ims[1:])
+            from .io import write_tiff
+            write_tiff(f"{out_dir}/{sheet}.tif", image)
         else:
             outs.append(image)
     if out_dir is None:

@@ -41,6 +41,20 @@ for n_items in (11, 1):
         assert allp.shape == (n_items, 1, 2, 3) and allp[:, 0, 0, 0].tolist() == list(range(n_items)), allp.shape
     else:
         assert allp is None
+# the path's two collectives in their product form: the [sums..., count] all-reduce of test_metrics(avg=True) and the stitched-
+# sheet gather of predict_sheets (three sheets of different shapes, rank 1 owns the last two)
+vec = D.allreduce_vector(torch.tensor([1.0 + r, 2.0, float(r)], dtype=torch.float64))
+assert vec.tolist() == [3.0, 4.0, 1.0]
+shapes = [(1, 4, 5), (2, 3, 3), (1, 2, 7)]
+owners = [0, 1, 1]
+local = {s: torch.full(shapes[s], 10 * s + 1, dtype=torch.uint8) for s in range(3) if owners[s] == r}
+got = D.gather_sheets(local, owners, shapes, torch.device("cpu"))
+if r == 0:
+    assert all(g.shape == shapes[s] and int(g.flatten()[0]) == 10 * s + 1 for s, g in enumerate(got))
+else:
+    assert got[0] is None and got[1] is not None and got[2] is not None
+g0, g1, lo3, hi3 = D.shard_groups([100, 100, 100], r, w)
+assert (g0, g1, lo3, hi3) == ((0, 2, 0, 200) if r == 0 else (2, 3, 200, 300)) or (g0, g1) in ((0, 1), (1, 3))
 dist.barrier()
 sys.stdout.write("rank" + str(r) + "-ok\n"); sys.stdout.flush()
 '''
@@ -65,3 +79,21 @@ def test_shard_bounds_properties():
             assert all(edges[i][1] == edges[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in edges]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_groups_properties():
+    """Sheet-aligned sharding: every group lands on exactly one rank, runs are contiguous, and the item load is as even as whole
+    groups allow (never worse than one group off the ideal prefix split)."""
+    from pssr2_b200.dist import shard_groups
+    for counts in ([100] * 8, [100] * 3, [5, 50, 5, 50, 5], [1, 2, 3, 4, 5, 6, 7], [10], [7, 0, 7]):
+        for w in (1, 2, 3, 8):
+            if w > len(counts):
+                continue
+            spans = [shard_groups(counts, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == len(counts)
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert all(s[2] == sum(counts[:s[0]]) and s[3] == sum(counts[:s[1]]) for s in spans)
+            ideal = sum(counts) / w
+            assert all(abs(spans[k][3] - ideal * (k + 1)) <= max(counts) for k in range(w))
+    spans = [shard_groups([100] * 8, r, 8) for r in range(8)]
+    assert [s[3] - s[2] for s in spans] == [100] * 8

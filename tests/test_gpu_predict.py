@@ -73,7 +73,7 @@ def test_test_metrics_vs_oracle():
             print(f"norm={norm} img{i}: mse {got['mse'][i]:.6g}/{mse:.6g} psnr {got['psnr'][i]:.5f}/{psnr:.5f} ssim {got['ssim'][i]:.6f}/{ssim:.6f}")
             assert abs(got["mse"][i] - mse) <= 1e-3 * mse + 1e-9
             assert abs(got["pixel"][i] - pixel) <= 1e-3 * pixel + 1e-6
-            assert abs(got["psnr"][i] - psnr) <= 1e-2
+            assert abs(got["psnr"][i] - psnr) <= 1e-3
             assert abs(got["ssim"][i] - ssim) <= 1e-3
     # reference quirk: every iteration scores dataset[0] (pssr/predict.py:180)
     q = run_metrics(model, ds, device="cuda", norm=False, avg=False)
