@@ -64,23 +64,25 @@ def test_file_backed_dataset_streams_like_memory(tmp_path):
     from pssr2_b200.predict import predict_images, predict_sheets
     model = _model()
     sheets = _sheets(4)
+    src = tmp_path / "sheets"          # (the datasets glob their directory recursively, like the reference: outputs live elsewhere)
+    src.mkdir()
     for k, v in sheets.items():
-        io.write_tiff(tmp_path / f"{k}.tif", v)
+        io.write_tiff(src / f"{k}.tif", v)
     kw = dict(hr_res=256, lr_scale=4, overlap=64, val_split=1, crappifier=None)
     want = predict_images(model, SlidingDataset(sheets, **kw), device="cuda", batch_size=4, out_dir=None)
-    ds = SlidingDataset(str(tmp_path), extension="tif", **kw)
+    ds = SlidingDataset(str(src), extension="tif", **kw)
     ds.max_resident_bytes = sheets["sheet0"].nbytes          # room for one sheet: the others stream through
     got = predict_images(model, ds, device="cuda", batch_size=4, out_dir=None)
     assert sorted(got) == sorted(want) and all(np.array_equal(got[k], want[k]) for k in want)
     assert sum(s is not None for s in ds._sheets) <= 2
     out = tmp_path / "preds"
-    assert predict_images(model, SlidingDataset(str(tmp_path), extension="tif", **kw), device="cuda", batch_size=3, out_dir=str(out), prefix="p") is None
+    assert predict_images(model, SlidingDataset(str(src), extension="tif", **kw), device="cuda", batch_size=3, out_dir=str(out), prefix="p") is None
     files = sorted(os.listdir(out))
     assert len(files) == len(want) and all(f.startswith("p_") for f in files)
     for k in want:
         assert np.array_equal(io.read_tiff(out / f"p_{k}.tif"), want[k])
     sd = tmp_path / "stitched"
-    predict_sheets(model, SlidingDataset(str(tmp_path), extension="tif", **kw), device="cuda", batch_size=4, margin=8, out_dir=str(sd))
+    predict_sheets(model, SlidingDataset(str(src), extension="tif", **kw), device="cuda", batch_size=4, margin=8, out_dir=str(sd))
     mem = predict_sheets(model, SlidingDataset(sheets, **kw), device="cuda", batch_size=4, margin=8)
     for i in range(4):
         assert np.array_equal(io.read_tiff(sd / f"sheet{i}.tif"), mem[i])
