@@ -410,8 +410,9 @@ __device__ __forceinline__ T load_reflect(const T* frame_base, int sheet_w, int 
 }
 
 // KS: compile-time bound of the filter window (9: scales <= 4, 17: scales <= 8; 0: generic loops)
-template <typename T, int KS>
-__global__ void __launch_bounds__(kCrapThreads, 3) crappify_kernel(const CrapK p) {
+// MINB: CTAs per SM the register allocation aims for (3: 85 registers, no spills; 4: 64 registers, ~70 bytes of spills)
+template <typename T, int KS, int MINB>
+__global__ void __launch_bounds__(kCrapThreads, MINB) crappify_kernel(const CrapK p) {
   extern __shared__ __align__(16) uint8_t csm[];
   const int TL = p.TL;
   int* lead = reinterpret_cast<int*>(csm);                         // [max_rows] byte offset of each staged row
@@ -777,11 +778,16 @@ extern "C" int pssr_crappify(const pssr_crappify_args_t* a, void* stream) {
     const long long blocks = (long long)a->n_tiles * a->lr_frames * p.tiles_per_side * p.tiles_per_side;
     PSSR_REQUIRE(blocks < (1ll << 31), PSSR_EUNSUP, "crappify: too many blocks");
     const int ks = getenv("PSSR_CRAP_GENERIC") != nullptr ? 0 : (p.ksize <= 9 ? 9 : (p.ksize <= 17 ? 17 : 0));
-#define PSSR_CRAP_LAUNCH(TT, KK)                                                                                              \
+    static const int minb = getenv("PSSR_CRAP_MINB") != nullptr ? atoi(getenv("PSSR_CRAP_MINB")) : 3;
+#define PSSR_CRAP_LAUNCH1(TT, KK, MB)                                                                                         \
   do {                                                                                                                        \
     static PerDeviceOnce attr;                                                                                                \
-    if (attr.first()) PSSR_CHECK_CUDA(cudaFuncSetAttribute(crappify_kernel<TT, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-    crappify_kernel<TT, KK><<<(unsigned)blocks, kCrapThreads, smem, st>>>(p);                                                 \
+    if (attr.first()) PSSR_CHECK_CUDA(cudaFuncSetAttribute(crappify_kernel<TT, KK, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+    crappify_kernel<TT, KK, MB><<<(unsigned)blocks, kCrapThreads, smem, st>>>(p);                                             \
+  } while (0)
+#define PSSR_CRAP_LAUNCH(TT, KK)                                                                                              \
+  do {                                                                                                                        \
+    if (minb == 4) PSSR_CRAP_LAUNCH1(TT, KK, 4); else PSSR_CRAP_LAUNCH1(TT, KK, 3);                                            \
   } while (0)
     if (a->elem_bytes == 1) {
       if (ks == 9) PSSR_CRAP_LAUNCH(uint8_t, 9); else if (ks == 17) PSSR_CRAP_LAUNCH(uint8_t, 17); else PSSR_CRAP_LAUNCH(uint8_t, 0);
@@ -789,6 +795,7 @@ extern "C" int pssr_crappify(const pssr_crappify_args_t* a, void* stream) {
       if (ks == 9) PSSR_CRAP_LAUNCH(uint16_t, 9); else if (ks == 17) PSSR_CRAP_LAUNCH(uint16_t, 17); else PSSR_CRAP_LAUNCH(uint16_t, 0);
     }
 #undef PSSR_CRAP_LAUNCH
+#undef PSSR_CRAP_LAUNCH1
     count_launch();
     PSSR_CHECK_CUDA(cudaGetLastError());
   }

@@ -26,15 +26,20 @@ __device__ __forceinline__ long long warp_sum(long long v) {
 
 // -------------------------------------------------------------------------- SSIM + SSE
 // Row-streaming design.  A CTA of 128 threads owns a strip of 512 input columns (4 per thread, one 32-bit load per image and
-// row) and a chunk of output rows.  Per input row every thread updates the VERTICAL 7-row running sums of a, b, a^2, b^2, ab
-// of its four columns (add the new row, subtract the row seven above: 8 integer instructions per column), publishes them
-// to shared memory (double-buffered, one barrier per row), slides the HORIZONTAL 7-window over its own four columns and the
-// six to the right, and evaluates the SSIM expression for four window positions.  Every input byte is read from HBM once
-// (the row seven above comes from L1/L2), all window sums are exact integers:
-//   S = (2 s0 s1 + c1)(2 (49 s4 - s0 s1) + c2) / ((s0^2 + s1^2 + c1)(49 (s2 + s3) - s0^2 - s1^2 + c2))
-// with s0..s4 the 49-pixel sums of a, b, a^2, b^2, ab, c1 = 49^2 C1, c2 = 49*48 C2 (skimage structural_similarity with
-// sample covariance: the 1/49^2 and 1/(49*48) factors cancel) -- two int->double conversions per factor pair and ONE
-// double division per window position instead of six.
+// row) and a chunk of output rows.  Per input row every thread updates the VERTICAL 7-row running sums of a, b, a^2 + b^2 and
+// ab of its four columns (add the new row, subtract the row seven above), publishes them to shared memory (double-buffered,
+// one barrier per row), slides the HORIZONTAL 7-window over its own four columns and the six to the right, and evaluates the
+// SSIM expression for four window positions.  Every input byte is read from HBM once (the row seven above comes from L1/L2).
+//   S = (2 s0 s1 + c1)(2 (49 s4 - s0 s1) + c2) / ((s0^2 + s1^2 + c1)(49 s23 - s0^2 - s1^2 + c2))
+// with s0, s1, s23, s4 the 49-pixel sums of a, b, a^2 + b^2, ab, c1 = 49^2 C1, c2 = 49*48 C2 (skimage structural_similarity
+// with sample covariance: the 1/49^2 and 1/(49*48) factors cancel).
+// Arithmetic.  Everything that cancels -- the window sums, 49 s4 - s0 s1, 49 s23 - s0^2 - s1^2 -- is EXACT int32 (all values
+// < 2^31); the four factors are converted to float once (relative 6e-8, after the cancellation), the quotient takes one
+// MUFU.RCP plus a Newton step, and a thread adds at most 16 rows x 4 windows in float before promoting to its double
+// accumulator.  Per-window error ~2e-7 with random sign: the image mean agrees with the float64 statement to ~1e-8 (asserted
+// <= 1e-6 in tests/test_gpu_ops.py; the tolerance of the path is 1e-3).  a^2 and b^2 only ever appear as a sum, so one running
+// sum serves both; the squares enter as (new - old)(new + old).  Round 1 evaluated the expression in double with five running
+// sums: 78 instructions per pixel, issue-bound at 0.38 TB/s; this version executes ~45.
 static constexpr int kMetThreads = 128;
 static constexpr int kMetCols = kMetThreads * 4;     // input columns per strip
 static constexpr int kMetStep = kMetCols - 8;        // output columns a strip owns (multiple of 4; the last strip takes up to +2 more)
@@ -59,7 +64,7 @@ template <bool VEC>
 __global__ void __launch_bounds__(kMetThreads) metric_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int h, int w,
                                                              int rows_per_chunk, int want_ssim, long long* __restrict__ sse_part,
                                                              double* __restrict__ ssim_part) {
-  __shared__ __align__(16) int vs[2][5][kMetCols + 8];
+  __shared__ __align__(16) int vs[2][4][kMetCols + 8];
   __shared__ double red_d[kMetThreads / 32];
   __shared__ long long red_l[kMetThreads / 32];
   const int strip = blockIdx.x, chunk = blockIdx.y, img = blockIdx.z;
@@ -77,7 +82,7 @@ __global__ void __launch_bounds__(kMetThreads) metric_kernel(const uint8_t* __re
   const uint8_t* pb = b + (size_t)img * h * w;
   if (tid < 8) {
 #pragma unroll
-    for (int q = 0; q < 5; ++q) { vs[0][q][kMetCols + tid] = 0; vs[1][q][kMetCols + tid] = 0; }
+    for (int q = 0; q < 4; ++q) { vs[0][q][kMetCols + tid] = 0; vs[1][q][kMetCols + tid] = 0; }
   }
   auto load4 = [&](const uint8_t* p, int y) -> uint32_t {
     if (VEC) {
@@ -89,14 +94,20 @@ __global__ void __launch_bounds__(kMetThreads) metric_kernel(const uint8_t* __re
       if (x0 + j < w) v |= (uint32_t)__ldg(p + (size_t)y * w + x0 + j) << (8 * j);
     return v;
   };
-  int V[5][4];
+  // columns this thread owns for the SSE / scores as window positions: masks instead of per-pixel compares
+  bool own[4], outp[4];
 #pragma unroll
-  for (int q = 0; q < 5; ++q)
+  for (int j = 0; j < 4; ++j) { own[j] = x0 + j < own_x_end; outp[j] = x0 + j < out_x_end; }
+  int V[4][4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
 #pragma unroll
     for (int j = 0; j < 4; ++j) V[q][j] = 0;
   long long sse = 0;
   double acc = 0.0;
-  const double c1 = 2401.0 * (0.01 * 255.0) * (0.01 * 255.0), c2 = 2352.0 * (0.03 * 255.0) * (0.03 * 255.0);
+  float accf = 0.f;
+  int rows_in_accf = 0;
+  const float c1 = (float)(2401.0 * (0.01 * 255.0) * (0.01 * 255.0)), c2 = (float)(2352.0 * (0.03 * 255.0) * (0.03 * 255.0));
   for (int y = y_begin; y < y_end; ++y) {
     const uint32_t na = load4(pa, y), nb = load4(pb, y);
     uint32_t oa = 0, ob = 0;
@@ -105,25 +116,26 @@ __global__ void __launch_bounds__(kMetThreads) metric_kernel(const uint8_t* __re
     int sq_row = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int an = (int)((na >> (8 * j)) & 255u), bn = (int)((nb >> (8 * j)) & 255u);
-      const int ao = (int)((oa >> (8 * j)) & 255u), bo = (int)((ob >> (8 * j)) & 255u);
-      V[0][j] += an - ao;
-      V[1][j] += bn - bo;
-      V[2][j] += an * an - ao * ao;
-      V[3][j] += bn * bn - bo * bo;
-      V[4][j] += an * bn - ao * bo;
-      if (x0 + j < own_x_end) sq_row += (an - bn) * (an - bn);
+      const int an = (int)__byte_perm(na, 0, 0x4440 + j), bn = (int)__byte_perm(nb, 0, 0x4440 + j);
+      const int ao = (int)__byte_perm(oa, 0, 0x4440 + j), bo = (int)__byte_perm(ob, 0, 0x4440 + j);
+      const int da = an - ao, db = bn - bo;
+      V[0][j] += da;
+      V[1][j] += db;
+      V[2][j] += da * (an + ao) + db * (bn + bo);       // a^2 + b^2, new minus old
+      V[3][j] += an * bn - ao * bo;
+      const int e = an - bn;
+      if (own[j]) sq_row += e * e;
     }
     if (y < own_y_end) sse += sq_row;
     const int oy = y - 6;                       // window rows [oy, oy+6] are summed in V now
     if (!want_ssim || oy < oy0 || oy >= oy1) continue;      // uniform across the CTA
     const int pbuf = y & 1;
 #pragma unroll
-    for (int q = 0; q < 5; ++q) *reinterpret_cast<int4*>(&vs[pbuf][q][4 * tid]) = make_int4(V[q][0], V[q][1], V[q][2], V[q][3]);
+    for (int q = 0; q < 4; ++q) *reinterpret_cast<int4*>(&vs[pbuf][q][4 * tid]) = make_int4(V[q][0], V[q][1], V[q][2], V[q][3]);
     __syncthreads();
-    int H[5][4];
+    int H[4][4];
 #pragma unroll
-    for (int q = 0; q < 5; ++q) {
+    for (int q = 0; q < 4; ++q) {
       const int4 r0 = *reinterpret_cast<const int4*>(&vs[pbuf][q][4 * tid + 4]);
       const int2 r1 = *reinterpret_cast<const int2*>(&vs[pbuf][q][4 * tid + 8]);
       const int v0 = V[q][0], v1 = V[q][1], v2 = V[q][2], v3 = V[q][3];
@@ -135,23 +147,21 @@ __global__ void __launch_bounds__(kMetThreads) metric_kernel(const uint8_t* __re
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if (x0 + j < out_x_end) {
-        const int s0 = H[0][j], s1 = H[1][j];
-        const int s01 = s0 * s1;
-        const int sq = s0 * s0 + s1 * s1;
-        const int cv = 49 * H[4][j] - s01;
-        const int vr = 49 * (H[2][j] + H[3][j]) - sq;
-        const double A1 = (double)(2 * s01) + c1, A2 = (double)(2 * cv) + c2;
-        const double B1 = (double)sq + c1, B2 = (double)vr + c2;
-        // N / D with one float reciprocal and one Newton step in double (relative error ~1e-14) instead of a full IEEE
-        // double division (~20 fp64-pipe instructions): the quotient is a mean over >= 10^5 windows, tolerance 1e-3
-        const double N = A1 * A2, D = B1 * B2;
-        const double r0 = (double)__frcp_rn((float)D);
-        const double r1 = fma(fma(-D, r0, 1.0), r0, r0);
-        acc += N * r1;
-      }
+      const int s0 = H[0][j], s1 = H[1][j];
+      const int s01 = s0 * s1;
+      const int sq = s0 * s0 + s1 * s1;
+      const int cv = 49 * H[3][j] - s01;
+      const int vr = 49 * H[2][j] - sq;
+      const float A1 = fmaf(2.f, (float)s01, c1), A2 = fmaf(2.f, (float)cv, c2);
+      const float B1 = (float)sq + c1, B2 = (float)vr + c2;
+      const float N = A1 * A2, D = B1 * B2;
+      float r = __frcp_rn(D);
+      r = fmaf(fmaf(-D, r, 1.f), r, r);          // one Newton step: ~1 ulp
+      if (outp[j]) accf = fmaf(N, r, accf);
     }
+    if (++rows_in_accf == 16) { acc += (double)accf; accf = 0.f; rows_in_accf = 0; }
   }
+  acc += (double)accf;
   acc = warp_sum(acc);
   sse = warp_sum(sse);
   const int warp = tid >> 5, lane = tid & 31;
