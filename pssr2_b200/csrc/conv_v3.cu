@@ -1055,6 +1055,14 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
       }
       const int buf = it & 1;
       const uint32_t par = (uint32_t)(it >> 1) & 1u;
+      if (ROWS && !TAIL && p.resid != nullptr && gvalid) {
+        // the residual rows of this unit start towards L2 while the MMAs are still running (the epilogue would otherwise wait
+        // for DRAM with the accumulators already done)
+        for (int mt = eg; mt < T; mt += 2) {
+          const uint16_t* rp = p.resid + (((size_t)gn * p.H + gy0 + mt) * p.W + gx0 + row) * p.resid_cstride + p.resid_choff + n_tile * block_n;
+          for (int b = 0; b < block_n; b += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + b) : "memory");
+        }
+      }
       mbar_wait(t_full(buf), par);
       tc_fence_after();
       if (warp == 4 && it < 31) V3_TRACE(64 + 2 * it);
@@ -1226,10 +1234,15 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
             // ---- 16-bit tile [32 pixels x 64 channels] -> swizzled shared memory -> one TMA store (two when the 32 flat
             // pixels wrap to the next image row); padding / out-of-range positions are clipped by the TMA unit ----------
             const uint32_t stg = smem_base + p.stage_off + (uint32_t)(warp - 4) * 4096u;
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous tile has left the buffer
-            __syncwarp();
             const uint32_t taddr2 = lane_addr + (uint32_t)(buf * 256 + mt * block_n + c_lo);
             const int nb = n_tile * block_n + c_lo;
+            // pass 0: the 16-bit tile; pass 1 (out_lo): what its rounding dropped, through the same staging buffer -- the accumulator
+            // is read from TMEM again rather than keeping 32 more registers alive
+            const int n_pass = p.out_lo != nullptr ? 2 : 1;
+#pragma unroll 1
+            for (int pass = 0; pass < n_pass; ++pass) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous tile has left the buffer
+            __syncwarp();
 #pragma unroll
             for (int cq = 0; cq < 2; ++cq) {
               uint32_t v[32];
@@ -1270,15 +1283,25 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
 #pragma unroll
               for (int j4 = 0; j4 < 4; ++j4) {
                 const uint32_t chunk = (uint32_t)(cq * 4 + j4) ^ (uint32_t)(lane & 7);
-                v3_st_shared_v4(stg + (uint32_t)lane * 128u + chunk * 16u, v3_pack2(f[8 * j4 + 0], f[8 * j4 + 1], p.fp16, relu_pack),
-                                v3_pack2(f[8 * j4 + 2], f[8 * j4 + 3], p.fp16, relu_pack), v3_pack2(f[8 * j4 + 4], f[8 * j4 + 5], p.fp16, relu_pack),
-                                v3_pack2(f[8 * j4 + 6], f[8 * j4 + 7], p.fp16, relu_pack));
+                uint32_t w[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) w[k] = v3_pack2(f[8 * j4 + 2 * k], f[8 * j4 + 2 * k + 1], p.fp16, relu_pack);
+                if (pass == 1) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const float2 hq = v3_unpack2(w[k], p.fp16);
+                    const float a0 = relu_pack ? fmaxf(f[8 * j4 + 2 * k], 0.f) : f[8 * j4 + 2 * k];
+                    const float a1 = relu_pack ? fmaxf(f[8 * j4 + 2 * k + 1], 0.f) : f[8 * j4 + 2 * k + 1];
+                    w[k] = v3_pack2(a0 - hq.x, a1 - hq.y, p.fp16, false);
+                  }
+                }
+                v3_st_shared_v4(stg + (uint32_t)lane * 128u + chunk * 16u, w[0], w[1], w[2], w[3]);
               }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0 && !(p.dbg & 1)) {
-              const CUtensorMap* tmo = p.tmaps + kTmOut;
+              const CUtensorMap* tmo = p.tmaps + (pass == 0 ? kTmOut : kTmOutLo);
               if (ROWS) {
                 if (gvalid) v3_tma_store_4d(tmo, stg, nb, gx0 + q4 * 32, gy0 + mt, gn);
               } else if (p.pad) {
@@ -1301,6 +1324,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
               }
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
+            }   // pass
             continue;
           }
           // sub-pixel / channel position of the item's first output column, advanced incrementally
@@ -1615,7 +1639,8 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
   // epilogue through shared memory + TMA stores (full 128-byte lines, asynchronous) where the output is a plain 16-bit NHWC view
   // and every 32-pixel box lies inside the image (rows mode, 1x1 layers).  Measured on B200: store boxes with out-of-range
   // coordinates on several sides raise an illegal-instruction fault, so the flat 3x3 mode keeps its direct stores.
-  p.tma_store = (!tail && d.shuffle == 1 && d.out != nullptr && d.out_f32 == nullptr && d.out_lo == nullptr && d.n_valid % 64 == 0 && block_n % 64 == 0 &&
+  p.tma_store = (!tail && d.shuffle == 1 && d.out != nullptr && d.out_f32 == nullptr && d.n_valid % 64 == 0 && block_n % 64 == 0 &&
+                 (d.out_lo == nullptr || getenv("PSSR_V3_NO_TMA_STORE_LO") == nullptr) &&
                  (p.rows_mode || !p.pad || getenv("PSSR_V3_TMA_STORE_FLAT") != nullptr) && getenv("PSSR_V3_NO_TMA_STORE") == nullptr) ? 1 : 0;
   const long long smem_cap0 = 226 * 1024 - 1024 - vec_bytes - tailw_bytes;
   const char* envG = getenv("PSSR_V3_G");
@@ -1841,6 +1866,25 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     PSSR_REQUIRE(r == CUDA_SUCCESS, PSSR_ECUDA, "cuTensorMapEncodeTiled(output) failed with %d", (int)r);
+    if (d.out_lo != nullptr) {        // the same view over the second output
+      uint8_t* lbase = reinterpret_cast<uint8_t*>(d.out_lo) + (size_t)d.out_lo_choff * 2;
+      if (p.pad) {
+        cuuint64_t gdim[4] = {(cuuint64_t)d.n_valid, (cuuint64_t)d.Wo, (cuuint64_t)d.Ho, (cuuint64_t)d.B};
+        cuuint64_t gstr[3] = {(cuuint64_t)d.out_lo_cstride * 2, (cuuint64_t)d.out_lo_cstride * 2 * d.Wo, (cuuint64_t)d.out_lo_cstride * 2 * d.Wo * d.Ho};
+        cuuint32_t box[4] = {64, 32, 1, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        r = enc(&op.tmaps[kTmOutLo], tdt, 4, lbase, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      } else {
+        cuuint64_t gdim[2] = {(cuuint64_t)d.n_valid, (cuuint64_t)d.Wo * d.Ho * d.B};
+        cuuint64_t gstr[1] = {(cuuint64_t)d.out_lo_cstride * 2};
+        cuuint32_t box[2] = {64, 32};
+        cuuint32_t estr[2] = {1, 1};
+        r = enc(&op.tmaps[kTmOutLo], tdt, 2, lbase, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      }
+      PSSR_REQUIRE(r == CUDA_SUCCESS, PSSR_ECUDA, "cuTensorMapEncodeTiled(out_lo) failed with %d", (int)r);
+    }
   }
 
   p.bias = d.bias;

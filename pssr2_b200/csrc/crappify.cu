@@ -778,7 +778,7 @@ extern "C" int pssr_crappify(const pssr_crappify_args_t* a, void* stream) {
     const long long blocks = (long long)a->n_tiles * a->lr_frames * p.tiles_per_side * p.tiles_per_side;
     PSSR_REQUIRE(blocks < (1ll << 31), PSSR_EUNSUP, "crappify: too many blocks");
     const int ks = getenv("PSSR_CRAP_GENERIC") != nullptr ? 0 : (p.ksize <= 9 ? 9 : (p.ksize <= 17 ? 17 : 0));
-    static const int minb = getenv("PSSR_CRAP_MINB") != nullptr ? atoi(getenv("PSSR_CRAP_MINB")) : 3;
+    static const int minb = getenv("PSSR_CRAP_MINB") != nullptr ? atoi(getenv("PSSR_CRAP_MINB")) : 4;     // measured: 4 CTAs/SM +10 %
 #define PSSR_CRAP_LAUNCH1(TT, KK, MB)                                                                                         \
   do {                                                                                                                        \
     static PerDeviceOnce attr;                                                                                                \

@@ -9,10 +9,10 @@ namespace pssr {
 
 // tensor-map table of one convolution: sources, 16-bit weights, 16-bit output, e5m2 weights, spare
 static constexpr int kTmapsPerConv = 8;
-static constexpr int kTmW = 4, kTmOut = 5, kTmW8 = 6;
+static constexpr int kTmW = 4, kTmOut = 5, kTmW8 = 6, kTmOutLo = 7;
 
 struct ConvOp {
-  CUtensorMap tmaps[kTmapsPerConv];   // host copies ([0..3] sources, [kTmW] weights, [kTmOut] output, [kTmW8] e5m2 weights); uploaded into the plan's device table
+  CUtensorMap tmaps[kTmapsPerConv];   // host copies ([0..3] sources, [kTmW] weights, [kTmOut] output, [kTmW8] e5m2 weights, [kTmOutLo] second output); uploaded into the plan's device table
   alignas(16) uint8_t kparams[640];
   int grid = 0;
   int smem_bytes = 0;

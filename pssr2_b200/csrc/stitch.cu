@@ -150,13 +150,13 @@ __global__ void __launch_bounds__(128) stitch_vec16_kernel(const uint8_t* __rest
 // one store.  Offsets are bytes inside one stack of tiles (< 2^31: checked on the host).
 static constexpr int kBandRows = 16;
 __global__ void __launch_bounds__(128) stitch_band16_kernel(const uint8_t* __restrict__ tiles, uint8_t* __restrict__ sheets, int n_rows,
-                                                            int n_cols, int T, int step, int margin, int out_h, int out_w) {
+                                                            int n_cols, int T, int step, int margin, int out_h, int out_w, int band) {
   __shared__ int s_roff[kBandRows][3];
   __shared__ int s_nr[kBandRows];
-  const int stack = blockIdx.z, Y0 = blockIdx.y * kBandRows;
+  const int stack = blockIdx.z, Y0 = blockIdx.y * band;
   const int X = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
   const int tile_px = T * T;
-  if (threadIdx.x < kBandRows) {
+  if (threadIdx.x < band) {
     const int Y = Y0 + threadIdx.x;
     int n = 0;
     if (Y < out_h) {
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(128) stitch_band16_kernel(const uint8_t* __res
   if (X >= out_w) return;
   const uint8_t* tb = tiles + (size_t)stack * n_rows * n_cols * tile_px;
   uint8_t* ob = sheets + ((size_t)stack * out_h + Y0) * out_w + X;
-  const int rows = min(kBandRows, out_h - Y0);
+  const int rows = min(band, out_h - Y0);
 #pragma unroll 4
   for (int i = 0; i < rows; ++i) {
     const int nr = s_nr[i];
@@ -245,8 +245,15 @@ extern "C" int pssr_stitch(const uint8_t* tiles, uint8_t* sheets, int32_t n_stac
                      (((uintptr_t)tiles | (uintptr_t)sheets) & 15) == 0 && tile / step < 3 && getenv("PSSR_STITCH_VEC4") == nullptr;
   const bool band = vec16 && (long long)n_rows * n_cols * tile * tile < (1ll << 31) && getenv("PSSR_STITCH_NOBAND") == nullptr;
   if (band) {
-    dim3 grid((out_w / 16 + 127) / 128, (out_h + kBandRows - 1) / kBandRows, n_stacks);
-    stitch_band16_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tiles, sheets, n_rows, n_cols, tile, step, margin, out_h, out_w);
+    // rows per CTA: as many as leave >= ~24 CTAs per SM in the grid (a single 3968^2 sheet: 4 rows; eight sheets: 16)
+    const long long xb = (out_w / 16 + 127) / 128;
+    int rows_per_cta = kBandRows;
+    while (rows_per_cta > 2 && xb * ((out_h + rows_per_cta - 1) / rows_per_cta) * n_stacks < 24LL * device_sm_count()) rows_per_cta >>= 1;
+    const char* envb = getenv("PSSR_STITCH_BAND");
+    if (envb != nullptr && atoi(envb) >= 1 && atoi(envb) <= kBandRows) rows_per_cta = atoi(envb);
+    dim3 grid((unsigned)xb, (out_h + rows_per_cta - 1) / rows_per_cta, n_stacks);
+    stitch_band16_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tiles, sheets, n_rows, n_cols, tile, step, margin, out_h, out_w,
+                                                                                   rows_per_cta);
   } else if (vec16) {
     dim3 grid((out_w / 16 + 127) / 128, out_h, n_stacks);
     stitch_vec16_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tiles, sheets, n_rows, n_cols, tile, step, margin, out_h, out_w);
