@@ -317,14 +317,21 @@ __device__ __forceinline__ void v3_tail_window_add(float (&win)[24], const uint3
 // its own A tiles and half of the weight rows, and drains its own TMEM.  ROWS: rows mode -- a tile is a 128-pixel row segment,
 // every worker walks a CONTIGUOUS range of row groups and keeps the input rows in a shared-memory ring (each row is fetched
 // once and prefetched several units ahead; all N tiles of a row group run against the same staged rows).
-template <int T, int G, bool RES, bool TAIL, bool PAIR, bool ROWS>
+// X: the compensated-precision extras (e5m2 segments, epilogue residual, second output, compensated tail) are compiled in; the
+// plain instantiation is what every other layer runs (the extras cost the lean issue loop and the epilogue ~25 % on the
+// 64-channel layers when they are merely present as untaken branches).
+template <int T, int G, bool RES, bool TAIL, bool PAIR, bool ROWS, bool X>
 __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_constant__ V3Params p) {
+  const bool x_tail_comp = X && p.tail_comp != 0;
+  const uint16_t* const x_resid = X ? p.resid : nullptr;
+  uint16_t* const x_out_lo = X ? p.out_lo : nullptr;
   constexpr int C = PAIR ? 2 : 1;
   const uint32_t rank = PAIR ? v3_cluster_rank() : 0u;
   const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // persistent worker (CTA or CTA pair)
   const int workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bars[4 + 2 * kV3MaxB + 8 + 2 * kV3MaxR];
+  __shared__ uint64_t rbars[8];      // X: one per epilogue warp -- its residual tile has landed in shared memory
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
@@ -351,7 +358,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
     // tail weights [9][64] fp32 -> 16-bit K-major SWIZZLE_128B operand tile [16 taps x 64 channels] (rows 9..15 zero);
     // a CTA pair splits the N rows: local row t of rank r is row r*NT/2 + t.  Compensated: N = 32, rows 16..31 hold
     // rn16(w - rn16(w)) of the same taps (the second half of the accumulator columns).
-    const int NT = p.tail_comp ? 32 : 16;
+    const int NT = x_tail_comp ? 32 : 16;
     for (int i = threadIdx.x; i < (NT / C) * 64; i += kV3Threads) {
       const int t = i >> 6, c = i & 63;
       const int grow = t + (int)rank * (NT / C);
@@ -362,7 +369,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
       const int chunk = (c >> 3) ^ (t & 7);
       reinterpret_cast<uint16_t*>(smem_al + tailw_off + t * 128 + chunk * 16)[c & 7] = val;
     }
-    if (p.tail_comp) {
+    if (x_tail_comp) {
       // e5m2 tile [16 taps x 64 channels] of w / 64, 64-byte rows, SWIZZLE_64B (16-byte chunk index ^ ((row >> 1) & 3))
       for (int i = threadIdx.x; i < (16 / C) * 64; i += kV3Threads) {
         const int t = i >> 6, c = i & 63;
@@ -391,6 +398,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
     for (int s = 0; s < kV3MaxB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
     for (int s = 0; s < kV3MaxR; ++s) { mbar_init(r_full(s), 1); mbar_init(r_empty(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(t_full(b), 1); mbar_init(t_empty(b), 8 * C); mbar_init(p_full(b), 8 * C); mbar_init(z_full(b), 1); }
+    if (X) for (int w8 = 0; w8 < 8; ++w8) mbar_init(smem_u32(&rbars[w8]), 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -466,7 +474,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
               for (int cb = 0; cb < p.seg_cblocks[sg]; ++cb) {
                 if (PAIR) v3_tma_4d_pair(dst, tm, fbar, cb * 64, x0, first_row + i, n);
                 else tma_load_4d(dst, tm, fbar, cb * 64, x0, first_row + i, n);
-                dst += p.seg_k16[sg] ? p.slot16_bytes : p.seg_f8[sg] ? p.slot8_bytes : p.slot_bytes;
+                dst += p.seg_k16[sg] ? p.slot16_bytes : (X && p.seg_f8[sg]) ? p.slot8_bytes : p.slot_bytes;
               }
             }
             if (++slot == p.ring_R) { slot = 0; phase ^= 1u; }
@@ -569,7 +577,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
             const int taps = p.seg_taps[sg], cbs = p.seg_cblocks[sg];
             const int gs = taps == 9 ? G : 1;
             // e5m2 segments: 64-byte weight rows from their own matrix, half a 16-bit tap block per tap
-            const bool f8 = ROWS && p.seg_f8[sg] != 0;
+            const bool f8 = X && ROWS && p.seg_f8[sg] != 0;
             tmB = f8 ? p.tmaps + kTmW8 : tmB16;
             const uint32_t tapb = f8 ? (p.tap_bytes >> 1) : p.tap_bytes;
             if (rm && taps != 9 && g != 1) continue;
@@ -599,7 +607,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
     // The whole warp walks the loops (warp-uniform control flow); one elected lane issues the tcgen05 instructions.
     // PAIR: M = 256 in the instruction descriptor (bits 24..28 hold M >> 4)
     const uint32_t idesc = umma_idesc_f16(p.fp16 ? 0 : 1, block_n) + (PAIR ? (8u << 24) : 0u);
-    const uint32_t tail_n = p.tail_comp ? 32u : 16u;
+    const uint32_t tail_n = x_tail_comp ? 32u : 16u;
     const uint32_t idesc_tail = umma_idesc_f16(p.fp16 ? 0 : 1, (int)tail_n) + (PAIR ? (8u << 24) : 0u);
     // kind::f8f6f4: fp32 accumulate, A and B e5m2 (format 1), K-major, N = 16
     const uint32_t idesc_f8 = (1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24) + (PAIR ? (8u << 24) : 0u);
@@ -637,7 +645,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
 
     auto issue_tail = [&](int pit) {
       const int pbuf = pit & 1;
-      if (PAIR && p.tail_comp) v3_mbar_wait_cluster(p_full(pbuf), (uint32_t)(pit >> 1) & 1u);
+      if (PAIR && x_tail_comp) v3_mbar_wait_cluster(p_full(pbuf), (uint32_t)(pit >> 1) & 1u);
       else mbar_wait(p_full(pbuf), (uint32_t)(pit >> 1) & 1u);
       tc_fence_after();
       if (elect_one()) {
@@ -649,7 +657,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
           const uint32_t d_col = cbase + region + 64u + (uint32_t)(s & 1) * tail_n;
 #pragma unroll
           for (int k = 0; k < 4; ++k) v3_mma_ts<PAIR>(d_col, a_col + 8u * k, tdesc + 2u * k, idesc_tail, k ? 1u : 0u);
-          if (p.tail_comp) {
+          if (x_tail_comp) {
             // + (64 * lo) x (w / 64), both e5m2, K = 32 per instruction: accumulates on the hi x W_hi columns
             const uint64_t ad = lo8desc + (uint64_t)(s * (8192 >> 4));
             v3_mma_f8<PAIR>(d_col, ad, w8desc, idesc_f8, 1u);
@@ -677,7 +685,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
         uint64_t plane_desc = sg == 0 ? segp[0] : sg == 1 ? segp[1] : sg == 2 ? segp[2] : sg == 3 ? segp[3] : sg == 4 ? segp[4] : segp[5];
         const bool nine = (sw & 1u) != 0;
         const bool k16 = ROWS && (sw >> 31) != 0;
-        const bool f8 = ROWS && ((sw >> 30) & 1u) != 0;
+        const bool f8 = X && ROWS && ((sw >> 30) & 1u) != 0;
         const int cbs = (int)((sw >> 1) & 0xffu);
         const int kb0 = (int)((sw >> 9) & 0x1fffffu);
         for (int cb = 0; cb < cbs; ++cb, plane_desc += (k16 ? slot16_desc : f8 ? slot8_desc : slot_desc)) {
@@ -828,7 +836,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
           uint64_t plane_desc = sg == 0 ? segp[0] : sg == 1 ? segp[1] : sg == 2 ? segp[2] : sg == 3 ? segp[3] : sg == 4 ? segp[4] : segp[5];
           const bool nine = (sw & 1u) != 0;
           const bool k16 = (sw >> 31) != 0;
-          const bool f8 = ((sw >> 30) & 1u) != 0;
+          const bool f8 = X && ((sw >> 30) & 1u) != 0;
           const int cbs = (int)((sw >> 1) & 0xffu);
           const int kb0 = (int)((sw >> 9) & 0x1fffffu);
           if (!nine && g != 1) continue;
@@ -1036,6 +1044,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
     const int steps = ROWS ? msteps * p.n_tiles : 0;
     asm volatile("griddepcontrol.wait;" ::: "memory");
     int it = 0;
+    uint32_t rphase = 0;            // X: parity of this warp's residual-tile barrier
     float win[24];                  // TAIL + window layout: this thread's pixel, persistent over the four N tiles of a row group
 #pragma unroll
     for (int k = 0; k < 24; ++k) win[k] = 0.f;
@@ -1055,13 +1064,17 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
       }
       const int buf = it & 1;
       const uint32_t par = (uint32_t)(it >> 1) & 1u;
-      if (ROWS && !TAIL && p.resid != nullptr && gvalid) {
-        // the residual rows of this unit start towards L2 while the MMAs are still running (the epilogue would otherwise wait
-        // for DRAM with the accumulators already done)
-        for (int mt = eg; mt < T; mt += 2) {
-          const uint16_t* rp = p.resid + (((size_t)gn * p.H + gy0 + mt) * p.W + gx0 + row) * p.resid_cstride + p.resid_choff + n_tile * block_n;
-          for (int b = 0; b < block_n; b += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + b) : "memory");
-        }
+      // X, rows mode with a TMA-store epilogue and at most one (tile, 64-column) item per warp and unit: the warp's residual tile
+      // [32 pixels x 64 channels] is fetched by TMA into its second staging tile while the MMAs of the unit are still running
+      // (loaded from global memory in the epilogue proper, the 128 bytes per thread cost the unit ~0.6 us of exposed latency)
+      const bool resid_tma = X && ROWS && !TAIL && x_resid != nullptr && p.tma_store && T * npairs <= 2;
+      const int my_item = T * npairs == 1 ? ((it & 1) == eg ? 0 : -1) : (eg < T * npairs ? eg : -1);
+      if (resid_tma && my_item >= 0 && gvalid && lane == 0) {
+        const int mt = my_item / npairs, pi = my_item - mt * npairs;
+        const uint32_t rb = smem_u32(&rbars[warp - 4]);
+        mbar_arrive_expect_tx(rb, 4096u);
+        tma_load_4d(smem_base + p.stage_off + (uint32_t)(8 + warp - 4) * 4096u, p.tmaps + kTmOutLo, rb, n_tile * block_n + pi * 64, gx0 + q4 * 32,
+                    gy0 + mt, gn);
       }
       mbar_wait(t_full(buf), par);
       tc_fence_after();
@@ -1076,7 +1089,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
           tmem_ld_32x32(region + (uint32_t)(c * 32), v);
           tmem_ld_wait();
           uint32_t o[16];
-          if (p.tail_comp) {
+          if (x_tail_comp) {
             // hi = rn16(y) goes back to TMEM; 64 * (y - hi) as e5m2 goes to this pixel's row of the sub-position's A tile in
             // shared memory (64-byte rows, SWIZZLE_64B): 32 channels = two 16-byte chunks
             uint32_t l8[8];
@@ -1105,13 +1118,13 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
           }
           v3_tmem_st16(region + (uint32_t)(c * 16), o);
         }
-        if (p.tail_comp) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the e5m2 tile is read by the tensor core
+        if (x_tail_comp) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the e5m2 tile is read by the tensor core
         v3_tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
           if (rank == 0) mbar_arrive(p_full(buf));
-          else if (p.tail_comp) v3_arrive_cluster_release(v3_mapa(p_full(buf), 0));
+          else if (x_tail_comp) v3_arrive_cluster_release(v3_mapa(p_full(buf), 0));
           else v3_arrive_cluster(v3_mapa(p_full(buf), 0));
         }
         // ---- phase 2: the nine per-tap projections of this thread's pixel, two sub-positions per warp -------------
@@ -1135,7 +1148,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
         const int planes = r * r * 9;
         if (ROWS && p.tail_win48) {
           uint32_t zv0[16], zv1[16];
-          if (p.tail_comp) {
+          if (x_tail_comp) {
             // accumulator columns per sub-position: [0, 16) hi x W_hi + lo x W, [16, 32) hi x W_lo
             uint32_t zl0[16], zl1[16];
             v3_tmem_ld16(region + 64u, zv0);
@@ -1172,7 +1185,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
 #pragma unroll
         for (int sl = 0; sl < 2; ++sl) {
           uint32_t zv[16];
-          if (p.tail_comp) {
+          if (x_tail_comp) {
             uint32_t zl[16];
             v3_tmem_ld16(region + 64u + (uint32_t)(sl * 32), zv);
             v3_tmem_ld16(region + 64u + (uint32_t)(sl * 32 + 16), zl);
@@ -1191,7 +1204,9 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
           }
         }
       } else {
-        for (int item = eg; item < T * npairs; item += 2) {
+        // two epilogue groups share the unit's (tile, 64-column) items; a unit with a single item goes to the groups in turn, so
+        // that the epilogues of consecutive units overlap instead of leaving four warps idle
+        for (int item = (T * npairs == 1 ? ((it & 1) == eg ? 0 : 1) : eg); item < T * npairs; item += 2) {
           const int mt = item / npairs;
           const int pi = item - mt * npairs;
           const int c_lo = pi * 64;
@@ -1234,14 +1249,13 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
             // ---- 16-bit tile [32 pixels x 64 channels] -> swizzled shared memory -> one TMA store (two when the 32 flat
             // pixels wrap to the next image row); padding / out-of-range positions are clipped by the TMA unit ----------
             const uint32_t stg = smem_base + p.stage_off + (uint32_t)(warp - 4) * 4096u;
+            const uint32_t stg_hi = stg;
             const uint32_t taddr2 = lane_addr + (uint32_t)(buf * 256 + mt * block_n + c_lo);
             const int nb = n_tile * block_n + c_lo;
-            // pass 0: the 16-bit tile; pass 1 (out_lo): what its rounding dropped, through the same staging buffer -- the accumulator
-            // is read from TMEM again rather than keeping 32 more registers alive
-            const int n_pass = p.out_lo != nullptr ? 2 : 1;
-#pragma unroll 1
-            for (int pass = 0; pass < n_pass; ++pass) {
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous tile has left the buffer
+            // second output (out_lo): what the 16-bit rounding dropped, staged in a second tile of this warp and stored by a
+            // second TMA store of the same box
+            const uint32_t stg_lo = stg + 8u * 4096u;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous tile(s) have left the buffers
             __syncwarp();
 #pragma unroll
             for (int cq = 0; cq < 2; ++cq) {
@@ -1257,8 +1271,27 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
                 f[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + bb.z;
                 f[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + bb.w;
               }
-              if (p.resid != nullptr && valid) {
-                const uint4* rp = reinterpret_cast<const uint4*>(p.resid + (((size_t)n * p.H + y) * p.W + x) * p.resid_cstride + p.resid_choff + nb + cq * 32);
+              if (X && resid_tma) {
+                if (cq == 0 && gvalid) mbar_wait(smem_u32(&rbars[warp - 4]), rphase);
+                if (gvalid) {
+#pragma unroll
+                  for (int j8 = 0; j8 < 4; ++j8) {
+                    uint4 rv;
+                    const uint32_t chunk = (uint32_t)(cq * 4 + j8) ^ (uint32_t)(lane & 7);
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w)
+                                 : "r"(stg_lo + (uint32_t)lane * 128u + chunk * 16u));
+                    const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                      const float2 r2 = v3_unpack2(rw[k], p.fp16);
+                      f[8 * j8 + 2 * k] = fmaf(p.resid_scale, r2.x, f[8 * j8 + 2 * k]);
+                      f[8 * j8 + 2 * k + 1] = fmaf(p.resid_scale, r2.y, f[8 * j8 + 2 * k + 1]);
+                    }
+                  }
+                }
+                if (cq == 1 && gvalid) rphase ^= 1u;
+              } else if (x_resid != nullptr && valid) {
+                const uint4* rp = reinterpret_cast<const uint4*>(x_resid + (((size_t)n * p.H + y) * p.W + x) * p.resid_cstride + p.resid_choff + nb + cq * 32);
 #pragma unroll
                 for (int j8 = 0; j8 < 4; ++j8) {
                   const uint4 rv = rp[j8];
@@ -1286,22 +1319,28 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
                 uint32_t w[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) w[k] = v3_pack2(f[8 * j4 + 2 * k], f[8 * j4 + 2 * k + 1], p.fp16, relu_pack);
-                if (pass == 1) {
+                v3_st_shared_v4(stg + (uint32_t)lane * 128u + chunk * 16u, w[0], w[1], w[2], w[3]);
+                if (X && x_out_lo != nullptr) {
+                  uint32_t wl[4];
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
                     const float2 hq = v3_unpack2(w[k], p.fp16);
                     const float a0 = relu_pack ? fmaxf(f[8 * j4 + 2 * k], 0.f) : f[8 * j4 + 2 * k];
                     const float a1 = relu_pack ? fmaxf(f[8 * j4 + 2 * k + 1], 0.f) : f[8 * j4 + 2 * k + 1];
-                    w[k] = v3_pack2(a0 - hq.x, a1 - hq.y, p.fp16, false);
+                    wl[k] = v3_pack2(a0 - hq.x, a1 - hq.y, p.fp16, false);
                   }
+                  v3_st_shared_v4(stg_lo + (uint32_t)lane * 128u + chunk * 16u, wl[0], wl[1], wl[2], wl[3]);
                 }
-                v3_st_shared_v4(stg + (uint32_t)lane * 128u + chunk * 16u, w[0], w[1], w[2], w[3]);
               }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0 && !(p.dbg & 1)) {
+            const int n_pass = (X && x_out_lo != nullptr) ? 2 : 1;
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass)
+            if (pass < n_pass && lane == 0 && !(p.dbg & 1)) {
               const CUtensorMap* tmo = p.tmaps + (pass == 0 ? kTmOut : kTmOutLo);
+              const uint32_t stg = pass == 0 ? stg_hi : stg_lo;
               if (ROWS) {
                 if (gvalid) v3_tma_store_4d(tmo, stg, nb, gx0 + q4 * 32, gy0 + mt, gn);
               } else if (p.pad) {
@@ -1324,7 +1363,6 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
               }
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
-            }   // pass
             continue;
           }
           // sub-pixel / channel position of the item's first output column, advanced incrementally
@@ -1357,8 +1395,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
                   f[4 * j4 + 2] = __uint_as_float(v[h * 16 + 4 * j4 + 2]) + bb.z;
                   f[4 * j4 + 3] = __uint_as_float(v[h * 16 + 4 * j4 + 3]) + bb.w;
                 }
-                if (p.resid != nullptr) {
-                  const uint4* rp = reinterpret_cast<const uint4*>(p.resid + (((size_t)n * p.H + y) * p.W + x) * p.resid_cstride + p.resid_choff + nn);
+                if (x_resid != nullptr) {
+                  const uint4* rp = reinterpret_cast<const uint4*>(x_resid + (((size_t)n * p.H + y) * p.W + x) * p.resid_cstride + p.resid_choff + nn);
 #pragma unroll
                   for (int j8 = 0; j8 < 2; ++j8) {
                     const uint4 rv = rp[j8];
@@ -1388,7 +1426,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
 #pragma unroll
                 for (int j = 0; j < 8; ++j) o[j] = v3_pack2(f[2 * j], f[2 * j + 1], p.fp16, relu_pack);
                 uint32_t ol[8];
-                if (p.out_lo != nullptr) {          // second output: what the 16-bit rounding of the activated value dropped
+                if (x_out_lo != nullptr) {          // second output: what the 16-bit rounding of the activated value dropped
 #pragma unroll
                   for (int j = 0; j < 8; ++j) {
                     const float2 h = v3_unpack2(o[j], p.fp16);
@@ -1399,7 +1437,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
                 if (p.wide_store) {
                   const size_t pix = pix00 + (size_t)si * p.Wout + (size_t)sj;
                   v3_st_global_v8(p.out + pix * p.out_cstride + p.out_choff + cc, o);
-                  if (p.out_lo != nullptr) v3_st_global_v8(p.out_lo + pix * p.lo_cstride + p.lo_choff + cc, ol);
+                  if (x_out_lo != nullptr) v3_st_global_v8(x_out_lo + pix * p.lo_cstride + p.lo_choff + cc, ol);
                   if (warp == 4 && it == 2 && h == 1) V3_TRACE(226 + 2 * ((c0 - c_lo) >> 5));
                 } else {
                   if (relu_pack && p.out_f32 != nullptr) {
@@ -1416,8 +1454,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
                       const size_t pix = ((size_t)n * p.Hout + (size_t)(y * r + si8)) * p.Wout + (size_t)(x * r + sj8);
                       if (p.out != nullptr)
                         *reinterpret_cast<uint4*>(p.out + pix * p.out_cstride + p.out_choff + cc8) = make_uint4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
-                      if (p.out_lo != nullptr)
-                        *reinterpret_cast<uint4*>(p.out_lo + pix * p.lo_cstride + p.lo_choff + cc8) = make_uint4(ol[4 * g], ol[4 * g + 1], ol[4 * g + 2], ol[4 * g + 3]);
+                      if (x_out_lo != nullptr)
+                        *reinterpret_cast<uint4*>(x_out_lo + pix * p.lo_cstride + p.lo_choff + cc8) = make_uint4(ol[4 * g], ol[4 * g + 1], ol[4 * g + 2], ol[4 * g + 3]);
                       if (p.out_f32 != nullptr) {
                         float4* d = reinterpret_cast<float4*>(p.out_f32 + pix * p.out_cstride + p.out_choff + cc8);
                         d[0] = make_float4(f[8 * g + 0], f[8 * g + 1], f[8 * g + 2], f[8 * g + 3]);
@@ -1480,8 +1518,9 @@ static EncodeTiledFn v3_encode_fn() {
 }
 
 typedef void (*V3Kernel)(const V3Params);
-struct V3Variant { int T, G, RES, TAIL, PAIR, ROWS; V3Kernel fn; };
-#define V3_VARIANT(T, G, RES, TAIL, PAIR, ROWS) {T, G, RES, TAIL, PAIR, ROWS, conv_v3_kernel<T, G, RES != 0, TAIL != 0, PAIR != 0, ROWS != 0>}
+struct V3Variant { int T, G, RES, TAIL, PAIR, ROWS, X; V3Kernel fn; };
+#define V3_VARIANT(T, G, RES, TAIL, PAIR, ROWS) {T, G, RES, TAIL, PAIR, ROWS, 0, conv_v3_kernel<T, G, RES != 0, TAIL != 0, PAIR != 0, ROWS != 0, false>}, \
+  {T, G, RES, TAIL, PAIR, ROWS, 1, conv_v3_kernel<T, G, RES != 0, TAIL != 0, PAIR != 0, ROWS != 0, true>}
 #define V3_VARIANTS_PR(PAIR, ROWS)                                                                                             \
   V3_VARIANT(1, 1, 0, 0, PAIR, ROWS), V3_VARIANT(1, 3, 0, 0, PAIR, ROWS), V3_VARIANT(1, 9, 1, 0, PAIR, ROWS),                  \
   V3_VARIANT(2, 1, 0, 0, PAIR, ROWS), V3_VARIANT(2, 3, 0, 0, PAIR, ROWS), V3_VARIANT(2, 9, 1, 0, PAIR, ROWS),                  \
@@ -1690,8 +1729,10 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
   // T = 1, a deep ring (2T+2 rows: plain K order, all nine taps of a block issued in one go) before a shallow one (T+2 rows:
   // filter-row-major order, the issuer releases the top rows early and awaits the bottom rows late so that the next rows load
   // while the unit computes), TMA-store staging before direct stores.  Whatever is left after the weights deepens the ring.
+  // per-warp 4 KB tiles: one per 16-bit output, or the second one as the landing tile of the epilogue residual
+  const long long stage_total = ((d.out_lo != nullptr || d.resid != nullptr) ? 16 : 8) * 4096;
   auto try_config = [&](int Tc, bool staged, bool res_only, bool deep) -> bool {
-    const long long cap = smem_cap0 - (staged ? 8 * 4096 : 0);
+    const long long cap = smem_cap0 - (staged ? stage_total : 0);
     long long a_min, ab = 0;
     if (p.rows_mode) {
       a_min = (long long)(deep ? 2 * Tc + 2 : Tc + 2) * p.group_bytes;      // deep: the current group and one group of prefetch
@@ -1729,7 +1770,7 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
     T = Tc; G = g_; RES = res_; b_stages = bst_; a_bytes = ab;
     p.row_major = (p.rows_mode && !deep) ? 1 : 0;
     p.tma_store = staged ? 1 : 0;
-    stage_bytes = staged ? 8 * 4096 : 0;
+    stage_bytes = staged ? (int)stage_total : 0;
     smem_cap = cap;
     return true;
   };
@@ -1884,6 +1925,16 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       }
       PSSR_REQUIRE(r == CUDA_SUCCESS, PSSR_ECUDA, "cuTensorMapEncodeTiled(out_lo) failed with %d", (int)r);
+    } else if (d.resid != nullptr && p.rows_mode) {
+      // the epilogue residual as 32-pixel x 64-channel boxes (rows mode; other modes read it from global memory)
+      uint8_t* rbase = reinterpret_cast<uint8_t*>(const_cast<void*>(d.resid)) + (size_t)d.resid_choff * 2;
+      cuuint64_t gdim[4] = {(cuuint64_t)d.n_valid, (cuuint64_t)d.Wo, (cuuint64_t)d.Ho, (cuuint64_t)d.B};
+      cuuint64_t gstr[3] = {(cuuint64_t)d.resid_cstride * 2, (cuuint64_t)d.resid_cstride * 2 * d.Wo, (cuuint64_t)d.resid_cstride * 2 * d.Wo * d.Ho};
+      cuuint32_t box[4] = {64, 32, 1, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      r = enc(&op.tmaps[kTmOutLo], tdt, 4, rbase, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      PSSR_REQUIRE(r == CUDA_SUCCESS, PSSR_ECUDA, "cuTensorMapEncodeTiled(resid) failed with %d", (int)r);
     }
   }
 
@@ -1896,6 +1947,7 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
   p.tail_win48 = (tail && d.tail_layout == PSSR_TAIL_WINDOW48) ? 1 : 0;
   p.tail_comp = tail_comp ? 1 : 0;
   p.tailw_bytes = (uint32_t)tailw_bytes;
+  PSSR_REQUIRE(d.resid == nullptr || d.out_lo == nullptr, PSSR_EUNSUP, "conv: resid and out_lo share the second staging tile");
   PSSR_REQUIRE(d.resid == nullptr || (!tail && d.shuffle == 1 && d.n == d.n_valid && d.n_valid % 16 == 0 && d.resid_cstride % 8 == 0 &&
                                       d.resid_choff % 8 == 0 && ((uintptr_t)d.resid & 15) == 0),
                PSSR_EUNSUP, "conv: the epilogue residual needs shuffle == 1, unpadded N and 16-byte aligned channel slices");
@@ -1930,9 +1982,10 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
   op.grid = workers * C;
   op.cluster = C;
   op.kernel_index = -1;
+  const int need_x = (num_kb8 > 0 || d.resid != nullptr || d.out_lo != nullptr || tail_comp) ? 1 : 0;
   for (int i = 0; i < kV3NumVariants; ++i)
     if (kV3Variants[i].T == T && kV3Variants[i].G == G && kV3Variants[i].RES == RES && kV3Variants[i].TAIL == (tail ? 1 : 0) &&
-        kV3Variants[i].PAIR == PAIR && kV3Variants[i].ROWS == p.rows_mode)
+        kV3Variants[i].PAIR == PAIR && kV3Variants[i].ROWS == p.rows_mode && kV3Variants[i].X == need_x)
       op.kernel_index = i;
   PSSR_REQUIRE(op.kernel_index >= 0, PSSR_EUNSUP, "conv: no kernel variant for T=%d G=%d RES=%d TAIL=%d PAIR=%d", T, G, RES, (int)tail, PAIR);
   static PerDeviceOnce attr_once;
