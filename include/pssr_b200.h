@@ -118,6 +118,10 @@ typedef struct {
    * is sheet_h x sheet_w (the reference datasets accept images of different sizes, data.py:536-551) */
   const int32_t* sheet_hs;
   const int32_t* sheet_ws;
+  /* Training-time augmentation (pssr/data.py:476-480, drawn per item at :108 / :244): optional per-tile transform of the
+   * cropped + reflect-padded hr_res x hr_res tile BEFORE the downscale, bit 0 = np.rot90(axes=(1,2)), then bit 1 = flip of axis 1
+   * (rows), bit 2 = flip of axis 2 (columns).  The HR outputs carry the same transform.  NULL = none (the predict path).        */
+  const int32_t* tile_xf;
 } pssr_crappify_args_t;
 
 int pssr_crappify(const pssr_crappify_args_t* args, void* stream);

@@ -110,10 +110,14 @@ def crappify_chain(lr, stages, clip=True):
     return lr
 
 
-def gen_pair(hr, hr_res, lr_scale, stages, n_frames=None, clip=True, multi=True):
-    """pssr/data.py:471-495 without rotation/transforms.  ``stages is None`` <=> crappifier=None.
-    ``multi=False`` models a bare (non-Multi) crappifier: no clip after the stage."""
+def gen_pair(hr, hr_res, lr_scale, stages, n_frames=None, clip=True, multi=True, rotation=False):
+    """pssr/data.py:471-495 without transforms.  ``stages is None`` <=> crappifier=None.
+    ``multi=False`` models a bare (non-Multi) crappifier: no clip after the stage.
+    ``rotation``: False or [rot90?, flip axis 1 | 2 | (1, 2)] as drawn at pssr/data.py:108 (applied at :478-480)."""
     hr = pad_image(square_crop(hr, hr_res), hr_res)
+    if rotation:
+        hr = np.rot90(hr, axes=(1, 2)) if rotation[0] else hr
+        hr = np.flip(hr, axis=rotation[1])
     lr = resize_bilinear(np.ascontiguousarray(hr), hr_res // lr_scale, hr_res // lr_scale).astype(np.float32)
     if stages is not None:
         lr = crappify_chain(lr, stages, clip=clip and multi)

@@ -73,7 +73,7 @@ class CrappifyArgs(Structure):
                 ("seed", c_uint64), ("tile_index0", c_uint64),
                 ("lr_out", c_void_p), ("hr_out", c_void_p), ("hr_u8_out", c_void_p),
                 ("hr_frame0", c_int32), ("hr_frames", c_int32), ("lr_frame0", c_int32), ("lr_frames", c_int32),
-                ("sheet_hs", c_void_p), ("sheet_ws", c_void_p)]
+                ("sheet_hs", c_void_p), ("sheet_ws", c_void_p), ("tile_xf", c_void_p)]
 
 
 class Src(Structure):

@@ -380,6 +380,7 @@ struct CrapK {
   int elem_bytes, sheet_h, sheet_w;
   const int32_t *sheet_hs, *sheet_ws;      // optional per-sheet dimensions
   const int32_t *tile_sheet, *tile_frame, *tile_y, *tile_x, *tile_vh, *tile_vw;
+  const int32_t* tile_xf;                  // optional per-tile rot90 / flip (training augmentation)
   int n_tiles, frames, lr_frame0, lr_frames, hr_res, lr_res;
   int TL, tiles_per_side, ksize;
   int max_rows, raw_pitch;  // shared staging geometry (bytes per raw row, multiple of 16)
@@ -398,6 +399,14 @@ struct CrapK {
   uint8_t* hr_u8;
   int hr_frame0, hr_frames, scale;
 };
+
+// (r, c) of the augmented tile -> (r, c) of the padded tile it was made from: T'[r][c] = R[r'][c'] with the flips applied to the
+// indices, and np.rot90(P, axes=(1, 2))[i][j] = P[j][N-1-i]  (pssr/data.py:478-480: rot90 first, then flip)
+__device__ __forceinline__ void untransform(int xf, int N, int& r, int& c) {
+  if (xf & 2) r = N - 1 - r;
+  if (xf & 4) c = N - 1 - c;
+  if (xf & 1) { const int t = r; r = c; c = N - 1 - t; }
+}
 
 template <typename T>
 __device__ __forceinline__ T load_reflect(const T* frame_base, int sheet_w, int ty, int tx, int r, int c, int vh,
@@ -444,8 +453,9 @@ __global__ void __launch_bounds__(kCrapThreads, MINB) crappify_kernel(const Crap
   const T* fbase = sheet + (size_t)(p.tile_frame[tile] + f) * frame_elems;
 
   // ---- stage 1: HR window -> shared (16-byte vectors on the aligned fast path) ----------
+  const int xf = p.tile_xf != nullptr ? p.tile_xf[tile] : 0;
   const bool interior = (row0 + nrows <= vh) && (col0 + ncols <= vw);
-  const bool vec_ok = interior && ((reinterpret_cast<uintptr_t>(sheet) & 15) == 0);
+  const bool vec_ok = interior && xf == 0 && ((reinterpret_cast<uintptr_t>(sheet) & 15) == 0);
   if (vec_ok) {
     const int vec_per_row = p.raw_pitch / 16;
     for (int i = threadIdx.x; i < nrows * vec_per_row; i += kCrapThreads) {
@@ -462,7 +472,9 @@ __global__ void __launch_bounds__(kCrapThreads, MINB) crappify_kernel(const Crap
   } else {
     for (int i = threadIdx.x; i < nrows * ncols; i += kCrapThreads) {
       const int r = i / ncols, c = i - r * ncols;
-      reinterpret_cast<T*>(raw + (size_t)r * p.raw_pitch)[c] = load_reflect<T>(fbase, sheet_w, ty, tx, row0 + r, col0 + c, vh, vw);
+      int pr = row0 + r, pc = col0 + c;
+      untransform(xf, p.hr_res, pr, pc);
+      reinterpret_cast<T*>(raw + (size_t)r * p.raw_pitch)[c] = load_reflect<T>(fbase, sheet_w, ty, tx, pr, pc, vh, vw);
     }
     for (int r = threadIdx.x; r < nrows; r += kCrapThreads) lead[r] = 0;
   }
@@ -618,7 +630,8 @@ template <typename T>
 __global__ void hr_gather_kernel(const void* const* sheets, const int32_t* tile_sheet, const int32_t* tile_frame,
                                  const int32_t* tile_y, const int32_t* tile_x, const int32_t* tile_vh,
                                  const int32_t* tile_vw, int sheet_h, int sheet_w, int hr_res, int hr_frame0,
-                                 int hr_frames, float* hr_out, uint8_t* hr_u8, const int32_t* sheet_hs, const int32_t* sheet_ws) {
+                                 int hr_frames, float* hr_out, uint8_t* hr_u8, const int32_t* sheet_hs, const int32_t* sheet_ws,
+                                 const int32_t* tile_xf) {
   const int tile = blockIdx.z;
   const int fo = blockIdx.y;
   if (sheet_hs != nullptr) { sheet_h = sheet_hs[tile_sheet[tile]]; sheet_w = sheet_ws[tile_sheet[tile]]; }
@@ -628,7 +641,8 @@ __global__ void hr_gather_kernel(const void* const* sheets, const int32_t* tile_
   const int centre = hr_frames / 2;  // _slice_center(x, 1) keeps index shape//2
   const size_t n = (size_t)hr_res * hr_res;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / hr_res), c = (int)(i - (size_t)r * hr_res);
+    int r = (int)(i / hr_res), c = (int)(i - (size_t)r * hr_res);
+    untransform(tile_xf != nullptr ? tile_xf[tile] : 0, hr_res, r, c);
     const T v = load_reflect<T>(fbase, sheet_w, ty, tx, r, c, vh, vw);
     if (hr_out) hr_out[((size_t)tile * hr_frames + fo) * n + i] = (float)v;
     if (hr_u8 && fo == centre) hr_u8[(size_t)tile * n + i] = (uint8_t)min((int)v, 255);
@@ -741,6 +755,7 @@ extern "C" int pssr_crappify(const pssr_crappify_args_t* a, void* stream) {
     p.sheet_ws = a->sheet_ws;
     p.tile_sheet = a->tile_sheet; p.tile_frame = a->tile_frame; p.tile_y = a->tile_y; p.tile_x = a->tile_x;
     p.tile_vh = a->tile_vh; p.tile_vw = a->tile_vw;
+    p.tile_xf = a->tile_xf;
     p.n_tiles = a->n_tiles; p.frames = a->frames; p.lr_frame0 = a->lr_frame0; p.lr_frames = a->lr_frames;
     p.hr_res = a->hr_res; p.lr_res = lr_res;
     int TL = 128 / a->lr_scale;
@@ -804,11 +819,11 @@ extern "C" int pssr_crappify(const pssr_crappify_args_t* a, void* stream) {
     if (a->elem_bytes == 1)
       hr_gather_kernel<uint8_t><<<grid, 256, 0, st>>>(a->sheets, a->tile_sheet, a->tile_frame, a->tile_y, a->tile_x, a->tile_vh,
                                                       a->tile_vw, a->sheet_h, a->sheet_w, a->hr_res, a->hr_frame0, a->hr_frames,
-                                                      a->hr_out, a->hr_u8_out, a->sheet_hs, a->sheet_ws);
+                                                      a->hr_out, a->hr_u8_out, a->sheet_hs, a->sheet_ws, a->tile_xf);
     else
       hr_gather_kernel<uint16_t><<<grid, 256, 0, st>>>(a->sheets, a->tile_sheet, a->tile_frame, a->tile_y, a->tile_x, a->tile_vh,
                                                        a->tile_vw, a->sheet_h, a->sheet_w, a->hr_res, a->hr_frame0, a->hr_frames,
-                                                       a->hr_out, a->hr_u8_out, a->sheet_hs, a->sheet_ws);
+                                                       a->hr_out, a->hr_u8_out, a->sheet_hs, a->sheet_ws, a->tile_xf);
     count_launch();
     PSSR_CHECK_CUDA(cudaGetLastError());
   }

@@ -16,6 +16,7 @@ and training-time rotation are outside the accelerated hot path (SURVEY.md §2 r
 """
 import glob
 import os
+import random
 import warnings
 from pathlib import Path
 
@@ -261,15 +262,50 @@ class _DeviceDataset(Dataset):
     def _frames_window(self, image_idx):
         return max(self.n_frames) if self.n_frames is not None else self._frames_total[image_idx]
 
-    def _table(self, indices):
+    def _table(self, indices, xf=None):
         locs = [self._locate(i) for i in indices]
         cols = list(zip(*locs))
         self._wait_sheets(cols[0])
-        return ops.TileTable(self._sheets, *cols)
+        return ops.TileTable(self._sheets, *cols, tile_xf=xf)
 
-    def batch(self, indices, want_hr=True, want_hr_u8=False, want_lr=True, tile_index0=None, seed=None):
+    def _draw_rotation(self, idx):
+        """pssr/data.py:108 / :244: training items (not validation ones) get a random rot90 and a flip of axis 1, 2 or both, drawn
+        from Python's ``random`` exactly as the reference draws them; encoded for the kernel (bit 0 rot90, 1 flip rows, 2 flip
+        columns)."""
+        if not self.rotation or idx in self._val_set():
+            return 0
+        rot, axes = bool(random.getrandbits(1)), random.choice((1, 2, (1, 2)))
+        axes = (axes,) if isinstance(axes, int) else axes
+        return (1 if rot else 0) | (2 if 1 in axes else 0) | (4 if 2 in axes else 0)
+
+    def _val_set(self):
+        vs = getattr(self, "_val_set_cache", None)
+        if vs is None or vs[0] is not self.val_idx:
+            vs = (self.val_idx, set(self.val_idx))
+            self._val_set_cache = vs
+        return vs[1]
+
+    def loader(self, batch_size, train=True):
+        """The data side of ``train_paired`` (pssr/train.py:75-96): yields ``(hr, lr)`` device batches, each from ONE fused
+        launch.  ``train=True`` walks the non-validation items in ``random.shuffle`` order with the reference's per-item
+        rotation / flip augmentation (``_RandomIterIdx(_invert_idx(val_idx, len))``); ``train=False`` walks the validation items
+        in the reference's seeded order (``_RandomIterIdx(val_idx, seed=True)``), unaugmented."""
+        if train:
+            vs = self._val_set()
+            idx = [i for i in range(len(self)) if i not in vs]
+            random.shuffle(idx)
+        else:
+            idx = list(self.val_idx)
+            np.random.seed(0)
+            np.random.shuffle(idx)
+        for s in range(0, len(idx), batch_size):
+            b = self.batch(idx[s:s + batch_size], want_hr=not self.is_lr, augment=train)
+            yield (b["hr"], b["lr"]) if not self.is_lr else b["lr"]
+
+    def batch(self, indices, want_hr=True, want_hr_u8=False, want_lr=True, tile_index0=None, seed=None, augment=False):
         """One fused launch for many items.  Returns dict(lr=[n,f_lr,h,w] f32, hr=[n,f_hr,H,W] f32 | None,
-        hr_u8=[n,1,H,W] u8 | None), all on the device.  (pssr/data.py:100-120 / :236-256 + _gen_pair :471-495)"""
+        hr_u8=[n,1,H,W] u8 | None), all on the device.  (pssr/data.py:100-120 / :236-256 + _gen_pair :471-495)
+        ``augment=True``: non-validation items are rotated / flipped at random like the reference's training path."""
         indices = list(indices)
         tiles_ = getattr(self, "tiles", None)
         windows = {self._frames_window(_get_image_idx(i, self.slices, tiles_)[0]) for i in indices}
@@ -279,13 +315,14 @@ class _DeviceDataset(Dataset):
             # items whose frame windows differ (n_frames=-1 over stacks of different depth) cannot share a launch, and a
             # crappifier with spread > 0 redraws its intensity for EVERY item (pssr/crappifiers.py:63,85,104): one launch each
             t0 = indices[0] if tile_index0 is None else tile_index0
-            parts = [self.batch([i], want_hr, want_hr_u8, want_lr, t0 + k, seed) for k, i in enumerate(indices)]
+            parts = [self.batch([i], want_hr, want_hr_u8, want_lr, t0 + k, seed, augment) for k, i in enumerate(indices)]
             if len(windows) > 1 and not self.is_lr and any(p["lr"].shape != parts[0]["lr"].shape for p in parts):
                 raise ValueError("the items of one batch have different frame counts (n_frames=-1 over stacks of different depth); "
                                  "use batch_size=1 or a fixed n_frames")
             return {k: (torch.cat([p[k] for p in parts]) if parts[0][k] is not None else None) for k in ("lr", "hr", "hr_u8")}
         frames = self._frames_window(_get_image_idx(indices[0], self.slices, tiles_)[0])
-        table = self._table(indices)
+        xf = [self._draw_rotation(i) for i in indices] if augment and not self.is_lr else None
+        table = self._table(indices, xf)
         lr_res_scale = self.lr_scale
         if self.is_lr:
             # LR mode (_ready_lr, data.py:518-524): crop/pad only -- identity resample, no noise
@@ -329,7 +366,7 @@ class _DeviceDataset(Dataset):
     def __getitem__(self, idx, pp=False):
         if idx >= len(self):
             raise IndexError(f"Tried to retrieve invalid image. Index {idx} is not less than {len(self)} total image frame slices.")
-        b = self.batch([idx])
+        b = self.batch([idx], augment=not pp)      # validation items and pp=True are never augmented (data.py:103,108)
         if self.is_lr:
             return b["lr"][0]
         return b["hr"][0], b["lr"][0]

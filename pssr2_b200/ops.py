@@ -31,7 +31,8 @@ class TileTable:
     are remapped), and the pointer table, the per-sheet dimensions and the six index columns travel in ONE pinned-host ->
     device copy on the current stream."""
 
-    def __init__(self, sheets, tile_sheet, tile_frame, tile_y, tile_x, tile_vh, tile_vw):
+    def __init__(self, sheets, tile_sheet, tile_frame, tile_y, tile_x, tile_vh, tile_vw, tile_xf=None):
+        """tile_xf: optional per-tile augmentation code (bit 0 rot90, bit 1 flip rows, bit 2 flip columns; pssr/data.py:478-480)."""
         tile_sheet = np.asarray(tile_sheet, dtype=np.int64)
         used = sorted(set(int(i) for i in tile_sheet))
         remap = {g: k for k, g in enumerate(used)}
@@ -52,14 +53,15 @@ class TileTable:
         local = np.asarray([remap[int(i)] for i in tile_sheet], dtype=np.int32)
         self.frames_of_tile = np.asarray([int(self.sheets[k].shape[0]) for k in local], dtype=np.int64)   # host copy: frame-range checks
         self.tile_frame_host = np.asarray(tile_frame, dtype=np.int64)
-        # packed header: [ns] int64 pointers | [2*ns] int32 sheet dims | [6*n] int32 columns
-        host = torch.empty(8 * ns + 4 * (2 * ns + 6 * n), dtype=torch.uint8, pin_memory=True)
+        # packed header: [ns] int64 pointers | [2*ns] int32 sheet dims | [7*n] int32 columns (the seventh: augmentation codes)
+        host = torch.empty(8 * ns + 4 * (2 * ns + 7 * n), dtype=torch.uint8, pin_memory=True)
         hv = host.numpy()
         hv[:8 * ns].view(np.int64)[:] = [s.data_ptr() for s in self.sheets]
         i32 = hv[8 * ns:].view(np.int32)
         i32[:ns] = [int(s.shape[1]) for s in self.sheets]
         i32[ns:2 * ns] = [int(s.shape[2]) for s in self.sheets]
-        i32[2 * ns:] = np.asarray([local, tile_frame, tile_y, tile_x, tile_vh, tile_vw], dtype=np.int32).reshape(-1)
+        xf = np.zeros(n, dtype=np.int32) if tile_xf is None else np.asarray(tile_xf, dtype=np.int32)
+        i32[2 * ns:] = np.asarray([local, tile_frame, tile_y, tile_x, tile_vh, tile_vw, xf], dtype=np.int32).reshape(-1)
         with _lib.on_device(dev):
             packed = host.to(dev, non_blocking=True)
         self._packed, self._host = packed, host            # the pinned source must outlive the asynchronous copy
@@ -67,8 +69,9 @@ class TileTable:
         d32 = packed[8 * ns:].view(torch.int32)
         # sheets of different sizes: per-sheet dimension arrays travel with the table
         self.sheet_dims = d32[:2 * ns].view(2, ns) if any(s.shape[1:] != s0.shape[1:] for s in self.sheets) else None
-        cols = d32[2 * ns:].view(6, n)
+        cols = d32[2 * ns:].view(7, n)
         self.tile_sheet, self.tile_frame, self.tile_y, self.tile_x, self.tile_vh, self.tile_vw = (cols[i] for i in range(6))
+        self.tile_xf = cols[6] if tile_xf is not None and bool(xf.any()) else None
         self.n_tiles = n
         self.device = dev
 
@@ -77,6 +80,7 @@ class TileTable:
         t.__dict__.update(self.__dict__)
         for k in ("tile_sheet", "tile_frame", "tile_y", "tile_x", "tile_vh", "tile_vw"):
             setattr(t, k, getattr(self, k)[start:start + count])
+        t.tile_xf = self.tile_xf[start:start + count] if self.tile_xf is not None else None
         t.frames_of_tile = self.frames_of_tile[start:start + count]
         t.tile_frame_host = self.tile_frame_host[start:start + count]
         t.n_tiles = count
@@ -110,6 +114,7 @@ def crappify(table: TileTable, hr_res, lr_scale, stages, *, frames=1, lr_frame0=
     a.tile_sheet, a.tile_frame = table.tile_sheet.data_ptr(), table.tile_frame.data_ptr()
     a.tile_y, a.tile_x = table.tile_y.data_ptr(), table.tile_x.data_ptr()
     a.tile_vh, a.tile_vw = table.tile_vh.data_ptr(), table.tile_vw.data_ptr()
+    a.tile_xf = table.tile_xf.data_ptr() if table.tile_xf is not None else None
     a.n_tiles, a.frames, a.hr_res, a.lr_scale = n, frames, hr_res, lr_scale
     keep = []
     stages = [] if stages is None else stages

@@ -67,6 +67,24 @@ def gen_pair_cases():
     np.savez_compressed(os.path.join(OUT, "gen_pair.npz"), **out)
 
 
+def gen_pair_rotation_cases():
+    """Training-time augmentation (pssr/data.py:476-480): every (rot90, flip axes) combination through the reference's _gen_pair,
+    crappifier=None, on a tile that needs reflect padding."""
+    rng = np.random.default_rng(43)
+    out = {}
+    hr = rng.integers(0, 60000, (2, 44, 60)).astype(np.uint16)
+    out["in"] = hr
+    k = 0
+    for rot in (False, True):
+        for axes in (1, 2, (1, 2)):
+            h, l = RD._gen_pair(hr, 64, 4, [rot, axes], None, None, None)
+            out[f"hr_{k}"], out[f"lr_{k}"] = h.numpy(), l.numpy()
+            out[f"code_{k}"] = np.array([int(rot), int(1 in (axes if isinstance(axes, tuple) else (axes,))),
+                                         int(2 in (axes if isinstance(axes, tuple) else (axes,)))])
+            k += 1
+    np.savez_compressed(os.path.join(OUT, "gen_pair_rot.npz"), **out)
+
+
 def tiling_stitch_cases():
     rng = np.random.default_rng(3)
     sheet = rng.integers(0, 256, (4, 150, 209)).astype(np.uint8)
@@ -119,7 +137,11 @@ def net_cases():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "rotation":      # added in round 2: does not touch the earlier fixtures
+        gen_pair_rotation_cases()
+        sys.exit(0)
     gen_pair_cases()
+    gen_pair_rotation_cases()
     tiling_stitch_cases()
     normalize_cases()
     net_cases()

@@ -91,3 +91,17 @@ def test_network_matches_reference_golden():
         err = float((y - torch.as_tensor(g[f"{tag}_y"])).abs().max())
         print(f"{tag}: max-abs vs the reference's golden output {err:.5f}")
         assert err < 2e-2          # reduced two-level nets (see tests/test_plan_cpu.py); the default-depth bar is 1e-2
+
+
+def test_training_rotation_matches_reference_golden():
+    from pssr2_b200 import ops
+    g = np.load(os.path.join(G, "gen_pair_rot.npz"))
+    src = g["in"]
+    F, h, w = src.shape
+    size = min(h, w, 64)
+    y0, x0 = (h - size) // 2, (w - size) // 2
+    for k in range(6):
+        rot, f1, f2 = (int(v) for v in g[f"code_{k}"])
+        table = ops.TileTable([_dev_sheet(src)], [0], [0], [y0], [x0], [size], [size], tile_xf=[rot | (f1 << 1) | (f2 << 2)])
+        lr, hr, _ = ops.crappify(table, 64, 4, None, frames=F, want_hr_f32=True)
+        assert np.array_equal(hr.cpu().numpy()[0], g[f"hr_{k}"]) and np.array_equal(lr.cpu().numpy()[0], g[f"lr_{k}"]), k

@@ -129,3 +129,48 @@ def test_second_device_while_first_is_current():
     assert all(np.array_equal(got[k], want[k]) for k in want)
     m = run_metrics(model, SlidingDataset(sheets, device="cuda:1", **kw), device="cuda:1", norm=True)
     assert all(np.isfinite(v) for v in m.values())
+
+
+def test_training_augmentation_matches_oracle():
+    """SURVEY 8f-2, the data side of train_paired: rot90 / flip of the padded tile before the downscale (pssr/data.py:476-480),
+    bit-exact against the oracle for every transform code, HR and LR, uint8 / uint16, with a reflect-padded tile; `loader`
+    walks the training items only and augments them, validation items never rotate."""
+    import random
+    from oracle import pipeline as OP
+    from pssr2_b200 import ops
+    from pssr2_b200.data import ImageDataset
+    rng = np.random.default_rng(3)
+    for dt, shape, hr_res, scale in ((np.uint8, (2, 64, 64), 64, 4), (np.uint16, (1, 50, 58), 64, 2)):
+        img = rng.integers(0, 255, shape).astype(dt)
+        for rot in (False, True):
+            for axes in (1, 2, (1, 2)):
+                ax = (axes,) if isinstance(axes, int) else axes
+                code = (1 if rot else 0) | (2 if 1 in ax else 0) | (4 if 2 in ax else 0)
+                F, h, w = img.shape
+                size = min(h, w, hr_res)
+                y0, x0 = ((h - size) // 2, (w - size) // 2) if [h, w] != [hr_res] * 2 else (0, 0)
+                t = torch.as_tensor(img.view(np.int16) if dt == np.uint16 else img).cuda()
+                table = ops.TileTable([t], [0], [0], [y0], [x0], [size], [size], tile_xf=[code])
+                lr, hr, hr8 = ops.crappify(table, hr_res, scale, None, frames=F, want_hr_f32=True, want_hr_u8=True)
+                whr, wlr = OP.gen_pair(img, hr_res, scale, None, rotation=[rot, axes])
+                assert np.array_equal(hr.cpu().numpy()[0], whr), (dt, rot, axes)
+                assert np.array_equal(lr.cpu().numpy()[0], wlr), (dt, rot, axes)
+                assert np.array_equal(hr8.cpu().numpy()[0, 0], np.clip(whr[F // 2], 0, 255).astype(np.uint8))
+    imgs = [rng.integers(0, 255, (1, 64, 64)).astype(np.uint8) for _ in range(10)]
+    ds = ImageDataset(imgs, hr_res=64, lr_scale=4, n_frames=1, val_split=0.2, crappifier=None, rotation=True)
+    assert len(ds.val_idx) == 2
+    plain = {i: ds.__getitem__(i, pp=True) for i in range(10)}
+    for i in ds.val_idx:                                   # validation items: never augmented
+        assert torch.equal(ds[i][0], plain[i][0])
+    random.seed(1)
+    seen, changed = 0, 0
+    for hr, lr in ds.loader(3, train=True):
+        assert hr.shape[1:] == (1, 64, 64) and lr.shape[1:] == (1, 16, 16)
+        seen += hr.shape[0]
+    assert seen == 8
+    random.seed(2)
+    for i in range(10):
+        if i not in ds.val_idx:
+            changed += int(not torch.equal(ds[i][0], plain[i][0]))
+    assert changed >= 5                                    # 7 of the 8 transform codes move pixels
+    assert sum(b[0].shape[0] for b in ds.loader(4, train=False)) == 2

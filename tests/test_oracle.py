@@ -106,3 +106,13 @@ def test_random_noise_sp_semantics():
     out = TP.random_noise(img, "s&p", 0.3, flipped=fl, salted=sa)
     assert out.dtype == np.float32
     assert np.all(out[fl & sa] == 1) and np.all(out[fl & ~sa] == 0) and np.array_equal(out[~fl], img[~fl])
+
+
+def test_gen_pair_rotation_golden():
+    """Training-time rot90 / flip (pssr/data.py:476-480) against the reference's own _gen_pair outputs."""
+    g = np.load(os.path.join(G, "gen_pair_rot.npz"))
+    for k in range(6):
+        rot, f1, f2 = (int(v) for v in g[f"code_{k}"])
+        axes = (1, 2) if f1 and f2 else (1 if f1 else 2)
+        hr, lr = OP.gen_pair(g["in"], 64, 4, None, rotation=[bool(rot), axes])
+        assert np.array_equal(hr, g[f"hr_{k}"]) and np.array_equal(lr, g[f"lr_{k}"]), k
