@@ -607,7 +607,7 @@ def run_ours(args):
     if not args.no_sub:
         with torch.no_grad():
             for key, fn in (("3", lambda: config3(c, sheets_per_rank=2, precision=args.precision)), ("4", lambda: config4(c, tiles_total=512)),
-                            ("5", lambda: config5(c, tiles_per_rank=8, precision=args.precision))):
+                            ("5", lambda: config5(c, tiles_per_rank=16, precision=args.precision))):
                 try:
                     subs[key] = fn()
                 except Exception as e:      # noqa: BLE001 -- a failing secondary config must not take the main line down

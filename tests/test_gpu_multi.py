@@ -72,5 +72,6 @@ def test_sharded_predict_equals_single(tmp_path):
     # stitched sheets: identical bytes, gathered on rank 0; each rank kept only its own sheets (+ at most one prefetched) resident
     assert outs[1]["sheet_shapes"] == outs[2]["sheet_shapes"] and len(outs[2]["sheets"]) == 3
     assert outs[1]["sheets"] == outs[2]["sheets"]
-    assert all(len(res) <= 2 for res in outs[2]["resident"]) and sorted(set(sum(outs[2]["resident"], []))) == [0, 1, 2]
+    # (three sheets of six tiles on two ranks: rank 0 owns sheets 0-1 and may have prefetched sheet 2, rank 1 touches sheet 2 only)
+    assert outs[2]["resident"][1] == [2] and set(outs[2]["resident"][0]) >= {0, 1}
     assert outs[1]["p3"] == outs[2]["p3"] and len(outs[2]["p3"]) == 18
