@@ -60,13 +60,16 @@ def _peak_sustained(burst_tf):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum summed over the conv launches of ONE step, from the ncu capture named below
-CONV_DRAM_BYTES_PER_STEP = 3876322304
-CONV_DRAM_SOURCE = ("profiles/r01_launches_v3_summary.txt (ncu launch list of `bench.py --kernels-only --precision fp16`, 37 conv launches "
-                    "of one step: 2823.8 MB read + 1052.6 MB written; the compensated fp16c plan adds the e5m2 copy of the last decoder "
-                    "output and the residual GEMM, see profiles/r02_*)")
+CONV_DRAM_BYTES = {"fp16c": 4775142400, "fp16": 3876322304, "bf16": 3876322304}
+CONV_DRAM_SOURCE = {"fp16c": "profiles/r02_launches_step_summary.txt (ncu launch list of `bench.py --kernels-only --no-sub`, 38 conv launches of one "
+                             "step of the compensated plan: 3467.1 MB read + 1308.0 MB written)",
+                    "fp16": "profiles/r01_launches_v3_summary.txt (37 conv launches of one step of the single-pass plan: 2823.8 MB read + 1052.6 MB written)"}
+CONV_DRAM_SOURCE["bf16"] = CONV_DRAM_SOURCE["fp16"]
 RECON_FLOPS_PER_TILE = 19.629e9
-RECON_DRAM_BYTES = 325600000
-RECON_DRAM_SOURCE = "profiles/r01_launches_v3_summary.txt launch #42 (175.1 MB read + 150.5 MB written)"
+RECON_DRAM_BYTES = {"fp16c": 446763776, "fp16": 325600000, "bf16": 325600000}
+RECON_DRAM_SOURCE = {"fp16c": "profiles/r02_v3_recon_pre.details.txt (ncu --set full: 280.2 MB read + 166.5 MB written)",
+                     "fp16": "profiles/r01_launches_v3_summary.txt launch #42 (175.1 MB read + 150.5 MB written)"}
+RECON_DRAM_SOURCE["bf16"] = RECON_DRAM_SOURCE["fp16"]
 
 
 def _synthetic_tiles(n, seed, device, size=TILE, frames=None, dtype="u16"):
@@ -637,7 +640,7 @@ def run_ours(args):
     roofline = {"bound": "tensor",
                 "kernel": f"conv_v3_kernel (tcgen05 cta_group::2 implicit GEMM: rows mode at 128^2, cols mode below): all {n_conv} conv launches of the step",
                 "achieved": round(achieved, 1), "peak": peak_sus, "unit": "TFLOP/s", "frac": round(achieved / peak_sus, 4),
-                "traffic": CONV_DRAM_BYTES_PER_STEP, "traffic_source": CONV_DRAM_SOURCE,
+                "traffic": CONV_DRAM_BYTES[args.precision], "traffic_source": CONV_DRAM_SOURCE[args.precision],
                 "peak_source": peak_src + " (bf16_tflops_sustained)", "peak_burst": peak_tf, "frac_of_burst": round(achieved / peak_tf, 4),
                 "algorithmic_flops_per_step": conv_flops, "issued_flops_per_step": issued,
                 "issued_tflops": round(issued / (conv_ms * 1e-3) / 1e12, 1),
@@ -649,7 +652,7 @@ def run_ours(args):
                     "ms": round(recon_ms, 3), "achieved": round(RECON_FLOPS_PER_TILE * BATCH / (recon_ms * 1e-3) / 1e12, 1),
                     "peak": peak_sus, "frac": round(RECON_FLOPS_PER_TILE * BATCH / (recon_ms * 1e-3) / 1e12 / peak_sus, 4),
                     "frac_of_burst": round(RECON_FLOPS_PER_TILE * BATCH / (recon_ms * 1e-3) / 1e12 / peak_tf, 4),
-                    "traffic": RECON_DRAM_BYTES, "traffic_source": RECON_DRAM_SOURCE},
+                    "traffic": RECON_DRAM_BYTES[args.precision], "traffic_source": RECON_DRAM_SOURCE[args.precision]},
                 "step_frac_of_peak": round(ALG_FLOPS_PER_TILE * BATCH / (ms_step * 1e-3) / 1e12 / peak_sus, 4)}
 
     # ---- the operand modes side by side (forward only, same weights): what the 1e-2 max-abs bar costs ---------
