@@ -49,10 +49,11 @@ static MetGeom metric_geom(int n, int h, int w) {
   MetGeom g;
   const int ow = w - 6 > 0 ? w - 6 : 1, oh = h - 6 > 0 ? h - 6 : 1;
   g.strips = ow <= kMetStep + 2 ? 1 : (ow - 2 + kMetStep - 1) / kMetStep;
-  // enough CTAs for ~6 per SM, at least 32 output rows per chunk (6 halo rows are re-computed per chunk: 19 % at 32 rows)
-  long long want = (148LL * 6 + (long long)n * g.strips - 1) / ((long long)n * g.strips);
+  // enough CTAs for ~10 per SM, at least 8 output rows per chunk (6 halo rows are re-read per chunk; taller chunks with fewer
+  // CTAs measured slower: 63 -> 68 us for 64 pairs of 512^2)
+  long long want = (148LL * 10 + (long long)n * g.strips - 1) / ((long long)n * g.strips);
   if (want < 1) want = 1;
-  int max_chunks = (oh + 31) / 32;
+  int max_chunks = (oh + 7) / 8;
   if (max_chunks < 1) max_chunks = 1;
   g.chunks = (int)(want < max_chunks ? want : max_chunks);
   g.rows_per_chunk = (oh + g.chunks - 1) / g.chunks;

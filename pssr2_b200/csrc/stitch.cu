@@ -153,10 +153,7 @@ __global__ void __launch_bounds__(128) stitch_band16_kernel(const uint8_t* __res
                                                             int n_cols, int T, int step, int margin, int out_h, int out_w, int band) {
   __shared__ int s_roff[kBandRows][3];
   __shared__ int s_nr[kBandRows];
-  __shared__ int s_multi;                  // some row of the band has more than one contributing tile row
   const int stack = blockIdx.z, Y0 = blockIdx.y * band;
-  if (threadIdx.x == 0) s_multi = 0;
-  __syncthreads();
   const int X = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
   const int tile_px = T * T;
   if (threadIdx.x < band) {
@@ -173,7 +170,6 @@ __global__ void __launch_bounds__(128) stitch_band16_kernel(const uint8_t* __res
       }
     }
     s_nr[threadIdx.x] = n;
-    if (n != 1 && Y < out_h) s_multi = 1;
   }
   int coff[3] = {0, 0, 0}, nc = 0;
   if (X < out_w) {
@@ -193,24 +189,6 @@ __global__ void __launch_bounds__(128) stitch_band16_kernel(const uint8_t* __res
   const uint8_t* tb = tiles + (size_t)stack * n_rows * n_cols * tile_px;
   uint8_t* ob = sheets + ((size_t)stack * out_h + Y0) * out_w + X;
   const int rows = min(band, out_h - Y0);
-  if (nc == 1 && s_multi == 0) {
-    // the common case -- this 16-pixel column and every row of the band lie inside ONE tile: a copy, four rows' loads in
-    // flight before the first store
-    const uint8_t* src = tb + coff[0];
-    int i = 0;
-    for (; i + 4 <= rows; i += 4) {
-      const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(src + s_roff[i][0]));
-      const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(src + s_roff[i + 1][0]));
-      const uint4 v2 = __ldg(reinterpret_cast<const uint4*>(src + s_roff[i + 2][0]));
-      const uint4 v3 = __ldg(reinterpret_cast<const uint4*>(src + s_roff[i + 3][0]));
-      *reinterpret_cast<uint4*>(ob + (size_t)i * out_w) = v0;
-      *reinterpret_cast<uint4*>(ob + (size_t)(i + 1) * out_w) = v1;
-      *reinterpret_cast<uint4*>(ob + (size_t)(i + 2) * out_w) = v2;
-      *reinterpret_cast<uint4*>(ob + (size_t)(i + 3) * out_w) = v3;
-    }
-    for (; i < rows; ++i) *reinterpret_cast<uint4*>(ob + (size_t)i * out_w) = __ldg(reinterpret_cast<const uint4*>(src + s_roff[i][0]));
-    return;
-  }
 #pragma unroll 4
   for (int i = 0; i < rows; ++i) {
     const int nr = s_nr[i];
