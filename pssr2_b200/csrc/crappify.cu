@@ -457,18 +457,28 @@ __global__ void __launch_bounds__(kCrapThreads, MINB) crappify_kernel(const Crap
   const bool interior = (row0 + nrows <= vh) && (col0 + ncols <= vw);
   const bool vec_ok = interior && xf == 0 && ((reinterpret_cast<uintptr_t>(sheet) & 15) == 0);
   if (vec_ok) {
+    // every 16-byte vector of the window goes global -> shared with cp.async: all ~2400 of them are in flight at once (the
+    // ld.global / st.shared loop exposed one DRAM latency per iteration) and the row / vector split is a multiply-shift
+    // (`i / vec_per_row` as an integer division was 17 % of the kernel's instructions)
     const int vec_per_row = p.raw_pitch / 16;
+    const uint32_t magic = ((1u << 22) + (uint32_t)vec_per_row - 1u) / (uint32_t)vec_per_row;     // exact for i * vec_per_row < 2^22
+    const uint8_t* g0 = reinterpret_cast<const uint8_t*>(fbase + (size_t)(ty + row0) * sheet_w + tx + col0);
+    const size_t row_bytes = (size_t)sheet_w * sizeof(T);
+    const uint32_t need = (uint32_t)ncols * (uint32_t)sizeof(T);
+    const uint32_t raw_s = (uint32_t)__cvta_generic_to_shared(raw);
     for (int i = threadIdx.x; i < nrows * vec_per_row; i += kCrapThreads) {
-      const int r = i / vec_per_row, v = i - r * vec_per_row;
-      const uint8_t* g = reinterpret_cast<const uint8_t*>(fbase + (size_t)(ty + row0 + r) * sheet_w + tx + col0);
-      const int ld = (int)(reinterpret_cast<uintptr_t>(g) & 15);
-      if (v == 0) lead[r] = ld;
-      const uint8_t* src = g - ld + (size_t)v * 16;
-      if (src < g + (size_t)ncols * sizeof(T)) {
-        // the vector holds at least one needed byte, lies inside the sheet's 16-byte-aligned extent
-        *reinterpret_cast<uint4*>(raw + (size_t)r * p.raw_pitch + v * 16) = __ldg(reinterpret_cast<const uint4*>(src));
-      }
+      const int r = (int)(((uint32_t)i * magic) >> 22), v = i - r * vec_per_row;
+      const uint8_t* g = g0 + (size_t)r * row_bytes;
+      const uint32_t ld = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15);
+      if (v == 0) lead[r] = (int)ld;
+      // the vector holds at least one needed byte, lies inside the sheet's 16-byte-aligned extent
+      if ((uint32_t)v * 16u < need + ld)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(raw_s + (uint32_t)r * (uint32_t)p.raw_pitch + (uint32_t)v * 16u),
+                     "l"(g - ld + (size_t)v * 16)
+                     : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else {
     for (int i = threadIdx.x; i < nrows * ncols; i += kCrapThreads) {
       const int r = i / ncols, c = i - r * ncols;
@@ -492,8 +502,8 @@ __global__ void __launch_bounds__(kCrapThreads, MINB) crappify_kernel(const Crap
       const int groups = (wown + 3) >> 2;
       const size_t n_hr = (size_t)p.hr_res * p.hr_res;
       const bool vec_st = (p.hr_res & 3) == 0 && (X0 & 3) == 0;
-      for (int i = threadIdx.x; i < hown * groups; i += kCrapThreads) {
-        const int ry = i / groups, g = i - ry * groups;
+      for (int ry = (int)(threadIdx.x >> 5); ry < hown; ry += kCrapThreads / 32)
+      for (int g = (int)(threadIdx.x & 31); g < groups; g += 32) {
         const int Y = Y0 + ry, X = X0 + 4 * g;
         const int r = Y - row0;
         const uint8_t* sb = raw + (size_t)r * p.raw_pitch + lead[r] + (size_t)(X - col0) * sizeof(T);
@@ -587,8 +597,8 @@ __global__ void __launch_bounds__(kCrapThreads, MINB) crappify_kernel(const Crap
 
   // ---- stage 3: vertical pass + noise chain + store -------------------------------------
   const Philox ph{p.seed_lo ^ (uint32_t)(p.tile_index0 + tile), p.seed_hi ^ (uint32_t)((p.tile_index0 + tile) >> 32)};
-  for (int i = threadIdx.x; i < ny * nx; i += kCrapThreads) {
-    const int yo = i / nx, xo = i - yo * nx;
+  for (int yo = (int)(threadIdx.x >> 5); yo < ny; yo += kCrapThreads / 32)
+  for (int xo = (int)(threadIdx.x & 31); xo < nx; xo += 32) {
     const int2 b = p.bounds[yy0 + yo];
     const T* src = inter + (size_t)(b.x - row0) * TL + xo;
     double val;  // carries either a float32 or a float64 quantity, exactly
