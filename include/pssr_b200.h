@@ -80,7 +80,10 @@ typedef struct {
 
 typedef struct {
   /* source sheets: `sheets` points at a DEVICE array of n_sheets device pointers; every sheet is
-   * [frames_total][sheet_h][sheet_w], dtype uint8 (elem_bytes=1) or uint16 (elem_bytes=2) */
+   * [frames_total][sheet_h][sheet_w], dtype uint8 (elem_bytes=1) or uint16 (elem_bytes=2).
+   * Allocation contract: 16-byte-aligned sheets are staged with aligned 16-byte vector copies, which may read up to 15 bytes
+   * past the last pixel of a sheet (never past its 16-byte granule): the allocation must extend to the next multiple of 16
+   * bytes, as cudaMalloc / torch allocations always do.  Misaligned sheets take the element-wise path. */
   const void* const* sheets;
   int32_t n_sheets;
   int32_t elem_bytes;

@@ -120,12 +120,25 @@ class _PlanModule(nn.Module):
         if x.dtype not in (torch.float32, torch.uint8):
             x = x.float()
         key = (tuple(x.shape), x.dtype, x.device.index, self.precision, self.fuse_tail)
+        # a plan holds folded / packed COPIES of the weights: any in-place update since it was built (optimizer step,
+        # p.data.copy_(), a BatchNorm buffer refresh) bumps a tensor version or moves a storage -> rebuild
+        stamp = self._weights_stamp()
         st = self._plans.get(key)
+        if st is not None and st.get("stamp") != stamp:
+            st["plan"].close()
+            st = None
         if st is None:
             with torch.no_grad():
                 st = self._build(x.shape, x.dtype, x.device)
+            st["stamp"] = stamp
             self._plans[key] = st
         return st, x
+
+    def _weights_stamp(self):
+        v = 0
+        for t in list(self.parameters()) + list(self.buffers()):
+            v = (v * 1000003 + t._version * 31 + t.data_ptr()) & 0xFFFFFFFFFFFF
+        return v
 
     @torch.no_grad()
     def forward(self, x):

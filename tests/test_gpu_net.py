@@ -168,3 +168,23 @@ def test_rdresunet_matches_oracle(cfg, shape):
     # the RDNet encoder's first stage (stem, LayerNorm, GELU expand / project at half resolution) sits on the same shallow path
     # to the output and is not compensated yet: emulated 1.2e-2 with the default layer scale, 2e-2 with the randomised one
     assert _psnr(got, want) >= 50.0 and d <= 3e-2
+
+
+def test_plan_follows_in_place_weight_updates():
+    """The plan caches folded copies of the weights; an in-place update after the first forward must invalidate it."""
+    from pssr2_b200.models import ResUNet
+    torch.manual_seed(7)
+    model = ResUNet(hidden=[64, 128], depth=0).eval().cuda()
+    x = torch.randint(0, 256, (1, 1, 32, 32), device="cuda").float()
+    y0 = model(x).clone()
+    assert torch.equal(model(x), y0)
+    with torch.no_grad():
+        model.encoder[0].conv[1].running_mean.add_(0.25)          # a BatchNorm buffer refresh
+    y1 = model(x).clone()
+    assert not torch.equal(y1, y0)
+    with torch.no_grad():
+        model.reconstruction.conv.weight.mul_(1.5)                 # an optimizer-style in-place step
+    assert not torch.equal(model(x), y1)
+    sd = {k: v.cpu().clone() for k, v in model.state_dict().items()}
+    want = resunet_forward(sd, x.cpu())
+    assert float((model(x).cpu() - want).abs().max()) <= 3e-2
