@@ -399,6 +399,20 @@ int pssr_normalize_preds(const uint8_t* hr, const uint8_t* hr_hat, uint8_t* hr_o
                          uint8_t* hr_hat_out, int32_t n, int32_t h, int32_t w, double pmin,
                          double pmax, void* workspace, void* stream);
 
+/* normalize_preds with hr_hat at a LOWER resolution than hr (pssr/util.py:179: `resize(hr_hat_norm, hr_norm.shape)` feeds the covariance
+ * only; `_collage_preds` normalises the low-resolution input against hr this way, pssr/predict.py:220-222).  The enlargement is
+ * skimage.transform.resize(order 1, mode "reflect") = scipy.ndimage.zoom(order=1, mode="mirror", grid_mode=True), evaluated in double.
+ * hr [n,h,w], hr_hat [n,hat_h,hat_w] uint8; outputs keep their own resolutions (either may be NULL).
+ * workspace: pssr_normalize_resized_workspace_bytes(n) bytes of device memory, 16-byte aligned. */
+int64_t pssr_normalize_resized_workspace_bytes(int32_t n);
+int pssr_normalize_preds_resized(const uint8_t* hr, const uint8_t* hr_hat, uint8_t* hr_out, uint8_t* hr_hat_out, int32_t n, int32_t h, int32_t w,
+                                 int32_t hat_h, int32_t hat_w, double pmin, double pmax, void* workspace, void* stream);
+
+/* Noise-profile histogram of `approximate_crappifier`'s objective (pssr/train.py:366-380):
+ * profile = float32(a) - float32(base); hist511 = np.histogram(profile, np.arange(-256, 256)) (int64 [511], last bin closed);
+ * *sum = sum of the profile (double).  a_kind: 0 uint8, 1 float32, 2 float64.  Both outputs are device memory, zeroed here. */
+int pssr_profile_hist(const void* a, int32_t a_kind, const uint8_t* base, int64_t n, int64_t* hist511, double* sum, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * File I/O edges: the reference reads sheets with tifffile.imread (pssr/data.py:566-571, :621-625) and
  * writes predictions / stitched sheets with tifffile.imwrite (pssr/predict.py:71, pssr/util.py:103).  These entry points

@@ -148,7 +148,8 @@ def normalize_minmax(x, pmin=0.1, pmax=99.9, eps=1e-20, dtype=np.float32):
 
 
 def normalize_preds(hr, hr_hat, pmin=0.1, pmax=99.9):
-    """pssr/util.py:139-191 for equal-shaped inputs (no skimage resize on this path)."""
+    """pssr/util.py:139-191; differing resolutions go through ``oracle.thirdparty.resize`` (util.py:179)."""
+    from .thirdparty import resize
     hr, hr_hat = np.asarray(hr), np.asarray(hr_hat)
     hr_shape, hh_shape = hr.shape, hr_hat.shape
     hr = hr.reshape(-1, *hr.shape[-2:])
@@ -162,7 +163,8 @@ def normalize_preds(hr, hr_hat, pmin=0.1, pmax=99.9):
         a = normalize_minmax(a, pmin, pmax)
         b = b - np.mean(b)
         a = a - np.mean(a)
-        amp = np.cov(b.flatten(), a.flatten())[0, 1] / np.var(b.flatten())
+        scaled = resize(b, a.shape) if b.shape != a.shape else b
+        amp = np.cov(scaled.flatten(), a.flatten())[0, 1] / np.var(b.flatten())
         b = amp * b
         a, b = (a - a.min()) * base_max, (b - a.min()) * base_max
         a, b = a / (a.mean() / base_mean), b / (b.mean() / base_mean)

@@ -72,10 +72,10 @@ def install_shims():
                          trunc_normal_=lambda t, std=1.0, **k: t.normal_(0, std))
         tm.models = _mod("timm.models", named_apply=tp.named_apply)
     if _absent("pytorch_msssim"):
-        _mod("pytorch_msssim", SSIM=_io_stub, MS_SSIM=_io_stub)
+        _mod("pytorch_msssim", SSIM=_io_stub, MS_SSIM=_io_stub, ssim=_io_stub, ms_ssim=_io_stub)
     if _absent("skopt"):
         sko = _mod("skopt", gp_minimize=_io_stub)
-        sko.space = _mod("skopt.space", Real=_io_stub, Integer=_io_stub)
+        sko.space = _mod("skopt.space", Real=_io_stub, Integer=_io_stub, Dimension=object)
         sko.utils = _mod("skopt.utils", use_named_args=_io_stub)
 
 

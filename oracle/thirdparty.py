@@ -80,8 +80,22 @@ def random_noise(image, mode="s&p", amount=0.05, rng=None, flipped=None, salted=
     return np.clip(out, low_clip, 1.0)
 
 
-def resize(image, output_shape, **kw):  # pssr/util.py:179, off the hot path
-    raise NotImplementedError("skimage.transform.resize is off the hot path")
+def resize(image, output_shape, **kw):
+    """skimage.transform.resize(image, output_shape) with its defaults (order 1, mode "reflect", clip, anti_aliasing only when an
+    axis shrinks), as called at pssr/util.py:179.  scikit-image >= 0.19 implements it as scipy.ndimage.zoom(order=1, mode="mirror",
+    grid_mode=True) -- scipy IS installed, so the interpolation itself is the library's; the wrapper around it is parity-unpinned
+    (scikit-image absent).  Shrinking (Gaussian anti-aliasing prefilter) is not restated."""
+    from scipy import ndimage as ndi
+    image = np.asarray(image)
+    if kw:
+        raise NotImplementedError("only the default arguments are restated")
+    if any(o < i for o, i in zip(output_shape, image.shape)):
+        raise NotImplementedError("anti-aliased shrinking is not restated")
+    if image.dtype == np.float16:
+        image = image.astype(np.float32)
+    zoom = [o / i for o, i in zip(output_shape, image.shape)]
+    out = ndi.zoom(image, zoom, order=1, mode="mirror", cval=0, grid_mode=True)
+    return np.clip(out, image.min(), image.max())          # clip=True: keep the input range
 
 
 def gaussian(image, sigma, channel_axis=None):  # Blur crappifier, out of scope

@@ -36,7 +36,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             return LIB_PATH
     objdir = os.path.join(_HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + os.environ.get("PSSR_NVCC_EXTRA", "").split()   # developer builds
     procs = []
     objs = []
     for s in srcs:
@@ -172,6 +172,10 @@ SYMBOLS = {
     "pssr_version": (c_char_p, []),
     "pssr_launch_count": (c_int64, []),
     "pssr_debug_trace": (c_int32, [c_void_p, c_int64]),
+    "pssr_normalize_resized_workspace_bytes": (c_int64, [c_int32]),
+    "pssr_normalize_preds_resized": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_double,
+                                               c_double, c_void_p, c_void_p]),
+    "pssr_profile_hist": (c_int32, [c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "pssr_tiff_probe": (c_int32, [c_char_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
     "pssr_tiff_read": (c_int32, [c_char_p, c_void_p, c_int64]),
     "pssr_tiff_write": (c_int32, [c_char_p, c_void_p, c_int32, c_int32, c_int32, c_int32]),

@@ -94,12 +94,26 @@ struct V3Params {
 
 // developer timeline (PSSR_DBG bit 16): per CTA 256 clock64 stamps -- [0] entry, [1] setup done, [2+2u] unit u: accumulator buffer
 // free (MMA warp), [3+2u] unit u committed, [64+2u] unit u accumulators ready (epilogue warp 4), [65+2u] unit u epilogue done,
-// [127] exit, [128+2u] unit u: first A stage landed, [192+u] TAIL: tail MMAs of unit u issued
+// [127] exit, [128+2u] unit u: first A stage landed, [129+2u] TAIL: MMA warp starts waiting for unit u's 16-bit activations,
+// [192+u] TAIL: tail MMAs of unit u issued, [232+2u] / [233+2u] (u < 8): epilogue warp 4 handed the activations over / saw the projections
 __device__ long long g_v3_trace[148 * 256];
 #define V3_TRACE(slot)                                                                                   \
   do {                                                                                                   \
     if ((p.dbg & 16) && lane == 0 && (slot) >= 0 && (slot) < 256) g_v3_trace[(blockIdx.x % 148) * 256 + (slot)] = clock64(); \
   } while (0)
+
+// developer build (-DPSSR_V3_WAITPROF): cycles the MMA warp spends in each kind of barrier wait, summed over the launch, in trace
+// slots [240] accumulator buffer, [241] input rows, [242] weight stages, [243] tail activations, [244] whole issue loop
+#ifdef PSSR_V3_WAITPROF
+#define V3_WAIT(cat, call)            \
+  do {                                \
+    const long long _t = clock64();   \
+    call;                             \
+    wprof[cat] += clock64() - _t;     \
+  } while (0)
+#else
+#define V3_WAIT(cat, call) call
+#endif
 
 __device__ __forceinline__ uint64_t v3_desc(uint32_t addr) {
   uint64_t d = (uint64_t)((addr >> 4) & 0x3FFFu);
@@ -588,6 +602,11 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
                 const int cnt = t_hi - t0 < gsf ? t_hi - t0 : gsf;
                 mbar_wait(b_empty(bs), bphase ^ 1u);
                 const uint32_t fbar = PAIR ? v3_mapa(b_full(bs), 0) : b_full(bs);
+                if ((p.dbg & 32) && k > 0) {            // developer ablation: stale weights, no shared-memory fill traffic
+                  if (rank == 0) mbar_arrive(b_full(bs));
+                  if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; }
+                  continue;
+                }
                 if (rank == 0) mbar_arrive_expect_tx(b_full(bs), (uint32_t)cnt * tapb * C);
                 for (int t = 0; t < cnt; ++t) {
                   const int kb = p.seg_kb0[sg] + (t0 + t) * cbs + cb;   // weights are packed tap-major, then channel block
@@ -631,6 +650,10 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
     int as = 0, bs = 0;
     uint32_t aphase = 0, bphase = 0;
     int it = 0;
+#ifdef PSSR_V3_WAITPROF
+    long long wprof[5] = {0, 0, 0, 0, 0};
+    const long long wprof_t0 = clock64();
+#endif
     // K segments packed into registers (bit 0: 3x3, bits 1..8: channel blocks, bits 9..: first K block): an indexed load from
     // the constant bank per segment would sit on the issue path of every unit
     uint32_t segw[6];
@@ -645,8 +668,9 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
 
     auto issue_tail = [&](int pit) {
       const int pbuf = pit & 1;
-      if (PAIR && x_tail_comp) v3_mbar_wait_cluster(p_full(pbuf), (uint32_t)(pit >> 1) & 1u);
-      else mbar_wait(p_full(pbuf), (uint32_t)(pit >> 1) & 1u);
+      if (pit < 31) V3_TRACE(129 + 2 * pit);
+      if (PAIR && x_tail_comp) V3_WAIT(3, v3_mbar_wait_cluster(p_full(pbuf), (uint32_t)(pit >> 1) & 1u));
+      else V3_WAIT(3, mbar_wait(p_full(pbuf), (uint32_t)(pit >> 1) & 1u));
       tc_fence_after();
       if (elect_one()) {
         const uint32_t cbase = tmem_base + (uint32_t)(pbuf * 256);
@@ -674,7 +698,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
     // the current group (row y0-1+i, pixel x0 = -1), plane 0.
     auto run_k = [&](const uint64_t (&ea)[T + 2]) {
       const int buf = it & 1;
-      mbar_wait(t_empty(buf), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      V3_WAIT(0, mbar_wait(t_empty(buf), ((uint32_t)(it >> 1) & 1u) ^ 1u));
       tc_fence_after();
       if (it < 31) V3_TRACE(2 + 2 * it);
       const uint32_t d0 = tmem_base + (uint32_t)(buf * 256);
@@ -691,7 +715,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
         for (int cb = 0; cb < cbs; ++cb, plane_desc += (k16 ? slot16_desc : f8 ? slot8_desc : slot_desc)) {
           uint64_t ad0 = 0;
           if (!ROWS) {
-            mbar_wait(a_full(as), aphase);
+            V3_WAIT(1, mbar_wait(a_full(as), aphase));
             tc_fence_after();
             ad0 = as ? adesc_s1 : adesc_s0;
           }
@@ -700,7 +724,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
             // e5m2 3x3 segment (streamed weights): two K = 32 MMAs per tap and 64-channel block, 2G taps per weight stage
 #pragma unroll
             for (int t0 = 0; t0 < 9; t0 += 2 * G) {
-              mbar_wait(b_full(bs), bphase);
+              V3_WAIT(2, mbar_wait(b_full(bs), bphase));
               tc_fence_after();
               const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)bs * bstep) + f8_fix;
               if (elect_one()) {
@@ -731,7 +755,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
               if (RES) {
                 bd = bdesc0 + (uint64_t)((uint32_t)(kb0 + t0 * cbs + cb) * tapstep);
               } else {
-                mbar_wait(b_full(bs), bphase);
+                V3_WAIT(2, mbar_wait(b_full(bs), bphase));
                 tc_fence_after();
                 bd = bdesc0 + (uint64_t)((uint32_t)bs * bstep);
               }
@@ -770,7 +794,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
             if (RES) {
               bd = bdesc0 + (uint64_t)((uint32_t)(kb0 + cb) * tapstep);
             } else {
-              mbar_wait(b_full(bs), bphase);
+              V3_WAIT(2, mbar_wait(b_full(bs), bphase));
               tc_fence_after();
               bd = bdesc0 + (uint64_t)((uint32_t)bs * bstep);
             }
@@ -815,7 +839,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
     // right after its last (bit i of relmask) -- with a ring of only T+2 rows the next rows load while this unit computes.
     auto run_k_rows = [&](const uint64_t (&ea)[T + 2], const int (&sl)[T + 2], const uint32_t (&ph)[T + 2], uint32_t newmask, uint32_t relmask) {
       const int buf = it & 1;
-      mbar_wait(t_empty(buf), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      V3_WAIT(0, mbar_wait(t_empty(buf), ((uint32_t)(it >> 1) & 1u) ^ 1u));
       tc_fence_after();
       if (it < 31) V3_TRACE(2 + 2 * it);
       const uint32_t d0 = tmem_base + (uint32_t)(buf * 256);
@@ -827,7 +851,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
 #pragma unroll
         for (int i = 0; i < T + 2; ++i) {
           const int need = (i - T) > -1 ? (i - T) : -1;
-          if (need == dy && ((newmask >> i) & 1u)) mbar_wait(r_full(sl[i]), ph[i]);
+          if (need == dy && ((newmask >> i) & 1u)) V3_WAIT(1, mbar_wait(r_full(sl[i]), ph[i]));
         }
         tc_fence_after();
         if (g == 0 && it < 31) V3_TRACE(128 + 2 * it);
@@ -845,7 +869,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
               constexpr int GS = G == 9 ? 3 : G;
 #pragma unroll
               for (int x0 = 0; x0 < 3; x0 += 2 * GS) {
-                mbar_wait(b_full(bs), bphase);
+                V3_WAIT(2, mbar_wait(b_full(bs), bphase));
                 tc_fence_after();
                 const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)bs * bstep) + f8_fix;
                 if (elect_one()) {
@@ -876,7 +900,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
                 if (RES) {
                   bd = bdesc0 + (uint64_t)((uint32_t)(kb0 + (3 * g + x0) * cbs + cb) * tapstep);
                 } else {
-                  mbar_wait(b_full(bs), bphase);
+                  V3_WAIT(2, mbar_wait(b_full(bs), bphase));
                   tc_fence_after();
                   bd = bdesc0 + (uint64_t)((uint32_t)bs * bstep);
                 }
@@ -913,7 +937,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
               if (RES) {
                 bd = bdesc0 + (uint64_t)((uint32_t)(kb0 + cb) * tapstep);
               } else {
-                mbar_wait(b_full(bs), bphase);
+                V3_WAIT(2, mbar_wait(b_full(bs), bphase));
                 tc_fence_after();
                 bd = bdesc0 + (uint64_t)((uint32_t)bs * bstep);
               }
@@ -1013,7 +1037,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
         } else {
 #pragma unroll
           for (int i = 0; i < T + 2; ++i)
-            if ((newmask >> i) & 1u) mbar_wait(r_full(sl[i]), ph[i]);
+            if ((newmask >> i) & 1u) V3_WAIT(1, mbar_wait(r_full(sl[i]), ph[i]));
           tc_fence_after();
           for (int nt = 0; nt < p.n_tiles; ++nt) run_k(ea);
           if (relmask != 0u) {
@@ -1032,6 +1056,11 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
       for (int unit = worker; unit < p.total_units; unit += workers) run_k(ea);
     }
     if (TAIL && it > 0) issue_tail(it - 1);
+#ifdef PSSR_V3_WAITPROF
+    wprof[4] = clock64() - wprof_t0;
+    if ((p.dbg & 16) && lane == 0)
+      for (int k = 0; k < 5; ++k) g_v3_trace[(blockIdx.x % 148) * 256 + 240 + k] = wprof[k];
+#endif
   } else if (warp >= 4) {
     // ==================================== epilogue ==========================================
     const int q4 = warp & 3;
@@ -1127,6 +1156,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
           else if (x_tail_comp) v3_arrive_cluster_release(v3_mapa(p_full(buf), 0));
           else v3_arrive_cluster(v3_mapa(p_full(buf), 0));
         }
+        if (warp == 4 && it < 8) V3_TRACE(232 + 2 * it);
         // ---- phase 2: the nine per-tap projections of this thread's pixel, two sub-positions per warp -------------
         int n, y, x;
         bool valid;
@@ -1145,6 +1175,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) conv_v3_kernel(const __grid_con
         }
         mbar_wait(z_full(buf), par);
         tc_fence_after();
+        if (warp == 4 && it < 8) V3_TRACE(233 + 2 * it);
         const int planes = r * r * 9;
         if (ROWS && p.tail_win48) {
           uint32_t zv0[16], zv1[16];

@@ -191,7 +191,9 @@ struct NormWs {                 // per image, 4096 bytes
   unsigned int hist_a[256];
   unsigned int hist_b[256];
   unsigned long long sum_ab;
-  unsigned long long pad[7];
+  unsigned long long n_b;       // differing resolutions: pixels of hr_hat (0: same size as hr)
+  double sza, sz;               // differing resolutions: sum zoom(hr_hat) * hr, sum zoom(hr_hat) over the hr grid
+  unsigned long long pad[4];
   uint8_t lut_a[256];
   uint8_t lut_b[256];
   uint8_t fill[4096 - 2048 - 64 - 512];
@@ -217,6 +219,73 @@ __global__ void __launch_bounds__(256) norm_stats_kernel(const uint8_t* __restri
   __syncthreads();
   if (ha[threadIdx.x]) atomicAdd(&ws[img].hist_a[threadIdx.x], ha[threadIdx.x]);
   if (hb[threadIdx.x]) atomicAdd(&ws[img].hist_b[threadIdx.x], hb[threadIdx.x]);
+}
+
+// 256-bin histogram of one image set (differing resolutions: hr and hr_hat are counted separately)
+__global__ void __launch_bounds__(256) norm_hist_kernel(const uint8_t* __restrict__ a, size_t n_px, NormWs* ws, int which) {
+  __shared__ unsigned int h[256];
+  const int img = blockIdx.y;
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const uint8_t* pa = a + (size_t)img * n_px;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_px; i += (size_t)gridDim.x * blockDim.x) atomicAdd(&h[pa[i]], 1u);
+  __syncthreads();
+  unsigned int* dst = which ? ws[img].hist_b : ws[img].hist_a;
+  if (h[threadIdx.x]) atomicAdd(&dst[threadIdx.x], h[threadIdx.x]);
+}
+
+// `resize(hr_hat_norm, hr_norm.shape)` of pssr/util.py:179 = skimage.transform.resize(order 1, mode "reflect", no anti-aliasing when
+// enlarging) = scipy.ndimage.zoom(order=1, mode="mirror", grid_mode=True): source coordinate (o + 0.5) * in / out - 0.5, reflected about
+// the first / last sample, linear interpolation.  Only two sums of the enlarged image are needed (the covariance is shift-invariant):
+// sum z * hr and sum z, per CTA in double, reduced in fixed order by norm_cross_finish_kernel.
+__device__ __forceinline__ void zoom_coord(int o, double zoom, int len, int& i0, int& i1, double& t) {
+  double cc = ((double)o + 0.5) * zoom - 0.5;
+  if (cc < 0.0) cc = -cc;
+  if (cc > (double)(len - 1)) cc = 2.0 * (double)(len - 1) - cc;
+  if (cc < 0.0) cc = 0.0;                     // len == 1
+  const double f = floor(cc);
+  i0 = (int)f;
+  t = cc - f;
+  i1 = i0 + 1 < len ? i0 + 1 : i0;
+}
+__global__ void __launch_bounds__(256) norm_cross_kernel(const uint8_t* __restrict__ hr, const uint8_t* __restrict__ hat, int h, int w, int hh, int hw,
+                                                         double* __restrict__ partials) {
+  const int img = blockIdx.y;
+  const uint8_t* pa = hr + (size_t)img * h * w;
+  const uint8_t* pb = hat + (size_t)img * hh * hw;
+  const double zy = (double)hh / (double)h, zx = (double)hw / (double)w;
+  double sza = 0.0, sz = 0.0;
+  const size_t n_px = (size_t)h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_px; i += (size_t)gridDim.x * blockDim.x) {
+    const int y = (int)(i / w), x = (int)(i - (size_t)y * w);
+    int y0, y1, x0, x1;
+    double ty, tx;
+    zoom_coord(y, zy, hh, y0, y1, ty);
+    zoom_coord(x, zx, hw, x0, x1, tx);
+    // scipy applies the separable weights as a product over the 2 x 2 support
+    const double z = (1.0 - ty) * ((1.0 - tx) * pb[(size_t)y0 * hw + x0] + tx * pb[(size_t)y0 * hw + x1]) +
+                     ty * ((1.0 - tx) * pb[(size_t)y1 * hw + x0] + tx * pb[(size_t)y1 * hw + x1]);
+    sza += z * (double)pa[i];
+    sz += z;
+  }
+  __shared__ double ra[8], rz[8];
+  sza = warp_sum(sza); sz = warp_sum(sz);
+  if ((threadIdx.x & 31) == 0) { ra[threadIdx.x >> 5] = sza; rz[threadIdx.x >> 5] = sz; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, z = 0.0;
+    for (int k = 0; k < 8; ++k) { a += ra[k]; z += rz[k]; }
+    partials[((size_t)img * gridDim.x + blockIdx.x) * 2 + 0] = a;
+    partials[((size_t)img * gridDim.x + blockIdx.x) * 2 + 1] = z;
+  }
+}
+__global__ void norm_cross_finish_kernel(const double* __restrict__ partials, int parts, unsigned long long n_b, NormWs* ws) {
+  const int img = blockIdx.x;
+  if (threadIdx.x == 0) {
+    double a = 0.0, z = 0.0;
+    for (int k = 0; k < parts; ++k) { a += partials[((size_t)img * parts + k) * 2]; z += partials[((size_t)img * parts + k) * 2 + 1]; }
+    ws[img].sza = a; ws[img].sz = z; ws[img].n_b = n_b;
+  }
 }
 
 // value at sorted position `idx` of the multiset described by a 256-bin histogram
@@ -247,6 +316,8 @@ __global__ void __launch_bounds__(256) norm_lut_kernel(NormWs* ws, unsigned long
   __shared__ double s_amp, s_mean_hh2;
   const int v = threadIdx.x;
   const double N = (double)n_px;
+  const bool resized = W.n_b != 0;                                       // hr_hat has its own resolution (util.py:179)
+  const double NB = resized ? (double)W.n_b : N;
   if (v == 0) {
     double sa = 0, sb = 0, sbb = 0;
     int amin = 255;
@@ -262,10 +333,11 @@ __global__ void __launch_bounds__(256) norm_lut_kernel(NormWs* ws, unsigned long
     double m = 0.0;
     for (int k = 0; k < 256; ++k) m += (double)W.hist_a[k] * (double)(((float)k - xmin) / den);
     const float mean_hn = (float)(m / N);
-    const float mean_b = (float)(sb / N);                               // util.py:176
+    const float mean_b = (float)(sb / NB);                              // util.py:176
     // np.cov(hr_hat_c, hr_c)[0,1] (ddof=1, float64) / np.var(hr_hat_c) (ddof=0)  -- util.py:180
-    const double cov = ((double)W.sum_ab - sa * sb / N) / (double)den / (N - 1.0);
-    const double var = (double)(float)((sbb - sb * sb / N) / N);
+    // (differing resolutions: hr_hat enlarged to the hr grid -- sum z * hr and sum z replace sum ab and sum b)
+    const double cov = resized ? (W.sza - sa * W.sz / N) / (double)den / (N - 1.0) : ((double)W.sum_ab - sa * sb / N) / (double)den / (N - 1.0);
+    const double var = (double)(float)((sbb - sb * sb / NB) / NB);
     s_amp = cov / var;
     s_xmin = xmin; s_den = den; s_mean_hn = mean_hn; s_mean_b = mean_b;
     s_min_hr = (((float)amin - xmin) / den) - mean_hn;                  // hr_norm.min() after centring
@@ -285,7 +357,7 @@ __global__ void __launch_bounds__(256) norm_lut_kernel(NormWs* ws, unsigned long
     double ma = 0, mb = 0;
     for (int k = 0; k < 256; ++k) { ma += red_a[k]; mb += red_b[k]; }
     s_mean_hr2 = (float)(ma / N);
-    s_mean_hh2 = mb / N;
+    s_mean_hh2 = mb / NB;
   }
   __syncthreads();
   const float hr3 = hr2 / (s_mean_hr2 / s_base_mean);                   // util.py:185
@@ -310,9 +382,87 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const uint8_t* __restri
   }
 }
 
+// ------------------------------------------------------------------- noise-profile histogram
+// `_Crappifier_Objective.sample` (pssr/train.py:366-380): profile = image.astype(float32) - base.astype(float32);
+// np.histogram(profile, np.arange(-256, 256)) -> 511 bins [k-256, k-255), the last one closed at 255; plus the profile's sum
+// (its mean is the objective's second term).  Shared-memory histogram per CTA, one global atomic per non-empty bin.
+template <typename A>
+__global__ void __launch_bounds__(256) profile_hist_kernel(const A* __restrict__ a, const uint8_t* __restrict__ base, size_t n,
+                                                           unsigned long long* __restrict__ hist, double* __restrict__ sum) {
+  __shared__ unsigned int h[511];
+  __shared__ double red[8];
+  for (int i = threadIdx.x; i < 511; i += blockDim.x) h[i] = 0u;
+  __syncthreads();
+  double s = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = (float)a[i] - (float)base[i];
+    s += (double)v;
+    if (v >= -256.f && v <= 255.f) {
+      int k = (int)floorf(v) + 256;
+      if (k > 510) k = 510;
+      atomicAdd(&h[k], 1u);
+    }
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    atomicAdd(sum, t);
+  }
+  for (int i = threadIdx.x; i < 511; i += blockDim.x)
+    if (h[i] != 0u) atomicAdd(&hist[i], (unsigned long long)h[i]);
+}
+
 }  // namespace pssr
 
 using namespace pssr;
+
+extern "C" int pssr_profile_hist(const void* a, int32_t a_kind, const uint8_t* base, int64_t n, int64_t* hist511, double* sum, void* stream) {
+  PSSR_REQUIRE(a && base && hist511 && sum && n >= 0 && a_kind >= 0 && a_kind <= 2, PSSR_EINVAL, "profile_hist: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  PSSR_CHECK_CUDA(cudaMemsetAsync(hist511, 0, 511 * sizeof(int64_t), st));
+  PSSR_CHECK_CUDA(cudaMemsetAsync(sum, 0, sizeof(double), st));
+  if (n == 0) return PSSR_OK;
+  long long blocks = (n + 256 * 8 - 1) / (256 * 8);
+  const long long cap = (long long)device_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  unsigned long long* h = reinterpret_cast<unsigned long long*>(hist511);
+  if (a_kind == 0) profile_hist_kernel<uint8_t><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(a), base, (size_t)n, h, sum);
+  else if (a_kind == 1) profile_hist_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float*>(a), base, (size_t)n, h, sum);
+  else profile_hist_kernel<double><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const double*>(a), base, (size_t)n, h, sum);
+  count_launch();
+  PSSR_CHECK_CUDA(cudaGetLastError());
+  return PSSR_OK;
+}
+
+extern "C" int64_t pssr_normalize_resized_workspace_bytes(int32_t n) { return n <= 0 ? 0 : (int64_t)n * (4096 + 256 * 16); }
+
+extern "C" int pssr_normalize_preds_resized(const uint8_t* hr, const uint8_t* hr_hat, uint8_t* hr_out, uint8_t* hr_hat_out, int32_t n, int32_t h,
+                                            int32_t w, int32_t hat_h, int32_t hat_w, double pmin, double pmax, void* workspace, void* stream) {
+  PSSR_REQUIRE(hr && hr_hat && workspace && n >= 1 && h >= 1 && w >= 1 && hat_h >= 1 && hat_w >= 1, PSSR_EINVAL, "normalize_preds: bad arguments");
+  PSSR_REQUIRE(((uintptr_t)workspace & 15) == 0, PSSR_EINVAL, "normalize_preds: workspace must be 16-byte aligned");
+  PSSR_REQUIRE(n <= 65535, PSSR_EUNSUP, "normalize_preds: at most 65535 images per call");
+  PSSR_REQUIRE(hat_h <= h && hat_w <= w, PSSR_EUNSUP, "normalize_preds: hr_hat larger than hr needs skimage's anti-aliasing filter (not on this path)");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  NormWs* ws = reinterpret_cast<NormWs*>(workspace);
+  double* partials = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(workspace) + sizeof(NormWs) * (size_t)n);
+  const size_t na = (size_t)h * w, nb = (size_t)hat_h * hat_w;
+  PSSR_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(NormWs) * (size_t)n, st));
+  auto blocks = [](size_t px, int cap) { long long b = (long long)((px + 256 * 16 - 1) / (256 * 16)); return (int)(b < 1 ? 1 : (b > cap ? cap : b)); };
+  norm_hist_kernel<<<dim3(blocks(na, 1024), n), 256, 0, st>>>(hr, na, ws, 0);
+  norm_hist_kernel<<<dim3(blocks(nb, 1024), n), 256, 0, st>>>(hr_hat, nb, ws, 1);
+  const int parts = blocks(na, 256);
+  norm_cross_kernel<<<dim3(parts, n), 256, 0, st>>>(hr, hr_hat, h, w, hat_h, hat_w, partials);
+  norm_cross_finish_kernel<<<n, 32, 0, st>>>(partials, parts, (unsigned long long)nb, ws);
+  norm_lut_kernel<<<n, 256, 0, st>>>(ws, (unsigned long long)na, pmin, pmax);
+  if (hr_out) norm_apply_kernel<<<dim3(blocks(na, 1024), n), 256, 0, st>>>(hr, hr, hr_out, nullptr, na, ws);
+  if (hr_hat_out) norm_apply_kernel<<<dim3(blocks(nb, 1024), n), 256, 0, st>>>(hr_hat, hr_hat, nullptr, hr_hat_out, nb, ws);
+  count_launch(5 + (hr_out ? 1 : 0) + (hr_hat_out ? 1 : 0));
+  PSSR_CHECK_CUDA(cudaGetLastError());
+  return PSSR_OK;
+}
 
 extern "C" int64_t pssr_metric_workspace_bytes(int32_t n, int32_t h, int32_t w) {
   if (n <= 0 || h <= 0 || w <= 0) return 0;

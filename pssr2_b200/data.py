@@ -321,7 +321,9 @@ class _DeviceDataset(Dataset):
                                  "use batch_size=1 or a fixed n_frames")
             return {k: (torch.cat([p[k] for p in parts]) if parts[0][k] is not None else None) for k in ("lr", "hr", "hr_u8")}
         frames = self._frames_window(_get_image_idx(indices[0], self.slices, tiles_)[0])
-        xf = [self._draw_rotation(i) for i in indices] if augment and not self.is_lr else None
+        xf = getattr(self, "_forced_xf", None)          # paired datasets hand the SAME codes to their HR and LR halves
+        if xf is None:
+            xf = [self._draw_rotation(i) for i in indices] if augment and not self.is_lr else None
         table = self._table(indices, xf)
         lr_res_scale = self.lr_scale
         if self.is_lr:
@@ -487,3 +489,134 @@ class ImageDataset(_DeviceDataset):
     def _get_name(self, idx):
         image_idx, idx = _get_image_idx(idx, self.slices)
         return self.hr_files[image_idx].split('.')[0] + (f"_{idx}" if self.n_frames is not None else "")
+
+
+class _PairedDataset(Dataset):
+    """Ground-truth high- / low-resolution pairs without a crappifier (pssr/data.py:268-346, :348-470, `_transform_pair` :497-516).
+    Two device-resident halves -- the HR images at ``hr_res`` and the LR images at ``hr_res // lr_scale``, each cropped / padded by
+    the gather kernel in its identity-resample mode -- indexed together and augmented with the same rot90 / flip code."""
+
+    is_lr = False
+    crappifier = None
+    extra_hr_files = None
+
+    def _pair(self, hr_ds, lr_ds, hr_res, lr_scale, rotation, nf, val_split, split_seed):
+        self._hr, self._lr = hr_ds, lr_ds
+        if len(hr_ds.hr_files) != len(lr_ds.hr_files):
+            raise FileNotFoundError(f"Mismatch between amounts of high-low-resolution images. Found {len(hr_ds.hr_files)} high-resolution "
+                                    f"and {len(lr_ds.hr_files)} low-resolution images.")
+        self.hr_files, self.lr_files = hr_ds.hr_files, lr_ds.hr_files
+        # the reference counts slices from the HR stack and max(n_frames) (data.py:312) and reads slice i of BOTH stacks; the halves
+        # count with their own frame window, so an item is addressed as (image, slice) in each of them
+        nfm = None if nf is None else max(nf)
+        self.slices = [1 if nfm is None else f // nfm for f in hr_ds._frames_total]
+        tiles = getattr(hr_ds, "tiles", None)
+        self.val_idx = _get_val_idx(self.slices, val_split, split_seed, tiles)
+        self.n_frames = nf
+        self.hr_res, self.lr_scale, self.rotation = hr_res, lr_scale, rotation
+        self.crop_res = hr_ds.crop_res
+        self.device = hr_ds.device
+
+    def __len__(self):
+        tiles = getattr(self, "tiles", None)
+        return sum(s * (t if tiles else 1) for s, t in zip(self.slices, tiles or [1] * len(self.slices)))
+
+    def _inner(self, ds, idx):
+        """Flat index of item ``idx`` (counted with this dataset's slices) inside one half (counted with its own)."""
+        tiles = getattr(self, "tiles", None)
+        image_idx, local = _get_image_idx(idx, self.slices, tiles)
+        if tiles:
+            tile, sl = local // self.slices[image_idx], local % self.slices[image_idx]
+            local = tile * ds.slices[image_idx] + sl
+        return sum(s * (t if tiles else 1) for s, t in zip(ds.slices[:image_idx], (tiles or [1] * len(ds.slices))[:image_idx])) + local
+
+    def batch(self, indices, augment=False, **_):
+        indices = list(indices)
+        xf = None
+        if augment and self.rotation:
+            vs = set(self.val_idx)
+            xf = []
+            for i in indices:
+                if i in vs:
+                    xf.append(0)
+                else:
+                    rot, axes = bool(random.getrandbits(1)), random.choice((1, 2, (1, 2)))
+                    axes = (axes,) if isinstance(axes, int) else axes
+                    xf.append((1 if rot else 0) | (2 if 1 in axes else 0) | (4 if 2 in axes else 0))
+        self._hr._forced_xf = self._lr._forced_xf = xf
+        try:
+            hr = self._hr.batch([self._inner(self._hr, i) for i in indices])["lr"]      # identity-resample mode: the cropped / padded tile
+            lr = self._lr.batch([self._inner(self._lr, i) for i in indices])["lr"]
+        finally:
+            self._hr._forced_xf = self._lr._forced_xf = None
+        return {"hr": hr, "lr": lr, "hr_u8": None}
+
+    def __getitem__(self, idx, pp=False):
+        if idx >= len(self):
+            raise IndexError(f"Tried to retrieve invalid image. Index {idx} is not less than {len(self)} total image frame slices.")
+        b = self.batch([idx], augment=not pp)
+        return b["hr"][0], b["lr"][0]
+
+    def loader(self, batch_size, train=True):
+        """See ``_DeviceDataset.loader``: paired batches for ``train_paired`` (pssr/train.py:75-96)."""
+        if train:
+            vs = set(self.val_idx)
+            idx = [i for i in range(len(self)) if i not in vs]
+            random.shuffle(idx)
+        else:
+            idx = list(self.val_idx)
+            np.random.seed(0)
+            np.random.shuffle(idx)
+        for s in range(0, len(idx), batch_size):
+            b = self.batch(idx[s:s + batch_size], augment=train)
+            yield b["hr"], b["lr"]
+
+
+def _silence(fn, *a, **k):
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return fn(*a, **k)
+
+
+class PairedImageDataset(_PairedDataset):
+    def __init__(self, hr_path, lr_path, hr_res: int = 512, lr_scale: int = 4, n_frames=-1, extension: str = "tif", val_split: float = 1,
+                 rotation: bool = True, split_seed: int = None, transforms=None, device="cuda"):
+        r"""Paired pre-tiled high- / low-resolution images (pssr/data.py:268-346)."""
+        super().__init__()
+        if transforms is not None:
+            raise NotImplementedError("transforms are outside the accelerated path")
+        nf = _get_n_frames(n_frames)
+        hr = _silence(ImageDataset, hr_path, hr_res=hr_res, lr_scale=-1, crappifier=None, n_frames=-1 if nf is None else nf[1], extension=extension,
+                      val_split=val_split, rotation=False, split_seed=split_seed, device=device)
+        lr = _silence(ImageDataset, lr_path, hr_res=hr_res // lr_scale, lr_scale=-1, crappifier=None, n_frames=-1 if nf is None else nf[0],
+                      extension=extension, val_split=val_split, rotation=False, split_seed=split_seed, device=device)
+        self._pair(hr, lr, hr_res, lr_scale, rotation, nf, val_split, split_seed)
+
+    def _get_name(self, idx):
+        image_idx, idx = _get_image_idx(idx, self.slices)
+        return self.lr_files[image_idx].split('.')[0] + (f"_{idx}" if self.n_frames is not None else "")
+
+
+class PairedSlidingDataset(_PairedDataset):
+    def __init__(self, hr_path, lr_path, hr_res: int = 512, lr_scale: int = 4, overlap: int = 128, n_frames=-1, slide: bool = False,
+                 stack: str = "TZ", extension: str = "tif", preload: bool = True, val_split: float = 1, rotation: bool = True,
+                 split_seed: int = None, transforms=None, device="cuda"):
+        r"""Paired high- / low-resolution image sheets tiled with matching windows (pssr/data.py:348-470)."""
+        super().__init__()
+        if transforms is not None:
+            raise NotImplementedError("transforms are outside the accelerated path")
+        nf = _get_n_frames(n_frames)
+        hr = _silence(SlidingDataset, hr_path, hr_res=hr_res, lr_scale=-1, crappifier=None, overlap=overlap, n_frames=-1 if nf is None else nf[1],
+                      slide=slide, stack=stack, extension=extension, preload=preload, val_split=val_split, rotation=False,
+                      split_seed=split_seed, device=device)
+        lr = _silence(SlidingDataset, lr_path, hr_res=hr_res // lr_scale, lr_scale=-1, crappifier=None, overlap=(overlap or 0) // lr_scale,
+                      n_frames=-1 if nf is None else nf[0], slide=slide, stack=stack, extension=extension, preload=preload,
+                      val_split=val_split, rotation=False, split_seed=split_seed, device=device)
+        self.tiles = hr.tiles
+        self._pair(hr, lr, hr_res, lr_scale, rotation, nf, val_split, split_seed)
+
+    def _get_name(self, idx):
+        image_idx, idx = _get_image_idx(idx, self.slices, self.tiles)
+        return f"{self.lr_files[image_idx].split('.')[0]}_{idx // self.slices[image_idx]}_{idx % self.slices[image_idx]}"

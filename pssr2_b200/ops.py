@@ -213,3 +213,34 @@ def normalize_preds_u8(hr: torch.Tensor, hr_hat: torch.Tensor, pmin=0.1, pmax=99
         _lib.check(_lib.lib().pssr_normalize_preds(hr.data_ptr(), hr_hat.data_ptr(), oa.data_ptr(), ob.data_ptr(), n, h, w, pmin, pmax,
                                                    ws.data_ptr(), _lib.current_stream_ptr(hr.device)), "pssr_normalize_preds")
     return oa, ob
+
+
+def normalize_preds_resized_u8(hr: torch.Tensor, hr_hat: torch.Tensor, pmin=0.1, pmax=99.9):
+    """normalize_preds (pssr/util.py:139-191) for uint8 hr [n,H,W] and a LOWER-resolution hr_hat [n,h,w] (util.py:179)."""
+    hr, hr_hat = _cuda(hr, "hr").contiguous(), _cuda(hr_hat, "hr_hat").contiguous()
+    _lib.same_device(hr, hr_hat)
+    n, h, w = hr.shape
+    hh, hw = hr_hat.shape[-2:]
+    oa, ob = torch.empty_like(hr), torch.empty_like(hr_hat)
+    with _lib.on_device(hr.device):
+        ws = torch.empty(int(_lib.lib().pssr_normalize_resized_workspace_bytes(n)), dtype=torch.uint8, device=hr.device)
+        _lib.check(_lib.lib().pssr_normalize_preds_resized(hr.data_ptr(), hr_hat.data_ptr(), oa.data_ptr(), ob.data_ptr(), n, h, w, hh, hw,
+                                                           pmin, pmax, ws.data_ptr(), _lib.current_stream_ptr(hr.device)),
+                   "pssr_normalize_preds_resized")
+    return oa, ob
+
+
+def profile_hist(a: torch.Tensor, base: torch.Tensor):
+    """Noise-profile histogram of `approximate_crappifier`'s objective (pssr/train.py:366-380): (int64 [511] counts of
+    float32(a) - float32(base) over np.arange(-256, 256), float64 sum of the profile).  a: uint8 / float32 / float64, base: uint8."""
+    a, base = _cuda(a, "a").contiguous(), _cuda(base, "base").contiguous()
+    _lib.same_device(a, base)
+    kind = {torch.uint8: 0, torch.float32: 1, torch.float64: 2}.get(a.dtype)
+    if kind is None or base.dtype != torch.uint8 or a.numel() != base.numel():
+        raise ValueError("profile_hist expects a uint8 / float32 / float64 tensor and a uint8 base of the same size")
+    hist = torch.empty(511, dtype=torch.int64, device=a.device)
+    total = torch.empty(1, dtype=torch.float64, device=a.device)
+    with _lib.on_device(a.device):
+        _lib.check(_lib.lib().pssr_profile_hist(a.data_ptr(), kind, base.data_ptr(), a.numel(), hist.data_ptr(), total.data_ptr(),
+                                                _lib.current_stream_ptr(a.device)), "pssr_profile_hist")
+    return hist, total

@@ -220,6 +220,81 @@ def predict_images(model: nn.Module, dataset, device: str = "cuda", batch_size=N
         return outs if rank_local else D.gather_dict(outs)
 
 
+def _collage_preds(lr8, hr_hat8, hr8, norm: bool = False, max_images: int = 5, crop_res: int = None, lr_scale: int = 4):
+    """pssr/predict.py:213-243 on uint8 device tensors [n,1,h,w] (what `_pred_array` yields): crop, normalise on the device
+    (hr_hat against hr, then the low-resolution input against the normalised hr -- the differing-resolution path of
+    `normalize_preds`, util.py:179), then the reference's Pillow layout: images stacked vertically, the three columns
+    (input enlarged with NEAREST | prediction | ground truth) side by side."""
+    from PIL import Image
+    from .util import normalize_preds
+    crop_res = hr_hat8.shape[-1] if crop_res is None else crop_res
+    lr_scale = int(hr_hat8.shape[-1] / lr8.shape[-1]) if lr_scale is None else lr_scale
+    lr8 = lr8[:, :, :crop_res // lr_scale, :crop_res // lr_scale].contiguous()
+    hr_hat8 = hr_hat8[:, :, :crop_res, :crop_res].contiguous()
+    hr8 = None if hr8 is None else hr8[:, :, :crop_res, :crop_res].contiguous()
+    if norm:
+        hr8, hr_hat8 = normalize_preds(hr8, hr_hat8)
+        _, lr8 = normalize_preds(hr8, lr8)
+
+    def stack(data):
+        images = [Image.fromarray(im) for im in data[:min(max_images, len(data)), 0].cpu().numpy()]
+        width, height = images[0].width, images[0].height
+        out = Image.new("L", (width, height * len(images)))
+        for k, im in enumerate(images):
+            out.paste(im, (0, height * k))
+        return out
+
+    lr_im, hat_im, hr_im = stack(lr8), stack(hr_hat8), None if hr8 is None else stack(hr8)
+    lr_im = lr_im.resize((hat_im.width, hat_im.height), Image.Resampling.NEAREST)
+    if hr_im is not None and hat_im.size != hr_im.size:
+        hat_im = hat_im.resize((hr_im.width, hr_im.height), Image.Resampling.NEAREST)
+    cols = [lr_im, hat_im] + ([hr_im] if hr_im is not None else [])
+    row = Image.new("L", (cols[0].width * len(cols), cols[0].height))
+    for k, im in enumerate(cols):
+        row.paste(im, (cols[0].width * k, 0))
+    return row
+
+
+def predict_collage(model: nn.Module, dataset, device: str = "cuda", norm: bool = True, n_images: int = None, prefix: str = None,
+                    out_dir: str = "preds", callbacks=None):
+    r"""Saves an image collage of vertically stacked rows of the low-resolution input, the PSSR prediction and the high-resolution
+    ground truth, in that order (pssr/predict.py:85-142).  Crappification, forward pass, `_pred_array` and the normalisation run on
+    the device; only the uint8 rows travel to the host, where Pillow lays them out and writes the PNG like the reference.
+    Only evaluation images are used; the order is the reference's (``np.random.seed(0)`` shuffle when ``val_split < 1``)."""
+    from PIL import Image
+    if norm and dataset.is_lr:
+        raise ValueError("Dataset must be paired with high-low-resolution images for normalization.")
+    if not str(device).startswith("cuda"):
+        raise RuntimeError("pssr2_b200.predict_collage runs on CUDA devices only (no CPU fallback); pass device='cuda'")
+    callbacks, callback_locals = _get_callbacks(callbacks)
+    n_images = min(50, len(dataset)) if n_images is None else n_images
+    _to_device(model, device)
+    model.eval()
+
+    order = list(dataset.val_idx)
+    if len(dataset.val_idx) < len(dataset):          # only shuffle if val_split < 1 (data.py:737-749, seed=True)
+        np.random.seed(0)
+        np.random.shuffle(order)
+    collage = Image.new("L", (dataset.crop_res * (2 if dataset.is_lr else 3), dataset.crop_res * n_images))
+    with torch.no_grad():
+        for idx, data_idx in enumerate(order):
+            lr, hr8 = _batch(dataset, [data_idx], device, want_hr_u8=not dataset.is_lr, tile_index0=idx)
+            hr_hat8 = _pred_u8(model, lr)
+            c = lr.shape[1] // 2
+            lr8 = lr[:, c:c + 1].clamp(0, 255).to(torch.uint8)         # `_pred_array` of the input
+            collage.paste(_collage_preds(lr8, hr_hat8, hr8, norm, 1, dataset.crop_res, dataset.lr_scale), (0, dataset.crop_res * idx))
+            for idx, callback in enumerate(callbacks):                 # (sic: the reference reuses `idx` here, predict.py:132)
+                if callback_locals[idx]:
+                    callback(locals())
+                else:
+                    callback()
+            if idx >= n_images - 1:
+                break
+    os.makedirs(out_dir, exist_ok=True)
+    collage.save(f"{out_dir}/{prefix + '_' if prefix else ''}collage_{n_images}.png")
+
+
+
 def test_metrics(model: nn.Module, dataset, device: str = "cuda", metrics=["mse", "pixel", "psnr", "ssim"], avg: bool = True,
                  norm: bool = True, callbacks=None, batch_size: int = 1, item0_quirk: bool = True):
     r"""Computes restoration metrics of predicted vs ground truth images (pssr/predict.py:144-211).

@@ -57,12 +57,16 @@ def normalize_preds(hr, hr_hat, pmin: float = 0.1, pmax: float = 99.9):
     a, b = a.reshape(-1, *a.shape[-2:]), b.reshape(-1, *b.shape[-2:])
     if len(a) != len(b):
         raise ValueError(f"hr and hr_hat must have the same number of images. Received {len(a)} and {len(b)} images respectively.")
-    if a.shape != b.shape:
-        raise NotImplementedError("normalize_preds with differing hr / hr_hat resolutions (skimage.transform.resize, util.py:179) "
-                                  "is off the accelerated path")
     if a.dtype != torch.uint8 or b.dtype != torch.uint8:
         raise TypeError("the device normalize_preds expects uint8 images (what `_pred_array` produces, predict.py:245-246)")
-    oa, ob = ops.normalize_preds_u8(a.cuda(), b.cuda(), pmin, pmax)
+    if a.shape != b.shape:
+        # util.py:179: hr_hat is enlarged to hr's grid for the covariance only (skimage.transform.resize); enlarging is what
+        # `_collage_preds` needs -- shrinking would add skimage's Gaussian anti-aliasing filter and is not on this path
+        if b.shape[-2] > a.shape[-2] or b.shape[-1] > a.shape[-1]:
+            raise NotImplementedError("normalize_preds with hr_hat larger than hr (anti-aliased skimage.transform.resize) is off the accelerated path")
+        oa, ob = ops.normalize_preds_resized_u8(a.cuda(), b.cuda(), pmin, pmax)
+    else:
+        oa, ob = ops.normalize_preds_u8(a.cuda(), b.cuda(), pmin, pmax)
     oa, ob = oa.reshape(sa), ob.reshape(sb)
     if as_numpy:
         return oa.cpu().numpy(), ob.cpu().numpy()

@@ -10,7 +10,7 @@ op = int(sys.argv[1]) if len(sys.argv) > 1 else 41
 B = 64
 torch.manual_seed(0)
 m = ResUNet().eval()
-m.precision = "fp16"
+m.precision = os.environ.get("PREC", "fp16")
 m = m.cuda()
 x = torch.randint(0, 256, (B, 1, 128, 128), device="cuda").float()
 st, _ = m._state(x)
@@ -31,4 +31,10 @@ for cta in (0, 1):
         if t[64 + 2 * u] <= 0:
             continue
         m_ = f"buffer free {t[2+2*u]-t0:7d} A landed {t[128+2*u]-t0:7d} committed {t[3+2*u]-t0:7d} tail issued {t[192+u]-t0:7d}" if t[2 + 2 * u] > 0 else " " * 80
-        print(f"   unit {u}: {m_} | acc ready {t[64+2*u]-t0:7d} epi done {t[65+2*u]-t0:7d} (epi {t[65+2*u]-t[64+2*u]})")
+        extra = f" | tail wait from {t[129+2*u]-t0:7d}" if t[129 + 2 * u] > 0 else ""
+        if u < 8 and t[232 + 2 * u] > 0:
+            extra += f" handed over {t[232+2*u]-t0:7d} z seen {t[233+2*u]-t0:7d}"
+        print(f"   unit {u}: {m_} | acc ready {t[64+2*u]-t0:7d} epi done {t[65+2*u]-t0:7d} (epi {t[65+2*u]-t[64+2*u]}){extra}")
+    if t[244] > 0:
+        names = ["accumulator buffer", "input rows", "weight stages", "tail activations"]
+        print("   MMA warp waits (cycles, whole launch): " + ", ".join(f"{n} {t[240+k]} ({100*t[240+k]/t[244]:.1f} %)" for k, n in enumerate(names)) + f"; issue loop {t[244]}")

@@ -136,14 +136,143 @@ def net_cases():
     np.savez_compressed(os.path.join(OUT, "net.npz"), **out)
 
 
+def _pillow_imread(path):
+    """Stand-in for tifffile.imread in THIS script only (tifffile is absent): multi-frame grayscale TIFF -> [frames, H, W]."""
+    from PIL import Image
+    im = Image.open(path)
+    fr = []
+    for k in range(getattr(im, "n_frames", 1)):
+        im.seek(k)
+        fr.append(np.asarray(im))
+    return np.stack(fr) if len(fr) > 1 else fr[0]
+
+
+def _write_stack(path, arr):
+    from PIL import Image
+    ims = [Image.fromarray(a) for a in arr]
+    ims[0].save(path, save_all=True, append_images=ims[1:])
+
+
+def paired_cases():
+    """the reference's own PairedImageDataset / PairedSlidingDataset read from TIFF files (pssr/data.py:268-431,
+    `_transform_pair` :497-516) with seeded rotation draws, and `_Crappifier_Objective.sample` (pssr/train.py:348-386) with a
+    deterministic crappifier on those pairs."""
+    import random
+    import tempfile
+    from pssr import train as RT
+    RD.tifffile.imread = _pillow_imread
+    rng = np.random.default_rng(77)
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        for sub in ("ih", "il", "sh", "sl"):
+            os.makedirs(os.path.join(d, sub))
+        # pre-tiled pairs: 3 stacks of 6 frames, HR 56x72 (cropped to 56, reflect-padded to 64), LR 14x18 (cropped to 14, padded to 16)
+        for i in range(3):
+            hr = rng.integers(0, 256, (6, 56, 72)).astype(np.uint8)
+            lr = rng.integers(0, 256, (6, 14, 18)).astype(np.uint8)
+            _write_stack(os.path.join(d, "ih", f"im{i}.tif"), hr)
+            _write_stack(os.path.join(d, "il", f"im{i}.tif"), lr)
+            out[f"img_hr_{i}"], out[f"img_lr_{i}"] = hr, lr
+        for tag, nf in (("a", -1), ("b", [3, 1]), ("c", 2)):
+            ds = RD.PairedImageDataset(os.path.join(d, "ih"), os.path.join(d, "il"), hr_res=64, lr_scale=4, n_frames=nf, val_split=0.34,
+                                       rotation=True)
+            out[f"img_{tag}_len"] = np.array([len(ds)])
+            out[f"img_{tag}_val"] = np.asarray(ds.val_idx)
+            random.seed(5)
+            for i in range(len(ds)):
+                h, l = ds[i]
+                out[f"img_{tag}_hr_{i}"], out[f"img_{tag}_lr_{i}"] = h.numpy(), l.numpy()
+        # sheets: 2 sheets of 4 frames, HR 96x128 -> tiles 64 / overlap 32, LR 24x32 -> tiles 16 / stride 8
+        for i in range(2):
+            hr = rng.integers(0, 256, (4, 96, 128)).astype(np.uint8)
+            lr = rng.integers(0, 256, (4, 24, 32)).astype(np.uint8)
+            _write_stack(os.path.join(d, "sh", f"sh{i}.tif"), hr)
+            _write_stack(os.path.join(d, "sl", f"sh{i}.tif"), lr)
+            out[f"sheet_hr_{i}"], out[f"sheet_lr_{i}"] = hr, lr
+        for tag, nf in (("a", [2, 1]), ("b", 1)):
+            ds = RD.PairedSlidingDataset(os.path.join(d, "sh"), os.path.join(d, "sl"), hr_res=64, lr_scale=4, overlap=32, n_frames=nf,
+                                         val_split=0.25, rotation=True)
+            out[f"sheet_{tag}_len"] = np.array([len(ds)])
+            out[f"sheet_{tag}_val"] = np.asarray(ds.val_idx)
+            random.seed(6)
+            for i in range(len(ds)):
+                h, l = ds[i]
+                out[f"sheet_{tag}_hr_{i}"], out[f"sheet_{tag}_lr_{i}"] = h.numpy(), l.numpy()
+            out[f"sheet_{tag}_names"] = np.asarray([ds._get_name(i) for i in range(len(ds))])
+
+        # the crappifier objective on image pairs whose LR half is a noisy downscale of the HR half
+        class Shift(RC.Crappifier):
+            """Deterministic stand-in crappifier: adds `amount` on a checkerboard (no random draws)."""
+            def __init__(self, amount):
+                self.amount = amount
+            def crappify(self, image):
+                yy, xx = np.mgrid[0:image.shape[-2], 0:image.shape[-1]]
+                return image.astype(np.float64) + self.amount * ((yy + xx) % 2)
+
+        class Pairs:
+            def __init__(self, items):
+                self.items = items
+            def __len__(self):
+                return len(self.items)
+            def __getitem__(self, i):
+                return self.items[i]
+
+        items = []
+        for i in range(4):
+            hr = rng.integers(0, 256, (1, 64, 64)).astype(np.float32)
+            lr = np.clip(rng.normal(hr[:, ::4, ::4], 9.0), 0, 255).astype(np.uint8).astype(np.float32)
+            items.append((torch.as_tensor(hr), torch.as_tensor(lr)))
+            out[f"obj_hr_{i}"], out[f"obj_lr_{i}"] = hr, lr
+        for k, amount in enumerate((0.0, 7.0, 23.5)):
+            random.seed(9)
+            out[f"obj_loss_{k}"] = np.array([RT._Crappifier_Objective(Shift, Pairs(items), 4).sample([amount]), amount])
+    def compact(a):          # pair tensors hold integer values 0..255 as float32: store them as uint8 (the test compares values)
+        a = np.asarray(a)
+        if a.dtype == np.float32 and a.size and np.array_equal(a, np.clip(np.rint(a), 0, 255)):
+            return a.astype(np.uint8)
+        return a
+    np.savez_compressed(os.path.join(OUT, "paired.npz"), **{k: compact(v) for k, v in out.items()})
+
+
+def collage_cases():
+    """`_collage_preds` (pssr/predict.py:213-243) with and without normalisation -- the second `normalize_preds` call inside it takes
+    the differing-resolution branch (pssr/util.py:179, skimage.transform.resize served by oracle/thirdparty.py through scipy) --
+    and `normalize_preds(hr, lr)` on its own."""
+    from pssr.predict import _collage_preds
+    rng = np.random.default_rng(11)
+    yy, xx = np.mgrid[0:64, 0:64]
+    hr = np.stack([(120 + 70 * np.sin(yy / (5.0 + k)) * np.cos(xx / 7.0) + rng.normal(0, 6, (64, 64))).clip(0, 255) for k in range(2)])[:, None]
+    hr = hr.astype(np.uint8)
+    hat = (hr.astype(np.float64) * 0.8 + 20 + rng.normal(0, 4, hr.shape)).clip(0, 255).astype(np.uint8)
+    lr = (hr[:, :, ::4, ::4].astype(np.float64) * 0.6 + 35 + rng.normal(0, 12, (2, 1, 16, 16))).clip(0, 255).astype(np.uint8)
+    out = {"hr": hr, "hat": hat, "lr": lr}
+    t = lambda a: torch.as_tensor(a.astype(np.float32))
+    for norm in (False, True):
+        im = _collage_preds(t(lr), t(hat), t(hr), norm, 5, 64, 4)
+        out[f"collage_norm{int(norm)}"] = np.asarray(im)
+    im = _collage_preds(t(lr), t(hat), None, False, 1, 64, 4)
+    out["collage_lr_mode"] = np.asarray(im)
+    a, b = RU.normalize_preds(hr, lr)
+    out["norm_hr"], out["norm_lr"] = a, b
+    np.savez_compressed(os.path.join(OUT, "collage.npz"), **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "rotation":      # added in round 2: does not touch the earlier fixtures
         gen_pair_rotation_cases()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "collage":
+        collage_cases()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "paired":
+        paired_cases()
         sys.exit(0)
     gen_pair_cases()
     gen_pair_rotation_cases()
     tiling_stitch_cases()
     normalize_cases()
     net_cases()
+    paired_cases()
+    collage_cases()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
