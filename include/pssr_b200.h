@@ -313,6 +313,7 @@ typedef struct {
   const float* weight;   /* [Cout][C*patch*patch] fp32                                               */
   const float* bias; const float* ln_w; const float* ln_b; float eps; int32_t reserved;
   void* out; int32_t out_cstride, out_choff;
+  void* out_lo;          /* compensated precision (optional): rn16(y - rn16(y)), same layout as `out`               */
 } pssr_stem_desc_t;
 
 /* PSSR_OP_LAYERNORM: LayerNorm2d over C of an NHWC 16-bit view (transition layers, _rdnet.py:57-58).  With
@@ -322,6 +323,8 @@ typedef struct {
   const void* in; int32_t in_cstride, in_choff, C; int32_t B, H, W; int32_t s2d;
   const float* w; const float* b; float eps; int32_t reserved;
   void* out; int32_t out_cstride, out_choff;
+  const void* in_lo;     /* compensated precision (optional): the input is in + in_lo (same layout as `in`) ...       */
+  void* out_lo;          /* ... and what the 16-bit rounding of the output dropped goes here (same layout as `out`)   */
 } pssr_ln_desc_t;
 
 /* PSSR_OP_DWCONV_LN: depthwise 7x7 conv (pad 3) + bias + LayerNorm2d (Block, _rdnet.py:181-183).     */
@@ -330,6 +333,8 @@ typedef struct {
   const float* dw_w;     /* [49][C] fp32                                                             */
   const float* dw_b; const float* ln_w; const float* ln_b; float eps; int32_t reserved2;
   void* out; int32_t out_cstride, out_choff;
+  const void* in_lo;     /* compensated precision (optional), as in pssr_ln_desc_t; with out_lo set the pre-LayerNorm */
+  void* out_lo;          /* values also travel as a hi + lo pair                                                     */
 } pssr_dwln_desc_t;
 
 /* PSSR_OP_ESE: EffectiveSEModule (timm) + layer-scale gamma (_rdnet.py:172-174,200-202):

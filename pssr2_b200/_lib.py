@@ -128,19 +128,20 @@ class StemDesc(Structure):
     _fields_ = [("x", c_void_p), ("x_u8", c_int32), ("B", c_int32), ("C", c_int32), ("H", c_int32), ("W", c_int32),
                 ("in_scale", c_void_p), ("in_shift", c_void_p), ("patch", c_int32), ("Cout", c_int32), ("weight", c_void_p),
                 ("bias", c_void_p), ("ln_w", c_void_p), ("ln_b", c_void_p), ("eps", c_float), ("reserved", c_int32),
-                ("out", c_void_p), ("out_cstride", c_int32), ("out_choff", c_int32)]
+                ("out", c_void_p), ("out_cstride", c_int32), ("out_choff", c_int32), ("out_lo", c_void_p)]
 
 
 class LnDesc(Structure):
     _fields_ = [("in_", c_void_p), ("in_cstride", c_int32), ("in_choff", c_int32), ("C", c_int32), ("B", c_int32), ("H", c_int32),
                 ("W", c_int32), ("s2d", c_int32), ("w", c_void_p), ("b", c_void_p), ("eps", c_float), ("reserved", c_int32),
-                ("out", c_void_p), ("out_cstride", c_int32), ("out_choff", c_int32)]
+                ("out", c_void_p), ("out_cstride", c_int32), ("out_choff", c_int32), ("in_lo", c_void_p), ("out_lo", c_void_p)]
 
 
 class DwLnDesc(Structure):
     _fields_ = [("in_", c_void_p), ("in_cstride", c_int32), ("in_choff", c_int32), ("C", c_int32), ("B", c_int32), ("H", c_int32),
                 ("W", c_int32), ("reserved", c_int32), ("dw_w", c_void_p), ("dw_b", c_void_p), ("ln_w", c_void_p), ("ln_b", c_void_p),
-                ("eps", c_float), ("reserved2", c_int32), ("out", c_void_p), ("out_cstride", c_int32), ("out_choff", c_int32)]
+                ("eps", c_float), ("reserved2", c_int32), ("out", c_void_p), ("out_cstride", c_int32), ("out_choff", c_int32),
+                ("in_lo", c_void_p), ("out_lo", c_void_p)]
 
 
 class EseDesc(Structure):

@@ -31,6 +31,22 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8], int fp16) {
   return make_uint4(pack2(f[0], f[1], fp16), pack2(f[2], f[3], fp16), pack2(f[4], f[5], fp16), pack2(f[6], f[7], fp16));
 }
 
+// compensated precision: a tensor travels as a (hi, lo) pair of 16-bit buffers of identical layout, value = hi + lo
+__device__ __forceinline__ void pack8_pair(const float (&f)[8], int fp16, uint4& hi, uint4& lo) {
+  hi = pack8(f, fp16);
+  float h[8], r[8];
+  unpack8(hi, h, fp16);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = f[j] - h[j];
+  lo = pack8(r, fp16);
+}
+__device__ __forceinline__ void add8(float (&f)[8], const uint4& v, int fp16) {
+  float t[8];
+  unpack8(v, t, fp16);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] += t[j];
+}
+
 static constexpr int kMaxGroupsPerLane = 6;   // channels <= 32 lanes * 6 groups * 8 = 1536
 
 // ------------------------------------------------------------------------------- stem
@@ -98,6 +114,7 @@ __global__ void __launch_bounds__(256) stem_kernel(pssr_stem_desc_t d, int fp16)
       }
     const float rstd = rsqrtf(warp_sum_f(q) / d.Cout + d.eps);
     uint16_t* out = reinterpret_cast<uint16_t*>(d.out) + (size_t)pix * d.out_cstride + d.out_choff;
+    uint16_t* out_lo = d.out_lo != nullptr ? reinterpret_cast<uint16_t*>(d.out_lo) + (size_t)pix * d.out_cstride + d.out_choff : nullptr;
 #pragma unroll
     for (int g = 0; g < kMaxGroupsPerLane; ++g) {
       const int c0 = lane * 8 + g * 256;
@@ -105,7 +122,14 @@ __global__ void __launch_bounds__(256) stem_kernel(pssr_stem_desc_t d, int fp16)
         float f[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = (vals[g * 8 + j] - mean) * rstd * lw_s[c0 + j] + lb_s[c0 + j];
-        *reinterpret_cast<uint4*>(out + c0) = pack8(f, fp16);
+        if (out_lo != nullptr) {
+          uint4 hi, lo;
+          pack8_pair(f, fp16, hi, lo);
+          *reinterpret_cast<uint4*>(out + c0) = hi;
+          *reinterpret_cast<uint4*>(out_lo + c0) = lo;
+        } else {
+          *reinterpret_cast<uint4*>(out + c0) = pack8(f, fp16);
+        }
       }
     }
   }
@@ -139,6 +163,7 @@ __global__ void __launch_bounds__(256) ln_kernel(pssr_ln_desc_t d, int fp16) {
   const long long total = (long long)d.B * d.H * d.W;
   const int lane = threadIdx.x & 31;
   const uint16_t* in = reinterpret_cast<const uint16_t*>(d.in) + d.in_choff;
+  const uint16_t* in_lo = d.in_lo != nullptr ? reinterpret_cast<const uint16_t*>(d.in_lo) + d.in_choff : nullptr;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long p0 = ((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5) * PX; p0 < total; p0 += warps * PX) {
     float vals[PX][G * 8];
@@ -151,6 +176,8 @@ __global__ void __launch_bounds__(256) ln_kernel(pssr_ln_desc_t d, int fp16) {
         const int c0 = lane * 8 + g * 256;
         if (c0 < d.C) {
           unpack8(__ldg(reinterpret_cast<const uint4*>(src + c0)), *reinterpret_cast<float(*)[8]>(&vals[px][g * 8]), fp16);
+          if (in_lo != nullptr)
+            add8(*reinterpret_cast<float(*)[8]>(&vals[px][g * 8]), __ldg(reinterpret_cast<const uint4*>(in_lo + (src - in) + c0)), fp16);
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) vals[px][g * 8 + j] = 0.f;
@@ -181,6 +208,7 @@ __global__ void __launch_bounds__(256) ln_kernel(pssr_ln_desc_t d, int fp16) {
         coff = ((y & 1) * 2 + (x & 1)) * d.C;
       }
       uint16_t* out = reinterpret_cast<uint16_t*>(d.out) + opix * d.out_cstride + d.out_choff + coff;
+      uint16_t* out_lo = d.out_lo != nullptr ? reinterpret_cast<uint16_t*>(d.out_lo) + opix * d.out_cstride + d.out_choff + coff : nullptr;
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         const int c0 = lane * 8 + g * 256;
@@ -191,7 +219,14 @@ __global__ void __launch_bounds__(256) ln_kernel(pssr_ln_desc_t d, int fp16) {
           float f[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = (vals[px][g * 8 + j] - mean) * rstd * wv[j] + bv[j];
-          *reinterpret_cast<uint4*>(out + c0) = pack8(f, fp16);
+          if (out_lo != nullptr) {
+            uint4 hi, lo;
+            pack8_pair(f, fp16, hi, lo);
+            *reinterpret_cast<uint4*>(out + c0) = hi;
+            *reinterpret_cast<uint4*>(out_lo + c0) = lo;
+          } else {
+            *reinterpret_cast<uint4*>(out + c0) = pack8(f, fp16);
+          }
         }
       }
     }
@@ -299,11 +334,15 @@ __global__ void __launch_bounds__(256) dwln_kernel(pssr_dwln_desc_t d, int fp16)
 // staged in shared memory; a thread computes 4 consecutive pixels of one row for 8 channels, so one filter row costs
 // 10 input + 14 weight 16-byte shared loads for 224 FMAs.  Output: pre-LayerNorm values, 16-bit NHWC.
 static constexpr int kDwTH = 8, kDwTW = 16, kDwC = 64;
+// LO (compensated precision): the input is a hi + lo pair (second halo tile behind the weights, summed in fp32 on use) and the
+// pre-LayerNorm result leaves as a pair too.
+template <bool LO>
 __global__ void __launch_bounds__(256) dwconv7_kernel(pssr_dwln_desc_t d, int fp16) {
   extern __shared__ __align__(16) uint8_t dw_sm[];
   uint4* tile = reinterpret_cast<uint4*>(dw_sm);                        // [row][col][8-ch group], 16 B each
   float* wsm = reinterpret_cast<float*>(dw_sm + (kDwTH + 6) * (kDwTW + 6) * (kDwC / 8) * 16);   // [49][64]
   float* bsm = wsm + 49 * kDwC;
+  uint4* tile_lo = reinterpret_cast<uint4*>(bsm + kDwC);               // LO only
   const int tiles_x = (d.W + kDwTW - 1) / kDwTW, tiles_y = (d.H + kDwTH - 1) / kDwTH;
   int bid = blockIdx.x;
   const int tx = bid % tiles_x; bid /= tiles_x;
@@ -327,6 +366,12 @@ __global__ void __launch_bounds__(256) dwconv7_kernel(pssr_dwln_desc_t d, int fp
     if (yy >= 0 && yy < d.H && xx >= 0 && xx < d.W && g * 8 < cw)
       v = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)n * d.H + yy) * d.W + xx) * d.in_cstride + g * 8));
     tile[i] = v;
+    if (LO) {
+      uint4 vl = make_uint4(0, 0, 0, 0);
+      if (yy >= 0 && yy < d.H && xx >= 0 && xx < d.W && g * 8 < cw)
+        vl = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(d.in_lo) + d.in_choff + c_base + (((size_t)n * d.H + yy) * d.W + xx) * d.in_cstride + g * 8));
+      tile_lo[i] = vl;
+    }
   }
   __syncthreads();
   const int g = threadIdx.x & 7;             // channel group
@@ -350,6 +395,7 @@ __global__ void __launch_bounds__(256) dwconv7_kernel(pssr_dwln_desc_t d, int fp
     for (int cx = 0; cx < 10; ++cx) {        // input column (xq*4 - 3 + cx): tap (cx - p4) of output pixel p4
       float f[8];
       unpack8(trow[cx * 8], f, fp16);
+      if (LO) add8(f, trow[cx * 8 + (tile_lo - tile)], fp16);
 #pragma unroll
       for (int p4 = 0; p4 < 4; ++p4) {
         const int kx = cx - p4;
@@ -366,7 +412,17 @@ __global__ void __launch_bounds__(256) dwconv7_kernel(pssr_dwln_desc_t d, int fp
 #pragma unroll
     for (int p4 = 0; p4 < 4; ++p4) {
       const int x = x0 + xq * 4 + p4;
-      if (x < d.W) *reinterpret_cast<uint4*>(out + (((size_t)n * d.H + y) * d.W + x) * d.out_cstride) = pack8(acc[p4], fp16);
+      if (x < d.W) {
+        const size_t off = (((size_t)n * d.H + y) * d.W + x) * d.out_cstride;
+        if (LO) {
+          uint4 hi, lo;
+          pack8_pair(acc[p4], fp16, hi, lo);
+          *reinterpret_cast<uint4*>(out + off) = hi;
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(d.out_lo) + d.out_choff + c_base + g * 8 + off) = lo;
+        } else {
+          *reinterpret_cast<uint4*>(out + off) = pack8(acc[p4], fp16);
+        }
+      }
     }
   }
 }
@@ -496,7 +552,9 @@ int dwln_launch(const pssr_dwln_desc_t& d, int dtype, cudaStream_t stream) {
   const long long sp_tiles = (long long)d.B * ((d.H + kDwTH - 1) / kDwTH) * ((d.W + kDwTW - 1) / kDwTW);
   const int slabs_all = (d.C + kDwC - 1) / kDwC;
   // enough spatial tiles to fill the machine twice over and at least two slabs to pipeline: the slab-walking kernel
-  if (sp_tiles >= 4LL * device_sm_count() && slabs_all >= 2 && ((uintptr_t)d.dw_w & 15) == 0 && d.C % 4 == 0 && getenv("PSSR_DW_NOPIPE") == nullptr) {
+  const bool lo = d.in_lo != nullptr || d.out_lo != nullptr;
+  PSSR_REQUIRE(!lo || (d.in_lo != nullptr && d.out_lo != nullptr), PSSR_EINVAL, "dwconv: in_lo and out_lo come together");
+  if (!lo && sp_tiles >= 4LL * device_sm_count() && slabs_all >= 2 && ((uintptr_t)d.dw_w & 15) == 0 && d.C % 4 == 0 && getenv("PSSR_DW_NOPIPE") == nullptr) {
     static PerDeviceOnce attr_pipe;
     if (attr_pipe.first()) PSSR_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kDwBufBytes));
     PSSR_REQUIRE(sp_tiles < (1ll << 31), PSSR_EUNSUP, "dwconv: too many blocks");
@@ -511,18 +569,22 @@ int dwln_launch(const pssr_dwln_desc_t& d, int dtype, cudaStream_t stream) {
   }
   const long long blocks = (long long)d.B * ((d.C + kDwC - 1) / kDwC) * ((d.H + kDwTH - 1) / kDwTH) * ((d.W + kDwTW - 1) / kDwTW);
   PSSR_REQUIRE(blocks < (1ll << 31), PSSR_EUNSUP, "dwconv: too many blocks");
-  const size_t smem = (size_t)(kDwTH + 6) * (kDwTW + 6) * (kDwC / 8) * 16 + (49 * kDwC + kDwC) * sizeof(float);
+  const size_t tile_bytes = (size_t)(kDwTH + 6) * (kDwTW + 6) * (kDwC / 8) * 16;
+  const size_t smem = tile_bytes * (lo ? 2 : 1) + (49 * kDwC + kDwC) * sizeof(float);
   static PerDeviceOnce attr_once;
   if (attr_once.first()) {
-    PSSR_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    PSSR_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    PSSR_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   }
-  dwconv7_kernel<<<(unsigned)blocks, 256, smem, stream>>>(d, dtype == PSSR_DT_FP16);
+  if (lo) dwconv7_kernel<true><<<(unsigned)blocks, 256, smem, stream>>>(d, dtype == PSSR_DT_FP16);
+  else dwconv7_kernel<false><<<(unsigned)blocks, 256, smem, stream>>>(d, dtype == PSSR_DT_FP16);
   count_launch();
   PSSR_CHECK_CUDA(cudaGetLastError());
   pssr_ln_desc_t ln;
   memset(&ln, 0, sizeof(ln));
   ln.in = d.out; ln.in_cstride = d.out_cstride; ln.in_choff = d.out_choff; ln.C = d.C; ln.B = d.B; ln.H = d.H; ln.W = d.W; ln.s2d = 1;
   ln.w = d.ln_w; ln.b = d.ln_b; ln.eps = d.eps; ln.out = d.out; ln.out_cstride = d.out_cstride; ln.out_choff = d.out_choff;
+  if (lo) { ln.in_lo = d.out_lo; ln.out_lo = d.out_lo; }
   return ln_launch(ln, dtype, stream);     // in place: a warp reads its whole pixel before writing it
 }
 

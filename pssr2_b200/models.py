@@ -157,7 +157,7 @@ class _PlanModule(nn.Module):
         return st["out"], st["out_u8"]
 
     # helpers used by subclasses ---------------------------------------------------------
-    def _emit_reconstruction(self, plan, final, xcol, B, H, W, dev, out=None, out_u8=None, zbuf=None, xcol_lo=None):
+    def _emit_reconstruction(self, plan, final, xcol, B, H, W, dev, out=None, out_u8=None, zbuf=None, xcol_lo=None, final_lo=None):
         """Reconstruction (resunet.py:90-95, _blocks.py:15-18): cat([x, xnorm]) -> pre -> relu -> shuffle(s) -> conv -> *128+128."""
         dt = plan.tdtype
         z = lambda *sh: torch.zeros(*sh, dtype=dt, device=dev)
@@ -188,11 +188,23 @@ class _PlanModule(nn.Module):
                 # Power-of-two scales put the largest |W_lo| in e5m2's [2^-9, 2^-8) binade (six normal binades below it) and
                 # final / 2^e next to it; the product carries no scale.
                 e = int(math.floor(-8.0 - math.log2(mx)))
-                final8 = torch.zeros(final.shape[0], H, W, hid0, dtype=torch.uint8, device=dev)
-                plan.cast8(View(final), View(final8), 2.0 ** -e)
-                w8 = pack_weight8([wlo], 2.0 ** e, s)
-                srcs.append(View(final8))
-                segs.append((len(srcs) - 1, 9, cbm, SEG_E5M2))
+                if final_lo is not None and hid0 == 64:
+                    # RDResUNet: `final` itself travels as hi + lo.  final_lo x W_hi is one more e5m2 term: both e5m2 operands share
+                    # one 128-channel source [final / 2^e | final_lo * 2^a] against [W_lo * 2^e | W_hi / 2^a]; a puts the largest
+                    # |W_hi| in e5m2's [2^-7, 2^-6) binade (eight normal binades below it), which leaves final_lo fifteen.
+                    a = int(math.floor(math.log2(float(wm.abs().max())))) + 7
+                    final8 = torch.zeros(final.shape[0], H, W, 2 * hid0, dtype=torch.uint8, device=dev)
+                    plan.cast8(View(final), View(final8, 0, hid0), 2.0 ** -e)
+                    plan.cast8(View(final_lo), View(final8, hid0, hid0), 2.0 ** a)
+                    w8 = pack_weight8([torch.cat([wlo * 2.0 ** e, wm * 2.0 ** -a], 1)], 1.0, s)
+                    srcs.append(View(final8))
+                    segs.append((len(srcs) - 1, 9, 2 * cbm, SEG_E5M2))
+                else:
+                    final8 = torch.zeros(final.shape[0], H, W, hid0, dtype=torch.uint8, device=dev)
+                    plan.cast8(View(final), View(final8), 2.0 ** -e)
+                    w8 = pack_weight8([wlo], 2.0 ** e, s)
+                    srcs.append(View(final8))
+                    segs.append((len(srcs) - 1, 9, cbm, SEG_E5M2))
             else:
                 parts.append(wlo)
                 segs.append((0, 9, cbm))
@@ -588,6 +600,7 @@ class RDNet(nn.Module):
 
 class RDResUNet(_PlanModule):
     """RDNet encoder + ResUNet decoder + upscaling block (pssr/models/rdresunet.py:8-133), default (non-atrous) path."""
+    comp_stages = (0,)      # RDNet stages whose tensors travel as (hi, lo) pairs under precision "fp16c"
 
     def __init__(self, channels=1, hidden=[1024, 1024, 512, 256], scale=4, depth=3, dilations=None, pool_sizes=None, encoder_pool=False,
                  rdnet_init=128, growth_rates=[64, 104, 128, 128, 128, 128, 224], ds_blocks=[False, True, True, False, False, False, True],
@@ -675,6 +688,15 @@ class RDResUNet(_PlanModule):
                 raise NotImplementedError("decoder widths must keep 8-channel alignment after pixel shuffle")
         cat = {}
         stage_view = []
+        # compensated precision: the first RDNet stage (stem, dense blocks at half resolution) sits on the shallow path
+        # stem -> dense block -> skip -> last respass -> `final` -> Reconstruction, like encoder.0 of ResUNet: its tensors travel as
+        # (hi, lo) pairs and its 1x1 GEMMs run x_hi W_hi + x_lo W_hi + x_hi W_lo (scripts/dev_error_budget_rd.py: these sites and
+        # `final` carry 15 of the 17e-6 variance the compensated Reconstruction leaves)
+        comp_stages = set(self.comp_stages) if plan.comp else set()
+        for i in comp_stages:
+            if any(len(blk.layers.layers) > 5 for blk in stage_mods[i][-1]):
+                raise NotImplementedError("compensated RDNet stages must be plain Blocks (no eSE gate)")
+        stage_lo = {}
         for i in range(n_st):
             hh, ww = hw[i]
             if i in dec_of_stage:
@@ -684,6 +706,8 @@ class RDResUNet(_PlanModule):
                 stage_view.append(View(buf, up[k], ctot[i]))
             else:
                 stage_view.append(View(z(B, hh, ww, ctot[i])))
+            if i in comp_stages:
+                stage_lo[i] = View(torch.zeros_like(stage_view[i].buf), stage_view[i].choff, ctot[i])
 
         def sub(v: View, c0, c):      # channel slice of a view
             return View(v.buf, v.choff + c0, c)
@@ -691,7 +715,7 @@ class RDResUNet(_PlanModule):
         # ---- stem (_rdnet.py:106-116) ---------------------------------------------------------------------
         st0 = enc.stem.stem
         plan.stem(x_in, sc, sh, pch, f32(st0[0].weight).reshape(st0[0].weight.shape[0], -1).contiguous(), f32(st0[0].bias), f32(st0[1].weight),
-                  f32(st0[1].bias), st0[1].eps, sub(stage_view[0], 0, cin_st[0]))
+                  f32(st0[1].bias), st0[1].eps, sub(stage_view[0], 0, cin_st[0]), out_lo=sub(stage_lo[0], 0, cin_st[0]) if 0 in stage_lo else None)
         max_px = max(B * a * b for a, b in hw)
         max_c = max(max(blk.in_chs for blk in mods[-1]) for mods in stage_mods)
         max_inter = max(max(blk.inter_chs for blk in mods[-1]) for mods in stage_mods)
@@ -701,14 +725,26 @@ class RDResUNet(_PlanModule):
         g_pool = torch.zeros(max_px * max_g, dtype=dt, device=dev)
         ln_pool = torch.zeros(max(B * a * b * c for (a, b), c in zip(hw, ctot)), dtype=dt, device=dev)
         gate_ws = torch.zeros(B * max_g, dtype=torch.float32, device=dev)
+        dw_pool_lo = torch.zeros_like(dw_pool) if comp_stages else None
+        mid_pool_lo = torch.zeros_like(mid_pool) if comp_stages else None
+        ln_pool_lo = torch.zeros_like(ln_pool) if any(i > 0 for i in comp_stages) else None
 
-        def pad_n(wt, bias, n_pad, extra=None):
+        def pad_n(wt, bias, n_pad, extra=None, lo=False):
             co = wt.shape[0]
             if n_pad > co:
                 bias = torch.cat([bias, torch.zeros(n_pad - co, device=dev)])
                 if extra is not None:
                     extra = torch.cat([extra, torch.zeros(n_pad - co, device=dev)])
-            return pack_weight([wt], plan.dtype, 1, n_pad), bias.contiguous(), (extra.contiguous() if extra is not None else None)
+            parts = [wt, wt, split_lo(wt, plan.dtype)] if lo else [wt]          # K segments x_hi W_hi, x_lo W_hi, x_hi W_lo
+            return pack_weight(parts, plan.dtype, 1, n_pad), bias.contiguous(), (extra.contiguous() if extra is not None else None)
+
+        def gemm(src, src_lo, cin, wp, bp, out, out_lo, **kw):
+            """1x1 convolution; with src_lo the three-segment compensated form."""
+            cb = ceil_div(cin, 64)
+            if src_lo is None:
+                plan.conv([src], [(0, 1, cb)], wp, bp, out, Ho=hh, Wo=ww, B=B, **kw)
+            else:
+                plan.conv([src, src_lo], [(0, 1, cb), (1, 1, cb), (0, 1, cb)], wp, bp, out, Ho=hh, Wo=ww, B=B, out_lo=out_lo, **kw)
 
         def r32(v):
             # GEMM N padding: wide layers get 128-column tiles (full-rate tcgen05 N), narrow ones waste as little as possible
@@ -726,31 +762,38 @@ class RDResUNet(_PlanModule):
                 prev = stage_view[i - 1]
                 cprev = ctot[i - 1]
                 lnb = ln_pool[:B * hh * ww * k * k * cprev].view(B, hh, ww, k * k * cprev)
-                plan.layernorm(prev, f32(ln.weight), f32(ln.bias), ln.eps, View(lnb), s2d=k)
+                c_lo = i in stage_lo
+                lnb_lo = View(ln_pool_lo[:lnb.numel()].view(lnb.shape)) if c_lo else None
+                plan.layernorm(prev, f32(ln.weight), f32(ln.bias), ln.eps, View(lnb), s2d=k, src_lo=stage_lo.get(i - 1), out_lo=lnb_lo)
                 wt = f32(cv.weight).permute(0, 2, 3, 1).reshape(cv.weight.shape[0], k * k * cprev, 1, 1)
                 cout = wt.shape[0]
-                wp, bp, _ = pad_n(wt, f32(cv.bias), r32(cout))
-                plan.conv([View(lnb)], [(0, 1, ceil_div(k * k * cprev, 64))], wp, bp, sub(sv, 0, cout), Ho=hh, Wo=ww, B=B, n_valid=cout)
+                wp, bp, _ = pad_n(wt, f32(cv.bias), r32(cout), lo=c_lo)
+                gemm(View(lnb), lnb_lo, k * k * cprev, wp, bp, sub(sv, 0, cout), sub(stage_lo[i], 0, cout) if c_lo else None, n_valid=cout)
                 plan.flops += 2 * wt.numel() * B * hh * ww
             for j, blk in enumerate(mods[-1]):
                 L = blk.layers.layers
                 ck, inter, g = blk.in_chs, blk.inter_chs, blk.growth_rate
                 xin = sub(sv, 0, ck)
+                c_lo = i in stage_lo
+                slo = stage_lo.get(i)
                 dwb = dw_pool[:B * hh * ww * ck].view(B, hh, ww, ck)
-                plan.dwconv_ln(xin, f32(L[0].weight).view(ck, 49).t().contiguous(), f32(L[0].bias), f32(L[1].weight), f32(L[1].bias), L[1].eps, View(dwb))
+                dwb_lo = View(dw_pool_lo[:dwb.numel()].view(dwb.shape)) if c_lo else None
+                plan.dwconv_ln(xin, f32(L[0].weight).view(ck, 49).t().contiguous(), f32(L[0].bias), f32(L[1].weight), f32(L[1].bias), L[1].eps, View(dwb),
+                               src_lo=sub(slo, 0, ck) if c_lo else None, out_lo=dwb_lo)
                 midb = mid_pool[:B * hh * ww * inter].view(B, hh, ww, inter)
-                w1, b1, _ = pad_n(f32(L[2].weight), f32(L[2].bias), r32(inter))
-                plan.conv([View(dwb)], [(0, 1, ceil_div(ck, 64))], w1, b1, View(midb), Ho=hh, Wo=ww, B=B, n_valid=inter, act=ACT_GELU)
+                midb_lo = View(mid_pool_lo[:midb.numel()].view(midb.shape)) if c_lo else None
+                w1, b1, _ = pad_n(f32(L[2].weight), f32(L[2].bias), r32(inter), lo=c_lo)
+                gemm(View(dwb), dwb_lo, ck, w1, b1, View(midb), midb_lo, n_valid=inter, act=ACT_GELU)
                 gamma = f32(blk.gamma) if blk.gamma is not None else None
                 dst = sub(sv, ck, g)
                 has_ese = len(L) > 5
-                w2, b2, gpad = pad_n(f32(L[4].weight), f32(L[4].bias), r32(g), None if has_ese else gamma)
+                w2, b2, gpad = pad_n(f32(L[4].weight), f32(L[4].bias), r32(g), None if has_ese else gamma, lo=c_lo)
                 if has_ese:
                     gb = g_pool[:B * hh * ww * g].view(B, hh, ww, g)
                     plan.conv([View(midb)], [(0, 1, ceil_div(inter, 64))], w2, b2, View(gb), Ho=hh, Wo=ww, B=B, n_valid=g)
                     plan.ese(View(gb), f32(L[5].fc.weight).view(g, g).contiguous(), f32(L[5].fc.bias), gamma, gate_ws, dst)
                 else:
-                    plan.conv([View(midb)], [(0, 1, ceil_div(inter, 64))], w2, b2, dst, Ho=hh, Wo=ww, B=B, n_valid=g, out_scale=gpad)
+                    gemm(View(midb), midb_lo, inter, w2, b2, dst, sub(slo, ck, g) if c_lo else None, n_valid=g, out_scale=gpad)
                 plan.flops += 2 * (L[2].weight.numel() + L[4].weight.numel() + 49 * ck) * B * hh * ww
 
         # ---- decoder (rdresunet.py:115-120) -------------------------------------------------------------------
@@ -762,6 +805,7 @@ class RDResUNet(_PlanModule):
         scratch_elems = max(B * dec_hw[k][0] * dec_hw[k][1] * hid[k] for k in range(n_dec))
         sbuf = [torch.zeros(scratch_elems, dtype=dt, device=dev) for _ in range(2)]
         final = z(B, H, W, hid[-1] // self.ratios[-1] ** 2)
+        final_lo = torch.zeros_like(final) if comp else None
         for k in range(n_dec):
             hh, ww = dec_hw[k]
             blk = self.decoder[k]
@@ -769,15 +813,23 @@ class RDResUNet(_PlanModule):
             srcs, segs = [dec_in[k]], [(0, 9, ceil_div(cin, 64))]
             w0f = lambda wt: [wt]
             wrf = (lambda cin: (lambda wt: ([wt], [(0, 1, ceil_div(cin, 64))])))(cin)
+            res_srcs = None
+            last_stage = skip_stage[0]
             if comp and k + 1 == n_dec:      # the last block's respass sits on the shallow path to the output: W_hi + W_lo
                 wrf = (lambda cin: (lambda wt: ([wt, split_lo(wt, plan.dtype)], [(0, 1, ceil_div(cin, 64))] * 2)))(cin)
+                if last_stage in stage_lo and k >= 1:      # ... and the low halves of its skip: skip_lo x W_hi
+                    c0, cs = up[k], ctot[last_stage]
+                    res_srcs = [dec_in[k], stage_lo[last_stage]]
+                    wrf = (lambda cin, c0, cs: (lambda wt: ([wt, split_lo(wt, plan.dtype), wt[:, c0:c0 + cs].contiguous()],
+                                                            [(0, 1, ceil_div(cin, 64))] * 2 + [(1, 1, ceil_div(cs, 64))])))(cin, c0, cs)
             n = B * hh * ww * hid[k]
             scr = [sb[:n].view(B, hh, ww, hid[k]) for sb in sbuf]
             shf = self.ratios[k + 1]
             dst = View(cat[k + 1], 0, up[k + 1]) if k + 1 < n_dec else View(final)
-            self._emit_resblock(plan, blk, srcs, segs, w0f, wrf, scr, dst, shf, B, hh, ww)
+            self._emit_resblock(plan, blk, srcs, segs, w0f, wrf, scr, dst, shf, B, hh, ww, res_srcs=res_srcs,
+                                out_lo=View(final_lo) if comp and k + 1 == n_dec else None)
 
         # ---- Reconstruction (rdresunet.py:125-130) -----------------------------------------------------------
-        self._emit_reconstruction(plan, final, xcol, B, H, W, dev, xcol_lo=xcol_lo)
+        self._emit_reconstruction(plan, final, xcol, B, H, W, dev, xcol_lo=xcol_lo, final_lo=final_lo)
         plan.finalize()
         return {"plan": plan, "x": x_in, "out": self._out, "out_u8": self._out_u8}

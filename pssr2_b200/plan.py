@@ -255,38 +255,49 @@ class Plan:
         self.keep += [z, out_f32, out_u8]
         self.records.append(("tailsum", dict(z=z, r=r, bias=float(bias), mul=mul, add=add, out_f32=out_f32, out_u8=out_u8, layout=layout)))
 
-    def stem(self, x, in_scale, in_shift, patch, weight, bias, ln_w, ln_b, eps, out: View):
+    @staticmethod
+    def _lo_ptr(v: View, lo: View):
+        """Compensated precision: a (hi, lo) pair shares one layout; returns the base pointer of the lo buffer (or None)."""
+        if lo is None:
+            return None
+        assert lo.buf.shape == v.buf.shape and lo.buf.dtype == v.buf.dtype and (lo.choff, lo.channels) == (v.choff, v.channels)
+        return lo.buf.data_ptr()
+
+    def stem(self, x, in_scale, in_shift, patch, weight, bias, ln_w, ln_b, eps, out: View, out_lo: View = None):
         B, C, H, W = x.shape
         cout = weight.shape[0]
         d = StemDesc(x.data_ptr(), 1 if x.dtype == torch.uint8 else 0, B, C, H, W, in_scale.data_ptr(), in_shift.data_ptr(), patch, cout,
-                     weight.data_ptr(), bias.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), eps, 0, out.buf.data_ptr(), out.cstride, out.choff)
+                     weight.data_ptr(), bias.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), eps, 0, out.buf.data_ptr(), out.cstride, out.choff,
+                     self._lo_ptr(out, out_lo))
         op = Op()
         op.kind = OP_STEM
         op.u.stem = d
         self.ops.append(op)
-        self.keep += [x, in_scale, in_shift, weight, bias, ln_w, ln_b, out.buf]
+        self.keep += [x, in_scale, in_shift, weight, bias, ln_w, ln_b, out.buf, out_lo.buf if out_lo is not None else None]
         self.records.append(("stem", dict(x=x, in_scale=in_scale, in_shift=in_shift, patch=patch, weight=weight, bias=bias, ln_w=ln_w,
-                                          ln_b=ln_b, eps=eps, out=out)))
+                                          ln_b=ln_b, eps=eps, out=out, out_lo=out_lo)))
 
-    def layernorm(self, src: View, w, b, eps, out: View, s2d=1):
+    def layernorm(self, src: View, w, b, eps, out: View, s2d=1, src_lo: View = None, out_lo: View = None):
         d = LnDesc(src.buf.data_ptr(), src.cstride, src.choff, src.channels, src.B, src.H, src.W, s2d, w.data_ptr(), b.data_ptr(), eps, 0,
-                   out.buf.data_ptr(), out.cstride, out.choff)
+                   out.buf.data_ptr(), out.cstride, out.choff, self._lo_ptr(src, src_lo), self._lo_ptr(out, out_lo))
         op = Op()
         op.kind = OP_LAYERNORM
         op.u.ln = d
         self.ops.append(op)
-        self.keep += [src.buf, w, b, out.buf]
-        self.records.append(("ln", dict(src=src, w=w, b=b, eps=eps, out=out, s2d=s2d)))
+        self.keep += [src.buf, w, b, out.buf] + [v.buf for v in (src_lo, out_lo) if v is not None]
+        self.records.append(("ln", dict(src=src, w=w, b=b, eps=eps, out=out, s2d=s2d, src_lo=src_lo, out_lo=out_lo)))
 
-    def dwconv_ln(self, src: View, dw_w, dw_b, ln_w, ln_b, eps, out: View):
+    def dwconv_ln(self, src: View, dw_w, dw_b, ln_w, ln_b, eps, out: View, src_lo: View = None, out_lo: View = None):
+        assert (src_lo is None) == (out_lo is None)
         d = DwLnDesc(src.buf.data_ptr(), src.cstride, src.choff, src.channels, src.B, src.H, src.W, 0, dw_w.data_ptr(), dw_b.data_ptr(),
-                     ln_w.data_ptr(), ln_b.data_ptr(), eps, 0, out.buf.data_ptr(), out.cstride, out.choff)
+                     ln_w.data_ptr(), ln_b.data_ptr(), eps, 0, out.buf.data_ptr(), out.cstride, out.choff, self._lo_ptr(src, src_lo),
+                     self._lo_ptr(out, out_lo))
         op = Op()
         op.kind = OP_DWCONV_LN
         op.u.dwln = d
         self.ops.append(op)
-        self.keep += [src.buf, dw_w, dw_b, ln_w, ln_b, out.buf]
-        self.records.append(("dwln", dict(src=src, dw_w=dw_w, dw_b=dw_b, ln_w=ln_w, ln_b=ln_b, eps=eps, out=out)))
+        self.keep += [src.buf, dw_w, dw_b, ln_w, ln_b, out.buf] + [v.buf for v in (src_lo, out_lo) if v is not None]
+        self.records.append(("dwln", dict(src=src, dw_w=dw_w, dw_b=dw_b, ln_w=ln_w, ln_b=ln_b, eps=eps, out=out, src_lo=src_lo, out_lo=out_lo)))
 
     def ese(self, src: View, fc_w, fc_b, gamma, gate_ws, out: View):
         d = EseDesc(src.buf.data_ptr(), src.cstride, src.channels, src.B, src.H, src.W, 0, fc_w.data_ptr(), fc_b.data_ptr(),

@@ -5,12 +5,18 @@ from pssr2_b200.models import RDResUNet
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 50
 torch.manual_seed(0)
 m = RDResUNet().eval().cuda()
+if len(sys.argv) > 2: m.precision = sys.argv[2]
 x = torch.randint(0, 256, (B, 1, 128, 128), device="cuda").float()
 st, _ = m._state(x)
 plan = st["plan"]
 for _ in range(3): plan.run()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for _ in range(3): plan.run()
+torch.cuda.synchronize(); e0.record()
+for _ in range(5): plan.run()
+e1.record(); torch.cuda.synchronize()
+print(f'forward {e0.elapsed_time(e1)/5:.3f} ms ({m.precision})')
 rows = []
 for i, (kind, r) in enumerate(plan.records):
     plan.run(i, 1); torch.cuda.synchronize()
@@ -20,7 +26,7 @@ for i, (kind, r) in enumerate(plan.records):
     t = e0.elapsed_time(e1) / 3
     extra = ""
     if kind == "conv":
-        extra = f"n={r['n']:5d} nv={r['n_valid']:5d} {r['Ho']:3d}x{r['Wo']:3d} kb={sum(t_*c for _,t_,c in r['segs']):4d} taps={[t_ for _,t_,_ in r['segs']]} issued {r['issued_flops']/t/1e9:6.0f} TF/s"
+        extra = f"n={r['n']:5d} nv={r['n_valid']:5d} {r['Ho']:3d}x{r['Wo']:3d} kb={sum(sg[1]*sg[2] for sg in r['segs']):4d} taps={[sg[1] for sg in r['segs']]} issued {r['issued_flops']/t/1e9:6.0f} TF/s"
     rows.append((t, i, kind, extra))
 tot = sum(r[0] for r in rows)
 print(f"B={B}: sum {tot:.3f} ms")

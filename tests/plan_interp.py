@@ -14,6 +14,19 @@ def _view_nchw(v, pad_to=None):
     return t
 
 
+def _store_pair(o, lo, y):
+    """y [B,H,W,C] fp32 -> o (16-bit) and, for the compensated precision, what that rounding dropped -> lo."""
+    c = y.shape[-1]
+    o.buf[..., o.choff:o.choff + c] = y.to(o.buf.dtype)
+    if lo is not None:
+        lo.buf[..., lo.choff:lo.choff + c] = (y - o.buf[..., o.choff:o.choff + c].float()).to(lo.buf.dtype)
+
+
+def _load_pair(v, lo):
+    x = _view_nchw(v)
+    return x if lo is None else x + _view_nchw(lo)
+
+
 def run_records(plan):
     for kind, r in plan.records:
         if kind == "prep":
@@ -131,24 +144,23 @@ def run_records(plan):
             w = r["weight"].view(r["weight"].shape[0], x.shape[1], pch, pch)
             y = F.conv2d(xn, w, r["bias"], stride=pch).permute(0, 2, 3, 1)
             y = F.layer_norm(y, (y.shape[-1],), r["ln_w"], r["ln_b"], r["eps"])
-            o = r["out"]
-            o.buf[..., o.choff:o.choff + y.shape[-1]] = y.to(o.buf.dtype)
+            _store_pair(r["out"], r.get("out_lo"), y)
         elif kind == "ln":
             v, o = r["src"], r["out"]
-            y = _view_nchw(v).permute(0, 2, 3, 1)
+            y = _load_pair(v, r.get("src_lo")).permute(0, 2, 3, 1)
             y = F.layer_norm(y, (y.shape[-1],), r["w"], r["b"], r["eps"])
             if r["s2d"] == 2:
                 B_, H, W, C = y.shape
                 y = y.view(B_, H // 2, 2, W // 2, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(B_, H // 2, W // 2, 4 * C)
-            o.buf[..., o.choff:o.choff + y.shape[-1]] = y.to(o.buf.dtype)
+            _store_pair(o, r.get("out_lo"), y)
         elif kind == "dwln":
             v, o = r["src"], r["out"]
-            x = _view_nchw(v)
+            x = _load_pair(v, r.get("src_lo"))
             C = x.shape[1]
             w = r["dw_w"].t().reshape(C, 1, 7, 7)
             y = F.conv2d(x, w, r["dw_b"], padding=3, groups=C).permute(0, 2, 3, 1)
             y = F.layer_norm(y, (C,), r["ln_w"], r["ln_b"], r["eps"])
-            o.buf[..., o.choff:o.choff + C] = y.to(o.buf.dtype)
+            _store_pair(o, r.get("out_lo"), y)
         elif kind == "ese":
             v, o = r["src"], r["out"]
             x = _view_nchw(v)

@@ -165,9 +165,9 @@ def test_rdresunet_matches_oracle(cfg, shape):
     d = float((got - want).abs().max())
     print(f"[rdresunet {shape}] max-abs vs fp32 oracle {d:.5f}, PSNR {_psnr(got, want):.1f} dB")
     assert got.shape == want.shape
-    # the RDNet encoder's first stage (stem, LayerNorm, GELU expand / project at half resolution) sits on the same shallow path
-    # to the output and is not compensated yet: emulated 1.2e-2 with the default layer scale, 2e-2 with the randomised one
-    assert _psnr(got, want) >= 50.0 and d <= 3e-2
+    # default model: the north star's 1e-2 (RDNet stage 0 and `final` travel as hi + lo pairs, scripts/dev_error_budget_rd.py);
+    # the reduced net puts relatively more weight on the uncompensated deeper stages
+    assert _psnr(got, want) >= 50.0 and d <= (1e-2 if not cfg else 3e-2)
 
 
 def test_plan_follows_in_place_weight_updates():

@@ -94,3 +94,27 @@ def test_rdresunet_plan_matches_oracle_on_cpu(dry_run, cfg):
     assert got.shape == want.shape
     err = float((got - want).abs().max())
     assert err < 6e-2, err      # 16-bit activations through ~60 layers incl. LayerNorm/GELU; packing bugs give O(1..100)
+
+
+def test_rdresunet_compensated_plan_on_cpu(dry_run):
+    """precision "fp16c": RDNet stage 0 (stem, dwconv + LayerNorm, expand / GELU / project) as (hi, lo) pairs, the low halves of the
+    stage-0 skip in the last respass and `final_lo` as a second e5m2 term of Reconstruction.pre -- the emitted plan must land below
+    the north star's 1e-2 where the single-pass plan sits at ~3e-2 (scripts/dev_error_budget_rd.py)."""
+    from oracle.models import rdresunet_forward
+    from pssr2_b200.models import RDResUNet
+    from tests.test_gpu_net import _randomise_rd
+    torch.manual_seed(0)
+    model = RDResUNet().eval()
+    _randomise_bn(model)
+    _randomise_rd(model)
+    x = torch.tensor(np.random.default_rng(0).integers(0, 256, (1, 1, 128, 128)).astype(np.float32))
+    want = rdresunet_forward(model.state_dict(), x)
+    model.precision = "fp16c"
+    st = model._build(x.shape, x.dtype, torch.device("cpu"))
+    recs = st["plan"].records
+    assert any(k == "stem" and r["out_lo"] is not None for k, r in recs) and any(k == "dwln" and r["src_lo"] is not None for k, r in recs)
+    assert any(k == "conv" and any(len(sg) > 3 and sg[3] == 1 and sg[2] == 2 for sg in r["segs"]) for k, r in recs)     # [final8 | final_lo8]
+    st["x"].copy_(x)
+    run_records(st["plan"])
+    err = float((st["out"] - want).abs().max())
+    assert err < 1e-2, err
