@@ -164,6 +164,7 @@ int pssr_resize_bilinear(const void* src, void* dst, int32_t n, int32_t h, int32
 #define PSSR_OP_TAILSUM 9     /* 9-tap gather of the fused Reconstruction tail + *128+128   */
 #define PSSR_OP_STEM 10       /* RDNet PatchifyStem: normalise + patch conv + LayerNorm2d   */
 #define PSSR_OP_CAST8 11      /* 16-bit NHWC view * scale -> e5m2 NHWC (operand of PSSR_SEG_E5M2 segments) */
+#define PSSR_OP_RESAMPLE 12   /* per-channel affine (+ReLU) / k x k max pool / bilinear enlargement of an NHWC view */
 
 /* One NHWC source view of an implicit-GEMM op. */
 typedef struct {
@@ -186,6 +187,8 @@ typedef struct {
                             MMAs (K = 32, twice the 16-bit rate) into the same fp32 accumulator -- the low-order terms of
                             the compensated precision only have to be known to a few bits.  3x3 segments of layers whose
                             width is a multiple of 128 only.                                                          */
+  int32_t dilation;      /* taps == 9 only: tap (dy,dx) reads the source at (y + dy*dilation, x + dx*dilation), zeros outside the
+                            image = nn.Conv2d(padding="same", dilation=d) of ResBlockA (pssr/models/_blocks.py:56).  0 and 1 mean dense. */
 } pssr_kseg_t;
 #define PSSR_SEG_F16 0
 #define PSSR_SEG_E5M2 1
@@ -303,6 +306,19 @@ typedef struct {
   void* out; int32_t out_cstride, out_choff;
 } pssr_cast8_desc_t;
 
+/* PSSR_OP_RESAMPLE: the CUDA-core pieces of the atrous / PSP variants (pssr/models/_blocks.py:43-92) on 16-bit NHWC views.
+ *   mode 0  out = act(in * scale[c] + shift[c])            the BatchNorm(eval) -> ReLU that PRECEDES each first convolution of a
+ *                                                          ResBlockA branch (:52-54; it cannot fold into a conv across the ReLU)
+ *   mode 1  out[b][y][x] = max over the k x k window       F.max_pool2d(x, kernel_size=k) (:85), output [B][H/k][W/k]
+ *   mode 2  bilinear enlargement to Ho x Wo                F.interpolate(size=size, mode="bilinear") (:85): align_corners=False,
+ *                                                          src = max((dst + 0.5) * in/out - 0.5, 0), fp32 lerp                      */
+typedef struct {
+  const void* in; int32_t in_cstride, in_choff, C; int32_t B, H, W;
+  int32_t mode, k, Ho, Wo, relu;
+  const float* scale; const float* shift;     /* mode 0: [C] fp32 (NULL = identity)              */
+  void* out; int32_t out_cstride, out_choff;
+} pssr_resample_desc_t;
+
 /* ---- RDNet encoder ops (pssr/models/_rdnet.py) ---------------------------------------------- */
 /* PSSR_OP_STEM: x/128-1 -> BatchNorm(eval) -> PatchifyStem conv (kernel = stride = patch, _rdnet.py:106-116)
  * -> LayerNorm2d over channels (timm, eps 1e-6).  Output NHWC 16-bit [B][H/patch][W/patch][.].        */
@@ -357,6 +373,7 @@ typedef struct {
     pssr_tail_desc_t tail;
     pssr_tailsum_desc_t tailsum;
     pssr_stem_desc_t stem;
+    pssr_resample_desc_t resample;
     pssr_ln_desc_t ln;
     pssr_dwln_desc_t dwln;
     pssr_ese_desc_t ese;

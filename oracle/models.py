@@ -70,6 +70,44 @@ def resblock(sd, prefix, x, emulate=None):
     return h
 
 
+def resblock_a(sd, prefix, x):
+    """ResBlockA (_blocks.py:43-68): relu( sum_d [BN -> ReLU -> conv3x3(dilation d, padding "same")]*(depth+1) (x)  +  conv1x1(x) );
+    the dilation of branch j is recovered from the state_dict by the caller (it is not stored): ``sd["__dilations__"][prefix]``."""
+    dils = sd["__dilations__"][prefix]
+    total = F.conv2d(x, sd[f"{prefix}.respass.weight"], sd[f"{prefix}.respass.bias"])
+    for j, d in enumerate(dils):
+        h = x
+        i = 0
+        while f"{prefix}.dilations.{j}.{3 * i + 2}.weight" in sd:
+            s, t = _bn_fold(sd, f"{prefix}.dilations.{j}.{3 * i}")
+            h = F.relu(h * s.view(1, -1, 1, 1) + t.view(1, -1, 1, 1))
+            h = F.conv2d(h, sd[f"{prefix}.dilations.{j}.{3 * i + 2}.weight"], sd[f"{prefix}.dilations.{j}.{3 * i + 2}.bias"], padding=d, dilation=d)
+            i += 1
+        total = total + h
+    return F.relu(total)
+
+
+def any_resblock(sd, prefix, x, emulate=None):
+    if f"{prefix}.dilations.0.0.weight" in sd:
+        return resblock_a(sd, prefix, x)
+    return resblock(sd, prefix, x, emulate)
+
+
+def psp_pooling(sd, prefix, x, sizes):
+    """PSP_Pooling.forward (_blocks.py:80-92): channel chunks -> max_pool(size) -> bilinear back to the input size -> conv1x1 + BN + ReLU;
+    concat -> conv1x1 + BN -> ReLU."""
+    size = x.shape[-2:]
+    outs = []
+    for i, chunk in enumerate(torch.chunk(x, len(sizes), 1)):
+        c = F.interpolate(F.max_pool2d(chunk, kernel_size=sizes[i]), size=size, mode="bilinear")
+        c = F.conv2d(c, sd[f"{prefix}.convs.{i}.0.weight"], sd[f"{prefix}.convs.{i}.0.bias"])
+        s, t = _bn_fold(sd, f"{prefix}.convs.{i}.1")
+        outs.append(F.relu(c * s.view(1, -1, 1, 1) + t.view(1, -1, 1, 1)))
+    x = F.conv2d(torch.cat(outs, 1), sd[f"{prefix}.conv_out.weight"], sd[f"{prefix}.conv_out.bias"])
+    s, t = _bn_fold(sd, f"{prefix}.norm_out")
+    return F.relu(x * s.view(1, -1, 1, 1) + t.view(1, -1, 1, 1))
+
+
 def reconstruction(sd, x, scale, emulate=None):
     """relu(pre(x)) -> pixel_shuffle(scale) -> conv   (_blocks.py:15-18)."""
     wp, bp = sd["reconstruction.pre.weight"], sd["reconstruction.pre.bias"]
@@ -89,9 +127,22 @@ def _input_norm(sd, x):
     return x
 
 
-def resunet_forward(sd, x, scale=None, emulate=None):
-    """ResUNet.forward (resunet.py:65-96), default (non-atrous, no PSP) configuration."""
-    sd = {k: v.float() for k, v in sd.items() if v.is_floating_point()}
+def _sd_float(sd, dilations=None, prefixes=()):
+    out = {k: v.float() for k, v in sd.items() if torch.is_tensor(v) and v.is_floating_point()}
+    if dilations:
+        out["__dilations__"] = dict(zip(prefixes, dilations))
+    return out
+
+
+def resunet_forward(sd, x, scale=None, emulate=None, dilations=None, pool_sizes=None):
+    """ResUNet.forward (resunet.py:65-96).  ``dilations`` (one list per hidden level, as the constructor takes them) selects the
+    atrous blocks, ``pool_sizes`` the PSP pooling layers the state_dict holds (reconstruction_pool, encoder_pool)."""
+    n_lv = 0
+    while f"encoder.{n_lv}.respass.weight" in sd:
+        n_lv += 1
+    pre = [f"encoder.{i}" for i in range(n_lv)] + [f"decoder.{i}" for i in range(n_lv - 1)]
+    dl = (list(dilations) + [dilations[-i - 1] for i in range(n_lv - 1)]) if dilations else None      # resunet.py:56-58
+    sd = _sd_float(sd, dl, pre)
     if scale is None:
         hidden0 = sd["reconstruction.conv.weight"].shape[1]
         scale = int(round((sd["reconstruction.pre.weight"].shape[0] / hidden0) ** 0.5))
@@ -101,14 +152,18 @@ def resunet_forward(sd, x, scale=None, emulate=None):
     x = _q(_input_norm(sd, x.float()), emulate)
     skips = [x]
     for i in range(n_enc):
-        x = resblock(sd, f"encoder.{i}", x, emulate)
+        x = any_resblock(sd, f"encoder.{i}", x, emulate)
         if i + 1 < n_enc:
             skips.append(x)
             x = F.max_pool2d(x, 2)
+    if "encoder_pool.conv_out.weight" in sd:             # resunet.py:78-79
+        x = psp_pooling(sd, "encoder_pool", x, pool_sizes)
     for i in range(n_enc - 1):
         x = F.pixel_shuffle(x, 2)
         x = torch.cat([x, skips.pop()], 1)
-        x = resblock(sd, f"decoder.{i}", x, emulate)
+        x = any_resblock(sd, f"decoder.{i}", x, emulate)
+    if "reconstruction_pool.conv_out.weight" in sd:      # resunet.py:87-88
+        x = psp_pooling(sd, "reconstruction_pool", x, pool_sizes)
     x = torch.cat([x, skips.pop()], 1)
     x = reconstruction(sd, x, scale, emulate)
     return x * 128 + 128                               # resunet.py:95
@@ -166,9 +221,12 @@ def rdnet_forward(sd, x, ds_blocks, prefix="encoder"):
 
 
 def rdresunet_forward(sd, x, ds_blocks=(False, True, True, False, False, False, True), scale=None,
-                      patch_size=2):
-    """RDResUNet.forward (rdresunet.py:104-130), default (non-atrous, no PSP) configuration."""
-    sd = {k: v.float() for k, v in sd.items() if v.is_floating_point()}
+                      patch_size=2, dilations=None, pool_sizes=None):
+    """RDResUNet.forward (rdresunet.py:104-130); ``dilations`` / ``pool_sizes`` as in ``resunet_forward``."""
+    nd = 0
+    while f"decoder.{nd}.respass.weight" in sd:
+        nd += 1
+    sd = _sd_float(sd, dilations, [f"decoder.{i}" for i in range(nd)])
     hidden_last = sd["reconstruction.conv.weight"].shape[1]
     if scale is None:
         scale = int(round((sd["reconstruction.pre.weight"].shape[0] / hidden_last) ** 0.5))
@@ -178,10 +236,14 @@ def rdresunet_forward(sd, x, ds_blocks=(False, True, True, False, False, False, 
     while f"decoder.{n_dec}.respass.weight" in sd:
         n_dec += 1
     ratios = [1] + [2] * (n_dec - 1) + [patch_size]
+    if "encoder_pool.conv_out.weight" in sd:             # rdresunet.py:111-112
+        skips[-1] = psp_pooling(sd, "encoder_pool", skips[-1], pool_sizes)
     for i in range(n_dec):
         x = torch.cat([x, skips.pop()], 1) if i != 0 else skips.pop()
-        x = resblock(sd, f"decoder.{i}", x)
+        x = any_resblock(sd, f"decoder.{i}", x)
         x = F.pixel_shuffle(x, ratios[i + 1])
+    if "reconstruction_pool.conv_out.weight" in sd:      # rdresunet.py:120-121
+        x = psp_pooling(sd, "reconstruction_pool", x, pool_sizes)
     x = torch.cat([x, skips.pop()], 1)
     x = reconstruction(sd, x, scale)
     return x * 128 + 128

@@ -82,7 +82,7 @@ class Src(Structure):
 
 
 class KSeg(Structure):
-    _fields_ = [("src", c_int32), ("taps", c_int32), ("cblocks", c_int32), ("fmt", c_int32)]
+    _fields_ = [("src", c_int32), ("taps", c_int32), ("cblocks", c_int32), ("fmt", c_int32), ("dilation", c_int32)]
 
 
 class ConvDesc(Structure):
@@ -144,6 +144,12 @@ class DwLnDesc(Structure):
                 ("in_lo", c_void_p), ("out_lo", c_void_p)]
 
 
+class ResampleDesc(Structure):
+    _fields_ = [("in_", c_void_p), ("in_cstride", c_int32), ("in_choff", c_int32), ("C", c_int32), ("B", c_int32), ("H", c_int32),
+                ("W", c_int32), ("mode", c_int32), ("k", c_int32), ("Ho", c_int32), ("Wo", c_int32), ("relu", c_int32),
+                ("scale", c_void_p), ("shift", c_void_p), ("out", c_void_p), ("out_cstride", c_int32), ("out_choff", c_int32)]
+
+
 class EseDesc(Structure):
     _fields_ = [("in_", c_void_p), ("in_cstride", c_int32), ("C", c_int32), ("B", c_int32), ("H", c_int32), ("W", c_int32),
                 ("reserved", c_int32), ("fc_w", c_void_p), ("fc_b", c_void_p), ("gamma", c_void_p), ("gate_ws", c_void_p),
@@ -151,7 +157,7 @@ class EseDesc(Structure):
 
 
 class _OpU(Union):
-    _fields_ = [("conv", ConvDesc), ("prep", PrepDesc), ("pool", PoolDesc), ("tail", TailDesc), ("tailsum", TailSumDesc), ("stem", StemDesc), ("ln", LnDesc), ("dwln", DwLnDesc), ("ese", EseDesc), ("cast8", Cast8Desc),
+    _fields_ = [("conv", ConvDesc), ("prep", PrepDesc), ("pool", PoolDesc), ("tail", TailDesc), ("tailsum", TailSumDesc), ("stem", StemDesc), ("ln", LnDesc), ("dwln", DwLnDesc), ("ese", EseDesc), ("cast8", Cast8Desc), ("resample", ResampleDesc),
                 ("pad", c_uint8 * 512)]
 
 
@@ -160,7 +166,7 @@ class Op(Structure):
 
 
 OP_CONV, OP_PREP, OP_MAXPOOL, OP_TAIL, OP_TAILSUM = 1, 2, 3, 4, 9
-OP_DWCONV_LN, OP_LAYERNORM, OP_ESE, OP_STEM, OP_CAST8 = 5, 6, 7, 10, 11
+OP_DWCONV_LN, OP_LAYERNORM, OP_ESE, OP_STEM, OP_CAST8, OP_RESAMPLE = 5, 6, 7, 10, 11, 12
 SEG_F16, SEG_E5M2 = 0, 1
 DT_BF16, DT_FP16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2

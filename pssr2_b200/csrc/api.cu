@@ -79,6 +79,7 @@ int pssr_plan_create(const pssr_op_t* ops, int32_t n_ops, int32_t dtype, pssr_pl
       case PSSR_OP_DWCONV_LN:
       case PSSR_OP_ESE:
       case PSSR_OP_CAST8:
+      case PSSR_OP_RESAMPLE:
         break;
       default:
         set_error("plan_create: op %d has unsupported kind %d", i, op.kind);
@@ -150,6 +151,9 @@ int pssr_plan_run_range(pssr_plan_t* plan, int32_t first, int32_t count, void* s
         break;
       case PSSR_OP_CAST8:
         rc = cast8_launch(op.u.cast8, plan->dtype, st);
+        break;
+      case PSSR_OP_RESAMPLE:
+        rc = resample_launch(op.u.resample, plan->dtype, st);
         break;
       default:
         set_error("plan_run: op %d has unsupported kind %d", i, op.kind);

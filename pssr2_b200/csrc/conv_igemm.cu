@@ -32,7 +32,7 @@ static constexpr int kMaxStages = 8;
 struct ConvKParams {
   const CUtensorMap* tmaps;  // device: [0..2] = sources, [3] = weights
   int n_segs;
-  int seg_src[6], seg_taps[6], seg_cblocks[6];
+  int seg_src[6], seg_taps[6], seg_cblocks[6], seg_dil[6];
   int num_kb;
   int Ho, Wo, B;
   int BW, BH, BNI;
@@ -47,6 +47,9 @@ struct ConvKParams {
   float* out_f32;
   uint16_t* out_lo;
   int lo_cstride, lo_choff;
+  const uint16_t* resid;      // y = act(acc + bias + resid_scale * resid[pixel][n]) (shuffle == 1)
+  int resid_cstride, resid_choff;
+  float resid_scale;
   int out_cstride, out_choff, shuffle, cps, act, fp16;
   int Hout, Wout;
 };
@@ -109,8 +112,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           for (int t = 0; t < taps; ++t) {
             int dy = 0, dx = 0, cs = 1;
             if (taps == 9) {
-              dy = t / 3 - 1;
-              dx = t % 3 - 1;
+              dy = (t / 3 - 1) * p.seg_dil[sg];      // atrous taps: the box moves by the dilation, TMA zero-fills outside the image
+              dx = (t % 3 - 1) * p.seg_dil[sg];
             } else if (taps == 4) {
               dy = t >> 1;
               dx = t & 1;
@@ -210,6 +213,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
               f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
               f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z;
               f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+              if (p.resid != nullptr) {
+                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.resid + (((size_t)n * p.Ho + y) * p.Wo + x) * p.resid_cstride + p.resid_choff + nn));
+                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  f[2 * k] = fmaf(p.resid_scale, unpack1((uint16_t)(rw[k] & 0xffffu), p.fp16), f[2 * k]);
+                  f[2 * k + 1] = fmaf(p.resid_scale, unpack1((uint16_t)(rw[k] >> 16), p.fp16), f[2 * k + 1]);
+                }
+              }
               if (p.act == PSSR_ACT_RELU) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
@@ -306,7 +318,9 @@ int conv_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
                "conv: output channel stride/offset must be multiples of 8");
   PSSR_REQUIRE(d.tail_z == nullptr, PSSR_EUNSUP, "conv: the fused Reconstruction tail needs the v3 kernel (64 channels per sub-position, N %% 256 == 0)");
   PSSR_REQUIRE(d.out != nullptr || d.out_f32 != nullptr, PSSR_EINVAL, "conv: no output buffer");
-  PSSR_REQUIRE(d.resid == nullptr, PSSR_EUNSUP, "conv: the epilogue residual needs the v3 kernel");
+  // (with a pixel shuffle the residual is indexed by GEMM column, i.e. it must come from a GEMM packed with the same N permutation)
+  PSSR_REQUIRE(d.resid == nullptr || (d.resid_cstride % 8 == 0 && d.resid_choff % 8 == 0 && ((uintptr_t)d.resid & 15) == 0),
+               PSSR_EUNSUP, "conv: the epilogue residual needs 16-byte aligned channel slices");
 
   ConvKParams& p = *reinterpret_cast<ConvKParams*>(op.kparams);
   static_assert(sizeof(ConvKParams) <= sizeof(op.kparams), "ConvOp::kparams too small");
@@ -346,6 +360,8 @@ int conv_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
     p.seg_src[s] = sg.src;
     p.seg_taps[s] = sg.taps;
     p.seg_cblocks[s] = sg.cblocks;
+    p.seg_dil[s] = sg.dilation > 1 ? sg.dilation : 1;
+    PSSR_REQUIRE(sg.dilation <= 1 || sg.taps == 9, PSSR_EINVAL, "conv: dilation applies to 3x3 segments");
     num_kb += sg.taps * sg.cblocks;
     if (sg.taps == 4) src_stride2[sg.src] = true;
   }
@@ -402,6 +418,10 @@ int conv_prepare(const pssr_conv_desc_t& d, int dtype, ConvOp& op) {
   p.lo_cstride = d.out_lo_cstride;
   p.lo_choff = d.out_lo_choff;
   PSSR_REQUIRE(d.out_lo == nullptr || (d.out != nullptr && d.out_lo_cstride % 8 == 0 && d.out_lo_choff % 8 == 0), PSSR_EUNSUP, "conv: out_lo needs a 16-bit primary output");
+  p.resid = reinterpret_cast<const uint16_t*>(d.resid);
+  p.resid_cstride = d.resid_cstride;
+  p.resid_choff = d.resid_choff;
+  p.resid_scale = d.resid_scale;
   p.out_cstride = d.out_cstride;
   p.out_choff = d.out_choff;
   p.shuffle = d.shuffle;

@@ -1583,8 +1583,9 @@ static bool v3_cols_geometry(const pssr_conv_desc_t& d, int* cR, int* cG) {
 bool v3_supported(const pssr_conv_desc_t& d) {
   if (getenv("PSSR_CONV_V1") != nullptr) return false;
   for (int s = 0; s < d.n_segs; ++s)
-    if (d.segs[s].taps != 1 && d.segs[s].taps != 9) return false;
+    if ((d.segs[s].taps != 1 && d.segs[s].taps != 9) || d.segs[s].dilation > 1) return false;     // atrous taps: box-per-tap kernel
   if (d.n % 32 != 0 || d.n < 32) return false;
+  if (d.resid != nullptr && (d.shuffle != 1 || d.n != d.n_valid || d.n_valid % 16 != 0)) return false;   // chained partial sums of the atrous blocks
   bool any9 = false;
   for (int s = 0; s < d.n_segs; ++s) any9 = any9 || d.segs[s].taps == 9;
   // small feature maps in flat mode: the padded pixel space wastes (1 - HW/((H+2)(W+2))) of the MMAs (36 % at 8x8, 21 % at

@@ -200,6 +200,86 @@ int cast8_launch(const pssr_cast8_desc_t& d, int dtype, cudaStream_t stream) {
   return PSSR_OK;
 }
 
+// --------------------------------------------------------------------------- resample
+// CUDA-core pieces of the atrous / PSP variants (include/pssr_b200.h PSSR_OP_RESAMPLE): one thread per (output pixel, 8 channels),
+// 16-byte loads and stores, fp32 math.
+__device__ __forceinline__ void rs_unpack8(const uint4& v, float (&f)[8], int fp16) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    f[2 * k] = unpack1((uint16_t)(w[k] & 0xFFFFu), fp16);
+    f[2 * k + 1] = unpack1((uint16_t)(w[k] >> 16), fp16);
+  }
+}
+__global__ void resample_kernel(pssr_resample_desc_t d, int fp16) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int groups = d.C / 8;
+  const int Ho = d.mode == 0 ? d.H : d.Ho, Wo = d.mode == 0 ? d.W : d.Wo;
+  const long long total = (long long)d.B * Ho * Wo * groups;
+  const uint16_t* in = reinterpret_cast<const uint16_t*>(d.in) + d.in_choff;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long pix = i / groups;
+    const int x = (int)(pix % Wo), y = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
+    float f[8];
+    if (d.mode == 0) {
+      rs_unpack8(__ldg(reinterpret_cast<const uint4*>(in + (size_t)pix * d.in_cstride + g * 8)), f, fp16);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (d.scale != nullptr) f[j] = fmaf(f[j], __ldg(d.scale + g * 8 + j), __ldg(d.shift + g * 8 + j));
+        if (d.relu) f[j] = fmaxf(f[j], 0.f);
+      }
+    } else if (d.mode == 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = -INFINITY;
+      for (int dy = 0; dy < d.k; ++dy)
+        for (int dx = 0; dx < d.k; ++dx) {
+          float t[8];
+          rs_unpack8(__ldg(reinterpret_cast<const uint4*>(in + (((size_t)n * d.H + y * d.k + dy) * d.W + x * d.k + dx) * d.in_cstride + g * 8)), t, fp16);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], t[j]);
+        }
+    } else {
+      // torch upsample_bilinear2d, align_corners=False: scale = in / out, src = max(scale * (dst + 0.5) - 0.5, 0)
+      const float sy = (float)d.H / (float)Ho, sx = (float)d.W / (float)Wo;
+      const float fy = fmaxf(sy * ((float)y + 0.5f) - 0.5f, 0.f), fx = fmaxf(sx * ((float)x + 0.5f) - 0.5f, 0.f);
+      const int y0 = (int)fy, x0 = (int)fx;
+      const int y1 = y0 + (y0 < d.H - 1 ? 1 : 0), x1 = x0 + (x0 < d.W - 1 ? 1 : 0);
+      const float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+      float a[8], b[8], c[8], e[8];
+      const size_t base = (size_t)n * d.H;
+      rs_unpack8(__ldg(reinterpret_cast<const uint4*>(in + ((base + y0) * d.W + x0) * d.in_cstride + g * 8)), a, fp16);
+      rs_unpack8(__ldg(reinterpret_cast<const uint4*>(in + ((base + y0) * d.W + x1) * d.in_cstride + g * 8)), b, fp16);
+      rs_unpack8(__ldg(reinterpret_cast<const uint4*>(in + ((base + y1) * d.W + x0) * d.in_cstride + g * 8)), c, fp16);
+      rs_unpack8(__ldg(reinterpret_cast<const uint4*>(in + ((base + y1) * d.W + x1) * d.in_cstride + g * 8)), e, fp16);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = hy * (hx * a[j] + lx * b[j]) + ly * (hx * c[j] + lx * e[j]);
+    }
+    const uint4 o = make_uint4(pack2(f[0], f[1], fp16), pack2(f[2], f[3], fp16), pack2(f[4], f[5], fp16), pack2(f[6], f[7], fp16));
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(d.out) + (size_t)pix * d.out_cstride + d.out_choff + g * 8) = o;
+  }
+}
+
+int resample_launch(const pssr_resample_desc_t& d, int dtype, cudaStream_t stream) {
+  PSSR_REQUIRE(d.in != nullptr && d.out != nullptr, PSSR_EINVAL, "resample: null pointer");
+  PSSR_REQUIRE(d.C > 0 && d.C % 8 == 0 && d.in_cstride % 8 == 0 && d.in_choff % 8 == 0 && d.out_cstride % 8 == 0 && d.out_choff % 8 == 0, PSSR_EUNSUP,
+               "resample: channel counts/strides/offsets must be multiples of 8");
+  PSSR_REQUIRE(d.mode >= 0 && d.mode <= 2, PSSR_EINVAL, "resample: mode %d", d.mode);
+  PSSR_REQUIRE(d.mode != 0 || (d.scale == nullptr) == (d.shift == nullptr), PSSR_EINVAL, "resample: scale and shift come together");
+  PSSR_REQUIRE(d.mode != 1 || (d.k >= 1 && d.Ho == d.H / d.k && d.Wo == d.W / d.k && d.Ho >= 1 && d.Wo >= 1), PSSR_EINVAL, "resample: pool geometry");
+  PSSR_REQUIRE(d.mode != 2 || (d.Ho >= 1 && d.Wo >= 1), PSSR_EINVAL, "resample: output size");
+  const long long total = (long long)d.B * (d.mode == 0 ? d.H : d.Ho) * (d.mode == 0 ? d.W : d.Wo) * (d.C / 8);
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = (long long)device_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  PSSR_CHECK_CUDA(launch_pdl(resample_kernel, dim3((unsigned)blocks), dim3(threads), 0, stream, d, (int)(dtype == PSSR_DT_FP16)));
+  count_launch();
+  return PSSR_OK;
+}
+
 // ------------------------------------------------------------------------------ pool
 __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b, int fp16) {
   if (fp16) {

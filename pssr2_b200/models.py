@@ -14,7 +14,7 @@ import os
 import torch
 import torch.nn as nn
 
-from .plan import ACT_NONE, ACT_RELU, SEG_E5M2, TAIL_COMP, Plan, View, ceil_div, pack_weight, pack_weight8, permute_n, split_lo
+from .plan import ACT_NONE, ACT_RELU, SEG_E5M2, SEG_F16, TAIL_COMP, Plan, View, ceil_div, pack_weight, pack_weight8, permute_n, split_lo
 
 
 def _force_list(item):
@@ -66,6 +66,67 @@ class ResBlock(nn.Module):
                 i += 1
             out.append((w, b))
         return out, (self.respass.weight.detach().float(), self.respass.bias.detach().float())
+
+
+def _bn_affine(bn):
+    s = bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + bn.eps)
+    return s, bn.bias.detach().float() - bn.running_mean.float() * s
+
+
+class ResBlockA(nn.Module):
+    """Parameter container mirroring pssr/models/_blocks.py:43-68: per dilation a pre-activation stack
+    dilations.{j}.{3i} BatchNorm2d, .{3i+1} ReLU, .{3i+2} Conv2d(3x3, padding "same", dilation d_j); respass 1x1."""
+
+    def __init__(self, in_channels, out_channels, dilations, depth, norm=True):
+        super().__init__()
+        self.dilations = nn.ModuleList()
+        for dilation in dilations:
+            conv = nn.Sequential()
+            n_layers = max(depth, 0) + 1
+            for i in range(n_layers):
+                if norm:
+                    conv.append(nn.BatchNorm2d(in_channels if i == 0 else out_channels))
+                conv.append(nn.ReLU(inplace=True))
+                conv.append(nn.Conv2d(in_channels if i == 0 else out_channels, out_channels, kernel_size=3, padding="same", dilation=dilation))
+            self.dilations.append(conv)
+        self.respass = nn.Conv2d(in_channels, out_channels, kernel_size=1)
+        self.dilation_values = [int(d) for d in dilations]
+        self.min_size = max(dilations) * 2 + 1
+        self.depth = depth
+        self.in_channels, self.out_channels = in_channels, out_channels
+
+
+class PSP_Pooling(nn.Module):
+    """Parameter container mirroring pssr/models/_blocks.py:70-92."""
+
+    def __init__(self, channels, sizes):
+        super().__init__()
+        small = channels // len(sizes)
+        self.convs = nn.ModuleList([nn.Sequential(nn.Conv2d(small, small, kernel_size=1), nn.BatchNorm2d(small)) for _ in sizes])
+        self.conv_out = nn.Conv2d(channels, channels, kernel_size=1)
+        self.norm_out = nn.BatchNorm2d(channels)
+        self.sizes = list(sizes)
+        self.channels = channels
+
+
+def get_resblock(in_channels, out_channels, dilations, depth, norm=True):
+    """pssr/models/_blocks.py:114-117."""
+    if dilations:
+        return ResBlockA(in_channels, out_channels, dilations, depth, norm)
+    return ResBlock(in_channels, out_channels, depth, norm)
+
+
+def _check_variant_args(hidden, dilations, pool_sizes, encoder_pool, pool_last):
+    """The constructor checks of pssr/models/resunet.py:42-48 / rdresunet.py:72-78."""
+    if dilations and len(dilations) != len(hidden):
+        raise ValueError(f"Amount of dilations must equal amount of hidden residual blocks. Given values are {len(dilations)} and {len(hidden)} respectively.")
+    if pool_sizes:
+        if hidden[0] % len(pool_sizes) != 0:
+            raise ValueError(f"hidden[0] must be divisible by len(pool_sizes). Given values are {hidden[0]} and {len(pool_sizes)} respectively.")
+        if encoder_pool and pool_last % len(pool_sizes) != 0:
+            raise ValueError(f"hidden[-1] must be divisible by len(pool_sizes) if encoder_pool is True. Given values are {pool_last} and {len(pool_sizes)} respectively.")
+    elif encoder_pool:
+        raise ValueError("encoder_pool cannot be True if pool_sizes are not provided.")
 
 
 class Reconstruction(nn.Module):
@@ -241,6 +302,112 @@ class _PlanModule(nn.Module):
             plan.tail(View(ps_out), wc.permute(0, 2, 3, 1).contiguous(), bc, 128.0, 128.0, out, out_u8)
         self._out, self._out_u8 = out, out_u8
 
+    # ---- atrous / PSP variants (pssr/models/_blocks.py:43-92): single-pass plans over the same conv op ---------------------
+    @staticmethod
+    def _emit_any_block(plan, blk, src, dst, shuffle, B, H, W, dev):
+        """One residual block (ResBlock or ResBlockA) reading the single view ``src`` and writing ``dst`` (pixel-shuffled by ``shuffle``)."""
+        cin = blk.in_channels
+        cb = ceil_div(cin, 64)
+        if isinstance(blk, ResBlock):
+            scr = [torch.zeros(B, H, W, blk.out_channels, dtype=plan.tdtype, device=dev) for _ in range(2)]
+            return _PlanModule._emit_resblock(plan, blk, [src], [(0, 9, cb)], lambda wt: [wt], lambda wt: ([wt], [(0, 1, cb)]), scr, dst, shuffle, B, H, W)
+        if W < blk.min_size:
+            raise ValueError(f"Tensor size {(B, cin, H, W)} is smaller than than dilation kernel size {blk.min_size}.")
+        cout = blk.out_channels
+        cbo = ceil_div(cout, 64)
+        z = lambda c: torch.zeros(B, H, W, c, dtype=plan.tdtype, device=dev)
+        c8 = ceil_div(cin, 8) * 8
+        src8 = View(src.buf, src.choff, c8)             # channels beyond cin are zeros (padded input plane) or get scale = shift = 0
+        finals = []                                     # (view, weight [cout, c, 3, 3], taps, cblocks, dilation) K segments of the last GEMM
+        bias = blk.respass.bias.detach().float().clone()
+        for d, seq in zip(blk.dilation_values, blk.dilations):
+            mods = list(seq)
+            bns = [m for m in mods if isinstance(m, nn.BatchNorm2d)]
+            convs = [m for m in mods if isinstance(m, nn.Conv2d)]
+            n = len(convs)
+            # BatchNorm -> ReLU ahead of the first convolution: its own pass (zero padding comes AFTER it, so it cannot fold)
+            a0 = z(c8)
+            if bns:
+                s0, t0 = _bn_affine(bns[0])
+            else:
+                s0, t0 = torch.ones(cin, device=dev), torch.zeros(cin, device=dev)
+            pad = torch.zeros(c8 - cin, device=dev)
+            plan.affine(src8, View(a0), torch.cat([s0, pad]).contiguous(), torch.cat([t0, pad]).contiguous(), relu=True)
+            cur, ccur = View(a0, 0, cin), cin
+            for i, cv in enumerate(convs):
+                w, b = cv.weight.detach().float(), cv.bias.detach().float()
+                plan.flops += 2 * w.numel() * B * H * W
+                if i + 1 == n:
+                    finals.append((cur, w, 9, ceil_div(ccur, 64), d))
+                    bias += b
+                    break
+                if bns:                                  # the NEXT layer's BatchNorm follows this conv directly: folded; then ReLU
+                    s1, t1 = _bn_affine(bns[i + 1])
+                    w, b = w * s1.view(-1, 1, 1, 1), b * s1 + t1
+                nxt = z(cout)
+                plan.conv([cur], [(0, 9, ceil_div(ccur, 64), SEG_F16, d)], pack_weight([w], plan.dtype), b.contiguous(), View(nxt), Ho=H, Wo=W, B=B, act=ACT_RELU)
+                cur, ccur = View(nxt), cout
+        wr = blk.respass.weight.detach().float()
+        plan.flops += 2 * wr.numel() * B * H * W
+        finals.append((src, wr, 1, cb, 1))
+        # relu(sum_d branch_d + respass): K segments of one GEMM; a conv op takes four sources, so longer sums chain through the
+        # epilogue residual (16-bit partial sums in the GEMM's own column order)
+        part = None
+        while finals:
+            group, finals = finals[:4], finals[4:]
+            last = not finals
+            wp = pack_weight([g[1] for g in group], plan.dtype, shuffle)
+            bp = permute_n(bias if part is None else torch.zeros_like(bias), shuffle).contiguous()
+            segs = [(k, g[2], g[3], SEG_F16, g[4]) for k, g in enumerate(group)]
+            out = dst if last else View(z(cout))
+            plan.conv([g[0] for g in group], segs, wp, bp, out, Ho=H, Wo=W, B=B, shuffle=shuffle if last else 1, act=ACT_RELU if last else ACT_NONE,
+                      resid=part)
+            part = out
+        return dst
+
+    @staticmethod
+    def _emit_psp(plan, psp, src, dst, shuffle, B, H, W, dev):
+        """PSP_Pooling.forward (_blocks.py:80-92) from the view ``src`` into ``dst``."""
+        C, ns = psp.channels, len(psp.sizes)
+        small = C // ns
+        if small % 8 or C != small * ns:
+            raise NotImplementedError(f"PSP pooling over {C} channels in {ns} chunks: chunks must be multiples of 8 channels")
+        z = lambda h, w, c: torch.zeros(B, h, w, c, dtype=plan.tdtype, device=dev)
+        up = z(H, W, C)
+        wblk = torch.zeros(C, C, 1, 1, device=dev)
+        bblk = torch.zeros(C, device=dev)
+        for i, k in enumerate(psp.sizes):
+            chunk = View(src.buf, src.choff + i * small, small)
+            dchunk = View(up, i * small, small)
+            if H // k < 1 or W // k < 1:
+                raise ValueError(f"PSP pooling size {k} exceeds the {H}x{W} feature map")
+            if k == 1:
+                plan._resample(chunk, dchunk, 0)
+            else:
+                pooled = z(H // k, W // k, small)
+                plan.maxpool_k(chunk, View(pooled), k)
+                plan.upsample_bilinear(View(pooled), dchunk)
+            cv, bn = psp.convs[i][0], psp.convs[i][1]
+            s1, t1 = _bn_affine(bn)
+            wblk[i * small:(i + 1) * small, i * small:(i + 1) * small] = cv.weight.detach().float() * s1.view(-1, 1, 1, 1)
+            bblk[i * small:(i + 1) * small] = cv.bias.detach().float() * s1 + t1
+            plan.flops += 2 * cv.weight.numel() * B * H * W
+        n_pad = ceil_div(C, 32) * 32
+        mid = z(H, W, C)
+        # the per-chunk 1x1 convolutions as ONE block-diagonal GEMM
+        plan.conv([View(up)], [(0, 1, ceil_div(C, 64))], pack_weight([wblk], plan.dtype, 1, n_pad), torch.cat([bblk, torch.zeros(n_pad - C, device=dev)]).contiguous(),
+                  View(mid), Ho=H, Wo=W, B=B, n_valid=C, act=ACT_RELU)
+        so, to = _bn_affine(psp.norm_out)
+        wo = psp.conv_out.weight.detach().float() * so.view(-1, 1, 1, 1)
+        bo = psp.conv_out.bias.detach().float() * so + to
+        plan.flops += 2 * wo.numel() * B * H * W
+        if shuffle == 1 and n_pad > C:
+            wpk, bpk = pack_weight([wo], plan.dtype, 1, n_pad), torch.cat([bo, torch.zeros(n_pad - C, device=dev)]).contiguous()
+        else:
+            wpk, bpk = pack_weight([wo], plan.dtype, shuffle), permute_n(bo, shuffle).contiguous()
+        plan.conv([View(mid)], [(0, 1, ceil_div(C, 64))], wpk, bpk, dst, Ho=H, Wo=W, B=B, n_valid=C, shuffle=shuffle, act=ACT_RELU)
+        return dst
+
     @staticmethod
     def _emit_resblock(plan, blk, srcs, seg_spec, w0_parts_fn, wr_parts_fn, scratch, dst, shuffle, B, H, W, res_srcs=None, out_lo=None,
                        resid=None, resid_scale=1.0):
@@ -327,27 +494,84 @@ class ResUNet(_PlanModule):
         super().__init__()
         channels = _force_list(channels)
         channels = channels * 2 if len(channels) == 1 else channels
-        if dilations or pool_sizes or encoder_pool:
-            raise NotImplementedError(
-                "pssr2_b200.ResUNet implements the default residual path; the atrous / PSP-pooling variants "
-                "(ResBlockA, PSP_Pooling) are outside the accelerated hot path")
         hidden = list(hidden)
-        self.norm = nn.BatchNorm2d(channels[0])
+        _check_variant_args(hidden, dilations, pool_sizes, encoder_pool, hidden[-1])
+        self.norm = nn.BatchNorm2d(channels[0]) if not dilations else None
         self.encoder, self.decoder = nn.ModuleList(), nn.ModuleList()
         layers = [channels[0], *hidden]
         n_layers = len(layers) - 1
         for i in range(n_layers):
-            self.encoder.append(ResBlock(layers[i], layers[i + 1], depth))
+            self.encoder.append(get_resblock(layers[i], layers[i + 1], dilations[i] if dilations else None, depth))
             if i + 1 < n_layers:
-                self.decoder.append(ResBlock(layers[-i - 1] - int(layers[-i - 2] / 2), layers[-i - 2], depth))
-        self.encoder_pool = None
-        self.reconstruction_pool = None
+                self.decoder.append(get_resblock(layers[-i - 1] - int(layers[-i - 2] / 2), layers[-i - 2], dilations[-i - 1] if dilations else None, depth))
+        self.encoder_pool = PSP_Pooling(hidden[-1], pool_sizes) if pool_sizes and encoder_pool else None
+        self.reconstruction_pool = PSP_Pooling(hidden[0], pool_sizes) if pool_sizes else None
         self.reconstruction = Reconstruction(channels[0], channels[1], hidden[0], scale)
         self.channels, self.hidden, self.scale = channels, hidden, scale
+        self.variant = bool(dilations or pool_sizes)      # atrous / PSP models run the single-pass variant plan (_build_variant)
 
     def extra_repr(self):
-        return (f"ResUNet with {self.reconstruction.scale}x upscaling\n{len(self.encoder)} residual decoder blocks with "
-                f"{self.encoder[0].depth} hidden layers each\nPSP pooling disabled")
+        return (f"{'Atrous ' if self.norm is None else ''}ResUNet with {self.reconstruction.scale}x upscaling\n{len(self.encoder)} residual decoder blocks with "
+                f"{self.encoder[0].depth} hidden layers each\nPSP pooling {'enabled' if self.reconstruction_pool else 'disabled'}")
+
+    def _input_affine(self, C, dev):
+        """x/128-1 followed by the input BatchNorm(eval), absent from the atrous models (resunet.py:50,66-68)."""
+        if self.norm is None:
+            return torch.ones(C, device=dev), torch.zeros(C, device=dev)
+        sc = (self.norm.weight.detach().float() / torch.sqrt(self.norm.running_var.float() + self.norm.eps)).contiguous()
+        return sc, (self.norm.bias.detach().float() - self.norm.running_mean.float() * sc).contiguous()
+
+    def _build_variant(self, shape, in_dtype, dev):
+        """Atrous residual blocks and / or PSP pooling (resunet.py:56-58,78-79,87-88): the same forward, block by block, through
+        ``_emit_any_block`` / ``_emit_psp``.  The normalised input is an ordinary (8-channel padded) NHWC tensor here: its 3x3 / atrous
+        taps are TMA boxes like any other layer's."""
+        B, C, H, W = shape
+        hid, L, s = self.hidden, len(self.hidden), self.scale
+        if C > 64:
+            raise NotImplementedError(f"{C} input channels: at most 64 are supported")
+        plan = Plan("fp16" if self.precision == "fp16c" else self.precision)     # the compensated terms exist for the default models only
+        dt = plan.tdtype
+        z = lambda *sh: torch.zeros(*sh, dtype=dt, device=dev)
+        x_in = torch.zeros(B, C, H, W, dtype=in_dtype, device=dev)
+        sc, sh = self._input_affine(C, dev)
+        xn = z(B, H, W, ceil_div(C, 8) * 8)
+        plan.prep(x_in, sc, sh, xn, centre_only=True)
+        up = [hid[l + 1] // 4 for l in range(L - 1)]
+        cat = [z(B, H >> l, W >> l, up[l] + hid[l]) for l in range(L - 1)]
+        cur = View(xn, 0, C)
+        for l in range(L):
+            h, w = H >> l, W >> l
+            blk = self.encoder[l]
+            if l + 1 < L:
+                dst = View(cat[l], up[l], hid[l])
+                self._emit_any_block(plan, blk, cur, dst, 1, B, h, w, dev)
+                pooled = z(B, h // 2, w // 2, hid[l])
+                plan.maxpool(dst, View(pooled))
+                cur = View(pooled)
+            elif self.encoder_pool is not None:
+                deep = View(z(B, h, w, hid[l]))
+                self._emit_any_block(plan, blk, cur, deep, 1, B, h, w, dev)
+                self._emit_psp(plan, self.encoder_pool, deep, View(cat[l - 1], 0, up[l - 1]), 2, B, h, w, dev)
+            else:
+                self._emit_any_block(plan, blk, cur, View(cat[l - 1], 0, up[l - 1]), 2, B, h, w, dev)
+        final = z(B, H, W, hid[0])
+        for j in range(L - 1):
+            l = L - 2 - j
+            h, w = H >> l, W >> l
+            if l > 0:
+                dst, shf = View(cat[l - 1], 0, up[l - 1]), 2
+            elif self.reconstruction_pool is not None:
+                dst, shf = View(z(B, H, W, hid[0])), 1
+            else:
+                dst, shf = View(final), 1
+            self._emit_any_block(plan, self.decoder[j], View(cat[l]), dst, shf, B, h, w, dev)
+        if self.reconstruction_pool is not None:
+            self._emit_psp(plan, self.reconstruction_pool, dst, View(final), 1, B, H, W, dev)
+        xcol = View(xn, 0, C)
+        xcol.wide_input = True
+        self._emit_reconstruction(plan, final, xcol, B, H, W, dev)
+        plan.finalize()
+        return {"plan": plan, "x": x_in, "out": self._out, "out_u8": self._out_u8}
 
     # -------------------------------------------------------------------------------------
     def _build(self, shape, in_dtype, dev):
@@ -355,6 +579,10 @@ class ResUNet(_PlanModule):
         hid, L, s = self.hidden, len(self.hidden), self.scale
         if C != self.channels[0]:
             raise ValueError(f"expected {self.channels[0]} input channels, got {C}")
+        if self.variant:
+            if L < 2 or H % (1 << (L - 1)) or W % (1 << (L - 1)):
+                raise ValueError(f"input size {H}x{W} must be divisible by {1 << (L - 1)}")
+            return self._build_variant(shape, in_dtype, dev)
         if L < 2:
             raise NotImplementedError("ResUNet needs at least two levels (hidden) in the plan builder")
         if H % (1 << (L - 1)) or W % (1 << (L - 1)):
@@ -492,6 +720,14 @@ class ResUNet(_PlanModule):
         return {"plan": plan, "x": x_in, "out": out, "out_u8": out_u8}
 
 
+class ResUNetA():
+    r""":class:`ResUNet` wrapper of Atrous Residual UNet with the reference's alternative defaults (pssr/models/resunet.py:101-140)."""
+
+    def __new__(cls, channels=1, hidden=[64, 128, 256, 512, 1024], scale=4, depth=3, dilations=[[1, 3, 15, 31], [1, 3, 15], [1, 3], [1], [1]],
+                pool_sizes=[1, 2, 4, 8], encoder_pool=False):
+        return ResUNet(channels, hidden, scale, depth, dilations, pool_sizes, encoder_pool)
+
+
 # =============================================================================== RDResUNet
 class LayerNorm2d(nn.Module):
     """Parameter container for timm.layers.LayerNorm2d (weight, bias; LayerNorm over C of NCHW, eps 1e-6)."""
@@ -609,11 +845,17 @@ class RDResUNet(_PlanModule):
         super().__init__()
         channels = _force_list(channels)
         channels = channels * 2 if len(channels) == 1 else channels
-        if dilations or pool_sizes or encoder_pool:
-            raise NotImplementedError("pssr2_b200.RDResUNet implements the default residual decoder; the atrous / PSP-pooling variants "
-                                      "are outside the accelerated hot path")
         hidden = list(hidden)
-        self.norm = nn.BatchNorm2d(channels[0])
+        if dilations and len(dilations) != len(hidden):
+            raise ValueError(f"Amount of dilations must equal amount of hidden residual blocks. Given values are {len(dilations)} and {len(hidden)} respectively.")
+        if pool_sizes:
+            if hidden[0] % len(pool_sizes) != 0:
+                raise ValueError(f"hidden[0] must be divisible by len(pool_sizes). Given values are {hidden[0]} and {len(pool_sizes)} respectively.")
+            if encoder_pool and hidden[-1] % len(pool_sizes) != 0:
+                raise ValueError(f"hidden[-1] must be divisible by len(pool_sizes) if encoder_pool is True. Given values are {hidden[-1]} and {len(pool_sizes)} respectively.")
+        elif encoder_pool:
+            raise ValueError("encoder_pool cannot be True if pool_sizes are not provided.")
+        self.norm = nn.BatchNorm2d(channels[0]) if not dilations else None
         if sum(ds_blocks) != len(hidden) - 1:
             raise ValueError(f"Number of downsampling blocks must be one less than ResUNet hidden layers. Given {sum(ds_blocks)} downsampling blocks but {len(hidden)} hidden layers.")
         self.encoder = RDNet(channels[0], rdnet_init, patch_size, growth_rates, ds_blocks, ese_blocks, n_blocks, bottleneck, drop_rate, compression)
@@ -625,16 +867,17 @@ class RDResUNet(_PlanModule):
         layers = [0, *hidden]
         self.decoder = nn.ModuleList()
         for i in range(len(layers) - 1):
-            self.decoder.append(ResBlock(layers[i] // self.ratios[i] ** 2 + skips[i], layers[i + 1], depth))
-        self.encoder_pool = None
-        self.reconstruction_pool = None
+            self.decoder.append(get_resblock(layers[i] // self.ratios[i] ** 2 + skips[i], layers[i + 1], dilations[i] if dilations else None, depth))
+        self.encoder_pool = PSP_Pooling(skips[0], pool_sizes) if pool_sizes and encoder_pool else None
+        self.reconstruction_pool = PSP_Pooling(hidden[-1] // self.ratios[-1] ** 2, pool_sizes) if pool_sizes else None
         self.reconstruction = Reconstruction(channels[0], channels[1], hidden[-1] // self.ratios[-1] ** 2, scale)
         self.skips = skips
         self.channels, self.hidden, self.scale, self.patch_size = channels, hidden, scale, patch_size
+        self.variant = bool(dilations or pool_sizes)      # atrous / PSP decoders: single-pass plan through _emit_any_block / _emit_psp
 
     def extra_repr(self):
-        return (f"RDResUNet with {self.reconstruction.scale}x upscaling\n{len(self.decoder)} residual blocks with {self.decoder[0].depth} "
-                f"hidden layers each\nSkip connection sizes: {self.skips}\nPSP pooling disabled")
+        return (f"{'Atrous ' if self.norm is None else ''}RDResUNet with {self.reconstruction.scale}x upscaling\n{len(self.decoder)} residual blocks with {self.decoder[0].depth} "
+                f"hidden layers each\nSkip connection sizes: {self.skips}\nPSP pooling {'enabled' if self.reconstruction_pool else 'disabled'}")
 
     # -------------------------------------------------------------------------------------
     def _build(self, shape, in_dtype, dev):
@@ -646,14 +889,16 @@ class RDResUNet(_PlanModule):
         n_ds = sum(enc.ds_blocks)
         if H % (pch << n_ds) or W % (pch << n_ds):
             raise ValueError(f"input size {H}x{W} must be divisible by {pch << n_ds}")
-        plan = Plan(self.precision)
+        plan = Plan("fp16" if (self.variant and self.precision == "fp16c") else self.precision)
         dt = plan.tdtype
         z = lambda *sh: torch.zeros(*sh, dtype=dt, device=dev)
         f32 = lambda t: t.detach().float().contiguous()
         x_in = torch.zeros(B, C, H, W, dtype=in_dtype, device=dev)
-        bn = self.norm
-        sc = (bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + bn.eps)).contiguous()
-        sh = (bn.bias.detach().float() - bn.running_mean.float() * sc).contiguous()
+        if self.norm is None:          # atrous models have no input BatchNorm (rdresunet.py:80)
+            sc, sh = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+        else:
+            sc, sh = _bn_affine(self.norm)
+            sc, sh = sc.contiguous(), sh.contiguous()
         wide_in = C * 9 > 64          # more than 7 input channels: no im2col, the normalised input is an ordinary 3x3 source
         if C > 64:
             raise NotImplementedError(f"{C} input channels: at most 64 are supported")
@@ -806,10 +1051,27 @@ class RDResUNet(_PlanModule):
         sbuf = [torch.zeros(scratch_elems, dtype=dt, device=dev) for _ in range(2)]
         final = z(B, H, W, hid[-1] // self.ratios[-1] ** 2)
         final_lo = torch.zeros_like(final) if comp else None
+        if self.encoder_pool is not None:          # rdresunet.py:111-112: PSP pooling of the deepest skip, in place of it
+            hh, ww = dec_hw[0]
+            pooled_skip = View(z(B, hh, ww, dec_in[0].channels))
+            self._emit_psp(plan, self.encoder_pool, dec_in[0], pooled_skip, 1, B, hh, ww, dev)
+            dec_in[0] = pooled_skip
         for k in range(n_dec):
             hh, ww = dec_hw[k]
             blk = self.decoder[k]
             cin = dec_in[k].channels
+            if self.variant:
+                shf = self.ratios[k + 1]
+                if k + 1 < n_dec:
+                    dst = View(cat[k + 1], 0, up[k + 1])
+                elif self.reconstruction_pool is not None:
+                    dst = View(z(B, H, W, final.shape[3]))
+                else:
+                    dst = View(final)
+                self._emit_any_block(plan, blk, dec_in[k], dst, shf, B, hh, ww, dev)
+                if k + 1 == n_dec and self.reconstruction_pool is not None:
+                    self._emit_psp(plan, self.reconstruction_pool, dst, View(final), 1, B, H, W, dev)
+                continue
             srcs, segs = [dec_in[k]], [(0, 9, ceil_div(cin, 64))]
             w0f = lambda wt: [wt]
             wrf = (lambda cin: (lambda wt: ([wt], [(0, 1, ceil_div(cin, 64))])))(cin)
@@ -833,3 +1095,14 @@ class RDResUNet(_PlanModule):
         self._emit_reconstruction(plan, final, xcol, B, H, W, dev, xcol_lo=xcol_lo, final_lo=final_lo)
         plan.finalize()
         return {"plan": plan, "x": x_in, "out": self._out, "out_u8": self._out_u8}
+
+
+class RDResUNetA():
+    r""":class:`RDResUNet` wrapper with an atrous decoder and the reference's alternative defaults (pssr/models/rdresunet.py:135-215)."""
+
+    def __new__(cls, channels=1, hidden=[1024, 1024, 512, 256], scale=4, depth=3, dilations=[[1], [1], [1, 3], [1, 3, 15]], pool_sizes=[1, 2, 4, 8],
+                encoder_pool=False, rdnet_init=128, growth_rates=[64, 104, 128, 128, 128, 128, 224],
+                ds_blocks=[False, True, True, False, False, False, True], ese_blocks=[False, False, True, True, True, True, True],
+                n_blocks=[3, 3, 3, 3, 3, 3, 3], patch_size=2, bottleneck=4, compression=0.5, drop_rate=0):
+        return RDResUNet(channels, hidden, scale, depth, dilations, pool_sizes, encoder_pool, rdnet_init, growth_rates, ds_blocks, ese_blocks,
+                         n_blocks, patch_size, bottleneck, compression, drop_rate)

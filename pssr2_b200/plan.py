@@ -12,8 +12,8 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, DT_BF16, DT_FP16, OP_CAST8, OP_CONV, OP_DWCONV_LN, OP_ESE, OP_LAYERNORM, OP_MAXPOOL,
-                   OP_PREP, OP_STEM, OP_TAIL, OP_TAILSUM, SEG_E5M2, SEG_F16, Cast8Desc, ConvDesc, DwLnDesc, EseDesc, KSeg, LnDesc, Op,
-                   PoolDesc, PrepDesc, Src, StemDesc, TailDesc, TailSumDesc)
+                   OP_PREP, OP_RESAMPLE, OP_STEM, OP_TAIL, OP_TAILSUM, SEG_E5M2, SEG_F16, Cast8Desc, ConvDesc, DwLnDesc, EseDesc, KSeg, LnDesc, Op,
+                   PoolDesc, PrepDesc, ResampleDesc, Src, StemDesc, TailDesc, TailSumDesc)
 
 TORCH_DT = {DT_BF16: torch.bfloat16, DT_FP16: torch.float16}
 DT_NAMES = {"bf16": DT_BF16, "fp16": DT_FP16, "fp16c": DT_FP16}
@@ -125,7 +125,7 @@ class Plan:
     def conv(self, srcs, segs, weight, bias, out: View, *, Ho, Wo, B, n=None, n_valid=None, shuffle=1, act=ACT_NONE,
              out_scale=None, out_f32=None, tail_weight=None, tail_z=None, tail_layout=0, out_lo: View = None, tail_flags=0, weight8=None,
              resid: View = None, resid_scale=1.0):
-        """srcs: list[View]; segs: list[(src_index, taps, cblocks[, fmt])]; weight [n, Ktot] 16-bit; bias [n] fp32;
+        """srcs: list[View]; segs: list[(src_index, taps, cblocks[, fmt[, dilation]])]; weight [n, Ktot] 16-bit; bias [n] fp32;
         weight8 [n, K8tot] uint8 (e5m2) for the segments with fmt == SEG_E5M2, whose sources are uint8 (e5m2) NHWC views."""
         d = ConvDesc()
         d.n_srcs = len(srcs)
@@ -133,10 +133,11 @@ class Plan:
             d.srcs[i] = Src(s.ptr(), s.channels, s.cstride, s.H, s.W, s.B, 0)
         assert len(srcs) <= 4 and len(segs) <= 6
         d.n_segs = len(segs)
-        segs = [tuple(sg) + (SEG_F16,) * (4 - len(sg)) for sg in segs]
+        segs = [(tuple(sg) + (SEG_F16, 1)[len(sg) - 3:]) for sg in segs]
         ktot = k8tot = 0
-        for i, (si, taps, cb, fmt) in enumerate(segs):
-            d.segs[i] = KSeg(si, taps, cb, fmt)
+        for i, (si, taps, cb, fmt, dil) in enumerate(segs):
+            d.segs[i] = KSeg(si, taps, cb, fmt, dil)
+            assert dil >= 1 and (dil == 1 or taps == 9)
             assert (srcs[si].buf.dtype == torch.uint8) == (fmt == SEG_E5M2)
             if fmt == SEG_E5M2:
                 k8tot += taps * cb * 64
@@ -171,7 +172,8 @@ class Plan:
             d.out_lo_cstride = out_lo.cstride
             d.out_lo_choff = out_lo.choff
         if resid is not None:
-            assert shuffle == 1 and (resid.B, resid.H, resid.W) == (B, Ho, Wo) and resid.buf.dtype == self.tdtype
+            # (with a pixel shuffle the residual is read in the GEMM's own column order: pack its producer with the same shuffle)
+            assert (resid.B, resid.H, resid.W) == (B, Ho, Wo) and resid.buf.dtype == self.tdtype and resid.channels >= d.n_valid
             d.resid = resid.ptr()
             d.resid_cstride = resid.cstride
             d.resid_choff = 0
@@ -220,6 +222,33 @@ class Plan:
         self.ops.append(op)
         self.keep += [src.buf, dst.buf]
         self.records.append(("cast8", dict(src=src, dst=dst, scale=float(scale))))
+
+    def _resample(self, src: View, dst: View, mode, k=1, relu=False, scale=None, shift=None):
+        Ho, Wo = (src.H, src.W) if mode == 0 else (dst.H, dst.W)
+        assert src.channels == dst.channels and src.channels % 8 == 0 and src.B == dst.B and (dst.H, dst.W) == (Ho, Wo)
+        d = ResampleDesc(src.buf.data_ptr(), src.cstride, src.choff, src.channels, src.B, src.H, src.W, mode, k, Ho, Wo, 1 if relu else 0,
+                         scale.data_ptr() if scale is not None else None, shift.data_ptr() if shift is not None else None,
+                         dst.buf.data_ptr(), dst.cstride, dst.choff)
+        op = Op()
+        op.kind = OP_RESAMPLE
+        op.u.resample = d
+        self.ops.append(op)
+        self.keep += [src.buf, dst.buf, scale, shift]
+        self.records.append(("resample", dict(src=src, dst=dst, mode=mode, k=k, relu=relu, scale=scale, shift=shift)))
+
+    def affine(self, src: View, dst: View, scale, shift, relu=True):
+        """dst = act(src * scale[c] + shift[c]): BatchNorm(eval) -> ReLU ahead of a ResBlockA branch (_blocks.py:52-54)."""
+        assert scale.shape == shift.shape == (src.channels,) and scale.dtype == shift.dtype == torch.float32
+        self._resample(src, dst, 0, relu=relu, scale=scale, shift=shift)
+
+    def maxpool_k(self, src: View, dst: View, k):
+        """F.max_pool2d(x, kernel_size=k) (PSP_Pooling, _blocks.py:85)."""
+        assert (dst.H, dst.W) == (src.H // k, src.W // k)
+        self._resample(src, dst, 1, k=k)
+
+    def upsample_bilinear(self, src: View, dst: View):
+        """F.interpolate(x, size=(dst.H, dst.W), mode="bilinear") (PSP_Pooling, _blocks.py:85)."""
+        self._resample(src, dst, 2)
 
     def maxpool(self, src: View, dst: View):
         d = PoolDesc(src.buf.data_ptr(), src.cstride, src.choff, dst.buf.data_ptr(), dst.cstride, dst.choff, src.B, src.H,

@@ -136,6 +136,46 @@ def net_cases():
     np.savez_compressed(os.path.join(OUT, "net.npz"), **out)
 
 
+VARIANT_CASES = [("resunet_atrous", "ResUNet", dict(hidden=[64, 128, 256], dilations=[[1, 3, 15], [1, 3], [1]], depth=1, scale=2), (2, 1, 32, 32)),
+                 ("resunet_psp", "ResUNet", dict(hidden=[64, 128], pool_sizes=[1, 2, 4, 8], encoder_pool=True, depth=1, scale=4), (1, 1, 32, 32)),
+                 ("resunet_a_default_dil", "ResUNet", dict(channels=[3, 1], hidden=[64, 128], dilations=[[1, 3, 15, 31], [1, 3, 15]], pool_sizes=[1, 2, 4, 8], depth=0, scale=2), (1, 3, 64, 64)),
+                 ("rdresunet_a", "RDResUNet", dict(hidden=[128, 128], growth_rates=[32, 40, 64], ds_blocks=[False, True, False], ese_blocks=[False, True, True],
+                                                   n_blocks=[2, 1, 2], rdnet_init=64, scale=2, depth=1, dilations=[[1], [1, 3]], pool_sizes=[1, 2, 4, 8]), (2, 1, 32, 32))]
+
+
+def randomise_variant(m):
+    """Non-trivial BatchNorm statistics / affine parameters and RDNet layer scales (the default gamma = 1e-6 hides the dense blocks)."""
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.copy_(torch.randn(mod.running_mean.shape, generator=g) * 0.1)
+                mod.running_var.copy_(torch.rand(mod.running_var.shape, generator=g) + 0.5)
+                mod.weight.copy_(torch.rand(mod.weight.shape, generator=g) * 0.4 + 0.8)
+                mod.bias.copy_(torch.randn(mod.bias.shape, generator=g) * 0.1)
+        for n, p_ in m.named_parameters():
+            if n.endswith("gamma"):
+                p_.copy_(torch.rand(p_.shape, generator=g) * 0.5 + 0.25)
+
+
+def net_variant_cases():
+    """Atrous residual blocks (ResBlockA) and PSP pooling (pssr/models/_blocks.py:43-92) through the reference's own modules."""
+    import pssr.models as RM
+    out = {}
+    rng = np.random.default_rng(11)
+    for tag, cls, kw, shape in VARIANT_CASES:
+        torch.manual_seed(4321)
+        m = getattr(RM, cls)(**kw).eval()
+        randomise_variant(m)
+        x = torch.tensor(rng.integers(0, 256, shape).astype(np.float32))
+        with torch.no_grad():
+            y = m(x)
+        out[f"{tag}_x"] = x.numpy()
+        out[f"{tag}_y"] = y.numpy()
+        out[f"{tag}_wsum"] = np.array([float(sum(p.double().sum() for p in m.state_dict().values() if p.is_floating_point()))])
+    np.savez_compressed(os.path.join(OUT, "net_variants.npz"), **out)
+
+
 def _pillow_imread(path):
     """Stand-in for tifffile.imread in THIS script only (tifffile is absent): multi-frame grayscale TIFF -> [frames, H, W]."""
     from PIL import Image
@@ -267,6 +307,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "paired":
         paired_cases()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "variants":
+        net_variant_cases()
+        sys.exit(0)
     gen_pair_cases()
     gen_pair_rotation_cases()
     tiling_stitch_cases()
@@ -274,5 +317,6 @@ if __name__ == "__main__":
     net_cases()
     paired_cases()
     collage_cases()
+    net_variant_cases()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

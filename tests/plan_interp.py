@@ -77,8 +77,9 @@ def run_records(plan):
                     wseg = W[:, k0:k0 + kw].reshape(n, taps, cb * 64)
                     k0 += kw
                     x = _view_nchw(v, cb * 64)
+                dil = sg[4] if len(sg) > 4 else 1
                 if taps == 9:
-                    y = F.conv2d(x, wseg.permute(0, 2, 1).reshape(n, cb * 64, 3, 3), padding=1)
+                    y = F.conv2d(x, wseg.permute(0, 2, 1).reshape(n, cb * 64, 3, 3), padding=dil, dilation=dil)
                 elif taps == 1:
                     y = F.conv2d(x, wseg.permute(0, 2, 1).reshape(n, cb * 64, 1, 1))
                 else:
@@ -87,7 +88,7 @@ def run_records(plan):
             assert k0 == W.shape[1]
             acc = acc + r["bias"].view(1, -1, 1, 1)
             if r.get("resid") is not None:
-                acc = acc + r["resid_scale"] * _view_nchw(r["resid"])
+                acc = acc + r["resid_scale"] * _view_nchw(r["resid"])[:, :acc.shape[1]]
             if r["act"] == 1:
                 acc = F.relu(acc)
             elif r["act"] == 2:
@@ -137,6 +138,18 @@ def run_records(plan):
                 ol.buf[..., ol.choff:ol.choff + acc.shape[1]] = (acc.permute(0, 2, 3, 1) - hi).to(ol.buf.dtype)
             if r["out_f32"] is not None:
                 r["out_f32"][..., :acc.shape[1]] = acc.permute(0, 2, 3, 1)
+        elif kind == "resample":
+            v, o = r["src"], r["dst"]
+            x = _view_nchw(v)
+            if r["mode"] == 0:
+                if r["scale"] is not None:
+                    x = x * r["scale"].view(1, -1, 1, 1) + r["shift"].view(1, -1, 1, 1)
+                y = F.relu(x) if r["relu"] else x
+            elif r["mode"] == 1:
+                y = F.max_pool2d(x, r["k"])
+            else:
+                y = F.interpolate(x, size=(o.H, o.W), mode="bilinear")
+            o.buf[..., o.choff:o.choff + y.shape[1]] = y.permute(0, 2, 3, 1).to(o.buf.dtype)
         elif kind == "stem":
             x = r["x"].float()
             xn = (x / 128 - 1) * r["in_scale"].view(1, -1, 1, 1) + r["in_shift"].view(1, -1, 1, 1)

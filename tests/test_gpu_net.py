@@ -170,6 +170,44 @@ def test_rdresunet_matches_oracle(cfg, shape):
     assert _psnr(got, want) >= 50.0 and d <= (1e-2 if not cfg else 3e-2)
 
 
+def test_atrous_and_psp_variants_match_reference_golden():
+    """ResBlockA / PSP_Pooling models (pssr/models/_blocks.py:43-92; ResUNetA-style dilations up to 31 on 64^2 maps, five-source
+    sums chained through the epilogue residual, encoder and reconstruction PSP pooling, an atrous RDResUNet decoder) on the device
+    against the REFERENCE's own outputs (tests/golden/net_variants.npz) -- and against the fp32 oracle when torch's seeded
+    initialisation does not reproduce the generator's weights on this box."""
+    import os
+    from tests.test_oracle import G, VARIANT_CASES, variant_model, variant_oracle
+    import pssr2_b200.models as M
+    g = np.load(os.path.join(G, "net_variants.npz"))
+    for tag, cls, kw in VARIANT_CASES:
+        m = variant_model(tag, cls, kw, g)
+        x = torch.as_tensor(g[f"{tag}_x"])
+        if m is not None:
+            want = torch.as_tensor(g[f"{tag}_y"])
+        else:
+            m = getattr(M, cls)(**kw).eval()
+            _randomise_bn(m)
+            want = variant_oracle(cls, kw, m.state_dict(), x)
+        got = m.cuda()(x.cuda()).cpu()
+        d = float((got - want).abs().max())
+        print(f"[{tag}] max-abs vs the reference {d:.5f}, PSNR {_psnr(got, want):.1f} dB")
+        assert got.shape == want.shape and _psnr(got, want) >= 50.0 and d <= 3e-2
+
+
+def test_resunet_a_wrapper_default_runs():
+    """ResUNetA() with the reference's default dilations [[1,3,15,31],[1,3,15],[1,3],[1],[1]] and PSP pooling at 128^2."""
+    from pssr2_b200.models import ResUNetA
+    torch.manual_seed(3)
+    m = ResUNetA().eval()
+    _randomise_bn(m, 2)
+    x = torch.tensor(np.random.default_rng(4).integers(0, 256, (1, 1, 128, 128)).astype(np.float32))
+    want = resunet_forward(m.state_dict(), x, dilations=[[1, 3, 15, 31], [1, 3, 15], [1, 3], [1], [1]], pool_sizes=[1, 2, 4, 8])
+    got = m.cuda()(x.cuda()).cpu()
+    d = float((got - want).abs().max())
+    print(f"[ResUNetA default] max-abs vs fp32 oracle {d:.5f}, PSNR {_psnr(got, want):.1f} dB")
+    assert got.shape == (1, 1, 512, 512) and _psnr(got, want) >= 50.0 and d <= 3e-2
+
+
 def test_plan_follows_in_place_weight_updates():
     """The plan caches folded copies of the weights; an in-place update after the first forward must invalidate it."""
     from pssr2_b200.models import ResUNet

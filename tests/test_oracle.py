@@ -76,6 +76,52 @@ def test_net_golden():
         assert (OP.pred_array(y.numpy()) != g[f"{tag}_pred"]).mean() < 1e-3
 
 
+VARIANT_CASES = [("resunet_atrous", "ResUNet", dict(hidden=[64, 128, 256], dilations=[[1, 3, 15], [1, 3], [1]], depth=1, scale=2)),
+                 ("resunet_psp", "ResUNet", dict(hidden=[64, 128], pool_sizes=[1, 2, 4, 8], encoder_pool=True, depth=1, scale=4)),
+                 ("resunet_a_default_dil", "ResUNet", dict(channels=[3, 1], hidden=[64, 128], dilations=[[1, 3, 15, 31], [1, 3, 15]], pool_sizes=[1, 2, 4, 8], depth=0, scale=2)),
+                 ("rdresunet_a", "RDResUNet", dict(hidden=[128, 128], growth_rates=[32, 40, 64], ds_blocks=[False, True, False], ese_blocks=[False, True, True],
+                                                   n_blocks=[2, 1, 2], rdnet_init=64, scale=2, depth=1, dilations=[[1], [1, 3]], pool_sizes=[1, 2, 4, 8]))]
+
+
+def variant_model(tag, cls, kw, g):
+    """The repo's module for a golden variant case with the generator script's seeded weights (tests/golden/gen_golden.py
+    net_variant_cases); None when torch's seeded initialisation does not reproduce them here."""
+    import pssr2_b200.models as M
+    torch.manual_seed(4321)
+    m = getattr(M, cls)(**kw).eval()
+    gen = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.copy_(torch.randn(mod.running_mean.shape, generator=gen) * 0.1)
+                mod.running_var.copy_(torch.rand(mod.running_var.shape, generator=gen) + 0.5)
+                mod.weight.copy_(torch.rand(mod.weight.shape, generator=gen) * 0.4 + 0.8)
+                mod.bias.copy_(torch.randn(mod.bias.shape, generator=gen) * 0.1)
+        for n, p_ in m.named_parameters():
+            if n.endswith("gamma"):
+                p_.copy_(torch.rand(p_.shape, generator=gen) * 0.5 + 0.25)
+    wsum = float(sum(p.double().sum() for p in m.state_dict().values() if p.is_floating_point()))
+    return m if abs(wsum - float(g[f"{tag}_wsum"][0])) <= 1e-6 else None
+
+
+def variant_oracle(cls, kw, sd, x):
+    from oracle.models import rdresunet_forward
+    if cls == "ResUNet":
+        return resunet_forward(sd, x, dilations=kw.get("dilations"), pool_sizes=kw.get("pool_sizes"))
+    return rdresunet_forward(sd, x, ds_blocks=kw["ds_blocks"], dilations=kw.get("dilations"), pool_sizes=kw.get("pool_sizes"))
+
+
+@pytest.mark.parametrize("tag,cls,kw", VARIANT_CASES)
+def test_net_variants_golden(tag, cls, kw):
+    """Atrous blocks / PSP pooling (pssr/models/_blocks.py:43-92): the oracle restatement against the reference's own output."""
+    g = np.load(os.path.join(G, "net_variants.npz"))
+    m = variant_model(tag, cls, kw, g)
+    if m is None:
+        pytest.skip("torch's seeded initialisation differs from the generator run; golden weights not reproducible here")
+    y = variant_oracle(cls, kw, m.state_dict(), torch.as_tensor(g[f"{tag}_x"]))
+    assert float((y - torch.as_tensor(g[f"{tag}_y"])).abs().max()) < 2e-4
+
+
 def test_ssim_psnr_bruteforce():
     """parity-unpinned restatement of skimage: check against a direct per-window evaluation."""
     rng = np.random.default_rng(0)

@@ -30,6 +30,39 @@ def test_models_match_reference(ref):
         assert float((r(x) - rdresunet_forward(r.state_dict(), x)).abs().max()) < 1e-4
 
 
+def test_variant_models_match_reference(ref):
+    """ResBlockA / PSP_Pooling (pssr/models/_blocks.py:43-92) and the wrappers' defaults: oracle forward and state_dict keys."""
+    import pssr.models as RM
+    import pssr2_b200.models as M
+    from oracle.models import rdresunet_forward, resunet_forward
+    from tests.test_oracle import VARIANT_CASES
+    torch.manual_seed(0)
+    for tag, cls, kw in VARIANT_CASES:
+        cin = kw.get("channels", [1, 1])[0]
+        x = torch.tensor(np.random.default_rng(1).integers(0, 256, (1, cin, 64, 64)).astype(np.float32))
+        m = getattr(RM, cls)(**kw).eval()
+        mine = getattr(M, cls)(**kw)
+        assert list(m.state_dict().keys()) == list(mine.state_dict().keys())
+        mine.load_state_dict(m.state_dict(), strict=True)
+        assert mine.extra_repr() == m.extra_repr()
+        with torch.no_grad():
+            if cls == "ResUNet":
+                y = resunet_forward(m.state_dict(), x, dilations=kw.get("dilations"), pool_sizes=kw.get("pool_sizes"))
+            else:
+                y = rdresunet_forward(m.state_dict(), x, ds_blocks=kw["ds_blocks"], dilations=kw.get("dilations"), pool_sizes=kw.get("pool_sizes"))
+            assert float((m(x) - y).abs().max()) < 1e-4, tag
+    a, b = RM.ResUNetA(), M.ResUNetA()
+    assert list(a.state_dict().keys()) == list(b.state_dict().keys()) and a.extra_repr() == b.extra_repr()
+    a, b = RM.RDResUNetA(), M.RDResUNetA()
+    assert list(a.state_dict().keys()) == list(b.state_dict().keys()) and a.extra_repr() == b.extra_repr()
+    for bad in (dict(dilations=[[1]]), dict(pool_sizes=[1, 2, 3]), dict(encoder_pool=True)):
+        with pytest.raises(ValueError) as e1:
+            RM.ResUNet(**bad)
+        with pytest.raises(ValueError) as e2:
+            M.ResUNet(**bad)
+        assert str(e1.value) == str(e2.value)
+
+
 def test_state_dict_keys_match_reference(ref):
     from pssr.models import ResUNet as RefResUNet
     from pssr2_b200.models import ResUNet
