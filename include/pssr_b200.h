@@ -165,6 +165,7 @@ int pssr_resize_bilinear(const void* src, void* dst, int32_t n, int32_t h, int32
 #define PSSR_OP_STEM 10       /* RDNet PatchifyStem: normalise + patch conv + LayerNorm2d   */
 #define PSSR_OP_CAST8 11      /* 16-bit NHWC view * scale -> e5m2 NHWC (operand of PSSR_SEG_E5M2 segments) */
 #define PSSR_OP_RESAMPLE 12   /* per-channel affine (+ReLU) / k x k max pool / bilinear enlargement of an NHWC view */
+#define PSSR_OP_WINATTN 13    /* SwinIR shifted-window multi-head attention on an NHWC qkv map            */
 
 /* One NHWC source view of an implicit-GEMM op. */
 typedef struct {
@@ -314,10 +315,22 @@ typedef struct {
  *                                                          src = max((dst + 0.5) * in/out - 0.5, 0), fp32 lerp                      */
 typedef struct {
   const void* in; int32_t in_cstride, in_choff, C; int32_t B, H, W;
-  int32_t mode, k, Ho, Wo, relu;
+  int32_t mode, k, Ho, Wo, relu;              /* relu: 0 none, 1 ReLU, 2 LeakyReLU(0.01) (swinir.py:171) */
   const float* scale; const float* shift;     /* mode 0: [C] fp32 (NULL = identity)              */
   void* out; int32_t out_cstride, out_choff;
 } pssr_resample_desc_t;
+
+/* PSSR_OP_WINATTN: the attention of one SwinTransformerBlock (pssr/models/swinir.py:335-373, :563-592) between its qkv and proj
+ * GEMMs.  qkv: NHWC 16-bit [B][H][W][cstride], channel = which*C + head*(C/heads) + e as nn.Linear(dim, 3*dim) leaves it.  The map is
+ * shifted by -shift, cut into ws x ws windows; per window and head softmax((q*scale) k^T + bias + mask) v, where
+ * biasT[head][j][i] = relative_position_bias_table[relative_position_index[i][j]][head] (fp32, TRANSPOSED) and the mask is -100 between
+ * tokens of different shifted regions (calculate_mask, :320-341; absent when shift == 0).  Tokens return to their unshifted place in
+ * out [B][H][W][out_cstride] at out_choff.  H, W multiples of ws; ws*ws <= 64; C/heads even and <= 32.                      */
+typedef struct {
+  const void* qkv; int32_t cstride, C, heads; int32_t B, H, W; int32_t ws, shift; float scale; int32_t reserved;
+  const float* biasT;
+  void* out; int32_t out_cstride, out_choff;
+} pssr_winattn_desc_t;
 
 /* ---- RDNet encoder ops (pssr/models/_rdnet.py) ---------------------------------------------- */
 /* PSSR_OP_STEM: x/128-1 -> BatchNorm(eval) -> PatchifyStem conv (kernel = stride = patch, _rdnet.py:106-116)
@@ -374,6 +387,7 @@ typedef struct {
     pssr_tailsum_desc_t tailsum;
     pssr_stem_desc_t stem;
     pssr_resample_desc_t resample;
+    pssr_winattn_desc_t winattn;
     pssr_ln_desc_t ln;
     pssr_dwln_desc_t dwln;
     pssr_ese_desc_t ese;

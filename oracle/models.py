@@ -247,3 +247,87 @@ def rdresunet_forward(sd, x, ds_blocks=(False, True, True, False, False, False, 
     x = torch.cat([x, skips.pop()], 1)
     x = reconstruction(sd, x, scale)
     return x * 128 + 128
+
+
+# ------------------------------------------------------------------------------ SwinIR
+def _swin_windows(t, ws):
+    """window_partition (swinir.py:722-736): [B, H, W, C] -> [B * nW, ws * ws, C]."""
+    B, H, W, C = t.shape
+    return t.view(B, H // ws, ws, W // ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws * ws, C)
+
+
+def _swin_mask(H, W, ws, shift):
+    """SwinTransformerBlock.calculate_mask (swinir.py:320-341)."""
+    img = torch.zeros(1, H, W, 1)
+    cnt = 0
+    for hs in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+        for wsl in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+            img[:, hs, wsl, :] = cnt
+            cnt += 1
+    mw = _swin_windows(img, ws).view(-1, ws * ws)
+    m = mw.unsqueeze(1) - mw.unsqueeze(2)
+    return m.masked_fill(m != 0, -100.0).masked_fill(m == 0, 0.0)
+
+
+def swinir_forward(sd, x):
+    """SwinIR.forward (pssr/models/swinir.py:221-258) for the default configuration family: upsampler "pixelshuffle", resi_connection
+    "1conv", patch_norm, no absolute position embedding, patch_size 1; depths, heads, window size and scale are read off the
+    state_dict.  Blocks: SwinTransformerBlock.forward :343-388, WindowAttention.forward :563-592, RSTB.forward :449-450."""
+    sd = {k: v.float() if v.is_floating_point() else v for k, v in sd.items()}
+    x = x.float()
+    H0, W0 = x.shape[2:]
+    tab0 = sd["layers.0.residual_group.blocks.0.attn.relative_position_bias_table"]
+    ws = (int(round(tab0.shape[0] ** 0.5)) + 1) // 2
+    x = F.pad(x, (0, (ws - W0 % ws) % ws, 0, (ws - H0 % ws) % ws), "reflect")          # check_image_size :201-206
+    B, _, H, W = x.shape
+    if min(H, W) <= ws:
+        raise NotImplementedError("maps no larger than one window change the block geometry (swinir.py:298-301)")
+    f0 = F.conv2d(x, sd["conv_first.weight"], sd["conv_first.bias"], padding=1)
+    C = f0.shape[1]
+    ln = lambda t, p: F.layer_norm(t, (C,), sd[p + ".weight"], sd[p + ".bias"], 1e-5)
+    t = f0.flatten(2).transpose(1, 2)
+    t = ln(t, "patch_embed.norm")
+    i = 0
+    while f"layers.{i}.conv.weight" in sd:
+        res = t
+        j = 0
+        while f"layers.{i}.residual_group.blocks.{j}.norm1.weight" in sd:
+            P = f"layers.{i}.residual_group.blocks.{j}"
+            shift = 0 if j % 2 == 0 else ws // 2
+            tab, idx = sd[P + ".attn.relative_position_bias_table"], sd[P + ".attn.relative_position_index"]
+            nh = tab.shape[1]
+            y = ln(t, P + ".norm1").view(B, H, W, C)
+            if shift:
+                y = torch.roll(y, shifts=(-shift, -shift), dims=(1, 2))
+            win = _swin_windows(y, ws)
+            qkv = F.linear(win, sd[P + ".attn.qkv.weight"], sd[P + ".attn.qkv.bias"]).reshape(-1, ws * ws, 3, nh, C // nh).permute(2, 0, 3, 1, 4)
+            attn = (qkv[0] * (C // nh) ** -0.5) @ qkv[1].transpose(-2, -1)
+            attn = attn + tab[idx.view(-1)].view(ws * ws, ws * ws, -1).permute(2, 0, 1).unsqueeze(0)
+            if shift:
+                m = _swin_mask(H, W, ws, shift)
+                attn = (attn.view(B, m.shape[0], nh, ws * ws, ws * ws) + m.unsqueeze(1).unsqueeze(0)).view(-1, nh, ws * ws, ws * ws)
+            y = (attn.softmax(-1) @ qkv[2]).transpose(1, 2).reshape(-1, ws * ws, C)
+            y = F.linear(y, sd[P + ".attn.proj.weight"], sd[P + ".attn.proj.bias"])
+            y = y.view(B, H // ws, W // ws, ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(B, H, W, C)       # window_reverse
+            if shift:
+                y = torch.roll(y, shifts=(shift, shift), dims=(1, 2))
+            t = t + y.view(B, H * W, C)
+            h = F.gelu(F.linear(ln(t, P + ".norm2"), sd[P + ".mlp.fc1.weight"], sd[P + ".mlp.fc1.bias"]))
+            t = t + F.linear(h, sd[P + ".mlp.fc2.weight"], sd[P + ".mlp.fc2.bias"])
+            j += 1
+        img = t.transpose(1, 2).reshape(B, C, H, W)
+        img = F.conv2d(img, sd[f"layers.{i}.conv.weight"], sd[f"layers.{i}.conv.bias"], padding=1)
+        t = img.flatten(2).transpose(1, 2) + res
+        i += 1
+    t = ln(t, "norm")
+    f = F.conv2d(t.transpose(1, 2).reshape(B, C, H, W), sd["conv_after_body.weight"], sd["conv_after_body.bias"], padding=1) + f0
+    f = F.leaky_relu(F.conv2d(f, sd["conv_before_upsample.0.weight"], sd["conv_before_upsample.0.bias"], padding=1), 0.01)
+    k, scale = 0, 1
+    while f"upsample.{k}.weight" in sd:
+        w = sd[f"upsample.{k}.weight"]
+        r = int(round((w.shape[0] / w.shape[1]) ** 0.5))
+        f = F.pixel_shuffle(F.conv2d(f, w, sd[f"upsample.{k}.bias"], padding=1), r)
+        scale *= r
+        k += 2
+    out = F.conv2d(f, sd["conv_last.weight"], sd["conv_last.bias"], padding=1)
+    return out[:, :, :H0 * scale, :W0 * scale]

@@ -69,7 +69,7 @@ def install_shims():
         tm.layers = _mod("timm.layers", DropPath=tp.DropPath, LayerNorm2d=tp.LayerNorm2d,
                          EffectiveSEModule=tp.EffectiveSEModule,
                          to_2tuple=lambda x: (x, x) if not isinstance(x, (tuple, list)) else tuple(x),
-                         trunc_normal_=lambda t, std=1.0, **k: t.normal_(0, std))
+                         trunc_normal_=lambda t, mean=0.0, std=1.0, a=-2.0, b=2.0: __import__('torch').nn.init.trunc_normal_(t, mean, std, a, b))      # timm's is torch's
         tm.models = _mod("timm.models", named_apply=tp.named_apply)
     if _absent("pytorch_msssim"):
         _mod("pytorch_msssim", SSIM=_io_stub, MS_SSIM=_io_stub, ssim=_io_stub, ms_ssim=_io_stub)

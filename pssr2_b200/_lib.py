@@ -13,7 +13,7 @@ from ctypes import (POINTER, Structure, Union, c_char_p, c_double, c_float, c_in
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libpssr_b200.so")
-SOURCES = ["api.cu", "conv_igemm.cu", "conv_v3.cu", "tiff_io.cu", "net_aux.cu", "rdnet.cu", "crappify.cu", "stitch.cu", "metrics.cu"]
+SOURCES = ["api.cu", "conv_igemm.cu", "conv_v3.cu", "tiff_io.cu", "net_aux.cu", "rdnet.cu", "swin.cu", "crappify.cu", "stitch.cu", "metrics.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
@@ -150,6 +150,12 @@ class ResampleDesc(Structure):
                 ("scale", c_void_p), ("shift", c_void_p), ("out", c_void_p), ("out_cstride", c_int32), ("out_choff", c_int32)]
 
 
+class WinAttnDesc(Structure):
+    _fields_ = [("qkv", c_void_p), ("cstride", c_int32), ("C", c_int32), ("heads", c_int32), ("B", c_int32), ("H", c_int32), ("W", c_int32),
+                ("ws", c_int32), ("shift", c_int32), ("scale", c_float), ("reserved", c_int32), ("biasT", c_void_p), ("out", c_void_p),
+                ("out_cstride", c_int32), ("out_choff", c_int32)]
+
+
 class EseDesc(Structure):
     _fields_ = [("in_", c_void_p), ("in_cstride", c_int32), ("C", c_int32), ("B", c_int32), ("H", c_int32), ("W", c_int32),
                 ("reserved", c_int32), ("fc_w", c_void_p), ("fc_b", c_void_p), ("gamma", c_void_p), ("gate_ws", c_void_p),
@@ -157,7 +163,7 @@ class EseDesc(Structure):
 
 
 class _OpU(Union):
-    _fields_ = [("conv", ConvDesc), ("prep", PrepDesc), ("pool", PoolDesc), ("tail", TailDesc), ("tailsum", TailSumDesc), ("stem", StemDesc), ("ln", LnDesc), ("dwln", DwLnDesc), ("ese", EseDesc), ("cast8", Cast8Desc), ("resample", ResampleDesc),
+    _fields_ = [("conv", ConvDesc), ("prep", PrepDesc), ("pool", PoolDesc), ("tail", TailDesc), ("tailsum", TailSumDesc), ("stem", StemDesc), ("ln", LnDesc), ("dwln", DwLnDesc), ("ese", EseDesc), ("cast8", Cast8Desc), ("resample", ResampleDesc), ("winattn", WinAttnDesc),
                 ("pad", c_uint8 * 512)]
 
 
@@ -166,7 +172,7 @@ class Op(Structure):
 
 
 OP_CONV, OP_PREP, OP_MAXPOOL, OP_TAIL, OP_TAILSUM = 1, 2, 3, 4, 9
-OP_DWCONV_LN, OP_LAYERNORM, OP_ESE, OP_STEM, OP_CAST8, OP_RESAMPLE = 5, 6, 7, 10, 11, 12
+OP_DWCONV_LN, OP_LAYERNORM, OP_ESE, OP_STEM, OP_CAST8, OP_RESAMPLE, OP_WINATTN = 5, 6, 7, 10, 11, 12, 13
 SEG_F16, SEG_E5M2 = 0, 1
 DT_BF16, DT_FP16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2

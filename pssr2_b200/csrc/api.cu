@@ -80,6 +80,7 @@ int pssr_plan_create(const pssr_op_t* ops, int32_t n_ops, int32_t dtype, pssr_pl
       case PSSR_OP_ESE:
       case PSSR_OP_CAST8:
       case PSSR_OP_RESAMPLE:
+      case PSSR_OP_WINATTN:
         break;
       default:
         set_error("plan_create: op %d has unsupported kind %d", i, op.kind);
@@ -154,6 +155,9 @@ int pssr_plan_run_range(pssr_plan_t* plan, int32_t first, int32_t count, void* s
         break;
       case PSSR_OP_RESAMPLE:
         rc = resample_launch(op.u.resample, plan->dtype, st);
+        break;
+      case PSSR_OP_WINATTN:
+        rc = winattn_launch(op.u.winattn, plan->dtype, st);
         break;
       default:
         set_error("plan_run: op %d has unsupported kind %d", i, op.kind);

@@ -228,7 +228,8 @@ __global__ void resample_kernel(pssr_resample_desc_t d, int fp16) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (d.scale != nullptr) f[j] = fmaf(f[j], __ldg(d.scale + g * 8 + j), __ldg(d.shift + g * 8 + j));
-        if (d.relu) f[j] = fmaxf(f[j], 0.f);
+        if (d.relu == 1) f[j] = fmaxf(f[j], 0.f);
+        else if (d.relu == 2) f[j] = f[j] > 0.f ? f[j] : 0.01f * f[j];
       }
     } else if (d.mode == 1) {
 #pragma unroll

@@ -38,6 +38,7 @@ int dwln_launch(const pssr_dwln_desc_t& d, int dtype, cudaStream_t stream);
 int ese_launch(const pssr_ese_desc_t& d, int dtype, cudaStream_t stream);
 int cast8_launch(const pssr_cast8_desc_t& d, int dtype, cudaStream_t stream);
 int resample_launch(const pssr_resample_desc_t& d, int dtype, cudaStream_t stream);
+int winattn_launch(const pssr_winattn_desc_t& d, int dtype, cudaStream_t stream);
 
 }  // namespace pssr
 

@@ -228,7 +228,8 @@ int stem_launch(const pssr_stem_desc_t& d, int dtype, cudaStream_t stream) {
     const int f16 = dtype == PSSR_DT_FP16;
     const int ppw = 256 / d.Cout * 4;                       // pixels per warp and iteration (PX = 4)
     long long nb = (total + 8LL * ppw - 1) / (8LL * ppw);
-    if (nb > cap) nb = cap;
+    const long long cap4 = (long long)device_sm_count() * 2;      // two resident CTAs per SM (56 parameter registers per thread are loaded once)
+    if (nb > cap4) nb = cap4;
     if (d.Cout == 64) stem4_kernel<8, 4><<<(int)nb, 256, 0, stream>>>(d, f16);
     else if (d.Cout == 128) stem4_kernel<16, 4><<<(int)nb, 256, 0, stream>>>(d, f16);
     else stem4_kernel<32, 4><<<(int)nb, 256, 0, stream>>>(d, f16);

@@ -1106,3 +1106,6 @@ class RDResUNetA():
                 n_blocks=[3, 3, 3, 3, 3, 3, 3], patch_size=2, bottleneck=4, compression=0.5, drop_rate=0):
         return RDResUNet(channels, hidden, scale, depth, dilations, pool_sizes, encoder_pool, rdnet_init, growth_rates, ds_blocks, ese_blocks,
                          n_blocks, patch_size, bottleneck, compression, drop_rate)
+
+
+from .swinir import SwinIR  # noqa: E402,F401  (pssr.models exports it next to the UNets; defined in its own file)

@@ -12,8 +12,8 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, DT_BF16, DT_FP16, OP_CAST8, OP_CONV, OP_DWCONV_LN, OP_ESE, OP_LAYERNORM, OP_MAXPOOL,
-                   OP_PREP, OP_RESAMPLE, OP_STEM, OP_TAIL, OP_TAILSUM, SEG_E5M2, SEG_F16, Cast8Desc, ConvDesc, DwLnDesc, EseDesc, KSeg, LnDesc, Op,
-                   PoolDesc, PrepDesc, ResampleDesc, Src, StemDesc, TailDesc, TailSumDesc)
+                   OP_PREP, OP_RESAMPLE, OP_STEM, OP_TAIL, OP_TAILSUM, OP_WINATTN, SEG_E5M2, SEG_F16, Cast8Desc, ConvDesc, DwLnDesc, EseDesc, KSeg, LnDesc, Op,
+                   PoolDesc, PrepDesc, ResampleDesc, Src, StemDesc, TailDesc, TailSumDesc, WinAttnDesc)
 
 TORCH_DT = {DT_BF16: torch.bfloat16, DT_FP16: torch.float16}
 DT_NAMES = {"bf16": DT_BF16, "fp16": DT_FP16, "fp16c": DT_FP16}
@@ -226,7 +226,7 @@ class Plan:
     def _resample(self, src: View, dst: View, mode, k=1, relu=False, scale=None, shift=None):
         Ho, Wo = (src.H, src.W) if mode == 0 else (dst.H, dst.W)
         assert src.channels == dst.channels and src.channels % 8 == 0 and src.B == dst.B and (dst.H, dst.W) == (Ho, Wo)
-        d = ResampleDesc(src.buf.data_ptr(), src.cstride, src.choff, src.channels, src.B, src.H, src.W, mode, k, Ho, Wo, 1 if relu else 0,
+        d = ResampleDesc(src.buf.data_ptr(), src.cstride, src.choff, src.channels, src.B, src.H, src.W, mode, k, Ho, Wo, int(relu),
                          scale.data_ptr() if scale is not None else None, shift.data_ptr() if shift is not None else None,
                          dst.buf.data_ptr(), dst.cstride, dst.choff)
         op = Op()
@@ -240,6 +240,23 @@ class Plan:
         """dst = act(src * scale[c] + shift[c]): BatchNorm(eval) -> ReLU ahead of a ResBlockA branch (_blocks.py:52-54)."""
         assert scale.shape == shift.shape == (src.channels,) and scale.dtype == shift.dtype == torch.float32
         self._resample(src, dst, 0, relu=relu, scale=scale, shift=shift)
+
+    def leaky_relu(self, src: View, dst: View):
+        """nn.LeakyReLU() with the default slope 0.01 (swinir.py:171)."""
+        self._resample(src, dst, 0, relu=2)
+
+    def winattn(self, qkv: View, biasT, heads, ws, shift, scale, out: View):
+        """Shifted-window attention between the qkv and proj GEMMs of a SwinTransformerBlock (PSSR_OP_WINATTN)."""
+        C = out.channels
+        assert qkv.choff == 0 and qkv.channels == 3 * C and biasT.shape == (heads, ws * ws, ws * ws) and biasT.dtype == torch.float32
+        d = WinAttnDesc(qkv.buf.data_ptr(), qkv.cstride, C, heads, qkv.B, qkv.H, qkv.W, ws, shift, float(scale), 0, biasT.data_ptr(),
+                        out.buf.data_ptr(), out.cstride, out.choff)
+        op = Op()
+        op.kind = OP_WINATTN
+        op.u.winattn = d
+        self.ops.append(op)
+        self.keep += [qkv.buf, biasT, out.buf]
+        self.records.append(("winattn", dict(qkv=qkv, biasT=biasT, heads=heads, ws=ws, shift=shift, scale=float(scale), out=out)))
 
     def maxpool_k(self, src: View, dst: View, k):
         """F.max_pool2d(x, kernel_size=k) (PSP_Pooling, _blocks.py:85)."""

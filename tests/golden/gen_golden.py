@@ -176,6 +176,37 @@ def net_variant_cases():
     np.savez_compressed(os.path.join(OUT, "net_variants.npz"), **out)
 
 
+SWINIR_CASES = [("swinir_small", dict(image_size=32, depths=[2, 2], num_heads=[6, 6]), (2, 1, 32, 32)),
+                ("swinir_w4_s2", dict(image_size=64, depths=[3], num_heads=[4], embed_dim=64, scale=2, channels=[3, 1], window_size=4), (1, 3, 40, 24))]
+
+
+def randomise_swinir(m):
+    """Biases and relative position tables away from their zero / tiny initial values, so that they matter."""
+    g = torch.Generator().manual_seed(2)
+    with torch.no_grad():
+        for n, p_ in m.named_parameters():
+            if "relative_position_bias_table" in n or n.endswith("bias"):
+                p_.copy_(torch.randn(p_.shape, generator=g) * 0.2)
+
+
+def swinir_cases():
+    """SwinIR (pssr/models/swinir.py) through the reference's own module (timm's to_2tuple / trunc_normal_ / DropPath from the shim)."""
+    from pssr.models import SwinIR
+    out = {}
+    rng = np.random.default_rng(12)
+    for tag, kw, shape in SWINIR_CASES:
+        torch.manual_seed(777)
+        m = SwinIR(**kw).eval()
+        randomise_swinir(m)
+        x = torch.tensor(rng.integers(0, 256, shape).astype(np.float32))
+        with torch.no_grad():
+            y = m(x)
+        out[f"{tag}_x"] = x.numpy()
+        out[f"{tag}_y"] = y.numpy()
+        out[f"{tag}_wsum"] = np.array([float(sum(p.double().sum() for p in m.state_dict().values() if p.is_floating_point()))])
+    np.savez_compressed(os.path.join(OUT, "swinir.npz"), **out)
+
+
 def _pillow_imread(path):
     """Stand-in for tifffile.imread in THIS script only (tifffile is absent): multi-frame grayscale TIFF -> [frames, H, W]."""
     from PIL import Image
@@ -307,6 +338,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "paired":
         paired_cases()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "swinir":
+        swinir_cases()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "variants":
         net_variant_cases()
         sys.exit(0)
@@ -318,5 +352,6 @@ if __name__ == "__main__":
     paired_cases()
     collage_cases()
     net_variant_cases()
+    swinir_cases()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -144,12 +144,36 @@ def run_records(plan):
             if r["mode"] == 0:
                 if r["scale"] is not None:
                     x = x * r["scale"].view(1, -1, 1, 1) + r["shift"].view(1, -1, 1, 1)
-                y = F.relu(x) if r["relu"] else x
+                y = F.relu(x) if r["relu"] == 1 else (F.leaky_relu(x, 0.01) if r["relu"] == 2 else x)
             elif r["mode"] == 1:
                 y = F.max_pool2d(x, r["k"])
             else:
                 y = F.interpolate(x, size=(o.H, o.W), mode="bilinear")
             o.buf[..., o.choff:o.choff + y.shape[1]] = y.permute(0, 2, 3, 1).to(o.buf.dtype)
+        elif kind == "winattn":
+            v, o = r["qkv"], r["out"]
+            ws, sh, nh = r["ws"], r["shift"], r["heads"]
+            t = v.buf[..., :v.channels].float()                       # [B, H, W, 3C]
+            B_, H, W, C3 = t.shape
+            C = C3 // 3
+            t = torch.roll(t, shifts=(-sh, -sh), dims=(1, 2)) if sh else t
+            win = t.view(B_, H // ws, ws, W // ws, ws, C3).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws * ws, 3, nh, C // nh).permute(2, 0, 3, 1, 4)
+            q, k, vv = win[0] * r["scale"], win[1], win[2]
+            attn = q @ k.transpose(-2, -1) + r["biasT"].transpose(1, 2).unsqueeze(0)
+            if sh:
+                img = torch.zeros(1, H, W, 1)
+                cnt = 0
+                for hs in (slice(0, -ws), slice(-ws, -sh), slice(-sh, None)):
+                    for wsl in (slice(0, -ws), slice(-ws, -sh), slice(-sh, None)):
+                        img[:, hs, wsl, :] = cnt
+                        cnt += 1
+                mw = img.view(1, H // ws, ws, W // ws, ws, 1).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws * ws)
+                mask = (mw.unsqueeze(1) - mw.unsqueeze(2) != 0).float() * -100.0        # [nW, N, N]
+                nW = mask.shape[0]
+                attn = (attn.view(B_, nW, nh, ws * ws, ws * ws) + mask.unsqueeze(1).unsqueeze(0)).view(-1, nh, ws * ws, ws * ws)
+            y = (attn.softmax(-1) @ vv).transpose(1, 2).reshape(B_, H // ws, W // ws, ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(B_, H, W, C)
+            y = torch.roll(y, shifts=(sh, sh), dims=(1, 2)) if sh else y
+            o.buf[..., o.choff:o.choff + C] = y.to(o.buf.dtype)
         elif kind == "stem":
             x = r["x"].float()
             xn = (x / 128 - 1) * r["in_scale"].view(1, -1, 1, 1) + r["in_shift"].view(1, -1, 1, 1)

@@ -35,10 +35,10 @@ def test_ctypes_layout_matches_c(L, tmp_path):
     names = {"pssr_noise_stage_t": L.NoiseStage, "pssr_crappify_args_t": L.CrappifyArgs, "pssr_src_t": L.Src, "pssr_kseg_t": L.KSeg,
              "pssr_conv_desc_t": L.ConvDesc, "pssr_prep_desc_t": L.PrepDesc, "pssr_pool_desc_t": L.PoolDesc,
              "pssr_tail_desc_t": L.TailDesc, "pssr_tailsum_desc_t": L.TailSumDesc, "pssr_stem_desc_t": L.StemDesc, "pssr_ln_desc_t": L.LnDesc,
-             "pssr_dwln_desc_t": L.DwLnDesc, "pssr_ese_desc_t": L.EseDesc, "pssr_cast8_desc_t": L.Cast8Desc, "pssr_resample_desc_t": L.ResampleDesc, "pssr_op_t": L.Op}
+             "pssr_dwln_desc_t": L.DwLnDesc, "pssr_ese_desc_t": L.EseDesc, "pssr_cast8_desc_t": L.Cast8Desc, "pssr_resample_desc_t": L.ResampleDesc, "pssr_winattn_desc_t": L.WinAttnDesc, "pssr_op_t": L.Op}
     probes = [("pssr_crappify_args_t", "lr_frames"), ("pssr_crappify_args_t", "seed"), ("pssr_conv_desc_t", "weights"),
               ("pssr_conv_desc_t", "out_f32"), ("pssr_conv_desc_t", "tail_z"), ("pssr_conv_desc_t", "out_lo"), ("pssr_conv_desc_t", "weights8"), ("pssr_conv_desc_t", "resid_scale"),
-              ("pssr_prep_desc_t", "im2col_lo"), ("pssr_cast8_desc_t", "out_choff"), ("pssr_kseg_t", "dilation"), ("pssr_resample_desc_t", "out_choff"), ("pssr_tailsum_desc_t", "out_u8"), ("pssr_stem_desc_t", "out_lo"), ("pssr_ln_desc_t", "out_lo"), ("pssr_dwln_desc_t", "out_lo"), ("pssr_ese_desc_t", "out_choff"), ("pssr_tail_desc_t", "out_u8"), ("pssr_noise_stage_t", "injected")]
+              ("pssr_prep_desc_t", "im2col_lo"), ("pssr_cast8_desc_t", "out_choff"), ("pssr_kseg_t", "dilation"), ("pssr_resample_desc_t", "out_choff"), ("pssr_winattn_desc_t", "out_choff"), ("pssr_tailsum_desc_t", "out_u8"), ("pssr_stem_desc_t", "out_lo"), ("pssr_ln_desc_t", "out_lo"), ("pssr_dwln_desc_t", "out_lo"), ("pssr_ese_desc_t", "out_choff"), ("pssr_tail_desc_t", "out_u8"), ("pssr_noise_stage_t", "injected")]
     src = '#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(){\n' % HEADER
     for n in names:
         src += f'printf("{n} %zu\\n", sizeof({n}));\n'

@@ -208,6 +208,38 @@ def test_resunet_a_wrapper_default_runs():
     assert got.shape == (1, 1, 512, 512) and _psnr(got, want) >= 50.0 and d <= 3e-2
 
 
+def test_swinir_matches_reference_golden():
+    """SwinIR (pssr/models/swinir.py) on the device against the REFERENCE's own outputs (tests/golden/swinir.npz; window 8 with six
+    heads and window 4 with four heads, shifted and unshifted blocks, a non-square map, scale 4 and 2) -- against the fp32 oracle when
+    torch's seeded initialisation does not reproduce the generator's weights on this box."""
+    import os
+    from oracle.models import swinir_forward
+    from tests.test_oracle import G, SWINIR_CASES, swinir_model
+    from pssr2_b200.models import SwinIR
+    g = np.load(os.path.join(G, "swinir.npz"))
+    for tag, kw in SWINIR_CASES:
+        m = swinir_model(tag, kw, g)
+        x = torch.as_tensor(g[f"{tag}_x"])
+        if m is not None:
+            want = torch.as_tensor(g[f"{tag}_y"])
+        else:
+            m = SwinIR(**kw).eval()
+            want = swinir_forward(m.state_dict(), x)
+        got = m.cuda()(x.cuda()).cpu()
+        d = float((got - want).abs().max())
+        print(f"[{tag}] max-abs vs the reference {d:.5f}, PSNR {_psnr(got, want):.1f} dB")
+        assert got.shape == want.shape and _psnr(got, want) >= 50.0 and d <= 5e-2
+    # the default model at its default size: 16 blocks of window attention over 128^2 tokens
+    torch.manual_seed(5)
+    m = SwinIR().eval()
+    x = torch.tensor(np.random.default_rng(6).integers(0, 256, (1, 1, 128, 128)).astype(np.float32))
+    want = swinir_forward(m.state_dict(), x)
+    got = m.cuda()(x.cuda()).cpu()
+    d = float((got - want).abs().max())
+    print(f"[SwinIR default] max-abs vs fp32 oracle {d:.5f}, PSNR {_psnr(got, want):.1f} dB")
+    assert got.shape == (1, 1, 512, 512) and _psnr(got, want) >= 50.0 and d <= 5e-2
+
+
 def test_plan_follows_in_place_weight_updates():
     """The plan caches folded copies of the weights; an in-place update after the first forward must invalidate it."""
     from pssr2_b200.models import ResUNet

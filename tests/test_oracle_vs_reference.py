@@ -63,6 +63,33 @@ def test_variant_models_match_reference(ref):
         assert str(e1.value) == str(e2.value)
 
 
+def test_swinir_matches_reference(ref):
+    """SwinIR (pssr/models/swinir.py): state_dict keys / shapes / buffers, extra_repr, error contract and the oracle forward."""
+    import pssr.models as RM
+    import pssr2_b200.models as M
+    from oracle.models import swinir_forward
+    from tests.test_oracle import SWINIR_CASES
+    torch.manual_seed(0)
+    for kw in [dict()] + [c[1] for c in SWINIR_CASES]:
+        a, b = RM.SwinIR(**kw).eval(), M.SwinIR(**kw).eval()
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa.keys()) == list(sb.keys())
+        assert all(sa[k].shape == sb[k].shape and sa[k].dtype == sb[k].dtype for k in sa)
+        assert all(torch.equal(sa[k], sb[k]) for k in sa if k.endswith("attn_mask") or k.endswith("relative_position_index"))
+        b.load_state_dict(sa, strict=True)
+        assert a.extra_repr() == b.extra_repr()
+        if kw:
+            cin = kw.get("channels", [1, 1])[0]
+            x = torch.tensor(np.random.default_rng(2).integers(0, 256, (1, cin, 48, 32)).astype(np.float32))
+            with torch.no_grad():
+                assert float((a(x) - swinir_forward(sa, x)).abs().max()) < 1e-4
+    with pytest.raises(ValueError) as e1:
+        RM.SwinIR(depths=[2], num_heads=[2, 2])
+    with pytest.raises(ValueError) as e2:
+        M.SwinIR(depths=[2], num_heads=[2, 2])
+    assert str(e1.value) == str(e2.value)
+
+
 def test_state_dict_keys_match_reference(ref):
     from pssr.models import ResUNet as RefResUNet
     from pssr2_b200.models import ResUNet

@@ -145,3 +145,28 @@ def test_variant_plans_match_reference_golden_on_cpu(dry_run):
         run_records(st["plan"])
         err = float((st["out"] - want).abs().max())
         assert err < 3e-2, (tag, err)      # single-pass fp16 plan (the variants carry no compensation terms)
+
+
+def test_swinir_plan_matches_reference_golden_on_cpu(dry_run):
+    """SwinIR as an emitted plan (1x1 GEMMs for the linear layers with residual / GELU epilogues, LayerNorm, shifted-window attention,
+    pixel-shuffle upsampling, CUDA-core last convolution), interpreted on the CPU, against the reference's own outputs."""
+    import os
+    from oracle.models import swinir_forward
+    from tests.test_oracle import G, SWINIR_CASES, swinir_model
+    g = np.load(os.path.join(G, "swinir.npz"))
+    for tag, kw in SWINIR_CASES:
+        m = swinir_model(tag, kw, g)
+        x = torch.as_tensor(g[f"{tag}_x"])
+        want = torch.as_tensor(g[f"{tag}_y"]) if m is not None else None
+        if m is None:
+            from pssr2_b200.models import SwinIR
+            m = SwinIR(**kw).eval()
+            want = swinir_forward(m.state_dict(), x)
+        st = m._build(x.shape, x.dtype, torch.device("cpu"))
+        assert sum(k == "winattn" for k, _ in st["plan"].records) == sum(kw["depths"])
+        st["x"].copy_(x)
+        run_records(st["plan"])
+        err = float((st["out"] - want).abs().max())
+        assert err < 8e-2, (tag, err)       # single-pass fp16 over 0..255-scale features (conv_first output is not normalised)
+        c = st["out"].shape[1] // 2
+        assert torch.equal(st["out_u8"], st["out"][:, c:c + 1].clamp(0, 255).to(torch.uint8))
