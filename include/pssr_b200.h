@@ -312,7 +312,9 @@ typedef struct {
  *                                                          ResBlockA branch (:52-54; it cannot fold into a conv across the ReLU)
  *   mode 1  out[b][y][x] = max over the k x k window       F.max_pool2d(x, kernel_size=k) (:85), output [B][H/k][W/k]
  *   mode 2  bilinear enlargement to Ho x Wo                F.interpolate(size=size, mode="bilinear") (:85): align_corners=False,
- *                                                          src = max((dst + 0.5) * in/out - 0.5, 0), fp32 lerp                      */
+ *                                                          src = max((dst + 0.5) * in/out - 0.5, 0), fp32 lerp
+ *   mode 3  out[c] = c < k ? in[in_choff + c] : 0          torch.chunk pieces whose width is not a multiple of 8 channels (in_choff and
+ *                                                          in_cstride may be any value here), re-laid 8-aligned and zero-padded to C   */
 typedef struct {
   const void* in; int32_t in_cstride, in_choff, C; int32_t B, H, W;
   int32_t mode, k, Ho, Wo, relu;              /* relu: 0 none, 1 ReLU, 2 LeakyReLU(0.01) (swinir.py:171) */

@@ -215,7 +215,7 @@ __global__ void resample_kernel(pssr_resample_desc_t d, int fp16) {
   pdl_launch_dependents();
   pdl_wait();
   const int groups = d.C / 8;
-  const int Ho = d.mode == 0 ? d.H : d.Ho, Wo = d.mode == 0 ? d.W : d.Wo;
+  const int Ho = (d.mode == 0 || d.mode == 3) ? d.H : d.Ho, Wo = (d.mode == 0 || d.mode == 3) ? d.W : d.Wo;
   const long long total = (long long)d.B * Ho * Wo * groups;
   const uint16_t* in = reinterpret_cast<const uint16_t*>(d.in) + d.in_choff;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -231,6 +231,10 @@ __global__ void resample_kernel(pssr_resample_desc_t d, int fp16) {
         if (d.relu == 1) f[j] = fmaxf(f[j], 0.f);
         else if (d.relu == 2) f[j] = f[j] > 0.f ? f[j] : 0.01f * f[j];
       }
+    } else if (d.mode == 3) {
+      // channel gather: k valid channels from an arbitrarily aligned channel offset, zero-filled up to C (scalar loads)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = g * 8 + j < d.k ? unpack1(in[(size_t)pix * d.in_cstride + g * 8 + j], fp16) : 0.f;
     } else if (d.mode == 1) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = -INFINITY;
@@ -264,13 +268,15 @@ __global__ void resample_kernel(pssr_resample_desc_t d, int fp16) {
 
 int resample_launch(const pssr_resample_desc_t& d, int dtype, cudaStream_t stream) {
   PSSR_REQUIRE(d.in != nullptr && d.out != nullptr, PSSR_EINVAL, "resample: null pointer");
-  PSSR_REQUIRE(d.C > 0 && d.C % 8 == 0 && d.in_cstride % 8 == 0 && d.in_choff % 8 == 0 && d.out_cstride % 8 == 0 && d.out_choff % 8 == 0, PSSR_EUNSUP,
-               "resample: channel counts/strides/offsets must be multiples of 8");
-  PSSR_REQUIRE(d.mode >= 0 && d.mode <= 2, PSSR_EINVAL, "resample: mode %d", d.mode);
+  PSSR_REQUIRE(d.C > 0 && d.C % 8 == 0 && (d.mode == 3 || (d.in_cstride % 8 == 0 && d.in_choff % 8 == 0)) && d.out_cstride % 8 == 0 && d.out_choff % 8 == 0,
+               PSSR_EUNSUP, "resample: channel counts/strides/offsets must be multiples of 8");
+  PSSR_REQUIRE(d.mode >= 0 && d.mode <= 3, PSSR_EINVAL, "resample: mode %d", d.mode);
+  PSSR_REQUIRE(d.mode != 3 || (d.k >= 1 && d.k <= d.C), PSSR_EINVAL, "resample: gather of %d channels into %d", d.k, d.C);
   PSSR_REQUIRE(d.mode != 0 || (d.scale == nullptr) == (d.shift == nullptr), PSSR_EINVAL, "resample: scale and shift come together");
   PSSR_REQUIRE(d.mode != 1 || (d.k >= 1 && d.Ho == d.H / d.k && d.Wo == d.W / d.k && d.Ho >= 1 && d.Wo >= 1), PSSR_EINVAL, "resample: pool geometry");
   PSSR_REQUIRE(d.mode != 2 || (d.Ho >= 1 && d.Wo >= 1), PSSR_EINVAL, "resample: output size");
-  const long long total = (long long)d.B * (d.mode == 0 ? d.H : d.Ho) * (d.mode == 0 ? d.W : d.Wo) * (d.C / 8);
+  const bool same = d.mode == 0 || d.mode == 3;
+  const long long total = (long long)d.B * (same ? d.H : d.Ho) * (same ? d.W : d.Wo) * (d.C / 8);
   const int threads = 256;
   long long blocks = (total + threads - 1) / threads;
   const long long cap = (long long)device_sm_count() * 16;

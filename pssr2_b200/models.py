@@ -370,42 +370,53 @@ class _PlanModule(nn.Module):
         """PSP_Pooling.forward (_blocks.py:80-92) from the view ``src`` into ``dst``."""
         C, ns = psp.channels, len(psp.sizes)
         small = C // ns
-        if small % 8 or C != small * ns:
-            raise NotImplementedError(f"PSP pooling over {C} channels in {ns} chunks: chunks must be multiples of 8 channels")
+        if C != small * ns:
+            raise ValueError(f"PSP pooling: {C} channels do not split into {ns} chunks")
         z = lambda h, w, c: torch.zeros(B, h, w, c, dtype=plan.tdtype, device=dev)
-        up = z(H, W, C)
-        wblk = torch.zeros(C, C, 1, 1, device=dev)
-        bblk = torch.zeros(C, device=dev)
+        sp = ceil_div(small, 8) * 8                      # chunk width in the working layout (8-channel aligned, zero padded)
+        Cp = sp * ns
+        if sp != small:                                   # e.g. RDResUNet's 1040-channel skip in four chunks of 260
+            work = z(H, W, Cp)
+            for i in range(ns):
+                plan.gather_channels(src.buf, src.choff + i * small, small, View(work, i * sp, sp))
+            src = View(work)
+        up = z(H, W, Cp)
+        wblk = torch.zeros(Cp, Cp, 1, 1, device=dev)
+        bblk = torch.zeros(Cp, device=dev)
         for i, k in enumerate(psp.sizes):
-            chunk = View(src.buf, src.choff + i * small, small)
-            dchunk = View(up, i * small, small)
+            chunk = View(src.buf, src.choff + i * sp, sp)
+            dchunk = View(up, i * sp, sp)
             if H // k < 1 or W // k < 1:
                 raise ValueError(f"PSP pooling size {k} exceeds the {H}x{W} feature map")
             if k == 1:
                 plan._resample(chunk, dchunk, 0)
             else:
-                pooled = z(H // k, W // k, small)
+                pooled = z(H // k, W // k, sp)
                 plan.maxpool_k(chunk, View(pooled), k)
                 plan.upsample_bilinear(View(pooled), dchunk)
             cv, bn = psp.convs[i][0], psp.convs[i][1]
             s1, t1 = _bn_affine(bn)
-            wblk[i * small:(i + 1) * small, i * small:(i + 1) * small] = cv.weight.detach().float() * s1.view(-1, 1, 1, 1)
-            bblk[i * small:(i + 1) * small] = cv.bias.detach().float() * s1 + t1
+            wblk[i * sp:i * sp + small, i * sp:i * sp + small] = cv.weight.detach().float() * s1.view(-1, 1, 1, 1)
+            bblk[i * sp:i * sp + small] = cv.bias.detach().float() * s1 + t1
             plan.flops += 2 * cv.weight.numel() * B * H * W
-        n_pad = ceil_div(C, 32) * 32
-        mid = z(H, W, C)
+        np_mid = ceil_div(Cp, 32) * 32
+        mid = z(H, W, Cp)
         # the per-chunk 1x1 convolutions as ONE block-diagonal GEMM
-        plan.conv([View(up)], [(0, 1, ceil_div(C, 64))], pack_weight([wblk], plan.dtype, 1, n_pad), torch.cat([bblk, torch.zeros(n_pad - C, device=dev)]).contiguous(),
-                  View(mid), Ho=H, Wo=W, B=B, n_valid=C, act=ACT_RELU)
+        plan.conv([View(up)], [(0, 1, ceil_div(Cp, 64))], pack_weight([wblk], plan.dtype, 1, np_mid), torch.cat([bblk, torch.zeros(np_mid - Cp, device=dev)]).contiguous(),
+                  View(mid), Ho=H, Wo=W, B=B, n_valid=Cp, act=ACT_RELU)
         so, to = _bn_affine(psp.norm_out)
-        wo = psp.conv_out.weight.detach().float() * so.view(-1, 1, 1, 1)
+        wo_ = psp.conv_out.weight.detach().float() * so.view(-1, 1, 1, 1)
+        wo = torch.zeros(C, Cp, 1, 1, device=dev)         # conv_out reads the chunks where the working layout keeps them
+        for i in range(ns):
+            wo[:, i * sp:i * sp + small] = wo_[:, i * small:(i + 1) * small]
         bo = psp.conv_out.bias.detach().float() * so + to
-        plan.flops += 2 * wo.numel() * B * H * W
+        plan.flops += 2 * wo_.numel() * B * H * W
+        n_pad = ceil_div(C, 32) * 32
         if shuffle == 1 and n_pad > C:
             wpk, bpk = pack_weight([wo], plan.dtype, 1, n_pad), torch.cat([bo, torch.zeros(n_pad - C, device=dev)]).contiguous()
         else:
             wpk, bpk = pack_weight([wo], plan.dtype, shuffle), permute_n(bo, shuffle).contiguous()
-        plan.conv([View(mid)], [(0, 1, ceil_div(C, 64))], wpk, bpk, dst, Ho=H, Wo=W, B=B, n_valid=C, shuffle=shuffle, act=ACT_RELU)
+        plan.conv([View(mid)], [(0, 1, ceil_div(Cp, 64))], wpk, bpk, dst, Ho=H, Wo=W, B=B, n_valid=C, shuffle=shuffle, act=ACT_RELU)
         return dst
 
     @staticmethod

@@ -258,6 +258,18 @@ class Plan:
         self.keep += [qkv.buf, biasT, out.buf]
         self.records.append(("winattn", dict(qkv=qkv, biasT=biasT, heads=heads, ws=ws, shift=shift, scale=float(scale), out=out)))
 
+    def gather_channels(self, buf, choff, valid, dst: View):
+        """dst[..., c] = buf[..., choff + c] for c < valid, zeros up to dst.channels: a torch.chunk piece at any channel offset."""
+        assert dst.channels % 8 == 0 and valid <= dst.channels and choff + valid <= buf.shape[3] and buf.shape[:3] == dst.buf.shape[:3]
+        d = ResampleDesc(buf.data_ptr(), buf.shape[3], choff, dst.channels, dst.B, dst.H, dst.W, 3, valid, dst.H, dst.W, 0, None, None,
+                         dst.buf.data_ptr(), dst.cstride, dst.choff)
+        op = Op()
+        op.kind = OP_RESAMPLE
+        op.u.resample = d
+        self.ops.append(op)
+        self.keep += [buf, dst.buf]
+        self.records.append(("gather", dict(buf=buf, choff=choff, valid=valid, dst=dst)))
+
     def maxpool_k(self, src: View, dst: View, k):
         """F.max_pool2d(x, kernel_size=k) (PSP_Pooling, _blocks.py:85)."""
         assert (dst.H, dst.W) == (src.H // k, src.W // k)

@@ -8,6 +8,7 @@ from pssr2_b200.models import RDResUNet
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 from test_gpu_net import _randomise_bn, _randomise_rd
 
+DW_HI_ONLY = False
 ON = None        # None: every site rounds; else only sites matching
 OFF = set()
 SPLIT = set()
@@ -46,7 +47,8 @@ def resblock(sd, prefix, x):
 def rd_block(sd, p, x, tag):
     L = p + ".layers.layers"
     c = x.shape[1]
-    h = F.conv2d(x, sd[L + ".0.weight"], sd[L + ".0.bias"], padding=3, groups=c)          # fp32 weights on CUDA cores
+    xin = x.half().float() if (DW_HI_ONLY and tag.startswith("s0")) else x
+    h = F.conv2d(xin, sd[L + ".0.weight"], sd[L + ".0.bias"], padding=3, groups=c)          # fp32 weights on CUDA cores
     h = q(OM._ln2d(h, sd[L + ".1.weight"], sd[L + ".1.bias"]), f"a.{tag}.dwln")
     h = F.conv2d(h, q(sd[L + ".2.weight"], f"w.{tag}.expand"), sd[L + ".2.bias"])
     h = q(F.gelu(h), f"a.{tag}.mid")
@@ -138,3 +140,6 @@ if __name__ == "__main__":
     run("fp16c + stage 0 + final split", off=COMP, split=S0 + ["a.decoder.3.3"])
     run("fp16c + stage 0 + final + s1 split", off=COMP, split=S0 + ["a.decoder.3.3", "a.s1.*", "w.s1.*"])
     run("fp16c + stage 0 acts only + final split", off=COMP, split=["a.stem", "a.s0.*", "a.decoder.3.3"])
+    DW_HI_ONLY = True
+    run("fp16c + stage 0 + final split, dw reads hi only", off=COMP, split=S0 + ["a.decoder.3.3"])
+    run("  ... and expand/project weights single (acts split)", off=COMP, split=["a.stem", "a.s0.*", "a.decoder.3.3"])

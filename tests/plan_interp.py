@@ -150,6 +150,10 @@ def run_records(plan):
             else:
                 y = F.interpolate(x, size=(o.H, o.W), mode="bilinear")
             o.buf[..., o.choff:o.choff + y.shape[1]] = y.permute(0, 2, 3, 1).to(o.buf.dtype)
+        elif kind == "gather":
+            o = r["dst"]
+            o.buf[..., o.choff:o.choff + o.channels] = 0
+            o.buf[..., o.choff:o.choff + r["valid"]] = r["buf"][..., r["choff"]:r["choff"] + r["valid"]]
         elif kind == "winattn":
             v, o = r["qkv"], r["out"]
             ws, sh, nh = r["ws"], r["shift"], r["heads"]

@@ -240,6 +240,46 @@ def test_swinir_matches_reference_golden():
     assert got.shape == (1, 1, 512, 512) and _psnr(got, want) >= 50.0 and d <= 5e-2
 
 
+@pytest.mark.parametrize("family,kwargs", [
+    ("ResUNet", {}), ("ResUNet", dict(channels=[3, 3])), ("ResUNet", dict(channels=[3, 1])),
+    ("ResUNet", dict(dilations=[[1, 3, 15, 31], [1, 3, 15], [1, 3], [1], [1]])), ("ResUNet", dict(pool_sizes=[1, 2, 4, 8])),
+    ("ResUNet", dict(pool_sizes=[1, 2, 4, 8], encoder_pool=True)),
+    ("RDResUNet", {}), ("RDResUNet", dict(channels=[3, 3])), ("RDResUNet", dict(channels=[3, 1])),
+    ("RDResUNet", dict(dilations=[[1], [1], [1, 3], [1, 3, 15]])), ("RDResUNet", dict(pool_sizes=[1, 2, 4, 8])),
+    ("RDResUNet", dict(pool_sizes=[1, 2, 4, 8], encoder_pool=True)),
+    ("ResUNetA", {}), ("RDResUNetA", {}), ("SwinIR", {})])
+def test_reference_model_grid(family, kwargs):
+    """The keyword grids of the reference's own tests/test_models.py:4-50 (which assert the output shape only), at its sizes
+    (batch 2, 128^2 -> 512^2): every constructor call a reference user makes runs here -- shape, str(model), and parity with the
+    fp32 oracle of the same state_dict on top."""
+    import pssr2_b200.models as M
+    from oracle.models import rdresunet_forward, swinir_forward
+    torch.manual_seed(11)
+    m = getattr(M, family)(**kwargs).eval()
+    assert str(m)
+    _randomise_bn(m, 4)
+    ch = kwargs.get("channels", [1, 1])
+    x = torch.tensor(np.random.default_rng(8).random((2, ch[0], 128, 128)).astype(np.float32) * 255)        # get_image(): uniform floats
+    sd = m.state_dict()
+    dil = kwargs.get("dilations") or ([[1, 3, 15, 31], [1, 3, 15], [1, 3], [1], [1]] if family == "ResUNetA" else [[1], [1], [1, 3], [1, 3, 15]] if family == "RDResUNetA" else None)
+    pools = kwargs.get("pool_sizes") or ([1, 2, 4, 8] if family.endswith("A") else None)
+    if family == "SwinIR":
+        want = swinir_forward(sd, x)
+    elif family.startswith("RD"):
+        want = rdresunet_forward(sd, x, dilations=dil, pool_sizes=pools)
+    else:
+        want = resunet_forward(sd, x, dilations=dil, pool_sizes=pools)
+    got = m.cuda()(x.cuda()).cpu()
+    assert tuple(got.shape) == (2, ch[1], 512, 512) == tuple(want.shape)
+    d = float((got - want).abs().max())
+    print(f"[{family} {kwargs}] max-abs vs fp32 oracle {d:.5f}, PSNR {_psnr(got, want):.1f} dB")
+    plain = family in ("ResUNet", "RDResUNet") and not (kwargs.get("dilations") or kwargs.get("pool_sizes"))
+    # default-precision plans of the plain models carry the compensation terms (single-channel output: 1e-2; the three-channel
+    # outputs go through the unfused tail); the variants and SwinIR are single-pass fp16 plans
+    tol = (1e-2 if ch[1] == 1 else 3e-2) if plain else 5e-2
+    assert _psnr(got, want) >= 50.0 and d <= tol
+
+
 def test_plan_follows_in_place_weight_updates():
     """The plan caches folded copies of the weights; an in-place update after the first forward must invalidate it."""
     from pssr2_b200.models import ResUNet
