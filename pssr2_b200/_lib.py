@@ -39,9 +39,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + os.environ.get("PSSR_NVCC_EXTRA", "").split()   # developer builds
     procs = []
     objs = []
+    hdr_time = max(os.path.getmtime(p) for p in deps[len(srcs):])
     for s in srcs:
         o = os.path.join(objdir, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
+        if not force and not os.environ.get("PSSR_NVCC_EXTRA") and os.path.exists(o) and os.path.getmtime(o) >= max(os.path.getmtime(s), hdr_time):
+            continue                      # this object is newer than its source and every header
         cmd = [_nvcc()] + flags + ["-c", s, "-o", o]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)

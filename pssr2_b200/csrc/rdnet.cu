@@ -250,8 +250,10 @@ int stem_launch(const pssr_stem_desc_t& d, int dtype, cudaStream_t stream) {
 // iteration -- all PX * G 16-byte loads are issued before the first reduction, so a warp keeps PX * C * 2 bytes in flight
 // instead of one pixel's (the one-pixel version ran at 0.75 TB/s: latency-bound).  In-place use is safe: a warp reads its
 // pixels completely before it writes them.
-template <int G, int PX>
-__global__ void __launch_bounds__(256) ln_kernel(pssr_ln_desc_t d, int fp16) {
+// MINB = CTAs per SM the register allocation is held to (ncu of the <2, 4> variant at 114 registers: 25 % occupancy, 28 % issue
+// slots busy, 13 cycles per issued instruction -- latency-bound; fewer pixels per warp and twice the warps hide it better).
+template <int G, int PX, int MINB>
+__global__ void __launch_bounds__(256, MINB) ln_kernel(pssr_ln_desc_t d, int fp16) {
   const long long total = (long long)d.B * d.H * d.W;
   const int lane = threadIdx.x & 31;
   const uint16_t* in = reinterpret_cast<const uint16_t*>(d.in) + d.in_choff;
@@ -295,7 +297,9 @@ __global__ void __launch_bounds__(256) ln_kernel(pssr_ln_desc_t d, int fp16) {
       size_t opix = (size_t)pix;
       int coff = 0;
       if (d.s2d == 2) {
-        const int x = (int)(pix % d.W), y = (int)((pix / d.W) % d.H), n = (int)(pix / ((long long)d.W * d.H));
+        // 32-bit index arithmetic (ln_launch checks B*H*W < 2^31): three 64-bit divisions per pixel cost more than the LayerNorm
+        const uint32_t pi = (uint32_t)pix, row = pi / (uint32_t)d.W;
+        const int x = (int)(pi - row * (uint32_t)d.W), n = (int)(row / (uint32_t)d.H), y = (int)(row - (uint32_t)n * (uint32_t)d.H);
         opix = ((size_t)n * (d.H / 2) + y / 2) * (d.W / 2) + x / 2;
         coff = ((y & 1) * 2 + (x & 1)) * d.C;
       }
@@ -330,18 +334,19 @@ int ln_launch(const pssr_ln_desc_t& d, int dtype, cudaStream_t stream) {
   PSSR_REQUIRE(d.in_cstride % 8 == 0 && d.in_choff % 8 == 0 && d.out_cstride % 8 == 0 && d.out_choff % 8 == 0, PSSR_EUNSUP, "layernorm: alignment");
   PSSR_REQUIRE(d.s2d == 1 || (d.s2d == 2 && d.H % 2 == 0 && d.W % 2 == 0), PSSR_EUNSUP, "layernorm: bad space-to-depth factor");
   const long long total = (long long)d.B * d.H * d.W;
+  PSSR_REQUIRE(total < (1ll << 31), PSSR_EUNSUP, "layernorm: more than 2^31 pixels");
   long long blocks = (total + 7) / 8;
   const long long cap = (long long)device_sm_count() * 16;
   if (blocks > cap) blocks = cap;
   const int G = (d.C + 255) / 256;
   const int f16 = dtype == PSSR_DT_FP16;
   switch (G) {
-    case 1: ln_kernel<1, 4><<<(int)blocks, 256, 0, stream>>>(d, f16); break;
-    case 2: ln_kernel<2, 4><<<(int)blocks, 256, 0, stream>>>(d, f16); break;
-    case 3: ln_kernel<3, 2><<<(int)blocks, 256, 0, stream>>>(d, f16); break;
-    case 4: ln_kernel<4, 2><<<(int)blocks, 256, 0, stream>>>(d, f16); break;
-    case 5: ln_kernel<5, 1><<<(int)blocks, 256, 0, stream>>>(d, f16); break;
-    default: ln_kernel<6, 1><<<(int)blocks, 256, 0, stream>>>(d, f16); break;
+    case 1: ln_kernel<1, 4, 4><<<(int)blocks, 256, 0, stream>>>(d, f16); break;
+    case 2: ln_kernel<2, 2, 4><<<(int)blocks, 256, 0, stream>>>(d, f16); break;
+    case 3: ln_kernel<3, 2, 3><<<(int)blocks, 256, 0, stream>>>(d, f16); break;
+    case 4: ln_kernel<4, 1, 4><<<(int)blocks, 256, 0, stream>>>(d, f16); break;
+    case 5: ln_kernel<5, 1, 3><<<(int)blocks, 256, 0, stream>>>(d, f16); break;
+    default: ln_kernel<6, 1, 3><<<(int)blocks, 256, 0, stream>>>(d, f16); break;
   }
   count_launch();
   PSSR_CHECK_CUDA(cudaGetLastError());
@@ -422,19 +427,22 @@ __global__ void __launch_bounds__(256) dwln_kernel(pssr_dwln_desc_t d, int fp16)
   }
 }
 
-// Tiled depthwise 7x7: a CTA owns an 8x16 pixel tile x 64 channels.  The (14 x 22) halo tile and the 49x64 weights are
-// staged in shared memory; a thread computes 4 consecutive pixels of one row for 8 channels, so one filter row costs
-// 10 input + 14 weight 16-byte shared loads for 224 FMAs.  Output: pre-LayerNorm values, 16-bit NHWC.
+// Tiled depthwise 7x7: a CTA of 512 threads owns an 8x16 pixel tile x 64 channels.  The (14 x 22) halo tile is converted to fp32
+// ONCE while it is staged in shared memory ([pixel][64 channels], 256 B per pixel; LO: hi + lo summed there, exact in fp32), so the
+// FMA loop has no conversions: a thread computes 4 consecutive pixels of one row for 4 channels and one filter row costs 10 input
+// + 7 weight 16-byte shared loads for 112 FMAs (87 % of the issued instructions are FMAs; the 16-bit tile with 8 channels per
+// thread spent 80 conversions per 224 FMAs and needed 116 registers -- 25 % occupancy, ncu: 35 % issue slots busy, latency-bound).
+// ~60 registers x 512 threads x 2 CTAs per SM.  Output: pre-LayerNorm values, 16-bit NHWC (LO: as a hi + lo pair).
 static constexpr int kDwTH = 8, kDwTW = 16, kDwC = 64;
-// LO (compensated precision): the input is a hi + lo pair (second halo tile behind the weights, summed in fp32 on use) and the
-// pre-LayerNorm result leaves as a pair too.
+static constexpr int kDwThreads = 512;
+static constexpr int kDwTileF32Bytes = (kDwTH + 6) * (kDwTW + 6) * kDwC * 4;
+static constexpr int kDwSmemF32 = kDwTileF32Bytes + (49 * kDwC + kDwC) * 4;
 template <bool LO>
-__global__ void __launch_bounds__(256) dwconv7_kernel(pssr_dwln_desc_t d, int fp16) {
+__global__ void __launch_bounds__(kDwThreads, 2) dwconv7_kernel(pssr_dwln_desc_t d, int fp16) {
   extern __shared__ __align__(16) uint8_t dw_sm[];
-  uint4* tile = reinterpret_cast<uint4*>(dw_sm);                        // [row][col][8-ch group], 16 B each
-  float* wsm = reinterpret_cast<float*>(dw_sm + (kDwTH + 6) * (kDwTW + 6) * (kDwC / 8) * 16);   // [49][64]
+  float4* tile = reinterpret_cast<float4*>(dw_sm);                      // [row][col][16 channel quads]
+  float* wsm = reinterpret_cast<float*>(dw_sm + kDwTileF32Bytes);       // [49][64]
   float* bsm = wsm + 49 * kDwC;
-  uint4* tile_lo = reinterpret_cast<uint4*>(bsm + kDwC);               // LO only
   const int tiles_x = (d.W + kDwTW - 1) / kDwTW, tiles_y = (d.H + kDwTH - 1) / kDwTH;
   int bid = blockIdx.x;
   const int tx = bid % tiles_x; bid /= tiles_x;
@@ -446,73 +454,70 @@ __global__ void __launch_bounds__(256) dwconv7_kernel(pssr_dwln_desc_t d, int fp
   const int cw = d.C - c_base < kDwC ? d.C - c_base : kDwC;   // channels in this slab (multiple of 8)
   const int x0 = tx * kDwTW, y0 = ty * kDwTH;
   const uint16_t* in = reinterpret_cast<const uint16_t*>(d.in) + d.in_choff + c_base;
-  for (int i = threadIdx.x; i < 49 * kDwC; i += 256) {
+  const uint16_t* in_lo = LO ? reinterpret_cast<const uint16_t*>(d.in_lo) + d.in_choff + c_base : nullptr;
+  for (int i = threadIdx.x; i < (kDwTH + 6) * (kDwTW + 6) * 8; i += kDwThreads) {
+    const int g = i & 7, pp = i >> 3;
+    const int yy = y0 + pp / (kDwTW + 6) - 3, xx = x0 + pp % (kDwTW + 6) - 3;
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (yy >= 0 && yy < d.H && xx >= 0 && xx < d.W && g * 8 < cw) {
+      const size_t off = (((size_t)n * d.H + yy) * d.W + xx) * d.in_cstride + g * 8;
+      unpack8(__ldg(reinterpret_cast<const uint4*>(in + off)), f, fp16);
+      if (LO) add8(f, __ldg(reinterpret_cast<const uint4*>(in_lo + off)), fp16);
+    }
+    tile[pp * 16 + g * 2] = make_float4(f[0], f[1], f[2], f[3]);
+    tile[pp * 16 + g * 2 + 1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+  for (int i = threadIdx.x; i < 49 * kDwC; i += kDwThreads) {
     const int t = i / kDwC, c = i % kDwC;
     wsm[i] = c < cw ? d.dw_w[(size_t)t * d.C + c_base + c] : 0.f;
   }
   if (threadIdx.x < kDwC) bsm[threadIdx.x] = threadIdx.x < cw ? d.dw_b[c_base + threadIdx.x] : 0.f;
-  for (int i = threadIdx.x; i < (kDwTH + 6) * (kDwTW + 6) * 8; i += 256) {
-    const int g = i & 7, pp = i >> 3;
-    const int yy = y0 + pp / (kDwTW + 6) - 3, xx = x0 + pp % (kDwTW + 6) - 3;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (yy >= 0 && yy < d.H && xx >= 0 && xx < d.W && g * 8 < cw)
-      v = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)n * d.H + yy) * d.W + xx) * d.in_cstride + g * 8));
-    tile[i] = v;
-    if (LO) {
-      uint4 vl = make_uint4(0, 0, 0, 0);
-      if (yy >= 0 && yy < d.H && xx >= 0 && xx < d.W && g * 8 < cw)
-        vl = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(d.in_lo) + d.in_choff + c_base + (((size_t)n * d.H + yy) * d.W + xx) * d.in_cstride + g * 8));
-      tile_lo[i] = vl;
-    }
-  }
   __syncthreads();
-  const int g = threadIdx.x & 7;             // channel group
-  const int xq = (threadIdx.x >> 3) & 3;     // which 4-pixel quad of the 16-wide row
-  const int row = threadIdx.x >> 5;          // 0..7
-  float acc[4][8];
+  const int q = threadIdx.x & 15;            // channel quad
+  const int xq = (threadIdx.x >> 4) & 3;     // which 4-pixel quad of the 16-wide row
+  const int row = threadIdx.x >> 6;          // 0..7
+  float acc[4][4];
+  {
+    const float4 bq = *reinterpret_cast<const float4*>(bsm + q * 4);
 #pragma unroll
-  for (int p4 = 0; p4 < 4; ++p4)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[p4][j] = bsm[g * 8 + j];
+    for (int p4 = 0; p4 < 4; ++p4) { acc[p4][0] = bq.x; acc[p4][1] = bq.y; acc[p4][2] = bq.z; acc[p4][3] = bq.w; }
+  }
+#pragma unroll 1
   for (int ky = 0; ky < 7; ++ky) {
-    float wr[7][8];
+    float4 wr[7];
 #pragma unroll
-    for (int kx = 0; kx < 7; ++kx) {
-      const float4 w0 = *reinterpret_cast<const float4*>(wsm + (ky * 7 + kx) * kDwC + g * 8);
-      const float4 w1 = *reinterpret_cast<const float4*>(wsm + (ky * 7 + kx) * kDwC + g * 8 + 4);
-      wr[kx][0] = w0.x; wr[kx][1] = w0.y; wr[kx][2] = w0.z; wr[kx][3] = w0.w; wr[kx][4] = w1.x; wr[kx][5] = w1.y; wr[kx][6] = w1.z; wr[kx][7] = w1.w;
-    }
-    const uint4* trow = tile + ((row + ky) * (kDwTW + 6) + xq * 4) * 8 + g;
+    for (int kx = 0; kx < 7; ++kx) wr[kx] = *reinterpret_cast<const float4*>(wsm + (ky * 7 + kx) * kDwC + q * 4);
+    const float4* trow = tile + ((row + ky) * (kDwTW + 6) + xq * 4) * 16 + q;
 #pragma unroll
     for (int cx = 0; cx < 10; ++cx) {        // input column (xq*4 - 3 + cx): tap (cx - p4) of output pixel p4
-      float f[8];
-      unpack8(trow[cx * 8], f, fp16);
-      if (LO) add8(f, trow[cx * 8 + (tile_lo - tile)], fp16);
+      const float4 f = trow[cx * 16];
 #pragma unroll
       for (int p4 = 0; p4 < 4; ++p4) {
         const int kx = cx - p4;
         if (kx >= 0 && kx < 7) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[p4][j] = fmaf(f[j], wr[kx][j], acc[p4][j]);
+          acc[p4][0] = fmaf(f.x, wr[kx].x, acc[p4][0]);
+          acc[p4][1] = fmaf(f.y, wr[kx].y, acc[p4][1]);
+          acc[p4][2] = fmaf(f.z, wr[kx].z, acc[p4][2]);
+          acc[p4][3] = fmaf(f.w, wr[kx].w, acc[p4][3]);
         }
       }
     }
   }
   const int y = y0 + row;
-  if (y < d.H && g * 8 < cw) {
-    uint16_t* out = reinterpret_cast<uint16_t*>(d.out) + d.out_choff + c_base + g * 8;
+  if (y < d.H && q * 4 < cw) {
+    uint16_t* out = reinterpret_cast<uint16_t*>(d.out) + d.out_choff + c_base + q * 4;
 #pragma unroll
     for (int p4 = 0; p4 < 4; ++p4) {
       const int x = x0 + xq * 4 + p4;
       if (x < d.W) {
         const size_t off = (((size_t)n * d.H + y) * d.W + x) * d.out_cstride;
+        const uint2 hi = make_uint2(pack2(acc[p4][0], acc[p4][1], fp16), pack2(acc[p4][2], acc[p4][3], fp16));
+        *reinterpret_cast<uint2*>(out + off) = hi;
         if (LO) {
-          uint4 hi, lo;
-          pack8_pair(acc[p4], fp16, hi, lo);
-          *reinterpret_cast<uint4*>(out + off) = hi;
-          *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(d.out_lo) + d.out_choff + c_base + g * 8 + off) = lo;
-        } else {
-          *reinterpret_cast<uint4*>(out + off) = pack8(acc[p4], fp16);
+          const float h0 = unpack1((uint16_t)(hi.x & 0xFFFFu), fp16), h1 = unpack1((uint16_t)(hi.x >> 16), fp16);
+          const float h2 = unpack1((uint16_t)(hi.y & 0xFFFFu), fp16), h3 = unpack1((uint16_t)(hi.y >> 16), fp16);
+          *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(d.out_lo) + d.out_choff + c_base + q * 4 + off) =
+              make_uint2(pack2(acc[p4][0] - h0, acc[p4][1] - h1, fp16), pack2(acc[p4][2] - h2, acc[p4][3] - h3, fp16));
         }
       }
     }
@@ -661,15 +666,14 @@ int dwln_launch(const pssr_dwln_desc_t& d, int dtype, cudaStream_t stream) {
   }
   const long long blocks = (long long)d.B * ((d.C + kDwC - 1) / kDwC) * ((d.H + kDwTH - 1) / kDwTH) * ((d.W + kDwTW - 1) / kDwTW);
   PSSR_REQUIRE(blocks < (1ll << 31), PSSR_EUNSUP, "dwconv: too many blocks");
-  const size_t tile_bytes = (size_t)(kDwTH + 6) * (kDwTW + 6) * (kDwC / 8) * 16;
-  const size_t smem = tile_bytes * (lo ? 2 : 1) + (49 * kDwC + kDwC) * sizeof(float);
+  const size_t smem = kDwSmemF32;
   static PerDeviceOnce attr_once;
   if (attr_once.first()) {
-    PSSR_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    PSSR_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    PSSR_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemF32));
+    PSSR_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemF32));
   }
-  if (lo) dwconv7_kernel<true><<<(unsigned)blocks, 256, smem, stream>>>(d, dtype == PSSR_DT_FP16);
-  else dwconv7_kernel<false><<<(unsigned)blocks, 256, smem, stream>>>(d, dtype == PSSR_DT_FP16);
+  if (lo) dwconv7_kernel<true><<<(unsigned)blocks, kDwThreads, smem, stream>>>(d, dtype == PSSR_DT_FP16);
+  else dwconv7_kernel<false><<<(unsigned)blocks, kDwThreads, smem, stream>>>(d, dtype == PSSR_DT_FP16);
   count_launch();
   PSSR_CHECK_CUDA(cudaGetLastError());
   pssr_ln_desc_t ln;
@@ -733,6 +737,88 @@ __global__ void __launch_bounds__(256) ese_gate_kernel(pssr_ese_desc_t d, int fp
   }
 }
 
+// Small maps (RDNet's eSE blocks sit on the 16^2 / 8^2 stages): ONE launch, one CTA of 512 threads per image.  Every thread keeps
+// its PXT 16-byte vectors of the image in registers (phase 1: per-channel sums through shared memory, fixed order), the C x C fc
+// runs as TPC = 2^k threads per output channel reading interleaved float4 columns of the weight row (coalesced, every load of the
+// phase in flight at once -- the two-kernel version walked C / 8 dependent warp-rounds), and the gated image is written straight
+// from the registers: no second pass over the image, no gate buffer.
+static constexpr int kEseT = 512;
+template <int PXT>
+__global__ void __launch_bounds__(kEseT) ese_fused_kernel(pssr_ese_desc_t d, int fp16) {
+  extern __shared__ __align__(16) float ese_sm[];          // [C] means, [C] gates, [nsets][C] partial sums
+  float* ese_mean = ese_sm;
+  float* gate = ese_sm + d.C;
+  float* part = ese_sm + 2 * d.C;
+  const int b = blockIdx.x;
+  const int HW = d.H * d.W;
+  const int groups = d.C / 8;
+  const int nsets = kEseT / groups;
+  const uint16_t* in = reinterpret_cast<const uint16_t*>(d.in) + (size_t)b * HW * d.in_cstride;
+  const int g = threadIdx.x % groups, ps = threadIdx.x / groups;
+  const bool own = ps < nsets;
+  uint4 v[PXT];
+#pragma unroll
+  for (int i = 0; i < PXT; ++i) {
+    const int p = ps + i * nsets;
+    v[i] = own && p < HW ? __ldg(reinterpret_cast<const uint4*>(in + (size_t)p * d.in_cstride + g * 8)) : make_uint4(0, 0, 0, 0);
+  }
+  if (own) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < PXT; ++i) add8(acc, v[i], fp16);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[(size_t)ps * d.C + g * 8 + j] = acc[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d.C; c += kEseT) {
+    float s = 0.f;
+    for (int k = 0; k < nsets; ++k) s += part[(size_t)k * d.C + c];
+    ese_mean[c] = s / HW;
+  }
+  __syncthreads();
+  int tpc = 1;
+  while (tpc * 2 * d.C <= kEseT && tpc < 32) tpc *= 2;
+  const int oc = threadIdx.x / tpc, ks = threadIdx.x % tpc;      // oc >= C: the thread only takes part in the shuffles
+  float a0 = 0.f, a1 = 0.f;
+  if (oc < d.C) {
+    const float4* wrow = reinterpret_cast<const float4*>(d.fc_w + (size_t)oc * d.C);
+    const float4* m4 = reinterpret_cast<const float4*>(ese_mean);
+    const int n4 = d.C / 4;
+    int j = ks;
+    for (; j + tpc < n4; j += 2 * tpc) {
+      const float4 w0 = __ldg(wrow + j), w1 = __ldg(wrow + j + tpc);
+      const float4 m0 = m4[j], m1 = m4[j + tpc];
+      a0 = fmaf(w0.x, m0.x, fmaf(w0.y, m0.y, fmaf(w0.z, m0.z, fmaf(w0.w, m0.w, a0))));
+      a1 = fmaf(w1.x, m1.x, fmaf(w1.y, m1.y, fmaf(w1.z, m1.z, fmaf(w1.w, m1.w, a1))));
+    }
+    if (j < n4) {
+      const float4 w0 = __ldg(wrow + j);
+      const float4 m0 = m4[j];
+      a0 = fmaf(w0.x, m0.x, fmaf(w0.y, m0.y, fmaf(w0.z, m0.z, fmaf(w0.w, m0.w, a0))));
+    }
+  }
+  float a = a0 + a1;
+  for (int o = tpc >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (oc < d.C && ks == 0) gate[oc] = fminf(fmaxf(a + d.fc_b[oc] + 3.f, 0.f), 6.f) / 6.f * (d.gamma != nullptr ? d.gamma[oc] : 1.f);
+  __syncthreads();
+  if (!own) return;
+  float gt[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) gt[j] = gate[g * 8 + j];
+  uint16_t* out = reinterpret_cast<uint16_t*>(d.out) + (size_t)b * HW * d.out_cstride + d.out_choff + g * 8;
+#pragma unroll
+  for (int i = 0; i < PXT; ++i) {
+    const int p = ps + i * nsets;
+    if (p < HW) {
+      float f[8];
+      unpack8(v[i], f, fp16);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] *= gt[j];
+      *reinterpret_cast<uint4*>(out + (size_t)p * d.out_cstride) = pack8(f, fp16);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) ese_apply_kernel(pssr_ese_desc_t d, int fp16) {
   const int groups = d.C / 8;
   const long long total = (long long)d.B * d.H * d.W * groups;
@@ -757,6 +843,22 @@ int ese_launch(const pssr_ese_desc_t& d, int dtype, cudaStream_t stream) {
   const int nsets = (groups > 0 && groups <= 256 && 256 % groups == 0) ? 256 / groups : 0;
   const size_t ese_smem = ((size_t)d.C + (size_t)nsets * d.C) * sizeof(float);
   PSSR_REQUIRE(d.C % 8 == 0 && ese_smem <= 48 * 1024, PSSR_EUNSUP, "ese: C=%d unsupported", d.C);
+  // small maps: the single-launch kernel (the image of a CTA fits its threads' registers)
+  if (groups <= kEseT && d.C <= kEseT && ((uintptr_t)d.fc_w & 15) == 0 && getenv("PSSR_ESE_TWOPASS") == nullptr) {
+    const int fsets = kEseT / groups;
+    const int need = (d.H * d.W + fsets - 1) / fsets;
+    const size_t sm = ((size_t)2 * d.C + (size_t)fsets * d.C) * sizeof(float);
+    if (need <= 8 && sm <= 48 * 1024) {
+      const int f16 = dtype == PSSR_DT_FP16;
+      if (need <= 1) ese_fused_kernel<1><<<d.B, kEseT, sm, stream>>>(d, f16);
+      else if (need <= 2) ese_fused_kernel<2><<<d.B, kEseT, sm, stream>>>(d, f16);
+      else if (need <= 4) ese_fused_kernel<4><<<d.B, kEseT, sm, stream>>>(d, f16);
+      else ese_fused_kernel<8><<<d.B, kEseT, sm, stream>>>(d, f16);
+      count_launch();
+      PSSR_CHECK_CUDA(cudaGetLastError());
+      return PSSR_OK;
+    }
+  }
   ese_gate_kernel<<<d.B, 256, ese_smem, stream>>>(d, dtype == PSSR_DT_FP16);
   const long long total = (long long)d.B * d.H * d.W * (d.C / 8);
   long long blocks = (total + 255) / 256;

@@ -30,5 +30,12 @@ for i, (kind, r) in enumerate(plan.records):
     rows.append((t, i, kind, extra))
 tot = sum(r[0] for r in rows)
 print(f"B={B}: sum {tot:.3f} ms")
-for t, i, kind, extra in sorted(rows, reverse=True)[:40]:
+if len(sys.argv) > 3 and sys.argv[3] == "all":
+    by = {}
+    for t, i, kind, extra in rows: by[kind] = by.get(kind, 0) + t
+    print("  per kind (ms):", {k: round(v, 3) for k, v in sorted(by.items(), key=lambda kv: -kv[1])})
+    sel = sorted(rows, key=lambda r: r[1])
+else:
+    sel = sorted(rows, reverse=True)[:40]
+for t, i, kind, extra in sel:
     print(f"  op{i:03d} {kind:8s} {t*1000:8.1f} us  {extra}")
