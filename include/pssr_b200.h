@@ -128,6 +128,13 @@ typedef struct {
 } pssr_crappify_args_t;
 
 int pssr_crappify(const pssr_crappify_args_t* args, void* stream);
+/* The tile table of a batch (a few KB: sheet pointers + the int32 columns above) reaches the device through a one-CTA kernel
+ * that reads the PINNED host buffer directly (unified addressing) instead of a cudaMemcpyAsync: a copy-engine transfer queues
+ * behind every bulk sheet upload already handed to the host->device engine (measured: the second batch of a 50-stack dataset
+ * waited 22 ms), a kernel on the compute stream does not.  `pinned_src` must be page-locked (cudaHostAlloc / cudaHostRegister)
+ * and stay valid until the stream has passed this call; `bytes` a multiple of 4.  The ingest side of
+ * pssr/data.py:471-495 (`_gen_pair` indexes host arrays; here the indices travel to the device).                              */
+int pssr_table_fetch(void* dst, const void* pinned_src, int64_t bytes, void* stream);
 /* The operator interface `Crappifier.crappify(image)` (pssr/crappifiers.py:13-24): the noise chain
  * alone on an arbitrary float32 / float64 array of n elements -- no downscale, no final round/clip.
  * Output is float64 (exactly representable when the reference would return float32). */

@@ -196,6 +196,7 @@ SYMBOLS = {
     "pssr_tiff_read": (c_int32, [c_char_p, c_void_p, c_int64]),
     "pssr_tiff_write": (c_int32, [c_char_p, c_void_p, c_int32, c_int32, c_int32, c_int32]),
     "pssr_crappify": (c_int32, [POINTER(CrappifyArgs), c_void_p]),
+    "pssr_table_fetch": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),
     "pssr_noise_chain": (c_int32, [c_void_p, c_int32, c_void_p, c_int64, POINTER(NoiseStage), c_int32, c_int32, c_uint64, c_void_p]),
     "pssr_resize_bilinear": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "pssr_plan_create": (c_int32, [POINTER(Op), c_int32, c_int32, POINTER(c_void_p)]),

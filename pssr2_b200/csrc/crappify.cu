@@ -723,6 +723,27 @@ __global__ void resize_plain_kernel(const T* src, T* dst, int n, int h, int w, i
 
 using namespace pssr;
 
+// One CTA copies the (few KB) tile table from pinned host memory, read in place over PCIe, into device memory.
+__global__ void __launch_bounds__(256) table_fetch_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, int64_t words) {
+  for (int64_t i = threadIdx.x; i < words; i += 256) dst[i] = src[i];
+}
+
+extern "C" int pssr_table_fetch(void* dst, const void* pinned_src, int64_t bytes, void* stream) {
+  PSSR_REQUIRE(dst != nullptr && pinned_src != nullptr && bytes >= 0 && bytes % 4 == 0, PSSR_EINVAL, "table_fetch: bad arguments");
+  if (bytes == 0) return PSSR_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  void* dev_view = nullptr;
+  if (cudaHostGetDevicePointer(&dev_view, const_cast<void*>(pinned_src), 0) != cudaSuccess || dev_view == nullptr) {
+    (void)cudaGetLastError();          // not mapped into the device address space: the copy engine after all
+    PSSR_CHECK_CUDA(cudaMemcpyAsync(dst, pinned_src, (size_t)bytes, cudaMemcpyHostToDevice, st));
+    return PSSR_OK;
+  }
+  table_fetch_kernel<<<1, 256, 0, st>>>(reinterpret_cast<uint32_t*>(dst), reinterpret_cast<const uint32_t*>(dev_view), bytes / 4);
+  count_launch();
+  PSSR_CHECK_CUDA(cudaGetLastError());
+  return PSSR_OK;
+}
+
 extern "C" int pssr_crappify(const pssr_crappify_args_t* a, void* stream) {
   PSSR_REQUIRE(a != nullptr, PSSR_EINVAL, "crappify: null args");
   PSSR_REQUIRE(a->elem_bytes == 1 || a->elem_bytes == 2, PSSR_EUNSUP, "crappify: elem_bytes must be 1 (uint8) or 2 (uint16)");

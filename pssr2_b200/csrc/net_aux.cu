@@ -33,9 +33,11 @@ __global__ void __launch_bounds__(kPrepThreads) prep_im2col_kernel(pssr_prep_des
 #pragma unroll
     for (int k = 0; k < 32; ++k) row[k] = rowl[k] = 0u;
     if (i < total) {
-      const int x = (int)(i % d.W);
-      const int y = (int)((i / d.W) % d.H);
-      const int n = (int)(i / ((long long)d.W * d.H));
+      // 32-bit index arithmetic (prep_launch checks the pixel count): three 64-bit divisions cost ~300 instructions per pixel
+      const uint32_t ii = (uint32_t)i, rr = ii / (uint32_t)d.W;
+      const int x = (int)(ii - rr * (uint32_t)d.W);
+      const int n = (int)(rr / (uint32_t)d.H);
+      const int y = (int)(rr - (uint32_t)n * (uint32_t)d.H);
       // channel / tap loops fully unrolled: every index into row[] is a compile-time constant, so the im2col row lives in
       // registers (a runtime index put it in local memory: 128 B of local stores + loads per pixel, 59 us for 1 M pixels)
 #pragma unroll
@@ -51,7 +53,8 @@ __global__ void __launch_bounds__(kPrepThreads) prep_im2col_kernel(pssr_prep_des
               const size_t idx = plane + (size_t)yy * d.W + xx;
               const float raw = d.x_u8 ? (float)reinterpret_cast<const uint8_t*>(d.x)[idx]
                                        : reinterpret_cast<const float*>(d.x)[idx];
-              v = __fadd_rn(__fmul_rn(__fsub_rn(__fdiv_rn(raw, 128.f), 1.f), s), t);  // no FMA contraction: same bits as the unfused ops
+              // no FMA contraction: same bits as the unfused ops (x / 128 == x * 2^-7 exactly)
+              v = __fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(raw, 0.0078125f), 1.f), s), t);
               if (tap == 4 && d.xnorm_f32 != nullptr) d.xnorm_f32[idx] = v;
             }
             const uint16_t hi16 = pack1(v, fp16);
@@ -151,6 +154,7 @@ int prep_launch(const pssr_prep_desc_t& d, int dtype, cudaStream_t stream) {
   PSSR_REQUIRE(d.x && d.im2col && d.scale && d.shift, PSSR_EINVAL, "prep: null pointer");
   PSSR_REQUIRE(d.cols == 0 || d.cols == 64 || (d.cols == 16 && d.C * 9 <= 16), PSSR_EUNSUP, "prep: im2col width %d unsupported", d.cols);
   const long long total = (long long)d.B * d.H * d.W;
+  PSSR_REQUIRE(total < (1ll << 31), PSSR_EUNSUP, "prep: more than 2^31 pixels");
   const int threads = kPrepThreads;
   long long blocks = (total + threads - 1) / threads;
   const long long cap = (long long)device_sm_count() * 32;
@@ -311,11 +315,12 @@ __global__ void maxpool2_kernel(pssr_pool_desc_t d, int fp16) {
   uint16_t* out = reinterpret_cast<uint16_t*>(d.out) + d.out_choff;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % groups);
-    long long pix = i / groups;
-    const int x = (int)(pix % Wo);
-    const int y = (int)((pix / Wo) % Ho);
-    const int n = (int)(pix / ((long long)Wo * Ho));
+    const uint32_t ii = (uint32_t)i, pix = ii / (uint32_t)groups;      // pool_launch checks total < 2^31
+    const int g = (int)(ii - pix * (uint32_t)groups);
+    const uint32_t rr = pix / (uint32_t)Wo;
+    const int x = (int)(pix - rr * (uint32_t)Wo);
+    const int n = (int)(rr / (uint32_t)Ho);
+    const int y = (int)(rr - (uint32_t)n * (uint32_t)Ho);
     const size_t p00 = (((size_t)n * d.H + 2 * y) * d.W + 2 * x) * d.in_cstride + g * 8;
     const size_t rowstride = (size_t)d.W * d.in_cstride;
     const uint4 a = __ldg(reinterpret_cast<const uint4*>(in + p00));
@@ -333,6 +338,7 @@ int pool_launch(const pssr_pool_desc_t& d, int dtype, cudaStream_t stream) {
                PSSR_EUNSUP, "pool: channel counts/strides/offsets must be multiples of 8");
   PSSR_REQUIRE(d.H % 2 == 0 && d.W % 2 == 0, PSSR_EUNSUP, "pool: odd spatial size %dx%d", d.H, d.W);
   const long long total = (long long)d.B * (d.H / 2) * (d.W / 2) * (d.C / 8);
+  PSSR_REQUIRE(total < (1ll << 31), PSSR_EUNSUP, "pool: more than 2^31 output vectors");
   const int threads = 256;
   long long blocks = (total + threads - 1) / threads;
   const long long cap = (long long)device_sm_count() * 16;

@@ -148,7 +148,7 @@ class _DeviceDataset(Dataset):
     group and with everything fitting the budget the whole dataset is uploaded at construction (``preload=True``)."""
 
     max_resident_bytes = None      # None: keep every sheet that was uploaded
-    preload_bytes = 64 << 20       # sheets uploaded at construction (always the first one); later ones are prefetched per batch
+    preload_bytes = None           # cap on what `preload` uploads at construction (None: everything; the first sheet always)
 
     def _upload(self, arrays, device, preload=True):
         dtypes = {str(a.dtype).replace("torch.", "").replace("int16", "uint16").replace("uuint16", "uint16") for a in arrays}
@@ -167,14 +167,15 @@ class _DeviceDataset(Dataset):
         self._frames_total = [a.shape[0] for a in arrays]
         self._shapes = [tuple(a.shape[1:]) for a in arrays]          # per image (heights / widths may differ)
         from . import dist as D
-        # preload: the leading sheets go up now, up to `preload_bytes`; the rest follow ONE sheet ahead of the batches.  Queuing
-        # every upload at construction would put tens of ms of bulk copies on the host->device copy engine in front of the first
-        # batches' (tiny) tile-table copies: measured, the second batch of a 50-stack dataset waited 22 ms for the last stack.
+        # preload: every upload is queued now, back to back on the side stream (`preload_bytes` bounds it; the rest then follow
+        # ahead of the batches).  The bulk copies own the host->device copy engine for a while, which is why a batch's tile table
+        # does NOT travel by cudaMemcpyAsync (ops.TileTable / pssr_table_fetch): measured, the second batch of a 50-stack dataset
+        # otherwise waits 22 ms behind the last stack.
         if preload and not D.is_dist():
             total = 0
             for i in range(len(arrays)):
                 total += self._sheet_bytes(i)
-                if i > 0 and total > self.preload_bytes:
+                if i > 0 and self.preload_bytes is not None and total > self.preload_bytes:
                     break
                 self._ensure(i)
 
@@ -238,18 +239,19 @@ class _DeviceDataset(Dataset):
         return ids
 
     def _prefetch_after(self, ids):
-        """Starts the upload of the sheet after the last one of `ids` (called AFTER the batch's tile table has been queued for its
-        own host->device copy, so that the table never waits behind a bulk upload on the copy engine)."""
-        nxt = ids[-1] + 1
+        """Starts the upload of the sheets the NEXT batch will touch: as many as this batch used, following its last one (a batch
+        of an ImageDataset spans one stack per item).  Called after the batch's tile table has been queued."""
         keep = set(ids)
-        if nxt < len(self._sheets) and (self.max_resident_bytes is None or
-                                         sum(self._sheet_bytes(i) for i in keep | {nxt}) <= self.max_resident_bytes):
+        for nxt in range(ids[-1] + 1, min(ids[-1] + 1 + len(ids), len(self._sheets))):
+            if self.max_resident_bytes is not None and sum(self._sheet_bytes(i) for i in keep | {nxt}) > self.max_resident_bytes:
+                break
             src = self._sources[nxt]
             if not hasattr(src, "read_pinned") or src.ready():
                 self._ensure(nxt)            # upload ahead (a file source only once its decode has finished: never block here)
                 keep.add(nxt)
             else:
                 src.prefetch()
+                break
         self._evict(keep)
 
     def sheet_item_counts(self):

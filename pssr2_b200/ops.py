@@ -3,6 +3,7 @@
 """
 import ctypes
 import math
+import threading
 
 import numpy as np
 import torch
@@ -22,6 +23,34 @@ class NoiseSpec:
 
     def __init__(self, kind, intensity=0.0, gain=0.0, mix_in_f32=True, injected=None):
         self.kind, self.intensity, self.gain, self.mix_in_f32, self.injected = kind, float(intensity), float(gain), mix_in_f32, injected
+
+
+class _TableStaging:
+    """Pinned staging buffers of the tile tables.  The table reaches the device through a kernel that reads the pinned buffer in
+    place (``pssr_table_fetch``), which torch's pinned-memory allocator knows nothing about: a buffer is handed out again only
+    after the event recorded behind its fetch kernel has completed."""
+
+    def __init__(self):
+        self._idle = {}                  # device -> [(pinned uint8 tensor, event recorded after its last fetch)]
+        self._lock = threading.Lock()
+
+    def take(self, nbytes, dev):
+        with self._lock:
+            pool = self._idle.setdefault(dev, [])
+            for k, (buf, ev) in enumerate(pool):
+                if buf.numel() >= nbytes and ev.query():
+                    pool.pop(k)
+                    return buf
+        return torch.empty(max(int(nbytes), 4096), dtype=torch.uint8, pin_memory=True)
+
+    def give_back(self, buf, dev):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        with self._lock:
+            self._idle.setdefault(dev, []).append((buf, ev))
+
+
+_table_staging = _TableStaging()
 
 
 class TileTable:
@@ -54,17 +83,22 @@ class TileTable:
         self.frames_of_tile = np.asarray([int(self.sheets[k].shape[0]) for k in local], dtype=np.int64)   # host copy: frame-range checks
         self.tile_frame_host = np.asarray(tile_frame, dtype=np.int64)
         # packed header: [ns] int64 pointers | [2*ns] int32 sheet dims | [7*n] int32 columns (the seventh: augmentation codes)
-        host = torch.empty(8 * ns + 4 * (2 * ns + 7 * n), dtype=torch.uint8, pin_memory=True)
-        hv = host.numpy()
+        nbytes = 8 * ns + 4 * (2 * ns + 7 * n)
+        host = _table_staging.take(nbytes, dev)
+        hv = host.numpy()[:nbytes]
         hv[:8 * ns].view(np.int64)[:] = [s.data_ptr() for s in self.sheets]
         i32 = hv[8 * ns:].view(np.int32)
         i32[:ns] = [int(s.shape[1]) for s in self.sheets]
         i32[ns:2 * ns] = [int(s.shape[2]) for s in self.sheets]
         xf = np.zeros(n, dtype=np.int32) if tile_xf is None else np.asarray(tile_xf, dtype=np.int32)
         i32[2 * ns:] = np.asarray([local, tile_frame, tile_y, tile_x, tile_vh, tile_vw, xf], dtype=np.int32).reshape(-1)
+        # a one-CTA kernel reads the pinned buffer in place (pssr_table_fetch): a copy-engine transfer would queue behind the bulk
+        # sheet uploads already handed to the host->device engine
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         with _lib.on_device(dev):
-            packed = host.to(dev, non_blocking=True)
-        self._packed, self._host = packed, host            # the pinned source must outlive the asynchronous copy
+            _lib.check(_lib.lib().pssr_table_fetch(packed.data_ptr(), host.data_ptr(), nbytes, _lib.current_stream_ptr(dev)))
+            _table_staging.give_back(host, dev)            # reusable once the stream has passed the fetch kernel
+        self._packed = packed
         self.ptrs = packed[:8 * ns].view(torch.int64)
         d32 = packed[8 * ns:].view(torch.int32)
         # sheets of different sizes: per-sheet dimension arrays travel with the table
