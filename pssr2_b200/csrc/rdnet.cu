@@ -455,23 +455,53 @@ __global__ void __launch_bounds__(kDwThreads, 2) dwconv7_kernel(pssr_dwln_desc_t
   const int x0 = tx * kDwTW, y0 = ty * kDwTH;
   const uint16_t* in = reinterpret_cast<const uint16_t*>(d.in) + d.in_choff + c_base;
   const uint16_t* in_lo = LO ? reinterpret_cast<const uint16_t*>(d.in_lo) + d.in_choff + c_base : nullptr;
-  for (int i = threadIdx.x; i < (kDwTH + 6) * (kDwTW + 6) * 8; i += kDwThreads) {
+  // staging: every global load of the thread (halo vectors, filter taps) is issued before the first conversion, so the CTA pays
+  // one memory latency instead of one per loop iteration (ncu: long-scoreboard stalls led the first version)
+  constexpr int kItems = (kDwTH + 6) * (kDwTW + 6) * 8, kIter = (kItems + kDwThreads - 1) / kDwThreads;
+  constexpr int kWIter = (49 * kDwC + kDwThreads - 1) / kDwThreads;
+  uint4 vh[kIter], vl[kIter];
+  float wv[kWIter];
+#pragma unroll
+  for (int it = 0; it < kIter; ++it) {
+    const int i = threadIdx.x + it * kDwThreads;
     const int g = i & 7, pp = i >> 3;
     const int yy = y0 + pp / (kDwTW + 6) - 3, xx = x0 + pp % (kDwTW + 6) - 3;
-    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (yy >= 0 && yy < d.H && xx >= 0 && xx < d.W && g * 8 < cw) {
+    vh[it] = make_uint4(0, 0, 0, 0);
+    if (LO) vl[it] = make_uint4(0, 0, 0, 0);
+    if (i < kItems && yy >= 0 && yy < d.H && xx >= 0 && xx < d.W && g * 8 < cw) {
       const size_t off = (((size_t)n * d.H + yy) * d.W + xx) * d.in_cstride + g * 8;
-      unpack8(__ldg(reinterpret_cast<const uint4*>(in + off)), f, fp16);
-      if (LO) add8(f, __ldg(reinterpret_cast<const uint4*>(in_lo + off)), fp16);
+      vh[it] = __ldg(reinterpret_cast<const uint4*>(in + off));
+      if (LO) vl[it] = __ldg(reinterpret_cast<const uint4*>(in_lo + off));
     }
-    tile[pp * 16 + g * 2] = make_float4(f[0], f[1], f[2], f[3]);
-    tile[pp * 16 + g * 2 + 1] = make_float4(f[4], f[5], f[6], f[7]);
   }
-  for (int i = threadIdx.x; i < 49 * kDwC; i += kDwThreads) {
+#pragma unroll
+  for (int k = 0; k < kWIter; ++k) {
+    const int i = threadIdx.x + k * kDwThreads;
     const int t = i / kDwC, c = i % kDwC;
-    wsm[i] = c < cw ? d.dw_w[(size_t)t * d.C + c_base + c] : 0.f;
+    wv[k] = (i < 49 * kDwC && c < cw) ? __ldg(d.dw_w + (size_t)t * d.C + c_base + c) : 0.f;
   }
   if (threadIdx.x < kDwC) bsm[threadIdx.x] = threadIdx.x < cw ? d.dw_b[c_base + threadIdx.x] : 0.f;
+#pragma unroll
+  for (int it = 0; it < kIter; ++it) {
+    const int i = threadIdx.x + it * kDwThreads;
+    if (i < kItems) {
+      const int g = i & 7, pp = i >> 3;
+      float f[8];
+      unpack8(vh[it], f, fp16);
+      if (LO) add8(f, vl[it], fp16);
+      // the two 16-byte halves of the group go out in swapped order for g >= 4: the eight threads of a quarter-warp then hit
+      // eight different 16-byte bank groups in each store (ncu: 3.7-way conflicts with the straight order)
+      const int sw = (g >> 2) & 1;
+      const float4 a = make_float4(f[0], f[1], f[2], f[3]), b = make_float4(f[4], f[5], f[6], f[7]);
+      tile[pp * 16 + g * 2 + sw] = sw ? b : a;
+      tile[pp * 16 + g * 2 + 1 - sw] = sw ? a : b;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kWIter; ++k) {
+    const int i = threadIdx.x + k * kDwThreads;
+    if (i < 49 * kDwC) wsm[i] = wv[k];
+  }
   __syncthreads();
   const int q = threadIdx.x & 15;            // channel quad
   const int xq = (threadIdx.x >> 4) & 3;     // which 4-pixel quad of the 16-wide row
