@@ -1700,6 +1700,13 @@ static int v3_prepare_impl(const pssr_conv_desc_t& d, int dtype, ConvOp& op, boo
   if (T > 2) T = 2;
   if (tail) T = 1;
   if (p.rows_mode && d.Ho % T != 0) T = 1;
+  // small maps: with two tiles per CTA a layer of few pixels occupies a fraction of the machine (the 16^2 project convolutions of
+  // RDNet, 12800 pixels: 25 CTA pairs of 74) -- one tile per CTA doubles the CTAs at work
+  if (T == 2 && !p.rows_mode && getenv("PSSR_V3_T2_ALWAYS") == nullptr) {
+    const long long px = (long long)d.B * d.Ho * d.Wo;
+    const long long units2 = ((px + 256 * C - 1) / (256 * C)) * ((d.n + block_n - 1) / block_n);
+    if (units2 < sms / C) T = 1;
+  }
   const char* envT = getenv("PSSR_V3_T");
   if (envT && atoi(envT) == 1) T = 1;
   const bool tail_comp = tail && (d.tail_flags & PSSR_TAIL_COMP) != 0 && getenv("PSSR_V3_NO_TAIL_COMP") == nullptr;
