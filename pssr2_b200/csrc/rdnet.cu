@@ -354,6 +354,8 @@ int ln_launch(const pssr_ln_desc_t& d, int dtype, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------- dwln
+// (developer builds only, -DPSSR_DEV_KERNELS: the warp-per-pixel fused depthwise + LayerNorm kernel that measured slower)
+#ifdef PSSR_DEV_KERNELS
 // One warp produces TWO horizontally adjacent pixels: the 8 input columns x-3..x+4 of a filter row are loaded once and
 // feed both outputs, and each weight vector is loaded once per pair.
 __global__ void __launch_bounds__(256) dwln_kernel(pssr_dwln_desc_t d, int fp16) {
@@ -426,6 +428,7 @@ __global__ void __launch_bounds__(256) dwln_kernel(pssr_dwln_desc_t d, int fp16)
     }
   }
 }
+#endif  // PSSR_DEV_KERNELS
 
 // Tiled depthwise 7x7: a CTA of 512 threads owns an 8x16 pixel tile x 64 channels.  The (14 x 22) halo tile is converted to fp32
 // ONCE while it is staged in shared memory ([pixel][64 channels], 256 B per pixel; LO: hi + lo summed there, exact in fp32), so the
@@ -666,6 +669,7 @@ int dwln_launch(const pssr_dwln_desc_t& d, int dtype, cudaStream_t stream) {
   PSSR_REQUIRE(d.C % 8 == 0 && d.C <= 256 * kMaxGroupsPerLane, PSSR_EUNSUP, "dwconv: C=%d unsupported", d.C);
   PSSR_REQUIRE(d.in_cstride % 8 == 0 && d.in_choff % 8 == 0 && d.out_cstride % 8 == 0 && d.out_choff % 8 == 0, PSSR_EUNSUP, "dwconv: alignment");
   PSSR_REQUIRE(((uintptr_t)d.dw_w & 15) == 0 && ((uintptr_t)d.dw_b & 15) == 0, PSSR_EINVAL, "dwconv: weights misaligned");
+#ifdef PSSR_DEV_KERNELS
   if (getenv("PSSR_DWLN_FUSED") != nullptr) {      // single fused kernel (one warp per pixel pair), kept for comparison
     const long long total = (long long)d.B * d.H * ((d.W + 1) / 2);
     long long blocks = (total + 7) / 8;
@@ -676,6 +680,7 @@ int dwln_launch(const pssr_dwln_desc_t& d, int dtype, cudaStream_t stream) {
     PSSR_CHECK_CUDA(cudaGetLastError());
     return PSSR_OK;
   }
+#endif
   const long long sp_tiles = (long long)d.B * ((d.H + kDwTH - 1) / kDwTH) * ((d.W + kDwTW - 1) / kDwTW);
   const int slabs_all = (d.C + kDwC - 1) / kDwC;
   // enough spatial tiles to fill the machine twice over and at least two slabs to pipeline: the slab-walking kernel
