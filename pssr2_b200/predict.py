@@ -385,8 +385,8 @@ def predict_sheets(model: nn.Module, dataset, device: str = "cuda", batch_size: 
 
     ``overlap`` / ``margin``: as in ``reassemble_sheets`` with ``lr_scale=1`` on the predicted tiles, in pixels of the
     PREDICTION (default overlap: the dataset's own tile overlap, scaled in LR mode).  Returns the list of stitched sheets
-    ``uint8 [stacks, rows*step+overlap, cols*step+overlap]`` in sheet order (rank 0: all sheets; other ranks: their own, None
-    elsewhere) or writes ``{out_dir}/{prefix_}{sheet}.tif``."""
+    ``uint8 [stacks, rows*step+overlap, cols*step+overlap]`` in sheet order (rank 0: all sheets; other ranks: a list of None,
+    their sheets travel to rank 0) or writes ``{out_dir}/{prefix_}{sheet}.tif`` (rank 0)."""
     if not hasattr(dataset, "tiles") or not hasattr(dataset, "_tiles_y"):
         raise TypeError("predict_sheets needs a SlidingDataset (tiled sheets)")
     if not str(device).startswith("cuda"):
@@ -415,6 +415,15 @@ def predict_sheets(model: nn.Module, dataset, device: str = "cuda", batch_size: 
     val_idx = list(dataset.val_idx)
     down = torch.cuda.Stream(device=dev)
     local, shapes, hosts = {}, [None] * len(runs), {}
+    # every rank knows every sheet's stitched shape (rank 0 posts the receives of a round before the senders are done)
+    for g in range(len(runs)):
+        img = runs[g][0]
+        ty = dataset._tiles_y[img]
+        tx = dataset.tiles[img] // ty
+        T = dataset.crop_res * (1 if not dataset.is_lr else max(1, getattr(model, "scale", 1)))
+        ovg = (dataset.hr_res - dataset.stride) * (T // dataset.crop_res) if overlap is None else overlap
+        shapes[g] = (dataset.slices[img], tx * (T - ovg) + ovg, ty * (T - ovg) + ovg)
+    gather = D.SheetGather(owners, shapes, dev)
     pos = lo
     with torch.no_grad(), torch.cuda.device(dev):
         cur = torch.cuda.current_stream(dev)
@@ -455,19 +464,20 @@ def predict_sheets(model: nn.Module, dataset, device: str = "cuda", batch_size: 
                         host.copy_(sheet, non_blocking=True)
                     sheet.record_stream(down)
                     hosts[g] = host
-            # every rank knows every sheet's stitched shape (needed to post the receives)
-            T = dataset.crop_res * (1 if not dataset.is_lr else max(1, getattr(model, "scale", 1)))
-            ovg = (dataset.hr_res - dataset.stride) * (T // dataset.crop_res) if overlap is None else overlap
-            shapes[g] = (n_sl, tx * (T - ovg) + ovg, ty * (T - ovg) + ovg)
-    gathered = D.gather_sheets(local, owners, shapes, dev) if D.is_dist() and w > 1 else None
+                # round j of the sheet gather: this rank's j-th sheet travels to rank 0 (NVLink -> rank 0's pinned host memory)
+                # beside the kernels of its next sheet (a pageable `.cpu()` per gathered sheet after the last forward cost rank 0
+                # 90 ms at 8 GPUs x 2 sheets, for 41 ms of forward time)
+                gather.post(g - g0, local)
+        for j in range(g1 - g0, gather.n_rounds):      # ranks with fewer sheets: the later rounds only concern rank 0's receives
+            gather.post(j, local)
+    hosts.update(gather.finish())
     down.synchronize()
     out = []
     for g in range(len(runs)):
         if g in hosts:
             out.append(hosts[g].numpy())
-        elif gathered is not None and gathered[g] is not None:
-            out.append(gathered[g].cpu().numpy())
-        else:
+        else:                                       # ranks > 0: their sheets have left for rank 0 (a pageable read-back of a
+                                                    # 3968^2 sheet costs 7 ms -- a third of its forward time -- for a copy nobody uses)
             out.append(None)
     if out_dir:
         from .io import write_tiff
