@@ -162,7 +162,9 @@ __global__ void __launch_bounds__(256) stem4_kernel(pssr_stem_desc_t d, int fp16
     for (int px = 0; px < PX; ++px) {
       long long pix = p0 + px * PPW + sub;
       if (pix >= total) pix = total - 1;
-      const int x = (int)(pix % Wo), y = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
+      // 32-bit index arithmetic (stem_launch checks the pixel count)
+      const uint32_t pi = (uint32_t)pix, rr = pi / (uint32_t)Wo;
+      const int x = (int)(pi - rr * (uint32_t)Wo), n = (int)(rr / (uint32_t)Ho), y = (int)(rr - (uint32_t)n * (uint32_t)Ho);
       const size_t idx = ((size_t)n * d.H + 2 * y) * d.W + 2 * x;
       if (d.x_u8) {
         const uint8_t* xp = reinterpret_cast<const uint8_t*>(d.x) + idx;
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(256) stem4_kernel(pssr_stem_desc_t d, int fp16
       for (int j = 0; j < 8; ++j) v[j] = bs[j];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float a = __fadd_rn(__fmul_rn(__fsub_rn(__fdiv_rn(raw[px][k], 128.f), 1.f), sc), sh);
+        const float a = __fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(raw[px][k], 0.0078125f), 1.f), sc), sh);     // x / 128 == x * 2^-7 exactly
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = fmaf(a, w[k][j], v[j]);
       }
@@ -219,6 +221,7 @@ int stem_launch(const pssr_stem_desc_t& d, int dtype, cudaStream_t stream) {
   PSSR_REQUIRE(d.patch >= 1 && d.H % d.patch == 0 && d.W % d.patch == 0, PSSR_EUNSUP, "stem: size not divisible by the patch");
   PSSR_REQUIRE(d.out_cstride % 8 == 0 && d.out_choff % 8 == 0, PSSR_EUNSUP, "stem: output alignment");
   const long long total = (long long)d.B * (d.H / d.patch) * (d.W / d.patch);
+  PSSR_REQUIRE(total < (1ll << 31), PSSR_EUNSUP, "stem: more than 2^31 output pixels");
   long long blocks = (total + 7) / 8;
   const long long cap = (long long)device_sm_count() * 16;
   if (blocks > cap) blocks = cap;
