@@ -433,18 +433,20 @@ __global__ void __launch_bounds__(256) dwln_kernel(pssr_dwln_desc_t d, int fp16)
 }
 #endif  // PSSR_DEV_KERNELS
 
-// Tiled depthwise 7x7: a CTA of 512 threads owns an 8x16 pixel tile x 64 channels.  The (14 x 22) halo tile is converted to fp32
+// Tiled depthwise 7x7: a CTA owns an 8x16 pixel tile x 64 channels.  The (14 x 22) halo tile is converted to fp32
 // ONCE while it is staged in shared memory ([pixel][64 channels], 256 B per pixel; LO: hi + lo summed there, exact in fp32), so the
-// FMA loop has no conversions: a thread computes 4 consecutive pixels of one row for 4 channels and one filter row costs 10 input
-// + 7 weight 16-byte shared loads for 112 FMAs (87 % of the issued instructions are FMAs; the 16-bit tile with 8 channels per
-// thread spent 80 conversions per 224 FMAs and needed 116 registers -- 25 % occupancy, ncu: 35 % issue slots busy, latency-bound).
-// ~60 registers x 512 threads x 2 CTAs per SM.  Output: pre-LayerNorm values, 16-bit NHWC (LO: as a hi + lo pair).
+// FMA loop has no conversions: a thread computes NPX = 8 consecutive pixels of one row for 4 channels and one filter row costs 14
+// input + 7 weight 16-byte shared loads for 224 FMAs (91 % of the issued instructions are FMAs; the first version -- a 16-bit tile,
+// 8 channels x 4 pixels per thread -- spent 80 conversions per 224 FMAs and sat at 35 % issue slots busy, latency-bound).
+// 256 threads x 2 CTAs per SM.  Output: pre-LayerNorm values, 16-bit NHWC (LO: as a hi + lo pair).
 static constexpr int kDwTH = 8, kDwTW = 16, kDwC = 64;
-static constexpr int kDwThreads = 512;
+// NPX = pixels of a row per thread (2048 / NPX threads)
 static constexpr int kDwTileF32Bytes = (kDwTH + 6) * (kDwTW + 6) * kDwC * 4;
 static constexpr int kDwSmemF32 = kDwTileF32Bytes + (49 * kDwC + kDwC) * 4;
-template <bool LO>
-__global__ void __launch_bounds__(kDwThreads, 2) dwconv7_kernel(pssr_dwln_desc_t d, int fp16) {
+template <bool LO, int NPX>
+__global__ void __launch_bounds__(2048 / NPX, 2) dwconv7_kernel(pssr_dwln_desc_t d, int fp16) {
+  constexpr int kDwThreads = 2048 / NPX;
+  constexpr int XQ = kDwTW / NPX;              // threads along a 16-pixel row
   extern __shared__ __align__(16) uint8_t dw_sm[];
   float4* tile = reinterpret_cast<float4*>(dw_sm);                      // [row][col][16 channel quads]
   float* wsm = reinterpret_cast<float*>(dw_sm + kDwTileF32Bytes);       // [49][64]
@@ -510,25 +512,25 @@ __global__ void __launch_bounds__(kDwThreads, 2) dwconv7_kernel(pssr_dwln_desc_t
   }
   __syncthreads();
   const int q = threadIdx.x & 15;            // channel quad
-  const int xq = (threadIdx.x >> 4) & 3;     // which 4-pixel quad of the 16-wide row
-  const int row = threadIdx.x >> 6;          // 0..7
-  float acc[4][4];
+  const int xq = (threadIdx.x >> 4) & (XQ - 1);     // which NPX-pixel run of the 16-wide row
+  const int row = threadIdx.x / (16 * XQ);          // 0..7
+  float acc[NPX][4];
   {
     const float4 bq = *reinterpret_cast<const float4*>(bsm + q * 4);
 #pragma unroll
-    for (int p4 = 0; p4 < 4; ++p4) { acc[p4][0] = bq.x; acc[p4][1] = bq.y; acc[p4][2] = bq.z; acc[p4][3] = bq.w; }
+    for (int p4 = 0; p4 < NPX; ++p4) { acc[p4][0] = bq.x; acc[p4][1] = bq.y; acc[p4][2] = bq.z; acc[p4][3] = bq.w; }
   }
 #pragma unroll 1
   for (int ky = 0; ky < 7; ++ky) {
     float4 wr[7];
 #pragma unroll
     for (int kx = 0; kx < 7; ++kx) wr[kx] = *reinterpret_cast<const float4*>(wsm + (ky * 7 + kx) * kDwC + q * 4);
-    const float4* trow = tile + ((row + ky) * (kDwTW + 6) + xq * 4) * 16 + q;
+    const float4* trow = tile + ((row + ky) * (kDwTW + 6) + xq * NPX) * 16 + q;
 #pragma unroll
-    for (int cx = 0; cx < 10; ++cx) {        // input column (xq*4 - 3 + cx): tap (cx - p4) of output pixel p4
+    for (int cx = 0; cx < NPX + 6; ++cx) {   // input column (xq*NPX - 3 + cx): tap (cx - p4) of output pixel p4
       const float4 f = trow[cx * 16];
 #pragma unroll
-      for (int p4 = 0; p4 < 4; ++p4) {
+      for (int p4 = 0; p4 < NPX; ++p4) {
         const int kx = cx - p4;
         if (kx >= 0 && kx < 7) {
           acc[p4][0] = fmaf(f.x, wr[kx].x, acc[p4][0]);
@@ -543,8 +545,8 @@ __global__ void __launch_bounds__(kDwThreads, 2) dwconv7_kernel(pssr_dwln_desc_t
   if (y < d.H && q * 4 < cw) {
     uint16_t* out = reinterpret_cast<uint16_t*>(d.out) + d.out_choff + c_base + q * 4;
 #pragma unroll
-    for (int p4 = 0; p4 < 4; ++p4) {
-      const int x = x0 + xq * 4 + p4;
+    for (int p4 = 0; p4 < NPX; ++p4) {
+      const int x = x0 + xq * NPX + p4;
       if (x < d.W) {
         const size_t off = (((size_t)n * d.H + y) * d.W + x) * d.out_cstride;
         const uint2 hi = make_uint2(pack2(acc[p4][0], acc[p4][1], fp16), pack2(acc[p4][2], acc[p4][3], fp16));
@@ -707,11 +709,14 @@ int dwln_launch(const pssr_dwln_desc_t& d, int dtype, cudaStream_t stream) {
   const size_t smem = kDwSmemF32;
   static PerDeviceOnce attr_once;
   if (attr_once.first()) {
-    PSSR_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemF32));
-    PSSR_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemF32));
+    PSSR_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemF32));
+    PSSR_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemF32));
   }
-  if (lo) dwconv7_kernel<true><<<(unsigned)blocks, kDwThreads, smem, stream>>>(d, dtype == PSSR_DT_FP16);
-  else dwconv7_kernel<false><<<(unsigned)blocks, kDwThreads, smem, stream>>>(d, dtype == PSSR_DT_FP16);
+  // 8 pixels per thread (256 threads): measured against 4 pixels x 512 threads on the RDResUNet plan, depthwise + LayerNorm ops
+  // 1.88 -> 1.71 ms (the 4-pixel kernel stalled on shared-memory issue: MIO throttle + short scoreboard led its ncu stall list)
+  const int f16 = dtype == PSSR_DT_FP16;
+  if (lo) dwconv7_kernel<true, 8><<<(unsigned)blocks, 256, smem, stream>>>(d, f16);
+  else dwconv7_kernel<false, 8><<<(unsigned)blocks, 256, smem, stream>>>(d, f16);
   count_launch();
   PSSR_CHECK_CUDA(cudaGetLastError());
   pssr_ln_desc_t ln;
