@@ -149,6 +149,7 @@ class _DeviceDataset(Dataset):
 
     max_resident_bytes = None      # None: keep every sheet that was uploaded
     preload_bytes = None           # cap on what `preload` uploads at construction (None: everything; the first sheet always)
+    auto_resident_frac = 0.5       # a dataset larger than this share of the free HBM gets `max_resident_bytes` set to it
 
     def _upload(self, arrays, device, preload=True):
         dtypes = {str(a.dtype).replace("torch.", "").replace("int16", "uint16").replace("uuint16", "uint16") for a in arrays}
@@ -166,6 +167,13 @@ class _DeviceDataset(Dataset):
         self._upload_stream = torch.cuda.Stream(device=self.device)
         self._frames_total = [a.shape[0] for a in arrays]
         self._shapes = [tuple(a.shape[1:]) for a in arrays]          # per image (heights / widths may differ)
+        # a dataset that does not fit beside the activations streams through on its own: without an explicit budget, more than
+        # `auto_resident_frac` of the free HBM switches the least-recently-used eviction on (pssr/data.py:553-564 `preload=False`)
+        total_bytes = sum(self._sheet_bytes(i) for i in range(len(arrays)))
+        if self.max_resident_bytes is None and total_bytes > 0:
+            free = torch.cuda.mem_get_info(self.device)[0]
+            if total_bytes > self.auto_resident_frac * free:
+                self.max_resident_bytes = int(self.auto_resident_frac * free)
         from . import dist as D
         # preload: every upload is queued now, back to back on the side stream (`preload_bytes` bounds it; the rest then follow
         # ahead of the batches).  The bulk copies own the host->device copy engine for a while, which is why a batch's tile table
@@ -175,7 +183,8 @@ class _DeviceDataset(Dataset):
             total = 0
             for i in range(len(arrays)):
                 total += self._sheet_bytes(i)
-                if i > 0 and self.preload_bytes is not None and total > self.preload_bytes:
+                if i > 0 and ((self.preload_bytes is not None and total > self.preload_bytes) or
+                              (self.max_resident_bytes is not None and total > self.max_resident_bytes)):
                     break
                 self._ensure(i)
 

@@ -75,6 +75,16 @@ def test_file_backed_dataset_streams_like_memory(tmp_path):
     got = predict_images(model, ds, device="cuda", batch_size=4, out_dir=None)
     assert sorted(got) == sorted(want) and all(np.array_equal(got[k], want[k]) for k in want)
     assert sum(s is not None for s in ds._sheets) <= 2
+    # no explicit budget: a dataset larger than half of the free HBM gets one by itself (here: "free" memory of 2.5 sheets)
+    real = torch.cuda.mem_get_info
+    try:
+        torch.cuda.mem_get_info = lambda *a, **k: (int(2.5 * sheets["sheet0"].nbytes), real()[1])
+        ds_auto = SlidingDataset(sheets, **kw)
+    finally:
+        torch.cuda.mem_get_info = real
+    assert ds_auto.max_resident_bytes == int(0.5 * int(2.5 * sheets["sheet0"].nbytes)) and sum(s is not None for s in ds_auto._sheets) == 1
+    got = predict_images(model, ds_auto, device="cuda", batch_size=4, out_dir=None)
+    assert all(np.array_equal(got[k], want[k]) for k in want) and sum(s is not None for s in ds_auto._sheets) <= 2
     out = tmp_path / "preds"
     assert predict_images(model, SlidingDataset(str(src), extension="tif", **kw), device="cuda", batch_size=3, out_dir=str(out), prefix="p") is None
     files = sorted(os.listdir(out))
