@@ -60,14 +60,14 @@ def _peak_sustained(burst_tf):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum summed over the conv launches of ONE step, from the ncu capture named below
-CONV_DRAM_BYTES = {"fp16c": 4775142400, "fp16": 3876322304, "bf16": 3876322304}
-CONV_DRAM_SOURCE = {"fp16c": "profiles/r02_launches_step_summary.txt (ncu launch list of `bench.py --kernels-only --no-sub`, 38 conv launches of one "
-                             "step of the compensated plan: 3467.1 MB read + 1308.0 MB written)",
+CONV_DRAM_BYTES = {"fp16c": 4763400000, "fp16": 3876322304, "bf16": 3876322304}
+CONV_DRAM_SOURCE = {"fp16c": "profiles/r02_final_launches_step_summary.txt (ncu launch list of `bench.py --kernels-only --no-sub`, 38 conv launches of "
+                             "one step of the compensated plan: 3467.1 MB read + 1296.3 MB written)",
                     "fp16": "profiles/r01_launches_v3_summary.txt (37 conv launches of one step of the single-pass plan: 2823.8 MB read + 1052.6 MB written)"}
 CONV_DRAM_SOURCE["bf16"] = CONV_DRAM_SOURCE["fp16"]
 RECON_FLOPS_PER_TILE = 19.629e9
-RECON_DRAM_BYTES = {"fp16c": 446763776, "fp16": 325600000, "bf16": 325600000}
-RECON_DRAM_SOURCE = {"fp16c": "profiles/r02_v3_recon_pre.details.txt (ncu --set full: 280.2 MB read + 166.5 MB written)",
+RECON_DRAM_BYTES = {"fp16c": 449149184, "fp16": 325600000, "bf16": 325600000}
+RECON_DRAM_SOURCE = {"fp16c": "profiles/r02_final_v3_recon_pre.details.txt (ncu --set full: 280.2 MB read + 168.9 MB written)",
                      "fp16": "profiles/r01_launches_v3_summary.txt launch #42 (175.1 MB read + 150.5 MB written)"}
 RECON_DRAM_SOURCE["bf16"] = RECON_DRAM_SOURCE["fp16"]
 
