@@ -170,3 +170,37 @@ def test_swinir_plan_matches_reference_golden_on_cpu(dry_run):
         assert err < 8e-2, (tag, err)       # single-pass fp16 over 0..255-scale features (conv_first output is not normalised)
         c = st["out"].shape[1] // 2
         assert torch.equal(st["out_u8"], st["out"][:, c:c + 1].clamp(0, 255).to(torch.uint8))
+
+
+def test_weights_stamp_sees_every_kind_of_update():
+    """The plan cache key of a model (`_PlanModule._weights_stamp`, taken on every forward without walking the module tree): in-place
+    parameter / buffer updates, replaced Parameter objects and storage moves all change it; copies and pickles of a model carry the
+    parameters but never its device plans."""
+    import copy
+    import pickle
+    from pssr2_b200.models import RDResUNet, ResUNet
+    for M in (ResUNet, RDResUNet):
+        m = M().eval()
+        s0 = m._weights_stamp()
+        assert m._weights_stamp() == s0 and "_stamp_modules" in m.__dict__
+        with torch.no_grad():
+            next(iter(m.parameters())).mul_(1.0)                        # version bump, same values
+        s1 = m._weights_stamp()
+        assert s1 != s0
+        bufs = [b for b in m.buffers() if b.is_floating_point()]
+        bufs[-1].add_(1.0)
+        s2 = m._weights_stamp()
+        assert s2 != s1
+        m.reconstruction.conv.weight = torch.nn.Parameter(m.reconstruction.conv.weight.detach().clone())       # a new object
+        s3 = m._weights_stamp()
+        assert s3 != s2
+        m.invalidate()
+        assert "_stamp_modules" not in m.__dict__ and m._weights_stamp() == s3
+    m = ResUNet().eval()
+    m._weights_stamp()
+    m._plans[("fake",)] = {"plan": object()}
+    for c in (copy.deepcopy(m), pickle.loads(pickle.dumps(m))):
+        assert c._plans == {} and "_stamp_modules" not in c.__dict__
+        assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), c.state_dict().values()))
+    assert ("fake",) in m._plans
+    del m._plans[("fake",)]
