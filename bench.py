@@ -488,6 +488,8 @@ def config5(c, tiles_per_rank=8, precision="fp16c"):
             "precision": precision, "tiles": n, "n_gpus": c.world, "seconds": round(dt, 4),
             "hr_mp_per_s": round(n * 2048 * 2048 / dt / 1e6, 1), "ms_per_tile_e2e": round(dt / tiles_per_rank * 1e3, 2),
             "ms_per_tile_forward": round(fwd_ms / bsz, 3),
+            "h2d_bytes_per_tile": 5 * 2048 * 2048 * 2,
+            "h2d_gbs_all_gpus": round(n * 5 * 2048 * 2048 * 2 / dt / 1e9, 1),     # what bounds this config on several GPUs (shared host links)
             "forward_tflops_algorithmic": round(S8_FLOPS_PER_TILE * bsz / (fwd_ms * 1e-3) / 1e12, 1),
             "conv_tflops_algorithmic": round(S8_FLOPS_PER_TILE * bsz / (conv_ms * 1e-3) / 1e12, 1),
             "conv_frac_of_burst": round(S8_FLOPS_PER_TILE * bsz / (conv_ms * 1e-3) / 1e12 / peak_tf, 4),
