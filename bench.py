@@ -471,13 +471,18 @@ def config5(c, tiles_per_rank=8, precision="fp16c"):
         ds = ImageDataset(stacks, hr_res=2048, lr_scale=8, n_frames=[5, 1], val_split=1, crappifier=crap, device=c.dev)
         return test_metrics(model, ds, device=str(c.dev), norm=True, item0_quirk=False, batch_size=bsz)
 
+    # the run is short (16 tiles, ~18 ms) and bound by host->device copies, which other tenants of the box's host disturb: three
+    # timed runs, the median is reported (all of them are in `seconds_all`)
+    dts = []
     with _quiet(), torch.no_grad():
         run()
-        _barrier(c)
-        t0 = time.perf_counter()
-        m = run()
-        torch.cuda.synchronize()
-        dt = _max_over_ranks(c, time.perf_counter() - t0)
+        for _ in range(3):
+            _barrier(c)
+            t0 = time.perf_counter()
+            m = run()
+            torch.cuda.synchronize()
+            dts.append(_max_over_ranks(c, time.perf_counter() - t0))
+    dt = sorted(dts)[1]
     st = next(iter(model._plans.values()))
     acc = _plan_conv_ms(st["plan"], reps=2)
     conv_ms = sum(t for t, (kind, _) in zip(acc, st["plan"].records) if kind == "conv")
@@ -485,7 +490,7 @@ def config5(c, tiles_per_rank=8, precision="fp16c"):
     peak_tf, _, _ = _peaks()
     return {"workload": f"ResUNet(channels=[5,1], scale=8), {n} synthetic 5-frame 2048^2 uint16 stacks ({tiles_per_rank} per GPU): test_metrics(norm=True) = "
                         "crappify (Poisson+AdditiveGaussian) + forward + normalize_preds + PSNR/SSIM/MSE, batch 4, from pinned host stacks",
-            "precision": precision, "tiles": n, "n_gpus": c.world, "seconds": round(dt, 4),
+            "precision": precision, "tiles": n, "n_gpus": c.world, "seconds": round(dt, 4), "seconds_all": [round(t, 4) for t in dts],
             "hr_mp_per_s": round(n * 2048 * 2048 / dt / 1e6, 1), "ms_per_tile_e2e": round(dt / tiles_per_rank * 1e3, 2),
             "ms_per_tile_forward": round(fwd_ms / bsz, 3),
             "h2d_bytes_per_tile": 5 * 2048 * 2048 * 2,
