@@ -599,15 +599,21 @@ def run_ours(args):
     with contextlib.redirect_stderr(io.StringIO()), contextlib.redirect_stdout(io.StringIO()):
         preds = e2e_run()
         del preds
-        _barrier(c)
-        t0 = time.perf_counter()
-        preds = e2e_run()
-        torch.cuda.synchronize()
-        e2e_dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
-        assert len(preds) == e2e_steps * BATCH
-        del preds
-    if world > 1:
-        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+        # three timed calls (each: max over ranks), the MEDIAN is reported and all three are listed: the call is host-driven and
+        # the pool's boxes are shared VMs (single calls scatter by ~5 %)
+        e2e_all = []
+        for _ in range(3):
+            _barrier(c)
+            t0 = time.perf_counter()
+            preds = e2e_run()
+            torch.cuda.synchronize()
+            e2e_dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+            assert len(preds) == e2e_steps * BATCH
+            del preds
+            if world > 1:
+                dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+            e2e_all.append(float(e2e_dt))
+    e2e_dt = sorted(e2e_all)[1]
     e2e_value = world * BATCH * TILE * TILE / float(e2e_dt) / 1e6
     h2d = BATCH * TILE * TILE * 2
     d2h = BATCH * TILE * TILE
@@ -722,7 +728,10 @@ def run_ours(args):
                        "l2": f"inputs rotate over {NB} resident batches ({NB * h2d / 1e6:.0f} MB) and each step streams >4 GB of "
                              "activations, both > 126 MB L2"},
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "ImageDataset(pinned host stacks, one per step) + one predict_images(batch_size=64, out_dir=None) call over all steps"
+                    "ms_per_step_all_calls": [round(t * 1e3, 3) for t in e2e_all], "steps_per_call": e2e_steps,
+                    "api": "ImageDataset(pinned host stacks, one per step) + one predict_images(batch_size=64, out_dir=None) call over all steps; "
+                           "three calls back to back, median reported (the board heats towards its 1 kW cap during them: a call after a "
+                           "pause runs ~4 % faster than the third one)"
                            + (" per rank (rank_local datasets: no gather)" if world > 1 else "")},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "precision_modes": modes, "hbm_kernels": hbm_kernels,
             "cpu_baseline": cpu, "configs": subs}
